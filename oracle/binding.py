@@ -1,0 +1,178 @@
+"""ctypes loaders for the two CPU checkers (TEST INFRASTRUCTURE ONLY).
+
+  OracleIndex  -> oracle/libfm_oracle.so   plain-C restatement (oracle/fm_oracle.c)
+  RefIndex     -> oracle/_ref/libfm_ref.so the reference's own sources behind oracle/ref_driver.cc
+
+Both take the TM and the queries as int32 CSR (tokens, int64 offsets) and return, per query, a list
+of (s_id, score, penalty, max_subseq, length) in the order the reference returns its matches.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "libfm_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libfm_ref.so")
+
+
+def build(verbose=False):
+    """Compile the restatement and, when /root/reference is present, the reference itself."""
+    out = subprocess.run(["make", "-C", HERE, "all"], capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout, out.stderr)
+    if out.returncode != 0:
+        raise RuntimeError("oracle build failed")
+
+
+class Params(C.Structure):
+    _fields_ = [("fuzzy", C.c_float), ("number_of_matches", C.c_int32), ("no_perfect", C.c_int32),
+                ("min_subseq_length", C.c_int32), ("min_subseq_ratio", C.c_float),
+                ("vocab_idf_penalty", C.c_float), ("insert_cost", C.c_float), ("delete_cost", C.c_float),
+                ("replace_cost", C.c_float), ("contrastive_factor", C.c_float),
+                ("contrast_reduce", C.c_int32), ("contrast_buffer", C.c_int32)]
+
+
+class RefParams(C.Structure):
+    _fields_ = [("fuzzy", C.c_float), ("number_of_matches", C.c_int32),
+                ("min_subseq_length", C.c_int32), ("min_subseq_ratio", C.c_float),
+                ("vocab_idf_penalty", C.c_float), ("insert_cost", C.c_float), ("delete_cost", C.c_float),
+                ("replace_cost", C.c_float), ("contrastive_factor", C.c_float),
+                ("contrast_reduce", C.c_int32), ("contrast_buffer", C.c_int32)]
+
+
+MATCH_DTYPE = np.dtype([("s_id", np.uint32), ("score", np.float32), ("penalty", np.float32),
+                        ("max_subseq", np.int32), ("length", np.int32), ("cost", np.float32)])
+REF_MATCH_DTYPE = np.dtype([("s_id", np.uint32), ("score", np.float32), ("penalty", np.float32),
+                            ("max_subseq", np.int32), ("length", np.int32)])
+CAND_DTYPE = np.dtype([("s_id", np.uint32), ("longest_match", np.int32), ("s_length", np.int32),
+                       ("cover", np.int32), ("rejected", np.int32), ("cost_full", np.float32),
+                       ("rowmin_max", np.float32), ("accepted", np.int32)])
+COUNTER_NAMES = ["queries", "equal_range_calls", "probes", "elements_walked", "candidates",
+                 "candidate_tokens", "dp_pairs", "dp_tokens", "dp_cells", "pattern_tokens", "matches_out"]
+
+
+def make_params(cls, fuzzy=0.7, n=1, ml=2, mr=0.0, idf=0.0, costs=(1.0, 1.0, 1.0), contrast=0.0,
+                reduce=0, buffer=-1, no_perfect=False):
+    p = cls()
+    p.fuzzy, p.number_of_matches, p.min_subseq_length, p.min_subseq_ratio = fuzzy, n, ml, mr
+    p.vocab_idf_penalty = idf
+    p.insert_cost, p.delete_cost, p.replace_cost = costs
+    p.contrastive_factor, p.contrast_reduce, p.contrast_buffer = contrast, reduce, buffer
+    if cls is Params:
+        p.no_perfect = int(no_perfect)
+    elif no_perfect:
+        raise ValueError("match(Tokens) of the reference has no no_perfect argument")
+    return p
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _csr(tokens, off):
+    return (np.ascontiguousarray(tokens, dtype=np.int32), np.ascontiguousarray(off, dtype=np.int64))
+
+
+def _split(out, cnt, cap):
+    res = []
+    for q in range(len(cnt)):
+        k = min(int(cnt[q]), cap)
+        res.append(out[q * cap:q * cap + k].copy())
+    return res
+
+
+class OracleIndex:
+    def __init__(self, tokens, off, vocab_size, max_tokens=300, sfreq_global=None, n_sent_global=0):
+        self.lib = lib = C.CDLL(ORACLE_SO)
+        lib.fmo_index_create.restype = C.c_void_p
+        lib.fmo_index_num_sentences.restype = C.c_int64
+        lib.fmo_index_num_suffixes.restype = C.c_int64
+        lib.fmo_index_sfreq.restype = C.POINTER(C.c_uint32)
+        lib.fmo_index_kept.restype = C.POINTER(C.c_int64)
+        lib.fmo_match_debug.restype = C.c_int64
+        tokens, off = _csr(tokens, off)
+        sf = None if sfreq_global is None else np.ascontiguousarray(sfreq_global, dtype=np.uint32)
+        self.vocab_size = int(vocab_size)
+        h = lib.fmo_index_create(_ptr(tokens), _ptr(off), C.c_int64(len(off) - 1), C.c_int32(vocab_size),
+                                 C.c_int32(max_tokens), None if sf is None else _ptr(sf), C.c_int64(n_sent_global))
+        if not h:
+            raise ValueError("fmo_index_create failed (TM token outside [2, vocab_size))")
+        self.h = C.c_void_p(h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.fmo_index_destroy(self.h)
+            self.h = None
+
+    @property
+    def num_sentences(self):
+        return self.lib.fmo_index_num_sentences(self.h)
+
+    @property
+    def sfreq(self):
+        return np.ctypeslib.as_array(self.lib.fmo_index_sfreq(self.h), shape=(self.vocab_size,)).copy()
+
+    def match_batch(self, q_tokens, q_off, cap=16, nthreads=1, counters=False, **kw):
+        q_tokens, q_off = _csr(q_tokens, q_off)
+        n_q = len(q_off) - 1
+        p = make_params(Params, **kw)
+        out = np.zeros(n_q * cap, dtype=MATCH_DTYPE)
+        cnt = np.zeros(n_q, dtype=np.int32)
+        ct = (C.c_int64 * len(COUNTER_NAMES))()
+        self.lib.fmo_match_batch(self.h, _ptr(q_tokens), _ptr(q_off), C.c_int64(n_q), C.byref(p), C.c_int(nthreads),
+                                 C.c_int64(cap), _ptr(out), _ptr(cnt), ct if counters else None)
+        res = _split(out, cnt, cap)
+        if counters:
+            return res, cnt, dict(zip(COUNTER_NAMES, list(ct)))
+        return res, cnt
+
+    def match_debug(self, pattern, cap=64, dbg_cap=4096, **kw):
+        pattern = np.ascontiguousarray(pattern, dtype=np.int32)
+        p = make_params(Params, **kw)
+        out = np.zeros(cap, dtype=MATCH_DTYPE)
+        dbg = np.zeros(dbg_cap, dtype=CAND_DTYPE)
+        dbg_n = C.c_int64(0)
+        n = self.lib.fmo_match_debug(self.h, _ptr(pattern), C.c_int64(len(pattern)), C.byref(p), C.c_int64(cap),
+                                     _ptr(out), _ptr(dbg), C.c_int64(dbg_cap), C.byref(dbg_n))
+        return out[:min(n, cap)].copy(), dbg[:dbg_n.value].copy()
+
+    def equal_range(self, ngram):
+        ngram = np.ascontiguousarray(ngram, dtype=np.int32)
+        lo, hi = C.c_int64(0), C.c_int64(0)
+        self.lib.fmo_equal_range(self.h, _ptr(ngram), C.c_int64(len(ngram)), C.byref(lo), C.byref(hi))
+        return lo.value, hi.value
+
+
+def ref_available():
+    return os.path.exists(REF_SO)
+
+
+class RefIndex:
+    """The unmodified reference (fuzzy::FuzzyMatch) behind oracle/ref_driver.cc."""
+
+    def __init__(self, tokens, off, max_tokens=300):
+        self.lib = lib = C.CDLL(REF_SO)
+        lib.fmref_create.restype = C.c_void_p
+        lib.fmref_match_batch.restype = C.c_double
+        tokens, off = _csr(tokens, off)
+        self.h = C.c_void_p(lib.fmref_create(C.c_int(max_tokens)))
+        lib.fmref_add_tm(self.h, _ptr(tokens), _ptr(off), C.c_int64(len(off) - 1))
+        lib.fmref_sort(self.h)
+        self.last_seconds = 0.0
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.fmref_destroy(self.h)
+            self.h = None
+
+    def match_batch(self, q_tokens, q_off, cap=16, nthreads=1, **kw):
+        q_tokens, q_off = _csr(q_tokens, q_off)
+        n_q = len(q_off) - 1
+        p = make_params(RefParams, **kw)
+        out = np.zeros(n_q * cap, dtype=REF_MATCH_DTYPE)
+        cnt = np.zeros(n_q, dtype=np.int32)
+        self.last_seconds = self.lib.fmref_match_batch(self.h, _ptr(q_tokens), _ptr(q_off), C.c_int64(n_q), C.byref(p),
+                                                       C.c_int(nthreads), C.c_int64(cap), _ptr(out), _ptr(cnt))
+        return _split(out, cnt, cap), cnt

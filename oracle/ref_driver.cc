@@ -1,0 +1,118 @@
+// oracle/ref_driver.cc -- TEST INFRASTRUCTURE, not product code.
+//
+// C-ABI driver around the UNMODIFIED reference implementation (fuzzy::FuzzyMatch, compiled from
+// /root/reference/src/*.cc by oracle/Makefile into oracle/_ref/libfm_ref.so). It feeds the
+// reference through its own public API only:
+//   FuzzyMatch::add_tm(id, Tokens, sort=false)   include/fuzzy/fuzzy_match.hh:52
+//   FuzzyMatch::sort()                           include/fuzzy/fuzzy_match.hh:57
+//   FuzzyMatch::match(Tokens, ...)               include/fuzzy/fuzzy_match.hh:59-69
+// Token ids are turned into decimal strings so that the reference's own VocabIndexer assigns
+// its ids; results (s_id, score, max_subseq, penalty, length) do not depend on that assignment.
+// Used (a) to pin the C restatement in oracle/fm_oracle.c and (b) as the "reference" CPU baseline
+// of bench.py (worker threads pulling queries from an atomic counter on one shared index, the
+// equivalent of FuzzyMatch-cli -N <threads>, cli/src/FuzzyMatch-cli.cc:112-193).
+#include <fuzzy/fuzzy_match.hh>
+
+#include <atomic>
+#include <chrono>
+#include <cstdint>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+struct RefHandle {
+  fuzzy::FuzzyMatch fm;
+  explicit RefHandle(int max_tok) : fm(fuzzy::FuzzyMatch::pt_none, (size_t)max_tok) {}
+};
+fuzzy::Tokens to_tokens(const int32_t* t, int64_t n) {
+  fuzzy::Tokens out;
+  out.reserve((size_t)n);
+  for (int64_t i = 0; i < n; i++) out.push_back(std::to_string(t[i]));
+  return out;
+}
+}  // namespace
+
+extern "C" {
+
+struct fmref_params {
+  float fuzzy;
+  int32_t number_of_matches;
+  int32_t min_subseq_length;
+  float min_subseq_ratio;
+  float vocab_idf_penalty;
+  float insert_cost, delete_cost, replace_cost;
+  float contrastive_factor;
+  int32_t contrast_reduce;  // 0 = MEAN, 1 = MAX
+  int32_t contrast_buffer;
+};
+
+struct fmref_match {
+  uint32_t s_id;
+  float score;
+  float penalty;
+  int32_t max_subseq;
+  int32_t length;
+};
+
+void* fmref_create(int max_tokens_in_pattern) { return new RefHandle(max_tokens_in_pattern); }
+void fmref_destroy(void* h) { delete static_cast<RefHandle*>(h); }
+
+void fmref_add_tm(void* h, const int32_t* tokens, const int64_t* off, int64_t n_sent) {
+  auto* r = static_cast<RefHandle*>(h);
+  for (int64_t s = 0; s < n_sent; s++)
+    r->fm.add_tm(std::to_string(s), to_tokens(tokens + off[s], off[s + 1] - off[s]), /*sort=*/false);
+}
+
+void fmref_sort(void* h) { static_cast<RefHandle*>(h)->fm.sort(); }
+
+// Runs match(Tokens) for every query. out is [n_q * cap]; out_count[q] = number of matches the
+// reference returned (may exceed cap; only the first cap are stored). Returns wall seconds spent
+// inside the matching loop (string conversion of the queries happens before the clock starts).
+double fmref_match_batch(void* h, const int32_t* q_tokens, const int64_t* q_off, int64_t n_q,
+                         const fmref_params* p, int nthreads, int64_t cap, fmref_match* out,
+                         int32_t* out_count) {
+  auto* r = static_cast<RefHandle*>(h);
+  std::vector<fuzzy::Tokens> queries((size_t)n_q);
+  for (int64_t q = 0; q < n_q; q++) queries[q] = to_tokens(q_tokens + q_off[q], q_off[q + 1] - q_off[q]);
+  const fuzzy::EditCosts costs(p->insert_cost, p->delete_cost, p->replace_cost);
+  const auto reduce = p->contrast_reduce ? fuzzy::ContrastReduce::MAX : fuzzy::ContrastReduce::MEAN;
+  std::atomic<int64_t> next(0);
+  auto work = [&]() {
+    std::vector<fuzzy::FuzzyMatch::Match> matches;
+    for (;;) {
+      const int64_t q = next.fetch_add(1);
+      if (q >= n_q) break;
+      matches.clear();
+      r->fm.match(queries[q], p->fuzzy, (unsigned)p->number_of_matches, matches, p->min_subseq_length,
+                  p->min_subseq_ratio, p->vocab_idf_penalty, costs, p->contrastive_factor, reduce,
+                  p->contrast_buffer);
+      if (out_count) out_count[q] = (int32_t)matches.size();
+      if (out)
+        for (size_t k = 0; k < matches.size() && (int64_t)k < cap; k++) {
+          fmref_match& o = out[q * cap + (int64_t)k];
+          o.s_id = matches[k].s_id;
+          o.score = matches[k].score;
+          // Match::penalty is never initialised by the reference unless contrastive rerank runs
+          // (fuzzy_match.hh:34-38); report 0 there.
+          o.penalty = p->contrastive_factor > 0 ? matches[k].penalty : 0.f;
+          o.max_subseq = matches[k].max_subseq;
+          o.length = matches[k].length;
+        }
+    }
+  };
+  const auto t0 = std::chrono::steady_clock::now();
+  if (nthreads <= 1) {
+    work();
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; t++) pool.emplace_back(work);
+    for (auto& t : pool) t.join();
+  }
+  const auto t1 = std::chrono::steady_clock::now();
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
+int64_t fmref_max_tokens_in_pattern(void* h) { return (int64_t) static_cast<RefHandle*>(h)->fm.max_tokens_in_pattern(); }
+
+}  // extern "C"

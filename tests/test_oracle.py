@@ -1,0 +1,83 @@
+"""CPU tests: the C restatement (oracle/fm_oracle.c) against (a) the committed golden vectors that
+were produced by the unmodified reference and (b) the reference itself when oracle/_ref exists."""
+import numpy as np
+import pytest
+
+from fuzzy_match_b200 import synth
+from oracle import binding as ob
+from tests.util import as_tuples, csr, fix_params, load_golden
+
+CASES = load_golden()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_oracle_matches_golden(case):
+    tok, off = csr(case["tm"])
+    q, qo = csr(case["queries"])
+    O = ob.OracleIndex(tok, off, case["vocab_size"], max_tokens=case["max_tokens"])
+    res, cnt = O.match_batch(q, qo, cap=64, **fix_params(case["params"]))
+    got = [as_tuples(r) for r in res]
+    want = [[tuple(m) for m in r] for r in case["expected"]]
+    assert got == want
+
+
+def test_reference_known_answers_are_in_golden():
+    """The gtest expectations themselves (test/test.cc), independent of how the golden file was made."""
+    by = {c["name"]: c for c in CASES}
+    f = lambda b: float(np.uint32(b).view(np.float32))
+    lcs = by["lcs_cost"]["expected"][0]
+    assert [m[0] for m in lcs] == [2, 1, 0]
+    assert abs(f(lcs[0][1]) - 1.0) < 1e-3 and abs(f(lcs[1][1]) - 5 / 6) < 1e-3 and abs(f(lcs[2][1]) - 0.5) < 1e-3
+    assert [len(r) for r in by["pre_reject"]["expected"]] == [2, 2]
+    for name in ("idf_weight_1", "idf_weight_2_lcs", "idf_weight_2_unit"):
+        r = by[name]["expected"][0]
+        assert [m[0] for m in r] == [0, 1]
+        assert abs(f(r[0][1]) - 0.6706515) < 1e-4 and abs(f(r[1][1]) - 0.6076691) < 1e-4
+    r = by["contrastive_reduce_mean"]["expected"][0]
+    assert [m[0] for m in r] == [0, 2, 1]
+    assert [round(f(m[1]) - f(m[2]), 3) for m in r] == [0.667, 0.5, 0.125]
+    r = by["contrastive_reduce_max"]["expected"][0]
+    assert [round(f(m[1]) - f(m[2]), 3) for m in r] == [0.667, 0.5, -0.25]
+    assert [m[0] for m in by["contrastive_buffer"]["expected"][0]] == [0, 3, 4]
+    assert [[m[0] for m in q] for q in by["small_sentence_matches"]["expected"]] == [[0], [1], [2]]
+    assert [len(q) for q in by["max_tokens_in_pattern"]["expected"]] == [0, 1]
+    assert [m[0] for m in by["Q1_order_dependence_N1"]["expected"][0]] == [1]
+    assert [m[0] for m in by["Q1_order_dependence_N2"]["expected"][0]] == [0, 1]
+
+
+PARAM_SETS = [
+    dict(fuzzy=0.8, n=1, ml=3, mr=0.3),
+    dict(fuzzy=0.5, n=5, ml=2),
+    dict(fuzzy=0.3, n=0, ml=2),
+    dict(fuzzy=0.5, n=10, ml=3, idf=1.0, contrast=0.5),
+    dict(fuzzy=0.4, n=4, ml=2, idf=0.7, costs=(1, 0, 1), contrast=0.5, reduce=1, buffer=8),
+    dict(fuzzy=0.4, n=4, ml=2, costs=(0.5, 1.5, 1.2)),
+]
+
+
+@pytest.mark.skipif(not ob.ref_available(), reason="oracle/_ref not built (no /root/reference here)")
+@pytest.mark.parametrize("params", PARAM_SETS, ids=[str(i) for i in range(len(PARAM_SETS))])
+def test_oracle_matches_live_reference(params):
+    tm, off, V = synth.make_tm(5000, vocab=800, seed=31)
+    q, qo = synth.make_queries(tm, off, 300, vocab=800, seed=32)
+    O = ob.OracleIndex(tm, off, V)
+    R = ob.RefIndex(tm, off)
+    ro, co = O.match_batch(q, qo, cap=32, **params)
+    rr, cr = R.match_batch(q, qo, cap=32, **params)
+    assert (co == cr).all()
+    for a, b in zip(ro, rr):
+        assert as_tuples(a) == as_tuples(b)
+
+
+def test_oracle_threads_agree():
+    tm, off, V = synth.make_tm(3000, vocab=500, seed=41)
+    q, qo = synth.make_queries(tm, off, 200, vocab=500, seed=42)
+    O = ob.OracleIndex(tm, off, V)
+    r1, c1 = O.match_batch(q, qo, cap=8, nthreads=1, fuzzy=0.5, n=3)
+    r4, c4 = O.match_batch(q, qo, cap=8, nthreads=4, fuzzy=0.5, n=3)
+    assert (c1 == c4).all() and all(as_tuples(a, True) == as_tuples(b, True) for a, b in zip(r1, r4))
+
+
+def test_oracle_rejects_bad_tm_tokens():
+    with pytest.raises(ValueError):
+        ob.OracleIndex(np.array([2, 1, 3], dtype=np.int32), np.array([0, 3], dtype=np.int64), 10)
