@@ -1,0 +1,209 @@
+"""ctypes binding of the C ABI declared in include/fuzzy_match_b200.h.
+
+This is the binding a maintainer of the reference would write for the hot path;
+nothing here computes anything -- all work happens in libfm_b200.so (hand-written sm_100a CUDA).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class FuzzyMatchError(RuntimeError):
+    pass
+
+
+def library_path():
+    return os.path.join(_HERE, "libfm_b200.so")
+
+
+def build_library(verbose=False):
+    """Compile csrc/*.cu for sm_100a into libfm_b200.so (nvcc cross-compiles without a GPU)."""
+    out = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc")], capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout, out.stderr)
+    if out.returncode != 0:
+        raise FuzzyMatchError("building libfm_b200.so failed")
+    return library_path()
+
+
+class Params(C.Structure):
+    """fm_params: the arguments of FuzzyMatch::match after the pattern (fuzzy_match.hh:59-82)."""
+    _fields_ = [("fuzzy", C.c_float), ("number_of_matches", C.c_int32), ("no_perfect", C.c_int32),
+                ("min_subseq_length", C.c_int32), ("min_subseq_ratio", C.c_float),
+                ("vocab_idf_penalty", C.c_float), ("insert_cost", C.c_float), ("delete_cost", C.c_float),
+                ("replace_cost", C.c_float), ("contrastive_factor", C.c_float),
+                ("contrast_reduce", C.c_int32), ("contrast_buffer", C.c_int32)]
+
+    @classmethod
+    def make(cls, fuzzy=0.7, n=1, ml=2, mr=0.0, idf=0.0, costs=(1.0, 1.0, 1.0), contrast=0.0, reduce=0, buffer=-1,
+             no_perfect=False):
+        p = cls()
+        p.fuzzy, p.number_of_matches, p.no_perfect = fuzzy, n, int(no_perfect)
+        p.min_subseq_length, p.min_subseq_ratio, p.vocab_idf_penalty = ml, mr, idf
+        p.insert_cost, p.delete_cost, p.replace_cost = costs
+        p.contrastive_factor, p.contrast_reduce, p.contrast_buffer = contrast, int(reduce), buffer
+        return p
+
+
+class Profile(C.Structure):
+    _fields_ = [("ms_prepare", C.c_float), ("ms_search", C.c_float), ("ms_gather", C.c_float), ("ms_scan", C.c_float),
+                ("ms_score", C.c_float), ("ms_replay", C.c_float), ("ms_total", C.c_float),
+                ("n_queries", C.c_int64), ("n_query_tokens", C.c_int64), ("n_slices", C.c_int64),
+                ("n_elements", C.c_int64), ("n_survivors", C.c_int64), ("n_matches", C.c_int64),
+                ("launches", C.c_int32), ("retries", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+MATCH_DTYPE = np.dtype([("s_id", np.uint32), ("score", np.float32), ("penalty", np.float32),
+                        ("max_subseq", np.int32), ("length", np.int32), ("cost", np.float32)])
+RECORD_DTYPE = np.dtype([("s_id", np.uint32), ("longest_match", np.int32), ("length", np.int32),
+                         ("cost", np.float32), ("rowmin_max", np.float32), ("reserved", np.int32, (3,))])
+
+EXPORTS = ["fm_index_create", "fm_index_destroy", "fm_index_num_sentences", "fm_index_num_suffixes",
+           "fm_index_max_tokens_in_pattern", "fm_index_device_bytes", "fm_index_kept_sources", "fm_index_sfreq",
+           "fm_index_sentence", "fm_match_batch", "fm_match_batch_device", "fm_shard_score_device",
+           "fm_merge_replay_device", "fm_set_profiling", "fm_get_profile", "fm_last_error", "fm_version"]
+
+
+def load_library():
+    """Loads libfm_b200.so; raises (never falls back) when it is missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise FuzzyMatchError("%s not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)" % path)
+    lib = C.CDLL(path)
+    lib.fm_last_error.restype = C.c_char_p
+    lib.fm_version.restype = C.c_char_p
+    for name in ("fm_index_num_sentences", "fm_index_num_suffixes", "fm_index_device_bytes"):
+        getattr(lib, name).restype = C.c_int64
+        getattr(lib, name).argtypes = [C.c_void_p]
+    lib.fm_index_max_tokens_in_pattern.restype = C.c_int32
+    lib.fm_index_max_tokens_in_pattern.argtypes = [C.c_void_p]
+    lib.fm_index_destroy.restype = None
+    lib.fm_index_destroy.argtypes = [C.c_void_p]
+    lib.fm_index_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
+                                    C.c_int64, C.c_int, C.POINTER(C.c_void_p)]
+    lib.fm_index_kept_sources.argtypes = [C.c_void_p, C.c_void_p]
+    lib.fm_index_sfreq.argtypes = [C.c_void_p, C.c_void_p]
+    lib.fm_index_sentence.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32)]
+    lib.fm_match_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Params), C.c_int64,
+                                   C.c_void_p, C.c_void_p]
+    lib.fm_match_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(Params),
+                                          C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.fm_shard_score_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(Params),
+                                          C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_void_p]
+    lib.fm_merge_replay_device.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p,
+                                           C.c_int64, C.POINTER(Params), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.fm_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    lib.fm_get_profile.argtypes = [C.c_void_p, C.POINTER(Profile)]
+    _LIB = lib
+    return lib
+
+
+def _check(lib, rc):
+    if rc != 0:
+        raise FuzzyMatchError("fuzzy_match_b200 error %d: %s" % (rc, lib.fm_last_error().decode()))
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class Index:
+    """One device-resident index (fm_index) and the calls that run batches against it."""
+
+    def __init__(self, tokens, sent_off, vocab_size, max_tokens=300, sfreq_global=None, n_sent_global=0, s_id_base=0,
+                 device=0):
+        self.lib = load_library()
+        tokens = np.ascontiguousarray(tokens, dtype=np.int32)
+        sent_off = np.ascontiguousarray(sent_off, dtype=np.int64)
+        sf = None if sfreq_global is None else np.ascontiguousarray(sfreq_global, dtype=np.uint32)
+        h = C.c_void_p()
+        _check(self.lib, self.lib.fm_index_create(_ptr(tokens), _ptr(sent_off), len(sent_off) - 1, int(vocab_size),
+                                                  int(max_tokens), _ptr(sf), int(n_sent_global), int(s_id_base),
+                                                  int(device), C.byref(h)))
+        self.h = h
+        self.vocab_size = int(vocab_size)
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.fm_index_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    num_sentences = property(lambda self: self.lib.fm_index_num_sentences(self.h))
+    num_suffixes = property(lambda self: self.lib.fm_index_num_suffixes(self.h))
+    max_tokens_in_pattern = property(lambda self: self.lib.fm_index_max_tokens_in_pattern(self.h))
+    device_bytes = property(lambda self: self.lib.fm_index_device_bytes(self.h))
+
+    def kept_sources(self):
+        out = np.zeros(self.num_sentences, dtype=np.int64)
+        _check(self.lib, self.lib.fm_index_kept_sources(self.h, _ptr(out)))
+        return out
+
+    def sfreq(self):
+        out = np.zeros(self.vocab_size, dtype=np.uint32)
+        _check(self.lib, self.lib.fm_index_sfreq(self.h, _ptr(out)))
+        return out
+
+    def sentence(self, s_id):
+        p, n = C.POINTER(C.c_int32)(), C.c_int32()
+        _check(self.lib, self.lib.fm_index_sentence(self.h, int(s_id), C.byref(p), C.byref(n)))
+        return np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+
+    def match_batch(self, q_tokens, q_off, cap=None, params=None, **kw):
+        """Host buffers in, host buffers out (fm_match_batch). Returns (matches[n_q, cap], counts[n_q])."""
+        p = params if params is not None else Params.make(**kw)
+        if cap is None:
+            cap = max(1, p.number_of_matches)
+        q_tokens = np.ascontiguousarray(q_tokens, dtype=np.int32)
+        q_off = np.ascontiguousarray(q_off, dtype=np.int64)
+        n_q = len(q_off) - 1
+        out = np.zeros((n_q, cap), dtype=MATCH_DTYPE)
+        cnt = np.zeros(n_q, dtype=np.int32)
+        _check(self.lib, self.lib.fm_match_batch(self.h, _ptr(q_tokens), _ptr(q_off), n_q, C.byref(p), cap, _ptr(out),
+                                                 _ptr(cnt)))
+        return out, cnt
+
+    def match_batch_device(self, d_q_tokens, d_q_off, n_q, n_tok, d_out, d_out_count, cap, stream=0, params=None, **kw):
+        """Raw device pointers (ints) in and out (fm_match_batch_device)."""
+        p = params if params is not None else Params.make(**kw)
+        _check(self.lib, self.lib.fm_match_batch_device(self.h, d_q_tokens, d_q_off, n_q, n_tok, C.byref(p), cap, d_out,
+                                                        d_out_count, stream))
+
+    def shard_score_device(self, d_q_tokens, d_q_off, n_q, n_tok, stream=0, params=None, **kw):
+        """Returns (d_rec_off ptr, d_rec ptr, n_rec) for the cross-shard replay."""
+        p = params if params is not None else Params.make(**kw)
+        off, rec, n = C.c_void_p(), C.c_void_p(), C.c_int64()
+        _check(self.lib, self.lib.fm_shard_score_device(self.h, d_q_tokens, d_q_off, n_q, n_tok, C.byref(p), C.byref(off),
+                                                        C.byref(rec), C.byref(n), stream))
+        return off.value, rec.value, n.value
+
+    def merge_replay_device(self, d_rec_offs, d_recs, d_q_off, n_q, d_out, d_out_count, cap, stream=0, params=None, **kw):
+        p = params if params is not None else Params.make(**kw)
+        k = len(d_rec_offs)
+        offs = (C.c_void_p * k)(*d_rec_offs)
+        recs = (C.c_void_p * k)(*d_recs)
+        _check(self.lib, self.lib.fm_merge_replay_device(self.h, k, offs, recs, d_q_off, n_q, C.byref(p), cap, d_out,
+                                                         d_out_count, stream))
+
+    def set_profiling(self, enabled=True):
+        _check(self.lib, self.lib.fm_set_profiling(self.h, int(enabled)))
+
+    def profile(self):
+        p = Profile()
+        _check(self.lib, self.lib.fm_get_profile(self.h, C.byref(p)))
+        return p.as_dict()

@@ -1,0 +1,439 @@
+// fm_api.cu -- the C ABI (include/fuzzy_match_b200.h): workspace management and batch orchestration.
+#include <algorithm>
+#include <cstring>
+
+#include "fm_internal.h"
+
+namespace fm {
+const std::string& get_error();
+
+template <class T>
+static int dev_realloc(T** p, size_t n) {
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  void* d = nullptr;
+  FM_CUDA(cudaMalloc(&d, (n ? n : 1) * sizeof(T)));
+  *p = static_cast<T*>(d);
+  return FM_OK;
+}
+
+static int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+static Workspace* acquire(Index* ix) {
+  std::lock_guard<std::mutex> g(ix->mu);
+  for (Workspace* w : ix->pool)
+    if (!w->in_use) { w->in_use = true; return w; }
+  Workspace* w = new Workspace();
+  w->device = ix->device;
+  w->in_use = true;
+  ix->pool.push_back(w);
+  return w;
+}
+static void release(Index* ix, Workspace* w) {
+  std::lock_guard<std::mutex> g(ix->mu);
+  w->in_use = false;
+}
+
+static int ensure_base(Workspace* w) {
+  if (!w->stream) {
+    FM_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+    for (auto& e : w->ev) FM_CUDA(cudaEventCreate(&e));
+    FM_CUDA(cudaMalloc((void**)&w->ctr, sizeof(Counters)));
+    FM_CUDA(cudaMallocHost((void**)&w->h_ctr, sizeof(Counters)));
+  }
+  return FM_OK;
+}
+
+static int ensure_queries(Workspace* w, int64_t n_q, int64_t n_tok, bool staging) {
+  int rc;
+  if (n_q > w->cap_q) {
+    const int64_t c = round_up(n_q + n_q / 4 + 1024, 1024);
+    if ((rc = dev_realloc(&w->qmeta, c)) || (rc = dev_realloc(&w->q_cnt, c + 1)) || (rc = dev_realloc(&w->q_base, c + 1)) ||
+        (rc = dev_realloc(&w->acc_cnt, c)) || (rc = dev_realloc(&w->d_q_off, c + 1)) || (rc = dev_realloc(&w->d_out_count, c + 1)))
+      return rc;
+    w->cap_q = c;
+    w->cap_surv = 0;  // heapbuf depends on cap_q
+  }
+  if (n_tok > w->cap_tok) {
+    const int64_t c = round_up(n_tok + n_tok / 4 + 4096, 4096);
+    if ((rc = dev_realloc(&w->pat, c)) || (rc = dev_realloc(&w->chain_q, c)) || (rc = dev_realloc(&w->tbl, 4 * c)) ||
+        (rc = dev_realloc(&w->d_q_tok, c)))
+      return rc;
+    w->cap_tok = c;
+  }
+  if (staging && n_q + 1 > w->cap_hq) {
+    if (w->h_q_off32) cudaFreeHost(w->h_q_off32);
+    w->h_q_off32 = nullptr;
+    const int64_t c = round_up(n_q + n_q / 4 + 1025, 1024);
+    FM_CUDA(cudaMallocHost((void**)&w->h_q_off32, c * sizeof(int32_t)));
+    w->cap_hq = c;
+  }
+  return FM_OK;
+}
+static int ensure_slices(Workspace* w, int64_t n) {
+  if (n <= w->cap_slices) return FM_OK;
+  int rc;
+  if ((rc = dev_realloc(&w->sl_start, n + 1)) || (rc = dev_realloc(&w->sl_rec, n))) return rc;
+  w->cap_slices = n;
+  return FM_OK;
+}
+static int ensure_survivors(Workspace* w, int64_t n) {
+  if (n <= w->cap_surv) return FM_OK;
+  int rc;
+  uint32_t hs = 1u << 20;
+  while ((int64_t)hs < 4 * n) hs <<= 1;
+  if ((rc = dev_realloc(&w->surv, n)) || (rc = dev_realloc(&w->surv_len, n)) || (rc = dev_realloc(&w->rec, n)) ||
+      (rc = dev_realloc(&w->heapbuf, n + w->cap_q + 1)) || (rc = dev_realloc(&w->hkey, (size_t)hs)) ||
+      (rc = dev_realloc(&w->hlm, (size_t)hs)))
+    return rc;
+  w->hsize = hs;
+  w->cap_surv = n;
+  return FM_OK;
+}
+static int ensure_out(Workspace* w, int64_t n_q, int64_t cap) {
+  if (n_q * cap <= w->cap_out) return FM_OK;
+  int rc;
+  const int64_t c = n_q * cap + 1024;
+  if ((rc = dev_realloc(&w->d_out, c))) return rc;
+  w->cap_out = c;
+  return FM_OK;
+}
+
+static void free_workspace(Workspace* w) {
+  cudaFree(w->d_q_tok); cudaFree(w->d_q_off); cudaFree(w->pat); cudaFree(w->chain_q); cudaFree(w->qmeta); cudaFree(w->tbl);
+  cudaFree(w->sl_start); cudaFree(w->sl_rec); cudaFree(w->hkey); cudaFree(w->hlm); cudaFree(w->surv); cudaFree(w->surv_len);
+  cudaFree(w->q_cnt); cudaFree(w->q_base); cudaFree(w->acc_cnt); cudaFree(w->rec); cudaFree(w->heapbuf); cudaFree(w->ctr);
+  cudaFree(w->d_out); cudaFree(w->d_out_count); cudaFree(w->mrec); cudaFree(w->m_cnt); cudaFree(w->m_base); cudaFree(w->m_acc); cudaFree(w->m_heap);
+  if (w->h_ctr) cudaFreeHost(w->h_ctr);
+  if (w->h_q_off32) cudaFreeHost(w->h_q_off32);
+  if (w->stream) {
+    cudaStreamDestroy(w->stream);
+    for (auto& e : w->ev) cudaEventDestroy(e);
+  }
+  delete w;
+}
+
+static int check_params(const fm_params* p, Params* out) {
+  if (!p) { set_error("params is NULL"); return FM_ERR_INVALID; }
+  out->fuzzy = p->fuzzy;
+  out->n_matches = p->number_of_matches;
+  out->no_perfect = p->no_perfect;
+  out->ml = p->min_subseq_length;
+  out->mr = p->min_subseq_ratio;
+  out->idf_penalty = p->vocab_idf_penalty;
+  out->ins = p->insert_cost; out->del = p->delete_cost; out->rep = p->replace_cost;
+  out->contrast = p->contrastive_factor;
+  out->reduce = p->contrast_reduce;
+  out->buffer = p->contrast_buffer == -1 ? p->number_of_matches : p->contrast_buffer;  // src/fuzzy_match.cc:451-452
+  if (p->number_of_matches < 0) { set_error("number_of_matches < 0"); return FM_ERR_INVALID; }
+  return FM_OK;
+}
+
+static BatchDev make_batch(Workspace* w, const int32_t* d_q_tok, const int32_t* d_q_off, int64_t n_q, int64_t n_tok) {
+  BatchDev b{};
+  b.q_tok_in = d_q_tok; b.q_off = d_q_off; b.n_q = (int32_t)n_q; b.n_tok = (int32_t)n_tok;
+  b.pat = w->pat; b.chain_q = w->chain_q; b.qmeta = w->qmeta; b.tbl = w->tbl;
+  b.sl_start = w->sl_start; b.sl_rec = w->sl_rec; b.slice_cap = w->cap_slices;
+  b.hkey = w->hkey; b.hlm = w->hlm; b.hmask = w->hsize - 1;
+  b.surv = w->surv; b.surv_len = w->surv_len; b.surv_cap = w->cap_surv;
+  b.q_cnt = w->q_cnt; b.q_base = w->q_base; b.rec = w->rec; b.heapbuf = w->heapbuf; b.acc_cnt = w->acc_cnt;
+  b.ctr = w->ctr;
+  return b;
+}
+
+// Shard half of the pipeline: prepare -> search -> gather -> scan -> score, all asynchronous on st.
+// Afterwards w->q_base / w->rec hold the scored candidates grouped by query (unless a worklist
+// overflowed, which later kernels detect through the counters and skip).
+static int launch_shard(Index* ix, Workspace* w, const int32_t* d_q_tok, const int32_t* d_q_off, int64_t n_q, int64_t n_tok,
+                        const Params& pr, cudaStream_t st, int* launches) {
+  BatchDev b = make_batch(w, d_q_tok, d_q_off, n_q, n_tok);
+  FM_CUDA(cudaMemsetAsync(w->ctr, 0, sizeof(Counters), st));
+  FM_CUDA(cudaMemsetAsync(w->hkey, 0xff, (size_t)w->hsize * sizeof(unsigned long long), st));
+  FM_CUDA(cudaMemsetAsync(w->hlm, 0, (size_t)w->hsize * sizeof(unsigned int), st));
+  if (ix->profiling) cudaEventRecord(w->ev[0], st);
+  launch_prepare(ix->dev, b, pr, st);
+  if (ix->profiling) cudaEventRecord(w->ev[1], st);
+  launch_search(ix->dev, b, pr, st);
+  if (ix->profiling) cudaEventRecord(w->ev[2], st);
+  launch_gather(ix->dev, b, pr, ix->sm_count, st);
+  if (ix->profiling) cudaEventRecord(w->ev[3], st);
+  launch_scan(w->q_cnt, w->q_base, (int32_t)n_q, st);
+  if (ix->profiling) cudaEventRecord(w->ev[4], st);
+  launch_score(ix->dev, b, pr, ix->sm_count, st);
+  if (ix->profiling) cudaEventRecord(w->ev[5], st);
+  *launches += 5;
+  return FM_OK;
+}
+
+static int initial_worklists(Workspace* w, int64_t n_q, int64_t n_tok) {
+  int rc;
+  if ((rc = ensure_slices(w, std::max<int64_t>(1 << 16, 8 * n_tok + 65536)))) return rc;
+  return ensure_survivors(w, std::max<int64_t>(1 << 18, 8 * n_q));
+}
+
+// Reads the counters back (one stream sync). Returns 1 if a worklist overflowed and was regrown
+// (the caller reruns the batch), 0 if the batch is complete, <0 on error (-rc).
+static int sync_and_check(Workspace* w, cudaStream_t st, int attempt, int* retries) {
+  cudaError_t e = cudaMemcpyAsync(w->h_ctr, w->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return -cuda_fail(e, "batch execution");
+  if (!w->h_ctr->overflow) return 0;
+  if (attempt >= 8) { set_error("workspace overflow persists"); return -FM_ERR_NOMEM; }
+  (*retries)++;
+  int rc;
+  const int64_t need_slices = (int64_t)(w->h_ctr->slice_elem >> kElemBits);
+  if (need_slices > w->cap_slices && (rc = ensure_slices(w, need_slices + need_slices / 8 + 1024))) return -rc;
+  if ((w->h_ctr->overflow & 2u) && (rc = ensure_survivors(w, w->cap_surv * 4))) return -rc;
+  return 1;
+}
+
+static int run_replay(Index* ix, Workspace* w, fm_record* rec, const int32_t* q_cnt, const int32_t* q_base, float* heapbuf,
+                      int32_t* acc_cnt, const int32_t* d_q_off, int64_t n_q, const Params& pr, int64_t cap, fm_match* d_out, int32_t* d_out_count,
+                      cudaStream_t st, int* launches) {
+  launch_replay(ix->dev, rec, q_cnt, q_base, heapbuf, acc_cnt, d_q_off, (int32_t)n_q, pr, cap, d_out, d_out_count, w->ctr, st);
+  (*launches)++;
+  if (pr.contrast > 0.f) {
+    launch_contrast(ix->dev, rec, q_base, acc_cnt, (int32_t)n_q, pr, cap, d_out, d_out_count, w->ctr, ix->sm_count, st);
+    (*launches)++;
+  }
+  if (ix->profiling) cudaEventRecord(w->ev[6], st);
+  return FM_OK;
+}
+
+static void finish_profile(Index* ix, Workspace* w, int64_t n_q, int64_t n_tok, int launches, int retries) {
+  if (!ix->profiling) return;
+  fm_profile p{};
+  float ms = 0;
+  cudaEventElapsedTime(&ms, w->ev[0], w->ev[1]); p.ms_prepare = ms;
+  cudaEventElapsedTime(&ms, w->ev[1], w->ev[2]); p.ms_search = ms;
+  cudaEventElapsedTime(&ms, w->ev[2], w->ev[3]); p.ms_gather = ms;
+  cudaEventElapsedTime(&ms, w->ev[3], w->ev[4]); p.ms_scan = ms;
+  cudaEventElapsedTime(&ms, w->ev[4], w->ev[5]); p.ms_score = ms;
+  cudaEventElapsedTime(&ms, w->ev[5], w->ev[6]); p.ms_replay = ms;
+  cudaEventElapsedTime(&ms, w->ev[0], w->ev[6]); p.ms_total = ms;
+  p.n_queries = n_q; p.n_query_tokens = n_tok;
+  p.n_slices = (int64_t)(w->h_ctr->slice_elem >> kElemBits);
+  p.n_elements = (int64_t)(w->h_ctr->slice_elem & ((1ull << kElemBits) - 1));
+  p.n_survivors = w->h_ctr->n_surv;
+  p.n_matches = w->h_ctr->n_matches;
+  p.launches = launches; p.retries = retries;
+  std::lock_guard<std::mutex> g(ix->mu);
+  ix->last_profile = p;
+}
+
+static int match_device(Index* ix, Workspace* w, const int32_t* d_q_tok, const int32_t* d_q_off, int64_t n_q, int64_t n_tok,
+                        const Params& pr, int64_t cap, fm_match* d_out, int32_t* d_out_count, cudaStream_t st) {
+  int rc, launches = 0, retries = 0;
+  if ((rc = initial_worklists(w, n_q, n_tok))) return rc;
+  for (int attempt = 0;; attempt++) {
+    if ((rc = launch_shard(ix, w, d_q_tok, d_q_off, n_q, n_tok, pr, st, &launches))) return rc;
+    if ((rc = run_replay(ix, w, w->rec, w->q_cnt, w->q_base, w->heapbuf, w->acc_cnt, d_q_off, n_q, pr, cap, d_out, d_out_count,
+                         st, &launches)))
+      return rc;
+    const int again = sync_and_check(w, st, attempt, &retries);
+    if (again < 0) return -again;
+    if (!again) break;
+  }
+  finish_profile(ix, w, n_q, n_tok, launches, retries);
+  return FM_OK;
+}
+
+}  // namespace fm
+
+using namespace fm;
+
+extern "C" {
+
+const char* fm_last_error(void) { return fm::get_error().c_str(); }
+const char* fm_version(void) { return "fuzzy_match_b200 0.1 (sm_100a)"; }
+
+int fm_index_create(const int32_t* tokens, const int64_t* sent_off, int64_t n_sent, int32_t vocab_size,
+                    int32_t max_tokens_in_pattern, const uint32_t* sfreq_global, int64_t n_sent_global, int64_t s_id_base,
+                    int device, fm_index** out) {
+  Index* ix = nullptr;
+  const int rc = build_index(tokens, sent_off, n_sent, vocab_size, max_tokens_in_pattern, sfreq_global, n_sent_global,
+                             s_id_base, device, &ix);
+  if (out) *out = reinterpret_cast<fm_index*>(ix);
+  return rc;
+}
+
+void fm_index_destroy(fm_index* index) {
+  Index* ix = reinterpret_cast<Index*>(index);
+  if (!ix) return;
+  cudaSetDevice(ix->device);
+  for (Workspace* w : ix->pool) free_workspace(w);
+  free_index(ix);
+}
+
+int64_t fm_index_num_sentences(const fm_index* index) { return reinterpret_cast<const Index*>(index)->n_sent; }
+int64_t fm_index_num_suffixes(const fm_index* index) { return reinterpret_cast<const Index*>(index)->n_suf; }
+int32_t fm_index_max_tokens_in_pattern(const fm_index* index) { return reinterpret_cast<const Index*>(index)->max_tokens; }
+int64_t fm_index_device_bytes(const fm_index* index) { return reinterpret_cast<const Index*>(index)->device_bytes; }
+
+int fm_index_kept_sources(const fm_index* index, int64_t* kept) {
+  const Index* ix = reinterpret_cast<const Index*>(index);
+  if (!ix || !kept) { set_error("NULL argument"); return FM_ERR_INVALID; }
+  std::copy(ix->kept.begin(), ix->kept.end(), kept);
+  return FM_OK;
+}
+int fm_index_sfreq(const fm_index* index, uint32_t* sfreq) {
+  const Index* ix = reinterpret_cast<const Index*>(index);
+  if (!ix || !sfreq) { set_error("NULL argument"); return FM_ERR_INVALID; }
+  std::copy(ix->sfreq.begin(), ix->sfreq.end(), sfreq);
+  return FM_OK;
+}
+int fm_index_sentence(const fm_index* index, uint32_t s, const int32_t** tokens, int32_t* length) {
+  const Index* ix = reinterpret_cast<const Index*>(index);
+  if (!ix || (int64_t)s >= ix->n_sent) { set_error("sentence id out of range"); return FM_ERR_INVALID; }
+  const int32_t st = ix->h_sent_start[s];
+  if (tokens) *tokens = ix->h_tok.data() + st;
+  if (length) {
+    int32_t n = 0;
+    while (ix->h_tok[st + n] != 0) n++;
+    *length = n;
+  }
+  return FM_OK;
+}
+
+int fm_match_batch(fm_index* index, const int32_t* q_tokens, const int64_t* q_off, int64_t n_q, const fm_params* params,
+                   int64_t cap, fm_match* out, int32_t* out_count) {
+  Index* ix = reinterpret_cast<Index*>(index);
+  Params pr;
+  int rc;
+  if (!ix || n_q < 0 || cap < 1 || (n_q > 0 && (!q_off || !out || !out_count))) { set_error("bad argument"); return FM_ERR_INVALID; }
+  if ((rc = check_params(params, &pr))) return rc;
+  if (n_q == 0) return FM_OK;
+  FM_CUDA(cudaSetDevice(ix->device));
+  Workspace* w = acquire(ix);
+  struct Releaser { Index* ix; Workspace* w; ~Releaser() { release(ix, w); } } rel{ix, w};
+  if ((rc = ensure_base(w))) return rc;
+  // chunk so that offsets stay int32 and the workspace stays bounded
+  const int64_t kMaxQ = 1 << 20, kMaxTok = 1 << 25;
+  int64_t q0 = 0;
+  while (q0 < n_q) {
+    int64_t q1 = std::min(n_q, q0 + kMaxQ);
+    while (q1 > q0 + 1 && q_off[q1] - q_off[q0] > kMaxTok) q1 = q0 + (q1 - q0) / 2;
+    const int64_t nq = q1 - q0, ntok = q_off[q1] - q_off[q0];
+    if (ntok < 0 || ntok > (int64_t(1) << 29)) { set_error("bad q_off"); return FM_ERR_INVALID; }
+    if ((rc = ensure_queries(w, nq, ntok, true)) || (rc = ensure_out(w, nq, cap))) return rc;
+    for (int64_t i = 0; i <= nq; i++) w->h_q_off32[i] = (int32_t)(q_off[q0 + i] - q_off[q0]);
+    cudaStream_t st = w->stream;
+    FM_CUDA(cudaMemcpyAsync(w->d_q_off, w->h_q_off32, (nq + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (ntok) FM_CUDA(cudaMemcpyAsync(w->d_q_tok, q_tokens + q_off[q0], ntok * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    FM_CUDA(cudaMemsetAsync(w->d_out, 0, nq * cap * sizeof(fm_match), st));
+    if ((rc = match_device(ix, w, w->d_q_tok, w->d_q_off, nq, ntok, pr, cap, w->d_out, w->d_out_count, st))) return rc;
+    FM_CUDA(cudaMemcpyAsync(out + q0 * cap, w->d_out, nq * cap * sizeof(fm_match), cudaMemcpyDeviceToHost, st));
+    FM_CUDA(cudaMemcpyAsync(out_count + q0, w->d_out_count, nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    FM_CUDA(cudaStreamSynchronize(st));
+    q0 = q1;
+  }
+  return FM_OK;
+}
+
+int fm_match_batch_device(fm_index* index, const int32_t* d_q_tokens, const int32_t* d_q_off, int64_t n_q,
+                          int64_t n_query_tokens, const fm_params* params, int64_t cap, fm_match* d_out, int32_t* d_out_count,
+                          void* stream) {
+  Index* ix = reinterpret_cast<Index*>(index);
+  Params pr;
+  int rc;
+  if (!ix || n_q < 0 || cap < 1 || n_q > (1 << 24) || n_query_tokens > (int64_t(1) << 29)) { set_error("bad argument"); return FM_ERR_INVALID; }
+  if ((rc = check_params(params, &pr))) return rc;
+  if (n_q == 0) return FM_OK;
+  FM_CUDA(cudaSetDevice(ix->device));
+  Workspace* w = acquire(ix);
+  struct Releaser { Index* ix; Workspace* w; ~Releaser() { release(ix, w); } } rel{ix, w};
+  if ((rc = ensure_base(w)) || (rc = ensure_queries(w, n_q, n_query_tokens, false))) return rc;
+  return match_device(ix, w, d_q_tokens, d_q_off, n_q, n_query_tokens, pr, cap, d_out, d_out_count,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int fm_shard_score_device(fm_index* index, const int32_t* d_q_tokens, const int32_t* d_q_off, int64_t n_q,
+                          int64_t n_query_tokens, const fm_params* params, const int32_t** d_rec_off, const fm_record** d_rec,
+                          int64_t* n_rec, void* stream) {
+  Index* ix = reinterpret_cast<Index*>(index);
+  Params pr;
+  int rc;
+  if (!ix || n_q < 1 || !d_rec_off || !d_rec || !n_rec) { set_error("bad argument"); return FM_ERR_INVALID; }
+  if ((rc = check_params(params, &pr))) return rc;
+  FM_CUDA(cudaSetDevice(ix->device));
+  // the shard workspace stays reserved for this index: pool[0] is dedicated to the sharded path
+  Workspace* w = acquire(ix);
+  struct Releaser { Index* ix; Workspace* w; ~Releaser() { release(ix, w); } } rel{ix, w};
+  if ((rc = ensure_base(w)) || (rc = ensure_queries(w, n_q, n_query_tokens, false))) return rc;
+  int launches = 0, retries = 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((rc = initial_worklists(w, n_q, n_query_tokens))) return rc;
+  for (int attempt = 0;; attempt++) {
+    if ((rc = launch_shard(ix, w, d_q_tokens, d_q_off, n_q, n_query_tokens, pr, st, &launches))) return rc;
+    if (ix->profiling) cudaEventRecord(w->ev[6], st);
+    const int again = sync_and_check(w, st, attempt, &retries);
+    if (again < 0) return -again;
+    if (!again) break;
+  }
+  finish_profile(ix, w, n_q, n_query_tokens, launches, retries);
+  *d_rec_off = w->q_base;
+  *d_rec = w->rec;
+  *n_rec = (int64_t)w->h_ctr->n_surv;
+  return FM_OK;
+}
+
+int fm_merge_replay_device(fm_index* index, int n_shards, const int32_t* const* d_rec_off, const fm_record* const* d_rec,
+                           const int32_t* d_q_off, int64_t n_q, const fm_params* params, int64_t cap, fm_match* d_out,
+                           int32_t* d_out_count, void* stream) {
+  Index* ix = reinterpret_cast<Index*>(index);
+  Params pr;
+  int rc;
+  if (!ix || n_shards < 1 || n_shards > 16 || n_q < 1 || !d_rec_off || !d_rec) { set_error("bad argument"); return FM_ERR_INVALID; }
+  if ((rc = check_params(params, &pr))) return rc;
+  if (pr.contrast > 0.f && n_shards > 1) {
+    set_error("contrastive rerank needs the sentences of every shard; not supported on a sharded TM");
+    return FM_ERR_INVALID;
+  }
+  FM_CUDA(cudaSetDevice(ix->device));
+  Workspace* w = acquire(ix);
+  struct Releaser { Index* ix; Workspace* w; ~Releaser() { release(ix, w); } } rel{ix, w};
+  if ((rc = ensure_base(w))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_q > w->cap_mq) {
+    if ((rc = dev_realloc(&w->m_cnt, n_q + 1)) || (rc = dev_realloc(&w->m_base, n_q + 1)) || (rc = dev_realloc(&w->m_acc, n_q + 1)))
+      return rc;
+    w->cap_mq = n_q;
+    w->cap_mrec = 0;  // m_heap depends on cap_mq
+  }
+  int launches = 0;
+  launch_merge_count(n_shards, d_rec_off, w->m_cnt, (int32_t)n_q, st);
+  launch_scan(w->m_cnt, w->m_base, (int32_t)n_q, st);
+  int32_t total = 0;
+  FM_CUDA(cudaMemcpyAsync(&total, w->m_base + n_q, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  FM_CUDA(cudaStreamSynchronize(st));
+  if (total + n_q + 1 > w->cap_mrec) {
+    const int64_t c = total + total / 4 + n_q + 1024;
+    if ((rc = dev_realloc(&w->mrec, c)) || (rc = dev_realloc(&w->m_heap, c + w->cap_mq + 1))) return rc;
+    w->cap_mrec = c;
+  }
+  launch_merge_copy(n_shards, d_rec_off, d_rec, w->m_base, w->mrec, (int32_t)n_q, st);
+  launches += 3;
+  FM_CUDA(cudaMemsetAsync(w->ctr, 0, sizeof(Counters), st));
+  if ((rc = run_replay(ix, w, w->mrec, w->m_cnt, w->m_base, w->m_heap, w->m_acc, d_q_off, n_q, pr, cap, d_out, d_out_count, st, &launches)))
+    return rc;
+  FM_CUDA(cudaStreamSynchronize(st));
+  FM_CUDA(cudaGetLastError());
+  return FM_OK;
+}
+
+int fm_set_profiling(fm_index* index, int enabled) {
+  Index* ix = reinterpret_cast<Index*>(index);
+  if (!ix) { set_error("NULL index"); return FM_ERR_INVALID; }
+  ix->profiling = enabled != 0;
+  return FM_OK;
+}
+int fm_get_profile(const fm_index* index, fm_profile* out) {
+  Index* ix = const_cast<Index*>(reinterpret_cast<const Index*>(index));
+  if (!ix || !out) { set_error("NULL argument"); return FM_ERR_INVALID; }
+  std::lock_guard<std::mutex> g(ix->mu);
+  *out = ix->last_profile;
+  return FM_OK;
+}
+
+}  // extern "C"

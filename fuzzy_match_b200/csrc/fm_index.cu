@@ -1,0 +1,194 @@
+// fm_index.cu -- host-side index build and upload.
+//
+// Replaces, for pre-tokenised int32 input, what the reference does in FuzzyMatch::add_tm(Tokens) +
+// sort() (reference src/suffix_array_index.cc:10-30, src/suffix_array.cc:9-27,58-102,253-261,
+// src/vocab_indexer.cc:73-90): drop empty / over-long sentences, count word-in-sentence
+// frequencies, sort the sentence-bounded suffixes and build the first-word bucket table.
+// The order among suffixes that compare equal is immaterial to match() (ranges are sets), so any
+// total order works; here ties break by position, which equals the reference's sentence-id order.
+// The build runs on host threads for now (a GPU build is the first "next" row of SURVEY.md 8f).
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <thread>
+
+#include "fm_internal.h"
+
+namespace fm {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+const std::string& get_error() { return g_error; }
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what);
+  return FM_ERR_CUDA;
+}
+
+template <class T>
+static int upload(const std::vector<T>& h, size_t extra, void** slot, const T** out, int64_t* bytes) {
+  void* d = nullptr;
+  const size_t n = (h.size() + extra) * sizeof(T);
+  FM_CUDA(cudaMalloc(&d, n ? n : 16));
+  FM_CUDA(cudaMemset(d, 0, n ? n : 16));
+  if (!h.empty()) FM_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *slot = d;
+  *out = static_cast<const T*>(d);
+  *bytes += (int64_t)n;
+  return FM_OK;
+}
+
+void free_index(Index* ix) {
+  if (!ix) return;
+  cudaSetDevice(ix->device);
+  for (void* p : ix->d_blocks)
+    if (p) cudaFree(p);
+  delete ix;
+}
+
+int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_in, int32_t vocab_size, int32_t max_tokens,
+                const uint32_t* sfreq_global, int64_t n_sent_global, int64_t s_id_base, int device, Index** out) {
+  if (!out) { set_error("out is NULL"); return FM_ERR_INVALID; }
+  *out = nullptr;
+  if (n_in < 0 || (n_in > 0 && (!tokens || !sent_off))) { set_error("bad TM arrays"); return FM_ERR_INVALID; }
+  if (vocab_size < 2) { set_error("vocab_size must be >= 2"); return FM_ERR_INVALID; }
+  if (max_tokens < 1 || max_tokens > FM_MAX_TOKENS) {
+    set_error("max_tokens_in_pattern must be in [1, " + std::to_string(FM_MAX_TOKENS) + "]");
+    return FM_ERR_INVALID;
+  }
+  Index* ix = new Index();
+  ix->device = device;
+  ix->vocab_size = vocab_size;
+  ix->max_tokens = max_tokens;
+
+  // ---- kept sentences and the padded token buffer
+  int64_t n_keep = 0, n_suf = 0, n_buf = 0;
+  for (int64_t s = 0; s < n_in; s++) {
+    const int64_t len = sent_off[s + 1] - sent_off[s];
+    if (len < 0) { delete ix; set_error("sent_off is not non-decreasing"); return FM_ERR_INVALID; }
+    if (len > 0 && len <= max_tokens) {
+      n_keep++;
+      n_suf += len;
+      n_buf += (len + 1 + 3) & ~int64_t(3);
+    }
+  }
+  n_buf += 8;  // zero tail so 128-bit loads of the last sentence stay in bounds
+  if (n_buf >= (int64_t(1) << 31) - 64) { delete ix; set_error("TM shard too large for int32 offsets"); return FM_ERR_INVALID; }
+  ix->n_sent = n_keep;
+  ix->n_suf = n_suf;
+  ix->n_buf = n_buf;
+  ix->h_tok.assign((size_t)n_buf, 0);
+  ix->h_sent_start.resize((size_t)n_keep + 1);
+  ix->kept.resize((size_t)n_keep);
+  ix->sfreq.assign((size_t)vocab_size, 0);
+  std::vector<uint32_t> meta_of_pos((size_t)n_buf, 0);
+  std::vector<int32_t> sid_at((size_t)(n_buf / 4) + 1, -1);
+  {
+    std::vector<int64_t> stamp((size_t)vocab_size, -1);
+    int64_t cur = 0, k = 0;
+    for (int64_t s = 0; s < n_in; s++) {
+      const int64_t len = sent_off[s + 1] - sent_off[s];
+      if (!(len > 0 && len <= max_tokens)) continue;
+      ix->h_sent_start[k] = (int32_t)cur;
+      ix->kept[k] = s;
+      sid_at[cur >> 2] = (int32_t)k;
+      for (int64_t i = 0; i < len; i++) {
+        const int32_t t = tokens[sent_off[s] + i];
+        if (t < 2 || t >= vocab_size) {
+          delete ix;
+          set_error("TM token id outside [2, vocab_size) in sentence " + std::to_string(s));
+          return FM_ERR_INVALID;
+        }
+        ix->h_tok[cur + i] = t;
+        meta_of_pos[cur + i] = ((uint32_t)len << 16) | (uint32_t)i;
+        if (stamp[t] != k) { stamp[t] = k; ix->sfreq[t]++; }
+      }
+      cur += (len + 1 + 3) & ~int64_t(3);
+      k++;
+    }
+    ix->h_sent_start[n_keep] = (int32_t)cur;
+  }
+
+  // ---- suffix sort: counting sort on the first token, then each bucket by the rest
+  std::vector<int32_t> qva((size_t)vocab_size + 1, 0);
+  std::vector<int32_t> sa((size_t)n_suf);
+  {
+    std::vector<int64_t> cnt((size_t)vocab_size + 1, 0);
+    for (int64_t k = 0; k < n_keep; k++)
+      for (int32_t pos = ix->h_sent_start[k]; ix->h_tok[pos] != 0; pos++) cnt[ix->h_tok[pos] + 1]++;
+    for (int32_t w = 0; w < vocab_size; w++) cnt[w + 1] += cnt[w];
+    for (int32_t w = 0; w <= vocab_size; w++) qva[w] = (int32_t)cnt[w];
+    for (int64_t k = 0; k < n_keep; k++)
+      for (int32_t pos = ix->h_sent_start[k]; ix->h_tok[pos] != 0; pos++) sa[cnt[ix->h_tok[pos]]++] = pos;
+  }
+  {
+    std::vector<int32_t> order;  // non-trivial buckets, largest first
+    for (int32_t w = 2; w < vocab_size; w++)
+      if (qva[w + 1] - qva[w] > 1) order.push_back(w);
+    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return qva[a + 1] - qva[a] > qva[b + 1] - qva[b]; });
+    const int32_t* tok = ix->h_tok.data();
+    auto less = [tok](int32_t a, int32_t b) {
+      const int32_t* x = tok + a + 1;
+      const int32_t* y = tok + b + 1;
+      for (;; x++, y++) {
+        if (*x != *y) return *x < *y;
+        if (*x == 0) return a < b;
+      }
+    };
+    std::atomic<size_t> next(0);
+    auto work = [&]() {
+      for (;;) {
+        const size_t i = next.fetch_add(1);
+        if (i >= order.size()) break;
+        const int32_t w = order[i];
+        std::sort(sa.begin() + qva[w], sa.begin() + qva[w + 1], less);
+      }
+    };
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt == 0) nt = 4;
+    if (nt > 64) nt = 64;
+    if (order.size() < 64) nt = 1;
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nt; t++) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+  }
+  std::vector<uint32_t> sa_meta((size_t)n_suf);
+  for (int64_t i = 0; i < n_suf; i++) sa_meta[i] = meta_of_pos[sa[i]];
+  std::vector<uint32_t>().swap(meta_of_pos);
+
+  // ---- IDF table, host libm exactly as src/fuzzy_match.cc:367-390
+  const uint32_t* sf = sfreq_global ? sfreq_global : ix->sfreq.data();
+  const unsigned num_sentences = (unsigned)(n_sent_global > 0 ? n_sent_global : n_keep);
+  std::vector<float> idf((size_t)vocab_size, 0.f);
+  for (int32_t w = 2; w < vocab_size; w++)
+    if (sf[w] > 0) idf[w] = std::log((float)num_sentences / (float)sf[w]);
+  if (sfreq_global) std::copy(sfreq_global, sfreq_global + vocab_size, ix->sfreq.begin());
+
+  // ---- upload
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { delete ix; return cuda_fail(e, "cudaSetDevice"); }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ix->sm_count = prop.multiProcessorCount;
+  int rc;
+  IndexDev& d = ix->dev;
+  if ((rc = upload(ix->h_tok, 0, &ix->d_blocks[0], &d.tok, &ix->device_bytes)) ||
+      (rc = upload(sa, 4, &ix->d_blocks[1], &d.sa_pos, &ix->device_bytes)) ||
+      (rc = upload(sa_meta, 4, &ix->d_blocks[2], &d.sa_meta, &ix->device_bytes)) ||
+      (rc = upload(qva, 0, &ix->d_blocks[3], &d.qva, &ix->device_bytes)) ||
+      (rc = upload(sid_at, 0, &ix->d_blocks[4], &d.sid_at, &ix->device_bytes)) ||
+      (rc = upload(idf, 0, &ix->d_blocks[5], &d.idf, &ix->device_bytes))) {
+    free_index(ix);
+    return rc;
+  }
+  d.vocab_size = vocab_size;
+  d.max_tokens = max_tokens;
+  d.n_suf = n_suf;
+  d.sid_base = (uint32_t)s_id_base;
+  d.idf_max = (float)std::log((double)num_sentences);
+  *out = ix;
+  return FM_OK;
+}
+
+}  // namespace fm

@@ -1,0 +1,193 @@
+// fm_internal.h -- shared declarations of the B200 fuzzy-match library (host + device).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/fuzzy_match_b200.h"
+
+namespace fm {
+
+// ---------------------------------------------------------------- device-resident index (HBM layout)
+//
+// tok      int32[n_buf]   kept sentences back to back; every sentence starts on a 16-byte boundary
+//                         (multiple of 4 tokens) and is followed by >= 1 zero (the separator); the zero
+//                         sorts before every word id, so "shorter suffix first" needs no length check.
+// sa_pos   int32[n_suf]   suffix array: absolute offset into tok of each suffix, sorted.
+// sa_meta  uint32[n_suf]  (sentence length << 16) | offset of the suffix inside its sentence, so the
+//                         range walk gets length + sentence start from one 8-byte (pos, meta) pair.
+// qva      int32[V+1]     first-word bucket table (reference _quickVocabAccess).
+// sid_at   int32[n_buf/4] local sentence id, stored at (sentence start / 4); only read for survivors.
+// idf      float[V]       logf(N / sfreq[w]) computed on the host with glibc (0 for unseen words).
+struct IndexDev {
+  const int32_t* tok;
+  const int32_t* sa_pos;
+  const uint32_t* sa_meta;
+  const int32_t* qva;
+  const int32_t* sid_at;
+  const float* idf;
+  int32_t vocab_size;
+  int32_t max_tokens;
+  int64_t n_suf;
+  uint32_t sid_base;
+  float idf_max;  // (float)log((double)N_sent_global)
+};
+
+// per-query metadata written by the prepare kernel
+//   x = pattern length p (0 if the query is skipped), y = effective min_subseq_length,
+//   z = offset of the pattern in the token arrays, w = 1 if the query takes part
+typedef int4 QMeta;
+
+struct SurvRec {  // one distinct (query, sentence) that passed both rejection bounds
+  int32_t q;
+  int32_t start;  // sentence start in tok (unique per sentence, ascending with s_id)
+  int32_t hslot;  // slot in the dedup table (holds the running max of the n-gram match length)
+  int32_t j;      // arrival index inside its query
+};
+
+struct Counters {
+  unsigned long long slice_elem;  // (n_slices << 38) | n_elements, one packed atomic
+  unsigned int n_surv;
+  unsigned int overflow;  // bit0 slices, bit1 survivors
+  unsigned int n_matches;
+  unsigned int pad[3];
+};
+static const int kElemBits = 38;
+
+// per-batch workspace pointers (device)
+struct BatchDev {
+  // inputs
+  const int32_t* q_tok_in;
+  const int32_t* q_off;  // [n_q+1]
+  int32_t n_q;
+  int32_t n_tok;
+  // prepared
+  int32_t* pat;      // [n_tok] sanitised pattern tokens
+  int32_t* chain_q;  // [n_tok] query of each chain (= pattern position)
+  QMeta* qmeta;      // [n_q]
+  int2* tbl;         // [4*n_tok] per-query open-addressing tables: (word, distinct_idx | count<<16)
+  // search output
+  long long* sl_start;  // [slice_cap+1] first flattened element of each slice (ascending)
+  int4* sl_rec;         // [slice_cap] (q, sa_begin, match_len, size)
+  int64_t slice_cap;
+  // gather output
+  unsigned long long* hkey;  // [hsize] (q<<32 | start), ~0 = empty
+  unsigned int* hlm;         // [hsize] max match length
+  uint32_t hmask;
+  SurvRec* surv;      // [surv_cap]
+  uint16_t* surv_len; // [surv_cap]
+  int64_t surv_cap;
+  int32_t* q_cnt;   // [n_q+1] distinct survivors per query
+  int32_t* q_base;  // [n_q+1] exclusive scan of q_cnt
+  // scoring / replay
+  fm_record* rec;   // [surv_cap] grouped by query
+  float* heapbuf;   // [surv_cap + n_q]
+  int32_t* acc_cnt; // [n_q] accepted matches per query (contrastive path)
+  Counters* ctr;
+};
+
+struct Params {  // fm_params + derived
+  float fuzzy;
+  int32_t n_matches;
+  int32_t no_perfect;
+  int32_t ml;
+  float mr;
+  float idf_penalty;
+  float ins, del, rep;
+  float contrast;
+  int32_t reduce;
+  int32_t buffer;  // already resolved (-1 -> n_matches)
+};
+
+// ---------------------------------------------------------------- host objects
+
+struct Workspace {
+  int device = 0;
+  cudaStream_t stream = nullptr;  // owned stream for the host-buffer API
+  // capacities
+  int64_t cap_q = 0, cap_tok = 0, cap_slices = 0, cap_surv = 0, cap_out = 0;
+  uint32_t hsize = 0;
+  // device buffers
+  int32_t *d_q_tok = nullptr, *d_q_off = nullptr;  // staging for host inputs
+  int32_t *pat = nullptr, *chain_q = nullptr;
+  QMeta* qmeta = nullptr;
+  int2* tbl = nullptr;
+  long long* sl_start = nullptr;
+  int4* sl_rec = nullptr;
+  unsigned long long* hkey = nullptr;
+  unsigned int* hlm = nullptr;
+  SurvRec* surv = nullptr;
+  uint16_t* surv_len = nullptr;
+  int32_t *q_cnt = nullptr, *q_base = nullptr, *acc_cnt = nullptr;
+  fm_record* rec = nullptr;
+  float* heapbuf = nullptr;
+  Counters* ctr = nullptr;
+  fm_match* d_out = nullptr;
+  int32_t* d_out_count = nullptr;
+  // merged-shard buffers
+  fm_record* mrec = nullptr;
+  int32_t *m_cnt = nullptr, *m_base = nullptr, *m_acc = nullptr;
+  float* m_heap = nullptr;
+  int64_t cap_mrec = 0, cap_mq = 0;
+  // pinned host staging
+  Counters* h_ctr = nullptr;
+  int32_t* h_q_off32 = nullptr;
+  int64_t cap_hq = 0;
+  // profiling
+  cudaEvent_t ev[8] = {};
+  bool in_use = false;
+};
+
+struct Index {
+  int device = 0;
+  IndexDev dev{};
+  // host copies
+  std::vector<int32_t> h_tok;
+  std::vector<int32_t> h_sent_start;  // [n_sent+1]
+  std::vector<int64_t> kept;
+  std::vector<uint32_t> sfreq;
+  int64_t n_sent = 0, n_suf = 0, n_buf = 0;
+  int64_t device_bytes = 0;
+  int32_t vocab_size = 0, max_tokens = 0;
+  void* d_blocks[8] = {};
+  int sm_count = 148;
+  // workspaces
+  std::mutex mu;
+  std::vector<Workspace*> pool;
+  bool profiling = false;
+  fm_profile last_profile{};
+};
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+#define FM_CUDA(call)                                     \
+  do {                                                    \
+    cudaError_t e__ = (call);                             \
+    if (e__ != cudaSuccess) return fm::cuda_fail(e__, #call); \
+  } while (0)
+
+// fm_index.cu
+int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_sent, int32_t vocab_size, int32_t max_tokens,
+                const uint32_t* sfreq_global, int64_t n_sent_global, int64_t s_id_base, int device, Index** out);
+void free_index(Index* ix);
+
+// fm_kernels.cu -- launchers (all asynchronous on `st`)
+void launch_prepare(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st);
+void launch_search(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st);
+void launch_gather(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st);
+void launch_scan(const int32_t* in, int32_t* out, int32_t n, cudaStream_t st);
+void launch_score(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st);
+void launch_replay(const IndexDev& ix, const fm_record* rec, const int32_t* q_cnt, const int32_t* q_base, float* heapbuf,
+                   int32_t* acc_cnt, const int32_t* q_off, int32_t n_q, const Params& p, int64_t cap, fm_match* out,
+                   int32_t* out_count, Counters* ctr, cudaStream_t st);
+void launch_contrast(const IndexDev& ix, fm_record* rec, const int32_t* q_base, const int32_t* acc_cnt, int32_t n_q,
+                     const Params& p, int64_t cap, fm_match* out, int32_t* out_count, Counters* ctr, int sm_count,
+                     cudaStream_t st);
+void launch_merge_count(int n_shards, const int32_t* const* d_rec_off_dev, int32_t* m_cnt, int32_t n_q, cudaStream_t st);
+void launch_merge_copy(int n_shards, const int32_t* const* d_rec_off_dev, const fm_record* const* d_rec_dev,
+                       const int32_t* m_base, fm_record* mrec, int32_t n_q, cudaStream_t st);
+
+}  // namespace fm

@@ -1,0 +1,788 @@
+// fm_kernels.cu -- hand-written sm_100a kernels of the fuzzy-match hot path.
+//
+// One batch of patterns streams through six launches (no host round trip in between):
+//   prepare  per query: clamp ml, sanitise ids, build the pattern's word table
+//   search   per (query, start position): narrow suffix-array ranges, emit range slices
+//   gather   per suffix-array element of every slice: length bound, sentence fetch, coverage bound,
+//            dedup (query, sentence) with max match length            <- the "suffix-range gather"
+//   scan     exclusive scan of survivors per query
+//   score    per surviving (query, sentence): warp-wide wavefront edit-distance DP
+//   replay   per query: the reference's sequential bound heap / top-N over the scored candidates
+//   (+ contrast: per query warp, contrastive rerank)
+//
+// Integer indexing and scalar fp32 only -- no tensor cores. All float arithmetic that reaches a
+// result is written with __fadd_rn/__fmul_rn/__fdiv_rn in the reference's evaluation order so no
+// FMA contraction or reassociation can change a bit (the file is also compiled with -fmad=false).
+#include <cfloat>
+
+#include "fm_internal.h"
+
+namespace fm {
+
+#define FULL 0xffffffffu
+
+// ---------------------------------------------------------------- small device helpers
+
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x = ((x >> 16) ^ x) * 0x45d9f3bu;
+  x = ((x >> 16) ^ x) * 0x45d9f3bu;
+  return (x >> 16) ^ x;
+}
+__device__ __forceinline__ uint32_t hash64(unsigned long long k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return (uint32_t)k;
+}
+__device__ __forceinline__ int next_pow2(int v) {  // smallest power of two >= v (v >= 1)
+  return v <= 1 ? 1 : 1 << (32 - __clz(v - 1));
+}
+__device__ __forceinline__ int4 ldg_nc_v4(const int4* p) {
+  int4 r;
+  asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+// Costs::get_normalizer (reference include/fuzzy/costs.hh:33-47)
+__device__ __forceinline__ float normalizer(int p, int s, const Params& pr) {
+  if (pr.ins == 0.f && pr.del == 0.f && pr.rep == 0.f) return 1.f;
+  const float fp = (float)p, fs = (float)s;
+  if (__fadd_rn(pr.ins, pr.del) <= pr.rep) return __fadd_rn(__fmul_rn(pr.ins, fp), __fmul_rn(pr.del, fs));
+  if (p <= s) return __fadd_rn(__fmul_rn(__fsub_rn(pr.rep, pr.del), fp), __fmul_rn(pr.del, fs));
+  return __fadd_rn(__fmul_rn(__fsub_rn(pr.rep, pr.ins), fs), __fmul_rn(pr.ins, fp));
+}
+// NGramMatches::theoretical_rejection (reference src/ngram_matches.cc:32-39)
+__device__ __forceinline__ bool reject_length(int p, int s, const Params& pr) {
+  const float diff = fabsf(__fsub_rn((float)p, (float)s));
+  const float rc = (p >= s) ? pr.ins : pr.del;
+  const float bound = __fsub_rn(1.f, __fdiv_rn(__fmul_rn(rc, diff), normalizer(p, s, pr)));
+  return (double)bound + 0.000005 < (double)pr.fuzzy;
+}
+// NGramMatches::theoretical_rejection_cover (reference src/ngram_matches.cc:42-59)
+__device__ __forceinline__ bool reject_cover(int p, int s, int cover, const Params& pr) {
+  const float fp = (float)p, fs = (float)s, fc = (float)cover;
+  float num;
+  if (__fadd_rn(pr.ins, pr.del) < pr.rep) {
+    num = __fadd_rn(__fmul_rn(pr.ins, __fsub_rn(fs, fc)), __fmul_rn(pr.del, __fsub_rn(fp, fc)));
+  } else {
+    const float rc = (p > s) ? pr.ins : pr.del;
+    const float mn = (p > s) ? fs : fp;
+    const float mx = (p > s) ? fp : fs;
+    num = __fadd_rn(__fmul_rn(pr.rep, __fsub_rn(mn, fc)), __fmul_rn(rc, __fsub_rn(mx, mn)));
+  }
+  const float bound = __fsub_rn(1.f, __fdiv_rn(num, normalizer(p, s, pr)));
+  return (double)bound + 0.000005 < (double)pr.fuzzy;
+}
+// score = int(10000 - cost*100) / 10000.0 narrowed to float (reference src/fuzzy_match.cc:598)
+__device__ __forceinline__ float score_of(float cost) {
+  const int v = (int)__fsub_rn(10000.f, __fmul_rn(cost, 100.f));
+  return (float)((double)v / 10000.0);
+}
+
+// ---------------------------------------------------------------- prepare
+
+// One warp per query. Guards and ml clamp of src/fuzzy_match.cc:450-467; ids outside the vocabulary
+// become VOCAB_UNK (src/vocab_indexer.cc:52-60); the table is PatternCoverage's multiset
+// (src/pattern_coverage.cc:8-13) as an open-addressing table: word -> (distinct index, multiplicity).
+__global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b, Params pr) {
+  const int lane = threadIdx.x & 31;
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= b.n_q) return;
+  const int off = b.q_off[q];
+  const int p = b.q_off[q + 1] - off;
+  const bool valid = p > 0 && p <= ix.max_tokens;
+  int ml = pr.ml;
+  if (ml < 0 || ml > p) ml = p;  // (size_t)ml > pattern.size()
+  const int by_ratio = (int)__fmul_rn(pr.mr, (float)p);
+  if (by_ratio > ml) ml = by_ratio;
+  if (lane == 0) {
+    b.qmeta[q] = make_int4(valid ? p : 0, ml, off, valid ? 1 : 0);
+    b.q_cnt[q] = 0;
+    if (q == 0) b.q_cnt[b.n_q] = 0;
+  }
+  if (p <= 0) return;
+  for (int j = lane; j < p; j += 32) {
+    const int t = b.q_tok_in[off + j];
+    b.pat[off + j] = (t >= 2 && t < ix.vocab_size) ? t : 1;
+    b.chain_q[off + j] = q;
+  }
+  if (!valid) return;
+  const int ts = next_pow2(2 * p);
+  int2* tbl = b.tbl + 4ll * off;
+  for (int j = lane; j < ts; j += 32) tbl[j] = make_int2(-1, 0);
+  __syncwarp();
+  if (lane == 0) {
+    int distinct = 0;
+    for (int j = 0; j < p; j++) {
+      const int w = b.pat[off + j];
+      int h = hash32((uint32_t)w) & (ts - 1);
+      while (tbl[h].x != -1 && tbl[h].x != w) h = (h + 1) & (ts - 1);
+      if (tbl[h].x == -1) tbl[h] = make_int2(w, (distinct++) | (1 << 16));
+      else tbl[h].y += 1 << 16;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- search
+
+// Warp-collective append of up to two range slices per lane. One packed 64-bit atomic per warp
+// reserves slice slots and flattened element offsets together, so slice order == element order.
+__device__ __forceinline__ void emit_slices(const BatchDev& b, int lane, int q, int n, int beg0, int sz0, int lm0, int beg1,
+                                            int sz1, int lm1) {
+  const unsigned long long mine = ((unsigned long long)n << kElemBits) | (unsigned long long)(unsigned)(sz0 + sz1);
+  unsigned long long incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long o = __shfl_up_sync(FULL, incl, d);
+    if (lane >= d) incl += o;
+  }
+  const unsigned long long total = __shfl_sync(FULL, incl, 31);
+  if (total == 0) return;
+  unsigned long long base = 0;
+  if (lane == 31) base = atomicAdd(&b.ctr->slice_elem, total);
+  base = __shfl_sync(FULL, base, 31);
+  const unsigned long long excl = base + incl - mine;
+  long long slot = (long long)(excl >> kElemBits);
+  long long start = (long long)(excl & ((1ull << kElemBits) - 1));
+  if (n > 0) {
+    if (slot + n > b.slice_cap) {
+      atomicOr(&b.ctr->overflow, 1u);
+      return;
+    }
+    if (sz0 > 0) {
+      b.sl_start[slot] = start;
+      b.sl_rec[slot] = make_int4(q, beg0, lm0, sz0);
+      slot++;
+      start += sz0;
+    }
+    if (sz1 > 0) {
+      b.sl_start[slot] = start;
+      b.sl_rec[slot] = make_int4(q, beg1, lm1, sz1);
+    }
+  }
+}
+
+// One thread per (query, start position) chain: the n-gram walk of src/fuzzy_match.cc:484-551 with
+// SuffixArray::equal_range (src/suffix_array.cc:105-212) restated as lower/upper bound on the ONE new
+// token at depth k inside the previous range (every suffix there already shares k tokens).
+__global__ void __launch_bounds__(256) fm_search_kernel(IndexDev ix, BatchDev b) {
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  int q = 0, it = 0, p = 0, ml = 0;
+  const int32_t* pat = b.pat;
+  bool live = c < b.n_tok;
+  if (live) {
+    q = b.chain_q[c];
+    const QMeta m = b.qmeta[q];
+    p = m.x; ml = m.y; it = c - m.z; pat = b.pat + m.z;
+    live = m.w != 0;
+  }
+  int lo = 0, hi = 0, len = 0;
+  if (live) {
+    const int t0 = pat[it];
+    if (t0 >= 2) { lo = ix.qva[t0]; hi = ix.qva[t0 + 1]; }
+    len = hi > lo ? 1 : 0;
+    live = len == 1;
+  }
+  // p == 1: the unigram range itself is registered (src/fuzzy_match.cc:484-493)
+  {
+    const bool uni = live && p == 1 && 1 >= ml;
+    emit_slices(b, lane, q, uni ? 1 : 0, lo, uni ? hi - lo : 0, 1, 0, 0, 0);
+  }
+  bool extending = live && it + 1 < p;
+  while (__any_sync(FULL, extending)) {
+    int n = 0, beg0 = 0, sz0 = 0, beg1 = 0, sz1 = 0;
+    if (extending) {
+      const int t = pat[it + len];  // token at depth len
+      int nlo = lo, nhi = lo;
+      if (t >= 2) {
+        int a = lo, e = hi;
+        while (a < e) {  // first suffix whose token at depth len is >= t
+          const int mid = (int)(((unsigned)a + (unsigned)e) >> 1);
+          const int v = __ldg(ix.tok + (__ldg(ix.sa_pos + mid) + len));
+          if (v < t) a = mid + 1; else e = mid;
+        }
+        nlo = a;
+        nhi = a;
+        if (a < hi && __ldg(ix.tok + (__ldg(ix.sa_pos + a) + len)) == t) {
+          int a2 = a + 1, e2 = hi;
+          while (a2 < e2) {  // first suffix whose token at depth len is > t
+            const int mid = (int)(((unsigned)a2 + (unsigned)e2) >> 1);
+            const int v = __ldg(ix.tok + (__ldg(ix.sa_pos + mid) + len));
+            if (v <= t) a2 = mid + 1; else e2 = mid;
+          }
+          nhi = a2;
+        }
+      }
+      if (nhi > nlo) {
+        // range for length len+1 is non-empty; the shaved-off parts matched exactly len tokens
+        if (len + 1 > 2 && len >= ml) {
+          beg0 = lo; sz0 = nlo - lo;
+          beg1 = nhi; sz1 = hi - nhi;
+          n = (sz0 > 0) + (sz1 > 0);
+        }
+        lo = nlo; hi = nhi; len++;
+        if (it + len >= p) extending = false;
+      } else {
+        extending = false;
+      }
+    }
+    emit_slices(b, lane, q, n, beg0, sz0, len - 1, beg1, sz1, len - 1);
+  }
+  {
+    const bool fin = live && len >= 2 && len >= ml;
+    emit_slices(b, lane, q, fin ? 1 : 0, lo, fin ? hi - lo : 0, len, 0, 0, 0);
+  }
+}
+
+// ---------------------------------------------------------------- gather
+
+// PatternCoverage::count_covered_words (src/pattern_coverage.cc:15-28) for one sentence token:
+// look the word up in the query's table; the first time a distinct pattern word is seen, add its
+// multiplicity. `seen` is a bitmask over distinct-word indices.
+template <int MW>
+__device__ __forceinline__ void cover_token(const int2* __restrict__ tbl, int tmask, int w, unsigned* seen, int& cover) {
+  int h = hash32((uint32_t)w) & tmask;
+  for (;;) {
+    const int2 e = __ldg(tbl + h);
+    if (e.x == w) {
+      const int d = e.y & 0xffff;
+      const unsigned bit = 1u << (d & 31);
+      unsigned& word = seen[MW == 1 ? 0 : (d >> 5)];
+      if (!(word & bit)) { word |= bit; cover += e.y >> 16; }
+      return;
+    }
+    if (e.x == -1) return;
+    h = (h + 1) & tmask;
+  }
+}
+
+template <int MW>
+__device__ __forceinline__ int cover_sentence(const int32_t* __restrict__ sent, int slen, const int2* tbl, int tmask) {
+  unsigned seen[MW];
+#pragma unroll
+  for (int i = 0; i < MW; i++) seen[i] = 0;
+  int cover = 0;
+  const int4* s4 = reinterpret_cast<const int4*>(sent);
+  for (int k = 0; k < slen; k += 4) {
+    const int4 t = ldg_nc_v4(s4 + (k >> 2));
+    cover_token<MW>(tbl, tmask, t.x, seen, cover);
+    if (k + 1 < slen) cover_token<MW>(tbl, tmask, t.y, seen, cover);
+    if (k + 2 < slen) cover_token<MW>(tbl, tmask, t.z, seen, cover);
+    if (k + 3 < slen) cover_token<MW>(tbl, tmask, t.w, seen, cover);
+  }
+  return cover;
+}
+
+// Insert (q, start) into the dedup table keeping the max match length: NGramMatches::_longest_matches
+// (src/ngram_matches.cc:79-81). The first inserter also claims the candidate's slot inside its query.
+__device__ __forceinline__ void add_survivor(const BatchDev& b, int q, int start, int slen, int lm) {
+  const unsigned long long key = ((unsigned long long)(unsigned)q << 32) | (unsigned)start;
+  uint32_t h = hash64(key) & b.hmask;
+  if (*(volatile unsigned int*)&b.ctr->n_surv >= (unsigned long long)b.surv_cap) {  // table (4x cap) must never fill up
+    atomicOr(&b.ctr->overflow, 2u);
+    return;
+  }
+  for (;;) {
+    const unsigned long long prev = atomicCAS(&b.hkey[h], ~0ull, key);
+    if (prev == ~0ull) {
+      const unsigned idx = atomicAdd(&b.ctr->n_surv, 1u);
+      if ((long long)idx >= b.surv_cap) {
+        atomicOr(&b.ctr->overflow, 2u);
+        return;
+      }
+      const int j = atomicAdd(&b.q_cnt[q], 1);
+      atomicMax(&b.hlm[h], (unsigned)lm);
+      b.surv[idx] = SurvRec{q, start, (int32_t)h, j};
+      b.surv_len[idx] = (uint16_t)slen;
+      return;
+    }
+    if (prev == key) {
+      atomicMax(&b.hlm[h], (unsigned)lm);
+      return;
+    }
+    h = (h + 1) & b.hmask;
+  }
+}
+
+// Persistent kernel over the flattened elements of all slices: register_suffix_range_match's walk
+// (src/ngram_matches.cc:62-84) fused with the candidate filter of src/fuzzy_match.cc:576-581.
+// Each warp takes spans of kSpan consecutive elements; element -> slice by one binary search per
+// span plus a 5-step shuffle search per 32 elements (every slice holds >= 1 element).
+static const int kSpan = 128;
+__global__ void __launch_bounds__(256) fm_gather_kernel(IndexDev ix, BatchDev b, Params pr) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const unsigned long long packed = b.ctr->slice_elem;
+  const long long total = (long long)(packed & ((1ull << kElemBits) - 1));
+  long long n_slices = (long long)(packed >> kElemBits);
+  if (n_slices > b.slice_cap) return;  // overflow: the host regrows and reruns
+  for (long long span = warp_id * kSpan; span < total; span += n_warps * kSpan) {
+    // slice containing the first element of the span (uniform across the warp)
+    long long a = 0, e = n_slices;  // largest k with sl_start[k] <= span
+    while (e - a > 1) {
+      const long long mid = (a + e) >> 1;
+      if (__ldg(b.sl_start + mid) <= span) a = mid; else e = mid;
+    }
+    long long k0 = a;
+    for (int u = 0; u < kSpan; u += 32) {
+      const long long el = span + u + lane;
+      if (span + u >= total) break;
+      const long long ks = k0 + lane;
+      const long long st = ks < n_slices ? __ldg(b.sl_start + ks) : 0x7fffffffffffffffll;
+      int j = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const long long v = __shfl_sync(FULL, st, j + step);
+        if (v <= el) j += step;
+      }
+      const long long my_start = __shfl_sync(FULL, st, j);
+      k0 = __shfl_sync(FULL, k0 + j, 31);
+      if (k0 >= n_slices) k0 = n_slices - 1;
+      if (el >= total) continue;
+      const int4 sr = __ldg(b.sl_rec + (ks - lane + j));
+      const int q = sr.x, lm = sr.z;
+      const int i = sr.y + (int)(el - my_start);
+      const int pos = __ldg(ix.sa_pos + i);
+      const unsigned meta = __ldg(ix.sa_meta + i);
+      const int slen = (int)(meta >> 16);
+      const QMeta qm = __ldg(b.qmeta + q);
+      const int p = qm.x;
+      if (reject_length(p, slen, pr)) continue;
+      const int start = pos - (int)(meta & 0xffffu);
+      const int2* tbl = b.tbl + 4ll * qm.z;
+      const int tmask = next_pow2(2 * p) - 1;
+      int cover;
+      if (p <= 32) cover = cover_sentence<1>(ix.tok + start, slen, tbl, tmask);
+      else cover = cover_sentence<32>(ix.tok + start, slen, tbl, tmask);
+      if (reject_cover(p, slen, cover, pr)) continue;
+      add_survivor(b, q, start, slen, lm);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- scan (single CTA, n <= a few million)
+
+__global__ void __launch_bounds__(1024) fm_scan_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, int n) {
+  __shared__ int sums[1024];
+  const int t = threadIdx.x;
+  const int per = (n + 1023) / 1024;
+  const int beg = min(n, t * per), end = min(n, beg + per);
+  int s = 0;
+  for (int i = beg; i < end; i++) s += in[i];
+  sums[t] = s;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
+    const int v = t >= d ? sums[t - d] : 0;
+    __syncthreads();
+    sums[t] += v;
+    __syncthreads();
+  }
+  int run = sums[t] - s;
+  for (int i = beg; i < end; i++) {
+    const int v = in[i];
+    out[i] = run;
+    run += v;
+  }
+  if (t == 1023) out[n] = sums[1023];
+}
+
+// ---------------------------------------------------------------- edit distance (warp wavefront)
+
+// Token-level Levenshtein of src/edit_distance.cc:5-77 (and :79-122 with pen == 0), rows = TM
+// sentence (n1 = s), columns = pattern (n2 = p). Lane l owns columns l*c+1 .. (l+1)*c; at step t it
+// works on row t-l, so the anti-diagonal moves one lane per step and the only exchange is one
+// __shfl_up of (left value, running row minimum). Column state lives in shared memory.
+// Returns C = arr[s][p] and K = max over rows of min_{j>=1} arr[i][j] in every lane.
+__device__ void warp_edit_distance(const int32_t* s_sent, int s, const int32_t* s_pat, int p, const float* s_pen,
+                                   float* s_up, float delw, float insw, float repw, float& C_out, float& K_out) {
+  const int lane = threadIdx.x & 31;
+  const int c = (p + 31) >> 5;
+  const int nl = (p + c - 1) / c;  // lanes that own columns
+  if (lane == 0) {                 // row 0: arr[0][j] = arr[0][j-1] + w*ins (+ idf penalty), :33-39
+    float v = 0.f;
+    for (int j = 1; j <= p; j++) {
+      v = __fadd_rn(__fadd_rn(v, insw), s_pen[j - 1]);
+      s_up[((j - 1) % c) * 32 + (j - 1) / c] = v;
+    }
+  }
+  __syncwarp();
+  float diag = lane == 0 ? 0.f : s_up[(c - 1) * 32 + (lane - 1)];  // arr[0][lane*c]
+  float col0 = 0.f;
+  float recv_left = 0.f, recv_min = FLT_MAX;
+  float K = -FLT_MAX, C = 0.f;
+  const int steps = s + nl - 1;
+  const int jbase = lane * c;
+  for (int t = 1; t <= steps; t++) {
+    const int i = t - lane;
+    const bool active = lane < nl && i >= 1 && i <= s;
+    float left = recv_left, rmin = recv_min;
+    if (active) {
+      if (lane == 0) {  // arr[i][0] = arr[i-1][0] + w*del, :28-32
+        diag = col0;
+        col0 = __fadd_rn(col0, delw);
+        left = col0;
+        rmin = FLT_MAX;
+      }
+      const float next_diag = left;
+      const int tok = s_sent[i - 1];
+      float d = left;
+      for (int r = 0; r < c; r++) {
+        const int j = jbase + r;  // 0-based column
+        if (j >= p) break;
+        const float up = s_up[r * 32 + lane];
+        const float pen = s_pen[j];
+        const float a = __fadd_rn(up, delw);
+        const float bb = __fadd_rn(__fadd_rn(left, insw), pen);
+        const float diff = (tok != s_pat[j]) ? __fadd_rn(repw, pen) : 0.f;
+        const float cc = __fadd_rn(diag, diff);
+        d = fminf(fminf(a, bb), cc);
+        s_up[r * 32 + lane] = d;
+        diag = up;
+        left = d;
+        rmin = fminf(rmin, d);
+      }
+      if (lane == nl - 1) {
+        K = fmaxf(K, rmin);
+        if (i == s) C = d;
+      }
+      diag = next_diag;  // arr[i][lane*c] is the diagonal of the next row
+    }
+    recv_left = __shfl_up_sync(FULL, left, 1);
+    recv_min = __shfl_up_sync(FULL, rmin, 1);
+  }
+  C_out = __shfl_sync(FULL, C, nl - 1);
+  K_out = __shfl_sync(FULL, K, nl - 1);
+  __syncwarp();
+}
+
+// One warp per surviving (query, sentence): Costs (include/fuzzy/costs.hh:54-57), idf weight
+// (src/fuzzy_match.cc:591) and the full edit distance without upper bound; writes the record at the
+// candidate's slot inside its query group.
+__global__ void __launch_bounds__(256) fm_score_kernel(IndexDev ix, BatchDev b, Params pr, int stride) {
+  extern __shared__ int smem[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  int32_t* s_sent = smem + wib * 4 * stride;
+  int32_t* s_pat = s_sent + stride;
+  float* s_pen = reinterpret_cast<float*>(s_pat + stride);
+  float* s_up = s_pen + stride;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long n = min((long long)b.ctr->n_surv, (long long)b.surv_cap);
+  if (b.ctr->overflow) return;
+  for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += n_warps) {
+    const SurvRec sr = b.surv[w];
+    const int slen = b.surv_len[w];
+    const QMeta qm = b.qmeta[sr.q];
+    const int p = qm.x;
+    const float norm = normalizer(p, slen, pr);
+    const float wdiff = __fdiv_rn(100.f, norm);
+    const float idf_weight = __fdiv_rn(__fmul_rn(wdiff, pr.idf_penalty), pr.idf_penalty != 0.f ? ix.idf_max : 0.01f);
+    for (int k = lane; k < slen; k += 32) s_sent[k] = ix.tok[sr.start + k];
+    for (int k = lane; k < p; k += 32) {
+      const int t = b.pat[qm.z + k];
+      s_pat[k] = t;
+      s_pen[k] = idf_weight != 0.f ? __fmul_rn(ix.idf[t], idf_weight) : 0.f;
+    }
+    __syncwarp();
+    float C, K;
+    warp_edit_distance(s_sent, slen, s_pat, p, s_pen, s_up, __fmul_rn(pr.del, wdiff), __fmul_rn(pr.ins, wdiff),
+                       __fmul_rn(pr.rep, wdiff), C, K);
+    if (lane == 0) {
+      fm_record r;
+      r.s_id = (uint32_t)ix.sid_at[sr.start >> 2] + ix.sid_base;
+      r.longest_match = (int32_t)b.hlm[sr.hslot];
+      r.length = slen;
+      r.cost = C;
+      r.rowmin_max = K;
+      r.reserved[0] = sr.start;
+      r.reserved[1] = 0;
+      r.reserved[2] = 0;
+      b.rec[b.q_base[sr.q] + sr.j] = r;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- replay
+
+__device__ __forceinline__ unsigned long long order_key(const fm_record& r) {  // lm desc, s_id asc
+  return ((unsigned long long)(unsigned)(0x7fffffff - r.longest_match) << 32) | r.s_id;
+}
+__device__ __forceinline__ unsigned long long result_key(const fm_record& r) {  // score desc, s_id asc
+  const unsigned u = __float_as_uint(r.rowmin_max);  // slot reused for the score
+  const unsigned ord = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending float order
+  return ((unsigned long long)(~ord) << 32) | r.s_id;
+}
+template <class KeyFn>
+__device__ void sort_records(fm_record* a, int n, KeyFn key) {
+  if (n <= 24) {  // insertion sort
+    for (int i = 1; i < n; i++) {
+      const fm_record x = a[i];
+      const unsigned long long kx = key(x);
+      int j = i - 1;
+      while (j >= 0 && key(a[j]) > kx) { a[j + 1] = a[j]; j--; }
+      a[j + 1] = x;
+    }
+    return;
+  }
+  // heap sort (ascending): build max-heap, then pop
+  auto sift = [&](int root, int end) {
+    const fm_record x = a[root];
+    const unsigned long long kx = key(x);
+    int i = root;
+    for (;;) {
+      int ch = 2 * i + 1;
+      if (ch >= end) break;
+      if (ch + 1 < end && key(a[ch + 1]) > key(a[ch])) ch++;
+      if (!(key(a[ch]) > kx)) break;
+      a[i] = a[ch];
+      i = ch;
+    }
+    a[i] = x;
+  };
+  for (int i = n / 2 - 1; i >= 0; i--) sift(i, n);
+  for (int end = n - 1; end > 0; end--) {
+    const fm_record t = a[0]; a[0] = a[end]; a[end] = t;
+    sift(0, end);
+  }
+}
+
+// std::priority_queue<float> lowest_costs (src/fuzzy_match.cc:567-568)
+__device__ __forceinline__ void heap_push(float* h, int& n, float v) {
+  int i = n++;
+  while (i > 0 && h[(i - 1) >> 1] < v) { h[i] = h[(i - 1) >> 1]; i = (i - 1) >> 1; }
+  h[i] = v;
+}
+__device__ __forceinline__ void heap_pop(float* h, int& n) {
+  const float v = h[--n];
+  int i = 0;
+  for (;;) {
+    int c = 2 * i + 1;
+    if (c >= n) break;
+    if (c + 1 < n && h[c + 1] > h[c]) c++;
+    if (!(h[c] > v)) break;
+    h[i] = h[c];
+    i = c;
+  }
+  if (n > 0) h[i] = v;
+}
+
+__device__ __forceinline__ fm_match to_match(const fm_record& r, float penalty) {
+  fm_match m;
+  m.s_id = r.s_id; m.score = r.rowmin_max; m.penalty = penalty; m.max_subseq = r.longest_match;
+  m.length = r.length; m.cost = r.cost;
+  return m;
+}
+
+// One thread per query: the candidate loop of src/fuzzy_match.cc:567-611 replayed over the scored
+// records in the reference's order (ngram_matches.cc:20-29). A candidate is dropped where the
+// reference's bounded edit distance would have exited early or exceeded the bound:
+// max(K, C) > bound. Accepted matches are then ordered like the result heap (:25-33, :670-679).
+__global__ void __launch_bounds__(128) fm_replay_kernel(fm_record* rec, const int32_t* __restrict__ q_cnt,
+                                                        const int32_t* __restrict__ q_base, float* heapbuf, int32_t* acc_cnt,
+                                                        const int32_t* __restrict__ q_off, int n_q, Params pr, long long cap,
+                                                        fm_match* out, int32_t* out_count, Counters* ctr) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_q) return;
+  if (ctr->overflow) return;
+  const int n = q_cnt[q];
+  const int p = q_off[q + 1] - q_off[q];
+  int nacc = 0;
+  fm_record* seg = rec + q_base[q];
+  if (n > 0) {
+    sort_records(seg, n, order_key);
+    float* heap = heapbuf + q_base[q] + q;
+    int hn = 0;
+    heap_push(heap, hn, FLT_MAX);
+    for (int c = 0; c < n; c++) {
+      fm_record r = seg[c];
+      const float bound = heap[0];
+      if (r.rowmin_max > bound || r.cost > bound) continue;
+      if (pr.no_perfect && r.cost == 0.f && r.length == p) continue;
+      const float score = score_of(r.cost);
+      heap_push(heap, hn, r.cost);
+      if (score < pr.fuzzy || (pr.buffer > 0 && hn > pr.buffer)) heap_pop(heap, hn);
+      if (score >= pr.fuzzy) {
+        r.rowmin_max = score;  // slot reused: score
+        r.reserved[1] = 0;     // contrastive accumulator
+        seg[nacc++] = r;
+      }
+    }
+    sort_records(seg, nacc, result_key);
+  }
+  if (pr.contrast > 0.f) {
+    acc_cnt[q] = nacc;
+    return;
+  }
+  const int want = pr.n_matches == 0 ? nacc : min(nacc, pr.n_matches);
+  out_count[q] = want;
+  for (int k = 0; k < want && k < cap; k++) out[(long long)q * cap + k] = to_match(seg[k], 0.f);
+  if (want) atomicAdd(&ctr->n_matches, (unsigned)want);
+}
+
+// One warp per query: contrastive rerank of src/fuzzy_match.cc:613-669. Penalties against the newly
+// selected match are edit distances between TM sentences (plain variant, unit costs), accumulated in
+// selection order (running float sum for MEAN, running max for MAX).
+__global__ void __launch_bounds__(256) fm_contrast_kernel(IndexDev ix, fm_record* rec, const int32_t* __restrict__ q_base,
+                                                          const int32_t* __restrict__ acc_cnt, int n_q, Params pr,
+                                                          long long cap, fm_match* out, int32_t* out_count, Counters* ctr,
+                                                          int stride) {
+  extern __shared__ int smem[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  int32_t* s_sent = smem + wib * 4 * stride;
+  int32_t* s_pat = s_sent + stride;
+  float* s_pen = reinterpret_cast<float*>(s_pat + stride);
+  float* s_up = s_pen + stride;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  if (ctr->overflow) return;
+  Params unit = pr;
+  unit.ins = unit.del = unit.rep = 1.f;
+  for (int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < n_q; q += n_warps) {
+    const int n = acc_cnt[q];
+    fm_record* seg = rec + q_base[q];
+    int n_out = 0, remaining = n, n_sel = 0;
+    int last = -1;
+    while (remaining > 0 && (pr.n_matches == 0 || n_out < pr.n_matches)) {
+      if (last >= 0) {
+        const fm_record lr = seg[last];
+        for (int k = lane; k < lr.length; k += 32) s_pat[k] = ix.tok[lr.reserved[0] + k];
+        for (int k = lane; k < lr.length; k += 32) s_pen[k] = 0.f;
+        __syncwarp();
+        for (int i = 0; i < n; i++) {
+          const fm_record cr = seg[i];
+          if (cr.reserved[2]) continue;  // already selected
+          for (int k = lane; k < cr.length; k += 32) s_sent[k] = ix.tok[cr.reserved[0] + k];
+          __syncwarp();
+          const float wdiff = __fdiv_rn(100.f, normalizer(cr.length, lr.length, unit));
+          float C, K;
+          warp_edit_distance(s_sent, cr.length, s_pat, lr.length, s_pen, s_up, wdiff, wdiff, wdiff, C, K);
+          if (lane == 0) {
+            const float pen = score_of(C);
+            float acc = __int_as_float(cr.reserved[1]);
+            if (pr.reduce == 1) acc = (n_sel == 1 || pen > acc) ? pen : acc;
+            else acc = __fadd_rn(acc, pen);
+            seg[i].reserved[1] = __float_as_int(acc);
+          }
+        }
+        __syncwarp();
+      }
+      int best = -1;
+      if (lane == 0) {  // std::max_element: first maximum of score - factor*penalty in list order
+        float best_key = 0.f;
+        for (int i = 0; i < n; i++) {
+          const fm_record cr = seg[i];
+          if (cr.reserved[2]) continue;
+          const float acc = __int_as_float(cr.reserved[1]);
+          const float pen = n_sel == 0 ? 0.f : (pr.reduce == 1 ? acc : __fdiv_rn(acc, (float)n_sel));
+          const float key = __fsub_rn(cr.rowmin_max, __fmul_rn(pr.contrast, pen));
+          if (best < 0 || best_key < key) { best = i; best_key = key; }
+        }
+        const fm_record br = seg[best];
+        const float acc = __int_as_float(br.reserved[1]);
+        const float pen = n_sel == 0 ? 0.f : (pr.reduce == 1 ? acc : __fdiv_rn(acc, (float)n_sel));
+        if (n_out < cap) out[(long long)q * cap + n_out] = to_match(br, pen);
+        seg[best].reserved[2] = 1;
+      }
+      best = __shfl_sync(FULL, best, 0);
+      last = best;
+      n_out++; n_sel++; remaining--;
+      __syncwarp();
+    }
+    if (lane == 0) {
+      out_count[q] = n_out;
+      if (n_out) atomicAdd(&ctr->n_matches, (unsigned)n_out);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- cross-shard merge helpers
+
+struct ShardPtrs {
+  const int32_t* off[16];
+  const fm_record* rec[16];
+};
+__global__ void fm_merge_count_kernel(ShardPtrs sp, int n_shards, int32_t* m_cnt, int n_q) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q > n_q) return;
+  int c = 0;
+  if (q < n_q)
+    for (int k = 0; k < n_shards; k++) c += sp.off[k][q + 1] - sp.off[k][q];
+  m_cnt[q] = c;
+}
+__global__ void fm_merge_copy_kernel(ShardPtrs sp, int n_shards, const int32_t* __restrict__ m_base, fm_record* mrec,
+                                     int n_q) {
+  const int lane = threadIdx.x & 31;
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= n_q) return;
+  int dst = m_base[q];
+  for (int k = 0; k < n_shards; k++) {
+    const int b0 = sp.off[k][q], b1 = sp.off[k][q + 1];
+    for (int i = b0 + lane; i < b1; i += 32) mrec[dst + (i - b0)] = sp.rec[k][i];
+    dst += b1 - b0;
+  }
+}
+
+// ---------------------------------------------------------------- launchers
+
+static int dp_stride(const IndexDev& ix) { return ((ix.max_tokens + 31) / 32) * 32 + 32; }
+
+void launch_prepare(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st) {
+  const int warps_per_block = 8;
+  const int grid = (b.n_q + warps_per_block - 1) / warps_per_block;
+  fm_prepare_kernel<<<grid, 256, 0, st>>>(ix, b, p);
+}
+void launch_search(const IndexDev& ix, const BatchDev& b, const Params&, cudaStream_t st) {
+  const int grid = (b.n_tok + 255) / 256;
+  if (grid > 0) fm_search_kernel<<<grid, 256, 0, st>>>(ix, b);
+}
+void launch_gather(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st) {
+  fm_gather_kernel<<<sm_count * 8, 256, 0, st>>>(ix, b, p);
+}
+void launch_scan(const int32_t* in, int32_t* out, int32_t n, cudaStream_t st) {
+  fm_scan_kernel<<<1, 1024, 0, st>>>(in, out, n);
+}
+void launch_score(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st) {
+  const int stride = dp_stride(ix);
+  const size_t smem = (size_t)8 * 4 * stride * sizeof(int);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(fm_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
+  }
+  fm_score_kernel<<<sm_count * 4, 256, smem, st>>>(ix, b, p, stride);
+}
+void launch_replay(const IndexDev&, const fm_record* rec, const int32_t* q_cnt, const int32_t* q_base, float* heapbuf,
+                   int32_t* acc_cnt, const int32_t* q_off, int32_t n_q, const Params& p, int64_t cap, fm_match* out,
+                   int32_t* out_count, Counters* ctr, cudaStream_t st) {
+  const int grid = (n_q + 127) / 128;
+  fm_replay_kernel<<<grid, 128, 0, st>>>(const_cast<fm_record*>(rec), q_cnt, q_base, heapbuf, acc_cnt, q_off, n_q, p,
+                                         (long long)cap, out, out_count, ctr);
+}
+void launch_contrast(const IndexDev& ix, fm_record* rec, const int32_t* q_base, const int32_t* acc_cnt, int32_t n_q,
+                     const Params& p, int64_t cap, fm_match* out, int32_t* out_count, Counters* ctr, int sm_count,
+                     cudaStream_t st) {
+  const int stride = dp_stride(ix);
+  const size_t smem = (size_t)8 * 4 * stride * sizeof(int);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(fm_contrast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
+  }
+  int grid = (n_q + 7) / 8;
+  if (grid > sm_count * 4) grid = sm_count * 4;
+  fm_contrast_kernel<<<grid, 256, smem, st>>>(ix, rec, q_base, acc_cnt, n_q, p, (long long)cap, out, out_count, ctr, stride);
+}
+
+void launch_merge_count(int n_shards, const int32_t* const* off, int32_t* m_cnt, int32_t n_q, cudaStream_t st) {
+  ShardPtrs sp{};
+  for (int k = 0; k < n_shards; k++) sp.off[k] = off[k];
+  fm_merge_count_kernel<<<(n_q + 256) / 256, 256, 0, st>>>(sp, n_shards, m_cnt, n_q);
+}
+void launch_merge_copy(int n_shards, const int32_t* const* off, const fm_record* const* rec, const int32_t* m_base,
+                       fm_record* mrec, int32_t n_q, cudaStream_t st) {
+  ShardPtrs sp{};
+  for (int k = 0; k < n_shards; k++) { sp.off[k] = off[k]; sp.rec[k] = rec[k]; }
+  fm_merge_copy_kernel<<<(n_q + 7) / 8, 256, 0, st>>>(sp, n_shards, m_base, mrec, n_q);
+}
+
+}  // namespace fm

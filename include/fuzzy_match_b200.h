@@ -1,0 +1,136 @@
+/*
+ * fuzzy_match_b200.h -- C ABI of the B200-native fuzzy-match hot path.
+ *
+ * Drop-in boundary: the reference has no FFI layer; its hot path is the public method
+ * fuzzy::FuzzyMatch::match (reference include/fuzzy/fuzzy_match.hh:59-82, src/fuzzy_match.cc:435-681)
+ * over an index built by add_tm/sort (fuzzy_match.hh:52-57, src/suffix_array_index.cc:10-30,
+ * src/suffix_array.cc:9-102). This header is what a binding for that path links against:
+ *   fm_index_create      <- FuzzyMatch::add_tm(id, Tokens) x N + FuzzyMatch::sort()
+ *   fm_match_batch       <- FuzzyMatch::match(Tokens, ...) for a batch of patterns (host buffers)
+ *   fm_match_batch_device<- same, device-resident inputs/outputs on a caller stream
+ *   fm_shard_score_device + fm_merge_replay_device <- the same path split at the per-shard / cross-shard boundary for a TM
+ *                           sharded by sentence-id range over several GPUs
+ * Plain pointers and sizes only; status codes, no exceptions; every function is safe to call from
+ * several host threads on one shared index (like the reference's const match()).
+ *
+ * Word ids: int32, >= 2 for vocabulary words (0 = sentence separator, 1 = unknown, as in reference
+ * src/vocab_indexer.cc:10-11). Query ids outside [2, vocab_size) or absent from the TM are "unknown".
+ * Sentence ids (s_id) number the KEPT sentences consecutively: empty sentences and sentences longer
+ * than max_tokens_in_pattern are dropped exactly as SuffixArrayIndex::add_tm does
+ * (src/suffix_array_index.cc:16).
+ */
+#ifndef FUZZY_MATCH_B200_H
+#define FUZZY_MATCH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FM_OK 0
+#define FM_ERR_INVALID 1   /* bad argument (see fm_last_error) */
+#define FM_ERR_CUDA 2      /* CUDA runtime failure */
+#define FM_ERR_NOMEM 3
+#define FM_MAX_TOKENS 1023 /* hard cap on max_tokens_in_pattern (reference default: 300) */
+
+typedef struct fm_index fm_index;
+
+/* Arguments of FuzzyMatch::match after the pattern (fuzzy_match.hh:59-82), same meaning/defaults. */
+typedef struct fm_params {
+  float fuzzy;               /* fuzzy threshold in [0,1] */
+  int32_t number_of_matches; /* N; 0 = all */
+  int32_t no_perfect;        /* skip cost==0 matches of equal length (Sentence overload only) */
+  int32_t min_subseq_length; /* ml */
+  float min_subseq_ratio;    /* mr */
+  float vocab_idf_penalty;
+  float insert_cost, delete_cost, replace_cost; /* EditCosts, include/fuzzy/costs.hh:7-29 */
+  float contrastive_factor;
+  int32_t contrast_reduce;   /* 0 = ContrastReduce::MEAN, 1 = MAX */
+  int32_t contrast_buffer;   /* -1 = number_of_matches */
+} fm_params;
+
+/* One FuzzyMatch::Match (fuzzy_match.hh:32-46) minus the id string and the token pointer, which the
+ * host adapter fills from its own tables; cost is the edit cost the score was derived from. */
+typedef struct fm_match {
+  uint32_t s_id;
+  float score;
+  float penalty;
+  int32_t max_subseq;
+  int32_t length;
+  float cost;
+} fm_match;
+
+/* A scored candidate of one (query, shard): everything the cross-shard replay needs.
+ * rowmin_max = max over DP rows of the row minimum (reproduces the reference's early exit). */
+typedef struct fm_record {
+  uint32_t s_id; /* global sentence id */
+  int32_t longest_match;
+  int32_t length;
+  float cost;
+  float rowmin_max;
+  int32_t reserved[3];
+} fm_record;
+
+/* Per-stage device times of the last completed batch on this index (milliseconds, CUDA events on
+ * the stream the kernels ran on) and the work it did. Filled only when profiling is enabled. */
+typedef struct fm_profile {
+  float ms_prepare, ms_search, ms_gather, ms_scan, ms_score, ms_replay, ms_total;
+  int64_t n_queries, n_query_tokens, n_slices, n_elements, n_survivors, n_matches;
+  int32_t launches; /* kernels launched for the batch */
+  int32_t retries;  /* workspace regrowths */
+} fm_profile;
+
+/* Build the device index for one GPU from a CSR translation memory.
+ *   sfreq_global / n_sent_global: optional IDF statistics of the whole TM when this index is one
+ *   sentence-id shard of it (NULL / 0 = use this TM's own); s_id_base is added to every s_id. */
+int fm_index_create(const int32_t* tokens, const int64_t* sent_off, int64_t n_sent, int32_t vocab_size,
+                    int32_t max_tokens_in_pattern, const uint32_t* sfreq_global, int64_t n_sent_global,
+                    int64_t s_id_base, int device, fm_index** out);
+void fm_index_destroy(fm_index* index);
+int64_t fm_index_num_sentences(const fm_index* index); /* kept sentences */
+int64_t fm_index_num_suffixes(const fm_index* index);
+int32_t fm_index_max_tokens_in_pattern(const fm_index* index); /* FuzzyMatch::max_tokens_in_pattern */
+int64_t fm_index_device_bytes(const fm_index* index);
+/* kept[s_id] = position of that sentence in the CSR given to fm_index_create (for the id table). */
+int fm_index_kept_sources(const fm_index* index, int64_t* kept);
+/* word-in-sentence frequencies of this TM (sfreq[vocab_size]), reference src/vocab_indexer.cc:73-90 */
+int fm_index_sfreq(const fm_index* index, uint32_t* sfreq);
+/* Host view of a kept sentence (Match::s / Match::length); valid for the life of the index. */
+int fm_index_sentence(const fm_index* index, uint32_t local_s_id, const int32_t** tokens, int32_t* length);
+
+/* match() for n_q patterns given as host CSR; out is [n_q * cap], out_count[q] = number of matches
+ * the reference would append (only min(count, cap) are stored). */
+int fm_match_batch(fm_index* index, const int32_t* q_tokens, const int64_t* q_off, int64_t n_q,
+                   const fm_params* params, int64_t cap, fm_match* out, int32_t* out_count);
+
+/* Same with device-resident buffers; q_off is int32 here ([n_q+1], device). Runs asynchronously on
+ * `stream` (a cudaStream_t) unless the workspace has to grow, and leaves results in d_out/d_out_count.
+ * n_query_tokens = q_off[n_q] (known to the caller). */
+int fm_match_batch_device(fm_index* index, const int32_t* d_q_tokens, const int32_t* d_q_off, int64_t n_q,
+                          int64_t n_query_tokens, const fm_params* params, int64_t cap, fm_match* d_out,
+                          int32_t* d_out_count, void* stream);
+
+/* Sharded TM: per-shard half. Scores every surviving candidate of this shard and returns them grouped
+ * by query: d_rec_off[n_q+1] (exclusive offsets) and d_rec[*n_rec] (device pointers owned by the index,
+ * valid until its next call). */
+int fm_shard_score_device(fm_index* index, const int32_t* d_q_tokens, const int32_t* d_q_off, int64_t n_q,
+                          int64_t n_query_tokens, const fm_params* params, const int32_t** d_rec_off,
+                          const fm_record** d_rec, int64_t* n_rec, void* stream);
+/* Sharded TM: cross-shard half. Replays the union of n_shards record sets (each grouped by query,
+ * shards in ascending s_id order: d_rec_off[k] -> [n_q+1], d_rec[k]) exactly like the single-index
+ * candidate loop (bound heap, top-N, contrastive rerank). Device pointers; host arrays of pointers. */
+int fm_merge_replay_device(fm_index* index, int n_shards, const int32_t* const* d_rec_off,
+                           const fm_record* const* d_rec, const int32_t* d_q_off, int64_t n_q,
+                           const fm_params* params, int64_t cap, fm_match* d_out, int32_t* d_out_count,
+                           void* stream);
+
+int fm_set_profiling(fm_index* index, int enabled);
+int fm_get_profile(const fm_index* index, fm_profile* out);
+const char* fm_last_error(void);
+const char* fm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,64 @@
+"""CPU tests of the boundary: the C-ABI library loads without a GPU and exports every symbol that
+include/fuzzy_match_b200.h declares; host-side argument checks fail loudly (no compute calls)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import fuzzy_match_b200 as fmb
+from fuzzy_match_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    capi.build_library()
+    return capi.load_library()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    header = open(os.path.join(ROOT, "include", "fuzzy_match_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(fm_[a-z_0-9]+)\s*\(", header)))
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(capi.EXPORTS) == declared
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(capi.Params) == 12 * 4
+    assert capi.MATCH_DTYPE.itemsize == 24
+    assert capi.RECORD_DTYPE.itemsize == 32
+
+
+def test_version_and_error_strings(lib):
+    assert b"sm_100a" in lib.fm_version()
+    assert isinstance(lib.fm_last_error(), bytes)
+
+
+def test_invalid_arguments_fail_before_touching_cuda(lib):
+    tok = np.array([2, 3], dtype=np.int32)
+    off = np.array([0, 2], dtype=np.int64)
+    h = C.c_void_p()
+    rc = lib.fm_index_create(C.c_void_p(tok.ctypes.data), C.c_void_p(off.ctypes.data), 1, 10, 5000, None, 0, 0, 0, C.byref(h))
+    assert rc == 1 and b"max_tokens_in_pattern" in lib.fm_last_error()
+    rc = lib.fm_index_create(C.c_void_p(tok.ctypes.data), C.c_void_p(off.ctypes.data), 1, 3, 300, None, 0, 0, 0, C.byref(h))
+    assert rc == 1 and b"token id" in lib.fm_last_error()
+
+
+def test_no_cpu_fallback_when_library_missing(monkeypatch):
+    monkeypatch.setattr(capi, "_LIB", None)
+    monkeypatch.setattr(capi, "library_path", lambda: "/nonexistent/libfm_b200.so")
+    with pytest.raises(fmb.FuzzyMatchError):
+        capi.load_library()
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "fuzzy_match_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".hh", ".cc")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no CPU fallback", ""), os.path.join(dirpath, f)

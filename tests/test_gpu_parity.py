@@ -1,0 +1,162 @@
+"""GPU parity tests (run with -m gpu on the B200 box). Everything goes through the C ABI
+(fm_index_create / fm_match_batch / ...) and is compared bit for bit with the CPU oracle and with
+the committed golden vectors produced by the unmodified reference."""
+import numpy as np
+import pytest
+
+import fuzzy_match_b200 as fmb
+from fuzzy_match_b200 import synth
+from oracle import binding as ob
+from tests.util import as_tuples, csr, fix_params, load_golden
+
+pytestmark = pytest.mark.gpu
+CASES = load_golden()
+
+
+def gpu_results(index, q, qo, cap, **params):
+    out, cnt = index.match_batch(q, qo, cap=cap, **params)
+    return [as_tuples(out[i, :min(cnt[i], cap)], True) for i in range(len(cnt))], cnt
+
+
+def assert_same(index, oracle, q, qo, cap=32, **params):
+    got, gcnt = gpu_results(index, q, qo, cap, **params)
+    ro, ocnt = oracle.match_batch(q, qo, cap=cap, **params)
+    want = [as_tuples(r, True) for r in ro]
+    assert (gcnt == ocnt).all(), "match counts differ at queries %s" % np.nonzero(gcnt != ocnt)[0][:10]
+    bad = [i for i in range(len(want)) if got[i] != want[i]]
+    assert not bad, "query %d: gpu %s != oracle %s" % (bad[0], got[bad[0]], want[bad[0]])
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_golden_vectors(case):
+    tok, off = csr(case["tm"])
+    q, qo = csr(case["queries"])
+    index = fmb.Index(tok, off, case["vocab_size"], max_tokens=case["max_tokens"])
+    out, cnt = index.match_batch(q, qo, cap=64, **fix_params(case["params"]))
+    got = [as_tuples(out[i, :cnt[i]]) for i in range(len(cnt))]
+    want = [[tuple(m) for m in r] for r in case["expected"]]
+    assert got == want
+
+
+PARAM_SETS = [
+    dict(fuzzy=0.8, n=1, ml=3, mr=0.3),
+    dict(fuzzy=0.7, n=1, ml=3),
+    dict(fuzzy=0.5, n=5, ml=2),
+    dict(fuzzy=0.3, n=0, ml=2),
+    dict(fuzzy=0.5, n=10, ml=3, idf=1.0, contrast=0.5),
+    dict(fuzzy=0.4, n=4, ml=2, idf=0.7, costs=(1, 0, 1), contrast=0.5, reduce=1, buffer=8),
+    dict(fuzzy=0.4, n=4, ml=2, costs=(0.5, 1.5, 1.2)),
+    dict(fuzzy=0.4, n=3, ml=2, costs=(0.4, 0.3, 1.2), idf=2.0),
+    dict(fuzzy=0.6, n=2, ml=0, costs=(1, 0, 1), no_perfect=True),
+    dict(fuzzy=0.0, n=3, ml=4, mr=0.2, buffer=1),
+]
+
+
+@pytest.fixture(scope="module")
+def medium():
+    tm, off, V = synth.make_tm(20000, vocab=5000, seed=51)
+    q, qo = synth.make_queries(tm, off, 1500, vocab=5000, seed=52)
+    return fmb.Index(tm, off, V), ob.OracleIndex(tm, off, V), q, qo
+
+
+@pytest.mark.parametrize("params", PARAM_SETS, ids=[str(i) for i in range(len(PARAM_SETS))])
+def test_random_tm_vs_oracle(medium, params):
+    index, oracle, q, qo = medium
+    assert_same(index, oracle, q, qo, cap=48, **params)
+
+
+def test_index_metadata(medium):
+    index, oracle, _, _ = medium
+    assert index.num_sentences == oracle.num_sentences
+    assert (index.sfreq() == oracle.sfreq).all()
+    assert (index.kept_sources() == np.arange(index.num_sentences)).all()
+
+
+def test_small_vocab_many_duplicates():
+    """Tiny vocabulary: every query has thousands of candidates, heavy dedup and ties."""
+    tm, off, V = synth.make_tm(3000, vocab=40, len_lo=1, len_hi=30, seed=61)
+    q, qo = synth.make_queries(tm, off, 200, vocab=40, seed=62, len_lo=1, len_hi=30)
+    index, oracle = fmb.Index(tm, off, V), ob.OracleIndex(tm, off, V)
+    for params in (dict(fuzzy=0.5, n=3, ml=2), dict(fuzzy=0.2, n=0, ml=1), dict(fuzzy=0.6, n=2, ml=3, costs=(1, 0, 1))):
+        assert_same(index, oracle, q, qo, cap=3000, **params)
+
+
+def test_long_patterns():
+    """200-300 token sentences: several DP columns per lane, multi-word coverage masks."""
+    tm, off, V = synth.make_tm(1500, vocab=3000, seed=71, n_long=300)
+    src = np.arange(1200, 1500)
+    q, qo = synth.make_queries(tm, off, 120, vocab=3000, seed=72, source_ids=src, frac_random=0.1, len_lo=200, len_hi=300)
+    index, oracle = fmb.Index(tm, off, V), ob.OracleIndex(tm, off, V)
+    for params in (dict(fuzzy=0.7, n=1, ml=3), dict(fuzzy=0.4, n=5, ml=3, idf=1.0), dict(fuzzy=0.5, n=3, ml=2, costs=(1, 0, 1))):
+        assert_same(index, oracle, q, qo, cap=16, **params)
+
+
+def test_max_tokens_cap_and_dropped_sentences():
+    tm, off, V = synth.make_tm(800, vocab=300, len_lo=1, len_hi=40, seed=81)
+    q, qo = synth.make_queries(tm, off, 150, vocab=300, seed=82, len_lo=1, len_hi=40)
+    index, oracle = fmb.Index(tm, off, V, max_tokens=25), ob.OracleIndex(tm, off, V, max_tokens=25)
+    assert index.num_sentences == oracle.num_sentences < 800
+    assert_same(index, oracle, q, qo, cap=8, fuzzy=0.5, n=4, ml=2)
+
+
+def test_workspace_regrowth_and_reuse():
+    """A batch whose worklists overflow the initial workspace must regrow and give the same answer,
+    and a later small batch on the same index must still be right."""
+    tm, off, V = synth.make_tm(60000, vocab=30, len_lo=8, len_hi=12, seed=91)
+    q, qo = synth.make_queries(tm, off, 64, vocab=30, seed=92, len_lo=8, len_hi=12)
+    index, oracle = fmb.Index(tm, off, V), ob.OracleIndex(tm, off, V)
+    index.set_profiling(True)
+    assert_same(index, oracle, q, qo, cap=8, fuzzy=0.45, n=4, ml=2)
+    assert index.profile()["n_elements"] > 0
+    assert_same(index, oracle, q[:qo[3]], qo[:4], cap=8, fuzzy=0.45, n=4, ml=2)
+
+
+def test_python_mirror_of_reference_api():
+    """The reference's own Tokens-API test (test/test.cc:337-375, lcs_cost) against the mirror class."""
+    fm = fmb.FuzzyMatch(max_tokens_in_pattern=300)
+    for s in ("a b c", "a b c d e x x x", "x x a b c d e f x x x x x"):
+        fm.add_tm("", s.split(), sort=False)
+    fm.sort()
+    matches = []
+    assert fm.match("a b c d e f".split(), 0, 10, matches, 3, 0.5, 0, fmb.EditCosts(1, 0, 1))
+    assert [m.s_id for m in matches] == [2, 1, 0]
+    assert abs(matches[0].score - 1.0) < 1e-3 and abs(matches[1].score - 5 / 6) < 1e-3 and abs(matches[2].score - 0.5) < 1e-3
+    # match() appends (src/fuzzy_match.cc:670-679) and returns False on an empty / over-long pattern
+    assert fm.match([], 0.5, 1, []) is False
+    assert fm.match(["a"] * 301, 0.5, 1, []) is False
+
+
+def test_errors_are_loud():
+    with pytest.raises(fmb.FuzzyMatchError):
+        fmb.Index(np.array([2, 1, 3], dtype=np.int32), np.array([0, 3], dtype=np.int64), 10)
+    with pytest.raises(fmb.FuzzyMatchError):
+        fmb.Index(np.array([2, 3], dtype=np.int32), np.array([0, 2], dtype=np.int64), 10, max_tokens=5000)
+
+
+def test_full_size_properties():
+    """Config-2-sized TM (1M sentences): size-independent properties instead of the slow oracle --
+    every unperturbed TM sentence finds itself with score 1.0, results are deterministic across
+    batch splits, and a sample of queries agrees with the oracle run on the same TM."""
+    tm, off, V = synth.make_tm(1000000, seed=1234)
+    index = fmb.Index(tm, off, V)
+    ids = np.arange(0, 1000000, 997)[:1000]
+    qo = np.zeros(len(ids) + 1, dtype=np.int64)
+    np.cumsum(off[ids + 1] - off[ids], out=qo[1:])
+    q = np.concatenate([tm[off[i]:off[i + 1]] for i in ids])
+    out, cnt = index.match_batch(q, qo, cap=1, fuzzy=0.7, n=1, ml=3)
+    assert (cnt == 1).all() and (out["score"][:, 0] == 1.0).all()
+    # the match is an identical sentence with the smallest s_id (ties broken by s_id asc)
+    for k in range(0, 1000, 50):
+        sid = int(out["s_id"][k, 0])
+        assert sid <= ids[k] and np.array_equal(index.sentence(sid), tm[off[ids[k]]:off[ids[k] + 1]])
+    q2, qo2 = synth.make_queries(tm, off, 20000, seed=5678)
+    a, ca = index.match_batch(q2, qo2, cap=1, fuzzy=0.7, n=1, ml=3)
+    half = 10000
+    b1, c1 = index.match_batch(q2[:qo2[half]], qo2[:half + 1], cap=1, fuzzy=0.7, n=1, ml=3)
+    b2, c2 = index.match_batch(q2[qo2[half]:], qo2[half:] - qo2[half], cap=1, fuzzy=0.7, n=1, ml=3)
+    assert (np.concatenate([c1, c2]) == ca).all()
+    assert np.concatenate([b1, b2]).tobytes() == a.tobytes()
+    oracle = ob.OracleIndex(tm, off, V)
+    ro, co = oracle.match_batch(q2[:qo2[2000]], qo2[:2001], cap=1, nthreads=8, fuzzy=0.7, n=1, ml=3)
+    assert (co == ca[:2000]).all()
+    assert [as_tuples(r, True) for r in ro] == [as_tuples(a[i, :ca[i]], True) for i in range(2000)]
