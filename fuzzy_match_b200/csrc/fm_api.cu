@@ -150,12 +150,14 @@ static int launch_shard(Index* ix, Workspace* w, const int32_t* d_q_tok, const i
   FM_CUDA(cudaMemsetAsync(w->ctr, 0, sizeof(Counters), st));
   FM_CUDA(cudaMemsetAsync(w->hkey, 0xff, (size_t)w->hsize * sizeof(unsigned long long), st));
   FM_CUDA(cudaMemsetAsync(w->hlm, 0, (size_t)w->hsize * sizeof(unsigned int), st));
+  if (getenv("FM_DEBUG_SYNC")) cudaStreamSynchronize(st);
   if (ix->profiling) cudaEventRecord(w->ev[0], st);
   launch_prepare(ix->dev, b, pr, st);
   if (ix->profiling) cudaEventRecord(w->ev[1], st);
   launch_search(ix->dev, b, pr, st);
   if (ix->profiling) cudaEventRecord(w->ev[2], st);
   launch_gather(ix->dev, b, pr, ix->sm_count, st);
+  if (getenv("FM_DEBUG_SYNC2")) cudaStreamSynchronize(st);
   if (ix->profiling) cudaEventRecord(w->ev[3], st);
   launch_scan(w->q_cnt, w->q_base, (int32_t)n_q, st);
   if (ix->profiling) cudaEventRecord(w->ev[4], st);
@@ -437,3 +439,30 @@ int fm_get_profile(const fm_index* index, fm_profile* out) {
 }
 
 }  // extern "C"
+
+// Debug hook (not part of the public header): copies the range slices of the last batch run on
+// the first workspace. rec = int4 (query, sa_begin, match_len, size) per slice.
+extern "C" int64_t fm_debug_last_slices(fm_index* index, int32_t* rec, int64_t* start, int64_t cap) {
+  Index* ix = reinterpret_cast<Index*>(index);
+  if (!ix || ix->pool.empty()) return -1;
+  Workspace* w = ix->pool[0];
+  cudaSetDevice(ix->device);
+  cudaDeviceSynchronize();
+  const int64_t n = std::min<int64_t>(cap, (int64_t)(w->h_ctr->slice_elem >> kElemBits));
+  cudaMemcpy(rec, w->sl_rec, n * sizeof(int4), cudaMemcpyDeviceToHost);
+  cudaMemcpy(start, w->sl_start, n * sizeof(long long), cudaMemcpyDeviceToHost);
+  return n;
+}
+extern "C" int64_t fm_debug_last_survivors(fm_index* index, int32_t* surv, uint32_t* lm, int64_t cap) {
+  Index* ix = reinterpret_cast<Index*>(index);
+  if (!ix || ix->pool.empty()) return -1;
+  Workspace* w = ix->pool[0];
+  cudaSetDevice(ix->device);
+  cudaDeviceSynchronize();
+  const int64_t n = std::min<int64_t>(cap, (int64_t)w->h_ctr->n_surv);
+  cudaMemcpy(surv, w->surv, n * sizeof(SurvRec), cudaMemcpyDeviceToHost);
+  std::vector<uint32_t> hl(w->hsize);
+  cudaMemcpy(hl.data(), w->hlm, (size_t)w->hsize * 4, cudaMemcpyDeviceToHost);
+  for (int64_t i = 0; i < n; i++) lm[i] = hl[surv[4 * i + 2]];
+  return n;
+}

@@ -306,7 +306,8 @@ __device__ __forceinline__ void add_survivor(const BatchDev& b, int q, int start
 // Persistent kernel over the flattened elements of all slices: register_suffix_range_match's walk
 // (src/ngram_matches.cc:62-84) fused with the candidate filter of src/fuzzy_match.cc:576-581.
 // Each warp takes spans of kSpan consecutive elements; element -> slice by one binary search per
-// span plus a 5-step shuffle search per 32 elements (every slice holds >= 1 element).
+// span plus a 6-step shuffle search per 32 elements (every slice holds >= 1 element, so the 32
+// elements of a group touch at most the 32 slices after the previous group's last slice).
 static const int kSpan = 128;
 __global__ void __launch_bounds__(256) fm_gather_kernel(IndexDev ix, BatchDev b, Params pr) {
   const int lane = threadIdx.x & 31;
@@ -323,23 +324,31 @@ __global__ void __launch_bounds__(256) fm_gather_kernel(IndexDev ix, BatchDev b,
       const long long mid = (a + e) >> 1;
       if (__ldg(b.sl_start + mid) <= span) a = mid; else e = mid;
     }
-    long long k0 = a;
+    long long k0 = a;                         // a slice at or one before the slice of the group's first element
+    long long s0 = __ldg(b.sl_start + a);     // its first element
     for (int u = 0; u < kSpan; u += 32) {
       const long long el = span + u + lane;
       if (span + u >= total) break;
-      const long long ks = k0 + lane;
-      const long long st = ks < n_slices ? __ldg(b.sl_start + ks) : 0x7fffffffffffffffll;
-      int j = 0;
+      // window = the 32 slices after k0; slice(el) = k0 + #{window starts <= el}
+      const long long ks = k0 + 1 + lane;
+      const long long wst = ks < n_slices ? __ldg(b.sl_start + ks) : 0x7fffffffffffffffll;
+      int c = 0;
 #pragma unroll
       for (int step = 16; step > 0; step >>= 1) {
-        const long long v = __shfl_sync(FULL, st, j + step);
-        if (v <= el) j += step;
+        const long long v = __shfl_sync(FULL, wst, c + step - 1);
+        if (v <= el) c += step;
       }
-      const long long my_start = __shfl_sync(FULL, st, j);
-      k0 = __shfl_sync(FULL, k0 + j, 31);
-      if (k0 >= n_slices) k0 = n_slices - 1;
+      {
+        const long long v = __shfl_sync(FULL, wst, c);  // c <= 31
+        if (v <= el) c += 1;
+      }
+      const long long prev_start = __shfl_sync(FULL, wst, c > 0 ? c - 1 : 0);
+      const long long my_start = c > 0 ? prev_start : s0;
+      const long long my_slice = k0 + c;
+      k0 = __shfl_sync(FULL, my_slice, 31);
+      s0 = __shfl_sync(FULL, my_start, 31);
       if (el >= total) continue;
-      const int4 sr = __ldg(b.sl_rec + (ks - lane + j));
+      const int4 sr = __ldg(b.sl_rec + my_slice);
       const int q = sr.x, lm = sr.z;
       const int i = sr.y + (int)(el - my_start);
       const int pos = __ldg(ix.sa_pos + i);
