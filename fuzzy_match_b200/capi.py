@@ -68,7 +68,7 @@ RECORD_DTYPE = np.dtype([("s_id", np.uint32), ("longest_match", np.int32), ("len
 
 EXPORTS = ["fm_index_create", "fm_index_destroy", "fm_index_num_sentences", "fm_index_num_suffixes",
            "fm_index_max_tokens_in_pattern", "fm_index_device_bytes", "fm_index_kept_sources", "fm_index_sfreq",
-           "fm_index_sentence", "fm_match_batch", "fm_match_batch_device", "fm_shard_score_device",
+           "fm_index_sentence", "fm_index_set_idf_stats", "fm_match_batch", "fm_match_batch_device", "fm_shard_score_device",
            "fm_merge_replay_device", "fm_set_profiling", "fm_get_profile", "fm_last_error", "fm_version"]
 
 
@@ -95,6 +95,7 @@ def load_library():
                                     C.c_int64, C.c_int, C.POINTER(C.c_void_p)]
     lib.fm_index_kept_sources.argtypes = [C.c_void_p, C.c_void_p]
     lib.fm_index_sfreq.argtypes = [C.c_void_p, C.c_void_p]
+    lib.fm_index_set_idf_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     lib.fm_index_sentence.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32)]
     lib.fm_match_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Params), C.c_int64,
                                    C.c_void_p, C.c_void_p]
@@ -159,21 +160,30 @@ class Index:
         _check(self.lib, self.lib.fm_index_sfreq(self.h, _ptr(out)))
         return out
 
+    def set_idf_stats(self, sfreq_global, n_sent_global):
+        sf = np.ascontiguousarray(sfreq_global, dtype=np.uint32)
+        assert len(sf) == self.vocab_size
+        _check(self.lib, self.lib.fm_index_set_idf_stats(self.h, _ptr(sf), int(n_sent_global)))
+
     def sentence(self, s_id):
         p, n = C.POINTER(C.c_int32)(), C.c_int32()
         _check(self.lib, self.lib.fm_index_sentence(self.h, int(s_id), C.byref(p), C.byref(n)))
         return np.ctypeslib.as_array(p, shape=(n.value,)).copy()
 
-    def match_batch(self, q_tokens, q_off, cap=None, params=None, **kw):
-        """Host buffers in, host buffers out (fm_match_batch). Returns (matches[n_q, cap], counts[n_q])."""
+    def match_batch(self, q_tokens, q_off, cap=None, params=None, out=None, cnt=None, **kw):
+        """Host buffers in, host buffers out (fm_match_batch). Returns (matches[n_q, cap], counts[n_q]).
+        out / cnt may be preallocated (e.g. views of pinned memory)."""
         p = params if params is not None else Params.make(**kw)
         if cap is None:
             cap = max(1, p.number_of_matches)
         q_tokens = np.ascontiguousarray(q_tokens, dtype=np.int32)
         q_off = np.ascontiguousarray(q_off, dtype=np.int64)
         n_q = len(q_off) - 1
-        out = np.zeros((n_q, cap), dtype=MATCH_DTYPE)
-        cnt = np.zeros(n_q, dtype=np.int32)
+        if out is None:
+            out = np.zeros((n_q, cap), dtype=MATCH_DTYPE)
+        if cnt is None:
+            cnt = np.zeros(n_q, dtype=np.int32)
+        assert out.dtype == MATCH_DTYPE and out.size == n_q * cap and out.flags.c_contiguous and len(cnt) == n_q
         _check(self.lib, self.lib.fm_match_batch(self.h, _ptr(q_tokens), _ptr(q_off), n_q, C.byref(p), cap, _ptr(out),
                                                  _ptr(cnt)))
         return out, cnt

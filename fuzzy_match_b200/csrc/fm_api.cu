@@ -1,5 +1,6 @@
 // fm_api.cu -- the C ABI (include/fuzzy_match_b200.h): workspace management and batch orchestration.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "fm_internal.h"
@@ -284,6 +285,12 @@ int fm_index_sfreq(const fm_index* index, uint32_t* sfreq) {
   if (!ix || !sfreq) { set_error("NULL argument"); return FM_ERR_INVALID; }
   std::copy(ix->sfreq.begin(), ix->sfreq.end(), sfreq);
   return FM_OK;
+}
+int fm_index_set_idf_stats(fm_index* index, const uint32_t* sfreq_global, int64_t n_sent_global) {
+  Index* ix = reinterpret_cast<Index*>(index);
+  if (!ix || !sfreq_global || n_sent_global < 1) { set_error("bad argument"); return FM_ERR_INVALID; }
+  FM_CUDA(cudaSetDevice(ix->device));
+  return set_idf_stats(ix, sfreq_global, n_sent_global);
 }
 int fm_index_sentence(const fm_index* index, uint32_t s, const int32_t** tokens, int32_t* length) {
   const Index* ix = reinterpret_cast<const Index*>(index);

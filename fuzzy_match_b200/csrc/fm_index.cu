@@ -39,6 +39,19 @@ static int upload(const std::vector<T>& h, size_t extra, void** slot, const T** 
   return FM_OK;
 }
 
+// IDF table with host libm exactly as src/fuzzy_match.cc:367-390: logf((float)N / (float)sfreq[w]) per
+// word, idf_max = (float)log((double)N).
+int set_idf_stats(Index* ix, const uint32_t* sf, int64_t n_sent_global) {
+  const unsigned num_sentences = (unsigned)n_sent_global;
+  std::vector<float> idf((size_t)ix->vocab_size, 0.f);
+  for (int32_t w = 2; w < ix->vocab_size; w++)
+    if (sf[w] > 0) idf[w] = std::log((float)num_sentences / (float)sf[w]);
+  FM_CUDA(cudaMemcpy(const_cast<float*>(ix->dev.idf), idf.data(), idf.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (sf != ix->sfreq.data()) std::copy(sf, sf + ix->vocab_size, ix->sfreq.begin());
+  ix->dev.idf_max = (float)std::log((double)num_sentences);
+  return FM_OK;
+}
+
 void free_index(Index* ix) {
   if (!ix) return;
   cudaSetDevice(ix->device);
@@ -158,14 +171,6 @@ int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_in, in
   for (int64_t i = 0; i < n_suf; i++) sa_meta[i] = meta_of_pos[sa[i]];
   std::vector<uint32_t>().swap(meta_of_pos);
 
-  // ---- IDF table, host libm exactly as src/fuzzy_match.cc:367-390
-  const uint32_t* sf = sfreq_global ? sfreq_global : ix->sfreq.data();
-  const unsigned num_sentences = (unsigned)(n_sent_global > 0 ? n_sent_global : n_keep);
-  std::vector<float> idf((size_t)vocab_size, 0.f);
-  for (int32_t w = 2; w < vocab_size; w++)
-    if (sf[w] > 0) idf[w] = std::log((float)num_sentences / (float)sf[w]);
-  if (sfreq_global) std::copy(sfreq_global, sfreq_global + vocab_size, ix->sfreq.begin());
-
   // ---- upload
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) { delete ix; return cuda_fail(e, "cudaSetDevice"); }
@@ -178,7 +183,8 @@ int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_in, in
       (rc = upload(sa_meta, 4, &ix->d_blocks[2], &d.sa_meta, &ix->device_bytes)) ||
       (rc = upload(qva, 0, &ix->d_blocks[3], &d.qva, &ix->device_bytes)) ||
       (rc = upload(sid_at, 0, &ix->d_blocks[4], &d.sid_at, &ix->device_bytes)) ||
-      (rc = upload(idf, 0, &ix->d_blocks[5], &d.idf, &ix->device_bytes))) {
+      (rc = upload(std::vector<float>((size_t)vocab_size, 0.f), 0, &ix->d_blocks[5], &d.idf, &ix->device_bytes)) ||
+      (rc = set_idf_stats(ix, sfreq_global ? sfreq_global : ix->sfreq.data(), n_sent_global > 0 ? n_sent_global : n_keep))) {
     free_index(ix);
     return rc;
   }
@@ -186,7 +192,6 @@ int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_in, in
   d.max_tokens = max_tokens;
   d.n_suf = n_suf;
   d.sid_base = (uint32_t)s_id_base;
-  d.idf_max = (float)std::log((double)num_sentences);
   *out = ix;
   return FM_OK;
 }

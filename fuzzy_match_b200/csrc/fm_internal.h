@@ -173,6 +173,7 @@ int cuda_fail(cudaError_t e, const char* what);
 int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_sent, int32_t vocab_size, int32_t max_tokens,
                 const uint32_t* sfreq_global, int64_t n_sent_global, int64_t s_id_base, int device, Index** out);
 void free_index(Index* ix);
+int set_idf_stats(Index* ix, const uint32_t* sfreq, int64_t n_sent_global);
 
 // fm_kernels.cu -- launchers (all asynchronous on `st`)
 void launch_prepare(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st);

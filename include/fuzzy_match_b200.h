@@ -96,6 +96,8 @@ int64_t fm_index_device_bytes(const fm_index* index);
 int fm_index_kept_sources(const fm_index* index, int64_t* kept);
 /* word-in-sentence frequencies of this TM (sfreq[vocab_size]), reference src/vocab_indexer.cc:73-90 */
 int fm_index_sfreq(const fm_index* index, uint32_t* sfreq);
+/* Replace the IDF statistics (e.g. with the all-reduced sfreq of every shard of a sharded TM). */
+int fm_index_set_idf_stats(fm_index* index, const uint32_t* sfreq_global, int64_t n_sent_global);
 /* Host view of a kept sentence (Match::s / Match::length); valid for the life of the index. */
 int fm_index_sentence(const fm_index* index, uint32_t local_s_id, const int32_t** tokens, int32_t* length);
 

@@ -160,3 +160,67 @@ def test_full_size_properties():
     ro, co = oracle.match_batch(q2[:qo2[2000]], qo2[:2001], cap=1, nthreads=8, fuzzy=0.7, n=1, ml=3)
     assert (co == ca[:2000]).all()
     assert [as_tuples(r, True) for r in ro] == [as_tuples(a[i, :ca[i]], True) for i in range(2000)]
+
+
+def test_sharded_tm_two_shards_one_gpu():
+    """The sharded path (fm_shard_score_device per shard + fm_merge_replay_device over the union)
+    must equal the unsharded oracle bit for bit: two sentence-id shards on one GPU, global IDF."""
+    import torch
+    from fuzzy_match_b200 import capi, sharded
+    tm, off, V = synth.make_tm(6000, vocab=700, len_lo=0, len_hi=30, seed=101)
+    q, qo = synth.make_queries(tm, off, 400, vocab=700, seed=102, len_lo=1, len_hi=30)
+    oracle = ob.OracleIndex(tm, off, V, max_tokens=28)
+    n_sent = len(off) - 1
+    shards, base = [], 0
+    for r in range(2):
+        lo, hi = sharded.shard_range(n_sent, r, 2)
+        ix = fmb.Index(tm[off[lo]:off[hi]], off[lo:hi + 1] - off[lo], V, max_tokens=28, s_id_base=base)
+        base += ix.num_sentences
+        shards.append(ix)
+    sf = sum(ix.sfreq().astype(np.int64) for ix in shards).astype(np.uint32)
+    assert (sf == oracle.sfreq).all() and base == oracle.num_sentences
+    for ix in shards:
+        ix.set_idf_stats(sf, base)
+    dev = torch.device("cuda", 0)
+    d_tok = torch.as_tensor(q, device=dev)
+    d_off = torch.as_tensor(qo.astype(np.int32), device=dev)
+    n_q, n_tok, cap = len(qo) - 1, int(qo[-1]), 8
+    st = torch.cuda.current_stream(dev).cuda_stream
+    for params in (dict(fuzzy=0.5, n=4, ml=2), dict(fuzzy=0.4, n=3, ml=3, idf=1.0, costs=(1, 0, 1)), dict(fuzzy=0.6, n=1, ml=3, mr=0.3)):
+        p = capi.Params.make(**params)
+        offs, recs = [], []
+        for ix in shards:
+            o, r, n = ix.shard_score_device(d_tok.data_ptr(), d_off.data_ptr(), n_q, n_tok, stream=st, params=p)
+            offs.append(o)
+            recs.append(r)
+        d_out = torch.zeros(n_q * cap * 24, dtype=torch.uint8, device=dev)
+        d_cnt = torch.zeros(n_q, dtype=torch.int32, device=dev)
+        shards[0].merge_replay_device(offs, recs, d_off.data_ptr(), n_q, d_out.data_ptr(), d_cnt.data_ptr(), cap, stream=st, params=p)
+        torch.cuda.synchronize()
+        out = d_out.cpu().numpy().view(capi.MATCH_DTYPE).reshape(n_q, cap)
+        cnt = d_cnt.cpu().numpy()
+        ro, oc = oracle.match_batch(q, qo, cap=cap, **params)
+        assert (cnt == oc).all()
+        assert [as_tuples(out[i, :cnt[i]], True) for i in range(n_q)] == [as_tuples(r, True) for r in ro]
+
+
+def test_device_resident_api_matches_host_api(medium):
+    import torch
+    from fuzzy_match_b200 import capi
+    index, _, q, qo = medium
+    dev = torch.device("cuda", 0)
+    d_tok = torch.as_tensor(q, device=dev)
+    d_off = torch.as_tensor(qo.astype(np.int32), device=dev)
+    n_q, cap = len(qo) - 1, 4
+    d_out = torch.zeros(n_q * cap * 24, dtype=torch.uint8, device=dev)
+    d_cnt = torch.zeros(n_q, dtype=torch.int32, device=dev)
+    stream = torch.cuda.Stream(dev)
+    with torch.cuda.stream(stream):
+        index.match_batch_device(d_tok.data_ptr(), d_off.data_ptr(), n_q, int(qo[-1]), d_out.data_ptr(), d_cnt.data_ptr(), cap,
+                                 stream=stream.cuda_stream, fuzzy=0.5, n=4, ml=2)
+    torch.cuda.synchronize()
+    out, cnt = index.match_batch(q, qo, cap=cap, fuzzy=0.5, n=4, ml=2)
+    assert (d_cnt.cpu().numpy() == cnt).all()
+    got = d_out.cpu().numpy().view(capi.MATCH_DTYPE).reshape(n_q, cap)
+    for i in range(n_q):
+        assert got[i, :cnt[i]].tobytes() == out[i, :cnt[i]].tobytes()

@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""Summarises ncu output for profiles/: a launch list (csv from --metrics gpu__time_duration.sum) into
+per-kernel averages and shares, and a .ncu-rep (--set full) into the metrics the roofline quotes.
+Usage: python tools/ncu_summary.py launches <launches.csv> | full <prof.ncu-rep>"""
+import csv
+import subprocess
+import sys
+from collections import defaultdict
+
+FULL = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum",
+        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+
+
+def launches(path):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0].isdigit()]
+    d = defaultdict(list)
+    for r in rows:
+        d[r[4].split("(")[0]].append(float(r[-1]) / 1e3)
+    tot = sum(sum(v) for v in d.values())
+    print("# per-kernel device time from `ncu --metrics gpu__time_duration.sum --clock-control none` (cold-cache, serialised)")
+    print("%-44s %5s %12s %8s" % ("kernel", "n", "avg_us", "share"))
+    for k, v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
+        print("%-44s %5d %12.1f %8.3f" % (k[:44], len(v), sum(v) / len(v), sum(v) / tot))
+
+
+def full(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    print("# from `ncu --set full --clock-control none --import-source on` (%s)" % path)
+    for r in rows[2:]:
+        print("kernel: %s" % r[idx["Kernel Name"]].split("(")[0])
+        for m in FULL:
+            if m in idx:
+                print("  %-72s %16s %s" % (m, r[idx[m]], units[idx[m]]))
+        rd, wr = float(r[idx["dram__bytes_read.sum"]]), float(r[idx["dram__bytes_write.sum"]])
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}
+        print("  %-72s %16.1f MB" % ("traffic = dram read + write",
+                                      (rd * scale[units[idx["dram__bytes_read.sum"]]] + wr * scale[units[idx["dram__bytes_write.sum"]]]) / 1e6))
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
