@@ -50,14 +50,14 @@ static int ensure_queries(Workspace* w, int64_t n_q, int64_t n_tok, bool staging
   if (n_q > w->cap_q) {
     const int64_t c = round_up(n_q + n_q / 4 + 1024, 1024);
     if ((rc = dev_realloc(&w->qmeta, c)) || (rc = dev_realloc(&w->q_cnt, c + 1)) || (rc = dev_realloc(&w->q_base, c + 1)) ||
-        (rc = dev_realloc(&w->acc_cnt, c)) || (rc = dev_realloc(&w->d_q_off, c + 1)) || (rc = dev_realloc(&w->d_out_count, c + 1)))
+        (rc = dev_realloc(&w->acc_cnt, c)) || (rc = dev_realloc(&w->qmask, 3 * c)) || (rc = dev_realloc(&w->d_q_off, c + 1)) || (rc = dev_realloc(&w->d_out_count, c + 1)))
       return rc;
     w->cap_q = c;
     w->cap_surv = 0;  // heapbuf depends on cap_q
   }
   if (n_tok > w->cap_tok) {
     const int64_t c = round_up(n_tok + n_tok / 4 + 4096, 4096);
-    if ((rc = dev_realloc(&w->pat, c)) || (rc = dev_realloc(&w->chain_q, c)) || (rc = dev_realloc(&w->tbl, 4 * c)) ||
+    if ((rc = dev_realloc(&w->pat, c)) || (rc = dev_realloc(&w->chain_q, c)) || (rc = dev_realloc(&w->tbl, 4 * c)) || (rc = dev_realloc(&w->cmin, 4 * c)) ||
         (rc = dev_realloc(&w->d_q_tok, c)))
       return rc;
     w->cap_tok = c;
@@ -101,7 +101,7 @@ static int ensure_out(Workspace* w, int64_t n_q, int64_t cap) {
 }
 
 static void free_workspace(Workspace* w) {
-  cudaFree(w->d_q_tok); cudaFree(w->d_q_off); cudaFree(w->pat); cudaFree(w->chain_q); cudaFree(w->qmeta); cudaFree(w->tbl);
+  cudaFree(w->d_q_tok); cudaFree(w->d_q_off); cudaFree(w->pat); cudaFree(w->chain_q); cudaFree(w->qmeta); cudaFree(w->tbl); cudaFree(w->cmin); cudaFree(w->qmask);
   cudaFree(w->sl_start); cudaFree(w->sl_rec); cudaFree(w->hkey); cudaFree(w->hlm); cudaFree(w->surv); cudaFree(w->surv_len);
   cudaFree(w->q_cnt); cudaFree(w->q_base); cudaFree(w->acc_cnt); cudaFree(w->rec); cudaFree(w->heapbuf); cudaFree(w->ctr);
   cudaFree(w->d_out); cudaFree(w->d_out_count); cudaFree(w->mrec); cudaFree(w->m_cnt); cudaFree(w->m_base); cudaFree(w->m_acc); cudaFree(w->m_heap);
@@ -133,7 +133,7 @@ static int check_params(const fm_params* p, Params* out) {
 static BatchDev make_batch(Workspace* w, const int32_t* d_q_tok, const int32_t* d_q_off, int64_t n_q, int64_t n_tok) {
   BatchDev b{};
   b.q_tok_in = d_q_tok; b.q_off = d_q_off; b.n_q = (int32_t)n_q; b.n_tok = (int32_t)n_tok;
-  b.pat = w->pat; b.chain_q = w->chain_q; b.qmeta = w->qmeta; b.tbl = w->tbl;
+  b.pat = w->pat; b.chain_q = w->chain_q; b.qmeta = w->qmeta; b.tbl = w->tbl; b.cmin = w->cmin; b.qmask = w->qmask;
   b.sl_start = w->sl_start; b.sl_rec = w->sl_rec; b.slice_cap = w->cap_slices;
   b.hkey = w->hkey; b.hlm = w->hlm; b.hmask = w->hsize - 1;
   b.surv = w->surv; b.surv_len = w->surv_len; b.surv_cap = w->cap_surv;

@@ -167,8 +167,22 @@ int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_in, in
     work();
     for (auto& t : pool) t.join();
   }
-  std::vector<uint32_t> sa_meta((size_t)n_suf);
-  for (int64_t i = 0; i < n_suf; i++) sa_meta[i] = meta_of_pos[sa[i]];
+  // per-suffix walk record: (sentence start, length, signature lo, signature hi)
+  std::vector<int4> sa_walk((size_t)n_suf);
+  {
+    std::vector<unsigned long long> sig_of_sent((size_t)n_keep, 0);
+    for (int64_t k = 0; k < n_keep; k++) {
+      unsigned long long sg = 0;
+      for (int32_t pos = ix->h_sent_start[k]; ix->h_tok[pos] != 0; pos++) sg |= 1ull << sig_bit(ix->h_tok[pos]);
+      sig_of_sent[k] = sg;
+    }
+    for (int64_t i = 0; i < n_suf; i++) {
+      const uint32_t m = meta_of_pos[sa[i]];
+      const int32_t start = sa[i] - (int32_t)(m & 0xffffu);
+      const unsigned long long sg = sig_of_sent[sid_at[start >> 2]];
+      sa_walk[i] = make_int4(start, (int32_t)(m >> 16), (int32_t)(uint32_t)sg, (int32_t)(uint32_t)(sg >> 32));
+    }
+  }
   std::vector<uint32_t>().swap(meta_of_pos);
 
   // ---- upload
@@ -180,7 +194,7 @@ int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_in, in
   IndexDev& d = ix->dev;
   if ((rc = upload(ix->h_tok, 0, &ix->d_blocks[0], &d.tok, &ix->device_bytes)) ||
       (rc = upload(sa, 4, &ix->d_blocks[1], &d.sa_pos, &ix->device_bytes)) ||
-      (rc = upload(sa_meta, 4, &ix->d_blocks[2], &d.sa_meta, &ix->device_bytes)) ||
+      (rc = upload(sa_walk, 4, &ix->d_blocks[2], &d.sa_walk, &ix->device_bytes)) ||
       (rc = upload(qva, 0, &ix->d_blocks[3], &d.qva, &ix->device_bytes)) ||
       (rc = upload(sid_at, 0, &ix->d_blocks[4], &d.sid_at, &ix->device_bytes)) ||
       (rc = upload(std::vector<float>((size_t)vocab_size, 0.f), 0, &ix->d_blocks[5], &d.idf, &ix->device_bytes)) ||

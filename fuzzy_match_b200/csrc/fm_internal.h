@@ -17,15 +17,17 @@ namespace fm {
 //                         (multiple of 4 tokens) and is followed by >= 1 zero (the separator); the zero
 //                         sorts before every word id, so "shorter suffix first" needs no length check.
 // sa_pos   int32[n_suf]   suffix array: absolute offset into tok of each suffix, sorted.
-// sa_meta  uint32[n_suf]  (sentence length << 16) | offset of the suffix inside its sentence, so the
-//                         range walk gets length + sentence start from one 8-byte (pos, meta) pair.
+// sa_walk  int4[n_suf]    what the range walk needs per suffix, one 128-bit load: (sentence start in tok,
+//                         sentence length, 64-bit word signature of the sentence: bit sig_bit(w) set for
+//                         every word w). The signature gives an upper bound on the coverage without
+//                         touching the sentence.
 // qva      int32[V+1]     first-word bucket table (reference _quickVocabAccess).
 // sid_at   int32[n_buf/4] local sentence id, stored at (sentence start / 4); only read for survivors.
 // idf      float[V]       logf(N / sfreq[w]) computed on the host with glibc (0 for unseen words).
 struct IndexDev {
   const int32_t* tok;
   const int32_t* sa_pos;
-  const uint32_t* sa_meta;
+  const int4* sa_walk;
   const int32_t* qva;
   const int32_t* sid_at;
   const float* idf;
@@ -38,8 +40,14 @@ struct IndexDev {
 
 // per-query metadata written by the prepare kernel
 //   x = pattern length p (0 if the query is skipped), y = effective min_subseq_length,
-//   z = offset of the pattern in the token arrays, w = 1 if the query takes part
+//   z = offset of the pattern in the token arrays,
+//   w = bit0: query takes part, bit1: bound tables valid, bits 8-19 / 20-31: smallest / largest
+//       sentence length that passes the length bound
 typedef int4 QMeta;
+static const int kQValid = 1, kQFast = 2;
+
+// word -> signature bit (must be identical on host and device)
+__host__ __device__ inline unsigned sig_bit(int w) { return ((unsigned)w * 0x9E3779B1u) >> 26; }
 
 struct SurvRec {  // one distinct (query, sentence) that passed both rejection bounds
   int32_t q;
@@ -69,6 +77,8 @@ struct BatchDev {
   int32_t* chain_q;  // [n_tok] query of each chain (= pattern position)
   QMeta* qmeta;      // [n_q]
   int2* tbl;         // [4*n_tok] per-query open-addressing tables: (word, distinct_idx | count<<16)
+  uint16_t* cmin;    // [4*n_tok] per query, for each passing sentence length: smallest coverage that passes
+  int4* qmask;       // [3*n_q] per query: signature masks M1..M5 (pattern positions per bit >= 1..5) + weight
   // search output
   long long* sl_start;  // [slice_cap+1] first flattened element of each slice (ascending)
   int4* sl_rec;         // [slice_cap] (q, sa_begin, match_len, size)
@@ -115,6 +125,8 @@ struct Workspace {
   int32_t *pat = nullptr, *chain_q = nullptr;
   QMeta* qmeta = nullptr;
   int2* tbl = nullptr;
+  uint16_t* cmin = nullptr;
+  int4* qmask = nullptr;
   long long* sl_start = nullptr;
   int4* sl_rec = nullptr;
   unsigned long long* hkey = nullptr;

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
   const int by_ratio = (int)__fmul_rn(pr.mr, (float)p);
   if (by_ratio > ml) ml = by_ratio;
   if (lane == 0) {
-    b.qmeta[q] = make_int4(valid ? p : 0, ml, off, valid ? 1 : 0);
+    b.qmeta[q] = make_int4(valid ? p : 0, ml, off, valid ? kQValid : 0);
     b.q_cnt[q] = 0;
     if (q == 0) b.q_cnt[b.n_q] = 0;
   }
@@ -117,6 +117,64 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
       while (tbl[h].x != -1 && tbl[h].x != w) h = (h + 1) & (ts - 1);
       if (tbl[h].x == -1) tbl[h] = make_int2(w, (distinct++) | (1 << 16));
       else tbl[h].y += 1 << 16;
+    }
+  }
+  // Bound tables. The length bound (ngram_matches.cc:32-39) accepts a window [smin, smax] of sentence
+  // lengths around p; for each of them cmin = the smallest coverage the coverage bound
+  // (ngram_matches.cc:42-59) lets through. Both are evaluated here with the exact float/double
+  // expressions, once per (query, length) instead of once per suffix-array element.
+  int smin = 0x7fffffff, smax = 0, n_ok = 0;
+  for (int base = 1; base <= ix.max_tokens; base += 32) {
+    const int sl = base + lane;
+    const bool ok = sl <= ix.max_tokens && !reject_length(p, sl, pr);
+    const unsigned bal = __ballot_sync(FULL, ok);
+    if (bal) {
+      smin = min(smin, base + __ffs(bal) - 1);
+      smax = max(smax, base + 31 - __clz(bal));
+      n_ok += __popc(bal);
+    }
+  }
+  const bool fast = n_ok > 0 && n_ok == smax - smin + 1 && n_ok <= 4 * p && pr.ins >= 0.f && pr.del >= 0.f && pr.rep >= 0.f;
+  if (fast) {
+    uint16_t* cm = b.cmin + 4ll * off;
+    for (int sl = smin + lane; sl <= smax; sl += 32) {
+      int need = p + 1;
+      if (!reject_cover(p, sl, p, pr)) {  // reject_cover is monotone in the coverage for costs >= 0
+        int lo = 0, hi = p;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (!reject_cover(p, sl, mid, pr)) hi = mid; else lo = mid + 1;
+        }
+        need = lo;
+      }
+      cm[sl - smin] = (uint16_t)need;
+    }
+  }
+  // Signature masks: M_l = bits that >= l pattern positions hash to (unknown words excluded).
+  // coverage <= sum_l popc(sig & M_l) (+ weight * popc(sig & M5) for bits with more than 4 positions).
+  {
+    int c_lo = 0, c_hi = 0;
+    for (int j = 0; j < p; j++) {
+      const int w = b.pat[off + j];
+      if (w < 2) continue;
+      const unsigned bit = sig_bit(w);
+      c_lo += bit == (unsigned)lane;
+      c_hi += bit == (unsigned)(lane + 32);
+    }
+    unsigned m[10];
+#pragma unroll
+    for (int l = 0; l < 5; l++) {
+      m[2 * l] = __ballot_sync(FULL, c_lo > l);
+      m[2 * l + 1] = __ballot_sync(FULL, c_hi > l);
+    }
+    int extra = max(max(c_lo, c_hi) - 4, 0);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) extra = max(extra, __shfl_xor_sync(FULL, extra, d));
+    if (lane == 0) {
+      b.qmask[3 * q + 0] = make_int4(m[0], m[1], m[2], m[3]);
+      b.qmask[3 * q + 1] = make_int4(m[4], m[5], m[6], m[7]);
+      b.qmask[3 * q + 2] = make_int4(m[8], m[9], extra, 0);
+      b.qmeta[q] = make_int4(p, ml, off, kQValid | (fast ? kQFast | (smin << 8) | (smax << 20) : 0));
     }
   }
 }
@@ -173,7 +231,7 @@ __global__ void __launch_bounds__(256) fm_search_kernel(IndexDev ix, BatchDev b)
     q = b.chain_q[c];
     const QMeta m = b.qmeta[q];
     p = m.x; ml = m.y; it = c - m.z; pat = b.pat + m.z;
-    live = m.w != 0;
+    live = (m.w & kQValid) != 0;
   }
   int lo = 0, hi = 0, len = 0;
   if (live) {
@@ -255,14 +313,16 @@ __device__ __forceinline__ void cover_token(const int2* __restrict__ tbl, int tm
   }
 }
 
+// Exact coverage of one sentence, stopping as soon as `need` is reached (the caller only compares
+// the result with `need`; pass need > p to get the exact count).
 template <int MW>
-__device__ __forceinline__ int cover_sentence(const int32_t* __restrict__ sent, int slen, const int2* tbl, int tmask) {
+__device__ __forceinline__ int cover_sentence(const int32_t* __restrict__ sent, int slen, const int2* tbl, int tmask, int need) {
   unsigned seen[MW];
 #pragma unroll
   for (int i = 0; i < MW; i++) seen[i] = 0;
   int cover = 0;
   const int4* s4 = reinterpret_cast<const int4*>(sent);
-  for (int k = 0; k < slen; k += 4) {
+  for (int k = 0; k < slen && cover < need; k += 4) {
     const int4 t = ldg_nc_v4(s4 + (k >> 2));
     cover_token<MW>(tbl, tmask, t.x, seen, cover);
     if (k + 1 < slen) cover_token<MW>(tbl, tmask, t.y, seen, cover);
@@ -303,14 +363,41 @@ __device__ __forceinline__ void add_survivor(const BatchDev& b, int q, int start
   }
 }
 
+// Second stage of the gather: exact coverage of a candidate that survived the signature bound.
+// item = (q, sentence start, sentence length | need << 16, match length).
+__device__ __forceinline__ void verify_candidate(const IndexDev& ix, const BatchDev& b, const Params& pr, int4 item) {
+  const int q = item.x, start = item.y, slen = item.z & 0xffff, need = (int)((unsigned)item.z >> 16);
+  const QMeta qm = __ldg(b.qmeta + q);
+  const int p = qm.x;
+  const int2* tbl = b.tbl + 4ll * qm.z;
+  const int tmask = next_pow2(2 * p) - 1;
+  if (need == 0xffff) {  // no bound table for this query: evaluate the bound itself
+    const int cover = p <= 32 ? cover_sentence<1>(ix.tok + start, slen, tbl, tmask, p + 1)
+                              : cover_sentence<32>(ix.tok + start, slen, tbl, tmask, p + 1);
+    if (reject_cover(p, slen, cover, pr)) return;
+  } else {
+    const int cover = p <= 32 ? cover_sentence<1>(ix.tok + start, slen, tbl, tmask, need)
+                              : cover_sentence<32>(ix.tok + start, slen, tbl, tmask, need);
+    if (cover < need) return;
+  }
+  add_survivor(b, q, start, slen, item.w);
+}
+
 // Persistent kernel over the flattened elements of all slices: register_suffix_range_match's walk
 // (src/ngram_matches.cc:62-84) fused with the candidate filter of src/fuzzy_match.cc:576-581.
 // Each warp takes spans of kSpan consecutive elements; element -> slice by one binary search per
 // span plus a 6-step shuffle search per 32 elements (every slice holds >= 1 element, so the 32
 // elements of a group touch at most the 32 slices after the previous group's last slice).
-static const int kSpan = 128;
+// Stage 1 (every element, one 128-bit load): length window + signature upper bound on the coverage.
+// Stage 2 (the few that pass): queued per warp in shared memory and verified 32 at a time against
+// the sentence tokens, so the expensive path runs with full warps.
+static const int kSpan = 256;
+static const int kQueue = 64;
 __global__ void __launch_bounds__(256) fm_gather_kernel(IndexDev ix, BatchDev b, Params pr) {
+  __shared__ int4 s_queue[8][kQueue];
   const int lane = threadIdx.x & 31;
+  int4* queue = s_queue[threadIdx.x >> 5];
+  int queued = 0;
   const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const unsigned long long packed = b.ctr->slice_elem;
@@ -324,49 +411,73 @@ __global__ void __launch_bounds__(256) fm_gather_kernel(IndexDev ix, BatchDev b,
       const long long mid = (a + e) >> 1;
       if (__ldg(b.sl_start + mid) <= span) a = mid; else e = mid;
     }
-    long long k0 = a;                         // a slice at or one before the slice of the group's first element
-    long long s0 = __ldg(b.sl_start + a);     // its first element
+    long long k0 = a;  // a slice at or one before the slice of the group's first element
+    // starts relative to the span: window starts are > span - 1, the current slice may begin earlier
+    int s0 = (int)max(__ldg(b.sl_start + a) - span, -0x7fffffffll);
     for (int u = 0; u < kSpan; u += 32) {
-      const long long el = span + u + lane;
       if (span + u >= total) break;
+      const int el = u + lane;
       // window = the 32 slices after k0; slice(el) = k0 + #{window starts <= el}
       const long long ks = k0 + 1 + lane;
-      const long long wst = ks < n_slices ? __ldg(b.sl_start + ks) : 0x7fffffffffffffffll;
+      const int wst = ks < n_slices ? (int)min(__ldg(b.sl_start + ks) - span, 0x7fffffffll) : 0x7fffffff;
       int c = 0;
 #pragma unroll
       for (int step = 16; step > 0; step >>= 1) {
-        const long long v = __shfl_sync(FULL, wst, c + step - 1);
+        const int v = __shfl_sync(FULL, wst, c + step - 1);
         if (v <= el) c += step;
       }
       {
-        const long long v = __shfl_sync(FULL, wst, c);  // c <= 31
+        const int v = __shfl_sync(FULL, wst, c);  // c <= 31
         if (v <= el) c += 1;
       }
-      const long long prev_start = __shfl_sync(FULL, wst, c > 0 ? c - 1 : 0);
-      const long long my_start = c > 0 ? prev_start : s0;
+      const int prev_start = __shfl_sync(FULL, wst, c > 0 ? c - 1 : 0);
+      const int my_start = c > 0 ? prev_start : s0;
       const long long my_slice = k0 + c;
       k0 = __shfl_sync(FULL, my_slice, 31);
       s0 = __shfl_sync(FULL, my_start, 31);
-      if (el >= total) continue;
-      const int4 sr = __ldg(b.sl_rec + my_slice);
-      const int q = sr.x, lm = sr.z;
-      const int i = sr.y + (int)(el - my_start);
-      const int pos = __ldg(ix.sa_pos + i);
-      const unsigned meta = __ldg(ix.sa_meta + i);
-      const int slen = (int)(meta >> 16);
-      const QMeta qm = __ldg(b.qmeta + q);
-      const int p = qm.x;
-      if (reject_length(p, slen, pr)) continue;
-      const int start = pos - (int)(meta & 0xffffu);
-      const int2* tbl = b.tbl + 4ll * qm.z;
-      const int tmask = next_pow2(2 * p) - 1;
-      int cover;
-      if (p <= 32) cover = cover_sentence<1>(ix.tok + start, slen, tbl, tmask);
-      else cover = cover_sentence<32>(ix.tok + start, slen, tbl, tmask);
-      if (reject_cover(p, slen, cover, pr)) continue;
-      add_survivor(b, q, start, slen, lm);
+      bool pass = false;
+      int4 item = make_int4(0, 0, 0, 0);
+      if (span + el < total) {
+        const int4 sr = __ldg(b.sl_rec + my_slice);
+        const int q = sr.x;
+        const int4 wr = ldg_nc_v4(ix.sa_walk + (sr.y + (el - my_start)));  // (start, slen, sig lo, sig hi)
+        const int slen = wr.y;
+        const QMeta qm = __ldg(b.qmeta + q);
+        if (qm.w & kQFast) {
+          const int smin = (qm.w >> 8) & 0xfff, smax = (qm.w >> 20) & 0xfff;
+          if (slen >= smin && slen <= smax) {
+            const int need = __ldg(b.cmin + 4ll * qm.z + (slen - smin));
+            if (need <= qm.x) {
+              const int4 m0 = __ldg(b.qmask + 3 * q), m1 = __ldg(b.qmask + 3 * q + 1), m2 = __ldg(b.qmask + 3 * q + 2);
+              const unsigned lo = (unsigned)wr.z, hi = (unsigned)wr.w;
+              const int ub = __popc(lo & m0.x) + __popc(hi & m0.y) + __popc(lo & m0.z) + __popc(hi & m0.w) +
+                             __popc(lo & m1.x) + __popc(hi & m1.y) + __popc(lo & m1.z) + __popc(hi & m1.w) +
+                             m2.z * (__popc(lo & m2.x) + __popc(hi & m2.y));
+              if (ub >= need) {
+                pass = true;
+                item = make_int4(q, wr.x, slen | (need << 16), sr.z);
+              }
+            }
+          }
+        } else if (!reject_length(qm.x, slen, pr)) {
+          pass = true;
+          item = make_int4(q, wr.x, slen | (0xffff << 16), sr.z);
+        }
+      }
+      const unsigned bal = __ballot_sync(FULL, pass);
+      if (bal) {
+        if (pass) queue[queued + __popc(bal & ((1u << lane) - 1))] = item;
+        queued += __popc(bal);
+        __syncwarp();
+        if (queued >= 32) {
+          queued -= 32;
+          verify_candidate(ix, b, pr, queue[queued + lane]);
+          __syncwarp();
+        }
+      }
     }
   }
+  if (lane < queued) verify_candidate(ix, b, pr, queue[lane]);
 }
 
 // ---------------------------------------------------------------- scan (single CTA, n <= a few million)
