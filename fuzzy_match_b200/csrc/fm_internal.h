@@ -136,6 +136,8 @@ struct Workspace {
   int32_t *q_cnt = nullptr, *q_base = nullptr, *acc_cnt = nullptr;
   fm_record* rec = nullptr;
   float* heapbuf = nullptr;
+  unsigned long long *sort_key = nullptr, *m_key = nullptr;
+  int32_t *sort_idx = nullptr, *m_idx = nullptr;
   Counters* ctr = nullptr;
   fm_match* d_out = nullptr;
   int32_t* d_out_count = nullptr;
@@ -194,11 +196,11 @@ void launch_gather(const IndexDev& ix, const BatchDev& b, const Params& p, int s
 void launch_scan(const int32_t* in, int32_t* out, int32_t n, cudaStream_t st);
 void launch_score(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st);
 void launch_replay(const IndexDev& ix, const fm_record* rec, const int32_t* q_cnt, const int32_t* q_base, float* heapbuf,
-                   int32_t* acc_cnt, const int32_t* q_off, int32_t n_q, const Params& p, int64_t cap, fm_match* out,
-                   int32_t* out_count, Counters* ctr, cudaStream_t st);
-void launch_contrast(const IndexDev& ix, fm_record* rec, const int32_t* q_base, const int32_t* acc_cnt, int32_t n_q,
-                     const Params& p, int64_t cap, fm_match* out, int32_t* out_count, Counters* ctr, int sm_count,
-                     cudaStream_t st);
+                   unsigned long long* sort_key, int32_t* sort_idx, int32_t* acc_cnt, const int32_t* q_off, int32_t n_q,
+                   const Params& p, int64_t cap, fm_match* out, int32_t* out_count, Counters* ctr, cudaStream_t st);
+void launch_contrast(const IndexDev& ix, fm_record* rec, const int32_t* q_base, const int32_t* sort_idx,
+                     const int32_t* acc_cnt, int32_t n_q, const Params& p, int64_t cap, fm_match* out, int32_t* out_count,
+                     Counters* ctr, int sm_count, cudaStream_t st);
 void launch_merge_count(int n_shards, const int32_t* const* d_rec_off_dev, int32_t* m_cnt, int32_t n_q, cudaStream_t st);
 void launch_merge_copy(int n_shards, const int32_t* const* d_rec_off_dev, const fm_record* const* d_rec_dev,
                        const int32_t* m_base, fm_record* mrec, int32_t n_q, cudaStream_t st);

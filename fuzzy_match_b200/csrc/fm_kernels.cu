@@ -107,18 +107,23 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
   if (!valid) return;
   const int ts = next_pow2(2 * p);
   int2* tbl = b.tbl + 4ll * off;
-  for (int j = lane; j < ts; j += 32) tbl[j] = make_int2(-1, 0);
+  __shared__ int2 s_tbl[8][128];
+  int2* wtbl = ts <= 128 ? s_tbl[threadIdx.x >> 5] : tbl;  // small tables are built in shared memory
+  for (int j = lane; j < ts; j += 32) wtbl[j] = make_int2(-1, 0);
   __syncwarp();
   if (lane == 0) {
     int distinct = 0;
     for (int j = 0; j < p; j++) {
       const int w = b.pat[off + j];
       int h = hash32((uint32_t)w) & (ts - 1);
-      while (tbl[h].x != -1 && tbl[h].x != w) h = (h + 1) & (ts - 1);
-      if (tbl[h].x == -1) tbl[h] = make_int2(w, (distinct++) | (1 << 16));
-      else tbl[h].y += 1 << 16;
+      while (wtbl[h].x != -1 && wtbl[h].x != w) h = (h + 1) & (ts - 1);
+      if (wtbl[h].x == -1) wtbl[h] = make_int2(w, (distinct++) | (1 << 16));
+      else wtbl[h].y += 1 << 16;
     }
   }
+  __syncwarp();
+  if (ts <= 128)
+    for (int j = lane; j < ts; j += 32) tbl[j] = wtbl[j];
   // Bound tables. The length bound (ngram_matches.cc:32-39) accepts a window [smin, smax] of sentence
   // lengths around p; for each of them cmin = the smallest coverage the coverage bound
   // (ngram_matches.cc:42-59) lets through. Both are evaluated here with the exact float/double
@@ -483,27 +488,47 @@ __global__ void __launch_bounds__(256) fm_gather_kernel(IndexDev ix, BatchDev b,
 // ---------------------------------------------------------------- scan (single CTA, n <= a few million)
 
 __global__ void __launch_bounds__(1024) fm_scan_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, int n) {
-  __shared__ int sums[1024];
-  const int t = threadIdx.x;
-  const int per = (n + 1023) / 1024;
-  const int beg = min(n, t * per), end = min(n, beg + per);
-  int s = 0;
-  for (int i = beg; i < end; i++) s += in[i];
-  sums[t] = s;
+  __shared__ int warp_sum[32];
+  __shared__ int carry_s;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  if (t == 0) carry_s = 0;
   __syncthreads();
-  for (int d = 1; d < 1024; d <<= 1) {
-    const int v = t >= d ? sums[t - d] : 0;
+  for (int base = 0; base < n; base += 4096) {
+    const int i0 = base + 4 * t;
+    int v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = i0 + k < n ? in[i0 + k] : 0;
+    const int mine = v[0] + v[1] + v[2] + v[3];
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(FULL, incl, d);
+      if (lane >= d) incl += o;
+    }
+    if (lane == 31) warp_sum[wid] = incl;
     __syncthreads();
-    sums[t] += v;
+    if (wid == 0) {
+      int ws = warp_sum[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(FULL, ws, d);
+        if (lane >= d) ws += o;
+      }
+      warp_sum[lane] = ws;  // inclusive over warps
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    int run = carry + (wid ? warp_sum[wid - 1] : 0) + incl - mine;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (i0 + k < n) out[i0 + k] = run;
+      run += v[k];
+    }
+    __syncthreads();
+    if (t == 0) carry_s = carry + warp_sum[31];
     __syncthreads();
   }
-  int run = sums[t] - s;
-  for (int i = beg; i < end; i++) {
-    const int v = in[i];
-    out[i] = run;
-    run += v;
-  }
-  if (t == 1023) out[n] = sums[1023];
+  if (t == 0) out[n] = carry_s;
 }
 
 // ---------------------------------------------------------------- edit distance (warp wavefront)
@@ -627,43 +652,34 @@ __global__ void __launch_bounds__(256) fm_score_kernel(IndexDev ix, BatchDev b, 
 __device__ __forceinline__ unsigned long long order_key(const fm_record& r) {  // lm desc, s_id asc
   return ((unsigned long long)(unsigned)(0x7fffffff - r.longest_match) << 32) | r.s_id;
 }
-__device__ __forceinline__ unsigned long long result_key(const fm_record& r) {  // score desc, s_id asc
-  const unsigned u = __float_as_uint(r.rowmin_max);  // slot reused for the score
-  const unsigned ord = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending float order
-  return ((unsigned long long)(~ord) << 32) | r.s_id;
+// Warp-cooperative ascending sort of (key, idx) pairs in global scratch: bitonic network written with
+// ascending comparators only, so the virtual +inf padding up to the next power of two never moves.
+__device__ void warp_sort_pairs(unsigned long long* keys, int32_t* idx, int n) {
+  const int lane = threadIdx.x & 31;
+  int np = 1;
+  while (np < n) np <<= 1;
+  for (int k = 2; k <= np; k <<= 1) {
+    for (int j = k >> 1, first = 1; j > 0; j >>= 1, first = 0) {
+      for (int i = lane; i < np; i += 32) {
+        const int l = first ? (i ^ (k - 1)) : (i ^ j);
+        if (l > i && l < n) {
+          const unsigned long long a = keys[i], c = keys[l];
+          if (a > c) {
+            keys[i] = c; keys[l] = a;
+            const int t = idx[i]; idx[i] = idx[l]; idx[l] = t;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
 }
-template <class KeyFn>
-__device__ void sort_records(fm_record* a, int n, KeyFn key) {
-  if (n <= 24) {  // insertion sort
-    for (int i = 1; i < n; i++) {
-      const fm_record x = a[i];
-      const unsigned long long kx = key(x);
-      int j = i - 1;
-      while (j >= 0 && key(a[j]) > kx) { a[j + 1] = a[j]; j--; }
-      a[j + 1] = x;
-    }
-    return;
-  }
-  // heap sort (ascending): build max-heap, then pop
-  auto sift = [&](int root, int end) {
-    const fm_record x = a[root];
-    const unsigned long long kx = key(x);
-    int i = root;
-    for (;;) {
-      int ch = 2 * i + 1;
-      if (ch >= end) break;
-      if (ch + 1 < end && key(a[ch + 1]) > key(a[ch])) ch++;
-      if (!(key(a[ch]) > kx)) break;
-      a[i] = a[ch];
-      i = ch;
-    }
-    a[i] = x;
-  };
-  for (int i = n / 2 - 1; i >= 0; i--) sift(i, n);
-  for (int end = n - 1; end > 0; end--) {
-    const fm_record t = a[0]; a[0] = a[end]; a[end] = t;
-    sift(0, end);
-  }
+
+// Order n <= 32 records held one per lane: rank = number of smaller keys (keys are distinct).
+__device__ __forceinline__ int warp_rank(unsigned long long key, int n) {
+  int rank = 0;
+  for (int j = 0; j < n; j++) rank += __shfl_sync(FULL, key, j) < key;
+  return rank;
 }
 
 // std::priority_queue<float> lowest_costs (src/fuzzy_match.cc:567-568)
@@ -693,56 +709,112 @@ __device__ __forceinline__ fm_match to_match(const fm_record& r, float penalty) 
   return m;
 }
 
-// One thread per query: the candidate loop of src/fuzzy_match.cc:567-611 replayed over the scored
-// records in the reference's order (ngram_matches.cc:20-29). A candidate is dropped where the
-// reference's bounded edit distance would have exited early or exceeded the bound:
-// max(K, C) > bound. Accepted matches are then ordered like the result heap (:25-33, :670-679).
-__global__ void __launch_bounds__(128) fm_replay_kernel(fm_record* rec, const int32_t* __restrict__ q_cnt,
-                                                        const int32_t* __restrict__ q_base, float* heapbuf, int32_t* acc_cnt,
+// One warp per query: the candidate loop of src/fuzzy_match.cc:567-611 replayed over the scored
+// records in the reference's order (ngram_matches.cc:20-29: longest match desc, s_id asc). A
+// candidate is dropped where the reference's bounded edit distance would have exited early or
+// exceeded the bound: max(K, C) > bound. Accepted matches are then ordered like the result heap
+// (:25-33, :670-679). The warp sorts and prefetches; lane 0 runs the inherently sequential bound heap.
+// On return idx[0..nacc) lists the accepted records best first (rowmin_max now holds the score).
+__global__ void __launch_bounds__(256) fm_replay_kernel(fm_record* rec, const int32_t* __restrict__ q_cnt,
+                                                        const int32_t* __restrict__ q_base, float* heapbuf,
+                                                        unsigned long long* sort_key, int32_t* sort_idx, int32_t* acc_cnt,
                                                         const int32_t* __restrict__ q_off, int n_q, Params pr, long long cap,
                                                         fm_match* out, int32_t* out_count, Counters* ctr) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float s_heap[8][64];
+  const int lane = threadIdx.x & 31;
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (q >= n_q) return;
   if (ctr->overflow) return;
   const int n = q_cnt[q];
+  if (n == 0) {
+    if (lane == 0) {
+      if (pr.contrast > 0.f) acc_cnt[q] = 0;
+      out_count[q] = 0;
+    }
+    return;
+  }
   const int p = q_off[q + 1] - q_off[q];
-  int nacc = 0;
-  fm_record* seg = rec + q_base[q];
-  if (n > 0) {
-    sort_records(seg, n, order_key);
-    float* heap = heapbuf + q_base[q] + q;
-    int hn = 0;
-    heap_push(heap, hn, FLT_MAX);
-    for (int c = 0; c < n; c++) {
-      fm_record r = seg[c];
-      const float bound = heap[0];
-      if (r.rowmin_max > bound || r.cost > bound) continue;
-      if (pr.no_perfect && r.cost == 0.f && r.length == p) continue;
-      const float score = score_of(r.cost);
-      heap_push(heap, hn, r.cost);
-      if (score < pr.fuzzy || (pr.buffer > 0 && hn > pr.buffer)) heap_pop(heap, hn);
-      if (score >= pr.fuzzy) {
-        r.rowmin_max = score;  // slot reused: score
-        r.reserved[1] = 0;     // contrastive accumulator
-        seg[nacc++] = r;
+  const int base = q_base[q];
+  fm_record* seg = rec + base;
+  unsigned long long* keys = sort_key + base;
+  int32_t* idx = sort_idx + base;
+  // 1. candidate order
+  if (n <= 32) {
+    const unsigned long long k = lane < n ? order_key(seg[lane]) : ~0ull;
+    const int r = warp_rank(k, n);
+    if (lane < n) idx[r] = lane;
+  } else {
+    for (int i = lane; i < n; i += 32) { keys[i] = order_key(seg[i]); idx[i] = i; }
+    __syncwarp();
+    warp_sort_pairs(keys, idx, n);
+  }
+  __syncwarp();
+  // 2. sequential replay; the bound heap lives in shared memory when it is known to stay small
+  float* heap = (pr.buffer > 0 && pr.buffer <= 62) ? s_heap[threadIdx.x >> 5] : heapbuf + base + q;
+  int hn = 0, nacc = 0;
+  if (lane == 0) heap_push(heap, hn, FLT_MAX);
+  for (int c0 = 0; c0 < n; c0 += 32) {
+    const int my = c0 + lane < n ? idx[c0 + lane] : 0;
+    const fm_record r = seg[my];
+    const int m = min(32, n - c0);
+    for (int t = 0; t < m; t++) {
+      const float cost = __shfl_sync(FULL, r.cost, t);
+      const float kmax = __shfl_sync(FULL, r.rowmin_max, t);
+      const int len = __shfl_sync(FULL, r.length, t);
+      const int id = __shfl_sync(FULL, my, t);
+      const unsigned sid = __shfl_sync(FULL, r.s_id, t);
+      if (lane == 0) {
+        const float bound = heap[0];
+        if (!(kmax > bound || cost > bound) && !(pr.no_perfect && cost == 0.f && len == p)) {
+          const float score = score_of(cost);
+          heap_push(heap, hn, cost);
+          if (score < pr.fuzzy || (pr.buffer > 0 && hn > pr.buffer)) heap_pop(heap, hn);
+          if (score >= pr.fuzzy) {
+            seg[id].rowmin_max = score;  // slot reused: score
+            seg[id].reserved[1] = 0;     // contrastive accumulator
+            seg[id].reserved[2] = 0;     // contrastive "selected" flag
+            const unsigned u = __float_as_uint(score);
+            const unsigned ord = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+            keys[nacc] = ((unsigned long long)(~ord) << 32) | sid;  // score desc, s_id asc
+            idx[nacc] = id;  // nacc <= c0 + t: this slot has already been consumed
+            nacc++;
+          }
+        }
       }
     }
-    sort_records(seg, nacc, result_key);
+    __syncwarp();
+  }
+  nacc = __shfl_sync(FULL, nacc, 0);
+  // 3. result order
+  if (nacc > 1) {
+    if (nacc <= 32) {
+      const unsigned long long k = lane < nacc ? keys[lane] : ~0ull;
+      const int id = lane < nacc ? idx[lane] : 0;
+      const int r = warp_rank(k, nacc);
+      __syncwarp();
+      if (lane < nacc) idx[r] = id;
+    } else {
+      warp_sort_pairs(keys, idx, nacc);
+    }
+    __syncwarp();
   }
   if (pr.contrast > 0.f) {
-    acc_cnt[q] = nacc;
+    if (lane == 0) acc_cnt[q] = nacc;
     return;
   }
   const int want = pr.n_matches == 0 ? nacc : min(nacc, pr.n_matches);
-  out_count[q] = want;
-  for (int k = 0; k < want && k < cap; k++) out[(long long)q * cap + k] = to_match(seg[k], 0.f);
-  if (want) atomicAdd(&ctr->n_matches, (unsigned)want);
+  for (int k = lane; k < want && k < cap; k += 32) out[(long long)q * cap + k] = to_match(seg[idx[k]], 0.f);
+  if (lane == 0) {
+    out_count[q] = want;
+    if (want) atomicAdd(&ctr->n_matches, (unsigned)want);
+  }
 }
 
 // One warp per query: contrastive rerank of src/fuzzy_match.cc:613-669. Penalties against the newly
 // selected match are edit distances between TM sentences (plain variant, unit costs), accumulated in
 // selection order (running float sum for MEAN, running max for MAX).
 __global__ void __launch_bounds__(256) fm_contrast_kernel(IndexDev ix, fm_record* rec, const int32_t* __restrict__ q_base,
+                                                          const int32_t* __restrict__ sort_idx,
                                                           const int32_t* __restrict__ acc_cnt, int n_q, Params pr,
                                                           long long cap, fm_match* out, int32_t* out_count, Counters* ctr,
                                                           int stride) {
@@ -760,16 +832,17 @@ __global__ void __launch_bounds__(256) fm_contrast_kernel(IndexDev ix, fm_record
   for (int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < n_q; q += n_warps) {
     const int n = acc_cnt[q];
     fm_record* seg = rec + q_base[q];
+    const int32_t* idx = sort_idx + q_base[q];  // accepted records, best first
     int n_out = 0, remaining = n, n_sel = 0;
     int last = -1;
     while (remaining > 0 && (pr.n_matches == 0 || n_out < pr.n_matches)) {
       if (last >= 0) {
-        const fm_record lr = seg[last];
+        const fm_record lr = seg[idx[last]];
         for (int k = lane; k < lr.length; k += 32) s_pat[k] = ix.tok[lr.reserved[0] + k];
         for (int k = lane; k < lr.length; k += 32) s_pen[k] = 0.f;
         __syncwarp();
         for (int i = 0; i < n; i++) {
-          const fm_record cr = seg[i];
+          const fm_record cr = seg[idx[i]];
           if (cr.reserved[2]) continue;  // already selected
           for (int k = lane; k < cr.length; k += 32) s_sent[k] = ix.tok[cr.reserved[0] + k];
           __syncwarp();
@@ -781,7 +854,7 @@ __global__ void __launch_bounds__(256) fm_contrast_kernel(IndexDev ix, fm_record
             float acc = __int_as_float(cr.reserved[1]);
             if (pr.reduce == 1) acc = (n_sel == 1 || pen > acc) ? pen : acc;
             else acc = __fadd_rn(acc, pen);
-            seg[i].reserved[1] = __float_as_int(acc);
+            seg[idx[i]].reserved[1] = __float_as_int(acc);
           }
         }
         __syncwarp();
@@ -790,18 +863,18 @@ __global__ void __launch_bounds__(256) fm_contrast_kernel(IndexDev ix, fm_record
       if (lane == 0) {  // std::max_element: first maximum of score - factor*penalty in list order
         float best_key = 0.f;
         for (int i = 0; i < n; i++) {
-          const fm_record cr = seg[i];
+          const fm_record cr = seg[idx[i]];
           if (cr.reserved[2]) continue;
           const float acc = __int_as_float(cr.reserved[1]);
           const float pen = n_sel == 0 ? 0.f : (pr.reduce == 1 ? acc : __fdiv_rn(acc, (float)n_sel));
           const float key = __fsub_rn(cr.rowmin_max, __fmul_rn(pr.contrast, pen));
           if (best < 0 || best_key < key) { best = i; best_key = key; }
         }
-        const fm_record br = seg[best];
+        const fm_record br = seg[idx[best]];
         const float acc = __int_as_float(br.reserved[1]);
         const float pen = n_sel == 0 ? 0.f : (pr.reduce == 1 ? acc : __fdiv_rn(acc, (float)n_sel));
         if (n_out < cap) out[(long long)q * cap + n_out] = to_match(br, pen);
-        seg[best].reserved[2] = 1;
+        seg[idx[best]].reserved[2] = 1;
       }
       best = __shfl_sync(FULL, best, 0);
       last = best;
@@ -872,14 +945,14 @@ void launch_score(const IndexDev& ix, const BatchDev& b, const Params& p, int sm
   fm_score_kernel<<<sm_count * 4, 256, smem, st>>>(ix, b, p, stride);
 }
 void launch_replay(const IndexDev&, const fm_record* rec, const int32_t* q_cnt, const int32_t* q_base, float* heapbuf,
-                   int32_t* acc_cnt, const int32_t* q_off, int32_t n_q, const Params& p, int64_t cap, fm_match* out,
-                   int32_t* out_count, Counters* ctr, cudaStream_t st) {
-  const int grid = (n_q + 127) / 128;
-  fm_replay_kernel<<<grid, 128, 0, st>>>(const_cast<fm_record*>(rec), q_cnt, q_base, heapbuf, acc_cnt, q_off, n_q, p,
-                                         (long long)cap, out, out_count, ctr);
+                   unsigned long long* sort_key, int32_t* sort_idx, int32_t* acc_cnt, const int32_t* q_off, int32_t n_q,
+                   const Params& p, int64_t cap, fm_match* out, int32_t* out_count, Counters* ctr, cudaStream_t st) {
+  const int grid = (n_q + 7) / 8;
+  fm_replay_kernel<<<grid, 256, 0, st>>>(const_cast<fm_record*>(rec), q_cnt, q_base, heapbuf, sort_key, sort_idx, acc_cnt,
+                                         q_off, n_q, p, (long long)cap, out, out_count, ctr);
 }
-void launch_contrast(const IndexDev& ix, fm_record* rec, const int32_t* q_base, const int32_t* acc_cnt, int32_t n_q,
-                     const Params& p, int64_t cap, fm_match* out, int32_t* out_count, Counters* ctr, int sm_count,
+void launch_contrast(const IndexDev& ix, fm_record* rec, const int32_t* q_base, const int32_t* sort_idx,
+                     const int32_t* acc_cnt, int32_t n_q, const Params& p, int64_t cap, fm_match* out, int32_t* out_count, Counters* ctr, int sm_count,
                      cudaStream_t st) {
   const int stride = dp_stride(ix);
   const size_t smem = (size_t)8 * 4 * stride * sizeof(int);
@@ -890,7 +963,7 @@ void launch_contrast(const IndexDev& ix, fm_record* rec, const int32_t* q_base, 
   }
   int grid = (n_q + 7) / 8;
   if (grid > sm_count * 4) grid = sm_count * 4;
-  fm_contrast_kernel<<<grid, 256, smem, st>>>(ix, rec, q_base, acc_cnt, n_q, p, (long long)cap, out, out_count, ctr, stride);
+  fm_contrast_kernel<<<grid, 256, smem, st>>>(ix, rec, q_base, sort_idx, acc_cnt, n_q, p, (long long)cap, out, out_count, ctr, stride);
 }
 
 void launch_merge_count(int n_shards, const int32_t* const* off, int32_t* m_cnt, int32_t n_q, cudaStream_t st) {
