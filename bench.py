@@ -267,12 +267,13 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---- value: device-resident, CUDA events on the launching stream
-    for i in range(args.warmup):
-        step_device(i)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(1.5)  # let nvidia-smi finish attaching before anything is timed
+    for i in range(max(args.warmup, n_batches)):  # every distinct batch once, so no workspace growth is timed
+        step_device(i)
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         ev0.record(stream)

@@ -18,6 +18,7 @@ static int dev_realloc(T** p, size_t n) {
   return FM_OK;
 }
 
+static const int64_t kSpanHost = 256;  // == kSpan in fm_kernels.cu
 static int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
 static Workspace* acquire(Index* ix) {
@@ -57,7 +58,7 @@ static int ensure_queries(Workspace* w, int64_t n_q, int64_t n_tok, bool staging
   }
   if (n_tok > w->cap_tok) {
     const int64_t c = round_up(n_tok + n_tok / 4 + 4096, 4096);
-    if ((rc = dev_realloc(&w->pat, c)) || (rc = dev_realloc(&w->chain_q, c)) || (rc = dev_realloc(&w->tbl, 4 * c)) || (rc = dev_realloc(&w->cmin, 4 * c)) ||
+    if ((rc = dev_realloc(&w->pat, c)) || (rc = dev_realloc(&w->chain_q, c)) || (rc = dev_realloc(&w->tbl, 4 * c)) ||
         (rc = dev_realloc(&w->d_q_tok, c)))
       return rc;
     w->cap_tok = c;
@@ -76,6 +77,21 @@ static int ensure_slices(Workspace* w, int64_t n) {
   int rc;
   if ((rc = dev_realloc(&w->sl_start, n + 1)) || (rc = dev_realloc(&w->sl_rec, n))) return rc;
   w->cap_slices = n;
+  return FM_OK;
+}
+static int ensure_spans(Workspace* w, int64_t n) {
+  if (n <= w->cap_spans) return FM_OK;
+  int rc;
+  if ((rc = dev_realloc(&w->span_slice, n))) return rc;
+  w->cap_spans = n;
+  return FM_OK;
+}
+static int ensure_bounds(Index* ix, Workspace* w) {
+  if (w->pinfo) return FM_OK;
+  int rc;
+  const int64_t t = ix->max_tokens;
+  if ((rc = dev_realloc(&w->pinfo, t + 2)) || (rc = dev_realloc(&w->cmin_tab, 2 * t * (t + 1) + 16))) return rc;
+  w->bounds_valid = false;
   return FM_OK;
 }
 static int ensure_survivors(Workspace* w, int64_t n) {
@@ -101,7 +117,7 @@ static int ensure_out(Workspace* w, int64_t n_q, int64_t cap) {
 }
 
 static void free_workspace(Workspace* w) {
-  cudaFree(w->d_q_tok); cudaFree(w->d_q_off); cudaFree(w->pat); cudaFree(w->chain_q); cudaFree(w->qmeta); cudaFree(w->tbl); cudaFree(w->cmin); cudaFree(w->qmask);
+  cudaFree(w->d_q_tok); cudaFree(w->d_q_off); cudaFree(w->pat); cudaFree(w->chain_q); cudaFree(w->qmeta); cudaFree(w->tbl); cudaFree(w->pinfo); cudaFree(w->cmin_tab); cudaFree(w->span_slice); cudaFree(w->qmask);
   cudaFree(w->sl_start); cudaFree(w->sl_rec); cudaFree(w->hkey); cudaFree(w->hlm); cudaFree(w->surv); cudaFree(w->surv_len);
   cudaFree(w->q_cnt); cudaFree(w->q_base); cudaFree(w->acc_cnt); cudaFree(w->rec); cudaFree(w->heapbuf); cudaFree(w->ctr);
   cudaFree(w->d_out); cudaFree(w->d_out_count); cudaFree(w->mrec); cudaFree(w->m_cnt); cudaFree(w->m_base); cudaFree(w->m_acc); cudaFree(w->m_heap); cudaFree(w->sort_key); cudaFree(w->sort_idx); cudaFree(w->m_key); cudaFree(w->m_idx);
@@ -133,7 +149,8 @@ static int check_params(const fm_params* p, Params* out) {
 static BatchDev make_batch(Workspace* w, const int32_t* d_q_tok, const int32_t* d_q_off, int64_t n_q, int64_t n_tok) {
   BatchDev b{};
   b.q_tok_in = d_q_tok; b.q_off = d_q_off; b.n_q = (int32_t)n_q; b.n_tok = (int32_t)n_tok;
-  b.pat = w->pat; b.chain_q = w->chain_q; b.qmeta = w->qmeta; b.tbl = w->tbl; b.cmin = w->cmin; b.qmask = w->qmask;
+  b.pat = w->pat; b.chain_q = w->chain_q; b.qmeta = w->qmeta; b.tbl = w->tbl; b.pinfo = w->pinfo; b.cmin_tab = w->cmin_tab; b.qmask = w->qmask;
+  b.span_slice = w->span_slice; b.span_cap = w->cap_spans;
   b.sl_start = w->sl_start; b.sl_rec = w->sl_rec; b.slice_cap = w->cap_slices;
   b.hkey = w->hkey; b.hlm = w->hlm; b.hmask = w->hsize - 1;
   b.surv = w->surv; b.surv_len = w->surv_len; b.surv_cap = w->cap_surv;
@@ -153,6 +170,12 @@ static int launch_shard(Index* ix, Workspace* w, const int32_t* d_q_tok, const i
   FM_CUDA(cudaMemsetAsync(w->hlm, 0, (size_t)w->hsize * sizeof(unsigned int), st));
   if (getenv("FM_DEBUG_SYNC")) cudaStreamSynchronize(st);
   if (ix->profiling) cudaEventRecord(w->ev[0], st);
+  if (!w->bounds_valid || memcmp(&w->bounds_params, &pr, sizeof(Params)) != 0) {  // per-length bound tables follow the parameters
+    launch_bounds(ix->dev, b, pr, st);
+    w->bounds_params = pr;
+    w->bounds_valid = true;
+    (*launches)++;
+  }
   launch_prepare(ix->dev, b, pr, st);
   if (ix->profiling) cudaEventRecord(w->ev[1], st);
   launch_search(ix->dev, b, pr, st);
@@ -168,9 +191,11 @@ static int launch_shard(Index* ix, Workspace* w, const int32_t* d_q_tok, const i
   return FM_OK;
 }
 
-static int initial_worklists(Workspace* w, int64_t n_q, int64_t n_tok) {
+static int initial_worklists(Index* ix, Workspace* w, int64_t n_q, int64_t n_tok) {
   int rc;
+  if ((rc = ensure_bounds(ix, w))) return rc;
   if ((rc = ensure_slices(w, std::max<int64_t>(1 << 16, 8 * n_tok + 65536)))) return rc;
+  if ((rc = ensure_spans(w, std::max<int64_t>(1 << 16, 2 * n_tok + 65536)))) return rc;
   return ensure_survivors(w, std::max<int64_t>(1 << 18, 8 * n_q));
 }
 
@@ -188,6 +213,8 @@ static int sync_and_check(Workspace* w, cudaStream_t st, int attempt, int* retri
   const int64_t need_slices = (int64_t)(w->h_ctr->slice_elem >> kElemBits);
   if (need_slices > w->cap_slices && (rc = ensure_slices(w, need_slices + need_slices / 8 + 1024))) return -rc;
   if ((w->h_ctr->overflow & 2u) && (rc = ensure_survivors(w, w->cap_surv * 4))) return -rc;
+  const int64_t need_spans = (int64_t)((w->h_ctr->slice_elem & ((1ull << kElemBits) - 1)) / kSpanHost) + 2;
+  if (need_spans > w->cap_spans && (rc = ensure_spans(w, need_spans + need_spans / 8))) return -rc;
   return 1;
 }
 
@@ -228,7 +255,7 @@ static void finish_profile(Index* ix, Workspace* w, int64_t n_q, int64_t n_tok, 
 static int match_device(Index* ix, Workspace* w, const int32_t* d_q_tok, const int32_t* d_q_off, int64_t n_q, int64_t n_tok,
                         const Params& pr, int64_t cap, fm_match* d_out, int32_t* d_out_count, cudaStream_t st) {
   int rc, launches = 0, retries = 0;
-  if ((rc = initial_worklists(w, n_q, n_tok))) return rc;
+  if ((rc = initial_worklists(ix, w, n_q, n_tok))) return rc;
   for (int attempt = 0;; attempt++) {
     if ((rc = launch_shard(ix, w, d_q_tok, d_q_off, n_q, n_tok, pr, st, &launches))) return rc;
     if ((rc = run_replay(ix, w, w->rec, w->q_cnt, w->q_base, w->heapbuf, w->sort_key, w->sort_idx, w->acc_cnt, d_q_off, n_q, pr, cap, d_out, d_out_count,
@@ -372,7 +399,7 @@ int fm_shard_score_device(fm_index* index, const int32_t* d_q_tokens, const int3
   if ((rc = ensure_base(w)) || (rc = ensure_queries(w, n_q, n_query_tokens, false))) return rc;
   int launches = 0, retries = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if ((rc = initial_worklists(w, n_q, n_query_tokens))) return rc;
+  if ((rc = initial_worklists(ix, w, n_q, n_query_tokens))) return rc;
   for (int attempt = 0;; attempt++) {
     if ((rc = launch_shard(ix, w, d_q_tokens, d_q_off, n_q, n_query_tokens, pr, st, &launches))) return rc;
     if (ix->profiling) cudaEventRecord(w->ev[6], st);

@@ -41,10 +41,9 @@ struct IndexDev {
 // per-query metadata written by the prepare kernel
 //   x = pattern length p (0 if the query is skipped), y = effective min_subseq_length,
 //   z = offset of the pattern in the token arrays,
-//   w = bit0: query takes part, bit1: bound tables valid, bits 8-19 / 20-31: smallest / largest
-//       sentence length that passes the length bound
+//   w = bit0: query takes part
 typedef int4 QMeta;
-static const int kQValid = 1, kQFast = 2;
+static const int kQValid = 1;
 
 // word -> signature bit (must be identical on host and device)
 __host__ __device__ inline unsigned sig_bit(int w) { return ((unsigned)w * 0x9E3779B1u) >> 26; }
@@ -59,7 +58,7 @@ struct SurvRec {  // one distinct (query, sentence) that passed both rejection b
 struct Counters {
   unsigned long long slice_elem;  // (n_slices << 38) | n_elements, one packed atomic
   unsigned int n_surv;
-  unsigned int overflow;  // bit0 slices, bit1 survivors
+  unsigned int overflow;  // bit0 slices, bit1 survivors, bit2 span index
   unsigned int n_matches;
   unsigned int pad[3];
 };
@@ -77,12 +76,15 @@ struct BatchDev {
   int32_t* chain_q;  // [n_tok] query of each chain (= pattern position)
   QMeta* qmeta;      // [n_q]
   int2* tbl;         // [4*n_tok] per-query open-addressing tables: (word, distinct_idx | count<<16)
-  uint16_t* cmin;    // [4*n_tok] per query, for each passing sentence length: smallest coverage that passes
+  const int4* pinfo;        // [max_tokens+1] per pattern length: (smin, smax, tables valid, row offset)
+  const uint16_t* cmin_tab; // per (pattern length, passing sentence length): smallest coverage that passes
   int4* qmask;       // [3*n_q] per query: signature masks M1..M5 (pattern positions per bit >= 1..5) + weight
   // search output
   long long* sl_start;  // [slice_cap+1] first flattened element of each slice (ascending)
-  int4* sl_rec;         // [slice_cap] (q, sa_begin, match_len, size)
+  int4* sl_rec;         // [slice_cap] (q, sa_begin, match_len | p << 16, size)
   int64_t slice_cap;
+  int32_t* span_slice;  // [span_cap] slice holding flattened element k*kSpan
+  int64_t span_cap;
   // gather output
   unsigned long long* hkey;  // [hsize] (q<<32 | start), ~0 = empty
   unsigned int* hlm;         // [hsize] max match length
@@ -125,7 +127,12 @@ struct Workspace {
   int32_t *pat = nullptr, *chain_q = nullptr;
   QMeta* qmeta = nullptr;
   int2* tbl = nullptr;
-  uint16_t* cmin = nullptr;
+  int4* pinfo = nullptr;
+  uint16_t* cmin_tab = nullptr;
+  int32_t* span_slice = nullptr;
+  int64_t cap_spans = 0;
+  Params bounds_params{};
+  bool bounds_valid = false;
   int4* qmask = nullptr;
   long long* sl_start = nullptr;
   int4* sl_rec = nullptr;
@@ -190,6 +197,7 @@ void free_index(Index* ix);
 int set_idf_stats(Index* ix, const uint32_t* sfreq, int64_t n_sent_global);
 
 // fm_kernels.cu -- launchers (all asynchronous on `st`)
+void launch_bounds(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st);
 void launch_prepare(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st);
 void launch_search(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st);
 void launch_gather(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st);

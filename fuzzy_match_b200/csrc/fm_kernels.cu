@@ -20,6 +20,7 @@
 namespace fm {
 
 #define FULL 0xffffffffu
+static const int kSpan = 256;  // flattened elements per gather work unit
 
 // ---------------------------------------------------------------- small device helpers
 
@@ -77,6 +78,47 @@ __device__ __forceinline__ float score_of(float cost) {
   return (float)((double)v / 10000.0);
 }
 
+// ---------------------------------------------------------------- bound tables (one warp per pattern length)
+
+// The length bound (ngram_matches.cc:32-39) accepts a window [smin, smax] of sentence lengths around
+// p; for each of them cmin = the smallest coverage the coverage bound (ngram_matches.cc:42-59) lets
+// through. Both depend only on (p, s, fuzzy, costs), so they are evaluated with the exact float/double
+// expressions once per pattern length when the parameters change, instead of once per suffix-array
+// element. pinfo[p] = (smin, smax, tables valid, offset of p's row in cmin_tab).
+__global__ void __launch_bounds__(256) fm_bounds_kernel(int max_tokens, Params pr, int4* pinfo, uint16_t* cmin_tab) {
+  const int lane = threadIdx.x & 31;
+  const int p = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) + 1;
+  if (p > max_tokens) return;
+  int smin = 0x7fffffff, smax = 0, n_ok = 0;
+  for (int base = 1; base <= max_tokens; base += 32) {
+    const int sl = base + lane;
+    const bool ok = sl <= max_tokens && !reject_length(p, sl, pr);
+    const unsigned bal = __ballot_sync(FULL, ok);
+    if (bal) {
+      smin = min(smin, base + __ffs(bal) - 1);
+      smax = max(smax, base + 31 - __clz(bal));
+      n_ok += __popc(bal);
+    }
+  }
+  const bool fast = n_ok > 0 && n_ok == smax - smin + 1 && n_ok <= 4 * p && pr.ins >= 0.f && pr.del >= 0.f && pr.rep >= 0.f;
+  const int row = 2 * p * (p - 1);  // sum_{k<p} 4k
+  if (fast) {
+    for (int sl = smin + lane; sl <= smax; sl += 32) {
+      int need = p + 1;
+      if (!reject_cover(p, sl, p, pr)) {  // reject_cover is monotone in the coverage for costs >= 0
+        int lo = 0, hi = p;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (!reject_cover(p, sl, mid, pr)) hi = mid; else lo = mid + 1;
+        }
+        need = lo;
+      }
+      cmin_tab[row + sl - smin] = (uint16_t)need;
+    }
+  }
+  if (lane == 0) pinfo[p] = make_int4(fast ? smin : 0, fast ? smax : 0, fast ? 1 : 0, row);
+}
+
 // ---------------------------------------------------------------- prepare
 
 // One warp per query. Guards and ml clamp of src/fuzzy_match.cc:450-467; ids outside the vocabulary
@@ -124,37 +166,6 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
   __syncwarp();
   if (ts <= 128)
     for (int j = lane; j < ts; j += 32) tbl[j] = wtbl[j];
-  // Bound tables. The length bound (ngram_matches.cc:32-39) accepts a window [smin, smax] of sentence
-  // lengths around p; for each of them cmin = the smallest coverage the coverage bound
-  // (ngram_matches.cc:42-59) lets through. Both are evaluated here with the exact float/double
-  // expressions, once per (query, length) instead of once per suffix-array element.
-  int smin = 0x7fffffff, smax = 0, n_ok = 0;
-  for (int base = 1; base <= ix.max_tokens; base += 32) {
-    const int sl = base + lane;
-    const bool ok = sl <= ix.max_tokens && !reject_length(p, sl, pr);
-    const unsigned bal = __ballot_sync(FULL, ok);
-    if (bal) {
-      smin = min(smin, base + __ffs(bal) - 1);
-      smax = max(smax, base + 31 - __clz(bal));
-      n_ok += __popc(bal);
-    }
-  }
-  const bool fast = n_ok > 0 && n_ok == smax - smin + 1 && n_ok <= 4 * p && pr.ins >= 0.f && pr.del >= 0.f && pr.rep >= 0.f;
-  if (fast) {
-    uint16_t* cm = b.cmin + 4ll * off;
-    for (int sl = smin + lane; sl <= smax; sl += 32) {
-      int need = p + 1;
-      if (!reject_cover(p, sl, p, pr)) {  // reject_cover is monotone in the coverage for costs >= 0
-        int lo = 0, hi = p;
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (!reject_cover(p, sl, mid, pr)) hi = mid; else lo = mid + 1;
-        }
-        need = lo;
-      }
-      cm[sl - smin] = (uint16_t)need;
-    }
-  }
   // Signature masks: M_l = bits that >= l pattern positions hash to (unknown words excluded).
   // coverage <= sum_l popc(sig & M_l) (+ weight * popc(sig & M5) for bits with more than 4 positions).
   {
@@ -179,7 +190,6 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
       b.qmask[3 * q + 0] = make_int4(m[0], m[1], m[2], m[3]);
       b.qmask[3 * q + 1] = make_int4(m[4], m[5], m[6], m[7]);
       b.qmask[3 * q + 2] = make_int4(m[8], m[9], extra, 0);
-      b.qmeta[q] = make_int4(p, ml, off, kQValid | (fast ? kQFast | (smin << 8) | (smax << 20) : 0));
     }
   }
 }
@@ -188,8 +198,15 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
 
 // Warp-collective append of up to two range slices per lane. One packed 64-bit atomic per warp
 // reserves slice slots and flattened element offsets together, so slice order == element order.
-__device__ __forceinline__ void emit_slices(const BatchDev& b, int lane, int q, int n, int beg0, int sz0, int lm0, int beg1,
-                                            int sz1, int lm1) {
+__device__ __forceinline__ void note_spans(const BatchDev& b, long long slot, long long start, int size) {
+  // span_slice[k] = slice that holds flattened element k*kSpan
+  for (long long k = (start + kSpan - 1) / kSpan; k * kSpan < start + size; k++) {
+    if (k < b.span_cap) b.span_slice[k] = (int32_t)slot;
+    else { atomicOr(&b.ctr->overflow, 4u); break; }
+  }
+}
+__device__ __forceinline__ void emit_slices(const BatchDev& b, int lane, int q, int p, int n, int beg0, int sz0, int lm0,
+                                            int beg1, int sz1, int lm1) {
   const unsigned long long mine = ((unsigned long long)n << kElemBits) | (unsigned long long)(unsigned)(sz0 + sz1);
   unsigned long long incl = mine;
 #pragma unroll
@@ -212,13 +229,15 @@ __device__ __forceinline__ void emit_slices(const BatchDev& b, int lane, int q, 
     }
     if (sz0 > 0) {
       b.sl_start[slot] = start;
-      b.sl_rec[slot] = make_int4(q, beg0, lm0, sz0);
+      b.sl_rec[slot] = make_int4(q, beg0, lm0 | (p << 16), sz0);
+      note_spans(b, slot, start, sz0);
       slot++;
       start += sz0;
     }
     if (sz1 > 0) {
       b.sl_start[slot] = start;
-      b.sl_rec[slot] = make_int4(q, beg1, lm1, sz1);
+      b.sl_rec[slot] = make_int4(q, beg1, lm1 | (p << 16), sz1);
+      note_spans(b, slot, start, sz1);
     }
   }
 }
@@ -248,7 +267,7 @@ __global__ void __launch_bounds__(256) fm_search_kernel(IndexDev ix, BatchDev b)
   // p == 1: the unigram range itself is registered (src/fuzzy_match.cc:484-493)
   {
     const bool uni = live && p == 1 && 1 >= ml;
-    emit_slices(b, lane, q, uni ? 1 : 0, lo, uni ? hi - lo : 0, 1, 0, 0, 0);
+    emit_slices(b, lane, q, p, uni ? 1 : 0, lo, uni ? hi - lo : 0, 1, 0, 0, 0);
   }
   bool extending = live && it + 1 < p;
   while (__any_sync(FULL, extending)) {
@@ -288,11 +307,11 @@ __global__ void __launch_bounds__(256) fm_search_kernel(IndexDev ix, BatchDev b)
         extending = false;
       }
     }
-    emit_slices(b, lane, q, n, beg0, sz0, len - 1, beg1, sz1, len - 1);
+    emit_slices(b, lane, q, p, n, beg0, sz0, len - 1, beg1, sz1, len - 1);
   }
   {
     const bool fin = live && len >= 2 && len >= ml;
-    emit_slices(b, lane, q, fin ? 1 : 0, lo, fin ? hi - lo : 0, len, 0, 0, 0);
+    emit_slices(b, lane, q, p, fin ? 1 : 0, lo, fin ? hi - lo : 0, len, 0, 0, 0);
   }
 }
 
@@ -396,7 +415,6 @@ __device__ __forceinline__ void verify_candidate(const IndexDev& ix, const Batch
 // Stage 1 (every element, one 128-bit load): length window + signature upper bound on the coverage.
 // Stage 2 (the few that pass): queued per warp in shared memory and verified 32 at a time against
 // the sentence tokens, so the expensive path runs with full warps.
-static const int kSpan = 256;
 static const int kQueue = 64;
 __global__ void __launch_bounds__(256) fm_gather_kernel(IndexDev ix, BatchDev b, Params pr) {
   __shared__ int4 s_queue[8][kQueue];
@@ -408,17 +426,12 @@ __global__ void __launch_bounds__(256) fm_gather_kernel(IndexDev ix, BatchDev b,
   const unsigned long long packed = b.ctr->slice_elem;
   const long long total = (long long)(packed & ((1ull << kElemBits) - 1));
   long long n_slices = (long long)(packed >> kElemBits);
-  if (n_slices > b.slice_cap) return;  // overflow: the host regrows and reruns
+  if (b.ctr->overflow) return;  // a worklist overflowed: the host regrows and reruns
   for (long long span = warp_id * kSpan; span < total; span += n_warps * kSpan) {
-    // slice containing the first element of the span (uniform across the warp)
-    long long a = 0, e = n_slices;  // largest k with sl_start[k] <= span
-    while (e - a > 1) {
-      const long long mid = (a + e) >> 1;
-      if (__ldg(b.sl_start + mid) <= span) a = mid; else e = mid;
-    }
-    long long k0 = a;  // a slice at or one before the slice of the group's first element
+    // slice containing the first element of the span (written by the search kernel)
+    long long k0 = __ldg(b.span_slice + span / kSpan);  // a slice at or one before the slice of the group's first element
     // starts relative to the span: window starts are > span - 1, the current slice may begin earlier
-    int s0 = (int)max(__ldg(b.sl_start + a) - span, -0x7fffffffll);
+    int s0 = (int)max(__ldg(b.sl_start + k0) - span, -0x7fffffffll);
     for (int u = 0; u < kSpan; u += 32) {
       if (span + u >= total) break;
       const int el = u + lane;
@@ -447,12 +460,12 @@ __global__ void __launch_bounds__(256) fm_gather_kernel(IndexDev ix, BatchDev b,
         const int q = sr.x;
         const int4 wr = ldg_nc_v4(ix.sa_walk + (sr.y + (el - my_start)));  // (start, slen, sig lo, sig hi)
         const int slen = wr.y;
-        const QMeta qm = __ldg(b.qmeta + q);
-        if (qm.w & kQFast) {
-          const int smin = (qm.w >> 8) & 0xfff, smax = (qm.w >> 20) & 0xfff;
-          if (slen >= smin && slen <= smax) {
-            const int need = __ldg(b.cmin + 4ll * qm.z + (slen - smin));
-            if (need <= qm.x) {
+        const int p = sr.z >> 16, lm = sr.z & 0xffff;
+        const int4 pi = __ldg(b.pinfo + p);  // (smin, smax, tables valid, row)
+        if (pi.z) {
+          if (slen >= pi.x && slen <= pi.y) {
+            const int need = __ldg(b.cmin_tab + pi.w + (slen - pi.x));
+            if (need <= p) {
               const int4 m0 = __ldg(b.qmask + 3 * q), m1 = __ldg(b.qmask + 3 * q + 1), m2 = __ldg(b.qmask + 3 * q + 2);
               const unsigned lo = (unsigned)wr.z, hi = (unsigned)wr.w;
               const int ub = __popc(lo & m0.x) + __popc(hi & m0.y) + __popc(lo & m0.z) + __popc(hi & m0.w) +
@@ -460,13 +473,13 @@ __global__ void __launch_bounds__(256) fm_gather_kernel(IndexDev ix, BatchDev b,
                              m2.z * (__popc(lo & m2.x) + __popc(hi & m2.y));
               if (ub >= need) {
                 pass = true;
-                item = make_int4(q, wr.x, slen | (need << 16), sr.z);
+                item = make_int4(q, wr.x, slen | (need << 16), lm);
               }
             }
           }
-        } else if (!reject_length(qm.x, slen, pr)) {
+        } else if (!reject_length(p, slen, pr)) {
           pass = true;
-          item = make_int4(q, wr.x, slen | (0xffff << 16), sr.z);
+          item = make_int4(q, wr.x, slen | (0xffff << 16), lm);
         }
       }
       const unsigned bal = __ballot_sync(FULL, pass);
@@ -919,6 +932,10 @@ __global__ void fm_merge_copy_kernel(ShardPtrs sp, int n_shards, const int32_t* 
 
 static int dp_stride(const IndexDev& ix) { return ((ix.max_tokens + 31) / 32) * 32 + 32; }
 
+void launch_bounds(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st) {
+  fm_bounds_kernel<<<(ix.max_tokens + 7) / 8, 256, 0, st>>>(ix.max_tokens, p, const_cast<int4*>(b.pinfo),
+                                                            const_cast<uint16_t*>(b.cmin_tab));
+}
 void launch_prepare(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st) {
   const int warps_per_block = 8;
   const int grid = (b.n_q + warps_per_block - 1) / warps_per_block;
