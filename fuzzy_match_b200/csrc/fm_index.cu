@@ -185,6 +185,33 @@ int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_in, in
   }
   std::vector<uint32_t>().swap(meta_of_pos);
 
+  // ---- bigram directory: one entry per distinct (word0, word1) with its suffix-array range
+  std::vector<int4> bg_tab;
+  uint32_t bg_mask = 0;
+  {
+    const int32_t* tok = ix->h_tok.data();
+    int64_t n_bg = 0;
+    for (int64_t i2 = 0; i2 < n_suf; i2++) {
+      const int32_t t1 = tok[sa[i2] + 1];
+      if (t1 != 0 && (i2 == 0 || tok[sa[i2 - 1]] != tok[sa[i2]] || tok[sa[i2 - 1] + 1] != t1)) n_bg++;
+    }
+    uint64_t cap = 1024;
+    while (cap < (uint64_t)n_bg * 2) cap <<= 1;
+    bg_mask = (uint32_t)(cap - 1);
+    bg_tab.assign((size_t)cap, make_int4(-1, -1, 0, 0));
+    for (int64_t i2 = 0; i2 < n_suf;) {
+      const int32_t t0 = tok[sa[i2]], t1 = tok[sa[i2] + 1];
+      int64_t j2 = i2 + 1;
+      while (j2 < n_suf && tok[sa[j2]] == t0 && tok[sa[j2] + 1] == t1) j2++;
+      if (t1 != 0) {
+        uint32_t hsl = bigram_hash(t0, t1) & bg_mask;
+        while (bg_tab[hsl].x != -1) hsl = (hsl + 1) & bg_mask;
+        bg_tab[hsl] = make_int4(t0, t1, (int32_t)i2, (int32_t)j2);
+      }
+      i2 = j2;
+    }
+  }
+
   // ---- upload
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) { delete ix; return cuda_fail(e, "cudaSetDevice"); }
@@ -196,12 +223,14 @@ int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_in, in
       (rc = upload(sa, 4, &ix->d_blocks[1], &d.sa_pos, &ix->device_bytes)) ||
       (rc = upload(sa_walk, 4, &ix->d_blocks[2], &d.sa_walk, &ix->device_bytes)) ||
       (rc = upload(qva, 0, &ix->d_blocks[3], &d.qva, &ix->device_bytes)) ||
+      (rc = upload(bg_tab, 0, &ix->d_blocks[6], &d.bg_tab, &ix->device_bytes)) ||
       (rc = upload(sid_at, 0, &ix->d_blocks[4], &d.sid_at, &ix->device_bytes)) ||
       (rc = upload(std::vector<float>((size_t)vocab_size, 0.f), 0, &ix->d_blocks[5], &d.idf, &ix->device_bytes)) ||
       (rc = set_idf_stats(ix, sfreq_global ? sfreq_global : ix->sfreq.data(), n_sent_global > 0 ? n_sent_global : n_keep))) {
     free_index(ix);
     return rc;
   }
+  d.bg_mask = bg_mask;
   d.vocab_size = vocab_size;
   d.max_tokens = max_tokens;
   d.n_suf = n_suf;

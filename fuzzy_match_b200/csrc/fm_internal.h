@@ -22,6 +22,9 @@ namespace fm {
 //                         every word w). The signature gives an upper bound on the coverage without
 //                         touching the sentence.
 // qva      int32[V+1]     first-word bucket table (reference _quickVocabAccess).
+// bg_tab   int4[pow2]     bigram directory: open-addressing table (word0, word1) -> [lo, hi) of the suffixes
+//                         that start with that bigram, so the two widest narrowing steps of every chain
+//                         (whole array -> first word -> bigram) cost one probe instead of ~40.
 // sid_at   int32[n_buf/4] local sentence id, stored at (sentence start / 4); only read for survivors.
 // idf      float[V]       logf(N / sfreq[w]) computed on the host with glibc (0 for unseen words).
 struct IndexDev {
@@ -29,6 +32,8 @@ struct IndexDev {
   const int32_t* sa_pos;
   const int4* sa_walk;
   const int32_t* qva;
+  const int4* bg_tab;
+  uint32_t bg_mask;
   const int32_t* sid_at;
   const float* idf;
   int32_t vocab_size;
@@ -47,6 +52,12 @@ static const int kQValid = 1;
 
 // word -> signature bit (must be identical on host and device)
 __host__ __device__ inline unsigned sig_bit(int w) { return ((unsigned)w * 0x9E3779B1u) >> 26; }
+// bigram -> slot hash (host build and device lookup)
+__host__ __device__ inline uint32_t bigram_hash(int w0, int w1) {
+  unsigned long long k = ((unsigned long long)(unsigned)w0 << 32) | (unsigned)w1;
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return (uint32_t)k;
+}
 
 struct SurvRec {  // one distinct (query, sentence) that passed both rejection bounds
   int32_t q;

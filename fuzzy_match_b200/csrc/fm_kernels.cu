@@ -260,16 +260,32 @@ __global__ void __launch_bounds__(256) fm_search_kernel(IndexDev ix, BatchDev b)
   int lo = 0, hi = 0, len = 0;
   if (live) {
     const int t0 = pat[it];
-    if (t0 >= 2) { lo = ix.qva[t0]; hi = ix.qva[t0 + 1]; }
-    len = hi > lo ? 1 : 0;
-    live = len == 1;
+    if (it + 1 < p) {
+      // whole array -> first word -> bigram in one probe of the bigram directory. A chain that does
+      // not reach length 2 registers nothing (src/fuzzy_match.cc:546-550), so length 1 is skipped.
+      const int t1 = pat[it + 1];
+      if (t0 >= 2 && t1 >= 2) {
+        uint32_t h = bigram_hash(t0, t1) & ix.bg_mask;
+        for (;;) {
+          const int4 e = __ldg(ix.bg_tab + h);
+          if (e.x == t0 && e.y == t1) { lo = e.z; hi = e.w; len = 2; break; }
+          if (e.x == -1) break;
+          h = (h + 1) & ix.bg_mask;
+        }
+      }
+      live = len == 2;
+    } else {
+      if (t0 >= 2) { lo = ix.qva[t0]; hi = ix.qva[t0 + 1]; }
+      len = hi > lo ? 1 : 0;
+      live = len == 1;
+    }
   }
   // p == 1: the unigram range itself is registered (src/fuzzy_match.cc:484-493)
   {
     const bool uni = live && p == 1 && 1 >= ml;
     emit_slices(b, lane, q, p, uni ? 1 : 0, lo, uni ? hi - lo : 0, 1, 0, 0, 0);
   }
-  bool extending = live && it + 1 < p;
+  bool extending = live && it + len < p;
   while (__any_sync(FULL, extending)) {
     int n = 0, beg0 = 0, sz0 = 0, beg1 = 0, sz1 = 0;
     if (extending) {
