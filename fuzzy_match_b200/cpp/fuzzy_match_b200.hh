@@ -1,0 +1,173 @@
+// fuzzy_match_b200.hh -- header-only C++ adapter: the reference's fuzzy::FuzzyMatch interface for the
+// pre-tokenised path, on top of the C ABI (include/fuzzy_match_b200.h, libfm_b200.so).
+//
+// Mirrors include/fuzzy/fuzzy_match.hh:17-119 of SYSTRAN/fuzzy-match: same class, nested Match,
+// EditCosts (include/fuzzy/costs.hh:7-29), ContrastReduce, Tokens, same argument order, defaults and
+// return conventions (match() APPENDS to `matches` and returns matches.size() > 0; empty or
+// over-long patterns return false; add_tm silently ignores empty / over-long sentences), so a caller
+// of add_tm(id, Tokens) / sort() / match(Tokens, ...) recompiles against this header unchanged.
+// The vocabulary (string -> id; reference src/vocab_indexer.cc) lives here on the host; everything
+// match() computes runs on the GPU. Extra: match_batch() feeds many patterns through one launch
+// sequence. The tokenizer front-end (match(std::string), penalty tokens) is out of scope.
+//
+// Define FUZZY_MATCH_B200_NAMESPACE before including to put the classes elsewhere than `fuzzy`.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/fuzzy_match_b200.h"
+
+#ifndef FUZZY_MATCH_B200_NAMESPACE
+#define FUZZY_MATCH_B200_NAMESPACE fuzzy
+#endif
+
+namespace FUZZY_MATCH_B200_NAMESPACE {
+
+typedef std::vector<std::string> Tokens;
+constexpr size_t DEFAULT_MAX_TOKENS_IN_PATTERN = 300;  // include/fuzzy/suffix_array_index.hh:15
+
+enum class ContrastReduce { MEAN, MAX };
+
+struct EditCosts {
+  const float insert_cost;
+  const float delete_cost;
+  const float replace_cost;
+  EditCosts() : insert_cost(1), delete_cost(1), replace_cost(1) {}
+  EditCosts(float insert_cost, float delete_cost, float replace_cost)
+      : insert_cost(insert_cost), delete_cost(delete_cost), replace_cost(replace_cost) {}
+};
+
+class FuzzyMatch {
+public:
+  enum penalty_token { pt_none = 0, pt_tag = 1 << 0, pt_pct = 1 << 1, pt_sep = 1 << 2, pt_jnr = 1 << 3, pt_nbr = 1 << 4, pt_cas = 1 << 5 };
+
+  struct Match {
+    Match(const unsigned* seq, int length) : length(length), s(seq) {}
+    Match() {}
+    float score = 0;
+    float penalty = 0;
+    int max_subseq = 0;
+    unsigned s_id = 0;
+    std::string id;
+    int length = 0;
+    const unsigned* s = nullptr;  // borrowed from the index, valid for the life of the FuzzyMatch
+  };
+
+  explicit FuzzyMatch(int pt = penalty_token::pt_none, size_t max_tokens_in_pattern = DEFAULT_MAX_TOKENS_IN_PATTERN, int device = 0)
+      : _max_tokens(max_tokens_in_pattern), _device(device) {
+    if (pt != pt_none) throw std::invalid_argument("penalty tokens need the tokenizer front-end (out of scope)");
+    _forms.push_back(std::string(1, '\0'));  // 0 = sentence separator, 1 = unknown (src/vocab_indexer.cc:10-19)
+    _forms.push_back("\xEF\xBD\x9Funk\xEF\xBD\xA0");
+  }
+  ~FuzzyMatch() { fm_index_destroy(_index); }
+  FuzzyMatch(const FuzzyMatch&) = delete;
+  FuzzyMatch& operator=(const FuzzyMatch&) = delete;
+
+  // add_tm(id, Tokens, sort): src/fuzzy_match.cc:196-203 + src/suffix_array_index.cc:10-30
+  bool add_tm(const std::string& id, const Tokens& norm, bool sort = true) {
+    if (!norm.empty() && norm.size() <= _max_tokens) {
+      for (const auto& w : norm) _tm_tokens.push_back((int32_t)add_word(w));
+      _tm_off.push_back((int64_t)_tm_tokens.size());
+      _ids.push_back(id);
+      _dirty = true;
+    }
+    if (sort) this->sort();
+    return true;
+  }
+
+  void sort() {
+    if (!_dirty && _index) return;
+    fm_index_destroy(_index);
+    _index = nullptr;
+    check(fm_index_create(_tm_tokens.data(), _tm_off.data(), (int64_t)_tm_off.size() - 1, (int32_t)_forms.size(),
+                          (int32_t)_max_tokens, nullptr, 0, 0, _device, &_index));
+    _dirty = false;
+  }
+
+  size_t max_tokens_in_pattern() const { return _max_tokens; }
+
+  // match(Tokens, ...): include/fuzzy/fuzzy_match.hh:59-69
+  bool match(const Tokens& pattern, float fuzzy, unsigned number_of_matches, std::vector<Match>& matches,
+             int min_subseq_length = 2, float min_subseq_ratio = 0, float vocab_idf_penalty = 0,
+             const EditCosts& edit_costs = EditCosts(), float contrastive_factor = 0,
+             ContrastReduce reduce = ContrastReduce::MEAN, int contrast_buffer = -1, bool no_perfect = false) const {
+    std::vector<std::vector<Match>> out(1);
+    match_batch({pattern}, fuzzy, number_of_matches, out, min_subseq_length, min_subseq_ratio, vocab_idf_penalty, edit_costs,
+                contrastive_factor, reduce, contrast_buffer, no_perfect);
+    matches.insert(matches.end(), out[0].begin(), out[0].end());
+    return matches.size() > 0;
+  }
+
+  // The batched front-end: out[i] receives the matches of patterns[i] (appended).
+  void match_batch(const std::vector<Tokens>& patterns, float fuzzy, unsigned number_of_matches,
+                   std::vector<std::vector<Match>>& out, int min_subseq_length = 2, float min_subseq_ratio = 0,
+                   float vocab_idf_penalty = 0, const EditCosts& edit_costs = EditCosts(), float contrastive_factor = 0,
+                   ContrastReduce reduce = ContrastReduce::MEAN, int contrast_buffer = -1, bool no_perfect = false) const {
+    if (!_index || _dirty) throw std::logic_error("FuzzyMatch::sort() must be called before match()");
+    std::vector<int32_t> q_tok;
+    std::vector<int64_t> q_off(1, 0);
+    for (const auto& p : patterns) {
+      for (const auto& w : p) {
+        auto it = _form2index.find(w);
+        q_tok.push_back(it == _form2index.end() ? 1 : (int32_t)it->second);  // VOCAB_UNK
+      }
+      q_off.push_back((int64_t)q_tok.size());
+    }
+    fm_params prm;
+    prm.fuzzy = fuzzy; prm.number_of_matches = (int32_t)number_of_matches; prm.no_perfect = no_perfect;
+    prm.min_subseq_length = min_subseq_length; prm.min_subseq_ratio = min_subseq_ratio; prm.vocab_idf_penalty = vocab_idf_penalty;
+    prm.insert_cost = edit_costs.insert_cost; prm.delete_cost = edit_costs.delete_cost; prm.replace_cost = edit_costs.replace_cost;
+    prm.contrastive_factor = contrastive_factor; prm.contrast_reduce = reduce == ContrastReduce::MAX; prm.contrast_buffer = contrast_buffer;
+    const int64_t n_q = (int64_t)patterns.size();
+    int64_t cap = number_of_matches > 0 ? number_of_matches : 64;
+    std::vector<fm_match> res;
+    std::vector<int32_t> cnt((size_t)n_q);
+    for (;;) {
+      res.assign((size_t)(n_q * cap), fm_match());
+      check(fm_match_batch(_index, q_tok.data(), q_off.data(), n_q, &prm, cap, res.data(), cnt.data()));
+      int64_t mx = 0;
+      for (auto c : cnt) mx = c > mx ? c : mx;
+      if (mx <= cap) break;
+      cap = mx;  // number_of_matches == 0 returns everything
+    }
+    out.resize((size_t)n_q);
+    for (int64_t q = 0; q < n_q; q++)
+      for (int32_t k = 0; k < cnt[q]; k++) {
+        const fm_match& r = res[(size_t)(q * cap + k)];
+        const int32_t* toks = nullptr;
+        int32_t len = 0;
+        check(fm_index_sentence(_index, r.s_id, &toks, &len));
+        Match m(reinterpret_cast<const unsigned*>(toks), r.length);
+        m.score = r.score; m.penalty = r.penalty; m.max_subseq = r.max_subseq; m.s_id = r.s_id; m.id = _ids[r.s_id];
+        out[(size_t)q].push_back(m);
+      }
+  }
+
+private:
+  unsigned add_word(const std::string& w) {
+    auto it = _form2index.find(w);
+    if (it != _form2index.end()) return it->second;
+    const unsigned id = (unsigned)_forms.size();
+    _form2index.emplace(w, id);
+    _forms.push_back(w);
+    return id;
+  }
+  static void check(int rc) {
+    if (rc != FM_OK) throw std::runtime_error(std::string("fuzzy_match_b200: ") + fm_last_error());
+  }
+
+  size_t _max_tokens;
+  int _device;
+  bool _dirty = true;
+  fm_index* _index = nullptr;
+  std::vector<std::string> _forms;
+  std::unordered_map<std::string, unsigned> _form2index;
+  std::vector<std::string> _ids;
+  std::vector<int32_t> _tm_tokens;
+  std::vector<int64_t> _tm_off = std::vector<int64_t>(1, 0);
+};
+
+}  // namespace FUZZY_MATCH_B200_NAMESPACE

@@ -224,3 +224,17 @@ def test_device_resident_api_matches_host_api(medium):
     got = d_out.cpu().numpy().view(capi.MATCH_DTYPE).reshape(n_q, cap)
     for i in range(n_q):
         assert got[i, :cnt[i]].tobytes() == out[i, :cnt[i]].tobytes()
+
+
+def test_cpp_adapter_runs_reference_gtests():
+    """tests/cpp/test_adapter.cc: the reference's Tokens-API gtest cases against the C++ adapter
+    (fuzzy_match_b200/cpp/fuzzy_match_b200.hh) on top of the C ABI."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "test_adapter")
+    if not os.path.exists(exe):
+        import __graft_entry__ as g
+        g.build()
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "all adapter tests passed" in out.stdout, out.stdout + out.stderr
