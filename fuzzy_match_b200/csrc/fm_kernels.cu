@@ -14,6 +14,7 @@
 // result is written with __fadd_rn/__fmul_rn/__fdiv_rn in the reference's evaluation order so no
 // FMA contraction or reassociation can change a bit (the file is also compiled with -fmad=false).
 #include <cfloat>
+#include <cstdlib>
 
 #include "fm_internal.h"
 
@@ -629,10 +630,95 @@ __device__ void warp_edit_distance(const int32_t* s_sent, int s, const int32_t* 
   __syncwarp();
 }
 
-// One warp per surviving (query, sentence): Costs (include/fuzzy/costs.hh:54-57), idf weight
-// (src/fuzzy_match.cc:591) and the full edit distance without upper bound; writes the record at the
-// candidate's slot inside its query group.
-__global__ void __launch_bounds__(256) fm_score_kernel(IndexDev ix, BatchDev b, Params pr, int stride) {
+// Same recurrence for short patterns (p <= 32), one THREAD per pair: the whole DP row, the pattern
+// and the IDF penalties live in registers (fully unrolled over the 32 possible columns), no
+// shuffles and no idle lanes -- ~30x fewer issue slots per pair than the warp wavefront, which
+// remains the path for p > 32. Identical float operations in identical order.
+template <bool IDF>
+__device__ __forceinline__ void thread_edit_distance(const int32_t* __restrict__ sent, int s, const int32_t* __restrict__ pat,
+                                                     int p, const float* __restrict__ idf, float idf_weight, float delw,
+                                                     float insw, float repw, float& C_out, float& K_out) {
+  int pt[32];
+  float pn[32], row[32];
+#pragma unroll
+  for (int j = 0; j < 32; j++) {
+    pt[j] = j < p ? __ldg(pat + j) : -1;
+    pn[j] = (IDF && j < p) ? __fmul_rn(__ldg(idf + pt[j]), idf_weight) : 0.f;
+  }
+  float v = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; j++) {
+    if (j < p) v = IDF ? __fadd_rn(__fadd_rn(v, insw), pn[j]) : __fadd_rn(v, insw);
+    row[j] = v;
+  }
+  float col0 = 0.f, K = -FLT_MAX;
+  for (int i = 0; i < s; i++) {
+    const int tok = __ldg(sent + i);
+    float diag = col0;
+    col0 = __fadd_rn(col0, delw);
+    float left = col0, rmin = FLT_MAX;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+      if (j < p) {
+        const float up = row[j];
+        const float a = __fadd_rn(up, delw);
+        const float bb = IDF ? __fadd_rn(__fadd_rn(left, insw), pn[j]) : __fadd_rn(left, insw);
+        const float diff = (tok != pt[j]) ? (IDF ? __fadd_rn(repw, pn[j]) : repw) : 0.f;
+        const float cc = __fadd_rn(diag, diff);
+        const float d = fminf(fminf(a, bb), cc);
+        row[j] = d;
+        diag = up;
+        left = d;
+        rmin = fminf(rmin, d);
+      }
+    }
+    K = fmaxf(K, rmin);
+  }
+  float C = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; j++)
+    if (j == p - 1) C = row[j];
+  C_out = C;
+  K_out = K;
+}
+
+__device__ __forceinline__ void write_record(const IndexDev& ix, const BatchDev& b, const SurvRec& sr, int slen, float C, float K) {
+  fm_record r;
+  r.s_id = (uint32_t)ix.sid_at[sr.start >> 2] + ix.sid_base;
+  r.longest_match = (int32_t)b.hlm[sr.hslot];
+  r.length = slen;
+  r.cost = C;
+  r.rowmin_max = K;
+  r.reserved[0] = sr.start;
+  r.reserved[1] = 0;
+  r.reserved[2] = 0;
+  b.rec[b.q_base[sr.q] + sr.j] = r;
+}
+
+// One thread per surviving (query, sentence) with p <= 32.
+template <bool IDF>
+__global__ void __launch_bounds__(128) fm_score_short_kernel(IndexDev ix, BatchDev b, Params pr) {
+  const long long n = min((long long)b.ctr->n_surv, (long long)b.surv_cap);
+  if (b.ctr->overflow) return;
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n) return;
+  const SurvRec sr = b.surv[w];
+  const int slen = b.surv_len[w];
+  const QMeta qm = b.qmeta[sr.q];
+  const int p = qm.x;
+  if (p > 32) return;
+  const float wdiff = __fdiv_rn(100.f, normalizer(p, slen, pr));
+  const float idf_weight = __fdiv_rn(__fmul_rn(wdiff, pr.idf_penalty), pr.idf_penalty != 0.f ? ix.idf_max : 0.01f);
+  float C, K;
+  thread_edit_distance<IDF>(ix.tok + sr.start, slen, b.pat + qm.z, p, ix.idf, idf_weight, __fmul_rn(pr.del, wdiff),
+                            __fmul_rn(pr.ins, wdiff), __fmul_rn(pr.rep, wdiff), C, K);
+  write_record(ix, b, sr, slen, C, K);
+}
+
+// One warp per surviving (query, sentence) with p > 32: Costs (include/fuzzy/costs.hh:54-57), idf
+// weight (src/fuzzy_match.cc:591) and the full edit distance without upper bound; writes the record
+// at the candidate's slot inside its query group.
+__global__ void __launch_bounds__(256) fm_score_kernel(IndexDev ix, BatchDev b, Params pr, int stride, int min_p) {
   extern __shared__ int smem[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -648,6 +734,7 @@ __global__ void __launch_bounds__(256) fm_score_kernel(IndexDev ix, BatchDev b, 
     const int slen = b.surv_len[w];
     const QMeta qm = b.qmeta[sr.q];
     const int p = qm.x;
+    if (p < min_p) continue;  // short patterns are scored by fm_score_short_kernel
     const float norm = normalizer(p, slen, pr);
     const float wdiff = __fdiv_rn(100.f, norm);
     const float idf_weight = __fdiv_rn(__fmul_rn(wdiff, pr.idf_penalty), pr.idf_penalty != 0.f ? ix.idf_max : 0.01f);
@@ -661,18 +748,7 @@ __global__ void __launch_bounds__(256) fm_score_kernel(IndexDev ix, BatchDev b, 
     float C, K;
     warp_edit_distance(s_sent, slen, s_pat, p, s_pen, s_up, __fmul_rn(pr.del, wdiff), __fmul_rn(pr.ins, wdiff),
                        __fmul_rn(pr.rep, wdiff), C, K);
-    if (lane == 0) {
-      fm_record r;
-      r.s_id = (uint32_t)ix.sid_at[sr.start >> 2] + ix.sid_base;
-      r.longest_match = (int32_t)b.hlm[sr.hslot];
-      r.length = slen;
-      r.cost = C;
-      r.rowmin_max = K;
-      r.reserved[0] = sr.start;
-      r.reserved[1] = 0;
-      r.reserved[2] = 0;
-      b.rec[b.q_base[sr.q] + sr.j] = r;
-    }
+    if (lane == 0) write_record(ix, b, sr, slen, C, K);
   }
 }
 
@@ -975,7 +1051,14 @@ void launch_score(const IndexDev& ix, const BatchDev& b, const Params& p, int sm
     cudaFuncSetAttribute(fm_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
-  fm_score_kernel<<<sm_count * 4, 256, smem, st>>>(ix, b, p, stride);
+  // FM_SCORE_WARP_ONLY=1 forces every pair through the warp wavefront (tests exercise both paths)
+  static const bool warp_only = getenv("FM_SCORE_WARP_ONLY") != nullptr;
+  if (!warp_only) {
+    const int grid = (int)((b.surv_cap + 127) / 128);
+    if (p.idf_penalty != 0.f) fm_score_short_kernel<true><<<grid, 128, 0, st>>>(ix, b, p);
+    else fm_score_short_kernel<false><<<grid, 128, 0, st>>>(ix, b, p);
+  }
+  fm_score_kernel<<<sm_count * 4, 256, smem, st>>>(ix, b, p, stride, warp_only ? 0 : 33);
 }
 void launch_replay(const IndexDev&, const fm_record* rec, const int32_t* q_cnt, const int32_t* q_base, float* heapbuf,
                    unsigned long long* sort_key, int32_t* sort_idx, int32_t* acc_cnt, const int32_t* q_off, int32_t n_q,
