@@ -71,7 +71,8 @@ struct Counters {
   unsigned int n_surv;
   unsigned int overflow;  // bit0 slices, bit1 survivors, bit2 span index
   unsigned int n_matches;
-  unsigned int pad[3];
+  unsigned int n_heavy;  // queries with more than 32 scored candidates
+  unsigned int pad[2];
 };
 static const int kElemBits = 38;
 
@@ -151,7 +152,7 @@ struct Workspace {
   unsigned int* hlm = nullptr;
   SurvRec* surv = nullptr;
   uint16_t* surv_len = nullptr;
-  int32_t *q_cnt = nullptr, *q_base = nullptr, *acc_cnt = nullptr;
+  int32_t *q_cnt = nullptr, *q_base = nullptr, *acc_cnt = nullptr, *heavy_q = nullptr, *m_heavy = nullptr;
   fm_record* rec = nullptr;
   float* heapbuf = nullptr;
   unsigned long long *sort_key = nullptr, *m_key = nullptr;
@@ -215,8 +216,9 @@ void launch_gather(const IndexDev& ix, const BatchDev& b, const Params& p, int s
 void launch_scan(const int32_t* in, int32_t* out, int32_t n, cudaStream_t st);
 void launch_score(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st);
 void launch_replay(const IndexDev& ix, const fm_record* rec, const int32_t* q_cnt, const int32_t* q_base, float* heapbuf,
-                   unsigned long long* sort_key, int32_t* sort_idx, int32_t* acc_cnt, const int32_t* q_off, int32_t n_q,
-                   const Params& p, int64_t cap, fm_match* out, int32_t* out_count, Counters* ctr, cudaStream_t st);
+                   unsigned long long* sort_key, int32_t* sort_idx, int32_t* acc_cnt, int32_t* heavy_q, const int32_t* q_off,
+                   int32_t n_q, const Params& p, int64_t cap, fm_match* out, int32_t* out_count, Counters* ctr, int sm_count,
+                   cudaStream_t st);
 void launch_contrast(const IndexDev& ix, fm_record* rec, const int32_t* q_base, const int32_t* sort_idx,
                      const int32_t* acc_cnt, int32_t n_q, const Params& p, int64_t cap, fm_match* out, int32_t* out_count,
                      Counters* ctr, int sm_count, cudaStream_t st);

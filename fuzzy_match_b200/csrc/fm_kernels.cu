@@ -433,7 +433,7 @@ __device__ __forceinline__ void verify_candidate(const IndexDev& ix, const Batch
 // Stage 2 (the few that pass): queued per warp in shared memory and verified 32 at a time against
 // the sentence tokens, so the expensive path runs with full warps.
 static const int kQueue = 64;
-__global__ void __launch_bounds__(256) fm_gather_kernel(IndexDev ix, BatchDev b, Params pr) {
+__global__ void __launch_bounds__(256, 8) fm_gather_kernel(IndexDev ix, BatchDev b, Params pr) {
   __shared__ int4 s_queue[8][kQueue];
   const int lane = threadIdx.x & 31;
   int4* queue = s_queue[threadIdx.x >> 5];
@@ -757,29 +757,6 @@ __global__ void __launch_bounds__(256) fm_score_kernel(IndexDev ix, BatchDev b, 
 __device__ __forceinline__ unsigned long long order_key(const fm_record& r) {  // lm desc, s_id asc
   return ((unsigned long long)(unsigned)(0x7fffffff - r.longest_match) << 32) | r.s_id;
 }
-// Warp-cooperative ascending sort of (key, idx) pairs in global scratch: bitonic network written with
-// ascending comparators only, so the virtual +inf padding up to the next power of two never moves.
-__device__ void warp_sort_pairs(unsigned long long* keys, int32_t* idx, int n) {
-  const int lane = threadIdx.x & 31;
-  int np = 1;
-  while (np < n) np <<= 1;
-  for (int k = 2; k <= np; k <<= 1) {
-    for (int j = k >> 1, first = 1; j > 0; j >>= 1, first = 0) {
-      for (int i = lane; i < np; i += 32) {
-        const int l = first ? (i ^ (k - 1)) : (i ^ j);
-        if (l > i && l < n) {
-          const unsigned long long a = keys[i], c = keys[l];
-          if (a > c) {
-            keys[i] = c; keys[l] = a;
-            const int t = idx[i]; idx[i] = idx[l]; idx[l] = t;
-          }
-        }
-      }
-      __syncwarp();
-    }
-  }
-}
-
 // Order n <= 32 records held one per lane: rank = number of smaller keys (keys are distinct).
 __device__ __forceinline__ int warp_rank(unsigned long long key, int n) {
   int rank = 0;
@@ -814,54 +791,43 @@ __device__ __forceinline__ fm_match to_match(const fm_record& r, float penalty) 
   return m;
 }
 
-// One warp per query: the candidate loop of src/fuzzy_match.cc:567-611 replayed over the scored
-// records in the reference's order (ngram_matches.cc:20-29: longest match desc, s_id asc). A
-// candidate is dropped where the reference's bounded edit distance would have exited early or
-// exceeded the bound: max(K, C) > bound. Accepted matches are then ordered like the result heap
-// (:25-33, :670-679). The warp sorts and prefetches; lane 0 runs the inherently sequential bound heap.
-// On return idx[0..nacc) lists the accepted records best first (rowmin_max now holds the score).
-__global__ void __launch_bounds__(256) fm_replay_kernel(fm_record* rec, const int32_t* __restrict__ q_cnt,
-                                                        const int32_t* __restrict__ q_base, float* heapbuf,
-                                                        unsigned long long* sort_key, int32_t* sort_idx, int32_t* acc_cnt,
-                                                        const int32_t* __restrict__ q_off, int n_q, Params pr, long long cap,
-                                                        fm_match* out, int32_t* out_count, Counters* ctr) {
-  __shared__ float s_heap[8][64];
-  const int lane = threadIdx.x & 31;
-  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (q >= n_q) return;
-  if (ctr->overflow) return;
-  const int n = q_cnt[q];
-  if (n == 0) {
-    if (lane == 0) {
-      if (pr.contrast > 0.f) acc_cnt[q] = 0;
-      out_count[q] = 0;
+// CTA-cooperative version of warp_sort_pairs (keys/idx in shared or global memory).
+__device__ void block_sort_pairs(unsigned long long* keys, int32_t* idx, int n) {
+  int np = 1;
+  while (np < n) np <<= 1;
+  for (int k = 2; k <= np; k <<= 1) {
+    for (int j = k >> 1, first = 1; j > 0; j >>= 1, first = 0) {
+      for (int i = threadIdx.x; i < np; i += blockDim.x) {
+        const int l = first ? (i ^ (k - 1)) : (i ^ j);
+        if (l > i && l < n) {
+          const unsigned long long a = keys[i], c = keys[l];
+          if (a > c) {
+            keys[i] = c; keys[l] = a;
+            const int t = idx[i]; idx[i] = idx[l]; idx[l] = t;
+          }
+        }
+      }
+      __syncthreads();
     }
-    return;
   }
-  const int p = q_off[q + 1] - q_off[q];
-  const int base = q_base[q];
-  fm_record* seg = rec + base;
-  unsigned long long* keys = sort_key + base;
-  int32_t* idx = sort_idx + base;
-  // 1. candidate order
-  if (n <= 32) {
-    const unsigned long long k = lane < n ? order_key(seg[lane]) : ~0ull;
-    const int r = warp_rank(k, n);
-    if (lane < n) idx[r] = lane;
-  } else {
-    for (int i = lane; i < n; i += 32) { keys[i] = order_key(seg[i]); idx[i] = i; }
-    __syncwarp();
-    warp_sort_pairs(keys, idx, n);
-  }
-  __syncwarp();
-  // 2. sequential replay; the bound heap lives in shared memory when it is known to stay small
-  float* heap = (pr.buffer > 0 && pr.buffer <= 62) ? s_heap[threadIdx.x >> 5] : heapbuf + base + q;
+}
+
+// The sequential heart of the candidate loop (src/fuzzy_match.cc:567-611), run by one warp over the
+// records seg[idx[0..n)] given in the reference's order. Lanes prefetch 32 records at a time and
+// hand them to lane 0, which owns the bound heap. A candidate is dropped where the reference's
+// bounded edit distance would have exited early or exceeded the bound: max(K, C) > bound.
+// On return idx[0..nacc) / keys[0..nacc) hold the accepted records and their result keys
+// (score desc, s_id asc; CompareMatch :25-33); rowmin_max of an accepted record now holds its score.
+__device__ int replay_sequence(fm_record* seg, int n, int p, int32_t* idx, unsigned long long* keys, float* heap,
+                               const Params& pr) {
+  const int lane = threadIdx.x & 31;
   int hn = 0, nacc = 0;
   if (lane == 0) heap_push(heap, hn, FLT_MAX);
   for (int c0 = 0; c0 < n; c0 += 32) {
     const int my = c0 + lane < n ? idx[c0 + lane] : 0;
     const fm_record r = seg[my];
     const int m = min(32, n - c0);
+    __syncwarp();
     for (int t = 0; t < m; t++) {
       const float cost = __shfl_sync(FULL, r.cost, t);
       const float kmax = __shfl_sync(FULL, r.rowmin_max, t);
@@ -880,7 +846,7 @@ __global__ void __launch_bounds__(256) fm_replay_kernel(fm_record* rec, const in
             seg[id].reserved[2] = 0;     // contrastive "selected" flag
             const unsigned u = __float_as_uint(score);
             const unsigned ord = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-            keys[nacc] = ((unsigned long long)(~ord) << 32) | sid;  // score desc, s_id asc
+            keys[nacc] = ((unsigned long long)(~ord) << 32) | sid;
             idx[nacc] = id;  // nacc <= c0 + t: this slot has already been consumed
             nacc++;
           }
@@ -889,18 +855,54 @@ __global__ void __launch_bounds__(256) fm_replay_kernel(fm_record* rec, const in
     }
     __syncwarp();
   }
-  nacc = __shfl_sync(FULL, nacc, 0);
-  // 3. result order
-  if (nacc > 1) {
-    if (nacc <= 32) {
-      const unsigned long long k = lane < nacc ? keys[lane] : ~0ull;
-      const int id = lane < nacc ? idx[lane] : 0;
-      const int r = warp_rank(k, nacc);
-      __syncwarp();
-      if (lane < nacc) idx[r] = id;
-    } else {
-      warp_sort_pairs(keys, idx, nacc);
+  return __shfl_sync(FULL, nacc, 0);
+}
+
+// One warp per query with <= 32 scored candidates (the common case): candidate order
+// (ngram_matches.cc:20-29: longest match desc, s_id asc) and result order by register rank sort,
+// top-N output (:670-679). Queries with more candidates are queued for fm_replay_heavy_kernel.
+__global__ void __launch_bounds__(256) fm_replay_kernel(fm_record* rec, const int32_t* __restrict__ q_cnt,
+                                                        const int32_t* __restrict__ q_base, float* heapbuf,
+                                                        unsigned long long* sort_key, int32_t* sort_idx, int32_t* acc_cnt,
+                                                        int32_t* heavy_q, const int32_t* __restrict__ q_off, int n_q, Params pr,
+                                                        long long cap, fm_match* out, int32_t* out_count, Counters* ctr) {
+  __shared__ float s_heap[8][64];
+  const int lane = threadIdx.x & 31;
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= n_q) return;
+  const int n = q_cnt[q];
+  if (n == 0 || n > 32) {
+    if (lane == 0) {
+      if (ctr->overflow) return;
+      if (n == 0) {
+        if (pr.contrast > 0.f) acc_cnt[q] = 0;
+        out_count[q] = 0;
+      } else {
+        heavy_q[atomicAdd(&ctr->n_heavy, 1u)] = q;
+      }
     }
+    return;
+  }
+  if (ctr->overflow) return;
+  const int p = q_off[q + 1] - q_off[q];
+  const int base = q_base[q];
+  fm_record* seg = rec + base;
+  unsigned long long* keys = sort_key + base;
+  int32_t* idx = sort_idx + base;
+  {
+    const unsigned long long k = lane < n ? order_key(seg[lane]) : ~0ull;
+    const int r = warp_rank(k, n);
+    if (lane < n) idx[r] = lane;
+  }
+  __syncwarp();
+  float* heap = (pr.buffer > 0 && pr.buffer <= 62) ? s_heap[threadIdx.x >> 5] : heapbuf + base + q;
+  const int nacc = replay_sequence(seg, n, p, idx, keys, heap, pr);
+  if (nacc > 1) {
+    const unsigned long long k = lane < nacc ? keys[lane] : ~0ull;
+    const int id = lane < nacc ? idx[lane] : 0;
+    const int r = warp_rank(k, nacc);
+    __syncwarp();
+    if (lane < nacc) idx[r] = id;
     __syncwarp();
   }
   if (pr.contrast > 0.f) {
@@ -912,6 +914,57 @@ __global__ void __launch_bounds__(256) fm_replay_kernel(fm_record* rec, const in
   if (lane == 0) {
     out_count[q] = want;
     if (want) atomicAdd(&ctr->n_matches, (unsigned)want);
+  }
+}
+
+// One CTA per query with more than 32 scored candidates: CTA-wide bitonic sorts (in shared memory up
+// to kHeavySmem candidates), warp 0 runs the sequential replay.
+static const int kHeavySmem = 4096;
+__global__ void __launch_bounds__(256) fm_replay_heavy_kernel(fm_record* rec, const int32_t* __restrict__ q_cnt,
+                                                              const int32_t* __restrict__ q_base, float* heapbuf,
+                                                              unsigned long long* sort_key, int32_t* sort_idx, int32_t* acc_cnt,
+                                                              const int32_t* __restrict__ heavy_q,
+                                                              const int32_t* __restrict__ q_off, Params pr, long long cap,
+                                                              fm_match* out, int32_t* out_count, Counters* ctr) {
+  extern __shared__ unsigned long long s_dyn[];
+  unsigned long long* s_keys = s_dyn;
+  int32_t* s_idx = reinterpret_cast<int32_t*>(s_dyn + kHeavySmem);
+  float* s_heap = reinterpret_cast<float*>(s_idx + kHeavySmem);
+  __shared__ int s_nacc;
+  if (ctr->overflow) return;
+  const int n_heavy = (int)ctr->n_heavy;
+  for (int h = blockIdx.x; h < n_heavy; h += gridDim.x) {
+    const int q = heavy_q[h];
+    const int n = q_cnt[q];
+    const int p = q_off[q + 1] - q_off[q];
+    const int base = q_base[q];
+    fm_record* seg = rec + base;
+    const bool in_smem = n <= kHeavySmem;
+    unsigned long long* keys = in_smem ? s_keys : sort_key + base;
+    int32_t* idx = in_smem ? s_idx : sort_idx + base;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { keys[i] = order_key(seg[i]); idx[i] = i; }
+    __syncthreads();
+    block_sort_pairs(keys, idx, n);
+    if (threadIdx.x < 32) {
+      float* heap = (pr.buffer > 0 && pr.buffer <= 62) ? s_heap : heapbuf + base + q;
+      const int nacc = replay_sequence(seg, n, p, idx, keys, heap, pr);
+      if (threadIdx.x == 0) s_nacc = nacc;
+    }
+    __syncthreads();
+    const int nacc = s_nacc;
+    block_sort_pairs(keys, idx, nacc);
+    if (pr.contrast > 0.f) {
+      for (int i = threadIdx.x; i < nacc; i += blockDim.x) sort_idx[base + i] = idx[i];
+      if (threadIdx.x == 0) acc_cnt[q] = nacc;
+    } else {
+      const int want = pr.n_matches == 0 ? nacc : min(nacc, pr.n_matches);
+      for (int k = threadIdx.x; k < want && k < cap; k += blockDim.x) out[(long long)q * cap + k] = to_match(seg[idx[k]], 0.f);
+      if (threadIdx.x == 0) {
+        out_count[q] = want;
+        if (want) atomicAdd(&ctr->n_matches, (unsigned)want);
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -1060,12 +1113,21 @@ void launch_score(const IndexDev& ix, const BatchDev& b, const Params& p, int sm
   }
   fm_score_kernel<<<sm_count * 4, 256, smem, st>>>(ix, b, p, stride, warp_only ? 0 : 33);
 }
-void launch_replay(const IndexDev&, const fm_record* rec, const int32_t* q_cnt, const int32_t* q_base, float* heapbuf,
-                   unsigned long long* sort_key, int32_t* sort_idx, int32_t* acc_cnt, const int32_t* q_off, int32_t n_q,
-                   const Params& p, int64_t cap, fm_match* out, int32_t* out_count, Counters* ctr, cudaStream_t st) {
+void launch_replay(const IndexDev& ix, const fm_record* rec, const int32_t* q_cnt, const int32_t* q_base, float* heapbuf,
+                   unsigned long long* sort_key, int32_t* sort_idx, int32_t* acc_cnt, int32_t* heavy_q, const int32_t* q_off,
+                   int32_t n_q, const Params& p, int64_t cap, fm_match* out, int32_t* out_count, Counters* ctr, int sm_count,
+                   cudaStream_t st) {
   const int grid = (n_q + 7) / 8;
   fm_replay_kernel<<<grid, 256, 0, st>>>(const_cast<fm_record*>(rec), q_cnt, q_base, heapbuf, sort_key, sort_idx, acc_cnt,
-                                         q_off, n_q, p, (long long)cap, out, out_count, ctr);
+                                         heavy_q, q_off, n_q, p, (long long)cap, out, out_count, ctr);
+  const size_t smem = (size_t)kHeavySmem * 12 + 64 * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(fm_replay_heavy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_done = true;
+  }
+  fm_replay_heavy_kernel<<<sm_count * 2, 256, smem, st>>>(const_cast<fm_record*>(rec), q_cnt, q_base, heapbuf, sort_key, sort_idx,
+                                                          acc_cnt, heavy_q, q_off, p, (long long)cap, out, out_count, ctr);
 }
 void launch_contrast(const IndexDev& ix, fm_record* rec, const int32_t* q_base, const int32_t* sort_idx,
                      const int32_t* acc_cnt, int32_t n_q, const Params& p, int64_t cap, fm_match* out, int32_t* out_count, Counters* ctr, int sm_count,
