@@ -212,6 +212,36 @@ int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_in, in
     }
   }
 
+  // ---- trigram directory: (slot of the bigram in bg_tab, word2) -> suffix-array range
+  std::vector<int4> tg_tab;
+  uint32_t tg_mask = 0;
+  {
+    const int32_t* tok = ix->h_tok.data();
+    auto is_tri = [&](int64_t k) { return tok[sa[k] + 1] != 0 && tok[sa[k] + 2] != 0; };
+    auto same_tri = [&](int64_t a, int64_t b2) {
+      return tok[sa[a]] == tok[sa[b2]] && tok[sa[a] + 1] == tok[sa[b2] + 1] && tok[sa[a] + 2] == tok[sa[b2] + 2];
+    };
+    int64_t n_tg = 0;
+    for (int64_t k = 0; k < n_suf; k++)
+      if (is_tri(k) && (k == 0 || !same_tri(k - 1, k))) n_tg++;
+    uint64_t cap = 1024;
+    while (cap < (uint64_t)n_tg * 2) cap <<= 1;
+    tg_mask = (uint32_t)(cap - 1);
+    tg_tab.assign((size_t)cap, make_int4(-1, -1, 0, 0));
+    for (int64_t k = 0; k < n_suf;) {
+      int64_t j2 = k + 1;
+      if (!is_tri(k)) { k = j2; continue; }
+      while (j2 < n_suf && same_tri(k, j2)) j2++;
+      const int32_t t0 = tok[sa[k]], t1 = tok[sa[k] + 1], t2 = tok[sa[k] + 2];
+      uint32_t bs = bigram_hash(t0, t1) & bg_mask;
+      while (!(bg_tab[bs].x == t0 && bg_tab[bs].y == t1)) bs = (bs + 1) & bg_mask;
+      uint32_t hsl = bigram_hash((int32_t)bs, t2) & tg_mask;
+      while (tg_tab[hsl].x != -1) hsl = (hsl + 1) & tg_mask;
+      tg_tab[hsl] = make_int4((int32_t)bs, t2, (int32_t)k, (int32_t)j2);
+      k = j2;
+    }
+  }
+
   // ---- upload
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) { delete ix; return cuda_fail(e, "cudaSetDevice"); }
@@ -224,6 +254,7 @@ int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_in, in
       (rc = upload(sa_walk, 4, &ix->d_blocks[2], &d.sa_walk, &ix->device_bytes)) ||
       (rc = upload(qva, 0, &ix->d_blocks[3], &d.qva, &ix->device_bytes)) ||
       (rc = upload(bg_tab, 0, &ix->d_blocks[6], &d.bg_tab, &ix->device_bytes)) ||
+      (rc = upload(tg_tab, 0, &ix->d_blocks[7], &d.tg_tab, &ix->device_bytes)) ||
       (rc = upload(sid_at, 0, &ix->d_blocks[4], &d.sid_at, &ix->device_bytes)) ||
       (rc = upload(std::vector<float>((size_t)vocab_size, 0.f), 0, &ix->d_blocks[5], &d.idf, &ix->device_bytes)) ||
       (rc = set_idf_stats(ix, sfreq_global ? sfreq_global : ix->sfreq.data(), n_sent_global > 0 ? n_sent_global : n_keep))) {
@@ -231,6 +262,7 @@ int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_in, in
     return rc;
   }
   d.bg_mask = bg_mask;
+  d.tg_mask = tg_mask;
   d.vocab_size = vocab_size;
   d.max_tokens = max_tokens;
   d.n_suf = n_suf;

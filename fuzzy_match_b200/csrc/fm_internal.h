@@ -21,6 +21,8 @@ namespace fm {
 //                         sentence length, 64-bit word signature of the sentence: bit sig_bit(w) set for
 //                         every word w). The signature gives an upper bound on the coverage without
 //                         touching the sentence.
+// tg_tab   int4[pow2]     trigram directory: (bigram slot, word2) -> [lo, hi); the third narrowing step in
+//                         one more probe (the reference's CLI default ml=3 only ever walks trigram ranges).
 // qva      int32[V+1]     first-word bucket table (reference _quickVocabAccess).
 // bg_tab   int4[pow2]     bigram directory: open-addressing table (word0, word1) -> [lo, hi) of the suffixes
 //                         that start with that bigram, so the two widest narrowing steps of every chain
@@ -34,6 +36,8 @@ struct IndexDev {
   const int32_t* qva;
   const int4* bg_tab;
   uint32_t bg_mask;
+  const int4* tg_tab;
+  uint32_t tg_mask;
   const int32_t* sid_at;
   const float* idf;
   int32_t vocab_size;
@@ -185,7 +189,7 @@ struct Index {
   int64_t n_sent = 0, n_suf = 0, n_buf = 0;
   int64_t device_bytes = 0;
   int32_t vocab_size = 0, max_tokens = 0;
-  void* d_blocks[8] = {};
+  void* d_blocks[12] = {};
   int sm_count = 148;
   // workspaces
   std::mutex mu;

@@ -151,26 +151,58 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
   const int ts = next_pow2(2 * p);
   int2* tbl = b.tbl + 4ll * off;
   __shared__ int2 s_tbl[8][128];
-  int2* wtbl = ts <= 128 ? s_tbl[threadIdx.x >> 5] : tbl;  // small tables are built in shared memory
-  for (int j = lane; j < ts; j += 32) wtbl[j] = make_int2(-1, 0);
-  __syncwarp();
-  if (lane == 0) {
-    int distinct = 0;
-    for (int j = 0; j < p; j++) {
+  __shared__ int s_cnt[8][64];
+  int c_lo = 0, c_hi = 0;  // pattern positions per signature bit (lane, lane + 32); unknown words excluded
+  if (ts <= 128) {
+    // Small pattern (p <= 64): lanes insert their words concurrently into a shared-memory table
+    // (CAS on the key, atomic add on the multiplicity), distinct indices are then handed out in slot
+    // order, and the per-bit position counts come from the table's (word, multiplicity) entries.
+    int2* wtbl = s_tbl[threadIdx.x >> 5];
+    int* cnt = s_cnt[threadIdx.x >> 5];
+    for (int j = lane; j < ts; j += 32) wtbl[j] = make_int2(-1, 0);
+    cnt[lane] = 0;
+    cnt[lane + 32] = 0;
+    __syncwarp();
+    for (int j = lane; j < p; j += 32) {
       const int w = b.pat[off + j];
       int h = hash32((uint32_t)w) & (ts - 1);
-      while (wtbl[h].x != -1 && wtbl[h].x != w) h = (h + 1) & (ts - 1);
-      if (wtbl[h].x == -1) wtbl[h] = make_int2(w, (distinct++) | (1 << 16));
-      else wtbl[h].y += 1 << 16;
+      for (;;) {
+        const int prev = atomicCAS(&wtbl[h].x, -1, w);
+        if (prev == -1 || prev == w) break;
+        h = (h + 1) & (ts - 1);
+      }
+      atomicAdd(&wtbl[h].y, 1 << 16);
     }
-  }
-  __syncwarp();
-  if (ts <= 128)
-    for (int j = lane; j < ts; j += 32) tbl[j] = wtbl[j];
-  // Signature masks: M_l = bits that >= l pattern positions hash to (unknown words excluded).
-  // coverage <= sum_l popc(sig & M_l) (+ weight * popc(sig & M5) for bits with more than 4 positions).
-  {
-    int c_lo = 0, c_hi = 0;
+    __syncwarp();
+    int distinct = 0;
+    for (int j0 = 0; j0 < ts; j0 += 32) {
+      const int2 e = j0 + lane < ts ? wtbl[j0 + lane] : make_int2(-1, 0);
+      const unsigned used = __ballot_sync(FULL, e.x != -1);
+      if (e.x != -1) {
+        const int d = distinct + __popc(used & ((1u << lane) - 1));
+        tbl[j0 + lane] = make_int2(e.x, e.y | d);
+        if (e.x >= 2) atomicAdd(&cnt[sig_bit(e.x)], e.y >> 16);
+      } else if (j0 + lane < ts) {
+        tbl[j0 + lane] = e;
+      }
+      distinct += __popc(used);
+    }
+    __syncwarp();
+    c_lo = cnt[lane];
+    c_hi = cnt[lane + 32];
+  } else {
+    for (int j = lane; j < ts; j += 32) tbl[j] = make_int2(-1, 0);
+    __syncwarp();
+    if (lane == 0) {
+      int distinct = 0;
+      for (int j = 0; j < p; j++) {
+        const int w = b.pat[off + j];
+        int h = hash32((uint32_t)w) & (ts - 1);
+        while (tbl[h].x != -1 && tbl[h].x != w) h = (h + 1) & (ts - 1);
+        if (tbl[h].x == -1) tbl[h] = make_int2(w, (distinct++) | (1 << 16));
+        else tbl[h].y += 1 << 16;
+      }
+    }
     for (int j = 0; j < p; j++) {
       const int w = b.pat[off + j];
       if (w < 2) continue;
@@ -178,6 +210,10 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
       c_lo += bit == (unsigned)lane;
       c_hi += bit == (unsigned)(lane + 32);
     }
+  }
+  // Signature masks: M_l = bits that >= l pattern positions hash to.
+  // coverage <= sum_l popc(sig & M_l) (+ weight * popc(sig & M5) for bits with more than 4 positions).
+  {
     unsigned m[10];
 #pragma unroll
     for (int l = 0; l < 5; l++) {
@@ -208,6 +244,7 @@ __device__ __forceinline__ void note_spans(const BatchDev& b, long long slot, lo
 }
 __device__ __forceinline__ void emit_slices(const BatchDev& b, int lane, int q, int p, int n, int beg0, int sz0, int lm0,
                                             int beg1, int sz1, int lm1) {
+  if (!__any_sync(FULL, n > 0)) return;
   const unsigned long long mine = ((unsigned long long)n << kElemBits) | (unsigned long long)(unsigned)(sz0 + sz1);
   unsigned long long incl = mine;
 #pragma unroll
@@ -259,6 +296,7 @@ __global__ void __launch_bounds__(256) fm_search_kernel(IndexDev ix, BatchDev b)
     live = (m.w & kQValid) != 0;
   }
   int lo = 0, hi = 0, len = 0;
+  uint32_t bslot = 0;  // slot of the chain's bigram in the bigram directory
   if (live) {
     const int t0 = pat[it];
     if (it + 1 < p) {
@@ -269,7 +307,7 @@ __global__ void __launch_bounds__(256) fm_search_kernel(IndexDev ix, BatchDev b)
         uint32_t h = bigram_hash(t0, t1) & ix.bg_mask;
         for (;;) {
           const int4 e = __ldg(ix.bg_tab + h);
-          if (e.x == t0 && e.y == t1) { lo = e.z; hi = e.w; len = 2; break; }
+          if (e.x == t0 && e.y == t1) { lo = e.z; hi = e.w; len = 2; bslot = h; break; }
           if (e.x == -1) break;
           h = (h + 1) & ix.bg_mask;
         }
@@ -292,7 +330,16 @@ __global__ void __launch_bounds__(256) fm_search_kernel(IndexDev ix, BatchDev b)
     if (extending) {
       const int t = pat[it + len];  // token at depth len
       int nlo = lo, nhi = lo;
-      if (t >= 2) {
+      if (t >= 2 && len == 2) {
+        // bigram -> trigram through the trigram directory
+        uint32_t h = bigram_hash((int)bslot, t) & ix.tg_mask;
+        for (;;) {
+          const int4 e = __ldg(ix.tg_tab + h);
+          if (e.x == (int)bslot && e.y == t) { nlo = e.z; nhi = e.w; break; }
+          if (e.x == -1) break;
+          h = (h + 1) & ix.tg_mask;
+        }
+      } else if (t >= 2) {
         int a = lo, e = hi;
         while (a < e) {  // first suffix whose token at depth len is >= t
           const int mid = (int)(((unsigned)a + (unsigned)e) >> 1);
