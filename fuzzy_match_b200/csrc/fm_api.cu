@@ -333,6 +333,61 @@ int fm_index_sentence(const fm_index* index, uint32_t s, const int32_t** tokens,
   return FM_OK;
 }
 
+// One chunk of a host batch in flight on its own workspace / stream.
+struct HostChunk {
+  Workspace* w = nullptr;
+  int64_t q0 = 0, nq = 0, ntok = 0;
+  bool in_flight = false;
+  int launches = 0;
+};
+
+// Enqueue H2D + the whole pipeline + D2H of one chunk; returns without waiting.
+static int launch_host_chunk(Index* ix, HostChunk& c, const int32_t* q_tokens, const int64_t* q_off, const Params& pr, int64_t cap,
+                             fm_match* out, int32_t* out_count) {
+  Workspace* w = c.w;
+  int rc;
+  if ((rc = ensure_queries(w, c.nq, c.ntok, true)) || (rc = ensure_out(w, c.nq, cap)) || (rc = initial_worklists(ix, w, c.nq, c.ntok)))
+    return rc;
+  for (int64_t i = 0; i <= c.nq; i++) w->h_q_off32[i] = (int32_t)(q_off[c.q0 + i] - q_off[c.q0]);
+  cudaStream_t st = w->stream;
+  FM_CUDA(cudaMemcpyAsync(w->d_q_off, w->h_q_off32, (c.nq + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  if (c.ntok) FM_CUDA(cudaMemcpyAsync(w->d_q_tok, q_tokens + q_off[c.q0], c.ntok * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  FM_CUDA(cudaMemsetAsync(w->d_out, 0, c.nq * cap * sizeof(fm_match), st));  // slots past the count read as zero
+  c.launches = 0;
+  if ((rc = launch_shard(ix, w, w->d_q_tok, w->d_q_off, c.nq, c.ntok, pr, st, &c.launches))) return rc;
+  if ((rc = run_replay(ix, w, w->rec, w->q_cnt, w->q_base, w->heapbuf, w->sort_key, w->sort_idx, w->acc_cnt, w->heavy_q, w->d_q_off,
+                       c.nq, pr, cap, w->d_out, w->d_out_count, st, &c.launches)))
+    return rc;
+  FM_CUDA(cudaMemcpyAsync(w->h_ctr, w->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  FM_CUDA(cudaMemcpyAsync(out + c.q0 * cap, w->d_out, c.nq * cap * sizeof(fm_match), cudaMemcpyDeviceToHost, st));
+  FM_CUDA(cudaMemcpyAsync(out_count + c.q0, w->d_out_count, c.nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  c.in_flight = true;
+  return FM_OK;
+}
+
+// Wait for a chunk; if one of its worklists overflowed, regrow and rerun it synchronously.
+static int finish_host_chunk(Index* ix, HostChunk& c, const Params& pr, int64_t cap, fm_match* out, int32_t* out_count) {
+  if (!c.in_flight) return FM_OK;
+  c.in_flight = false;
+  Workspace* w = c.w;
+  cudaStream_t st = w->stream;
+  int retries = 0;
+  for (int attempt = 0;; attempt++) {
+    const int again = sync_and_check(w, st, attempt, &retries);
+    if (again < 0) return -again;
+    if (!again) break;
+    int rc;
+    if ((rc = launch_shard(ix, w, w->d_q_tok, w->d_q_off, c.nq, c.ntok, pr, st, &c.launches))) return rc;
+    if ((rc = run_replay(ix, w, w->rec, w->q_cnt, w->q_base, w->heapbuf, w->sort_key, w->sort_idx, w->acc_cnt, w->heavy_q,
+                         w->d_q_off, c.nq, pr, cap, w->d_out, w->d_out_count, st, &c.launches)))
+      return rc;
+    FM_CUDA(cudaMemcpyAsync(out + c.q0 * cap, w->d_out, c.nq * cap * sizeof(fm_match), cudaMemcpyDeviceToHost, st));
+    FM_CUDA(cudaMemcpyAsync(out_count + c.q0, w->d_out_count, c.nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  }
+  finish_profile(ix, w, c.nq, c.ntok, c.launches, retries);
+  return FM_OK;
+}
+
 int fm_match_batch(fm_index* index, const int32_t* q_tokens, const int64_t* q_off, int64_t n_q, const fm_params* params,
                    int64_t cap, fm_match* out, int32_t* out_count) {
   Index* ix = reinterpret_cast<Index*>(index);
@@ -342,29 +397,38 @@ int fm_match_batch(fm_index* index, const int32_t* q_tokens, const int64_t* q_of
   if ((rc = check_params(params, &pr))) return rc;
   if (n_q == 0) return FM_OK;
   FM_CUDA(cudaSetDevice(ix->device));
-  Workspace* w = acquire(ix);
-  struct Releaser { Index* ix; Workspace* w; ~Releaser() { release(ix, w); } } rel{ix, w};
-  if ((rc = ensure_base(w))) return rc;
-  // chunk so that offsets stay int32 and the workspace stays bounded
-  const int64_t kMaxQ = 1 << 20, kMaxTok = 1 << 25;
+  // The batch is cut into chunks that run on up to kSlots workspaces / streams, so the H2D copy of
+  // one chunk and the D2H copy of another overlap the kernels of a third. Chunks also keep the
+  // offsets int32 and the workspaces bounded.
+  const int kSlots = 3;
+  const int64_t kMaxTok = 1 << 25;
+  // (measured on B200: for 100k-query batches one chunk is fastest -- per-chunk launch and tail costs
+  // outweigh the copy overlap -- so chunking only bounds very large batches unless FM_HOST_CHUNKS asks)
+  static const int n_chunks = getenv("FM_HOST_CHUNKS") ? std::max(1, atoi(getenv("FM_HOST_CHUNKS"))) : 1;
+  const int64_t chunk_q = std::min<int64_t>(1 << 20, std::max<int64_t>(16384, (n_q + n_chunks - 1) / n_chunks));
+  HostChunk slots[kSlots];
+  struct Releaser {
+    Index* ix; HostChunk* s; int n;
+    ~Releaser() { for (int i = 0; i < n; i++) if (s[i].w) { if (s[i].in_flight) cudaStreamSynchronize(s[i].w->stream); release(ix, s[i].w); } }
+  } rel{ix, slots, kSlots};
   int64_t q0 = 0;
-  while (q0 < n_q) {
-    int64_t q1 = std::min(n_q, q0 + kMaxQ);
+  for (int k = 0; q0 < n_q; k++) {
+    int64_t q1 = std::min(n_q, q0 + chunk_q);
     while (q1 > q0 + 1 && q_off[q1] - q_off[q0] > kMaxTok) q1 = q0 + (q1 - q0) / 2;
-    const int64_t nq = q1 - q0, ntok = q_off[q1] - q_off[q0];
+    const int64_t ntok = q_off[q1] - q_off[q0];
     if (ntok < 0 || ntok > (int64_t(1) << 29)) { set_error("bad q_off"); return FM_ERR_INVALID; }
-    if ((rc = ensure_queries(w, nq, ntok, true)) || (rc = ensure_out(w, nq, cap))) return rc;
-    for (int64_t i = 0; i <= nq; i++) w->h_q_off32[i] = (int32_t)(q_off[q0 + i] - q_off[q0]);
-    cudaStream_t st = w->stream;
-    FM_CUDA(cudaMemcpyAsync(w->d_q_off, w->h_q_off32, (nq + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    if (ntok) FM_CUDA(cudaMemcpyAsync(w->d_q_tok, q_tokens + q_off[q0], ntok * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    FM_CUDA(cudaMemsetAsync(w->d_out, 0, nq * cap * sizeof(fm_match), st));
-    if ((rc = match_device(ix, w, w->d_q_tok, w->d_q_off, nq, ntok, pr, cap, w->d_out, w->d_out_count, st))) return rc;
-    FM_CUDA(cudaMemcpyAsync(out + q0 * cap, w->d_out, nq * cap * sizeof(fm_match), cudaMemcpyDeviceToHost, st));
-    FM_CUDA(cudaMemcpyAsync(out_count + q0, w->d_out_count, nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    FM_CUDA(cudaStreamSynchronize(st));
+    HostChunk& c = slots[k % kSlots];
+    if ((rc = finish_host_chunk(ix, c, pr, cap, out, out_count))) return rc;
+    if (!c.w) {
+      c.w = acquire(ix);
+      if ((rc = ensure_base(c.w))) return rc;
+    }
+    c.q0 = q0; c.nq = q1 - q0; c.ntok = ntok;
+    if ((rc = launch_host_chunk(ix, c, q_tokens, q_off, pr, cap, out, out_count))) return rc;
     q0 = q1;
   }
+  for (int i = 0; i < kSlots; i++)
+    if ((rc = finish_host_chunk(ix, slots[i], pr, cap, out, out_count))) return rc;
   return FM_OK;
 }
 
