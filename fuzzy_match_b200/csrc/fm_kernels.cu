@@ -870,35 +870,42 @@ __device__ int replay_sequence(fm_record* seg, int n, int p, int32_t* idx, unsig
   const int lane = threadIdx.x & 31;
   int hn = 0, nacc = 0;
   if (lane == 0) heap_push(heap, hn, FLT_MAX);
+  float bound = FLT_MAX;
   for (int c0 = 0; c0 < n; c0 += 32) {
-    const int my = c0 + lane < n ? idx[c0 + lane] : 0;
+    const bool have = c0 + lane < n;
+    const int my = have ? idx[c0 + lane] : 0;
     const fm_record r = seg[my];
-    const int m = min(32, n - c0);
     __syncwarp();
-    for (int t = 0; t < m; t++) {
+    int pos = 0;  // candidates before pos are done
+    for (;;) {
+      // every lane tests its candidate against the current bound; skipped candidates have no side
+      // effect (src/fuzzy_match.cc:595), so only the first one that passes needs the sequential step
+      const bool pass = have && lane >= pos && !(r.rowmin_max > bound || r.cost > bound) &&
+                        !(pr.no_perfect && r.cost == 0.f && r.length == p);
+      const unsigned bal = __ballot_sync(FULL, pass);
+      if (!bal) break;
+      const int t = __ffs(bal) - 1;
       const float cost = __shfl_sync(FULL, r.cost, t);
-      const float kmax = __shfl_sync(FULL, r.rowmin_max, t);
-      const int len = __shfl_sync(FULL, r.length, t);
       const int id = __shfl_sync(FULL, my, t);
       const unsigned sid = __shfl_sync(FULL, r.s_id, t);
       if (lane == 0) {
-        const float bound = heap[0];
-        if (!(kmax > bound || cost > bound) && !(pr.no_perfect && cost == 0.f && len == p)) {
-          const float score = score_of(cost);
-          heap_push(heap, hn, cost);
-          if (score < pr.fuzzy || (pr.buffer > 0 && hn > pr.buffer)) heap_pop(heap, hn);
-          if (score >= pr.fuzzy) {
-            seg[id].rowmin_max = score;  // slot reused: score
-            seg[id].reserved[1] = 0;     // contrastive accumulator
-            seg[id].reserved[2] = 0;     // contrastive "selected" flag
-            const unsigned u = __float_as_uint(score);
-            const unsigned ord = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-            keys[nacc] = ((unsigned long long)(~ord) << 32) | sid;
-            idx[nacc] = id;  // nacc <= c0 + t: this slot has already been consumed
-            nacc++;
-          }
+        const float score = score_of(cost);
+        heap_push(heap, hn, cost);
+        if (score < pr.fuzzy || (pr.buffer > 0 && hn > pr.buffer)) heap_pop(heap, hn);
+        if (score >= pr.fuzzy) {
+          seg[id].rowmin_max = score;  // slot reused: score
+          seg[id].reserved[1] = 0;     // contrastive accumulator
+          seg[id].reserved[2] = 0;     // contrastive "selected" flag
+          const unsigned u = __float_as_uint(score);
+          const unsigned ord = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+          keys[nacc] = ((unsigned long long)(~ord) << 32) | sid;
+          idx[nacc] = id;  // nacc <= c0 + t: this slot has already been consumed
+          nacc++;
         }
+        bound = heap[0];
       }
+      bound = __shfl_sync(FULL, bound, 0);
+      pos = t + 1;
     }
     __syncwarp();
   }
@@ -964,19 +971,37 @@ __global__ void __launch_bounds__(256) fm_replay_kernel(fm_record* rec, const in
   }
 }
 
-// One CTA per query with more than 32 scored candidates: CTA-wide bitonic sorts (in shared memory up
-// to kHeavySmem candidates), warp 0 runs the sequential replay.
-static const int kHeavySmem = 4096;
+// CTA-cooperative ascending bitonic sort of 64-bit keys (ascending comparators only, so the virtual
+// +inf padding up to the next power of two never moves).
+__device__ void block_sort_keys(unsigned long long* keys, int n) {
+  int np = 1;
+  while (np < n) np <<= 1;
+  for (int k = 2; k <= np; k <<= 1) {
+    for (int j = k >> 1, first = 1; j > 0; j >>= 1, first = 0) {
+      for (int i = threadIdx.x; i < np; i += blockDim.x) {
+        const int l = first ? (i ^ (k - 1)) : (i ^ j);
+        if (l > i && l < n) {
+          const unsigned long long a = keys[i], c = keys[l];
+          if (a > c) { keys[i] = c; keys[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// One CTA per query with more than 32 scored candidates. The candidate order is sorted as ONE packed
+// 64-bit key per record -- (1023 - match length) << 52 | s_id << 20 | record index -- in shared
+// memory (up to kHeavySmem records, else in global scratch); warp 0 then runs the replay.
+static const int kHeavySmem = 24576;
 __global__ void __launch_bounds__(256) fm_replay_heavy_kernel(fm_record* rec, const int32_t* __restrict__ q_cnt,
                                                               const int32_t* __restrict__ q_base, float* heapbuf,
                                                               unsigned long long* sort_key, int32_t* sort_idx, int32_t* acc_cnt,
                                                               const int32_t* __restrict__ heavy_q,
                                                               const int32_t* __restrict__ q_off, Params pr, long long cap,
                                                               fm_match* out, int32_t* out_count, Counters* ctr) {
-  extern __shared__ unsigned long long s_dyn[];
-  unsigned long long* s_keys = s_dyn;
-  int32_t* s_idx = reinterpret_cast<int32_t*>(s_dyn + kHeavySmem);
-  float* s_heap = reinterpret_cast<float*>(s_idx + kHeavySmem);
+  extern __shared__ unsigned long long s_keys[];
+  __shared__ float s_heap[64];
   __shared__ int s_nacc;
   if (ctr->overflow) return;
   const int n_heavy = (int)ctr->n_heavy;
@@ -986,22 +1011,32 @@ __global__ void __launch_bounds__(256) fm_replay_heavy_kernel(fm_record* rec, co
     const int p = q_off[q + 1] - q_off[q];
     const int base = q_base[q];
     fm_record* seg = rec + base;
-    const bool in_smem = n <= kHeavySmem;
-    unsigned long long* keys = in_smem ? s_keys : sort_key + base;
-    int32_t* idx = in_smem ? s_idx : sort_idx + base;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) { keys[i] = order_key(seg[i]); idx[i] = i; }
+    unsigned long long* gkeys = sort_key + base;
+    int32_t* idx = sort_idx + base;
+    if (n < (1 << 20)) {
+      unsigned long long* keys = n <= kHeavySmem ? s_keys : gkeys;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const fm_record r = seg[i];
+        keys[i] = ((unsigned long long)(unsigned)(1023 - r.longest_match) << 52) | ((unsigned long long)r.s_id << 20) | (unsigned)i;
+      }
+      __syncthreads();
+      block_sort_keys(keys, n);
+      for (int i = threadIdx.x; i < n; i += blockDim.x) idx[i] = (int)(keys[i] & 0xfffffu);
+    } else {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) { gkeys[i] = order_key(seg[i]); idx[i] = i; }
+      __syncthreads();
+      block_sort_pairs(gkeys, idx, n);
+    }
     __syncthreads();
-    block_sort_pairs(keys, idx, n);
     if (threadIdx.x < 32) {
       float* heap = (pr.buffer > 0 && pr.buffer <= 62) ? s_heap : heapbuf + base + q;
-      const int nacc = replay_sequence(seg, n, p, idx, keys, heap, pr);
+      const int nacc = replay_sequence(seg, n, p, idx, gkeys, heap, pr);
       if (threadIdx.x == 0) s_nacc = nacc;
     }
     __syncthreads();
     const int nacc = s_nacc;
-    block_sort_pairs(keys, idx, nacc);
+    block_sort_pairs(gkeys, idx, nacc);
     if (pr.contrast > 0.f) {
-      for (int i = threadIdx.x; i < nacc; i += blockDim.x) sort_idx[base + i] = idx[i];
       if (threadIdx.x == 0) acc_cnt[q] = nacc;
     } else {
       const int want = pr.n_matches == 0 ? nacc : min(nacc, pr.n_matches);
@@ -1167,7 +1202,7 @@ void launch_replay(const IndexDev& ix, const fm_record* rec, const int32_t* q_cn
   const int grid = (n_q + 7) / 8;
   fm_replay_kernel<<<grid, 256, 0, st>>>(const_cast<fm_record*>(rec), q_cnt, q_base, heapbuf, sort_key, sort_idx, acc_cnt,
                                          heavy_q, q_off, n_q, p, (long long)cap, out, out_count, ctr);
-  const size_t smem = (size_t)kHeavySmem * 12 + 64 * sizeof(float);
+  const size_t smem = (size_t)kHeavySmem * sizeof(unsigned long long);
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(fm_replay_heavy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
