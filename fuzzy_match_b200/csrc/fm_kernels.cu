@@ -496,27 +496,33 @@ __global__ void __launch_bounds__(256, 8) fm_gather_kernel(IndexDev ix, BatchDev
     long long k0 = __ldg(b.span_slice + span / kSpan);  // a slice at or one before the slice of the group's first element
     // starts relative to the span: window starts are > span - 1, the current slice may begin earlier
     int s0 = (int)max(__ldg(b.sl_start + k0) - span, -0x7fffffffll);
+    int z0 = __ldg(&b.sl_rec[k0].w);  // size of slice k0
     for (int u = 0; u < kSpan; u += 32) {
       if (span + u >= total) break;
       const int el = u + lane;
-      // window = the 32 slices after k0; slice(el) = k0 + #{window starts <= el}
-      const long long ks = k0 + 1 + lane;
-      const int wst = ks < n_slices ? (int)min(__ldg(b.sl_start + ks) - span, 0x7fffffffll) : 0x7fffffff;
-      int c = 0;
+      int my_start = s0;
+      long long my_slice = k0;
+      if (u + 31 >= s0 + z0) {  // (uniform) the group reaches past slice k0: find each lane's slice
+        // window = the 32 slices after k0; slice(el) = k0 + #{window starts <= el}
+        const long long ks = k0 + 1 + lane;
+        const int wst = ks < n_slices ? (int)min(__ldg(b.sl_start + ks) - span, 0x7fffffffll) : 0x7fffffff;
+        int c = 0;
 #pragma unroll
-      for (int step = 16; step > 0; step >>= 1) {
-        const int v = __shfl_sync(FULL, wst, c + step - 1);
-        if (v <= el) c += step;
+        for (int step = 16; step > 0; step >>= 1) {
+          const int v = __shfl_sync(FULL, wst, c + step - 1);
+          if (v <= el) c += step;
+        }
+        {
+          const int v = __shfl_sync(FULL, wst, c);  // c <= 31
+          if (v <= el) c += 1;
+        }
+        const int prev_start = __shfl_sync(FULL, wst, c > 0 ? c - 1 : 0);
+        my_start = c > 0 ? prev_start : s0;
+        my_slice = k0 + c;
+        k0 = __shfl_sync(FULL, my_slice, 31);
+        s0 = __shfl_sync(FULL, my_start, 31);
+        z0 = __ldg(&b.sl_rec[k0].w);
       }
-      {
-        const int v = __shfl_sync(FULL, wst, c);  // c <= 31
-        if (v <= el) c += 1;
-      }
-      const int prev_start = __shfl_sync(FULL, wst, c > 0 ? c - 1 : 0);
-      const int my_start = c > 0 ? prev_start : s0;
-      const long long my_slice = k0 + c;
-      k0 = __shfl_sync(FULL, my_slice, 31);
-      s0 = __shfl_sync(FULL, my_start, 31);
       bool pass = false;
       int4 item = make_int4(0, 0, 0, 0);
       if (span + el < total) {
