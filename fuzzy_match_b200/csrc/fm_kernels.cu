@@ -226,15 +226,23 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
     if (lane == 0) {
       b.qmask[3 * q + 0] = make_int4(m[0], m[1], m[2], m[3]);
       b.qmask[3 * q + 1] = make_int4(m[4], m[5], m[6], m[7]);
-      b.qmask[3 * q + 2] = make_int4(m[8], m[9], extra, 0);
+      b.qmask[3 * q + 2] = make_int4(m[8], m[9], extra, (m[4] | m[5]) != 0);
     }
   }
 }
 
 // ---------------------------------------------------------------- search
 
-// Warp-collective append of up to two range slices per lane. One packed 64-bit atomic per warp
-// reserves slice slots and flattened element offsets together, so slice order == element order.
+// Range slices are first buffered per thread in shared memory (kSliceBuf slots) and appended to the
+// global slice list by warp-collective flushes: one packed 64-bit atomic per warp and flush reserves
+// slice slots and flattened element offsets together, so slice order == element order. Buffering keeps
+// the number of same-address atomics near one per warp instead of one per warp and n-gram level.
+static const int kSliceBuf = 6;
+struct SliceBuf {
+  int beg[kSliceBuf][256];
+  int sz[kSliceBuf][256];
+  int lm[kSliceBuf][256];
+};
 __device__ __forceinline__ void note_spans(const BatchDev& b, long long slot, long long start, int size) {
   // span_slice[k] = slice that holds flattened element k*kSpan
   for (long long k = (start + kSpan - 1) / kSpan; k * kSpan < start + size; k++) {
@@ -242,10 +250,16 @@ __device__ __forceinline__ void note_spans(const BatchDev& b, long long slot, lo
     else { atomicOr(&b.ctr->overflow, 4u); break; }
   }
 }
-__device__ __forceinline__ void emit_slices(const BatchDev& b, int lane, int q, int p, int n, int beg0, int sz0, int lm0,
-                                            int beg1, int sz1, int lm1) {
-  if (!__any_sync(FULL, n > 0)) return;
-  const unsigned long long mine = ((unsigned long long)n << kElemBits) | (unsigned long long)(unsigned)(sz0 + sz1);
+__device__ __forceinline__ void push_slice(SliceBuf& sb, int& nbuf, int beg, int sz, int lm) {
+  sb.beg[nbuf][threadIdx.x] = beg;
+  sb.sz[nbuf][threadIdx.x] = sz;
+  sb.lm[nbuf][threadIdx.x] = lm;
+  nbuf++;
+}
+__device__ __forceinline__ void flush_slices(const BatchDev& b, SliceBuf& sb, int& nbuf, int lane, int q, int p) {
+  int elems = 0;
+  for (int k = 0; k < nbuf; k++) elems += sb.sz[k][threadIdx.x];
+  const unsigned long long mine = ((unsigned long long)nbuf << kElemBits) | (unsigned long long)(unsigned)elems;
   unsigned long long incl = mine;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -260,30 +274,29 @@ __device__ __forceinline__ void emit_slices(const BatchDev& b, int lane, int q, 
   const unsigned long long excl = base + incl - mine;
   long long slot = (long long)(excl >> kElemBits);
   long long start = (long long)(excl & ((1ull << kElemBits) - 1));
-  if (n > 0) {
-    if (slot + n > b.slice_cap) {
+  if (nbuf > 0) {
+    if (slot + nbuf > b.slice_cap) {
       atomicOr(&b.ctr->overflow, 1u);
-      return;
-    }
-    if (sz0 > 0) {
-      b.sl_start[slot] = start;
-      b.sl_rec[slot] = make_int4(q, beg0, lm0 | (p << 16), sz0);
-      note_spans(b, slot, start, sz0);
-      slot++;
-      start += sz0;
-    }
-    if (sz1 > 0) {
-      b.sl_start[slot] = start;
-      b.sl_rec[slot] = make_int4(q, beg1, lm1 | (p << 16), sz1);
-      note_spans(b, slot, start, sz1);
+    } else {
+      for (int k = 0; k < nbuf; k++) {
+        const int sz = sb.sz[k][threadIdx.x];
+        b.sl_start[slot] = start;
+        b.sl_rec[slot] = make_int4(q, sb.beg[k][threadIdx.x], sb.lm[k][threadIdx.x] | (p << 16), sz);
+        note_spans(b, slot, start, sz);
+        slot++;
+        start += sz;
+      }
     }
   }
+  nbuf = 0;
 }
 
 // One thread per (query, start position) chain: the n-gram walk of src/fuzzy_match.cc:484-551 with
 // SuffixArray::equal_range (src/suffix_array.cc:105-212) restated as lower/upper bound on the ONE new
 // token at depth k inside the previous range (every suffix there already shares k tokens).
 __global__ void __launch_bounds__(256) fm_search_kernel(IndexDev ix, BatchDev b) {
+  __shared__ SliceBuf sb;
+  int nbuf = 0;
   const int lane = threadIdx.x & 31;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   int q = 0, it = 0, p = 0, ml = 0;
@@ -320,13 +333,11 @@ __global__ void __launch_bounds__(256) fm_search_kernel(IndexDev ix, BatchDev b)
     }
   }
   // p == 1: the unigram range itself is registered (src/fuzzy_match.cc:484-493)
-  {
-    const bool uni = live && p == 1 && 1 >= ml;
-    emit_slices(b, lane, q, p, uni ? 1 : 0, lo, uni ? hi - lo : 0, 1, 0, 0, 0);
-  }
+  if (live && p == 1 && 1 >= ml) push_slice(sb, nbuf, lo, hi - lo, 1);
   bool extending = live && it + len < p;
+  int pos1 = -1;  // sa_pos[lo] once the range has shrunk to one suffix
   while (__any_sync(FULL, extending)) {
-    int n = 0, beg0 = 0, sz0 = 0, beg1 = 0, sz1 = 0;
+    if (__any_sync(FULL, nbuf > kSliceBuf - 2)) flush_slices(b, sb, nbuf, lane, q, p);  // room for two more
     if (extending) {
       const int t = pat[it + len];  // token at depth len
       int nlo = lo, nhi = lo;
@@ -339,6 +350,10 @@ __global__ void __launch_bounds__(256) fm_search_kernel(IndexDev ix, BatchDev b)
           if (e.x == -1) break;
           h = (h + 1) & ix.tg_mask;
         }
+      } else if (t >= 2 && hi - lo == 1) {
+        // a single suffix left: follow its tokens directly (its position stays in a register)
+        if (pos1 < 0) pos1 = __ldg(ix.sa_pos + lo);
+        if (__ldg(ix.tok + (pos1 + len)) == t) { nlo = lo; nhi = hi; }
       } else if (t >= 2) {
         int a = lo, e = hi;
         while (a < e) {  // first suffix whose token at depth len is >= t
@@ -361,22 +376,20 @@ __global__ void __launch_bounds__(256) fm_search_kernel(IndexDev ix, BatchDev b)
       if (nhi > nlo) {
         // range for length len+1 is non-empty; the shaved-off parts matched exactly len tokens
         if (len + 1 > 2 && len >= ml) {
-          beg0 = lo; sz0 = nlo - lo;
-          beg1 = nhi; sz1 = hi - nhi;
-          n = (sz0 > 0) + (sz1 > 0);
+          if (nlo > lo) push_slice(sb, nbuf, lo, nlo - lo, len);
+          if (hi > nhi) push_slice(sb, nbuf, nhi, hi - nhi, len);
         }
+        if (nlo != lo || nhi != hi) pos1 = -1;
         lo = nlo; hi = nhi; len++;
         if (it + len >= p) extending = false;
       } else {
         extending = false;
       }
     }
-    emit_slices(b, lane, q, p, n, beg0, sz0, len - 1, beg1, sz1, len - 1);
   }
-  {
-    const bool fin = live && len >= 2 && len >= ml;
-    emit_slices(b, lane, q, p, fin ? 1 : 0, lo, fin ? hi - lo : 0, len, 0, 0, 0);
-  }
+  if (__any_sync(FULL, nbuf > kSliceBuf - 1)) flush_slices(b, sb, nbuf, lane, q, p);
+  if (live && len >= 2 && len >= ml) push_slice(sb, nbuf, lo, hi - lo, len);
+  flush_slices(b, sb, nbuf, lane, q, p);
 }
 
 // ---------------------------------------------------------------- gather
@@ -536,11 +549,13 @@ __global__ void __launch_bounds__(256, 8) fm_gather_kernel(IndexDev ix, BatchDev
           if (slen >= pi.x && slen <= pi.y) {
             const int need = __ldg(b.cmin_tab + pi.w + (slen - pi.x));
             if (need <= p) {
-              const int4 m0 = __ldg(b.qmask + 3 * q), m1 = __ldg(b.qmask + 3 * q + 1), m2 = __ldg(b.qmask + 3 * q + 2);
+              const int4 m0 = __ldg(b.qmask + 3 * q), m2 = __ldg(b.qmask + 3 * q + 2);
+              const int4 m1 = m2.w ? __ldg(b.qmask + 3 * q + 1) : make_int4(0, 0, 0, 0);
               const unsigned lo = (unsigned)wr.z, hi = (unsigned)wr.w;
-              const int ub = __popc(lo & m0.x) + __popc(hi & m0.y) + __popc(lo & m0.z) + __popc(hi & m0.w) +
-                             __popc(lo & m1.x) + __popc(hi & m1.y) + __popc(lo & m1.z) + __popc(hi & m1.w) +
-                             m2.z * (__popc(lo & m2.x) + __popc(hi & m2.y));
+              int ub = __popc(lo & m0.x) + __popc(hi & m0.y) + __popc(lo & m0.z) + __popc(hi & m0.w);
+              if (m2.w)  // some signature bit collects 3 or more pattern positions (rare)
+                ub += __popc(lo & m1.x) + __popc(hi & m1.y) + __popc(lo & m1.z) + __popc(hi & m1.w) +
+                      m2.z * (__popc(lo & m2.x) + __popc(hi & m2.y));
               if (ub >= need) {
                 pass = true;
                 item = make_int4(q, wr.x, slen | (need << 16), lm);
