@@ -41,6 +41,8 @@ static int ensure_base(Workspace* w) {
     FM_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     for (auto& e : w->ev) FM_CUDA(cudaEventCreate(&e));
     FM_CUDA(cudaMalloc((void**)&w->ctr, sizeof(Counters)));
+    FM_CUDA(cudaMalloc((void**)&w->scan_chain, 256 * sizeof(unsigned long long)));
+    FM_CUDA(cudaMemset(w->scan_chain, 0, 256 * sizeof(unsigned long long)));
     FM_CUDA(cudaMallocHost((void**)&w->h_ctr, sizeof(Counters)));
   }
   return FM_OK;
@@ -119,7 +121,7 @@ static int ensure_out(Workspace* w, int64_t n_q, int64_t cap) {
 static void free_workspace(Workspace* w) {
   cudaFree(w->d_q_tok); cudaFree(w->d_q_off); cudaFree(w->pat); cudaFree(w->chain_q); cudaFree(w->qmeta); cudaFree(w->tbl); cudaFree(w->pinfo); cudaFree(w->cmin_tab); cudaFree(w->span_slice); cudaFree(w->qmask);
   cudaFree(w->sl_start); cudaFree(w->sl_rec); cudaFree(w->hkey); cudaFree(w->hlm); cudaFree(w->surv); cudaFree(w->surv_len);
-  cudaFree(w->q_cnt); cudaFree(w->q_base); cudaFree(w->acc_cnt); cudaFree(w->rec); cudaFree(w->heapbuf); cudaFree(w->ctr);
+  cudaFree(w->q_cnt); cudaFree(w->q_base); cudaFree(w->acc_cnt); cudaFree(w->rec); cudaFree(w->heapbuf); cudaFree(w->ctr); cudaFree(w->scan_chain);
   cudaFree(w->d_out); cudaFree(w->d_out_count); cudaFree(w->mrec); cudaFree(w->m_cnt); cudaFree(w->m_base); cudaFree(w->m_acc); cudaFree(w->m_heap); cudaFree(w->heavy_q); cudaFree(w->m_heavy); cudaFree(w->sort_key); cudaFree(w->sort_idx); cudaFree(w->m_key); cudaFree(w->m_idx);
   if (w->h_ctr) cudaFreeHost(w->h_ctr);
   if (w->h_q_off32) cudaFreeHost(w->h_q_off32);
@@ -183,7 +185,7 @@ static int launch_shard(Index* ix, Workspace* w, const int32_t* d_q_tok, const i
   launch_gather(ix->dev, b, pr, ix->sm_count, st);
   if (getenv("FM_DEBUG_SYNC2")) cudaStreamSynchronize(st);
   if (ix->profiling) cudaEventRecord(w->ev[3], st);
-  launch_scan(w->q_cnt, w->q_base, (int32_t)n_q, st);
+  launch_scan(w->q_cnt, w->q_base, (int32_t)n_q, w->scan_chain, ++w->scan_epoch, ix->sm_count, st);
   if (ix->profiling) cudaEventRecord(w->ev[4], st);
   launch_score(ix->dev, b, pr, ix->sm_count, st);
   if (ix->profiling) cudaEventRecord(w->ev[5], st);
@@ -505,7 +507,7 @@ int fm_merge_replay_device(fm_index* index, int n_shards, const int32_t* const* 
   }
   int launches = 0;
   launch_merge_count(n_shards, d_rec_off, w->m_cnt, (int32_t)n_q, st);
-  launch_scan(w->m_cnt, w->m_base, (int32_t)n_q, st);
+  launch_scan(w->m_cnt, w->m_base, (int32_t)n_q, w->scan_chain, ++w->scan_epoch, ix->sm_count, st);
   int32_t total = 0;
   FM_CUDA(cudaMemcpyAsync(&total, w->m_base + n_q, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   FM_CUDA(cudaStreamSynchronize(st));

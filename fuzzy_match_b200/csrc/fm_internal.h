@@ -162,6 +162,8 @@ struct Workspace {
   unsigned long long *sort_key = nullptr, *m_key = nullptr;
   int32_t *sort_idx = nullptr, *m_idx = nullptr;
   Counters* ctr = nullptr;
+  unsigned long long* scan_chain = nullptr;  // chained-scan mailboxes
+  unsigned int scan_epoch = 0;
   fm_match* d_out = nullptr;
   int32_t* d_out_count = nullptr;
   // merged-shard buffers
@@ -217,7 +219,8 @@ void launch_bounds(const IndexDev& ix, const BatchDev& b, const Params& p, cudaS
 void launch_prepare(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st);
 void launch_search(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st);
 void launch_gather(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st);
-void launch_scan(const int32_t* in, int32_t* out, int32_t n, cudaStream_t st);
+void launch_scan(const int32_t* in, int32_t* out, int32_t n, unsigned long long* chain, unsigned int epoch, int sm_count,
+                 cudaStream_t st);
 void launch_score(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st);
 void launch_replay(const IndexDev& ix, const fm_record* rec, const int32_t* q_cnt, const int32_t* q_base, float* heapbuf,
                    unsigned long long* sort_key, int32_t* sort_idx, int32_t* acc_cnt, int32_t* heavy_q, const int32_t* q_off,

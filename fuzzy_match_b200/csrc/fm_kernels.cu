@@ -585,17 +585,46 @@ __global__ void __launch_bounds__(256, 8) fm_gather_kernel(IndexDev ix, BatchDev
 
 // ---------------------------------------------------------------- scan (single CTA, n <= a few million)
 
-__global__ void __launch_bounds__(1024) fm_scan_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, int n) {
+// Exclusive scan of the per-query survivor counts, chained over co-resident CTAs: CTA i scans its tile,
+// waits for the running total of CTA i-1 (a flag/value pair in `chain`), publishes its own. The grid
+// (<= 128 CTAs of 1024 threads) is always fully resident, so the spin cannot deadlock.
+static const int kScanCtas = 128;
+__global__ void __launch_bounds__(1024) fm_scan_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, int n,
+                                                       unsigned long long* chain, unsigned int epoch) {
   __shared__ int warp_sum[32];
   __shared__ int carry_s;
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  if (t == 0) carry_s = 0;
+  const int per_cta = (((n + gridDim.x - 1) / gridDim.x) + 4095) / 4096 * 4096;
+  const int beg = blockIdx.x * per_cta, end = min(n, beg + per_cta);
+  // pass 1: tile total
+  int total = 0;
+  for (int i = beg + t; i < end; i += 1024) total += in[i];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(FULL, total, d);
+  if (lane == 0) warp_sum[wid] = total;
   __syncthreads();
-  for (int base = 0; base < n; base += 4096) {
+  if (t == 0) {
+    int tile = 0;
+    for (int w = 0; w < 32; w++) tile += warp_sum[w];
+    unsigned long long prev = 0;
+    if (blockIdx.x > 0) {  // wait for the predecessor's inclusive total of this epoch
+      volatile unsigned long long* p = chain + blockIdx.x - 1;
+      do { prev = *p; } while ((unsigned)(prev >> 32) != epoch);
+    }
+    const int carry = (int)(unsigned)prev;
+    carry_s = carry;
+    __threadfence();
+    *(volatile unsigned long long*)(chain + blockIdx.x) = ((unsigned long long)epoch << 32) | (unsigned)(carry + tile);
+    if (blockIdx.x == gridDim.x - 1) out[n] = carry + tile;
+  }
+  __syncthreads();
+  // pass 2: exclusive scan of the tile, 4096 items per round
+  int carry = carry_s;
+  for (int base = beg; base < end; base += 4096) {
     const int i0 = base + 4 * t;
     int v[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) v[k] = i0 + k < n ? in[i0 + k] : 0;
+    for (int k = 0; k < 4; k++) v[k] = i0 + k < end ? in[i0 + k] : 0;
     const int mine = v[0] + v[1] + v[2] + v[3];
     int incl = mine;
 #pragma unroll
@@ -603,6 +632,7 @@ __global__ void __launch_bounds__(1024) fm_scan_kernel(const int32_t* __restrict
       const int o = __shfl_up_sync(FULL, incl, d);
       if (lane >= d) incl += o;
     }
+    __syncthreads();
     if (lane == 31) warp_sum[wid] = incl;
     __syncthreads();
     if (wid == 0) {
@@ -612,21 +642,17 @@ __global__ void __launch_bounds__(1024) fm_scan_kernel(const int32_t* __restrict
         const int o = __shfl_up_sync(FULL, ws, d);
         if (lane >= d) ws += o;
       }
-      warp_sum[lane] = ws;  // inclusive over warps
+      warp_sum[lane] = ws;
     }
     __syncthreads();
-    const int carry = carry_s;
     int run = carry + (wid ? warp_sum[wid - 1] : 0) + incl - mine;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      if (i0 + k < n) out[i0 + k] = run;
+      if (i0 + k < end) out[i0 + k] = run;
       run += v[k];
     }
-    __syncthreads();
-    if (t == 0) carry_s = carry + warp_sum[31];
-    __syncthreads();
+    carry += warp_sum[31];
   }
-  if (t == 0) out[n] = carry_s;
 }
 
 // ---------------------------------------------------------------- edit distance (warp wavefront)
@@ -1196,8 +1222,12 @@ void launch_search(const IndexDev& ix, const BatchDev& b, const Params&, cudaStr
 void launch_gather(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st) {
   fm_gather_kernel<<<sm_count * 8, 256, 0, st>>>(ix, b, p);
 }
-void launch_scan(const int32_t* in, int32_t* out, int32_t n, cudaStream_t st) {
-  fm_scan_kernel<<<1, 1024, 0, st>>>(in, out, n);
+void launch_scan(const int32_t* in, int32_t* out, int32_t n, unsigned long long* chain, unsigned int epoch, int sm_count,
+                 cudaStream_t st) {
+  int ctas = (n + 4095) / 4096;
+  ctas = ctas < 1 ? 1 : (ctas > kScanCtas ? kScanCtas : ctas);
+  if (ctas > sm_count) ctas = sm_count;  // all CTAs must be co-resident
+  fm_scan_kernel<<<ctas, 1024, 0, st>>>(in, out, n, chain, epoch);
 }
 void launch_score(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st) {
   const int stride = dp_stride(ix);
