@@ -391,7 +391,13 @@ def main():
         peak, peak_src = measured_peak()
         stages = {k[3:]: prof[k] for k in ("ms_prepare", "ms_search", "ms_gather", "ms_scan", "ms_score", "ms_replay")}
         dom = max(stages, key=stages.get)
-        roof = {"bound": "hbm", "kernel": "fm_%s_kernel" % dom, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None,
+        traffic = None
+        try:  # DRAM bytes per launch from the committed ncu --set full capture of this workload
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                traffic = json.load(f)["fm_%s_kernel" % dom]["traffic_bytes_per_launch"]
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "kernel": "fm_%s_kernel" % dom, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": traffic,
                 "stage_ms": {k: round(v, 4) for k, v in stages.items()}, "elements_per_step": prof["n_elements"],
                 "slices_per_step": prof["n_slices"], "survivors_per_step": prof["n_survivors"]}
         if counters:
