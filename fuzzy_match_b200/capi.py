@@ -66,7 +66,7 @@ MATCH_DTYPE = np.dtype([("s_id", np.uint32), ("score", np.float32), ("penalty", 
 RECORD_DTYPE = np.dtype([("s_id", np.uint32), ("longest_match", np.int32), ("length", np.int32),
                          ("cost", np.float32), ("rowmin_max", np.float32), ("reserved", np.int32, (3,))])
 
-EXPORTS = ["fm_index_create", "fm_index_destroy", "fm_index_num_sentences", "fm_index_num_suffixes",
+EXPORTS = ["fm_index_create", "fm_index_destroy", "fm_index_save", "fm_index_load", "fm_index_num_sentences", "fm_index_num_suffixes",
            "fm_index_max_tokens_in_pattern", "fm_index_device_bytes", "fm_index_kept_sources", "fm_index_sfreq",
            "fm_index_sentence", "fm_index_set_idf_stats", "fm_match_batch", "fm_match_batch_device", "fm_shard_score_device",
            "fm_merge_replay_device", "fm_set_profiling", "fm_get_profile", "fm_last_error", "fm_version"]
@@ -93,6 +93,8 @@ def load_library():
     lib.fm_index_destroy.argtypes = [C.c_void_p]
     lib.fm_index_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
                                     C.c_int64, C.c_int, C.POINTER(C.c_void_p)]
+    lib.fm_index_save.argtypes = [C.c_void_p, C.c_char_p]
+    lib.fm_index_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
     lib.fm_index_kept_sources.argtypes = [C.c_void_p, C.c_void_p]
     lib.fm_index_sfreq.argtypes = [C.c_void_p, C.c_void_p]
     lib.fm_index_set_idf_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
@@ -136,6 +138,19 @@ class Index:
         self.h = h
         self.vocab_size = int(vocab_size)
         self.device = int(device)
+
+    @classmethod
+    def load(cls, path, vocab_size, device=0):
+        """fm_index_load: an index written by save()."""
+        self = cls.__new__(cls)
+        self.lib = load_library()
+        h = C.c_void_p()
+        _check(self.lib, self.lib.fm_index_load(str(path).encode(), int(device), C.byref(h)))
+        self.h, self.vocab_size, self.device = h, int(vocab_size), int(device)
+        return self
+
+    def save(self, path):
+        _check(self.lib, self.lib.fm_index_save(self.h, str(path).encode()))
 
     def close(self):
         if getattr(self, "h", None):

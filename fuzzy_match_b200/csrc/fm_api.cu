@@ -291,6 +291,19 @@ int fm_index_create(const int32_t* tokens, const int64_t* sent_off, int64_t n_se
   return rc;
 }
 
+int fm_index_save(const fm_index* index, const char* path) {
+  const Index* ix = reinterpret_cast<const Index*>(index);
+  if (!ix || !path) { set_error("NULL argument"); return FM_ERR_INVALID; }
+  return save_index(ix, path);
+}
+int fm_index_load(const char* path, int device, fm_index** out) {
+  if (!path || !out) { set_error("NULL argument"); return FM_ERR_INVALID; }
+  Index* ix = nullptr;
+  const int rc = load_index(path, device, &ix);
+  *out = reinterpret_cast<fm_index*>(ix);
+  return rc;
+}
+
 void fm_index_destroy(fm_index* index) {
   Index* ix = reinterpret_cast<Index*>(index);
   if (!ix) return;

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <numeric>
 #include <thread>
@@ -27,15 +28,108 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 template <class T>
-static int upload(const std::vector<T>& h, size_t extra, void** slot, const T** out, int64_t* bytes) {
+static int upload(const std::vector<T>& h, size_t extra, Index* ix, int blk, const T** out) {
   void* d = nullptr;
   const size_t n = (h.size() + extra) * sizeof(T);
   FM_CUDA(cudaMalloc(&d, n ? n : 16));
   FM_CUDA(cudaMemset(d, 0, n ? n : 16));
   if (!h.empty()) FM_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
-  *slot = d;
+  ix->d_blocks[blk] = d;
+  ix->blk_bytes[blk] = n;
   *out = static_cast<const T*>(d);
-  *bytes += (int64_t)n;
+  ix->device_bytes += (int64_t)n;
+  return FM_OK;
+}
+
+// ---- on-disk format: one flat little-endian file (replaces the reference's
+// Boost binary archive, src/fuzzy_matcher_binarization.cc). Header, then the device blocks exactly as
+// they sit in HBM, then the host-side tables. Loading is read + upload: no sort, no hashing.
+static const char kMagic[8] = {'F', 'M', 'B', '2', '0', '0', 'I', 1};
+enum { BLK_TOK = 0, BLK_SA = 1, BLK_WALK = 2, BLK_QVA = 3, BLK_SID = 4, BLK_IDF = 5, BLK_BG = 6, BLK_TG = 7, N_BLK = 8 };
+
+static void bind_blocks(Index* ix) {
+  IndexDev& d = ix->dev;
+  d.tok = static_cast<const int32_t*>(ix->d_blocks[BLK_TOK]);
+  d.sa_pos = static_cast<const int32_t*>(ix->d_blocks[BLK_SA]);
+  d.sa_walk = static_cast<const int4*>(ix->d_blocks[BLK_WALK]);
+  d.qva = static_cast<const int32_t*>(ix->d_blocks[BLK_QVA]);
+  d.sid_at = static_cast<const int32_t*>(ix->d_blocks[BLK_SID]);
+  d.idf = static_cast<const float*>(ix->d_blocks[BLK_IDF]);
+  d.bg_tab = static_cast<const int4*>(ix->d_blocks[BLK_BG]);
+  d.tg_tab = static_cast<const int4*>(ix->d_blocks[BLK_TG]);
+}
+
+int save_index(const Index* ix, const char* path) {
+  FILE* f = fopen(path, "wb");
+  if (!f) { set_error(std::string("cannot open ") + path + " for writing"); return FM_ERR_INVALID; }
+  FM_CUDA(cudaSetDevice(ix->device));
+  int64_t hdr[16] = {1, ix->vocab_size, ix->max_tokens, ix->n_sent, ix->n_suf, ix->n_buf, (int64_t)ix->dev.bg_mask,
+                     (int64_t)ix->dev.tg_mask, (int64_t)ix->dev.sid_base, ix->n_sent_global, 0, 0, 0, 0, 0, 0};
+  memcpy(&hdr[10], &ix->dev.idf_max, sizeof(float));
+  bool ok = fwrite(kMagic, 1, 8, f) == 8 && fwrite(hdr, sizeof(int64_t), 16, f) == 16;
+  std::vector<char> buf;
+  for (int k = 0; k < N_BLK && ok; k++) {
+    const int64_t n = (int64_t)ix->blk_bytes[k];
+    buf.resize((size_t)n);
+    if (n && cudaMemcpy(buf.data(), ix->d_blocks[k], (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess) ok = false;
+    ok = ok && fwrite(&n, sizeof n, 1, f) == 1 && (n == 0 || fwrite(buf.data(), 1, (size_t)n, f) == (size_t)n);
+  }
+  ok = ok && fwrite(ix->h_sent_start.data(), sizeof(int32_t), ix->h_sent_start.size(), f) == ix->h_sent_start.size();
+  ok = ok && fwrite(ix->kept.data(), sizeof(int64_t), ix->kept.size(), f) == ix->kept.size();
+  ok = ok && fwrite(ix->sfreq.data(), sizeof(uint32_t), ix->sfreq.size(), f) == ix->sfreq.size();
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) { set_error(std::string("write to ") + path + " failed"); return FM_ERR_INVALID; }
+  return FM_OK;
+}
+
+int load_index(const char* path, int device, Index** out) {
+  *out = nullptr;
+  FILE* f = fopen(path, "rb");
+  if (!f) { set_error(std::string("cannot open ") + path); return FM_ERR_INVALID; }
+  char magic[8];
+  int64_t hdr[16];
+  if (fread(magic, 1, 8, f) != 8 || memcmp(magic, kMagic, 8) != 0 || fread(hdr, sizeof(int64_t), 16, f) != 16 || hdr[0] != 1) {
+    fclose(f);
+    set_error(std::string(path) + " is not a fuzzy_match_b200 index (version 1)");
+    return FM_ERR_INVALID;
+  }
+  Index* ix = new Index();
+  ix->device = device;
+  ix->vocab_size = (int32_t)hdr[1]; ix->max_tokens = (int32_t)hdr[2];
+  ix->n_sent = hdr[3]; ix->n_suf = hdr[4]; ix->n_buf = hdr[5]; ix->n_sent_global = hdr[9];
+  cudaError_t e = cudaSetDevice(device);
+  cudaDeviceProp prop;
+  if (e == cudaSuccess && cudaGetDeviceProperties(&prop, device) == cudaSuccess) ix->sm_count = prop.multiProcessorCount;
+  bool ok = e == cudaSuccess;
+  std::vector<char> buf;
+  for (int k = 0; k < N_BLK && ok; k++) {
+    int64_t n = 0;
+    ok = fread(&n, sizeof n, 1, f) == 1 && n >= 0 && n < (int64_t(1) << 40);
+    if (!ok) break;
+    buf.resize((size_t)n);
+    ok = n == 0 || fread(buf.data(), 1, (size_t)n, f) == (size_t)n;
+    void* d = nullptr;
+    ok = ok && cudaMalloc(&d, n ? (size_t)n : 16) == cudaSuccess;
+    ok = ok && (n == 0 || cudaMemcpy(d, buf.data(), (size_t)n, cudaMemcpyHostToDevice) == cudaSuccess);
+    ix->d_blocks[k] = d;
+    ix->blk_bytes[k] = (size_t)n;
+    ix->device_bytes += n;
+    if (k == BLK_TOK && ok) ix->h_tok.assign(reinterpret_cast<int32_t*>(buf.data()), reinterpret_cast<int32_t*>(buf.data()) + n / 4);
+  }
+  ix->h_sent_start.resize((size_t)ix->n_sent + 1);
+  ix->kept.resize((size_t)ix->n_sent);
+  ix->sfreq.resize((size_t)ix->vocab_size);
+  ok = ok && fread(ix->h_sent_start.data(), sizeof(int32_t), ix->h_sent_start.size(), f) == ix->h_sent_start.size();
+  ok = ok && fread(ix->kept.data(), sizeof(int64_t), ix->kept.size(), f) == ix->kept.size();
+  ok = ok && fread(ix->sfreq.data(), sizeof(uint32_t), ix->sfreq.size(), f) == ix->sfreq.size();
+  fclose(f);
+  if (!ok) { free_index(ix); set_error(std::string("reading ") + path + " failed (truncated file or CUDA error)"); return FM_ERR_INVALID; }
+  bind_blocks(ix);
+  IndexDev& d = ix->dev;
+  d.vocab_size = ix->vocab_size; d.max_tokens = ix->max_tokens; d.n_suf = ix->n_suf;
+  d.bg_mask = (uint32_t)hdr[6]; d.tg_mask = (uint32_t)hdr[7]; d.sid_base = (uint32_t)hdr[8];
+  memcpy(&d.idf_max, &hdr[10], sizeof(float));
+  *out = ix;
   return FM_OK;
 }
 
@@ -49,6 +143,7 @@ int set_idf_stats(Index* ix, const uint32_t* sf, int64_t n_sent_global) {
   FM_CUDA(cudaMemcpy(const_cast<float*>(ix->dev.idf), idf.data(), idf.size() * sizeof(float), cudaMemcpyHostToDevice));
   if (sf != ix->sfreq.data()) std::copy(sf, sf + ix->vocab_size, ix->sfreq.begin());
   ix->dev.idf_max = (float)std::log((double)num_sentences);
+  ix->n_sent_global = n_sent_global;
   return FM_OK;
 }
 
@@ -249,14 +344,14 @@ int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_in, in
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ix->sm_count = prop.multiProcessorCount;
   int rc;
   IndexDev& d = ix->dev;
-  if ((rc = upload(ix->h_tok, 0, &ix->d_blocks[0], &d.tok, &ix->device_bytes)) ||
-      (rc = upload(sa, 4, &ix->d_blocks[1], &d.sa_pos, &ix->device_bytes)) ||
-      (rc = upload(sa_walk, 4, &ix->d_blocks[2], &d.sa_walk, &ix->device_bytes)) ||
-      (rc = upload(qva, 0, &ix->d_blocks[3], &d.qva, &ix->device_bytes)) ||
-      (rc = upload(bg_tab, 0, &ix->d_blocks[6], &d.bg_tab, &ix->device_bytes)) ||
-      (rc = upload(tg_tab, 0, &ix->d_blocks[7], &d.tg_tab, &ix->device_bytes)) ||
-      (rc = upload(sid_at, 0, &ix->d_blocks[4], &d.sid_at, &ix->device_bytes)) ||
-      (rc = upload(std::vector<float>((size_t)vocab_size, 0.f), 0, &ix->d_blocks[5], &d.idf, &ix->device_bytes)) ||
+  if ((rc = upload(ix->h_tok, 0, ix, BLK_TOK, &d.tok)) ||
+      (rc = upload(sa, 4, ix, BLK_SA, &d.sa_pos)) ||
+      (rc = upload(sa_walk, 4, ix, BLK_WALK, &d.sa_walk)) ||
+      (rc = upload(qva, 0, ix, BLK_QVA, &d.qva)) ||
+      (rc = upload(bg_tab, 0, ix, BLK_BG, &d.bg_tab)) ||
+      (rc = upload(tg_tab, 0, ix, BLK_TG, &d.tg_tab)) ||
+      (rc = upload(sid_at, 0, ix, BLK_SID, &d.sid_at)) ||
+      (rc = upload(std::vector<float>((size_t)vocab_size, 0.f), 0, ix, BLK_IDF, &d.idf)) ||
       (rc = set_idf_stats(ix, sfreq_global ? sfreq_global : ix->sfreq.data(), n_sent_global > 0 ? n_sent_global : n_keep))) {
     free_index(ix);
     return rc;

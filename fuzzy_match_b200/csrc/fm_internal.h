@@ -192,6 +192,8 @@ struct Index {
   int64_t device_bytes = 0;
   int32_t vocab_size = 0, max_tokens = 0;
   void* d_blocks[12] = {};
+  size_t blk_bytes[12] = {};
+  int64_t n_sent_global = 0;
   int sm_count = 148;
   // workspaces
   std::mutex mu;
@@ -212,6 +214,8 @@ int cuda_fail(cudaError_t e, const char* what);
 int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_sent, int32_t vocab_size, int32_t max_tokens,
                 const uint32_t* sfreq_global, int64_t n_sent_global, int64_t s_id_base, int device, Index** out);
 void free_index(Index* ix);
+int save_index(const Index* ix, const char* path);
+int load_index(const char* path, int device, Index** out);
 int set_idf_stats(Index* ix, const uint32_t* sfreq, int64_t n_sent_global);
 
 // fm_kernels.cu -- launchers (all asynchronous on `st`)

@@ -88,6 +88,11 @@ int fm_index_create(const int32_t* tokens, const int64_t* sent_off, int64_t n_se
                     int32_t max_tokens_in_pattern, const uint32_t* sfreq_global, int64_t n_sent_global,
                     int64_t s_id_base, int device, fm_index** out);
 void fm_index_destroy(fm_index* index);
+/* Flat on-disk form of a built index (replaces the reference's .fmi Boost archive,
+ * src/fuzzy_matcher_binarization.cc:10-51): save writes the HBM-resident arrays as they are, load is
+ * read + upload (no sort). The id strings stay with the caller. */
+int fm_index_save(const fm_index* index, const char* path);
+int fm_index_load(const char* path, int device, fm_index** out);
 int64_t fm_index_num_sentences(const fm_index* index); /* kept sentences */
 int64_t fm_index_num_suffixes(const fm_index* index);
 int32_t fm_index_max_tokens_in_pattern(const fm_index* index); /* FuzzyMatch::max_tokens_in_pattern */

@@ -238,3 +238,44 @@ def test_cpp_adapter_runs_reference_gtests():
         g.build()
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "all adapter tests passed" in out.stdout, out.stdout + out.stderr
+
+
+def test_index_save_load_roundtrip(tmp_path, medium):
+    """fm_index_save / fm_index_load: the reloaded index answers bit-identically and keeps its tables."""
+    index, _, q, qo = medium
+    path = tmp_path / "tm.fmb"
+    index.save(path)
+    again = fmb.Index.load(path, index.vocab_size)
+    assert again.num_sentences == index.num_sentences and again.num_suffixes == index.num_suffixes
+    assert (again.sfreq() == index.sfreq()).all() and (again.kept_sources() == index.kept_sources()).all()
+    assert np.array_equal(again.sentence(17), index.sentence(17))
+    for params in (dict(fuzzy=0.5, n=4, ml=2), dict(fuzzy=0.4, n=3, ml=3, idf=1.0)):
+        a, ca = index.match_batch(q, qo, cap=4, **params)
+        b, cb = again.match_batch(q, qo, cap=4, **params)
+        assert (ca == cb).all() and a.tobytes() == b.tobytes()
+    with pytest.raises(fmb.FuzzyMatchError):
+        fmb.Index.load(tmp_path / "missing.fmb", 10)
+
+
+def test_concurrent_host_threads(medium):
+    """fm_match_batch is re-entrant on one shared index (like the reference's const match(), called by the
+    CLI's N worker threads, cli/src/FuzzyMatch-cli.cc:139-147): 4 threads, different parameters."""
+    import threading
+    index, oracle, q, qo = medium
+    params = [dict(fuzzy=0.5, n=4, ml=2), dict(fuzzy=0.7, n=1, ml=3), dict(fuzzy=0.4, n=3, ml=3, idf=1.0), dict(fuzzy=0.6, n=2, ml=2, costs=(1, 0, 1))]
+    results = [None] * 4
+
+    def work(k):
+        for _ in range(3):
+            results[k] = index.match_batch(q, qo, cap=4, **params[k])
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for k in range(4):
+        out, cnt = results[k]
+        ro, oc = oracle.match_batch(q, qo, cap=4, **params[k])
+        assert (cnt == oc).all()
+        assert all(out[i, :cnt[i]].tobytes() == ro[i].tobytes() for i in range(len(oc)))
