@@ -190,7 +190,7 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, extra=None):
@@ -209,8 +209,28 @@ def workload_config(args, extra=None):
 # ------------------------------------------------------------------------------------------ GPU arm
 
 
+_REAL_STDOUT = None
+
+
+def _capture_stdout():
+    """Everything libraries print on fd 1 (e.g. the NCCL version banner) goes to stderr; only the JSON
+    line is written to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse()
+    _capture_stdout()
     if args.impl == "reference":
         reference_arm(args)
         return
@@ -417,7 +437,7 @@ def main():
             roof["whole_step"] = {"bytes_per_query": round(total_bytes, 1), "achieved": total_bytes * n_q / (prof["ms_total"] * 1e-3) / 1e9,
                                   "frac": total_bytes * n_q / (prof["ms_total"] * 1e-3) / 1e9 / peak}
         line["roofline"] = roof
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
