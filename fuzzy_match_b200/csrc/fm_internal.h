@@ -159,7 +159,7 @@ struct Workspace {
   int32_t *q_cnt = nullptr, *q_base = nullptr, *acc_cnt = nullptr, *heavy_q = nullptr, *m_heavy = nullptr;
   fm_record* rec = nullptr;
   float* heapbuf = nullptr;
-  unsigned long long *sort_key = nullptr, *m_key = nullptr;
+  unsigned long long *sort_key = nullptr, *m_key = nullptr, *sort_key2 = nullptr, *m_key2 = nullptr;
   int32_t *sort_idx = nullptr, *m_idx = nullptr;
   Counters* ctr = nullptr;
   unsigned long long* scan_chain = nullptr;  // chained-scan mailboxes
@@ -227,9 +227,9 @@ void launch_scan(const int32_t* in, int32_t* out, int32_t n, unsigned long long*
                  cudaStream_t st);
 void launch_score(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st);
 void launch_replay(const IndexDev& ix, const fm_record* rec, const int32_t* q_cnt, const int32_t* q_base, float* heapbuf,
-                   unsigned long long* sort_key, int32_t* sort_idx, int32_t* acc_cnt, int32_t* heavy_q, const int32_t* q_off,
-                   int32_t n_q, const Params& p, int64_t cap, fm_match* out, int32_t* out_count, Counters* ctr, int sm_count,
-                   cudaStream_t st);
+                   unsigned long long* sort_key, unsigned long long* sort_key2, int32_t* sort_idx, int32_t* acc_cnt,
+                   int32_t* heavy_q, const int32_t* q_off, int32_t n_q, const Params& p, int64_t cap, fm_match* out,
+                   int32_t* out_count, Counters* ctr, int sm_count, cudaStream_t st);
 void launch_contrast(const IndexDev& ix, fm_record* rec, const int32_t* q_base, const int32_t* sort_idx,
                      const int32_t* acc_cnt, int32_t n_q, const Params& p, int64_t cap, fm_match* out, int32_t* out_count,
                      Counters* ctr, int sm_count, cudaStream_t st);

@@ -13,6 +13,7 @@
 // Integer indexing and scalar fp32 only -- no tensor cores. All float arithmetic that reaches a
 // result is written with __fadd_rn/__fmul_rn/__fdiv_rn in the reference's evaluation order so no
 // FMA contraction or reassociation can change a bit (the file is also compiled with -fmad=false).
+#include <algorithm>
 #include <cfloat>
 #include <cstdlib>
 
@@ -959,20 +960,43 @@ __device__ int replay_sequence(fm_record* seg, int n, int p, int32_t* idx, unsig
   return __shfl_sync(FULL, nacc, 0);
 }
 
-// One warp per query with <= 32 scored candidates (the common case): candidate order
-// (ngram_matches.cc:20-29: longest match desc, s_id asc) and result order by register rank sort,
-// top-N output (:670-679). Queries with more candidates are queued for fm_replay_heavy_kernel.
+// Warp-cooperative ascending bitonic sort of 64-bit keys in shared memory (ascending comparators only,
+// so the virtual +inf padding up to the next power of two never moves).
+__device__ void warp_sort_keys(unsigned long long* keys, int n) {
+  const int lane = threadIdx.x & 31;
+  int np = 32;
+  while (np < n) np <<= 1;
+  for (int k = 2; k <= np; k <<= 1) {
+    for (int j = k >> 1, first = 1; j > 0; j >>= 1, first = 0) {
+      for (int i = lane; i < np; i += 32) {
+        const int l = first ? (i ^ (k - 1)) : (i ^ j);
+        if (l > i && l < n) {
+          const unsigned long long a = keys[i], c = keys[l];
+          if (a > c) { keys[i] = c; keys[l] = a; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// One warp per query with <= kWarpMax scored candidates: candidate order (ngram_matches.cc:20-29:
+// longest match desc, s_id asc) by register rank sort (<= 32) or a shared-memory bitonic sort of packed
+// keys, the replay, result order, top-N output (:670-679). Larger queries are queued for
+// fm_replay_heavy_kernel.
+static const int kWarpMax = 256;
 __global__ void __launch_bounds__(256) fm_replay_kernel(fm_record* rec, const int32_t* __restrict__ q_cnt,
                                                         const int32_t* __restrict__ q_base, float* heapbuf,
                                                         unsigned long long* sort_key, int32_t* sort_idx, int32_t* acc_cnt,
                                                         int32_t* heavy_q, const int32_t* __restrict__ q_off, int n_q, Params pr,
                                                         long long cap, fm_match* out, int32_t* out_count, Counters* ctr) {
   __shared__ float s_heap[8][64];
+  __shared__ unsigned long long s_keys[8][kWarpMax];
   const int lane = threadIdx.x & 31;
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (q >= n_q) return;
   const int n = q_cnt[q];
-  if (n == 0 || n > 32) {
+  if (n == 0 || n > kWarpMax) {
     if (lane == 0) {
       if (ctr->overflow) return;
       if (n == 0) {
@@ -990,20 +1014,51 @@ __global__ void __launch_bounds__(256) fm_replay_kernel(fm_record* rec, const in
   fm_record* seg = rec + base;
   unsigned long long* keys = sort_key + base;
   int32_t* idx = sort_idx + base;
-  {
+  if (n <= 32) {
     const unsigned long long k = lane < n ? order_key(seg[lane]) : ~0ull;
     const int r = warp_rank(k, n);
     if (lane < n) idx[r] = lane;
+  } else {
+    unsigned long long* sk = s_keys[threadIdx.x >> 5];
+    for (int i = lane; i < n; i += 32) {
+      const fm_record r = seg[i];
+      sk[i] = ((unsigned long long)(unsigned)(1023 - r.longest_match) << 52) | ((unsigned long long)r.s_id << 20) | (unsigned)i;
+    }
+    __syncwarp();
+    warp_sort_keys(sk, n);
+    for (int i = lane; i < n; i += 32) idx[i] = (int)(sk[i] & 0xfffffu);
   }
   __syncwarp();
   float* heap = (pr.buffer > 0 && pr.buffer <= 62) ? s_heap[threadIdx.x >> 5] : heapbuf + base + q;
   const int nacc = replay_sequence(seg, n, p, idx, keys, heap, pr);
   if (nacc > 1) {
-    const unsigned long long k = lane < nacc ? keys[lane] : ~0ull;
-    const int id = lane < nacc ? idx[lane] : 0;
-    const int r = warp_rank(k, nacc);
-    __syncwarp();
-    if (lane < nacc) idx[r] = id;
+    if (nacc <= 32) {
+      const unsigned long long k = lane < nacc ? keys[lane] : ~0ull;
+      const int id = lane < nacc ? idx[lane] : 0;
+      const int r = warp_rank(k, nacc);
+      __syncwarp();
+      if (lane < nacc) idx[r] = id;
+    } else {
+      // (score, s_id) keys do not fit one word with the index: rank every accepted record against all
+      unsigned long long* sk = s_keys[threadIdx.x >> 5];
+      for (int i = lane; i < nacc; i += 32) sk[i] = keys[i];
+      __syncwarp();
+      int my_rank[kWarpMax / 32], my_id[kWarpMax / 32];
+#pragma unroll
+      for (int c = 0; c < kWarpMax / 32; c++) {
+        const int i = c * 32 + lane;
+        my_rank[c] = 0;
+        my_id[c] = i < nacc ? idx[i] : 0;
+        if (i < nacc) {
+          const unsigned long long k = sk[i];
+          for (int j = 0; j < nacc; j++) my_rank[c] += sk[j] < k;
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < kWarpMax / 32; c++)
+        if (c * 32 + lane < nacc) idx[my_rank[c]] = my_id[c];
+    }
     __syncwarp();
   }
   if (pr.contrast > 0.f) {
@@ -1037,19 +1092,78 @@ __device__ void block_sort_keys(unsigned long long* keys, int n) {
   }
 }
 
-// One CTA per query with more than 32 scored candidates. The candidate order is sorted as ONE packed
+// CTA-cooperative stable LSD radix sort (8-bit digits over key bits [lo_bit, hi_bit)) of 64-bit keys
+// in global memory, for candidate lists too long for shared memory. Every warp owns a contiguous
+// chunk: per-warp digit histograms, one scan over (digit, warp), then each warp scatters its chunk in
+// order with intra-warp ranks from __match_any_sync. Passes whose digit is constant are skipped.
+// Returns the buffer that holds the sorted keys.
+__device__ unsigned long long* block_radix_sort_keys(unsigned long long* a, unsigned long long* b, int n, int lo_bit,
+                                                     int hi_bit, int (*s_off)[256], int* s_tot, int* s_flag) {
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int per_warp = (((n + 7) / 8) + 31) / 32 * 32;
+  const int beg = min(n, w * per_warp), end = min(n, beg + per_warp);
+  for (int shift = lo_bit; shift < hi_bit; shift += 8) {
+    for (int k = 0; k < 8; k++) s_off[k][t] = 0;
+    if (t == 0) *s_flag = 0;
+    __syncthreads();
+    for (int i = beg + lane; i < end; i += 32) atomicAdd(&s_off[w][(int)((a[i] >> shift) & 255)], 1);
+    __syncthreads();
+    {  // thread t owns digit t
+      int tot = 0;
+      for (int k = 0; k < 8; k++) tot += s_off[k][t];
+      if (tot == n) *s_flag = 1;
+      int incl = tot;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += o;
+      }
+      if (lane == 31) s_tot[w] = incl;
+      __syncthreads();
+      int base = incl - tot;
+      for (int k = 0; k < w; k++) base += s_tot[k];
+      for (int k = 0; k < 8; k++) {
+        const int c = s_off[k][t];
+        s_off[k][t] = base;
+        base += c;
+      }
+    }
+    __syncthreads();
+    if (*s_flag) continue;  // all keys share this digit
+    for (int i0 = beg; i0 < end; i0 += 32) {
+      const int i = i0 + lane;
+      const bool valid = i < end;
+      const unsigned long long key = valid ? a[i] : 0;
+      const int d = valid ? (int)((key >> shift) & 255) : 256 + lane;
+      const unsigned m = __match_any_sync(FULL, d);
+      const int rank = __popc(m & ((1u << lane) - 1));
+      if (valid) b[s_off[w][d] + rank] = key;
+      __syncwarp();
+      if (valid && rank == 0) s_off[w][d] += __popc(m);
+      __syncwarp();
+    }
+    __syncthreads();
+    unsigned long long* tmp = a; a = b; b = tmp;
+  }
+  return a;
+}
+
+// One CTA per query with more than kWarpMax scored candidates. The candidate order is sorted as ONE packed
 // 64-bit key per record -- (1023 - match length) << 52 | s_id << 20 | record index -- in shared
 // memory (up to kHeavySmem records, else in global scratch); warp 0 then runs the replay.
 static const int kHeavySmem = 24576;
 __global__ void __launch_bounds__(256) fm_replay_heavy_kernel(fm_record* rec, const int32_t* __restrict__ q_cnt,
                                                               const int32_t* __restrict__ q_base, float* heapbuf,
-                                                              unsigned long long* sort_key, int32_t* sort_idx, int32_t* acc_cnt,
+                                                              unsigned long long* sort_key, unsigned long long* sort_key2,
+                                                              int32_t* sort_idx, int32_t* acc_cnt,
                                                               const int32_t* __restrict__ heavy_q,
                                                               const int32_t* __restrict__ q_off, Params pr, long long cap,
-                                                              fm_match* out, int32_t* out_count, Counters* ctr) {
+                                                              fm_match* out, int32_t* out_count, Counters* ctr, int smem_cap) {
   extern __shared__ unsigned long long s_keys[];
   __shared__ float s_heap[64];
   __shared__ int s_nacc;
+  __shared__ int s_tot[8];
+  __shared__ int s_flag;
   if (ctr->overflow) return;
   const int n_heavy = (int)ctr->n_heavy;
   for (int h = blockIdx.x; h < n_heavy; h += gridDim.x) {
@@ -1061,13 +1175,14 @@ __global__ void __launch_bounds__(256) fm_replay_heavy_kernel(fm_record* rec, co
     unsigned long long* gkeys = sort_key + base;
     int32_t* idx = sort_idx + base;
     if (n < (1 << 20)) {
-      unsigned long long* keys = n <= kHeavySmem ? s_keys : gkeys;
+      unsigned long long* keys = n <= smem_cap ? s_keys : gkeys;
       for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const fm_record r = seg[i];
         keys[i] = ((unsigned long long)(unsigned)(1023 - r.longest_match) << 52) | ((unsigned long long)r.s_id << 20) | (unsigned)i;
       }
       __syncthreads();
-      block_sort_keys(keys, n);
+      if (n <= smem_cap) block_sort_keys(keys, n);
+      else keys = block_radix_sort_keys(gkeys, sort_key2 + base, n, 20, 62, reinterpret_cast<int(*)[256]>(s_keys), s_tot, &s_flag);
       for (int i = threadIdx.x; i < n; i += blockDim.x) idx[i] = (int)(keys[i] & 0xfffffu);
     } else {
       for (int i = threadIdx.x; i < n; i += blockDim.x) { gkeys[i] = order_key(seg[i]); idx[i] = i; }
@@ -1247,20 +1362,22 @@ void launch_score(const IndexDev& ix, const BatchDev& b, const Params& p, int sm
   fm_score_kernel<<<sm_count * 4, 256, smem, st>>>(ix, b, p, stride, warp_only ? 0 : 33);
 }
 void launch_replay(const IndexDev& ix, const fm_record* rec, const int32_t* q_cnt, const int32_t* q_base, float* heapbuf,
-                   unsigned long long* sort_key, int32_t* sort_idx, int32_t* acc_cnt, int32_t* heavy_q, const int32_t* q_off,
-                   int32_t n_q, const Params& p, int64_t cap, fm_match* out, int32_t* out_count, Counters* ctr, int sm_count,
-                   cudaStream_t st) {
+                   unsigned long long* sort_key, unsigned long long* sort_key2, int32_t* sort_idx, int32_t* acc_cnt,
+                   int32_t* heavy_q, const int32_t* q_off, int32_t n_q, const Params& p, int64_t cap, fm_match* out,
+                   int32_t* out_count, Counters* ctr, int sm_count, cudaStream_t st) {
   const int grid = (n_q + 7) / 8;
   fm_replay_kernel<<<grid, 256, 0, st>>>(const_cast<fm_record*>(rec), q_cnt, q_base, heapbuf, sort_key, sort_idx, acc_cnt,
                                          heavy_q, q_off, n_q, p, (long long)cap, out, out_count, ctr);
   const size_t smem = (size_t)kHeavySmem * sizeof(unsigned long long);
+  // FM_HEAVY_SMEM=<n> lowers the shared-memory sort limit so that tests reach the radix-sort path
+  static const int smem_cap = getenv("FM_HEAVY_SMEM") ? std::max(64, std::min(kHeavySmem, atoi(getenv("FM_HEAVY_SMEM")))) : kHeavySmem;
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(fm_replay_heavy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done = true;
   }
-  fm_replay_heavy_kernel<<<sm_count * 2, 256, smem, st>>>(const_cast<fm_record*>(rec), q_cnt, q_base, heapbuf, sort_key, sort_idx,
-                                                          acc_cnt, heavy_q, q_off, p, (long long)cap, out, out_count, ctr);
+  fm_replay_heavy_kernel<<<sm_count * 2, 256, smem, st>>>(const_cast<fm_record*>(rec), q_cnt, q_base, heapbuf, sort_key, sort_key2,
+                                                          sort_idx, acc_cnt, heavy_q, q_off, p, (long long)cap, out, out_count, ctr, smem_cap);
 }
 void launch_contrast(const IndexDev& ix, fm_record* rec, const int32_t* q_base, const int32_t* sort_idx,
                      const int32_t* acc_cnt, int32_t n_q, const Params& p, int64_t cap, fm_match* out, int32_t* out_count, Counters* ctr, int sm_count,
