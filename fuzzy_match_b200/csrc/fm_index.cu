@@ -13,11 +13,23 @@
 #include <cstdio>
 #include <cstring>
 #include <numeric>
+#include <chrono>
 #include <thread>
 
 #include "fm_internal.h"
 
 namespace fm {
+
+struct PhaseTimer {
+  bool on = getenv("FM_BUILD_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!on) return;
+    const auto n = std::chrono::steady_clock::now();
+    fprintf(stderr, "[fm build] %-28s %.3f s\n", what, std::chrono::duration<double>(n - t).count());
+    t = n;
+  }
+};
 
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
@@ -147,6 +159,174 @@ int set_idf_stats(Index* ix, const uint32_t* sf, int64_t n_sent_global) {
   return FM_OK;
 }
 
+
+// ---------------------------------------------------------------- device side of the build
+// Once the token buffer and the sorted suffix array are in HBM, everything derived from them is
+// data-parallel and is built by these kernels instead of host loops: per-sentence signatures, the
+// per-suffix walk records, and the bigram / trigram directories (run boundaries of the suffix array
+// inserted into open-addressing tables with 64-bit CAS).
+
+__global__ void fm_build_sentence_kernel(const int32_t* __restrict__ tok, const int32_t* __restrict__ sent_start, int n_sent,
+                                         unsigned long long* sig, int32_t* sent_len, int32_t* sid_at) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_sent) return;
+  const int st = sent_start[s];
+  unsigned long long sg = 0;
+  int n = 0;
+  for (int t; (t = tok[st + n]) != 0; n++) sg |= 1ull << sig_bit(t);
+  sig[s] = sg;
+  sent_len[s] = n;
+  sid_at[st >> 2] = s;
+}
+
+__global__ void fm_build_walk_kernel(const int32_t* __restrict__ sa_pos, long long n_suf, const int32_t* __restrict__ sent_start,
+                                     int n_sent, const unsigned long long* __restrict__ sig,
+                                     const int32_t* __restrict__ sent_len, int4* sa_walk) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_suf) return;
+  const int pos = sa_pos[i];
+  int a = 0, e = n_sent;  // sentence whose start is the largest one <= pos
+  while (e - a > 1) {
+    const int mid = (a + e) >> 1;
+    if (sent_start[mid] <= pos) a = mid; else e = mid;
+  }
+  const unsigned long long sg = sig[a];
+  sa_walk[i] = make_int4(sent_start[a], sent_len[a], (int)(unsigned)sg, (int)(unsigned)(sg >> 32));
+}
+
+// counts[0] = distinct bigrams, counts[1] = distinct trigrams (run starts in the suffix array)
+__global__ void fm_count_runs_kernel(const int32_t* __restrict__ tok, const int32_t* __restrict__ sa_pos, long long n_suf,
+                                     unsigned long long* counts) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int bg = 0, tg = 0;
+  if (i < n_suf) {
+    const int p = sa_pos[i];
+    const int t0 = tok[p], t1 = tok[p + 1];
+    if (t1 != 0) {
+      const int t2 = tok[p + 2];
+      int q0 = -1, q1 = -1, q2 = -1;
+      if (i > 0) { const int pp = sa_pos[i - 1]; q0 = tok[pp]; q1 = tok[pp + 1]; q2 = q1 ? tok[pp + 2] : 0; }
+      bg = q0 != t0 || q1 != t1;
+      tg = t2 != 0 && (bg || q2 != t2);
+    }
+  }
+  const unsigned b1 = __ballot_sync(0xffffffffu, bg), b2 = __ballot_sync(0xffffffffu, tg);
+  if ((threadIdx.x & 31) == 0) {
+    if (b1) atomicAdd(&counts[0], (unsigned long long)__popc(b1));
+    if (b2) atomicAdd(&counts[1], (unsigned long long)__popc(b2));
+  }
+}
+
+__device__ __forceinline__ uint32_t dir_insert(int4* tab, uint32_t mask, int k0, int k1) {
+  const unsigned long long key = ((unsigned long long)(unsigned)k1 << 32) | (unsigned)k0;  // (x, y) little-endian
+  uint32_t h = bigram_hash(k0, k1) & mask;
+  for (;;) {
+    const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(tab + h), ~0ull, key);
+    if (prev == ~0ull || prev == key) return h;
+    h = (h + 1) & mask;
+  }
+}
+__device__ __forceinline__ uint32_t dir_find(const int4* tab, uint32_t mask, int k0, int k1) {
+  uint32_t h = bigram_hash(k0, k1) & mask;
+  while (!(tab[h].x == k0 && tab[h].y == k1)) h = (h + 1) & mask;
+  return h;
+}
+
+// pass 0: run starts insert their key and write lo; pass 1: run ends write hi (keys are all present)
+__global__ void fm_build_bigram_kernel(const int32_t* __restrict__ tok, const int32_t* __restrict__ sa_pos, long long n_suf,
+                                       int4* bg_tab, uint32_t bg_mask, int pass) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_suf) return;
+  const int p = sa_pos[i];
+  const int t0 = tok[p], t1 = tok[p + 1];
+  if (t1 == 0) return;
+  if (pass == 0) {
+    bool start = i == 0;
+    if (!start) { const int pp = sa_pos[i - 1]; start = tok[pp] != t0 || tok[pp + 1] != t1; }
+    if (start) bg_tab[dir_insert(bg_tab, bg_mask, t0, t1)].z = (int)i;
+  } else {
+    bool end = i == n_suf - 1;
+    if (!end) { const int pn = sa_pos[i + 1]; end = tok[pn] != t0 || tok[pn + 1] != t1; }
+    if (end) bg_tab[dir_find(bg_tab, bg_mask, t0, t1)].w = (int)(i + 1);
+  }
+}
+__global__ void fm_build_trigram_kernel(const int32_t* __restrict__ tok, const int32_t* __restrict__ sa_pos, long long n_suf,
+                                        const int4* __restrict__ bg_tab, uint32_t bg_mask, int4* tg_tab, uint32_t tg_mask,
+                                        int pass) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_suf) return;
+  const int p = sa_pos[i];
+  const int t0 = tok[p], t1 = tok[p + 1];
+  if (t1 == 0) return;
+  const int t2 = tok[p + 2];
+  if (t2 == 0) return;
+  const long long j = pass == 0 ? i - 1 : i + 1;
+  bool edge = j < 0 || j >= n_suf;
+  if (!edge) { const int pj = sa_pos[j]; edge = tok[pj] != t0 || tok[pj + 1] != t1 || tok[pj + 2] != t2; }
+  if (!edge) return;
+  const int bs = (int)dir_find(bg_tab, bg_mask, t0, t1);
+  if (pass == 0) tg_tab[dir_insert(tg_tab, tg_mask, bs, t2)].z = (int)i;
+  else tg_tab[dir_find(tg_tab, tg_mask, bs, t2)].w = (int)(i + 1);
+}
+
+template <class T>
+static int dev_alloc(Index* ix, int blk, size_t count, int fill_byte, const T** out) {
+  void* d = nullptr;
+  const size_t n = count * sizeof(T);
+  FM_CUDA(cudaMalloc(&d, n ? n : 16));
+  FM_CUDA(cudaMemset(d, fill_byte, n ? n : 16));
+  ix->d_blocks[blk] = d;
+  ix->blk_bytes[blk] = n;
+  ix->device_bytes += (int64_t)n;
+  *out = static_cast<const T*>(d);
+  return FM_OK;
+}
+
+// Builds sa_walk, sid_at and the two directories on the device from tok + sa_pos (already uploaded).
+static int build_on_device(Index* ix, const std::vector<int32_t>& sent_start) {
+  IndexDev& d = ix->dev;
+  const long long n_suf = ix->n_suf;
+  const int n_sent = (int)ix->n_sent;
+  int32_t* d_start = nullptr; int32_t* d_len = nullptr; unsigned long long* d_sig = nullptr; unsigned long long* d_counts = nullptr;
+  FM_CUDA(cudaMalloc((void**)&d_start, (size_t)(n_sent + 1) * 4));
+  FM_CUDA(cudaMalloc((void**)&d_len, (size_t)(n_sent + 1) * 4));
+  FM_CUDA(cudaMalloc((void**)&d_sig, (size_t)(n_sent + 1) * 8));
+  FM_CUDA(cudaMalloc((void**)&d_counts, 16));
+  FM_CUDA(cudaMemset(d_counts, 0, 16));
+  FM_CUDA(cudaMemcpy(d_start, sent_start.data(), (size_t)(n_sent + 1) * 4, cudaMemcpyHostToDevice));
+  int rc;
+  if ((rc = dev_alloc(ix, BLK_SID, (size_t)(ix->n_buf / 4) + 1, 0xff, &d.sid_at)) ||
+      (rc = dev_alloc(ix, BLK_WALK, (size_t)n_suf + 4, 0, &d.sa_walk)))
+    return rc;
+  const int tb = 256;
+  const unsigned gs = (unsigned)((n_suf + tb - 1) / tb);
+  if (n_sent > 0)
+    fm_build_sentence_kernel<<<(n_sent + tb - 1) / tb, tb>>>(d.tok, d_start, n_sent, d_sig, d_len, const_cast<int32_t*>(d.sid_at));
+  unsigned long long counts[2] = {0, 0};
+  if (n_suf > 0) {
+    fm_build_walk_kernel<<<gs, tb>>>(d.sa_pos, n_suf, d_start, n_sent, d_sig, d_len, const_cast<int4*>(d.sa_walk));
+    fm_count_runs_kernel<<<gs, tb>>>(d.tok, d.sa_pos, n_suf, d_counts);
+  }
+  FM_CUDA(cudaMemcpy(counts, d_counts, 16, cudaMemcpyDeviceToHost));
+  uint64_t cap_bg = 1024, cap_tg = 1024;
+  while (cap_bg < counts[0] * 2) cap_bg <<= 1;
+  while (cap_tg < counts[1] * 2) cap_tg <<= 1;
+  d.bg_mask = (uint32_t)(cap_bg - 1);
+  d.tg_mask = (uint32_t)(cap_tg - 1);
+  if ((rc = dev_alloc(ix, BLK_BG, (size_t)cap_bg, 0xff, &d.bg_tab)) || (rc = dev_alloc(ix, BLK_TG, (size_t)cap_tg, 0xff, &d.tg_tab)))
+    return rc;
+  if (n_suf > 0) {
+    fm_build_bigram_kernel<<<gs, tb>>>(d.tok, d.sa_pos, n_suf, const_cast<int4*>(d.bg_tab), d.bg_mask, 0);
+    fm_build_bigram_kernel<<<gs, tb>>>(d.tok, d.sa_pos, n_suf, const_cast<int4*>(d.bg_tab), d.bg_mask, 1);
+    fm_build_trigram_kernel<<<gs, tb>>>(d.tok, d.sa_pos, n_suf, d.bg_tab, d.bg_mask, const_cast<int4*>(d.tg_tab), d.tg_mask, 0);
+    fm_build_trigram_kernel<<<gs, tb>>>(d.tok, d.sa_pos, n_suf, d.bg_tab, d.bg_mask, const_cast<int4*>(d.tg_tab), d.tg_mask, 1);
+  }
+  FM_CUDA(cudaDeviceSynchronize());
+  FM_CUDA(cudaGetLastError());
+  cudaFree(d_start); cudaFree(d_len); cudaFree(d_sig); cudaFree(d_counts);
+  return FM_OK;
+}
+
 void free_index(Index* ix) {
   if (!ix) return;
   cudaSetDevice(ix->device);
@@ -190,8 +370,6 @@ int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_in, in
   ix->h_sent_start.resize((size_t)n_keep + 1);
   ix->kept.resize((size_t)n_keep);
   ix->sfreq.assign((size_t)vocab_size, 0);
-  std::vector<uint32_t> meta_of_pos((size_t)n_buf, 0);
-  std::vector<int32_t> sid_at((size_t)(n_buf / 4) + 1, -1);
   {
     std::vector<int64_t> stamp((size_t)vocab_size, -1);
     int64_t cur = 0, k = 0;
@@ -200,7 +378,6 @@ int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_in, in
       if (!(len > 0 && len <= max_tokens)) continue;
       ix->h_sent_start[k] = (int32_t)cur;
       ix->kept[k] = s;
-      sid_at[cur >> 2] = (int32_t)k;
       for (int64_t i = 0; i < len; i++) {
         const int32_t t = tokens[sent_off[s] + i];
         if (t < 2 || t >= vocab_size) {
@@ -209,7 +386,6 @@ int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_in, in
           return FM_ERR_INVALID;
         }
         ix->h_tok[cur + i] = t;
-        meta_of_pos[cur + i] = ((uint32_t)len << 16) | (uint32_t)i;
         if (stamp[t] != k) { stamp[t] = k; ix->sfreq[t]++; }
       }
       cur += (len + 1 + 3) & ~int64_t(3);
@@ -218,6 +394,8 @@ int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_in, in
     ix->h_sent_start[n_keep] = (int32_t)cur;
   }
 
+  PhaseTimer pt;
+  pt.lap("token buffer + sfreq");
   // ---- suffix sort: counting sort on the first token, then each bucket by the rest
   std::vector<int32_t> qva((size_t)vocab_size + 1, 0);
   std::vector<int32_t> sa((size_t)n_suf);
@@ -262,81 +440,7 @@ int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_in, in
     work();
     for (auto& t : pool) t.join();
   }
-  // per-suffix walk record: (sentence start, length, signature lo, signature hi)
-  std::vector<int4> sa_walk((size_t)n_suf);
-  {
-    std::vector<unsigned long long> sig_of_sent((size_t)n_keep, 0);
-    for (int64_t k = 0; k < n_keep; k++) {
-      unsigned long long sg = 0;
-      for (int32_t pos = ix->h_sent_start[k]; ix->h_tok[pos] != 0; pos++) sg |= 1ull << sig_bit(ix->h_tok[pos]);
-      sig_of_sent[k] = sg;
-    }
-    for (int64_t i = 0; i < n_suf; i++) {
-      const uint32_t m = meta_of_pos[sa[i]];
-      const int32_t start = sa[i] - (int32_t)(m & 0xffffu);
-      const unsigned long long sg = sig_of_sent[sid_at[start >> 2]];
-      sa_walk[i] = make_int4(start, (int32_t)(m >> 16), (int32_t)(uint32_t)sg, (int32_t)(uint32_t)(sg >> 32));
-    }
-  }
-  std::vector<uint32_t>().swap(meta_of_pos);
-
-  // ---- bigram directory: one entry per distinct (word0, word1) with its suffix-array range
-  std::vector<int4> bg_tab;
-  uint32_t bg_mask = 0;
-  {
-    const int32_t* tok = ix->h_tok.data();
-    int64_t n_bg = 0;
-    for (int64_t i2 = 0; i2 < n_suf; i2++) {
-      const int32_t t1 = tok[sa[i2] + 1];
-      if (t1 != 0 && (i2 == 0 || tok[sa[i2 - 1]] != tok[sa[i2]] || tok[sa[i2 - 1] + 1] != t1)) n_bg++;
-    }
-    uint64_t cap = 1024;
-    while (cap < (uint64_t)n_bg * 2) cap <<= 1;
-    bg_mask = (uint32_t)(cap - 1);
-    bg_tab.assign((size_t)cap, make_int4(-1, -1, 0, 0));
-    for (int64_t i2 = 0; i2 < n_suf;) {
-      const int32_t t0 = tok[sa[i2]], t1 = tok[sa[i2] + 1];
-      int64_t j2 = i2 + 1;
-      while (j2 < n_suf && tok[sa[j2]] == t0 && tok[sa[j2] + 1] == t1) j2++;
-      if (t1 != 0) {
-        uint32_t hsl = bigram_hash(t0, t1) & bg_mask;
-        while (bg_tab[hsl].x != -1) hsl = (hsl + 1) & bg_mask;
-        bg_tab[hsl] = make_int4(t0, t1, (int32_t)i2, (int32_t)j2);
-      }
-      i2 = j2;
-    }
-  }
-
-  // ---- trigram directory: (slot of the bigram in bg_tab, word2) -> suffix-array range
-  std::vector<int4> tg_tab;
-  uint32_t tg_mask = 0;
-  {
-    const int32_t* tok = ix->h_tok.data();
-    auto is_tri = [&](int64_t k) { return tok[sa[k] + 1] != 0 && tok[sa[k] + 2] != 0; };
-    auto same_tri = [&](int64_t a, int64_t b2) {
-      return tok[sa[a]] == tok[sa[b2]] && tok[sa[a] + 1] == tok[sa[b2] + 1] && tok[sa[a] + 2] == tok[sa[b2] + 2];
-    };
-    int64_t n_tg = 0;
-    for (int64_t k = 0; k < n_suf; k++)
-      if (is_tri(k) && (k == 0 || !same_tri(k - 1, k))) n_tg++;
-    uint64_t cap = 1024;
-    while (cap < (uint64_t)n_tg * 2) cap <<= 1;
-    tg_mask = (uint32_t)(cap - 1);
-    tg_tab.assign((size_t)cap, make_int4(-1, -1, 0, 0));
-    for (int64_t k = 0; k < n_suf;) {
-      int64_t j2 = k + 1;
-      if (!is_tri(k)) { k = j2; continue; }
-      while (j2 < n_suf && same_tri(k, j2)) j2++;
-      const int32_t t0 = tok[sa[k]], t1 = tok[sa[k] + 1], t2 = tok[sa[k] + 2];
-      uint32_t bs = bigram_hash(t0, t1) & bg_mask;
-      while (!(bg_tab[bs].x == t0 && bg_tab[bs].y == t1)) bs = (bs + 1) & bg_mask;
-      uint32_t hsl = bigram_hash((int32_t)bs, t2) & tg_mask;
-      while (tg_tab[hsl].x != -1) hsl = (hsl + 1) & tg_mask;
-      tg_tab[hsl] = make_int4((int32_t)bs, t2, (int32_t)k, (int32_t)j2);
-      k = j2;
-    }
-  }
-
+  pt.lap("suffix sort");
   // ---- upload
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) { delete ix; return cuda_fail(e, "cudaSetDevice"); }
@@ -346,18 +450,14 @@ int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_in, in
   IndexDev& d = ix->dev;
   if ((rc = upload(ix->h_tok, 0, ix, BLK_TOK, &d.tok)) ||
       (rc = upload(sa, 4, ix, BLK_SA, &d.sa_pos)) ||
-      (rc = upload(sa_walk, 4, ix, BLK_WALK, &d.sa_walk)) ||
       (rc = upload(qva, 0, ix, BLK_QVA, &d.qva)) ||
-      (rc = upload(bg_tab, 0, ix, BLK_BG, &d.bg_tab)) ||
-      (rc = upload(tg_tab, 0, ix, BLK_TG, &d.tg_tab)) ||
-      (rc = upload(sid_at, 0, ix, BLK_SID, &d.sid_at)) ||
+      (rc = build_on_device(ix, ix->h_sent_start)) ||
       (rc = upload(std::vector<float>((size_t)vocab_size, 0.f), 0, ix, BLK_IDF, &d.idf)) ||
       (rc = set_idf_stats(ix, sfreq_global ? sfreq_global : ix->sfreq.data(), n_sent_global > 0 ? n_sent_global : n_keep))) {
     free_index(ix);
     return rc;
   }
-  d.bg_mask = bg_mask;
-  d.tg_mask = tg_mask;
+  pt.lap("upload + device build");
   d.vocab_size = vocab_size;
   d.max_tokens = max_tokens;
   d.n_suf = n_suf;
