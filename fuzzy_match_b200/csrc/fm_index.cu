@@ -1,12 +1,13 @@
-// fm_index.cu -- host-side index build and upload.
+// fm_index.cu -- index build, upload, save / load.
 //
 // Replaces, for pre-tokenised int32 input, what the reference does in FuzzyMatch::add_tm(Tokens) +
 // sort() (reference src/suffix_array_index.cc:10-30, src/suffix_array.cc:9-27,58-102,253-261,
 // src/vocab_indexer.cc:73-90): drop empty / over-long sentences, count word-in-sentence
 // frequencies, sort the sentence-bounded suffixes and build the first-word bucket table.
-// The order among suffixes that compare equal is immaterial to match() (ranges are sets), so any
-// total order works; here ties break by position, which equals the reference's sentence-id order.
-// The build runs on host threads for now (a GPU build is the first "next" row of SURVEY.md 8f).
+// The host only lays out the token buffer, counts sfreq and the bucket table (one pass over the
+// tokens); the suffix sort (fm_sort.cu) and everything derived from the sorted array (walk records,
+// signatures, bigram / trigram directories, kernels below) run on the GPU. The order among suffixes
+// that compare equal is immaterial to match() (ranges are sets), so any total order works.
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -396,18 +397,31 @@ int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_in, in
 
   PhaseTimer pt;
   pt.lap("token buffer + sfreq");
-  // ---- suffix sort: counting sort on the first token, then each bucket by the rest
+  // ---- first-word bucket table (reference _quickVocabAccess, src/suffix_array.cc:82-98)
   std::vector<int32_t> qva((size_t)vocab_size + 1, 0);
-  std::vector<int32_t> sa((size_t)n_suf);
+  std::vector<int32_t> compact_off((size_t)n_keep + 1, 0);  // suffixes before each sentence
+  int max_len = 0;
   {
     std::vector<int64_t> cnt((size_t)vocab_size + 1, 0);
-    for (int64_t k = 0; k < n_keep; k++)
-      for (int32_t pos = ix->h_sent_start[k]; ix->h_tok[pos] != 0; pos++) cnt[ix->h_tok[pos] + 1]++;
+    for (int64_t k = 0; k < n_keep; k++) {
+      int32_t len = 0;
+      for (int32_t pos = ix->h_sent_start[k]; ix->h_tok[pos] != 0; pos++, len++) cnt[ix->h_tok[pos] + 1]++;
+      compact_off[k + 1] = compact_off[k] + len;
+      max_len = std::max(max_len, (int)len);
+    }
     for (int32_t w = 0; w < vocab_size; w++) cnt[w + 1] += cnt[w];
     for (int32_t w = 0; w <= vocab_size; w++) qva[w] = (int32_t)cnt[w];
-    for (int64_t k = 0; k < n_keep; k++)
-      for (int32_t pos = ix->h_sent_start[k]; ix->h_tok[pos] != 0; pos++) sa[cnt[ix->h_tok[pos]]++] = pos;
   }
+  // ---- suffix sort: on the GPU (fm_sort.cu); FM_HOST_SORT=1 keeps the host-thread sort for cross-checks
+  const bool host_sort = getenv("FM_HOST_SORT") != nullptr;
+  std::vector<int32_t> sa;
+  if (host_sort) {
+    sa.resize((size_t)n_suf);
+    {
+      std::vector<int64_t> cnt(qva.begin(), qva.end());
+      for (int64_t k = 0; k < n_keep; k++)
+        for (int32_t pos = ix->h_sent_start[k]; ix->h_tok[pos] != 0; pos++) sa[cnt[ix->h_tok[pos]]++] = pos;
+    }
   {
     std::vector<int32_t> order;  // non-trivial buckets, largest first
     for (int32_t w = 2; w < vocab_size; w++)
@@ -440,7 +454,8 @@ int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_in, in
     work();
     for (auto& t : pool) t.join();
   }
-  pt.lap("suffix sort");
+  }
+  pt.lap("host tables (+ host sort)");
   // ---- upload
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) { delete ix; return cuda_fail(e, "cudaSetDevice"); }
@@ -448,8 +463,14 @@ int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_in, in
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ix->sm_count = prop.multiProcessorCount;
   int rc;
   IndexDev& d = ix->dev;
-  if ((rc = upload(ix->h_tok, 0, ix, BLK_TOK, &d.tok)) ||
-      (rc = upload(sa, 4, ix, BLK_SA, &d.sa_pos)) ||
+  rc = upload(ix->h_tok, 0, ix, BLK_TOK, &d.tok);
+  pt.lap("upload tokens");
+  if (!rc) rc = host_sort ? upload(sa, 4, ix, BLK_SA, &d.sa_pos) : dev_alloc(ix, BLK_SA, (size_t)n_suf + 4, 0, &d.sa_pos);
+  if (!rc && !host_sort)
+    rc = gpu_suffix_sort(d.tok, n_buf, ix->h_sent_start, compact_off, n_suf, max_len, vocab_size, ix->sm_count,
+                         const_cast<int32_t*>(d.sa_pos));
+  pt.lap("suffix sort (device)");
+  if (rc ||
       (rc = upload(qva, 0, ix, BLK_QVA, &d.qva)) ||
       (rc = build_on_device(ix, ix->h_sent_start)) ||
       (rc = upload(std::vector<float>((size_t)vocab_size, 0.f), 0, ix, BLK_IDF, &d.idf)) ||
@@ -457,7 +478,7 @@ int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_in, in
     free_index(ix);
     return rc;
   }
-  pt.lap("upload + device build");
+  pt.lap("walk records + directories");
   d.vocab_size = vocab_size;
   d.max_tokens = max_tokens;
   d.n_suf = n_suf;

@@ -218,6 +218,11 @@ int save_index(const Index* ix, const char* path);
 int load_index(const char* path, int device, Index** out);
 int set_idf_stats(Index* ix, const uint32_t* sfreq, int64_t n_sent_global);
 
+// fm_sort.cu
+int gpu_suffix_sort(const int32_t* d_tok, int64_t n_buf, const std::vector<int32_t>& sent_start,
+                    const std::vector<int32_t>& compact_off, int64_t n_suf, int max_len, int32_t vocab_size, int sm_count,
+                    int32_t* d_sa);
+
 // fm_kernels.cu -- launchers (all asynchronous on `st`)
 void launch_bounds(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st);
 void launch_prepare(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st);

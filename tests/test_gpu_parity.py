@@ -279,3 +279,24 @@ def test_concurrent_host_threads(medium):
         ro, oc = oracle.match_batch(q, qo, cap=4, **params[k])
         assert (cnt == oc).all()
         assert all(out[i, :cnt[i]].tobytes() == ro[i].tobytes() for i in range(len(oc)))
+
+
+def test_gpu_suffix_sort_matches_host_sort(monkeypatch):
+    """The GPU-built index (prefix-doubling suffix sort, fm_sort.cu) and the host-thread build
+    (FM_HOST_SORT=1, comparator sort like SuffixArray::sort) must answer identically, including on a TM
+    full of repeated sentences (true ties in the suffix order)."""
+    tm, off, V = synth.make_tm(4000, vocab=25, len_lo=1, len_hi=40, seed=301)
+    tm = np.concatenate([tm, tm[:off[500]]])              # 500 duplicated sentences
+    off = np.concatenate([off, off[-1] + off[1:501]])
+    q, qo = synth.make_queries(tm, off, 300, vocab=25, seed=302, len_lo=1, len_hi=40)
+    gpu_built = fmb.Index(tm, off, V)
+    monkeypatch.setenv("FM_HOST_SORT", "1")
+    host_built = fmb.Index(tm, off, V)
+    monkeypatch.delenv("FM_HOST_SORT")
+    oracle = ob.OracleIndex(tm, off, V)
+    for params in (dict(fuzzy=0.5, n=5, ml=2), dict(fuzzy=0.3, n=0, ml=3, idf=1.0), dict(fuzzy=0.6, n=3, ml=1, costs=(1, 0, 1))):
+        a, ca = gpu_built.match_batch(q, qo, cap=64, **params)
+        b, cb = host_built.match_batch(q, qo, cap=64, **params)
+        assert (ca == cb).all() and a.tobytes() == b.tobytes()
+        ro, oc = oracle.match_batch(q, qo, cap=64, **params)
+        assert (ca == oc).all() and all(a[i, :min(ca[i], 64)].tobytes() == ro[i].tobytes() for i in range(len(oc)))
