@@ -92,3 +92,28 @@ def make_queries(tm_tokens, tm_off, n_q, vocab=50000, seed=5678, len_lo=5, len_h
     q_off = np.zeros(n_q + 1, dtype=np.int64)
     np.cumsum(full_len, out=q_off[1:])
     return out, q_off
+
+
+ITOKS = [b"", b" ", b",", b".", b"T", b", ", b"...", b"(", b")"]  # id 0 = no penalty token
+
+
+def itok_table(itoks=ITOKS):
+    """(blob uint8, off int32[K+1]) of the penalty-token strings; id 0 is the empty string."""
+    off = np.zeros(len(itoks) + 1, dtype=np.int32)
+    np.cumsum([len(x) for x in itoks], out=off[1:])
+    return np.frombuffer(b"".join(itoks) + b"\0", dtype=np.uint8).copy(), off
+
+
+def make_real(tokens, off, seed, p_variant=0.15, p_case=0.1, p_itok=0.15, n_itok=len(ITOKS)):
+    """Synthetic real tokens and penalty tokens for the Sentence API: real[k] = (form id << 1) | case class,
+    where the form id is word*4 + variant; gaps = n+1 itok ids per sentence at off[s] + s."""
+    n_tok, n_sent = len(tokens), len(off) - 1
+    u = _uniform(seed, 11, n_tok)
+    variant = (u < p_variant).astype(np.int32)
+    cls = (_uniform(seed, 12, n_tok) < p_case).astype(np.int32)
+    real = (((tokens.astype(np.int64) * 4 + variant) << 1) | cls).astype(np.int32)
+    n_gap = n_tok + n_sent
+    ug = _uniform(seed, 13, n_gap)
+    pick = (1 + np.floor(_uniform(seed, 14, n_gap) * (n_itok - 1))).astype(np.int32)
+    gaps = np.where(ug < p_itok, pick, 0).astype(np.int32)
+    return real, gaps

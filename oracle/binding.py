@@ -128,6 +128,29 @@ class OracleIndex:
             return res, cnt, dict(zip(COUNTER_NAMES, list(ct)))
         return res, cnt
 
+    def set_real(self, real, gaps, off, itok_blob, itok_off):
+        """Attach real tokens / penalty tokens (Sentence API) to the indexed sentences."""
+        real = np.ascontiguousarray(real, dtype=np.int32)
+        gaps = np.ascontiguousarray(gaps, dtype=np.int32)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        self._itok = (np.ascontiguousarray(itok_blob, dtype=np.uint8), np.ascontiguousarray(itok_off, dtype=np.int32))
+        rc = self.lib.fmo_index_set_real(self.h, _ptr(real), _ptr(gaps), _ptr(off), _ptr(self._itok[0]), _ptr(self._itok[1]),
+                                         C.c_int32(len(itok_off) - 1))
+        if rc:
+            raise ValueError("fmo_index_set_real failed (itok id out of range)")
+
+    def match_batch_real(self, q_tokens, q_real, q_gaps, q_off, cap=16, nthreads=1, **kw):
+        q_tokens, q_off = _csr(q_tokens, q_off)
+        q_real = np.ascontiguousarray(q_real, dtype=np.int32)
+        q_gaps = np.ascontiguousarray(q_gaps, dtype=np.int32)
+        n_q = len(q_off) - 1
+        p = make_params(Params, **kw)
+        out = np.zeros(n_q * cap, dtype=MATCH_DTYPE)
+        cnt = np.zeros(n_q, dtype=np.int32)
+        self.lib.fmo_match_batch_real(self.h, _ptr(q_tokens), _ptr(q_real), _ptr(q_gaps), _ptr(q_off), C.c_int64(n_q), C.byref(p),
+                                      C.c_int(nthreads), C.c_int64(cap), _ptr(out), _ptr(cnt), None)
+        return _split(out, cnt, cap), cnt
+
     def match_debug(self, pattern, cap=64, dbg_cap=4096, **kw):
         pattern = np.ascontiguousarray(pattern, dtype=np.int32)
         p = make_params(Params, **kw)
@@ -145,22 +168,53 @@ class OracleIndex:
         return lo.value, hi.value
 
 
+def _scrub_uninitialised_penalty(res):
+    """FuzzyMatch::Match::penalty is never initialised (include/fuzzy/fuzzy_match.hh:34-40); the first match
+    picked by the contrastive rerank therefore carries stack garbage (observed: a denormal). The reference's
+    own tests rely on it reading as 0 (test/test.cc:537), so report 0."""
+    for r in res:
+        r["penalty"][~(np.abs(r["penalty"]) >= 1e-30)] = 0.0
+    return res
+
+
 def ref_available():
     return os.path.exists(REF_SO)
 
 
 class RefIndex:
-    """The unmodified reference (fuzzy::FuzzyMatch) behind oracle/ref_driver.cc."""
+    """The unmodified reference (fuzzy::FuzzyMatch) behind oracle/ref_driver.cc. With real / gaps / itok
+    table it is built through add_tm(id, Sentence, Tokens) and queried through match(Sentence, Tokens, ...)."""
 
-    def __init__(self, tokens, off, max_tokens=300):
+    def __init__(self, tokens, off, max_tokens=300, real=None, gaps=None, itok_blob=None, itok_off=None):
         self.lib = lib = C.CDLL(REF_SO)
         lib.fmref_create.restype = C.c_void_p
         lib.fmref_match_batch.restype = C.c_double
+        lib.fmref_match_batch_real.restype = C.c_double
         tokens, off = _csr(tokens, off)
         self.h = C.c_void_p(lib.fmref_create(C.c_int(max_tokens)))
-        lib.fmref_add_tm(self.h, _ptr(tokens), _ptr(off), C.c_int64(len(off) - 1))
+        if real is None:
+            lib.fmref_add_tm(self.h, _ptr(tokens), _ptr(off), C.c_int64(len(off) - 1))
+        else:
+            real = np.ascontiguousarray(real, dtype=np.int32)
+            gaps = np.ascontiguousarray(gaps, dtype=np.int32)
+            self._itok = (np.ascontiguousarray(itok_blob, dtype=np.uint8), np.ascontiguousarray(itok_off, dtype=np.int32))
+            lib.fmref_add_tm_real(self.h, _ptr(tokens), _ptr(real), _ptr(gaps), _ptr(off), C.c_int64(len(off) - 1),
+                                  _ptr(self._itok[0]), _ptr(self._itok[1]))
         lib.fmref_sort(self.h)
         self.last_seconds = 0.0
+
+    def match_batch_real(self, q_tokens, q_real, q_gaps, q_off, cap=16, nthreads=1, no_perfect=False, **kw):
+        q_tokens, q_off = _csr(q_tokens, q_off)
+        q_real = np.ascontiguousarray(q_real, dtype=np.int32)
+        q_gaps = np.ascontiguousarray(q_gaps, dtype=np.int32)
+        n_q = len(q_off) - 1
+        p = make_params(RefParams, **kw)
+        out = np.zeros(n_q * cap, dtype=REF_MATCH_DTYPE)
+        cnt = np.zeros(n_q, dtype=np.int32)
+        self.last_seconds = self.lib.fmref_match_batch_real(self.h, _ptr(q_tokens), _ptr(q_real), _ptr(q_gaps), _ptr(q_off),
+                                                            C.c_int64(n_q), C.byref(p), C.c_int(int(no_perfect)), C.c_int(nthreads),
+                                                            C.c_int64(cap), _ptr(out), _ptr(cnt), _ptr(self._itok[0]), _ptr(self._itok[1]))
+        return _scrub_uninitialised_penalty(_split(out, cnt, cap)), cnt
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -175,4 +229,4 @@ class RefIndex:
         cnt = np.zeros(n_q, dtype=np.int32)
         self.last_seconds = self.lib.fmref_match_batch(self.h, _ptr(q_tokens), _ptr(q_off), C.c_int64(n_q), C.byref(p),
                                                        C.c_int(nthreads), C.c_int64(cap), _ptr(out), _ptr(cnt))
-        return _split(out, cnt, cap), cnt
+        return _scrub_uninitialised_penalty(_split(out, cnt, cap)), cnt

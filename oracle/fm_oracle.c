@@ -92,6 +92,10 @@ typedef struct fmo_index {
   uint32_t* sfreq;   /* [vocab_size] number of sentences containing the word */
   int64_t n_sent_global;
   int64_t* kept_src; /* [n_sent] index of each kept sentence in the caller's CSR */
+  /* optional real tokens / penalty tokens (Sentence API), same layout as buf */
+  int32_t* real;     /* (real form id << 1) | case class, per token */
+  int32_t* gap;      /* itok id of the gap before each token; the separator slot holds the trailing gap */
+  char* itok_blob; int32_t* itok_off; int32_t n_itok; /* itok strings, id 0 = none (empty) */
 } fmo_index;
 
 /* ------------------------------------------------------------------ index build */
@@ -221,7 +225,7 @@ fmo_index* fmo_index_create(const int32_t* tokens, const int64_t* off, int64_t n
 void fmo_index_destroy(fmo_index* ix) {
   if (!ix) return;
   free(ix->buf); free(ix->sent_pos); free(ix->sa_pos); free(ix->sa_sid); free(ix->sa_len);
-  free(ix->qva); free(ix->sfreq); free(ix->kept_src); free(ix);
+  free(ix->qva); free(ix->sfreq); free(ix->kept_src); free(ix->real); free(ix->gap); free(ix->itok_blob); free(ix->itok_off); free(ix);
 }
 
 int64_t fmo_index_num_sentences(const fmo_index* ix) { return ix->n_sent; }
@@ -392,6 +396,95 @@ static float edit_distance_plain(const int32_t* s1, int n1, const int32_t* s2, i
   return prev[n2];
 }
 
+/* _edit_distance_char (reference include/fuzzy/edit_distance.hxx:7-35) on two penalty-token strings */
+static int edit_distance_char(const char* s1, int n1, const char* s2, int n2) {
+  if (n1 == 0) return n2;
+  if (n2 == 0) return n1;
+  int prev[64], cur[64];
+  if (n2 > 62) n2 = 62; /* itoks are a few characters */
+  for (int j = 0; j <= n2; j++) prev[j] = j;
+  for (int i = 1; i <= n1; i++) {
+    cur[0] = i;
+    for (int j = 1; j <= n2; j++) {
+      int d = prev[j] + 1;
+      if (cur[j - 1] + 1 < d) d = cur[j - 1] + 1;
+      const int c = prev[j - 1] + (s1[i - 1] == s2[j - 1] ? 0 : 1);
+      if (c < d) d = c;
+      cur[j] = d;
+    }
+    memcpy(prev, cur, sizeof(int) * (size_t)(n2 + 1));
+  }
+  return prev[n2];
+}
+static int itok_len(const fmo_index* ix, int id) { return ix->itok_off[id + 1] - ix->itok_off[id]; }
+static int cost_tag(const fmo_index* ix, int a, int b) {
+  return edit_distance_char(ix->itok_blob + ix->itok_off[a], itok_len(ix, a), ix->itok_blob + ix->itok_off[b], itok_len(ix, b));
+}
+
+/* _edit_distance, full variant WITH real-token and penalty-token terms (reference
+ * src/edit_distance.cc:5-77). g1 / g2: itok ids of the n1+1 / n2+1 gaps; r1 / r2: real tokens. */
+static float edit_distance_real(const fmo_index* ix, const int32_t* s1, const int32_t* r1, const int32_t* g1, int n1,
+                                const int32_t* s2, const int32_t* r2, const int32_t* g2, int n2, const float* idf_penalty,
+                                float idf_weight, const fmo_params* pr, float diff_word, float max_fuzzyness,
+                                float* rowmin_max, float* scratch) {
+  float* prev = scratch;
+  float* cur = scratch + (n2 + 1);
+  prev[0] = (float)cost_tag(ix, g1[n1], g2[n2]); /* :25 trailing penalty tokens */
+  for (int j = 1; j < n2 + 1; j++) {
+    prev[j] = prev[j - 1] + diff_word * pr->insert_cost + itok_len(ix, g2[j]); /* :35 */
+    if (idf_weight) prev[j] += idf_penalty[j - 1] * idf_weight;
+  }
+  float col0 = prev[0], kmax = -FLT_MAX;
+  for (int i = 1; i < n1 + 1; i++) {
+    col0 = col0 + diff_word * pr->delete_cost + itok_len(ix, g1[i]); /* :30 */
+    cur[0] = col0;
+    float min = FLT_MAX;
+    for (int j = 1; j < n2 + 1; j++) {
+      float diff = 0.f, penalty_j1 = 0.f;
+      if (idf_weight) penalty_j1 = idf_penalty[j - 1] * idf_weight;
+      if (s1[i - 1] != s2[j - 1]) diff = pr->replace_cost * diff_word + penalty_j1;
+      else if (r1[i - 1] != r2[j - 1]) diff = (r1[i - 1] & 1) ? pr->replace_cost * 1.0f : pr->replace_cost * 2.0f; /* :53-59 */
+      const float a = prev[j] + pr->delete_cost * diff_word + cost_tag(ix, g1[i - 1], g2[j]);
+      const float b = cur[j - 1] + pr->insert_cost * diff_word + cost_tag(ix, g1[i], g2[j - 1]) + penalty_j1;
+      const float c = prev[j - 1] + diff + cost_tag(ix, g1[i - 1], g2[j - 1]);
+      float d = a < b ? a : b;
+      d = c < d ? c : d;
+      cur[j] = d;
+      if (d < min) min = d;
+    }
+    if (min > kmax) kmax = min;
+    if (min > max_fuzzyness) { if (rowmin_max) *rowmin_max = kmax; return min; }
+    float* t = prev; prev = cur; cur = t;
+  }
+  if (rowmin_max) *rowmin_max = kmax;
+  return prev[n2];
+}
+
+/* Attach real tokens / penalty tokens to the indexed sentences (FuzzyMatch::add_tm(id, Sentence, Tokens),
+ * reference include/fuzzy/fuzzy_match.hh:53). real / gaps follow the CSR given to fmo_index_create:
+ * real[off[s] + i], gaps[off[s] + s + i] (n+1 gaps per sentence). */
+int fmo_index_set_real(fmo_index* ix, const int32_t* real, const int32_t* gaps, const int64_t* off, const char* itok_blob,
+                       const int32_t* itok_off, int32_t n_itok) {
+  const int64_t total = ix->sent_pos[ix->n_sent];
+  ix->real = (int32_t*)calloc((size_t)total + 1, 4);
+  ix->gap = (int32_t*)calloc((size_t)total + 1, 4);
+  for (int64_t k = 0; k < ix->n_sent; k++) {
+    const int64_t s = ix->kept_src[k], n = ix->sent_pos[k + 1] - ix->sent_pos[k] - 1;
+    for (int64_t i = 0; i < n; i++) ix->real[ix->sent_pos[k] + i] = real[off[s] + i];
+    for (int64_t i = 0; i <= n; i++) {
+      const int32_t g = gaps[off[s] + s + i];
+      if (g < 0 || g >= n_itok) return 1;
+      ix->gap[ix->sent_pos[k] + i] = g;
+    }
+  }
+  ix->n_itok = n_itok;
+  ix->itok_off = (int32_t*)malloc((size_t)(n_itok + 1) * 4);
+  memcpy(ix->itok_off, itok_off, (size_t)(n_itok + 1) * 4);
+  ix->itok_blob = (char*)malloc((size_t)itok_off[n_itok] + 1);
+  memcpy(ix->itok_blob, itok_blob, (size_t)itok_off[n_itok]);
+  return 0;
+}
+
 /* ------------------------------------------------------------------ per-thread scratch */
 
 typedef struct { uint32_t sid; uint32_t lm; } sidlm;
@@ -493,9 +586,9 @@ static void register_range(const fmo_index* ix, scratch_t* sc, int64_t begin, in
 /* FuzzyMatch::match core (reference src/fuzzy_match.cc:435-681). Writes up to cap matches, returns
  * the number the reference would append. dbg (optional, dbg_cap entries) receives the candidate
  * records in processing order; *dbg_n their count. */
-static int64_t match_one(const fmo_index* ix, const int32_t* pattern_in, int64_t p_length, const fmo_params* pr,
-                         scratch_t* sc, fmo_match* out, int64_t cap, fmo_counters* ct, fmo_candidate* dbg,
-                         int64_t dbg_cap, int64_t* dbg_n) {
+static int64_t match_one(const fmo_index* ix, const int32_t* pattern_in, const int32_t* p_real, const int32_t* p_gap,
+                         int64_t p_length, const fmo_params* pr, scratch_t* sc, fmo_match* out, int64_t cap,
+                         fmo_counters* ct, fmo_candidate* dbg, int64_t dbg_cap, int64_t* dbg_n) {
   if (dbg_n) *dbg_n = 0;
   if (ct) ct->queries++;
   int contrast_buffer = pr->contrast_buffer;
@@ -593,12 +686,25 @@ static int64_t match_one(const fmo_index* ix, const int32_t* pattern_in, int64_t
     const float cost_upper_bound = sc->heap[0];
     const float idf_weight = diff_word * vocab_idf_penalty / idf_max;
     if (ct) { ct->dp_pairs++; ct->dp_tokens += s_length; ct->dp_cells += s_length * p_length; }
-    const float cost = edit_distance_full(sentence, (int)s_length, pattern, (int)p_length, sc->idf, idf_weight, pr,
-                                          diff_word, cost_upper_bound, NULL, sc->dp);
-    if (d) {
-      d->rejected = 0;
-      d->cost_full = edit_distance_full(sentence, (int)s_length, pattern, (int)p_length, sc->idf, idf_weight, pr,
-                                        diff_word, FLT_MAX, &d->rowmin_max, sc->dp);
+    float cost;
+    if (p_real && ix->real) { /* Sentence API: real-token and penalty-token terms */
+      const int32_t* r1 = ix->real + ix->sent_pos[s_id];
+      const int32_t* g1 = ix->gap + ix->sent_pos[s_id];
+      cost = edit_distance_real(ix, sentence, r1, g1, (int)s_length, pattern, p_real, p_gap, (int)p_length, sc->idf,
+                                idf_weight, pr, diff_word, cost_upper_bound, NULL, sc->dp);
+      if (d) {
+        d->rejected = 0;
+        d->cost_full = edit_distance_real(ix, sentence, r1, g1, (int)s_length, pattern, p_real, p_gap, (int)p_length,
+                                          sc->idf, idf_weight, pr, diff_word, FLT_MAX, &d->rowmin_max, sc->dp);
+      }
+    } else {
+      cost = edit_distance_full(sentence, (int)s_length, pattern, (int)p_length, sc->idf, idf_weight, pr, diff_word,
+                                cost_upper_bound, NULL, sc->dp);
+      if (d) {
+        d->rejected = 0;
+        d->cost_full = edit_distance_full(sentence, (int)s_length, pattern, (int)p_length, sc->idf, idf_weight, pr,
+                                          diff_word, FLT_MAX, &d->rowmin_max, sc->dp);
+      }
     }
     if ((pr->no_perfect && cost == 0 && s_length == p_length) || cost > cost_upper_bound) continue;
     const float score = (float)((int)(10000 - cost * 100) / 10000.0);
@@ -676,6 +782,7 @@ static int64_t match_one(const fmo_index* ix, const int32_t* pattern_in, int64_t
 typedef struct job_t {
   const fmo_index* ix;
   const int32_t* q_tokens; const int64_t* q_off; int64_t n_q;
+  const int32_t* q_real; const int32_t* q_gaps; /* optional (Sentence API) */
   const fmo_params* pr;
   int64_t cap; fmo_match* out; int32_t* out_count;
   int64_t next; pthread_mutex_t mu;
@@ -692,7 +799,8 @@ static void* worker(void* arg) {
     if (q0 >= jb->n_q) break;
     const int64_t q1 = q0 + 16 < jb->n_q ? q0 + 16 : jb->n_q;
     for (int64_t q = q0; q < q1; q++) {
-      const int64_t n = match_one(jb->ix, jb->q_tokens + jb->q_off[q], jb->q_off[q + 1] - jb->q_off[q], jb->pr, &sc,
+      const int64_t n = match_one(jb->ix, jb->q_tokens + jb->q_off[q], jb->q_real ? jb->q_real + jb->q_off[q] : NULL,
+                                  jb->q_gaps ? jb->q_gaps + jb->q_off[q] + q : NULL, jb->q_off[q + 1] - jb->q_off[q], jb->pr, &sc,
                                   jb->out ? jb->out + q * jb->cap : NULL, jb->cap, jb->want_counters ? &ct : NULL, NULL, 0, NULL);
       if (jb->out_count) jb->out_count[q] = (int32_t)n;
     }
@@ -709,11 +817,21 @@ static void* worker(void* arg) {
 
 /* Matches n_q queries (CSR) with nthreads workers sharing the index. out is [n_q*cap];
  * out_count[q] is the number of matches the reference would return (may exceed cap). */
+void fmo_match_batch_real(const fmo_index* ix, const int32_t* q_tokens, const int32_t* q_real, const int32_t* q_gaps,
+                          const int64_t* q_off, int64_t n_q, const fmo_params* pr, int nthreads, int64_t cap,
+                          fmo_match* out, int32_t* out_count, fmo_counters* counters);
 void fmo_match_batch(const fmo_index* ix, const int32_t* q_tokens, const int64_t* q_off, int64_t n_q,
                      const fmo_params* pr, int nthreads, int64_t cap, fmo_match* out, int32_t* out_count,
                      fmo_counters* counters) {
+  fmo_match_batch_real(ix, q_tokens, NULL, NULL, q_off, n_q, pr, nthreads, cap, out, out_count, counters);
+}
+/* Same with the pattern's real tokens and penalty tokens (match(const Sentence& real, const Tokens&, ...),
+ * reference include/fuzzy/fuzzy_match.hh:70-82); q_gaps holds n+1 itok ids per query at q_off[q] + q. */
+void fmo_match_batch_real(const fmo_index* ix, const int32_t* q_tokens, const int32_t* q_real, const int32_t* q_gaps,
+                          const int64_t* q_off, int64_t n_q, const fmo_params* pr, int nthreads, int64_t cap,
+                          fmo_match* out, int32_t* out_count, fmo_counters* counters) {
   job_t jb; memset(&jb, 0, sizeof jb);
-  jb.ix = ix; jb.q_tokens = q_tokens; jb.q_off = q_off; jb.n_q = n_q; jb.pr = pr;
+  jb.ix = ix; jb.q_tokens = q_tokens; jb.q_off = q_off; jb.n_q = n_q; jb.pr = pr; jb.q_real = q_real; jb.q_gaps = q_gaps;
   jb.cap = cap; jb.out = out; jb.out_count = out_count; jb.want_counters = counters != NULL;
   pthread_mutex_init(&jb.mu, NULL);
   if (nthreads <= 1) {
@@ -733,7 +851,7 @@ void fmo_match_batch(const fmo_index* ix, const int32_t* q_tokens, const int64_t
 int64_t fmo_match_debug(const fmo_index* ix, const int32_t* pattern, int64_t p_length, const fmo_params* pr,
                         int64_t cap, fmo_match* out, fmo_candidate* dbg, int64_t dbg_cap, int64_t* dbg_n) {
   scratch_t sc; memset(&sc, 0, sizeof sc);
-  const int64_t n = match_one(ix, pattern, p_length, pr, &sc, out, cap, NULL, dbg, dbg_cap, dbg_n);
+  const int64_t n = match_one(ix, pattern, NULL, NULL, p_length, pr, &sc, out, cap, NULL, dbg, dbg_cap, dbg_n);
   scratch_free(&sc);
   return n;
 }

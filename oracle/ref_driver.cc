@@ -113,6 +113,78 @@ double fmref_match_batch(void* h, const int32_t* q_tokens, const int64_t* q_off,
   return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// ---- Sentence API: real tokens and penalty tokens (itoks) given explicitly
+// (FuzzyMatch::add_tm(id, Sentence, Tokens) fuzzy_match.hh:53, match(Sentence, Tokens, ...) :70-82).
+// real[k] = (real form id << 1) | case_class: the real token string is "L<id>" when case_class is set
+// (a case-feature token, first character in "LUMC", src/edit_distance.cc:55) and "r<id>" otherwise, so
+// string equality == (id, class) equality. gaps: for a sentence of n tokens, n+1 itok ids (0 = none)
+// at positions off[s] + s ... ; itok strings come from (itok_blob, itok_off).
+static fuzzy::Sentence make_sentence(const int32_t* real, const int32_t* gaps, int64_t n, const char* blob,
+                                     const int32_t* itok_off) {
+  fuzzy::Sentence s;
+  for (int64_t i = 0; i < n; i++) s.push_back(std::string(real[i] & 1 ? "L" : "r") + std::to_string(real[i] >> 1));
+  for (int64_t i = 0; i <= n; i++)
+    if (gaps[i]) s.set_itok((size_t)i, std::string(blob + itok_off[gaps[i]], blob + itok_off[gaps[i] + 1]));
+  return s;
+}
+
+void fmref_add_tm_real(void* h, const int32_t* tokens, const int32_t* real, const int32_t* gaps, const int64_t* off,
+                       int64_t n_sent, const char* itok_blob, const int32_t* itok_off) {
+  auto* r = static_cast<RefHandle*>(h);
+  for (int64_t s = 0; s < n_sent; s++) {
+    const int64_t n = off[s + 1] - off[s];
+    r->fm.add_tm(std::to_string(s), make_sentence(real + off[s], gaps + off[s] + s, n, itok_blob, itok_off),
+                 to_tokens(tokens + off[s], n), /*sort=*/false);
+  }
+}
+
+double fmref_match_batch_real(void* h, const int32_t* q_tokens, const int32_t* q_real, const int32_t* q_gaps,
+                              const int64_t* q_off, int64_t n_q, const fmref_params* p, int no_perfect, int nthreads,
+                              int64_t cap, fmref_match* out, int32_t* out_count, const char* itok_blob,
+                              const int32_t* itok_off) {
+  auto* r = static_cast<RefHandle*>(h);
+  std::vector<fuzzy::Tokens> queries((size_t)n_q);
+  std::vector<fuzzy::Sentence> reals((size_t)n_q);
+  for (int64_t q = 0; q < n_q; q++) {
+    const int64_t n = q_off[q + 1] - q_off[q];
+    queries[q] = to_tokens(q_tokens + q_off[q], n);
+    reals[q] = make_sentence(q_real + q_off[q], q_gaps + q_off[q] + q, n, itok_blob, itok_off);
+  }
+  const fuzzy::EditCosts costs(p->insert_cost, p->delete_cost, p->replace_cost);
+  const auto reduce = p->contrast_reduce ? fuzzy::ContrastReduce::MAX : fuzzy::ContrastReduce::MEAN;
+  std::atomic<int64_t> next(0);
+  auto work = [&]() {
+    std::vector<fuzzy::FuzzyMatch::Match> matches;
+    for (;;) {
+      const int64_t q = next.fetch_add(1);
+      if (q >= n_q) break;
+      matches.clear();
+      r->fm.match(reals[q], queries[q], p->fuzzy, (unsigned)p->number_of_matches, no_perfect != 0, matches,
+                  p->min_subseq_length, p->min_subseq_ratio, p->vocab_idf_penalty, costs, p->contrastive_factor, reduce,
+                  p->contrast_buffer);
+      if (out_count) out_count[q] = (int32_t)matches.size();
+      if (out)
+        for (size_t k = 0; k < matches.size() && (int64_t)k < cap; k++) {
+          fmref_match& o = out[q * cap + (int64_t)k];
+          o.s_id = matches[k].s_id;
+          o.score = matches[k].score;
+          o.penalty = p->contrastive_factor > 0 ? matches[k].penalty : 0.f;
+          o.max_subseq = matches[k].max_subseq;
+          o.length = matches[k].length;
+        }
+    }
+  };
+  const auto t0 = std::chrono::steady_clock::now();
+  if (nthreads <= 1) {
+    work();
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; t++) pool.emplace_back(work);
+    for (auto& t : pool) t.join();
+  }
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
 int64_t fmref_max_tokens_in_pattern(void* h) { return (int64_t) static_cast<RefHandle*>(h)->fm.max_tokens_in_pattern(); }
 
 }  // extern "C"

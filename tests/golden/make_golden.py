@@ -46,8 +46,15 @@ def uncsr(tok, off):
 def run_ref(case):
     tok, off = csr(case["tm"])
     q, qo = csr(case["queries"])
-    R = ob.RefIndex(tok, off, max_tokens=case["max_tokens"])
-    res, cnt = R.match_batch(q, qo, cap=64, **case["params"])
+    if "tm_real" in case:  # Sentence API: real tokens + penalty tokens
+        blob, ioff = synth.itok_table()
+        R = ob.RefIndex(tok, off, max_tokens=case["max_tokens"], real=np.array(case["tm_real"], dtype=np.int32),
+                        gaps=np.array(case["tm_gaps"], dtype=np.int32), itok_blob=blob, itok_off=ioff)
+        res, cnt = R.match_batch_real(q, np.array(case["q_real"], dtype=np.int32), np.array(case["q_gaps"], dtype=np.int32), qo,
+                                      cap=64, **case["params"])
+    else:
+        R = ob.RefIndex(tok, off, max_tokens=case["max_tokens"])
+        res, cnt = R.match_batch(q, qo, cap=64, **case["params"])
     case["expected"] = [[[int(m["s_id"]), int(m["score"].view(np.uint32)), int(m["penalty"].view(np.uint32)),
                           int(m["max_subseq"]), int(m["length"])] for m in r] for r in res]
     assert all(c <= 64 for c in cnt)
@@ -115,6 +122,18 @@ def main():
     q, qo = synth.make_queries(tm, off, 12, vocab=300, seed=22, len_lo=40, len_hi=120)
     cases.append(dict(name="random_long", source="synth seed 21/22", vocab_size=V, max_tokens=100, tm=uncsr(tm, off),
                       queries=uncsr(q, qo), params=dict(fuzzy=0.5, n=3, ml=3)))
+    # Sentence API (real tokens, case class, penalty tokens): match(const Sentence&, const Tokens&, ...)
+    real_params = [dict(fuzzy=0.5, n=5, ml=2), dict(fuzzy=0.3, n=20, ml=2, idf=1.0, costs=(1, 0, 1)),
+                   dict(fuzzy=0.4, n=4, ml=3, contrast=0.5, costs=(0.5, 1.5, 1.2)), dict(fuzzy=0.6, n=2, ml=2, no_perfect=True),
+                   dict(fuzzy=0.7, n=1, ml=3, mr=0.3)]
+    tm, off, V = synth.make_tm(300, vocab=50, len_lo=1, len_hi=18, seed=31)
+    q, qo = synth.make_queries(tm, off, 30, vocab=50, seed=32, len_lo=1, len_hi=18)
+    real, gaps = synth.make_real(tm, off, 33)
+    qreal, qgaps = synth.make_real(q, qo, 34)
+    for i, ps in enumerate(real_params):
+        cases.append(dict(name="sentence_api_%d" % i, source="synth seed 31-34, include/fuzzy/fuzzy_match.hh:53,70-82",
+                          vocab_size=V, max_tokens=300, tm=uncsr(tm, off), queries=uncsr(q, qo), tm_real=real.tolist(),
+                          tm_gaps=gaps.tolist(), q_real=qreal.tolist(), q_gaps=qgaps.tolist(), params=ps))
     out = [run_ref(c) for c in cases]
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "kat.json")
     with open(path, "w") as f:

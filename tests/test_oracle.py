@@ -15,7 +15,12 @@ def test_oracle_matches_golden(case):
     tok, off = csr(case["tm"])
     q, qo = csr(case["queries"])
     O = ob.OracleIndex(tok, off, case["vocab_size"], max_tokens=case["max_tokens"])
-    res, cnt = O.match_batch(q, qo, cap=64, **fix_params(case["params"]))
+    if "tm_real" in case:
+        blob, ioff = synth.itok_table()
+        O.set_real(case["tm_real"], case["tm_gaps"], off, blob, ioff)
+        res, cnt = O.match_batch_real(q, case["q_real"], case["q_gaps"], qo, cap=64, **fix_params(case["params"]))
+    else:
+        res, cnt = O.match_batch(q, qo, cap=64, **fix_params(case["params"]))
     got = [as_tuples(r) for r in res]
     want = [[tuple(m) for m in r] for r in case["expected"]]
     assert got == want
@@ -81,3 +86,23 @@ def test_oracle_threads_agree():
 def test_oracle_rejects_bad_tm_tokens():
     with pytest.raises(ValueError):
         ob.OracleIndex(np.array([2, 1, 3], dtype=np.int32), np.array([0, 3], dtype=np.int64), 10)
+
+
+@pytest.mark.skipif(not ob.ref_available(), reason="oracle/_ref not built (no /root/reference here)")
+@pytest.mark.parametrize("params", [dict(fuzzy=0.5, n=5, ml=2), dict(fuzzy=0.3, n=0, ml=2, idf=1.0, costs=(1, 0, 1)),
+                                    dict(fuzzy=0.4, n=4, ml=3, contrast=0.5, costs=(0.5, 1.5, 1.2))], ids=["0", "1", "2"])
+def test_oracle_matches_live_reference_sentence_api(params):
+    """Real tokens, case class and penalty tokens through add_tm(id, Sentence, Tokens) / match(Sentence, ...)."""
+    blob, ioff = synth.itok_table()
+    tm, off, V = synth.make_tm(3000, vocab=300, len_lo=1, len_hi=20, seed=71)
+    q, qo = synth.make_queries(tm, off, 300, vocab=300, seed=72, len_lo=1, len_hi=20)
+    real, gaps = synth.make_real(tm, off, 73)
+    qreal, qgaps = synth.make_real(q, qo, 74)
+    O = ob.OracleIndex(tm, off, V)
+    O.set_real(real, gaps, off, blob, ioff)
+    R = ob.RefIndex(tm, off, real=real, gaps=gaps, itok_blob=blob, itok_off=ioff)
+    ro, co = O.match_batch_real(q, qreal, qgaps, qo, cap=32, **params)
+    rr, cr = R.match_batch_real(q, qreal, qgaps, qo, cap=32, **params)
+    assert (co == cr).all()
+    for a, b in zip(ro, rr):
+        assert as_tuples(a) == as_tuples(b)
