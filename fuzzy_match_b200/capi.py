@@ -68,7 +68,7 @@ RECORD_DTYPE = np.dtype([("s_id", np.uint32), ("longest_match", np.int32), ("len
 
 EXPORTS = ["fm_index_create", "fm_index_destroy", "fm_index_save", "fm_index_load", "fm_index_num_sentences", "fm_index_num_suffixes",
            "fm_index_max_tokens_in_pattern", "fm_index_device_bytes", "fm_index_kept_sources", "fm_index_sfreq",
-           "fm_index_sentence", "fm_index_set_idf_stats", "fm_match_batch", "fm_match_batch_device", "fm_shard_score_device",
+           "fm_index_sentence", "fm_index_set_idf_stats", "fm_index_set_real", "fm_match_batch", "fm_match_batch_real", "fm_match_batch_device", "fm_shard_score_device",
            "fm_merge_replay_device", "fm_set_profiling", "fm_get_profile", "fm_last_error", "fm_version"]
 
 
@@ -101,6 +101,9 @@ def load_library():
     lib.fm_index_sentence.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32)]
     lib.fm_match_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Params), C.c_int64,
                                    C.c_void_p, C.c_void_p]
+    lib.fm_index_set_real.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    lib.fm_match_batch_real.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Params),
+                                        C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
     lib.fm_match_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(Params),
                                           C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.fm_shard_score_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(Params),
@@ -120,6 +123,27 @@ def _check(lib, rc):
 
 def _ptr(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def itok_distance_table(itoks):
+    """Pairwise _edit_distance_char (reference include/fuzzy/edit_distance.hxx:7-35) of penalty-token byte
+    strings; row / column 0 (the empty string) hold the lengths. Host-side table, a few entries."""
+    k = len(itoks)
+    dist = np.zeros((k, k), dtype=np.int32)
+    for a in range(k):
+        for b in range(k):
+            s1, s2 = itoks[a], itoks[b]
+            if not s1 or not s2:
+                dist[a, b] = len(s1) + len(s2)
+                continue
+            prev = list(range(len(s2) + 1))
+            for i in range(1, len(s1) + 1):
+                cur = [i] + [0] * len(s2)
+                for j in range(1, len(s2) + 1):
+                    cur[j] = min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (0 if s1[i - 1] == s2[j - 1] else 1))
+                prev = cur
+            dist[a, b] = prev[len(s2)]
+    return dist
 
 
 class Index:
@@ -201,6 +225,31 @@ class Index:
         assert out.dtype == MATCH_DTYPE and out.size == n_q * cap and out.flags.c_contiguous and len(cnt) == n_q
         _check(self.lib, self.lib.fm_match_batch(self.h, _ptr(q_tokens), _ptr(q_off), n_q, C.byref(p), cap, _ptr(out),
                                                  _ptr(cnt)))
+        return out, cnt
+
+    def set_real(self, real, gaps, sent_off):
+        """fm_index_set_real: real tokens ((form id << 1) | case class) and gap penalty-token ids of the TM."""
+        real = np.ascontiguousarray(real, dtype=np.int32)
+        gaps = np.ascontiguousarray(gaps, dtype=np.int32)
+        sent_off = np.ascontiguousarray(sent_off, dtype=np.int64)
+        _check(self.lib, self.lib.fm_index_set_real(self.h, _ptr(real), _ptr(gaps), _ptr(sent_off), len(sent_off) - 1))
+
+    def match_batch_real(self, q_tokens, q_real, q_gaps, q_off, itok_dist, cap=None, params=None, **kw):
+        """fm_match_batch_real: match(Sentence real, Tokens pattern, ...) for a batch (host buffers)."""
+        p = params if params is not None else Params.make(**kw)
+        if cap is None:
+            cap = max(1, p.number_of_matches)
+        q_tokens = np.ascontiguousarray(q_tokens, dtype=np.int32)
+        q_real = np.ascontiguousarray(q_real, dtype=np.int32)
+        q_gaps = np.ascontiguousarray(q_gaps, dtype=np.int32)
+        q_off = np.ascontiguousarray(q_off, dtype=np.int64)
+        dist = np.ascontiguousarray(itok_dist, dtype=np.int32)
+        assert dist.ndim == 2 and dist.shape[0] == dist.shape[1]
+        n_q = len(q_off) - 1
+        out = np.zeros((n_q, cap), dtype=MATCH_DTYPE)
+        cnt = np.zeros(n_q, dtype=np.int32)
+        _check(self.lib, self.lib.fm_match_batch_real(self.h, _ptr(q_tokens), _ptr(q_real), _ptr(q_gaps), _ptr(q_off), n_q,
+                                                      C.byref(p), _ptr(dist), dist.shape[0], cap, _ptr(out), _ptr(cnt)))
         return out, cnt
 
     def match_batch_device(self, d_q_tokens, d_q_off, n_q, n_tok, d_out, d_out_count, cap, stream=0, params=None, **kw):

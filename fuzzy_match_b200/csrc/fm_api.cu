@@ -119,7 +119,7 @@ static int ensure_out(Workspace* w, int64_t n_q, int64_t cap) {
 }
 
 static void free_workspace(Workspace* w) {
-  cudaFree(w->d_q_tok); cudaFree(w->d_q_off); cudaFree(w->pat); cudaFree(w->chain_q); cudaFree(w->qmeta); cudaFree(w->tbl); cudaFree(w->pinfo); cudaFree(w->cmin_tab); cudaFree(w->span_slice); cudaFree(w->qmask);
+  cudaFree(w->d_q_tok); cudaFree(w->d_q_off); cudaFree(w->d_q_real); cudaFree(w->d_q_gap); cudaFree(w->d_itok_dist); cudaFree(w->pat); cudaFree(w->chain_q); cudaFree(w->qmeta); cudaFree(w->tbl); cudaFree(w->pinfo); cudaFree(w->cmin_tab); cudaFree(w->span_slice); cudaFree(w->qmask);
   cudaFree(w->sl_start); cudaFree(w->sl_rec); cudaFree(w->hkey); cudaFree(w->hlm); cudaFree(w->surv); cudaFree(w->surv_len);
   cudaFree(w->q_cnt); cudaFree(w->q_base); cudaFree(w->acc_cnt); cudaFree(w->rec); cudaFree(w->heapbuf); cudaFree(w->ctr); cudaFree(w->scan_chain);
   cudaFree(w->d_out); cudaFree(w->d_out_count); cudaFree(w->mrec); cudaFree(w->m_cnt); cudaFree(w->m_base); cudaFree(w->m_acc); cudaFree(w->m_heap); cudaFree(w->heavy_q); cudaFree(w->m_heavy); cudaFree(w->sort_key); cudaFree(w->sort_key2); cudaFree(w->m_key2); cudaFree(w->sort_idx); cudaFree(w->m_key); cudaFree(w->m_idx);
@@ -158,6 +158,7 @@ static BatchDev make_batch(Workspace* w, const int32_t* d_q_tok, const int32_t* 
   b.surv = w->surv; b.surv_len = w->surv_len; b.surv_cap = w->cap_surv;
   b.q_cnt = w->q_cnt; b.q_base = w->q_base; b.rec = w->rec; b.heapbuf = w->heapbuf; b.acc_cnt = w->acc_cnt;
   b.ctr = w->ctr;
+  if (w->real_active) { b.q_real = w->d_q_real; b.q_gap = w->d_q_gap; b.itok_dist = w->d_itok_dist; b.n_itok = w->n_itok; }
   return b;
 }
 
@@ -259,6 +260,7 @@ static void finish_profile(Index* ix, Workspace* w, int64_t n_q, int64_t n_tok, 
 static int match_device(Index* ix, Workspace* w, const int32_t* d_q_tok, const int32_t* d_q_off, int64_t n_q, int64_t n_tok,
                         const Params& pr, int64_t cap, fm_match* d_out, int32_t* d_out_count, cudaStream_t st) {
   int rc, launches = 0, retries = 0;
+  w->real_active = false;
   if ((rc = initial_worklists(ix, w, n_q, n_tok))) return rc;
   for (int attempt = 0;; attempt++) {
     if ((rc = launch_shard(ix, w, d_q_tok, d_q_off, n_q, n_tok, pr, st, &launches))) return rc;
@@ -358,8 +360,40 @@ struct HostChunk {
 };
 
 // Enqueue H2D + the whole pipeline + D2H of one chunk; returns without waiting.
+struct RealInputs {  // Sentence API extras of a host batch (all NULL / 0 when absent)
+  const int32_t* q_real = nullptr;
+  const int32_t* q_gaps = nullptr;
+  const int32_t* itok_dist = nullptr;
+  int32_t n_itok = 0;
+};
+
+static int stage_real(Workspace* w, const HostChunk& c, const int64_t* q_off, const RealInputs& ri, cudaStream_t st) {
+  w->real_active = ri.q_real != nullptr;
+  if (!w->real_active) return FM_OK;
+  int rc;
+  if (c.ntok > w->cap_real_tok) {
+    if ((rc = dev_realloc(&w->d_q_real, c.ntok + c.ntok / 4 + 1024))) return rc;
+    w->cap_real_tok = c.ntok + c.ntok / 4 + 1024;
+  }
+  if (c.ntok + c.nq > w->cap_real_gap) {
+    const int64_t n = c.ntok + c.nq + (c.ntok + c.nq) / 4 + 1024;
+    if ((rc = dev_realloc(&w->d_q_gap, n))) return rc;
+    w->cap_real_gap = n;
+  }
+  const int64_t nd = (int64_t)ri.n_itok * ri.n_itok;
+  if (nd > w->cap_itok) {
+    if ((rc = dev_realloc(&w->d_itok_dist, nd))) return rc;
+    w->cap_itok = nd;
+  }
+  w->n_itok = ri.n_itok;
+  if (c.ntok) FM_CUDA(cudaMemcpyAsync(w->d_q_real, ri.q_real + q_off[c.q0], c.ntok * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  FM_CUDA(cudaMemcpyAsync(w->d_q_gap, ri.q_gaps + q_off[c.q0] + c.q0, (c.ntok + c.nq) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  FM_CUDA(cudaMemcpyAsync(w->d_itok_dist, ri.itok_dist, nd * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  return FM_OK;
+}
+
 static int launch_host_chunk(Index* ix, HostChunk& c, const int32_t* q_tokens, const int64_t* q_off, const Params& pr, int64_t cap,
-                             fm_match* out, int32_t* out_count) {
+                             fm_match* out, int32_t* out_count, const RealInputs& ri) {
   Workspace* w = c.w;
   int rc;
   if ((rc = ensure_queries(w, c.nq, c.ntok, true)) || (rc = ensure_out(w, c.nq, cap)) || (rc = initial_worklists(ix, w, c.nq, c.ntok)))
@@ -368,6 +402,7 @@ static int launch_host_chunk(Index* ix, HostChunk& c, const int32_t* q_tokens, c
   cudaStream_t st = w->stream;
   FM_CUDA(cudaMemcpyAsync(w->d_q_off, w->h_q_off32, (c.nq + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   if (c.ntok) FM_CUDA(cudaMemcpyAsync(w->d_q_tok, q_tokens + q_off[c.q0], c.ntok * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  if ((rc = stage_real(w, c, q_off, ri, st))) return rc;
   FM_CUDA(cudaMemsetAsync(w->d_out, 0, c.nq * cap * sizeof(fm_match), st));  // slots past the count read as zero
   c.launches = 0;
   if ((rc = launch_shard(ix, w, w->d_q_tok, w->d_q_off, c.nq, c.ntok, pr, st, &c.launches))) return rc;
@@ -404,12 +439,16 @@ static int finish_host_chunk(Index* ix, HostChunk& c, const Params& pr, int64_t 
   return FM_OK;
 }
 
-int fm_match_batch(fm_index* index, const int32_t* q_tokens, const int64_t* q_off, int64_t n_q, const fm_params* params,
-                   int64_t cap, fm_match* out, int32_t* out_count) {
+static int match_batch_host(fm_index* index, const int32_t* q_tokens, const int64_t* q_off, int64_t n_q, const fm_params* params,
+                            int64_t cap, fm_match* out, int32_t* out_count, const RealInputs& ri) {
   Index* ix = reinterpret_cast<Index*>(index);
   Params pr;
   int rc;
   if (!ix || n_q < 0 || cap < 1 || (n_q > 0 && (!q_off || !out || !out_count))) { set_error("bad argument"); return FM_ERR_INVALID; }
+  if (ri.q_real && (!ix->dev.real || !ri.q_gaps || !ri.itok_dist || ri.n_itok < 1 || ri.n_itok > 2048)) {
+    set_error("Sentence API needs fm_index_set_real on the index, gaps and a penalty-token table (1..2048 entries)");
+    return FM_ERR_INVALID;
+  }
   if ((rc = check_params(params, &pr))) return rc;
   if (n_q == 0) return FM_OK;
   FM_CUDA(cudaSetDevice(ix->device));
@@ -440,12 +479,33 @@ int fm_match_batch(fm_index* index, const int32_t* q_tokens, const int64_t* q_of
       if ((rc = ensure_base(c.w))) return rc;
     }
     c.q0 = q0; c.nq = q1 - q0; c.ntok = ntok;
-    if ((rc = launch_host_chunk(ix, c, q_tokens, q_off, pr, cap, out, out_count))) return rc;
+    if ((rc = launch_host_chunk(ix, c, q_tokens, q_off, pr, cap, out, out_count, ri))) return rc;
     q0 = q1;
   }
   for (int i = 0; i < kSlots; i++)
     if ((rc = finish_host_chunk(ix, slots[i], pr, cap, out, out_count))) return rc;
   return FM_OK;
+}
+
+int fm_match_batch(fm_index* index, const int32_t* q_tokens, const int64_t* q_off, int64_t n_q, const fm_params* params,
+                   int64_t cap, fm_match* out, int32_t* out_count) {
+  return match_batch_host(index, q_tokens, q_off, n_q, params, cap, out, out_count, RealInputs());
+}
+
+int fm_match_batch_real(fm_index* index, const int32_t* q_tokens, const int32_t* q_real, const int32_t* q_gaps,
+                        const int64_t* q_off, int64_t n_q, const fm_params* params, const int32_t* itok_dist, int32_t n_itok,
+                        int64_t cap, fm_match* out, int32_t* out_count) {
+  if (!q_real) { set_error("q_real is NULL"); return FM_ERR_INVALID; }
+  RealInputs ri;
+  ri.q_real = q_real; ri.q_gaps = q_gaps; ri.itok_dist = itok_dist; ri.n_itok = n_itok;
+  return match_batch_host(index, q_tokens, q_off, n_q, params, cap, out, out_count, ri);
+}
+
+int fm_index_set_real(fm_index* index, const int32_t* real, const int32_t* gaps, const int64_t* sent_off, int64_t n_sent) {
+  Index* ix = reinterpret_cast<Index*>(index);
+  if (!ix || !real || !gaps || !sent_off) { set_error("NULL argument"); return FM_ERR_INVALID; }
+  FM_CUDA(cudaSetDevice(ix->device));
+  return set_real(ix, real, gaps, sent_off, n_sent);
 }
 
 int fm_match_batch_device(fm_index* index, const int32_t* d_q_tokens, const int32_t* d_q_off, int64_t n_q,
@@ -480,6 +540,7 @@ int fm_shard_score_device(fm_index* index, const int32_t* d_q_tokens, const int3
   if ((rc = ensure_base(w)) || (rc = ensure_queries(w, n_q, n_query_tokens, false))) return rc;
   int launches = 0, retries = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  w->real_active = false;
   if ((rc = initial_worklists(ix, w, n_q, n_query_tokens))) return rc;
   for (int attempt = 0;; attempt++) {
     if ((rc = launch_shard(ix, w, d_q_tokens, d_q_off, n_q, n_query_tokens, pr, st, &launches))) return rc;

@@ -58,7 +58,7 @@ static int upload(const std::vector<T>& h, size_t extra, Index* ix, int blk, con
 // Boost binary archive, src/fuzzy_matcher_binarization.cc). Header, then the device blocks exactly as
 // they sit in HBM, then the host-side tables. Loading is read + upload: no sort, no hashing.
 static const char kMagic[8] = {'F', 'M', 'B', '2', '0', '0', 'I', 1};
-enum { BLK_TOK = 0, BLK_SA = 1, BLK_WALK = 2, BLK_QVA = 3, BLK_SID = 4, BLK_IDF = 5, BLK_BG = 6, BLK_TG = 7, N_BLK = 8 };
+enum { BLK_TOK = 0, BLK_SA = 1, BLK_WALK = 2, BLK_QVA = 3, BLK_SID = 4, BLK_IDF = 5, BLK_BG = 6, BLK_TG = 7, BLK_REAL = 8, BLK_GAP = 9, N_BLK = 10 };
 
 static void bind_blocks(Index* ix) {
   IndexDev& d = ix->dev;
@@ -70,6 +70,8 @@ static void bind_blocks(Index* ix) {
   d.idf = static_cast<const float*>(ix->d_blocks[BLK_IDF]);
   d.bg_tab = static_cast<const int4*>(ix->d_blocks[BLK_BG]);
   d.tg_tab = static_cast<const int4*>(ix->d_blocks[BLK_TG]);
+  d.real = ix->blk_bytes[BLK_REAL] ? static_cast<const int32_t*>(ix->d_blocks[BLK_REAL]) : nullptr;
+  d.gap = ix->blk_bytes[BLK_GAP] ? static_cast<const int32_t*>(ix->d_blocks[BLK_GAP]) : nullptr;
 }
 
 int save_index(const Index* ix, const char* path) {
@@ -77,7 +79,7 @@ int save_index(const Index* ix, const char* path) {
   if (!f) { set_error(std::string("cannot open ") + path + " for writing"); return FM_ERR_INVALID; }
   FM_CUDA(cudaSetDevice(ix->device));
   int64_t hdr[16] = {1, ix->vocab_size, ix->max_tokens, ix->n_sent, ix->n_suf, ix->n_buf, (int64_t)ix->dev.bg_mask,
-                     (int64_t)ix->dev.tg_mask, (int64_t)ix->dev.sid_base, ix->n_sent_global, 0, 0, 0, 0, 0, 0};
+                     (int64_t)ix->dev.tg_mask, (int64_t)ix->dev.sid_base, ix->n_sent_global, 0, N_BLK, 0, 0, 0, 0};
   memcpy(&hdr[10], &ix->dev.idf_max, sizeof(float));
   bool ok = fwrite(kMagic, 1, 8, f) == 8 && fwrite(hdr, sizeof(int64_t), 16, f) == 16;
   std::vector<char> buf;
@@ -115,7 +117,8 @@ int load_index(const char* path, int device, Index** out) {
   if (e == cudaSuccess && cudaGetDeviceProperties(&prop, device) == cudaSuccess) ix->sm_count = prop.multiProcessorCount;
   bool ok = e == cudaSuccess;
   std::vector<char> buf;
-  for (int k = 0; k < N_BLK && ok; k++) {
+  const int n_blk = (int)std::min<int64_t>(std::max<int64_t>(hdr[11], 8), N_BLK);  // files written before the Sentence API hold 8
+  for (int k = 0; k < n_blk && ok; k++) {
     int64_t n = 0;
     ok = fread(&n, sizeof n, 1, f) == 1 && n >= 0 && n < (int64_t(1) << 40);
     if (!ok) break;
@@ -325,6 +328,29 @@ static int build_on_device(Index* ix, const std::vector<int32_t>& sent_start) {
   FM_CUDA(cudaDeviceSynchronize());
   FM_CUDA(cudaGetLastError());
   cudaFree(d_start); cudaFree(d_len); cudaFree(d_sig); cudaFree(d_counts);
+  return FM_OK;
+}
+
+// Real tokens and penalty tokens of the TM (FuzzyMatch::add_tm(id, Sentence, Tokens), reference
+// include/fuzzy/fuzzy_match.hh:53, include/fuzzy/sentence.hh:24-48) laid out parallel to the token buffer.
+int set_real(Index* ix, const int32_t* real, const int32_t* gaps, const int64_t* sent_off, int64_t n_sent) {
+  for (int64_t k = 0; k < ix->n_sent; k++)
+    if (ix->kept[k] >= n_sent) { set_error("sent_off does not match the CSR the index was built from"); return FM_ERR_INVALID; }
+  std::vector<int32_t> h_real((size_t)ix->n_buf, 0), h_gap((size_t)ix->n_buf, 0);
+  for (int64_t k = 0; k < ix->n_sent; k++) {
+    const int64_t s = ix->kept[k], st = ix->h_sent_start[k];
+    const int64_t n = sent_off[s + 1] - sent_off[s];
+    for (int64_t j = 0; j < n; j++) h_real[st + j] = real[sent_off[s] + j];
+    for (int64_t j = 0; j <= n; j++) {
+      const int32_t g = gaps[sent_off[s] + s + j];
+      if (g < 0 || g >= 2048) { set_error("penalty-token id outside [0, 2048)"); return FM_ERR_INVALID; }
+      h_gap[st + j] = g;
+    }
+  }
+  for (int blk : {BLK_REAL, BLK_GAP})
+    if (ix->d_blocks[blk]) { cudaFree(ix->d_blocks[blk]); ix->device_bytes -= (int64_t)ix->blk_bytes[blk]; ix->d_blocks[blk] = nullptr; }
+  int rc;
+  if ((rc = upload(h_real, 0, ix, BLK_REAL, &ix->dev.real)) || (rc = upload(h_gap, 0, ix, BLK_GAP, &ix->dev.gap))) return rc;
   return FM_OK;
 }
 

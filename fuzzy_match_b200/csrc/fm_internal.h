@@ -40,6 +40,8 @@ struct IndexDev {
   uint32_t tg_mask;
   const int32_t* sid_at;
   const float* idf;
+  const int32_t* real;  // optional (Sentence API): (real form id << 1) | case class, parallel to tok
+  const int32_t* gap;   // optional: penalty-token id of the gap before each token (separator slot = trailing gap)
   int32_t vocab_size;
   int32_t max_tokens;
   int64_t n_suf;
@@ -85,6 +87,10 @@ struct BatchDev {
   // inputs
   const int32_t* q_tok_in;
   const int32_t* q_off;  // [n_q+1]
+  const int32_t* q_real;     // optional (Sentence API) [n_tok]
+  const int32_t* q_gap;      // optional [n_tok + n_q]: p+1 gaps per query at q_off[q] + q
+  const int32_t* itok_dist;  // optional [n_itok^2] pairwise _edit_distance_char of the penalty tokens
+  int32_t n_itok;
   int32_t n_q;
   int32_t n_tok;
   // prepared
@@ -140,6 +146,10 @@ struct Workspace {
   uint32_t hsize = 0;
   // device buffers
   int32_t *d_q_tok = nullptr, *d_q_off = nullptr;  // staging for host inputs
+  int32_t *d_q_real = nullptr, *d_q_gap = nullptr, *d_itok_dist = nullptr;  // Sentence API staging
+  int64_t cap_real_tok = 0, cap_real_gap = 0, cap_itok = 0;
+  int32_t n_itok = 0;
+  bool real_active = false;  // the batch in flight carries real tokens / penalty tokens
   int32_t *pat = nullptr, *chain_q = nullptr;
   QMeta* qmeta = nullptr;
   int2* tbl = nullptr;
@@ -217,6 +227,7 @@ void free_index(Index* ix);
 int save_index(const Index* ix, const char* path);
 int load_index(const char* path, int device, Index** out);
 int set_idf_stats(Index* ix, const uint32_t* sfreq, int64_t n_sent_global);
+int set_real(Index* ix, const int32_t* real, const int32_t* gaps, const int64_t* sent_off, int64_t n_sent);
 
 // fm_sort.cu
 int gpu_suffix_sort(const int32_t* d_tok, int64_t n_buf, const std::vector<int32_t>& sent_start,

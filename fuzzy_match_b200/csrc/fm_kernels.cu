@@ -663,21 +663,39 @@ __global__ void __launch_bounds__(1024) fm_scan_kernel(const int32_t* __restrict
 // works on row t-l, so the anti-diagonal moves one lane per step and the only exchange is one
 // __shfl_up of (left value, running row minimum). Column state lives in shared memory.
 // Returns C = arr[s][p] and K = max over rows of min_{j>=1} arr[i][j] in every lane.
+// With REAL (Sentence API: src/edit_distance.cc:19-26,31,38,53-62): rs holds the real tokens and gap
+// itok ids of both sides in shared memory; ct(a, b) = _edit_distance_char of two penalty tokens comes
+// from the caller's table dist[a * n_itok + b] (dist[0][b] = length of b).
+struct RealSide {
+  const int32_t* real1;  // [s]   (form id << 1) | case class of the TM sentence
+  const int32_t* gap1;   // [s+1] itok id of each gap of the TM sentence
+  const int32_t* real2;  // [p]   pattern
+  const int32_t* gap2;   // [p+1]
+  const int32_t* dist;   // [n_itok * n_itok]
+  int n_itok;
+  float rep;             // replace cost (for the case / real-form differences)
+};
+template <bool REAL>
 __device__ void warp_edit_distance(const int32_t* s_sent, int s, const int32_t* s_pat, int p, const float* s_pen,
-                                   float* s_up, float delw, float insw, float repw, float& C_out, float& K_out) {
+                                   float* s_up, float delw, float insw, float repw, float& C_out, float& K_out,
+                                   const RealSide& rs) {
   const int lane = threadIdx.x & 31;
   const int c = (p + 31) >> 5;
   const int nl = (p + c - 1) / c;  // lanes that own columns
-  if (lane == 0) {                 // row 0: arr[0][j] = arr[0][j-1] + w*ins (+ idf penalty), :33-39
-    float v = 0.f;
+  float origin = 0.f;               // arr[0][0]: edit distance of the trailing penalty tokens, :25
+  if (REAL) origin = (float)__ldg(rs.dist + rs.gap1[s] * rs.n_itok + rs.gap2[p]);
+  if (lane == 0) {  // row 0: arr[0][j] = arr[0][j-1] + w*ins + sn2[j] (+ idf penalty), :33-39
+    float v = origin;
     for (int j = 1; j <= p; j++) {
-      v = __fadd_rn(__fadd_rn(v, insw), s_pen[j - 1]);
+      v = __fadd_rn(v, insw);
+      if (REAL) v = __fadd_rn(v, (float)__ldg(rs.dist + rs.gap2[j]));
+      v = __fadd_rn(v, s_pen[j - 1]);
       s_up[((j - 1) % c) * 32 + (j - 1) / c] = v;
     }
   }
   __syncwarp();
-  float diag = lane == 0 ? 0.f : s_up[(c - 1) * 32 + (lane - 1)];  // arr[0][lane*c]
-  float col0 = 0.f;
+  float diag = lane == 0 ? origin : s_up[(c - 1) * 32 + (lane - 1)];  // arr[0][lane*c]
+  float col0 = origin;
   float recv_left = 0.f, recv_min = FLT_MAX;
   float K = -FLT_MAX, C = 0.f;
   const int steps = s + nl - 1;
@@ -687,24 +705,38 @@ __device__ void warp_edit_distance(const int32_t* s_sent, int s, const int32_t* 
     const bool active = lane < nl && i >= 1 && i <= s;
     float left = recv_left, rmin = recv_min;
     if (active) {
-      if (lane == 0) {  // arr[i][0] = arr[i-1][0] + w*del, :28-32
+      if (lane == 0) {  // arr[i][0] = arr[i-1][0] + w*del + sn1[i], :28-32
         diag = col0;
         col0 = __fadd_rn(col0, delw);
+        if (REAL) col0 = __fadd_rn(col0, (float)__ldg(rs.dist + rs.gap1[i] * rs.n_itok));
         left = col0;
         rmin = FLT_MAX;
       }
       const float next_diag = left;
       const int tok = s_sent[i - 1];
+      int r1 = 0, ga_up = 0, ga = 0;
+      if (REAL) {
+        r1 = rs.real1[i - 1];
+        ga_up = rs.gap1[i - 1] * rs.n_itok;  // row of the table for the gap above / on this row
+        ga = rs.gap1[i] * rs.n_itok;
+      }
       float d = left;
       for (int r = 0; r < c; r++) {
-        const int j = jbase + r;  // 0-based column
+        const int j = jbase + r;  // 0-based column; the cell is (i, j+1)
         if (j >= p) break;
         const float up = s_up[r * 32 + lane];
         const float pen = s_pen[j];
-        const float a = __fadd_rn(up, delw);
-        const float bb = __fadd_rn(__fadd_rn(left, insw), pen);
-        const float diff = (tok != s_pat[j]) ? __fadd_rn(repw, pen) : 0.f;
-        const float cc = __fadd_rn(diag, diff);
+        float a = __fadd_rn(up, delw);
+        float bb = __fadd_rn(left, insw);
+        float diff = (tok != s_pat[j]) ? __fadd_rn(repw, pen) : 0.f;
+        if (REAL && tok == s_pat[j] && r1 != rs.real2[j]) diff = (r1 & 1) ? __fmul_rn(rs.rep, 1.f) : __fmul_rn(rs.rep, 2.f);
+        float cc = __fadd_rn(diag, diff);
+        if (REAL) {
+          a = __fadd_rn(a, (float)__ldg(rs.dist + ga_up + rs.gap2[j + 1]));   // cost_tag[i-1][j]
+          bb = __fadd_rn(bb, (float)__ldg(rs.dist + ga + rs.gap2[j]));        // cost_tag[i][j-1]
+          cc = __fadd_rn(cc, (float)__ldg(rs.dist + ga_up + rs.gap2[j]));     // cost_tag[i-1][j-1]
+        }
+        bb = __fadd_rn(bb, pen);
         d = fminf(fminf(a, bb), cc);
         s_up[r * 32 + lane] = d;
         diag = up;
@@ -813,14 +845,20 @@ __global__ void __launch_bounds__(128) fm_score_short_kernel(IndexDev ix, BatchD
 // One warp per surviving (query, sentence) with p > 32: Costs (include/fuzzy/costs.hh:54-57), idf
 // weight (src/fuzzy_match.cc:591) and the full edit distance without upper bound; writes the record
 // at the candidate's slot inside its query group.
+template <bool REAL>
 __global__ void __launch_bounds__(256) fm_score_kernel(IndexDev ix, BatchDev b, Params pr, int stride, int min_p) {
   extern __shared__ int smem[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  int32_t* s_sent = smem + wib * 4 * stride;
+  const int n_arr = REAL ? 8 : 4;
+  int32_t* s_sent = smem + wib * n_arr * stride;
   int32_t* s_pat = s_sent + stride;
   float* s_pen = reinterpret_cast<float*>(s_pat + stride);
   float* s_up = s_pen + stride;
+  int32_t* s_real1 = reinterpret_cast<int32_t*>(s_up + stride);
+  int32_t* s_gap1 = s_real1 + stride;
+  int32_t* s_real2 = s_gap1 + stride;
+  int32_t* s_gap2 = s_real2 + stride;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const long long n = min((long long)b.ctr->n_surv, (long long)b.surv_cap);
   if (b.ctr->overflow) return;
@@ -839,10 +877,19 @@ __global__ void __launch_bounds__(256) fm_score_kernel(IndexDev ix, BatchDev b, 
       s_pat[k] = t;
       s_pen[k] = idf_weight != 0.f ? __fmul_rn(ix.idf[t], idf_weight) : 0.f;
     }
+    RealSide rs{};
+    if (REAL) {
+      for (int k = lane; k < slen; k += 32) s_real1[k] = ix.real[sr.start + k];
+      for (int k = lane; k <= slen; k += 32) s_gap1[k] = ix.gap[sr.start + k];
+      for (int k = lane; k < p; k += 32) s_real2[k] = b.q_real[qm.z + k];
+      for (int k = lane; k <= p; k += 32) s_gap2[k] = b.q_gap[qm.z + sr.q + k];
+      rs.real1 = s_real1; rs.gap1 = s_gap1; rs.real2 = s_real2; rs.gap2 = s_gap2;
+      rs.dist = b.itok_dist; rs.n_itok = b.n_itok; rs.rep = pr.rep;
+    }
     __syncwarp();
     float C, K;
-    warp_edit_distance(s_sent, slen, s_pat, p, s_pen, s_up, __fmul_rn(pr.del, wdiff), __fmul_rn(pr.ins, wdiff),
-                       __fmul_rn(pr.rep, wdiff), C, K);
+    warp_edit_distance<REAL>(s_sent, slen, s_pat, p, s_pen, s_up, __fmul_rn(pr.del, wdiff), __fmul_rn(pr.ins, wdiff),
+                             __fmul_rn(pr.rep, wdiff), C, K, rs);
     if (lane == 0) write_record(ix, b, sr, slen, C, K);
   }
 }
@@ -1250,7 +1297,7 @@ __global__ void __launch_bounds__(256) fm_contrast_kernel(IndexDev ix, fm_record
           __syncwarp();
           const float wdiff = __fdiv_rn(100.f, normalizer(cr.length, lr.length, unit));
           float C, K;
-          warp_edit_distance(s_sent, cr.length, s_pat, lr.length, s_pen, s_up, wdiff, wdiff, wdiff, C, K);
+          warp_edit_distance<false>(s_sent, cr.length, s_pat, lr.length, s_pen, s_up, wdiff, wdiff, wdiff, C, K, RealSide{});
           if (lane == 0) {
             const float pen = score_of(C);
             float acc = __int_as_float(cr.reserved[1]);
@@ -1346,12 +1393,18 @@ void launch_scan(const int32_t* in, int32_t* out, int32_t n, unsigned long long*
 }
 void launch_score(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st) {
   const int stride = dp_stride(ix);
-  const size_t smem = (size_t)8 * 4 * stride * sizeof(int);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(fm_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(fm_score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(fm_score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
+  if (b.q_real) {  // Sentence API: every pair through the wavefront kernel with the real-token terms
+    const int warps = 4;  // 8 staging arrays per warp
+    fm_score_kernel<true><<<sm_count * 4, warps * 32, (size_t)warps * 8 * stride * sizeof(int), st>>>(ix, b, p, stride, 0);
+    return;
+  }
+  const size_t smem = (size_t)8 * 4 * stride * sizeof(int);
   // FM_SCORE_WARP_ONLY=1 forces every pair through the warp wavefront (tests exercise both paths)
   static const bool warp_only = getenv("FM_SCORE_WARP_ONLY") != nullptr;
   if (!warp_only) {
@@ -1359,7 +1412,7 @@ void launch_score(const IndexDev& ix, const BatchDev& b, const Params& p, int sm
     if (p.idf_penalty != 0.f) fm_score_short_kernel<true><<<grid, 128, 0, st>>>(ix, b, p);
     else fm_score_short_kernel<false><<<grid, 128, 0, st>>>(ix, b, p);
   }
-  fm_score_kernel<<<sm_count * 4, 256, smem, st>>>(ix, b, p, stride, warp_only ? 0 : 33);
+  fm_score_kernel<false><<<sm_count * 4, 256, smem, st>>>(ix, b, p, stride, warp_only ? 0 : 33);
 }
 void launch_replay(const IndexDev& ix, const fm_record* rec, const int32_t* q_cnt, const int32_t* q_base, float* heapbuf,
                    unsigned long long* sort_key, unsigned long long* sort_key2, int32_t* sort_idx, int32_t* acc_cnt,

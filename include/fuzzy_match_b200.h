@@ -106,6 +106,21 @@ int fm_index_set_idf_stats(fm_index* index, const uint32_t* sfreq_global, int64_
 /* Host view of a kept sentence (Match::s / Match::length); valid for the life of the index. */
 int fm_index_sentence(const fm_index* index, uint32_t local_s_id, const int32_t** tokens, int32_t* length);
 
+/* Sentence API (reference include/fuzzy/sentence.hh:24-48): the "real" surface form of every token and
+ * the penalty tokens (itoks: tags, punctuation, separators...) in the gaps between tokens, as
+ * FuzzyMatch::add_tm(id, Sentence, Tokens) (fuzzy_match.hh:53) stores them. real[k] = (real form id << 1) |
+ * case_class, two tokens have the same real form iff the values are equal, case_class = first character
+ * of the real form is one of "LUMC" (src/edit_distance.cc:55); gaps holds n+1 penalty-token ids (0 = none)
+ * per sentence at sent_off[s] + s. sent_off / n_sent are those given to fm_index_create. */
+int fm_index_set_real(fm_index* index, const int32_t* real, const int32_t* gaps, const int64_t* sent_off, int64_t n_sent);
+/* match(const Sentence& real, const Tokens& pattern, ...) (fuzzy_match.hh:70-82) for a batch: adds the
+ * real-token / case / penalty-token terms of _edit_distance (src/edit_distance.cc:19-26,30-31,35-38,53-62).
+ * itok_dist[a * n_itok + b] = _edit_distance_char of penalty tokens a and b (include/fuzzy/edit_distance.hxx),
+ * with row / column 0 = the lengths; ids are shared with fm_index_set_real. */
+int fm_match_batch_real(fm_index* index, const int32_t* q_tokens, const int32_t* q_real, const int32_t* q_gaps,
+                        const int64_t* q_off, int64_t n_q, const fm_params* params, const int32_t* itok_dist,
+                        int32_t n_itok, int64_t cap, fm_match* out, int32_t* out_count);
+
 /* match() for n_q patterns given as host CSR; out is [n_q * cap], out_count[q] = number of matches
  * the reference would append (only min(count, cap) are stored). */
 int fm_match_batch(fm_index* index, const int32_t* q_tokens, const int64_t* q_off, int64_t n_q,

@@ -32,7 +32,13 @@ def test_golden_vectors(case):
     tok, off = csr(case["tm"])
     q, qo = csr(case["queries"])
     index = fmb.Index(tok, off, case["vocab_size"], max_tokens=case["max_tokens"])
-    out, cnt = index.match_batch(q, qo, cap=64, **fix_params(case["params"]))
+    if "tm_real" in case:  # Sentence API: real tokens, case class, penalty tokens
+        from fuzzy_match_b200 import capi
+        index.set_real(case["tm_real"], case["tm_gaps"], off)
+        out, cnt = index.match_batch_real(q, case["q_real"], case["q_gaps"], qo, capi.itok_distance_table(synth.ITOKS), cap=64,
+                                          **fix_params(case["params"]))
+    else:
+        out, cnt = index.match_batch(q, qo, cap=64, **fix_params(case["params"]))
     got = [as_tuples(out[i, :cnt[i]]) for i in range(len(cnt))]
     want = [[tuple(m) for m in r] for r in case["expected"]]
     assert got == want
@@ -300,3 +306,31 @@ def test_gpu_suffix_sort_matches_host_sort(monkeypatch):
         assert (ca == cb).all() and a.tobytes() == b.tobytes()
         ro, oc = oracle.match_batch(q, qo, cap=64, **params)
         assert (ca == oc).all() and all(a[i, :min(ca[i], 64)].tobytes() == ro[i].tobytes() for i in range(len(oc)))
+
+
+def test_sentence_api_vs_oracle(tmp_path):
+    """Real tokens / case class / penalty tokens (fm_index_set_real + fm_match_batch_real) against the oracle,
+    incl. long patterns, and after a save / load round trip of the index."""
+    from fuzzy_match_b200 import capi
+    blob, ioff = synth.itok_table()
+    dist = capi.itok_distance_table(synth.ITOKS)
+    tm, off, V = synth.make_tm(4000, vocab=300, len_lo=0, len_hi=60, seed=401)
+    q, qo = synth.make_queries(tm, off, 400, vocab=300, seed=402, len_lo=1, len_hi=60)
+    real, gaps = synth.make_real(tm, off, 403)
+    qreal, qgaps = synth.make_real(q, qo, 404)
+    index, oracle = fmb.Index(tm, off, V, max_tokens=50), ob.OracleIndex(tm, off, V, max_tokens=50)
+    index.set_real(real, gaps, off)
+    oracle.set_real(real, gaps, off, blob, ioff)
+    path = tmp_path / "real.fmb"
+    index.save(path)
+    for ix in (index, fmb.Index.load(path, V)):
+        for params in (dict(fuzzy=0.5, n=5, ml=2), dict(fuzzy=0.3, n=8, ml=2, idf=1.0, costs=(1, 0, 1)),
+                       dict(fuzzy=0.4, n=4, ml=3, contrast=0.5, costs=(0.5, 1.5, 1.2)), dict(fuzzy=0.6, n=2, ml=2, no_perfect=True)):
+            out, cnt = ix.match_batch_real(q, qreal, qgaps, qo, dist, cap=16, **params)
+            ro, oc = oracle.match_batch_real(q, qreal, qgaps, qo, cap=16, **params)
+            assert (cnt == oc).all()
+            assert [as_tuples(out[i, :cnt[i]], True) for i in range(len(oc))] == [as_tuples(r, True) for r in ro]
+    # the plain call on the same index still ignores the real side
+    out, cnt = index.match_batch(q, qo, cap=4, fuzzy=0.5, n=4, ml=2)
+    ro, oc = ob.OracleIndex(tm, off, V, max_tokens=50).match_batch(q, qo, cap=4, fuzzy=0.5, n=4, ml=2)
+    assert (cnt == oc).all() and all(out[i, :cnt[i]].tobytes() == ro[i].tobytes() for i in range(len(oc)))
