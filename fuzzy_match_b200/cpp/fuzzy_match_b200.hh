@@ -12,7 +12,9 @@
 //
 // Define FUZZY_MATCH_B200_NAMESPACE before including to put the classes elsewhere than `fuzzy`.
 #pragma once
+#include <algorithm>
 #include <cstdint>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -38,6 +40,26 @@ struct EditCosts {
   EditCosts() : insert_cost(1), delete_cost(1), replace_cost(1) {}
   EditCosts(float insert_cost, float delete_cost, float replace_cost)
       : insert_cost(insert_cost), delete_cost(delete_cost), replace_cost(replace_cost) {}
+};
+
+// include/fuzzy/sentence.hh:24-48: the real (surface) tokens of a sentence plus the penalty tokens
+// (itoks) that sit in the gaps between them; gap i is in front of token i, gap size() is trailing.
+class Sentence {
+public:
+  Sentence() {}
+  Sentence(const Tokens& s) : _tokens(s) {}
+  operator Tokens() const { return _tokens; }
+  const std::string& operator[](size_t i) const { return _tokens[i]; }
+  void push_back(const std::string& token) { _tokens.push_back(token); }
+  void reserve(size_t n) { _tokens.reserve(n); }
+  size_t size() const { return _tokens.size(); }
+  bool empty() const { return _tokens.empty(); }
+  void set_itok(size_t idx, const std::string& itok) { _itoks[idx] += itok; }
+  const std::unordered_map<size_t, std::string>& itoks() const { return _itoks; }
+
+private:
+  Tokens _tokens;
+  std::unordered_map<size_t, std::string> _itoks;
 };
 
 class FuzzyMatch {
@@ -67,9 +89,16 @@ public:
   FuzzyMatch& operator=(const FuzzyMatch&) = delete;
 
   // add_tm(id, Tokens, sort): src/fuzzy_match.cc:196-203 + src/suffix_array_index.cc:10-30
-  bool add_tm(const std::string& id, const Tokens& norm, bool sort = true) {
-    if (!norm.empty() && norm.size() <= _max_tokens) {
+  bool add_tm(const std::string& id, const Tokens& norm, bool sort = true) { return add_tm(id, Sentence(norm), norm, sort); }
+
+  // add_tm(id, Sentence, Tokens, sort): src/fuzzy_match.cc:205-211; kept iff the real sentence is
+  // non-empty and the normalised one is not longer than the cap (src/suffix_array_index.cc:16)
+  bool add_tm(const std::string& id, const Sentence& source, const Tokens& norm, bool sort = true) {
+    if (!source.empty() && norm.size() <= _max_tokens) {
+      if (source.size() != norm.size()) throw std::invalid_argument("real and normalised sentences differ in length");
       for (const auto& w : norm) _tm_tokens.push_back((int32_t)add_word(w));
+      append_real(source, _tm_real, _tm_gaps);
+      if (!source.itoks().empty() || static_cast<Tokens>(source) != norm) _tm_plain = false;
       _tm_off.push_back((int64_t)_tm_tokens.size());
       _ids.push_back(id);
       _dirty = true;
@@ -84,6 +113,7 @@ public:
     _index = nullptr;
     check(fm_index_create(_tm_tokens.data(), _tm_off.data(), (int64_t)_tm_off.size() - 1, (int32_t)_forms.size(),
                           (int32_t)_max_tokens, nullptr, 0, 0, _device, &_index));
+    _real_uploaded = false;
     _dirty = false;
   }
 
@@ -101,19 +131,46 @@ public:
     return matches.size() > 0;
   }
 
+  // match(Sentence real, Tokens pattern, ..., no_perfect, ...): include/fuzzy/fuzzy_match.hh:70-82 --
+  // adds the real-token / case / penalty-token terms of _edit_distance (src/edit_distance.cc:19-62).
+  bool match(const Sentence& real, const Tokens& pattern, float fuzzy, unsigned number_of_matches, bool no_perfect,
+             std::vector<Match>& matches, int min_subseq_length = 3, float min_subseq_ratio = 0.3f, float vocab_idf_penalty = 0,
+             const EditCosts& edit_costs = EditCosts(), float contrastive_factor = 0,
+             ContrastReduce reduce = ContrastReduce::MEAN, int contrast_buffer = -1) const {
+    std::vector<std::vector<Match>> out(1);
+    const std::vector<Sentence> reals(1, real);
+    run_batch({pattern}, &reals, fuzzy, number_of_matches, out, min_subseq_length, min_subseq_ratio, vocab_idf_penalty, edit_costs,
+              contrastive_factor, reduce, contrast_buffer, no_perfect);
+    matches.insert(matches.end(), out[0].begin(), out[0].end());
+    return matches.size() > 0;
+  }
+
   // The batched front-end: out[i] receives the matches of patterns[i] (appended).
   void match_batch(const std::vector<Tokens>& patterns, float fuzzy, unsigned number_of_matches,
                    std::vector<std::vector<Match>>& out, int min_subseq_length = 2, float min_subseq_ratio = 0,
                    float vocab_idf_penalty = 0, const EditCosts& edit_costs = EditCosts(), float contrastive_factor = 0,
                    ContrastReduce reduce = ContrastReduce::MEAN, int contrast_buffer = -1, bool no_perfect = false) const {
+    run_batch(patterns, nullptr, fuzzy, number_of_matches, out, min_subseq_length, min_subseq_ratio, vocab_idf_penalty, edit_costs,
+              contrastive_factor, reduce, contrast_buffer, no_perfect);
+  }
+
+private:
+  // reals == nullptr: the real sentence of every pattern is the pattern itself (Tokens overload)
+  void run_batch(const std::vector<Tokens>& patterns, const std::vector<Sentence>* reals, float fuzzy, unsigned number_of_matches,
+                 std::vector<std::vector<Match>>& out, int min_subseq_length, float min_subseq_ratio, float vocab_idf_penalty,
+                 const EditCosts& edit_costs, float contrastive_factor, ContrastReduce reduce, int contrast_buffer,
+                 bool no_perfect) const {
     if (!_index || _dirty) throw std::logic_error("FuzzyMatch::sort() must be called before match()");
-    std::vector<int32_t> q_tok;
+    std::vector<int32_t> q_tok, q_real, q_gaps;
     std::vector<int64_t> q_off(1, 0);
-    for (const auto& p : patterns) {
+    for (size_t k = 0; k < patterns.size(); k++) {
+      const Tokens& p = patterns[k];
       for (const auto& w : p) {
         auto it = _form2index.find(w);
         q_tok.push_back(it == _form2index.end() ? 1 : (int32_t)it->second);  // VOCAB_UNK
       }
+      if (reals && (*reals)[k].size() != p.size()) throw std::invalid_argument("real and normalised pattern differ in length");
+      append_real(reals ? (*reals)[k] : Sentence(p), q_real, q_gaps);
       q_off.push_back((int64_t)q_tok.size());
     }
     fm_params prm;
@@ -127,7 +184,16 @@ public:
     std::vector<int32_t> cnt((size_t)n_q);
     for (;;) {
       res.assign((size_t)(n_q * cap), fm_match());
-      check(fm_match_batch(_index, q_tok.data(), q_off.data(), n_q, &prm, cap, res.data(), cnt.data()));
+      if (!reals && _tm_plain) {  // nothing but normalised tokens anywhere: the plain path is equivalent
+        check(fm_match_batch(_index, q_tok.data(), q_off.data(), n_q, &prm, cap, res.data(), cnt.data()));
+      } else {
+        if (!_real_uploaded) {
+          check(fm_index_set_real(_index, _tm_real.data(), _tm_gaps.data(), _tm_off.data(), (int64_t)_tm_off.size() - 1));
+          _real_uploaded = true;
+        }
+        check(fm_match_batch_real(_index, q_tok.data(), q_real.data(), q_gaps.data(), q_off.data(), n_q, &prm, itok_table().data(),
+                                  (int32_t)_itoks.size(), cap, res.data(), cnt.data()));
+      }
       int64_t mx = 0;
       for (auto c : cnt) mx = c > mx ? c : mx;
       if (mx <= cap) break;
@@ -146,7 +212,49 @@ public:
       }
   }
 
-private:
+  // real forms and penalty tokens are interned here; equal strings <=> equal ids
+  void append_real(const Sentence& s, std::vector<int32_t>& real, std::vector<int32_t>& gaps) const {
+    for (size_t i = 0; i < s.size(); i++) {
+      const std::string& t = s[i];
+      auto it = _real2id.find(t);
+      if (it == _real2id.end()) it = _real2id.emplace(t, (int32_t)_real2id.size()).first;
+      const bool case_class = t.empty() || std::strchr("LUMC", t[0]) != nullptr;  // src/edit_distance.cc:55
+      real.push_back((it->second << 1) | (case_class ? 1 : 0));
+    }
+    const size_t g0 = gaps.size();
+    gaps.resize(g0 + s.size() + 1, 0);
+    for (const auto& kv : s.itoks()) {
+      if (kv.first > s.size() || kv.second.empty()) continue;
+      auto it = _itok2id.find(kv.second);
+      if (it == _itok2id.end()) {
+        it = _itok2id.emplace(kv.second, (int32_t)_itoks.size()).first;
+        _itoks.push_back(kv.second);
+        _itok_dist.clear();  // rebuilt on demand
+      }
+      gaps[g0 + kv.first] = it->second;
+    }
+  }
+  // pairwise _edit_distance_char (include/fuzzy/edit_distance.hxx:7-35); row / column 0 = lengths
+  const std::vector<int32_t>& itok_table() const {
+    const size_t k = _itoks.size();
+    if (_itok_dist.size() == k * k) return _itok_dist;
+    _itok_dist.assign(k * k, 0);
+    for (size_t a = 0; a < k; a++)
+      for (size_t b = 0; b < k; b++) {
+        const std::string &s1 = _itoks[a], &s2 = _itoks[b];
+        if (s1.empty() || s2.empty()) { _itok_dist[a * k + b] = (int32_t)(s1.size() + s2.size()); continue; }
+        std::vector<int> prev(s2.size() + 1), cur(s2.size() + 1);
+        for (size_t j = 0; j <= s2.size(); j++) prev[j] = (int)j;
+        for (size_t i = 1; i <= s1.size(); i++) {
+          cur[0] = (int)i;
+          for (size_t j = 1; j <= s2.size(); j++)
+            cur[j] = std::min(std::min(prev[j] + 1, cur[j - 1] + 1), prev[j - 1] + (s1[i - 1] == s2[j - 1] ? 0 : 1));
+          prev.swap(cur);
+        }
+        _itok_dist[a * k + b] = prev[s2.size()];
+      }
+    return _itok_dist;
+  }
   unsigned add_word(const std::string& w) {
     auto it = _form2index.find(w);
     if (it != _form2index.end()) return it->second;
@@ -162,12 +270,20 @@ private:
   size_t _max_tokens;
   int _device;
   bool _dirty = true;
+  bool _tm_plain = true;               // every TM sentence so far had real == normalised tokens and no itoks
+  mutable bool _real_uploaded = false;  // fm_index_set_real done for the current index
   fm_index* _index = nullptr;
   std::vector<std::string> _forms;
   std::unordered_map<std::string, unsigned> _form2index;
   std::vector<std::string> _ids;
-  std::vector<int32_t> _tm_tokens;
+  std::vector<int32_t> _tm_tokens, _tm_real, _tm_gaps;
   std::vector<int64_t> _tm_off = std::vector<int64_t>(1, 0);
+  // interning tables grow during const match() calls, like a cache (not thread-safe across concurrent
+  // match() calls that introduce new real forms; guard externally or pre-intern)
+  mutable std::unordered_map<std::string, int32_t> _real2id;
+  mutable std::unordered_map<std::string, int32_t> _itok2id;
+  mutable std::vector<std::string> _itoks = std::vector<std::string>(1);  // id 0 = no penalty token
+  mutable std::vector<int32_t> _itok_dist;
 };
 
 }  // namespace FUZZY_MATCH_B200_NAMESPACE

@@ -131,6 +131,40 @@ static void batch_and_append() {
   EXPECT(m.size() == 2);
 }
 
+static void sentence_api() {
+  // Real tokens, case class and penalty tokens through add_tm(id, Sentence, Tokens) / match(Sentence, ...).
+  // Expected scores come from the unmodified reference on the same inputs (tests/golden/make_golden.py
+  // conventions): s0 differs from q0 by a case-class real form (+1) and a "," itok (+1): 0.98.
+  fuzzy::FuzzyMatch fm;
+  fuzzy::Sentence s0({"Lower-a", "b", "c"});
+  s0.set_itok(1, ",");
+  fm.add_tm("s0", s0, {"a", "b", "c"}, false);
+  fuzzy::Sentence s1({"a", "B2", "c", "d"});
+  s1.set_itok(4, ".");
+  fm.add_tm("s1", s1, {"a", "b", "c", "d"}, false);
+  fm.sort();
+  {
+    std::vector<fuzzy::FuzzyMatch::Match> m;
+    fm.match(fuzzy::Sentence(fuzzy::Tokens{"a", "b", "c"}), {"a", "b", "c"}, 0.f, 4, false, m, 2, 0.f);
+    EXPECT(m.size() == 2);
+    if (m.size() == 2) {
+      EXPECT(m[0].s_id == 0 && m[0].id == "s0"); EXPECT_NEAR(m[0].score, 0.98f, 1e-6);
+      EXPECT(m[1].s_id == 1); EXPECT_NEAR(m[1].score, 0.72f, 1e-6);
+    }
+  }
+  {
+    fuzzy::Sentence q1({"a", "b", "c", "d"});
+    q1.set_itok(2, " ");
+    std::vector<fuzzy::FuzzyMatch::Match> m;
+    fm.match(q1, {"a", "b", "c", "d"}, 0.f, 4, false, m, 2, 0.f);
+    EXPECT(m.size() == 2);
+    if (m.size() == 2) {
+      EXPECT(m[0].s_id == 1); EXPECT_NEAR(m[0].score, 0.96f, 1e-6);
+      EXPECT(m[1].s_id == 0); EXPECT_NEAR(m[1].score, 0.72f, 1e-6);
+    }
+  }
+}
+
 int main() {
   small_sentence_matches();
   max_tokens_in_pattern();
@@ -139,6 +173,7 @@ int main() {
   idf_weight();
   contrastive();
   batch_and_append();
+  sentence_api();
   std::printf(failures ? "%d FAILURES\n" : "all adapter tests passed\n", failures);
   return failures ? 1 : 0;
 }
