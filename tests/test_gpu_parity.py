@@ -334,3 +334,31 @@ def test_sentence_api_vs_oracle(tmp_path):
     out, cnt = index.match_batch(q, qo, cap=4, fuzzy=0.5, n=4, ml=2)
     ro, oc = ob.OracleIndex(tm, off, V, max_tokens=50).match_batch(q, qo, cap=4, fuzzy=0.5, n=4, ml=2)
     assert (cnt == oc).all() and all(out[i, :cnt[i]].tobytes() == ro[i].tobytes() for i in range(len(oc)))
+
+
+def test_cli_config1_output_equals_oracle(tmp_path):
+    """BASELINE.json configs[0]: 1K-sentence TM, 100 queries, f=0.8, n=1, CLI defaults ml=3 mr=0.3 -- the
+    streaming driver's stdout must equal the oracle's "score\\tid" lines (9 significant digits, ids = 1-based
+    corpus line numbers, empty line when nothing matches; cli/src/FuzzyMatch-cli.cc:219-233)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "fuzzy_match_b200", "fm_cli")
+    if not os.path.exists(exe):
+        import __graft_entry__ as g
+        g.build()
+    tm, off, V = synth.make_tm(1000, vocab=400, seed=1234)
+    q, qo = synth.make_queries(tm, off, 100, vocab=400, seed=5678)
+    text = lambda tok, o, i: " ".join("w%d" % t for t in tok[o[i]:o[i + 1]])
+    corpus = tmp_path / "tm.txt"
+    corpus.write_text("".join(text(tm, off, i) + "\n" for i in range(1000)))
+    queries = "".join(text(q, qo, i) + "\n" for i in range(100))
+    for extra, params in (([], dict(fuzzy=0.8, n=1, ml=3, mr=0.3)),
+                          (["-n", "3", "-f", "0.5", "--ml", "2", "--mr", "0", "-I", "1", "--batch", "7"], dict(fuzzy=0.5, n=3, ml=2, idf=1.0))):
+        args = [exe, "-c", str(corpus), "-f", "0.8", "-n", "1"] + extra
+        out = subprocess.run(args, input=queries, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr
+        ro, oc = ob.OracleIndex(tm, off, V).match_batch(q, qo, cap=3, **params)
+        want = ["\t".join("%.9g\t%d" % (float(m["score"]), int(m["s_id"]) + 1) for m in r) for r in ro]
+        assert out.stdout.split("\n")[:-1] == want
+        assert "NMATCH\t%d\t/\t100" % int((oc > 0).sum()) in out.stderr
