@@ -362,3 +362,69 @@ def test_cli_config1_output_equals_oracle(tmp_path):
         want = ["\t".join("%.9g\t%d" % (float(m["score"]), int(m["s_id"]) + 1) for m in r) for r in ro]
         assert out.stdout.split("\n")[:-1] == want
         assert "NMATCH\t%d\t/\t100" % int((oc > 0).sum()) in out.stderr
+
+
+# cost sets whose normaliser (include/fuzzy/costs.hh:33-47) stays positive: with e.g. (1, 0, 0) the reference
+# divides by zero and crashes, so there is nothing to be compatible with
+COST_SETS = [(1, 1, 1), (1, 0, 1), (0.5, 1.5, 1.2), (0.4, 0.3, 1.2), (1.7, 1, 0.4), (1, 1, 2.5), (0.4, 0.4, 1.0)]
+
+
+def test_randomised_parameters_vs_oracle():
+    """Seeded sweep over TM shapes and every match() parameter (incl. ml 0/1, mr above 1, fuzzy above 1 and
+    below 0, N=0, buffer 0/1/large, zero and fractional costs, idf, contrastive, no_perfect)."""
+    rng = np.random.default_rng(20251017)
+    for trial in range(40):
+        vocab = int(rng.choice([6, 20, 80, 600]))
+        hi = int(rng.choice([3, 8, 20, 45]))
+        n_sent = int(rng.choice([1, 40, 700, 2500]))
+        tm, off, V = synth.make_tm(n_sent, vocab=vocab, len_lo=0, len_hi=hi, seed=1000 + trial)
+        q, qo = synth.make_queries(tm, off, 60, vocab=vocab, seed=2000 + trial, len_lo=0, len_hi=hi)
+        q = q.copy()
+        if len(q):
+            q[rng.integers(0, len(q), size=max(1, len(q) // 15))] = rng.choice([-3, 0, 1, V, V + 7, 2**31 - 1])  # junk ids
+        max_tokens = int(rng.choice([300, hi, max(1, hi // 2)]))
+        params = dict(fuzzy=float(rng.choice([-0.2, 0.0, 0.3, 0.5, 0.7, 0.9, 1.0, 1.1])), n=int(rng.choice([0, 1, 2, 5])),
+                      ml=int(rng.choice([-1, 0, 1, 2, 3, 5])), mr=float(rng.choice([0.0, 0.3, 0.9, 1.5])),
+                      idf=float(rng.choice([0.0, 0.0, 0.5, 2.0])),
+                      costs=COST_SETS[int(rng.integers(0, len(COST_SETS)))],
+                      contrast=float(rng.choice([0.0, 0.0, 0.5, 1.0])), reduce=int(rng.integers(0, 2)),
+                      buffer=int(rng.choice([-1, 0, 1, 3, 50])), no_perfect=bool(rng.integers(0, 2)))
+        if params["idf"] and n_sent == 1:
+            params["idf"] = 0.0  # log(1) == 0 divides the idf weight by zero in the reference (NaN costs)
+        try:
+            index = fmb.Index(tm, off, V, max_tokens=max_tokens)
+        except fmb.FuzzyMatchError:
+            raise
+        oracle = ob.OracleIndex(tm, off, V, max_tokens=max_tokens)
+        cap = 4096
+        out, cnt = index.match_batch(q, qo, cap=cap, **params)
+        ro, oc = oracle.match_batch(q, qo, cap=cap, **params)
+        assert (cnt == oc).all(), (trial, params)
+        for i in range(len(oc)):
+            assert out[i, :cnt[i]].tobytes() == ro[i].tobytes(), (trial, i, params)
+
+
+def test_maximum_sentence_length():
+    """max_tokens_in_pattern at the hard cap (1023): 32 DP columns per lane, 32-word coverage masks."""
+    tm, off, V = synth.make_tm(60, vocab=900, seed=501, n_long=40, long_lo=700, long_hi=1023)
+    q, qo = synth.make_queries(tm, off, 16, vocab=900, seed=502, source_ids=np.arange(20, 60), frac_random=0.0, len_lo=700, len_hi=1023)
+    keep = np.diff(qo) <= 1023
+    index, oracle = fmb.Index(tm, off, V, max_tokens=1023), ob.OracleIndex(tm, off, V, max_tokens=1023)
+    for params in (dict(fuzzy=0.6, n=2, ml=3), dict(fuzzy=0.5, n=3, ml=3, idf=1.0, costs=(1, 0, 1))):
+        out, cnt = index.match_batch(q, qo, cap=4, **params)
+        ro, oc = oracle.match_batch(q, qo, cap=4, **params)
+        assert (cnt == oc).all() and keep.any()
+        assert all(out[i, :cnt[i]].tobytes() == ro[i].tobytes() for i in range(len(oc)))
+
+
+def test_degenerate_inputs():
+    empty = fmb.Index(np.zeros(0, dtype=np.int32), np.zeros(1, dtype=np.int64), 10)
+    out, cnt = empty.match_batch(np.array([2, 3, 4], dtype=np.int32), np.array([0, 3], dtype=np.int64), cap=2, fuzzy=0.5, n=2)
+    assert empty.num_sentences == 0 and cnt.tolist() == [0]
+    dropped = fmb.Index(np.array([2, 3, 4, 5], dtype=np.int32), np.array([0, 0, 4], dtype=np.int64), 10, max_tokens=3)
+    assert dropped.num_sentences == 0
+    index = fmb.Index(np.array([2, 3, 4], dtype=np.int32), np.array([0, 3], dtype=np.int64), 10)
+    out, cnt = index.match_batch(np.zeros(0, dtype=np.int32), np.zeros(1, dtype=np.int64), cap=1, fuzzy=0.5, n=1)
+    assert len(cnt) == 0
+    out, cnt = index.match_batch(np.array([2, 3, 4], dtype=np.int32), np.array([0, 0, 3, 3], dtype=np.int64), cap=1, fuzzy=0.5, n=1)
+    assert cnt.tolist() == [0, 1, 0] and out[1, 0]["score"] == 1.0

@@ -106,3 +106,41 @@ def test_oracle_matches_live_reference_sentence_api(params):
     assert (co == cr).all()
     for a, b in zip(ro, rr):
         assert as_tuples(a) == as_tuples(b)
+
+
+COST_SETS = [(1, 1, 1), (1, 0, 1), (0.5, 1.5, 1.2), (0.4, 0.3, 1.2), (1.7, 1, 0.4), (1, 1, 2.5), (0.4, 0.4, 1.0)]
+
+
+@pytest.mark.skipif(not ob.ref_available(), reason="oracle/_ref not built (no /root/reference here)")
+def test_oracle_matches_live_reference_randomised():
+    """Seeded sweep over TM shapes and every match() parameter (ml -1/0/1, mr above 1, fuzzy outside [0,1],
+    N=0, buffer 0/1/large, idf, contrastive, no_perfect, junk query ids). The reference is driven through
+    the Sentence overload with real == norm so that no_perfect is reachable."""
+    blob, ioff = synth.itok_table()
+    rng = np.random.default_rng(20251017)
+    for trial in range(30):
+        vocab = int(rng.choice([6, 20, 80, 600]))
+        hi = int(rng.choice([3, 8, 20, 45]))
+        n_sent = int(rng.choice([1, 40, 700, 2500]))
+        tm, off, V = synth.make_tm(n_sent, vocab=vocab, len_lo=0, len_hi=hi, seed=1000 + trial)
+        q, qo = synth.make_queries(tm, off, 60, vocab=vocab, seed=2000 + trial, len_lo=0, len_hi=hi)
+        q = q.copy()
+        if len(q):
+            q[rng.integers(0, len(q), size=max(1, len(q) // 15))] = rng.choice([-3, 0, 1, V, V + 7, 2**31 - 1])
+        max_tokens = int(rng.choice([300, hi, max(1, hi // 2)]))
+        params = dict(fuzzy=float(rng.choice([-0.2, 0.0, 0.3, 0.5, 0.7, 0.9, 1.0, 1.1])), n=int(rng.choice([0, 1, 2, 5])),
+                      ml=int(rng.choice([-1, 0, 1, 2, 3, 5])), mr=float(rng.choice([0.0, 0.3, 0.9, 1.5])),
+                      idf=float(rng.choice([0.0, 0.0, 0.5, 2.0])), costs=COST_SETS[int(rng.integers(0, len(COST_SETS)))],
+                      contrast=float(rng.choice([0.0, 0.0, 0.5, 1.0])), reduce=int(rng.integers(0, 2)),
+                      buffer=int(rng.choice([-1, 0, 1, 3, 50])), no_perfect=bool(rng.integers(0, 2)))
+        if params["idf"] and n_sent == 1:
+            params["idf"] = 0.0  # log(1) == 0: the reference divides the idf weight by zero
+        O = ob.OracleIndex(tm, off, V, max_tokens=max_tokens)
+        real = (tm.astype(np.int64) * 2).astype(np.int32)
+        R = ob.RefIndex(tm, off, max_tokens=max_tokens, real=real, gaps=np.zeros(len(tm) + len(off) - 1, dtype=np.int32),
+                        itok_blob=blob, itok_off=ioff)
+        qreal = (q.astype(np.int64) * 2 % (2**31)).astype(np.int32)
+        ro, oc = O.match_batch(q, qo, cap=4096, **params)
+        rr, cr = R.match_batch_real(q, qreal, np.zeros(len(q) + len(qo) - 1, dtype=np.int32), qo, cap=4096, **params)
+        assert (oc == cr).all(), (trial, params)
+        assert all(as_tuples(a) == as_tuples(b) for a, b in zip(ro, rr)), (trial, params)
