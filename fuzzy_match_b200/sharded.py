@@ -106,6 +106,7 @@ class ShardedIndex:
         self.s_id_base, self.n_sent_global = base, n_global
         self._send = None
         self._recv = None
+        self._part = self._part_cnt = self._all = self._all_cnt = None
         self.last_gather_bytes = 0
 
     def match_batch_device(self, d_q_tok, d_q_off, n_q, n_tok, d_out, d_out_count, cap, params, stream=None):
@@ -131,10 +132,27 @@ class ShardedIndex:
             recv = gather_records(buf, self.group, self._recv)
             self.last_gather_bytes = recv.numel() * 4
             hw = header_words(n_q)
-            offs = [recv[k].data_ptr() for k in range(self.world)]
-            recs = [recv[k].data_ptr() + hw * 4 for k in range(self.world)]
-            self.index.merge_replay_device(offs, recs, d_q_off.data_ptr(), n_q, d_out.data_ptr(), d_out_count.data_ptr(),
-                                           cap, stream=sp, params=params)
+            # Every rank holds every shard's records now; the replay of the union is split by query
+            # range (rank r replays queries [r*per, (r+1)*per)), then two small all-gathers hand every
+            # rank the complete result.
+            per = (n_q + self.world - 1) // self.world
+            q_lo = min(n_q, self.rank * per)
+            q_cnt = min(n_q, q_lo + per) - q_lo
+            msz = cap * capi.MATCH_DTYPE.itemsize
+            if self._part is None or self._part.numel() < per * msz:
+                self._part = torch.zeros(per * msz, dtype=torch.uint8, device=self.device)
+                self._part_cnt = torch.zeros(per, dtype=torch.int32, device=self.device)
+                self._all = torch.zeros(self.world * per * msz, dtype=torch.uint8, device=self.device)
+                self._all_cnt = torch.zeros(self.world * per, dtype=torch.int32, device=self.device)
+            if q_cnt > 0:
+                offs = [recv[k].data_ptr() + q_lo * 4 for k in range(self.world)]
+                recs = [recv[k].data_ptr() + hw * 4 for k in range(self.world)]
+                self.index.merge_replay_device(offs, recs, d_q_off.data_ptr() + q_lo * 4, q_cnt, self._part.data_ptr(),
+                                               self._part_cnt.data_ptr(), cap, stream=sp, params=params)
+            dist.all_gather_into_tensor(self._all[:self.world * per * msz], self._part[:per * msz], group=self.group)
+            dist.all_gather_into_tensor(self._all_cnt[:self.world * per], self._part_cnt[:per], group=self.group)
+            d_out.view(torch.uint8).reshape(-1)[:n_q * msz].copy_(self._all[:n_q * msz])
+            d_out_count[:n_q].copy_(self._all_cnt[:n_q])
 
     def match_batch(self, q_tokens, q_off, cap, **kw):
         """Host CSR in, numpy (matches[n_q, cap], counts[n_q]) out -- convenience for tests."""
