@@ -26,7 +26,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -388,7 +387,7 @@ def main():
         "config": workload_config(args, extra={
             "parallelism": ("tm-sharded x%d + NCCL all-gather" % world) if shard_tm else ("query-sharded replicas x%d" % world if world > 1 else "1 GPU"),
             "index_build_s": round(build_s, 2), "index_device_bytes": int(index.device_bytes), "found_fraction": found / n_q}),
-        "gpu_launches": int((prof["launches"] if prof else 6) * args.steps),
+        "gpu_launches": int((prof["launches"] if prof else 8) * args.steps),
         "clocks": clocks,
     }
     if e2e_ms is not None:

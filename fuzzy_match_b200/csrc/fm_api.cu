@@ -190,7 +190,7 @@ static int launch_shard(Index* ix, Workspace* w, const int32_t* d_q_tok, const i
   if (ix->profiling) cudaEventRecord(w->ev[4], st);
   launch_score(ix->dev, b, pr, ix->sm_count, st);
   if (ix->profiling) cudaEventRecord(w->ev[5], st);
-  *launches += 5;
+  *launches += w->real_active ? 5 : 6;  // prepare, search, gather, scan, score (short + wavefront kernels)
   return FM_OK;
 }
 
@@ -619,8 +619,11 @@ int fm_get_profile(const fm_index* index, fm_profile* out) {
 
 }  // extern "C"
 
-// Debug hook (not part of the public header): copies the range slices of the last batch run on
-// the first workspace. rec = int4 (query, sa_begin, match_len, size) per slice.
+// Debug hooks (not part of the public header, used while bringing the kernels up and kept for
+// stage-level inspection): fm_debug_last_slices copies the range slices of the last batch run on the
+// first workspace, rec = int4 (query, sa_begin, match_len | p << 16, size) per slice;
+// fm_debug_last_survivors copies its (query, sentence start, table slot, arrival index) records and the
+// max match length recorded for each.
 extern "C" int64_t fm_debug_last_slices(fm_index* index, int32_t* rec, int64_t* start, int64_t cap) {
   Index* ix = reinterpret_cast<Index*>(index);
   if (!ix || ix->pool.empty()) return -1;

@@ -1,14 +1,19 @@
 // fm_kernels.cu -- hand-written sm_100a kernels of the fuzzy-match hot path.
 //
-// One batch of patterns streams through six launches (no host round trip in between):
-//   prepare  per query: clamp ml, sanitise ids, build the pattern's word table
-//   search   per (query, start position): narrow suffix-array ranges, emit range slices
-//   gather   per suffix-array element of every slice: length bound, sentence fetch, coverage bound,
-//            dedup (query, sentence) with max match length            <- the "suffix-range gather"
-//   scan     exclusive scan of survivors per query
-//   score    per surviving (query, sentence): warp-wide wavefront edit-distance DP
-//   replay   per query: the reference's sequential bound heap / top-N over the scored candidates
-//   (+ contrast: per query warp, contrastive rerank)
+// One batch of patterns streams through eight launches (no host round trip in between):
+//   prepare      per query: clamp ml, sanitise ids, build the pattern's word table and signature masks
+//   search       per (query, start position): bigram / trigram directory probes, then narrow the
+//                suffix-array range token by token; emit range slices
+//   gather       per suffix-array element of every slice: length window + signature bound from one
+//                128-bit load, exact coverage for the few that pass, dedup (query, sentence) with max
+//                match length                                          <- the "suffix-range gather"
+//   scan         exclusive scan of survivors per query (chained CTAs)
+//   score        per surviving (query, sentence): edit-distance DP -- registers for p <= 32 (thread per
+//                pair), warp-wide wavefront in shared memory above     <- the "DP kernel"
+//   replay       per query: the reference's sequential bound heap / top-N over the scored candidates
+//                (warp per query, CTA per query for very long candidate lists)
+//   (+ bounds when the parameters change: per pattern length tables of the two rejection bounds;
+//    + contrast: per query warp, contrastive rerank)
 //
 // Integer indexing and scalar fp32 only -- no tensor cores. All float arithmetic that reaches a
 // result is written with __fadd_rn/__fmul_rn/__fdiv_rn in the reference's evaluation order so no
