@@ -76,6 +76,8 @@ static int ensure_queries(Workspace* w, int64_t n_q, int64_t n_tok, bool staging
 }
 static int ensure_slices(Workspace* w, int64_t n) {
   if (n <= w->cap_slices) return FM_OK;
+  // the packed (slices << 38 | elements) counter leaves 26 bits for the slice count
+  if (n >= (int64_t(1) << 26) - 65536) { set_error("too many suffix-array range slices in one batch: split the batch"); return FM_ERR_NOMEM; }
   int rc;
   if ((rc = dev_realloc(&w->sl_start, n + 1)) || (rc = dev_realloc(&w->sl_rec, n))) return rc;
   w->cap_slices = n;
@@ -99,6 +101,7 @@ static int ensure_bounds(Index* ix, Workspace* w) {
 static int ensure_survivors(Workspace* w, int64_t n) {
   if (n <= w->cap_surv) return FM_OK;
   int rc;
+  if (n > (int64_t(1) << 28)) { set_error("too many surviving candidates in one batch: split the batch"); return FM_ERR_NOMEM; }
   uint32_t hs = 1u << 20;
   while ((int64_t)hs < 4 * n) hs <<= 1;
   if ((rc = dev_realloc(&w->surv, n)) || (rc = dev_realloc(&w->surv_len, n)) || (rc = dev_realloc(&w->rec, n)) ||
@@ -197,7 +200,7 @@ static int launch_shard(Index* ix, Workspace* w, const int32_t* d_q_tok, const i
 static int initial_worklists(Index* ix, Workspace* w, int64_t n_q, int64_t n_tok) {
   int rc;
   if ((rc = ensure_bounds(ix, w))) return rc;
-  if ((rc = ensure_slices(w, std::max<int64_t>(1 << 16, 8 * n_tok + 65536)))) return rc;
+  if ((rc = ensure_slices(w, std::min<int64_t>((int64_t(1) << 26) - (1 << 17), std::max<int64_t>(1 << 16, 8 * n_tok + 65536))))) return rc;
   if ((rc = ensure_spans(w, std::max<int64_t>(1 << 16, 2 * n_tok + 65536)))) return rc;
   return ensure_survivors(w, std::max<int64_t>(1 << 18, 8 * n_q));
 }
@@ -456,11 +459,11 @@ static int match_batch_host(fm_index* index, const int32_t* q_tokens, const int6
   // one chunk and the D2H copy of another overlap the kernels of a third. Chunks also keep the
   // offsets int32 and the workspaces bounded.
   const int kSlots = 3;
-  const int64_t kMaxTok = 1 << 25;
+  const int64_t kMaxTok = 1 << 22;
   // (measured on B200: for 100k-query batches one chunk is fastest -- per-chunk launch and tail costs
   // outweigh the copy overlap -- so chunking only bounds very large batches unless FM_HOST_CHUNKS asks)
   static const int n_chunks = getenv("FM_HOST_CHUNKS") ? std::max(1, atoi(getenv("FM_HOST_CHUNKS"))) : 1;
-  const int64_t chunk_q = std::min<int64_t>(1 << 20, std::max<int64_t>(16384, (n_q + n_chunks - 1) / n_chunks));
+  const int64_t chunk_q = std::min<int64_t>(1 << 18, std::max<int64_t>(16384, (n_q + n_chunks - 1) / n_chunks));
   HostChunk slots[kSlots];
   struct Releaser {
     Index* ix; HostChunk* s; int n;
@@ -514,7 +517,10 @@ int fm_match_batch_device(fm_index* index, const int32_t* d_q_tokens, const int3
   Index* ix = reinterpret_cast<Index*>(index);
   Params pr;
   int rc;
-  if (!ix || n_q < 0 || cap < 1 || n_q > (1 << 24) || n_query_tokens > (int64_t(1) << 29)) { set_error("bad argument"); return FM_ERR_INVALID; }
+  if (!ix || n_q < 0 || cap < 1 || n_q > (1 << 20) || n_query_tokens > (int64_t(1) << 25)) {
+    set_error("bad argument (device batches hold at most 2^20 queries / 2^25 tokens)");
+    return FM_ERR_INVALID;
+  }
   if ((rc = check_params(params, &pr))) return rc;
   if (n_q == 0) return FM_OK;
   FM_CUDA(cudaSetDevice(ix->device));
