@@ -53,7 +53,7 @@ static int ensure_queries(Workspace* w, int64_t n_q, int64_t n_tok, bool staging
   if (n_q > w->cap_q) {
     const int64_t c = round_up(n_q + n_q / 4 + 1024, 1024);
     if ((rc = dev_realloc(&w->qmeta, c)) || (rc = dev_realloc(&w->q_cnt, c + 1)) || (rc = dev_realloc(&w->q_base, c + 1)) ||
-        (rc = dev_realloc(&w->acc_cnt, c)) || (rc = dev_realloc(&w->heavy_q, c)) || (rc = dev_realloc(&w->qmask, 3 * c)) || (rc = dev_realloc(&w->d_q_off, c + 1)) || (rc = dev_realloc(&w->d_out_count, c + 1)))
+        (rc = dev_realloc(&w->acc_cnt, c)) || (rc = dev_realloc(&w->heavy_q, c)) || (rc = dev_realloc(&w->mid_q, c)) || (rc = dev_realloc(&w->qmask, 3 * c)) || (rc = dev_realloc(&w->d_q_off, c + 1)) || (rc = dev_realloc(&w->d_out_count, c + 1)))
       return rc;
     w->cap_q = c;
     w->cap_surv = 0;  // heapbuf depends on cap_q
@@ -125,7 +125,7 @@ static void free_workspace(Workspace* w) {
   cudaFree(w->d_q_tok); cudaFree(w->d_q_off); cudaFree(w->d_q_real); cudaFree(w->d_q_gap); cudaFree(w->d_itok_dist); cudaFree(w->pat); cudaFree(w->chain_q); cudaFree(w->qmeta); cudaFree(w->tbl); cudaFree(w->pinfo); cudaFree(w->cmin_tab); cudaFree(w->span_slice); cudaFree(w->qmask);
   cudaFree(w->sl_start); cudaFree(w->sl_rec); cudaFree(w->hkey); cudaFree(w->hlm); cudaFree(w->surv); cudaFree(w->surv_len);
   cudaFree(w->q_cnt); cudaFree(w->q_base); cudaFree(w->acc_cnt); cudaFree(w->rec); cudaFree(w->heapbuf); cudaFree(w->ctr); cudaFree(w->scan_chain);
-  cudaFree(w->d_out); cudaFree(w->d_out_count); cudaFree(w->mrec); cudaFree(w->m_cnt); cudaFree(w->m_base); cudaFree(w->m_acc); cudaFree(w->m_heap); cudaFree(w->heavy_q); cudaFree(w->m_heavy); cudaFree(w->sort_key); cudaFree(w->sort_key2); cudaFree(w->m_key2); cudaFree(w->sort_idx); cudaFree(w->m_key); cudaFree(w->m_idx);
+  cudaFree(w->d_out); cudaFree(w->d_out_count); cudaFree(w->mrec); cudaFree(w->m_cnt); cudaFree(w->m_base); cudaFree(w->m_acc); cudaFree(w->m_heap); cudaFree(w->heavy_q); cudaFree(w->m_heavy); cudaFree(w->mid_q); cudaFree(w->m_mid); cudaFree(w->sort_key); cudaFree(w->sort_key2); cudaFree(w->m_key2); cudaFree(w->sort_idx); cudaFree(w->m_key); cudaFree(w->m_idx);
   if (w->h_ctr) cudaFreeHost(w->h_ctr);
   if (w->h_q_off32) cudaFreeHost(w->h_q_off32);
   if (w->stream) {
@@ -226,11 +226,11 @@ static int sync_and_check(Workspace* w, cudaStream_t st, int attempt, int* retri
 
 static int run_replay(Index* ix, Workspace* w, fm_record* rec, const int32_t* q_cnt, const int32_t* q_base, float* heapbuf,
                       unsigned long long* sort_key, unsigned long long* sort_key2, int32_t* sort_idx, int32_t* acc_cnt,
-                      int32_t* heavy_q, const int32_t* d_q_off, int64_t n_q, const Params& pr, int64_t cap, fm_match* d_out, int32_t* d_out_count,
+                      int32_t* mid_q, int32_t* heavy_q, const int32_t* d_q_off, int64_t n_q, const Params& pr, int64_t cap, fm_match* d_out, int32_t* d_out_count,
                       cudaStream_t st, int* launches) {
-  launch_replay(ix->dev, rec, q_cnt, q_base, heapbuf, sort_key, sort_key2, sort_idx, acc_cnt, heavy_q, d_q_off, (int32_t)n_q, pr, cap, d_out,
+  launch_replay(ix->dev, rec, q_cnt, q_base, heapbuf, sort_key, sort_key2, sort_idx, acc_cnt, mid_q, heavy_q, d_q_off, (int32_t)n_q, pr, cap, d_out,
                 d_out_count, w->ctr, ix->sm_count, st);
-  (*launches) += 2;
+  (*launches) += 3;
   if (pr.contrast > 0.f) {
     launch_contrast(ix->dev, rec, q_base, sort_idx, acc_cnt, (int32_t)n_q, pr, cap, d_out, d_out_count, w->ctr, ix->sm_count, st);
     (*launches)++;
@@ -267,7 +267,7 @@ static int match_device(Index* ix, Workspace* w, const int32_t* d_q_tok, const i
   if ((rc = initial_worklists(ix, w, n_q, n_tok))) return rc;
   for (int attempt = 0;; attempt++) {
     if ((rc = launch_shard(ix, w, d_q_tok, d_q_off, n_q, n_tok, pr, st, &launches))) return rc;
-    if ((rc = run_replay(ix, w, w->rec, w->q_cnt, w->q_base, w->heapbuf, w->sort_key, w->sort_key2, w->sort_idx, w->acc_cnt, w->heavy_q, d_q_off, n_q, pr, cap, d_out, d_out_count,
+    if ((rc = run_replay(ix, w, w->rec, w->q_cnt, w->q_base, w->heapbuf, w->sort_key, w->sort_key2, w->sort_idx, w->acc_cnt, w->mid_q, w->heavy_q, d_q_off, n_q, pr, cap, d_out, d_out_count,
                          st, &launches)))
       return rc;
     const int again = sync_and_check(w, st, attempt, &retries);
@@ -409,7 +409,7 @@ static int launch_host_chunk(Index* ix, HostChunk& c, const int32_t* q_tokens, c
   FM_CUDA(cudaMemsetAsync(w->d_out, 0, c.nq * cap * sizeof(fm_match), st));  // slots past the count read as zero
   c.launches = 0;
   if ((rc = launch_shard(ix, w, w->d_q_tok, w->d_q_off, c.nq, c.ntok, pr, st, &c.launches))) return rc;
-  if ((rc = run_replay(ix, w, w->rec, w->q_cnt, w->q_base, w->heapbuf, w->sort_key, w->sort_key2, w->sort_idx, w->acc_cnt, w->heavy_q, w->d_q_off,
+  if ((rc = run_replay(ix, w, w->rec, w->q_cnt, w->q_base, w->heapbuf, w->sort_key, w->sort_key2, w->sort_idx, w->acc_cnt, w->mid_q, w->heavy_q, w->d_q_off,
                        c.nq, pr, cap, w->d_out, w->d_out_count, st, &c.launches)))
     return rc;
   FM_CUDA(cudaMemcpyAsync(w->h_ctr, w->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
@@ -432,7 +432,7 @@ static int finish_host_chunk(Index* ix, HostChunk& c, const Params& pr, int64_t 
     if (!again) break;
     int rc;
     if ((rc = launch_shard(ix, w, w->d_q_tok, w->d_q_off, c.nq, c.ntok, pr, st, &c.launches))) return rc;
-    if ((rc = run_replay(ix, w, w->rec, w->q_cnt, w->q_base, w->heapbuf, w->sort_key, w->sort_key2, w->sort_idx, w->acc_cnt, w->heavy_q,
+    if ((rc = run_replay(ix, w, w->rec, w->q_cnt, w->q_base, w->heapbuf, w->sort_key, w->sort_key2, w->sort_idx, w->acc_cnt, w->mid_q, w->heavy_q,
                          w->d_q_off, c.nq, pr, cap, w->d_out, w->d_out_count, st, &c.launches)))
       return rc;
     FM_CUDA(cudaMemcpyAsync(out + c.q0 * cap, w->d_out, c.nq * cap * sizeof(fm_match), cudaMemcpyDeviceToHost, st));
@@ -581,7 +581,7 @@ int fm_merge_replay_device(fm_index* index, int n_shards, const int32_t* const* 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (n_q > w->cap_mq) {
     if ((rc = dev_realloc(&w->m_cnt, n_q + 1)) || (rc = dev_realloc(&w->m_base, n_q + 1)) || (rc = dev_realloc(&w->m_acc, n_q + 1)) ||
-        (rc = dev_realloc(&w->m_heavy, n_q + 1)))
+        (rc = dev_realloc(&w->m_heavy, n_q + 1)) || (rc = dev_realloc(&w->m_mid, n_q + 1)))
       return rc;
     w->cap_mq = n_q;
     w->cap_mrec = 0;  // m_heap depends on cap_mq
@@ -602,7 +602,7 @@ int fm_merge_replay_device(fm_index* index, int n_shards, const int32_t* const* 
   launch_merge_copy(n_shards, d_rec_off, d_rec, w->m_base, w->mrec, (int32_t)n_q, st);
   launches += 3;
   FM_CUDA(cudaMemsetAsync(w->ctr, 0, sizeof(Counters), st));
-  if ((rc = run_replay(ix, w, w->mrec, w->m_cnt, w->m_base, w->m_heap, w->m_key, w->m_key2, w->m_idx, w->m_acc, w->m_heavy, d_q_off, n_q, pr, cap, d_out, d_out_count, st, &launches)))
+  if ((rc = run_replay(ix, w, w->mrec, w->m_cnt, w->m_base, w->m_heap, w->m_key, w->m_key2, w->m_idx, w->m_acc, w->m_mid, w->m_heavy, d_q_off, n_q, pr, cap, d_out, d_out_count, st, &launches)))
     return rc;
   FM_CUDA(cudaStreamSynchronize(st));
   FM_CUDA(cudaGetLastError());

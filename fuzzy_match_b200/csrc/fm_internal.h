@@ -77,8 +77,9 @@ struct Counters {
   unsigned int n_surv;
   unsigned int overflow;  // bit0 slices, bit1 survivors, bit2 span index
   unsigned int n_matches;
-  unsigned int n_heavy;  // queries with more than 32 scored candidates
-  unsigned int pad[2];
+  unsigned int n_heavy;  // queries with more than kWarpMax scored candidates (CTA each)
+  unsigned int n_mid;    // queries with 2..kWarpMax scored candidates (warp each)
+  unsigned int pad[1];
 };
 static const int kElemBits = 38;
 
@@ -166,7 +167,7 @@ struct Workspace {
   unsigned int* hlm = nullptr;
   SurvRec* surv = nullptr;
   uint16_t* surv_len = nullptr;
-  int32_t *q_cnt = nullptr, *q_base = nullptr, *acc_cnt = nullptr, *heavy_q = nullptr, *m_heavy = nullptr;
+  int32_t *q_cnt = nullptr, *q_base = nullptr, *acc_cnt = nullptr, *heavy_q = nullptr, *m_heavy = nullptr, *mid_q = nullptr, *m_mid = nullptr;
   fm_record* rec = nullptr;
   float* heapbuf = nullptr;
   unsigned long long *sort_key = nullptr, *m_key = nullptr, *sort_key2 = nullptr, *m_key2 = nullptr;
@@ -244,8 +245,8 @@ void launch_scan(const int32_t* in, int32_t* out, int32_t n, unsigned long long*
 void launch_score(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st);
 void launch_replay(const IndexDev& ix, const fm_record* rec, const int32_t* q_cnt, const int32_t* q_base, float* heapbuf,
                    unsigned long long* sort_key, unsigned long long* sort_key2, int32_t* sort_idx, int32_t* acc_cnt,
-                   int32_t* heavy_q, const int32_t* q_off, int32_t n_q, const Params& p, int64_t cap, fm_match* out,
-                   int32_t* out_count, Counters* ctr, int sm_count, cudaStream_t st);
+                   int32_t* mid_q, int32_t* heavy_q, const int32_t* q_off, int32_t n_q, const Params& p, int64_t cap,
+                   fm_match* out, int32_t* out_count, Counters* ctr, int sm_count, cudaStream_t st);
 void launch_contrast(const IndexDev& ix, fm_record* rec, const int32_t* q_base, const int32_t* sort_idx,
                      const int32_t* acc_cnt, int32_t n_q, const Params& p, int64_t cap, fm_match* out, int32_t* out_count,
                      Counters* ctr, int sm_count, cudaStream_t st);

@@ -1032,6 +1032,53 @@ __device__ void warp_sort_keys(unsigned long long* keys, int n) {
   }
 }
 
+// One THREAD per query: queries with no scored candidate or exactly one (the great majority at the
+// headline configuration) are finished here -- with a single candidate the bound is still FLT_MAX, so
+// the loop of src/fuzzy_match.cc:570-611 reduces to the no_perfect / score tests. Queries with 2..kWarpMax
+// candidates are queued for fm_replay_kernel (a warp each), longer ones for fm_replay_heavy_kernel.
+__global__ void __launch_bounds__(256) fm_replay_small_kernel(fm_record* rec, const int32_t* __restrict__ q_cnt,
+                                                              const int32_t* __restrict__ q_base, int32_t* sort_idx,
+                                                              int32_t* acc_cnt, int32_t* mid_q, int32_t* heavy_q,
+                                                              const int32_t* __restrict__ q_off, int n_q, Params pr, long long cap,
+                                                              fm_match* out, int32_t* out_count, Counters* ctr, int warp_max) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_q) return;
+  if (ctr->overflow) return;
+  const int n = q_cnt[q];
+  if (n > 1) {
+    if (n <= warp_max) mid_q[atomicAdd(&ctr->n_mid, 1u)] = q;
+    else heavy_q[atomicAdd(&ctr->n_heavy, 1u)] = q;
+    return;
+  }
+  int nacc = 0;
+  if (n == 1) {
+    const int base = q_base[q];
+    fm_record r = rec[base];
+    const int p = q_off[q + 1] - q_off[q];
+    const float bound = FLT_MAX;
+    if (!(r.rowmin_max > bound || r.cost > bound) && !(pr.no_perfect && r.cost == 0.f && r.length == p)) {
+      const float score = score_of(r.cost);
+      if (score >= pr.fuzzy) {
+        r.rowmin_max = score;  // slot reused: score
+        r.reserved[1] = 0;
+        r.reserved[2] = 0;
+        rec[base] = r;
+        sort_idx[base] = 0;
+        nacc = 1;
+      }
+    }
+    if (pr.contrast <= 0.f && nacc && cap > 0) out[(long long)q * cap] = to_match(r, 0.f);
+  }
+  if (pr.contrast > 0.f) {
+    acc_cnt[q] = nacc;
+    if (n == 0) out_count[q] = 0;
+    return;
+  }
+  const int want = pr.n_matches == 0 ? nacc : min(nacc, pr.n_matches);
+  out_count[q] = want;
+  if (want) atomicAdd(&ctr->n_matches, 1u);
+}
+
 // One warp per query with <= kWarpMax scored candidates: candidate order (ngram_matches.cc:20-29:
 // longest match desc, s_id asc) by register rank sort (<= 32) or a shared-memory bitonic sort of packed
 // keys, the replay, result order, top-N output (:670-679). Larger queries are queued for
@@ -1040,27 +1087,18 @@ static const int kWarpMax = 256;
 __global__ void __launch_bounds__(256) fm_replay_kernel(fm_record* rec, const int32_t* __restrict__ q_cnt,
                                                         const int32_t* __restrict__ q_base, float* heapbuf,
                                                         unsigned long long* sort_key, int32_t* sort_idx, int32_t* acc_cnt,
-                                                        int32_t* heavy_q, const int32_t* __restrict__ q_off, int n_q, Params pr,
-                                                        long long cap, fm_match* out, int32_t* out_count, Counters* ctr) {
+                                                        const int32_t* __restrict__ mid_q, const int32_t* __restrict__ q_off,
+                                                        Params pr, long long cap, fm_match* out, int32_t* out_count,
+                                                        Counters* ctr) {
   __shared__ float s_heap[8][64];
   __shared__ unsigned long long s_keys[8][kWarpMax];
   const int lane = threadIdx.x & 31;
-  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (q >= n_q) return;
-  const int n = q_cnt[q];
-  if (n == 0 || n > kWarpMax) {
-    if (lane == 0) {
-      if (ctr->overflow) return;
-      if (n == 0) {
-        if (pr.contrast > 0.f) acc_cnt[q] = 0;
-        out_count[q] = 0;
-      } else {
-        heavy_q[atomicAdd(&ctr->n_heavy, 1u)] = q;
-      }
-    }
-    return;
-  }
   if (ctr->overflow) return;
+  const int n_mid = (int)ctr->n_mid;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < n_mid; m += n_warps) {
+  const int q = mid_q[m];
+  const int n = q_cnt[q];
   const int p = q_off[q + 1] - q_off[q];
   const int base = q_base[q];
   fm_record* seg = rec + base;
@@ -1115,13 +1153,16 @@ __global__ void __launch_bounds__(256) fm_replay_kernel(fm_record* rec, const in
   }
   if (pr.contrast > 0.f) {
     if (lane == 0) acc_cnt[q] = nacc;
-    return;
+    __syncwarp();
+    continue;
   }
   const int want = pr.n_matches == 0 ? nacc : min(nacc, pr.n_matches);
   for (int k = lane; k < want && k < cap; k += 32) out[(long long)q * cap + k] = to_match(seg[idx[k]], 0.f);
   if (lane == 0) {
     out_count[q] = want;
     if (want) atomicAdd(&ctr->n_matches, (unsigned)want);
+  }
+  __syncwarp();
   }
 }
 
@@ -1421,11 +1462,14 @@ void launch_score(const IndexDev& ix, const BatchDev& b, const Params& p, int sm
 }
 void launch_replay(const IndexDev& ix, const fm_record* rec, const int32_t* q_cnt, const int32_t* q_base, float* heapbuf,
                    unsigned long long* sort_key, unsigned long long* sort_key2, int32_t* sort_idx, int32_t* acc_cnt,
-                   int32_t* heavy_q, const int32_t* q_off, int32_t n_q, const Params& p, int64_t cap, fm_match* out,
-                   int32_t* out_count, Counters* ctr, int sm_count, cudaStream_t st) {
-  const int grid = (n_q + 7) / 8;
-  fm_replay_kernel<<<grid, 256, 0, st>>>(const_cast<fm_record*>(rec), q_cnt, q_base, heapbuf, sort_key, sort_idx, acc_cnt,
-                                         heavy_q, q_off, n_q, p, (long long)cap, out, out_count, ctr);
+                   int32_t* mid_q, int32_t* heavy_q, const int32_t* q_off, int32_t n_q, const Params& p, int64_t cap,
+                   fm_match* out, int32_t* out_count, Counters* ctr, int sm_count, cudaStream_t st) {
+  fm_replay_small_kernel<<<(n_q + 255) / 256, 256, 0, st>>>(const_cast<fm_record*>(rec), q_cnt, q_base, sort_idx, acc_cnt, mid_q,
+                                                            heavy_q, q_off, n_q, p, (long long)cap, out, out_count, ctr, kWarpMax);
+  int grid = (n_q + 7) / 8;
+  if (grid > sm_count * 8) grid = sm_count * 8;
+  fm_replay_kernel<<<grid, 256, 0, st>>>(const_cast<fm_record*>(rec), q_cnt, q_base, heapbuf, sort_key, sort_idx, acc_cnt, mid_q,
+                                         q_off, p, (long long)cap, out, out_count, ctr);
   const size_t smem = (size_t)kHeavySmem * sizeof(unsigned long long);
   // FM_HEAVY_SMEM=<n> lowers the shared-memory sort limit so that tests reach the radix-sort path
   static const int smem_cap = getenv("FM_HEAVY_SMEM") ? std::max(64, std::min(kHeavySmem, atoi(getenv("FM_HEAVY_SMEM")))) : kHeavySmem;
