@@ -176,7 +176,6 @@ static int launch_shard(Index* ix, Workspace* w, const int32_t* d_q_tok, const i
   FM_CUDA(cudaMemsetAsync(w->ctr, 0, sizeof(Counters), st));
   FM_CUDA(cudaMemsetAsync(w->hkey, 0xff, (size_t)w->hsize * sizeof(unsigned long long), st));
   FM_CUDA(cudaMemsetAsync(w->hlm, 0, (size_t)w->hsize * sizeof(unsigned int), st));
-  if (getenv("FM_DEBUG_SYNC")) cudaStreamSynchronize(st);
   if (ix->profiling) cudaEventRecord(w->ev[0], st);
   if (!w->bounds_valid || memcmp(&w->bounds_params, &pr, sizeof(Params)) != 0) {  // per-length bound tables follow the parameters
     launch_bounds(ix->dev, b, pr, st);
@@ -189,7 +188,6 @@ static int launch_shard(Index* ix, Workspace* w, const int32_t* d_q_tok, const i
   launch_search(ix->dev, b, pr, st);
   if (ix->profiling) cudaEventRecord(w->ev[2], st);
   launch_gather(ix->dev, b, pr, ix->sm_count, st);
-  if (getenv("FM_DEBUG_SYNC2")) cudaStreamSynchronize(st);
   if (ix->profiling) cudaEventRecord(w->ev[3], st);
   launch_scan(w->q_cnt, w->q_base, (int32_t)n_q, w->scan_chain, ++w->scan_epoch, ix->sm_count, st);
   if (ix->profiling) cudaEventRecord(w->ev[4], st);
@@ -277,82 +275,6 @@ static int match_device(Index* ix, Workspace* w, const int32_t* d_q_tok, const i
     if (!again) break;
   }
   finish_profile(ix, w, n_q, n_tok, launches, retries);
-  return FM_OK;
-}
-
-}  // namespace fm
-
-using namespace fm;
-
-extern "C" {
-
-const char* fm_last_error(void) { return fm::get_error().c_str(); }
-const char* fm_version(void) { return "fuzzy_match_b200 0.1 (sm_100a)"; }
-
-int fm_index_create(const int32_t* tokens, const int64_t* sent_off, int64_t n_sent, int32_t vocab_size,
-                    int32_t max_tokens_in_pattern, const uint32_t* sfreq_global, int64_t n_sent_global, int64_t s_id_base,
-                    int device, fm_index** out) {
-  Index* ix = nullptr;
-  const int rc = build_index(tokens, sent_off, n_sent, vocab_size, max_tokens_in_pattern, sfreq_global, n_sent_global,
-                             s_id_base, device, &ix);
-  if (out) *out = reinterpret_cast<fm_index*>(ix);
-  return rc;
-}
-
-int fm_index_save(const fm_index* index, const char* path) {
-  const Index* ix = reinterpret_cast<const Index*>(index);
-  if (!ix || !path) { set_error("NULL argument"); return FM_ERR_INVALID; }
-  return save_index(ix, path);
-}
-int fm_index_load(const char* path, int device, fm_index** out) {
-  if (!path || !out) { set_error("NULL argument"); return FM_ERR_INVALID; }
-  Index* ix = nullptr;
-  const int rc = load_index(path, device, &ix);
-  *out = reinterpret_cast<fm_index*>(ix);
-  return rc;
-}
-
-void fm_index_destroy(fm_index* index) {
-  Index* ix = reinterpret_cast<Index*>(index);
-  if (!ix) return;
-  cudaSetDevice(ix->device);
-  for (Workspace* w : ix->pool) free_workspace(w);
-  free_index(ix);
-}
-
-int64_t fm_index_num_sentences(const fm_index* index) { return reinterpret_cast<const Index*>(index)->n_sent; }
-int64_t fm_index_num_suffixes(const fm_index* index) { return reinterpret_cast<const Index*>(index)->n_suf; }
-int32_t fm_index_max_tokens_in_pattern(const fm_index* index) { return reinterpret_cast<const Index*>(index)->max_tokens; }
-int64_t fm_index_device_bytes(const fm_index* index) { return reinterpret_cast<const Index*>(index)->device_bytes; }
-
-int fm_index_kept_sources(const fm_index* index, int64_t* kept) {
-  const Index* ix = reinterpret_cast<const Index*>(index);
-  if (!ix || !kept) { set_error("NULL argument"); return FM_ERR_INVALID; }
-  std::copy(ix->kept.begin(), ix->kept.end(), kept);
-  return FM_OK;
-}
-int fm_index_sfreq(const fm_index* index, uint32_t* sfreq) {
-  const Index* ix = reinterpret_cast<const Index*>(index);
-  if (!ix || !sfreq) { set_error("NULL argument"); return FM_ERR_INVALID; }
-  std::copy(ix->sfreq.begin(), ix->sfreq.end(), sfreq);
-  return FM_OK;
-}
-int fm_index_set_idf_stats(fm_index* index, const uint32_t* sfreq_global, int64_t n_sent_global) {
-  Index* ix = reinterpret_cast<Index*>(index);
-  if (!ix || !sfreq_global || n_sent_global < 1) { set_error("bad argument"); return FM_ERR_INVALID; }
-  FM_CUDA(cudaSetDevice(ix->device));
-  return set_idf_stats(ix, sfreq_global, n_sent_global);
-}
-int fm_index_sentence(const fm_index* index, uint32_t s, const int32_t** tokens, int32_t* length) {
-  const Index* ix = reinterpret_cast<const Index*>(index);
-  if (!ix || (int64_t)s >= ix->n_sent) { set_error("sentence id out of range"); return FM_ERR_INVALID; }
-  const int32_t st = ix->h_sent_start[s];
-  if (tokens) *tokens = ix->h_tok.data() + st;
-  if (length) {
-    int32_t n = 0;
-    while (ix->h_tok[st + n] != 0) n++;
-    *length = n;
-  }
   return FM_OK;
 }
 
@@ -460,6 +382,7 @@ static int finish_host_chunk(Index* ix, HostChunk& c, const Params& pr, int64_t 
   return FM_OK;
 }
 
+// fm_match_batch / fm_match_batch_real: chunk the host batch, keep up to kSlots chunks in flight.
 static int match_batch_host(fm_index* index, const int32_t* q_tokens, const int64_t* q_off, int64_t n_q, const fm_params* params,
                             int64_t cap, fm_match* out, int32_t* out_count, const RealInputs& ri) {
   Index* ix = reinterpret_cast<Index*>(index);
@@ -508,6 +431,82 @@ static int match_batch_host(fm_index* index, const int32_t* q_tokens, const int6
   return FM_OK;
 }
 
+}  // namespace fm
+
+using namespace fm;
+
+extern "C" {
+
+const char* fm_last_error(void) { return fm::get_error().c_str(); }
+const char* fm_version(void) { return "fuzzy_match_b200 0.1 (sm_100a)"; }
+
+int fm_index_create(const int32_t* tokens, const int64_t* sent_off, int64_t n_sent, int32_t vocab_size,
+                    int32_t max_tokens_in_pattern, const uint32_t* sfreq_global, int64_t n_sent_global, int64_t s_id_base,
+                    int device, fm_index** out) {
+  Index* ix = nullptr;
+  const int rc = build_index(tokens, sent_off, n_sent, vocab_size, max_tokens_in_pattern, sfreq_global, n_sent_global,
+                             s_id_base, device, &ix);
+  if (out) *out = reinterpret_cast<fm_index*>(ix);
+  return rc;
+}
+
+int fm_index_save(const fm_index* index, const char* path) {
+  const Index* ix = reinterpret_cast<const Index*>(index);
+  if (!ix || !path) { set_error("NULL argument"); return FM_ERR_INVALID; }
+  return save_index(ix, path);
+}
+int fm_index_load(const char* path, int device, fm_index** out) {
+  if (!path || !out) { set_error("NULL argument"); return FM_ERR_INVALID; }
+  Index* ix = nullptr;
+  const int rc = load_index(path, device, &ix);
+  *out = reinterpret_cast<fm_index*>(ix);
+  return rc;
+}
+
+void fm_index_destroy(fm_index* index) {
+  Index* ix = reinterpret_cast<Index*>(index);
+  if (!ix) return;
+  cudaSetDevice(ix->device);
+  for (Workspace* w : ix->pool) free_workspace(w);
+  free_index(ix);
+}
+
+int64_t fm_index_num_sentences(const fm_index* index) { return reinterpret_cast<const Index*>(index)->n_sent; }
+int64_t fm_index_num_suffixes(const fm_index* index) { return reinterpret_cast<const Index*>(index)->n_suf; }
+int32_t fm_index_max_tokens_in_pattern(const fm_index* index) { return reinterpret_cast<const Index*>(index)->max_tokens; }
+int64_t fm_index_device_bytes(const fm_index* index) { return reinterpret_cast<const Index*>(index)->device_bytes; }
+
+int fm_index_kept_sources(const fm_index* index, int64_t* kept) {
+  const Index* ix = reinterpret_cast<const Index*>(index);
+  if (!ix || !kept) { set_error("NULL argument"); return FM_ERR_INVALID; }
+  std::copy(ix->kept.begin(), ix->kept.end(), kept);
+  return FM_OK;
+}
+int fm_index_sfreq(const fm_index* index, uint32_t* sfreq) {
+  const Index* ix = reinterpret_cast<const Index*>(index);
+  if (!ix || !sfreq) { set_error("NULL argument"); return FM_ERR_INVALID; }
+  std::copy(ix->sfreq.begin(), ix->sfreq.end(), sfreq);
+  return FM_OK;
+}
+int fm_index_set_idf_stats(fm_index* index, const uint32_t* sfreq_global, int64_t n_sent_global) {
+  Index* ix = reinterpret_cast<Index*>(index);
+  if (!ix || !sfreq_global || n_sent_global < 1) { set_error("bad argument"); return FM_ERR_INVALID; }
+  FM_CUDA(cudaSetDevice(ix->device));
+  return set_idf_stats(ix, sfreq_global, n_sent_global);
+}
+int fm_index_sentence(const fm_index* index, uint32_t s, const int32_t** tokens, int32_t* length) {
+  const Index* ix = reinterpret_cast<const Index*>(index);
+  if (!ix || (int64_t)s >= ix->n_sent) { set_error("sentence id out of range"); return FM_ERR_INVALID; }
+  const int32_t st = ix->h_sent_start[s];
+  if (tokens) *tokens = ix->h_tok.data() + st;
+  if (length) {
+    int32_t n = 0;
+    while (ix->h_tok[st + n] != 0) n++;
+    *length = n;
+  }
+  return FM_OK;
+}
+
 int fm_match_batch(fm_index* index, const int32_t* q_tokens, const int64_t* q_off, int64_t n_q, const fm_params* params,
                    int64_t cap, fm_match* out, int32_t* out_count) {
   return match_batch_host(index, q_tokens, q_off, n_q, params, cap, out, out_count, RealInputs());
@@ -545,8 +544,9 @@ int fm_match_batch_device(fm_index* index, const int32_t* d_q_tokens, const int3
   Workspace* w = acquire(ix);
   struct Releaser { Index* ix; Workspace* w; ~Releaser() { release(ix, w); } } rel{ix, w};
   if ((rc = ensure_base(w)) || (rc = ensure_queries(w, n_q, n_query_tokens, false))) return rc;
-  return match_device(ix, w, d_q_tokens, d_q_off, n_q, n_query_tokens, pr, cap, d_out, d_out_count,
-                      static_cast<cudaStream_t>(stream));
+  rc = match_device(ix, w, d_q_tokens, d_q_off, n_q, n_query_tokens, pr, cap, d_out, d_out_count, static_cast<cudaStream_t>(stream));
+  if (rc) cudaStreamSynchronize(static_cast<cudaStream_t>(stream));  // nothing of this call may still run on the workspace
+  return rc;
 }
 
 int fm_shard_score_device(fm_index* index, const int32_t* d_q_tokens, const int32_t* d_q_off, int64_t n_q,

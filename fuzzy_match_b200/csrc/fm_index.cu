@@ -58,13 +58,14 @@ static int upload(const std::vector<T>& h, size_t extra, Index* ix, int blk, con
 // Boost binary archive, src/fuzzy_matcher_binarization.cc). Header, then the device blocks exactly as
 // they sit in HBM, then the host-side tables. Loading is read + upload: no sort, no hashing.
 static const char kMagic[8] = {'F', 'M', 'B', '2', '0', '0', 'I', 1};
-enum { BLK_TOK = 0, BLK_SA = 1, BLK_WALK = 2, BLK_QVA = 3, BLK_SID = 4, BLK_IDF = 5, BLK_BG = 6, BLK_TG = 7, BLK_REAL = 8, BLK_GAP = 9, N_BLK = 10 };
+enum { BLK_TOK = 0, BLK_SA = 1, BLK_WALK = 2, BLK_QVA = 3, BLK_SID = 4, BLK_IDF = 5, BLK_BG = 6, BLK_TG = 7, BLK_REAL = 8, BLK_GAP = 9, BLK_NEXT = 10, N_BLK = 11 };
 
 static void bind_blocks(Index* ix) {
   IndexDev& d = ix->dev;
   d.tok = static_cast<const int32_t*>(ix->d_blocks[BLK_TOK]);
   d.sa_pos = static_cast<const int32_t*>(ix->d_blocks[BLK_SA]);
   d.sa_walk = static_cast<const int4*>(ix->d_blocks[BLK_WALK]);
+  d.sa_next = static_cast<const int32_t*>(ix->d_blocks[BLK_NEXT]);
   d.qva = static_cast<const int32_t*>(ix->d_blocks[BLK_QVA]);
   d.sid_at = static_cast<const int32_t*>(ix->d_blocks[BLK_SID]);
   d.idf = static_cast<const float*>(ix->d_blocks[BLK_IDF]);
@@ -96,6 +97,8 @@ int save_index(const Index* ix, const char* path) {
   if (!ok) { set_error(std::string("write to ") + path + " failed"); return FM_ERR_INVALID; }
   return FM_OK;
 }
+
+static int derive_next(Index* ix);
 
 int load_index(const char* path, int device, Index** out) {
   *out = nullptr;
@@ -140,6 +143,7 @@ int load_index(const char* path, int device, Index** out) {
   ok = ok && fread(ix->sfreq.data(), sizeof(uint32_t), ix->sfreq.size(), f) == ix->sfreq.size();
   fclose(f);
   if (!ok) { free_index(ix); set_error(std::string("reading ") + path + " failed (truncated file or CUDA error)"); return FM_ERR_INVALID; }
+  if (!ix->d_blocks[BLK_NEXT] && derive_next(ix) != FM_OK) { free_index(ix); return FM_ERR_CUDA; }  // file older than sa_next
   bind_blocks(ix);
   IndexDev& d = ix->dev;
   d.vocab_size = ix->vocab_size; d.max_tokens = ix->max_tokens; d.n_suf = ix->n_suf;
@@ -196,6 +200,15 @@ __global__ void fm_build_walk_kernel(const int32_t* __restrict__ sa_pos, long lo
   }
   const unsigned long long sg = sig[a];
   sa_walk[i] = make_int4(sent_start[a], sent_len[a], (int)(unsigned)sg, (int)(unsigned)(sg >> 32));
+}
+
+// sa_next[i] = token at depth 3 of suffix i (0 if it has fewer than four tokens)
+__global__ void fm_build_next_kernel(const int32_t* __restrict__ tok, const int32_t* __restrict__ sa_pos, long long n_suf,
+                                     int32_t* sa_next) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_suf) return;
+  const int p = sa_pos[i];
+  sa_next[i] = (tok[p + 1] != 0 && tok[p + 2] != 0) ? tok[p + 3] : 0;
 }
 
 // counts[0] = distinct bigrams, counts[1] = distinct trigrams (run starts in the suffix array)
@@ -286,7 +299,18 @@ static int dev_alloc(Index* ix, int blk, size_t count, int fill_byte, const T** 
   return FM_OK;
 }
 
-// Builds sa_walk, sid_at and the two directories on the device from tok + sa_pos (already uploaded).
+static int derive_next(Index* ix) {
+  const int32_t* next = nullptr;
+  int rc = dev_alloc(ix, BLK_NEXT, (size_t)ix->n_suf + 4, 0, &next);
+  if (rc || ix->n_suf == 0) return rc;
+  fm_build_next_kernel<<<(unsigned)((ix->n_suf + 255) / 256), 256>>>(static_cast<const int32_t*>(ix->d_blocks[BLK_TOK]),
+                                                                      static_cast<const int32_t*>(ix->d_blocks[BLK_SA]), ix->n_suf,
+                                                                      const_cast<int32_t*>(next));
+  FM_CUDA(cudaDeviceSynchronize());
+  return FM_OK;
+}
+
+// Builds sa_walk, sa_next, sid_at and the two directories on the device from tok + sa_pos (already uploaded).
 static int build_on_device(Index* ix, const std::vector<int32_t>& sent_start) {
   IndexDev& d = ix->dev;
   const long long n_suf = ix->n_suf;
@@ -300,8 +324,9 @@ static int build_on_device(Index* ix, const std::vector<int32_t>& sent_start) {
   FM_CUDA(cudaMemcpy(d_start, sent_start.data(), (size_t)(n_sent + 1) * 4, cudaMemcpyHostToDevice));
   int rc;
   if ((rc = dev_alloc(ix, BLK_SID, (size_t)(ix->n_buf / 4) + 1, 0xff, &d.sid_at)) ||
-      (rc = dev_alloc(ix, BLK_WALK, (size_t)n_suf + 4, 0, &d.sa_walk)))
+      (rc = dev_alloc(ix, BLK_WALK, (size_t)n_suf + 4, 0, &d.sa_walk)) || (rc = derive_next(ix)))
     return rc;
+  d.sa_next = static_cast<const int32_t*>(ix->d_blocks[BLK_NEXT]);
   const int tb = 256;
   const unsigned gs = (unsigned)((n_suf + tb - 1) / tb);
   if (n_sent > 0)

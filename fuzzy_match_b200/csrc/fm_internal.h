@@ -21,6 +21,9 @@ namespace fm {
 //                         sentence length, 64-bit word signature of the sentence: bit sig_bit(w) set for
 //                         every word w). The signature gives an upper bound on the coverage without
 //                         touching the sentence.
+// sa_next  int32[n_suf]   token at depth 3 of each suffix (tok[sa_pos[k] + 3], 0 when the suffix is shorter):
+//                         the binary search that narrows a trigram range -- the only level where ranges are
+//                         still wide -- reads ONE array instead of sa_pos -> tok (two dependent misses).
 // tg_tab   int4[pow2]     trigram directory: (bigram slot, word2) -> [lo, hi); the third narrowing step in
 //                         one more probe (the reference's CLI default ml=3 only ever walks trigram ranges).
 // qva      int32[V+1]     first-word bucket table (reference _quickVocabAccess).
@@ -33,6 +36,7 @@ struct IndexDev {
   const int32_t* tok;
   const int32_t* sa_pos;
   const int4* sa_walk;
+  const int32_t* sa_next;
   const int32_t* qva;
   const int4* bg_tab;
   uint32_t bg_mask;

@@ -361,22 +361,39 @@ __global__ void __launch_bounds__(256) fm_search_kernel(IndexDev ix, BatchDev b)
         if (pos1 < 0) pos1 = __ldg(ix.sa_pos + lo);
         if (__ldg(ix.tok + (pos1 + len)) == t) { nlo = lo; nhi = hi; }
       } else if (t >= 2) {
-        int a = lo, e = hi;
-        while (a < e) {  // first suffix whose token at depth len is >= t
+        // equal range of t at depth len inside [lo, hi): one search until a probe hits t, then the
+        // lower and the upper bound advance together (two independent loads per step), so the
+        // dependent chain is log2(range) probes instead of 2*log2(range). At depth 3 -- the only
+        // level where ranges are still wide -- the key comes from sa_next in one load.
+        const bool d3 = len == 3;
+        int a = lo, e = hi, m = -1;
+        while (a < e) {
           const int mid = (int)(((unsigned)a + (unsigned)e) >> 1);
-          const int v = __ldg(ix.tok + (__ldg(ix.sa_pos + mid) + len));
-          if (v < t) a = mid + 1; else e = mid;
+          const int v = d3 ? __ldg(ix.sa_next + mid) : __ldg(ix.tok + (__ldg(ix.sa_pos + mid) + len));
+          if (v < t) a = mid + 1;
+          else if (v > t) e = mid;
+          else { m = mid; break; }
         }
-        nlo = a;
-        nhi = a;
-        if (a < hi && __ldg(ix.tok + (__ldg(ix.sa_pos + a) + len)) == t) {
-          int a2 = a + 1, e2 = hi;
-          while (a2 < e2) {  // first suffix whose token at depth len is > t
-            const int mid = (int)(((unsigned)a2 + (unsigned)e2) >> 1);
-            const int v = __ldg(ix.tok + (__ldg(ix.sa_pos + mid) + len));
-            if (v <= t) a2 = mid + 1; else e2 = mid;
+        if (m >= 0) {
+          int la = a, le = m;      // first suffix in [a, m) whose key is >= t
+          int ua = m + 1, ue = e;  // first suffix in (m, e) whose key is > t
+          while (la < le || ua < ue) {
+            const bool dl = la < le, du = ua < ue;
+            const int ml2 = (int)(((unsigned)la + (unsigned)le) >> 1), mu = (int)(((unsigned)ua + (unsigned)ue) >> 1);
+            int vl = 0, vu = 0;
+            if (d3) {
+              if (dl) vl = __ldg(ix.sa_next + ml2);
+              if (du) vu = __ldg(ix.sa_next + mu);
+            } else {
+              const int pl = dl ? __ldg(ix.sa_pos + ml2) : 0, pu = du ? __ldg(ix.sa_pos + mu) : 0;
+              if (dl) vl = __ldg(ix.tok + (pl + len));
+              if (du) vu = __ldg(ix.tok + (pu + len));
+            }
+            if (dl) { if (vl < t) la = ml2 + 1; else le = ml2; }
+            if (du) { if (vu <= t) ua = mu + 1; else ue = mu; }
           }
-          nhi = a2;
+          nlo = la;
+          nhi = ua;
         }
       }
       if (nhi > nlo) {
