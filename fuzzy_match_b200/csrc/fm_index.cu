@@ -282,8 +282,15 @@ __global__ void fm_build_trigram_kernel(const int32_t* __restrict__ tok, const i
   if (!edge) { const int pj = sa_pos[j]; edge = tok[pj] != t0 || tok[pj + 1] != t1 || tok[pj + 2] != t2; }
   if (!edge) return;
   const int bs = (int)dir_find(bg_tab, bg_mask, t0, t1);
-  if (pass == 0) tg_tab[dir_insert(tg_tab, tg_mask, bs, t2)].z = (int)i;
-  else tg_tab[dir_find(tg_tab, tg_mask, bs, t2)].w = (int)(i + 1);
+  if (pass == 0) {
+    tg_tab[dir_insert(tg_tab, tg_mask, bs, t2)].z = (int)i;
+  } else {
+    // hi, or for a trigram that occurs once -(position) - 1: the search then follows that suffix
+    // without reading sa_pos
+    bool single = i == 0;
+    if (!single) { const int pj = sa_pos[i - 1]; single = tok[pj] != t0 || tok[pj + 1] != t1 || tok[pj + 2] != t2; }
+    tg_tab[dir_find(tg_tab, tg_mask, bs, t2)].w = single ? -p - 1 : (int)(i + 1);
+  }
 }
 
 template <class T>

@@ -24,7 +24,8 @@ namespace fm {
 // sa_next  int32[n_suf]   token at depth 3 of each suffix (tok[sa_pos[k] + 3], 0 when the suffix is shorter):
 //                         the binary search that narrows a trigram range -- the only level where ranges are
 //                         still wide -- reads ONE array instead of sa_pos -> tok (two dependent misses).
-// tg_tab   int4[pow2]     trigram directory: (bigram slot, word2) -> [lo, hi); the third narrowing step in
+// tg_tab   int4[pow2]     trigram directory: (bigram slot, word2) -> [lo, hi), or (lo, -position-1) for a
+//                         trigram that occurs once; the third narrowing step in
 //                         one more probe (the reference's CLI default ml=3 only ever walks trigram ranges).
 // qva      int32[V+1]     first-word bucket table (reference _quickVocabAccess).
 // bg_tab   int4[pow2]     bigram directory: open-addressing table (word0, word1) -> [lo, hi) of the suffixes

@@ -300,7 +300,7 @@ __device__ __forceinline__ void flush_slices(const BatchDev& b, SliceBuf& sb, in
 // One thread per (query, start position) chain: the n-gram walk of src/fuzzy_match.cc:484-551 with
 // SuffixArray::equal_range (src/suffix_array.cc:105-212) restated as lower/upper bound on the ONE new
 // token at depth k inside the previous range (every suffix there already shares k tokens).
-__global__ void __launch_bounds__(256) fm_search_kernel(IndexDev ix, BatchDev b) {
+__global__ void __launch_bounds__(256, 8) fm_search_kernel(IndexDev ix, BatchDev b) {
   __shared__ SliceBuf sb;
   int nbuf = 0;
   const int lane = threadIdx.x & 31;
@@ -346,51 +346,74 @@ __global__ void __launch_bounds__(256) fm_search_kernel(IndexDev ix, BatchDev b)
     if (__any_sync(FULL, nbuf > kSliceBuf - 2)) flush_slices(b, sb, nbuf, lane, q, p);  // room for two more
     if (extending) {
       const int t = pat[it + len];  // token at depth len
-      int nlo = lo, nhi = lo;
+      int nlo = lo, nhi = lo, npos1 = -1;
+      bool last = false;
       if (t >= 2 && len == 2) {
         // bigram -> trigram through the trigram directory
         uint32_t h = bigram_hash((int)bslot, t) & ix.tg_mask;
         for (;;) {
           const int4 e = __ldg(ix.tg_tab + h);
-          if (e.x == (int)bslot && e.y == t) { nlo = e.z; nhi = e.w; break; }
+          if (e.x == (int)bslot && e.y == t) {
+            nlo = e.z;
+            nhi = e.w;
+            if (e.w < 0) { nhi = e.z + 1; npos1 = -e.w - 1; }  // a trigram that occurs once carries its position
+            break;
+          }
           if (e.x == -1) break;
           h = (h + 1) & ix.tg_mask;
         }
       } else if (t >= 2 && hi - lo == 1) {
-        // a single suffix left: follow its tokens directly (its position stays in a register)
+        // a single suffix left: the rest of the chain is the common prefix of the pattern and that
+        // suffix, and nothing is shaved off on the way (the separator 0 never equals a pattern token)
         if (pos1 < 0) pos1 = __ldg(ix.sa_pos + lo);
-        if (__ldg(ix.tok + (pos1 + len)) == t) { nlo = lo; nhi = hi; }
+        int l2 = len;
+        while (it + l2 < p && __ldg(ix.tok + (pos1 + l2)) == pat[it + l2]) l2++;
+        if (l2 > len) { nlo = lo; nhi = hi; len = l2 - 1; }
+        last = true;
       } else if (t >= 2) {
-        // equal range of t at depth len inside [lo, hi): one search until a probe hits t, then the
-        // lower and the upper bound advance together (two independent loads per step), so the
-        // dependent chain is log2(range) probes instead of 2*log2(range). At depth 3 -- the only
-        // level where ranges are still wide -- the key comes from sa_next in one load.
+        // equal range of t at depth len inside [lo, hi). The search is latency bound, so it trades
+        // probes for dependent steps: (1) quaternary narrowing, three independent pivots per step,
+        // until a pivot hits t; (2) from the hit the two ends of the run of t gallop outwards together
+        // (runs are short: the typical 4-gram range is 1-2 suffixes) and finish by bisection. At depth 3
+        // -- the only level where ranges are still wide -- the key comes from sa_next in one load.
         const bool d3 = len == 3;
+        auto key = [&](int k) { return d3 ? __ldg(ix.sa_next + k) : __ldg(ix.tok + (__ldg(ix.sa_pos + k) + len)); };
         int a = lo, e = hi, m = -1;
-        while (a < e) {
-          const int mid = (int)(((unsigned)a + (unsigned)e) >> 1);
-          const int v = d3 ? __ldg(ix.sa_next + mid) : __ldg(ix.tok + (__ldg(ix.sa_pos + mid) + len));
-          if (v < t) a = mid + 1;
-          else if (v > t) e = mid;
-          else { m = mid; break; }
+        while (m < 0 && a < e) {
+          const int n = e - a;
+          const int q1 = a + (n >> 2), q2 = a + (n >> 1), q3 = a + ((3 * n) >> 2);
+          const int v1 = key(q1), v2 = key(q2), v3 = key(q3);
+          if (v1 < t) a = q1 + 1;
+          if (v2 < t) a = q2 + 1;
+          if (v3 < t) a = q3 + 1;
+          if (v3 > t) e = q3;
+          if (v2 > t) e = q2;
+          if (v1 > t) e = q1;
+          m = v1 == t ? q1 : v2 == t ? q2 : v3 == t ? q3 : -1;
         }
         if (m >= 0) {
-          int la = a, le = m;      // first suffix in [a, m) whose key is >= t
-          int ua = m + 1, ue = e;  // first suffix in (m, e) whose key is > t
+          // keys in [.., a) are < t, keys in [e, ..) are > t, key[m] == t
+          int la = a, le = m, ls = 1;      // run start in [la, le]; keys in [le, m] == t
+          int ua = m + 1, ue = e, us = 1;  // run end in [ua, ue]; keys in [m, ua) == t
           while (la < le || ua < ue) {
             const bool dl = la < le, du = ua < ue;
-            const int ml2 = (int)(((unsigned)la + (unsigned)le) >> 1), mu = (int)(((unsigned)ua + (unsigned)ue) >> 1);
+            const int pl = ls ? max(le - ls, la) : (int)(((unsigned)la + (unsigned)le) >> 1);
+            const int pu = us ? min(ua + us - 1, ue - 1) : (int)(((unsigned)ua + (unsigned)ue) >> 1);
             int vl = 0, vu = 0;
             if (d3) {
-              if (dl) vl = __ldg(ix.sa_next + ml2);
-              if (du) vu = __ldg(ix.sa_next + mu);
+              if (dl) vl = __ldg(ix.sa_next + pl);
+              if (du) vu = __ldg(ix.sa_next + pu);
             } else {
-              const int pl = dl ? __ldg(ix.sa_pos + ml2) : 0, pu = du ? __ldg(ix.sa_pos + mu) : 0;
-              if (dl) vl = __ldg(ix.tok + (pl + len));
-              if (du) vu = __ldg(ix.tok + (pu + len));
+              const int sl = dl ? __ldg(ix.sa_pos + pl) : 0, su = du ? __ldg(ix.sa_pos + pu) : 0;
+              if (dl) vl = __ldg(ix.tok + (sl + len));
+              if (du) vu = __ldg(ix.tok + (su + len));
             }
-            if (dl) { if (vl < t) la = ml2 + 1; else le = ml2; }
-            if (du) { if (vu <= t) ua = mu + 1; else ue = mu; }
+            if (dl) {
+              if (vl < t) { la = pl + 1; ls = 0; } else { le = pl; ls <<= 1; }
+            }
+            if (du) {
+              if (vu > t) { ue = pu; us = 0; } else { ua = pu + 1; us <<= 1; }
+            }
           }
           nlo = la;
           nhi = ua;
@@ -402,9 +425,9 @@ __global__ void __launch_bounds__(256) fm_search_kernel(IndexDev ix, BatchDev b)
           if (nlo > lo) push_slice(sb, nbuf, lo, nlo - lo, len);
           if (hi > nhi) push_slice(sb, nbuf, nhi, hi - nhi, len);
         }
-        if (nlo != lo || nhi != hi) pos1 = -1;
+        if (nlo != lo || nhi != hi || npos1 >= 0) pos1 = npos1;
         lo = nlo; hi = nhi; len++;
-        if (it + len >= p) extending = false;
+        if (it + len >= p || last) extending = false;
       } else {
         extending = false;
       }
