@@ -42,6 +42,9 @@ static int ensure_base(Workspace* w) {
   if (!w->stream) {
     FM_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     for (auto& e : w->ev) FM_CUDA(cudaEventCreate(&e));
+    FM_CUDA(cudaStreamCreateWithFlags(&w->stream2, cudaStreamNonBlocking));
+    FM_CUDA(cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming));
+    FM_CUDA(cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming));
     FM_CUDA(cudaMalloc((void**)&w->ctr, sizeof(Counters)));
     FM_CUDA(cudaMalloc((void**)&w->scan_chain, 256 * sizeof(unsigned long long)));
     FM_CUDA(cudaMemset(w->scan_chain, 0, 256 * sizeof(unsigned long long)));
@@ -55,7 +58,7 @@ static int ensure_queries(Workspace* w, int64_t n_q, int64_t n_tok, bool staging
   if (n_q > w->cap_q) {
     const int64_t c = round_up(n_q + n_q / 4 + 1024, 1024);
     if ((rc = dev_realloc(&w->qmeta, c)) || (rc = dev_realloc(&w->q_cnt, c + 1)) || (rc = dev_realloc(&w->q_base, c + 1)) ||
-        (rc = dev_realloc(&w->acc_cnt, c)) || (rc = dev_realloc(&w->heavy_q, c)) || (rc = dev_realloc(&w->mid_q, c)) || (rc = dev_realloc(&w->qmask, 3 * c)) || (rc = dev_realloc(&w->d_q_off, c + 1)) || (rc = dev_realloc(&w->d_out_count, c + 1)))
+        (rc = dev_realloc(&w->acc_cnt, c)) || (rc = dev_realloc(&w->heavy_q, c)) || (rc = dev_realloc(&w->mid_q, c)) || (rc = dev_realloc(&w->qmask, 2 * c)) || (rc = dev_realloc(&w->d_q_off, c + 1)) || (rc = dev_realloc(&w->d_out_count, c + 1)))
       return rc;
     w->cap_q = c;
     w->cap_surv = 0;  // heapbuf depends on cap_q
@@ -132,6 +135,9 @@ static void free_workspace(Workspace* w) {
   if (w->h_q_off32) cudaFreeHost(w->h_q_off32);
   if (w->stream) {
     cudaStreamDestroy(w->stream);
+    if (w->stream2) cudaStreamDestroy(w->stream2);
+    if (w->ev_fork) cudaEventDestroy(w->ev_fork);
+    if (w->ev_join) cudaEventDestroy(w->ev_join);
     for (auto& e : w->ev) cudaEventDestroy(e);
   }
   delete w;
@@ -229,7 +235,7 @@ static int run_replay(Index* ix, Workspace* w, fm_record* rec, const int32_t* q_
                       int32_t* mid_q, int32_t* heavy_q, const int32_t* d_q_off, int64_t n_q, const Params& pr, int64_t cap, fm_match* d_out, int32_t* d_out_count,
                       cudaStream_t st, int* launches) {
   launch_replay(ix->dev, rec, q_cnt, q_base, heapbuf, sort_key, sort_key2, sort_idx, acc_cnt, mid_q, heavy_q, d_q_off, (int32_t)n_q, pr, cap, d_out,
-                d_out_count, w->ctr, ix->sm_count, st);
+                d_out_count, w->ctr, ix->sm_count, st, w->stream2, w->ev_fork, w->ev_join);
   (*launches) += 3;
   if (pr.contrast > 0.f) {
     launch_contrast(ix->dev, rec, q_base, sort_idx, acc_cnt, (int32_t)n_q, pr, cap, d_out, d_out_count, w->ctr, ix->sm_count, st);

@@ -84,7 +84,7 @@ struct Counters {
   unsigned int n_matches;
   unsigned int n_heavy;  // queries with more than kWarpMax scored candidates (CTA each)
   unsigned int n_mid;    // queries with 2..kWarpMax scored candidates (warp each)
-  unsigned int pad[1];
+  unsigned int n_long;  // != 0: some survivor's pattern is longer than 32 tokens (set by fm_score_short_kernel)
 };
 static const int kElemBits = 38;
 
@@ -106,7 +106,7 @@ struct BatchDev {
   int2* tbl;         // [4*n_tok] per-query open-addressing tables: (word, distinct_idx | count<<16)
   const int4* pinfo;        // [max_tokens+1] per pattern length: (smin, smax, tables valid, row offset)
   const uint16_t* cmin_tab; // per (pattern length, passing sentence length): smallest coverage that passes
-  int4* qmask;       // [3*n_q] per query: signature masks M1..M5 (pattern positions per bit >= 1..5) + weight
+  int4* qmask;       // [2*n_q] per query: bit-sliced pattern-position counts per signature bit (B0,B1 | B2,extra)
   // search output
   long long* sl_start;  // [slice_cap+1] first flattened element of each slice (ascending)
   int4* sl_rec;         // [slice_cap] (q, sa_begin, match_len | p << 16, size)
@@ -147,6 +147,8 @@ struct Params {  // fm_params + derived
 struct Workspace {
   int device = 0;
   cudaStream_t stream = nullptr;  // owned stream for the host-buffer API
+  cudaStream_t stream2 = nullptr;  // side stream: the CTA-per-query replay runs next to the warp-per-query one
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // capacities
   int64_t cap_q = 0, cap_tok = 0, cap_slices = 0, cap_surv = 0, cap_out = 0;
   uint32_t hsize = 0;
@@ -251,7 +253,7 @@ void launch_score(const IndexDev& ix, const BatchDev& b, const Params& p, int sm
 void launch_replay(const IndexDev& ix, const fm_record* rec, const int32_t* q_cnt, const int32_t* q_base, float* heapbuf,
                    unsigned long long* sort_key, unsigned long long* sort_key2, int32_t* sort_idx, int32_t* acc_cnt,
                    int32_t* mid_q, int32_t* heavy_q, const int32_t* q_off, int32_t n_q, const Params& p, int64_t cap,
-                   fm_match* out, int32_t* out_count, Counters* ctr, int sm_count, cudaStream_t st);
+                   fm_match* out, int32_t* out_count, Counters* ctr, int sm_count, cudaStream_t st, cudaStream_t st2, cudaEvent_t ev_fork, cudaEvent_t ev_join);
 void launch_contrast(const IndexDev& ix, fm_record* rec, const int32_t* q_base, const int32_t* sort_idx,
                      const int32_t* acc_cnt, int32_t n_q, const Params& p, int64_t cap, fm_match* out, int32_t* out_count,
                      Counters* ctr, int sm_count, cudaStream_t st);

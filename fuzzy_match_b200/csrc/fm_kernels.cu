@@ -217,22 +217,23 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
       c_hi += bit == (unsigned)(lane + 32);
     }
   }
-  // Signature masks: M_l = bits that >= l pattern positions hash to.
-  // coverage <= sum_l popc(sig & M_l) (+ weight * popc(sig & M5) for bits with more than 4 positions).
+  // Signature masks, bit-sliced: plane k holds bit k of the number of pattern positions that hash to
+  // each signature bit, so coverage <= popc(sig & B0) + 2 popc(sig & B1) + 4 popc(sig & B2); a bit with
+  // 8 or more positions (long patterns) is stored as 7 and `extra` covers the rest.
   {
-    unsigned m[10];
+    const int k_lo = min(c_lo, 7), k_hi = min(c_hi, 7);
+    unsigned m[6];
 #pragma unroll
-    for (int l = 0; l < 5; l++) {
-      m[2 * l] = __ballot_sync(FULL, c_lo > l);
-      m[2 * l + 1] = __ballot_sync(FULL, c_hi > l);
+    for (int l = 0; l < 3; l++) {
+      m[2 * l] = __ballot_sync(FULL, (k_lo >> l) & 1);
+      m[2 * l + 1] = __ballot_sync(FULL, (k_hi >> l) & 1);
     }
-    int extra = max(max(c_lo, c_hi) - 4, 0);
+    int extra = max(max(c_lo, c_hi) - 7, 0);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) extra = max(extra, __shfl_xor_sync(FULL, extra, d));
     if (lane == 0) {
-      b.qmask[3 * q + 0] = make_int4(m[0], m[1], m[2], m[3]);
-      b.qmask[3 * q + 1] = make_int4(m[4], m[5], m[6], m[7]);
-      b.qmask[3 * q + 2] = make_int4(m[8], m[9], extra, (m[4] | m[5]) != 0);
+      b.qmask[2 * q + 0] = make_int4(m[0], m[1], m[2], m[3]);
+      b.qmask[2 * q + 1] = make_int4(m[4], m[5], extra, 0);
     }
   }
 }
@@ -595,13 +596,13 @@ __global__ void __launch_bounds__(256, 8) fm_gather_kernel(IndexDev ix, BatchDev
           if (slen >= pi.x && slen <= pi.y) {
             const int need = __ldg(b.cmin_tab + pi.w + (slen - pi.x));
             if (need <= p) {
-              const int4 m0 = __ldg(b.qmask + 3 * q), m2 = __ldg(b.qmask + 3 * q + 2);
-              const int4 m1 = m2.w ? __ldg(b.qmask + 3 * q + 1) : make_int4(0, 0, 0, 0);
+              const int4 m0 = __ldg(b.qmask + 2 * q), m1 = __ldg(b.qmask + 2 * q + 1);  // planes (B0, B1), (B2, extra)
               const unsigned lo = (unsigned)wr.z, hi = (unsigned)wr.w;
-              int ub = __popc(lo & m0.x) + __popc(hi & m0.y) + __popc(lo & m0.z) + __popc(hi & m0.w);
-              if (m2.w)  // some signature bit collects 3 or more pattern positions (rare)
-                ub += __popc(lo & m1.x) + __popc(hi & m1.y) + __popc(lo & m1.z) + __popc(hi & m1.w) +
-                      m2.z * (__popc(lo & m2.x) + __popc(hi & m2.y));
+              int ub = __popc(lo & m0.x) + __popc(hi & m0.y) + 2 * (__popc(lo & m0.z) + __popc(hi & m0.w));
+              if (m1.x | m1.y) {  // some signature bit collects 4 or more pattern positions
+                ub += 4 * (__popc(lo & m1.x) + __popc(hi & m1.y));
+                if (m1.z) ub += m1.z * (__popc(lo & m1.x & m0.x & m0.z) + __popc(hi & m1.y & m0.y & m0.w));
+              }
               if (ub >= need) {
                 pass = true;
                 item = make_int4(q, wr.x, slen | (need << 16), lm);
@@ -631,8 +632,8 @@ __global__ void __launch_bounds__(256, 8) fm_gather_kernel(IndexDev ix, BatchDev
 
 // ---------------------------------------------------------------- scan (single CTA, n <= a few million)
 
-// Exclusive scan of the per-query survivor counts, chained over co-resident CTAs: CTA i scans its tile,
-// waits for the running total of CTA i-1 (a flag/value pair in `chain`), publishes its own. The grid
+// Exclusive scan of the per-query survivor counts over co-resident CTAs: CTA i reduces its tile,
+// publishes the total (a flag/value pair in `chain`) and sums the totals of CTAs 0..i-1. The grid
 // (<= 128 CTAs of 1024 threads) is always fully resident, so the spin cannot deadlock.
 static const int kScanCtas = 128;
 __global__ void __launch_bounds__(1024) fm_scan_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, int n,
@@ -649,19 +650,26 @@ __global__ void __launch_bounds__(1024) fm_scan_kernel(const int32_t* __restrict
   for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(FULL, total, d);
   if (lane == 0) warp_sum[wid] = total;
   __syncthreads();
-  if (t == 0) {
-    int tile = 0;
-    for (int w = 0; w < 32; w++) tile += warp_sum[w];
-    unsigned long long prev = 0;
-    if (blockIdx.x > 0) {  // wait for the predecessor's inclusive total of this epoch
-      volatile unsigned long long* p = chain + blockIdx.x - 1;
-      do { prev = *p; } while ((unsigned)(prev >> 32) != epoch);
+  if (wid == 0) {
+    // publish this tile's total, then add up the totals of all predecessors (each one is read as soon
+    // as its CTA has published it: no serial hand-over from CTA to CTA)
+    int tile = warp_sum[lane];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) tile += __shfl_xor_sync(FULL, tile, d);
+    if (lane == 0) *(volatile unsigned long long*)(chain + blockIdx.x) = ((unsigned long long)epoch << 32) | (unsigned)tile;
+    int carry = 0;
+    for (int j = lane; j < (int)blockIdx.x; j += 32) {
+      volatile unsigned long long* pj = chain + j;
+      unsigned long long v;
+      do { v = *pj; } while ((unsigned)(v >> 32) != epoch);
+      carry += (int)(unsigned)v;
     }
-    const int carry = (int)(unsigned)prev;
-    carry_s = carry;
-    __threadfence();
-    *(volatile unsigned long long*)(chain + blockIdx.x) = ((unsigned long long)epoch << 32) | (unsigned)(carry + tile);
-    if (blockIdx.x == gridDim.x - 1) out[n] = carry + tile;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) carry += __shfl_xor_sync(FULL, carry, d);
+    if (lane == 0) {
+      carry_s = carry;
+      if (blockIdx.x == gridDim.x - 1) out[n] = carry + tile;
+    }
   }
   __syncthreads();
   // pass 2: exclusive scan of the tile, 4096 items per round
@@ -878,7 +886,10 @@ __global__ void __launch_bounds__(128) fm_score_short_kernel(IndexDev ix, BatchD
   const int slen = b.surv_len[w];
   const QMeta qm = b.qmeta[sr.q];
   const int p = qm.x;
-  if (p > 32) return;
+  if (p > 32) {  // left to the wavefront kernel, which only scans the survivors when this flag is set
+    b.ctr->n_long = 1;
+    return;
+  }
   const float wdiff = __fdiv_rn(100.f, normalizer(p, slen, pr));
   const float idf_weight = __fdiv_rn(__fmul_rn(wdiff, pr.idf_penalty), pr.idf_penalty != 0.f ? ix.idf_max : 0.01f);
   float C, K;
@@ -907,6 +918,7 @@ __global__ void __launch_bounds__(256) fm_score_kernel(IndexDev ix, BatchDev b, 
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const long long n = min((long long)b.ctr->n_surv, (long long)b.surv_cap);
   if (b.ctr->overflow) return;
+  if (min_p > 32 && b.ctr->n_long == 0) return;  // nothing for the wavefront: every pattern fits the register kernel
   for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += n_warps) {
     const SurvRec sr = b.surv[w];
     const int slen = b.surv_len[w];
@@ -1503,13 +1515,10 @@ void launch_score(const IndexDev& ix, const BatchDev& b, const Params& p, int sm
 void launch_replay(const IndexDev& ix, const fm_record* rec, const int32_t* q_cnt, const int32_t* q_base, float* heapbuf,
                    unsigned long long* sort_key, unsigned long long* sort_key2, int32_t* sort_idx, int32_t* acc_cnt,
                    int32_t* mid_q, int32_t* heavy_q, const int32_t* q_off, int32_t n_q, const Params& p, int64_t cap,
-                   fm_match* out, int32_t* out_count, Counters* ctr, int sm_count, cudaStream_t st) {
+                   fm_match* out, int32_t* out_count, Counters* ctr, int sm_count, cudaStream_t st, cudaStream_t st2,
+                   cudaEvent_t ev_fork, cudaEvent_t ev_join) {
   fm_replay_small_kernel<<<(n_q + 255) / 256, 256, 0, st>>>(const_cast<fm_record*>(rec), q_cnt, q_base, sort_idx, acc_cnt, mid_q,
                                                             heavy_q, q_off, n_q, p, (long long)cap, out, out_count, ctr, kWarpMax);
-  int grid = (n_q + 7) / 8;
-  if (grid > sm_count * 8) grid = sm_count * 8;
-  fm_replay_kernel<<<grid, 256, 0, st>>>(const_cast<fm_record*>(rec), q_cnt, q_base, heapbuf, sort_key, sort_idx, acc_cnt, mid_q,
-                                         q_off, p, (long long)cap, out, out_count, ctr);
   const size_t smem = (size_t)kHeavySmem * sizeof(unsigned long long);
   // FM_HEAVY_SMEM=<n> lowers the shared-memory sort limit so that tests reach the radix-sort path
   static const int smem_cap = getenv("FM_HEAVY_SMEM") ? std::max(64, std::min(kHeavySmem, atoi(getenv("FM_HEAVY_SMEM")))) : kHeavySmem;
@@ -1518,8 +1527,21 @@ void launch_replay(const IndexDev& ix, const fm_record* rec, const int32_t* q_cn
     cudaFuncSetAttribute(fm_replay_heavy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done = true;
   }
-  fm_replay_heavy_kernel<<<sm_count * 2, 256, smem, st>>>(const_cast<fm_record*>(rec), q_cnt, q_base, heapbuf, sort_key, sort_key2,
+  // The two remaining kernels work on disjoint queries (the lists the small kernel wrote). The heavy
+  // one is a few long sequential replays, so it runs on a side stream next to the warp-per-query one.
+  cudaStream_t sh = st2 ? st2 : st;
+  if (st2) {
+    cudaEventRecord(ev_fork, st);
+    cudaStreamWaitEvent(st2, ev_fork, 0);
+  }
+  fm_replay_heavy_kernel<<<sm_count * 2, 256, smem, sh>>>(const_cast<fm_record*>(rec), q_cnt, q_base, heapbuf, sort_key, sort_key2,
                                                           sort_idx, acc_cnt, heavy_q, q_off, p, (long long)cap, out, out_count, ctr, smem_cap);
+  if (st2) cudaEventRecord(ev_join, st2);
+  int grid = (n_q + 7) / 8;
+  if (grid > sm_count * 8) grid = sm_count * 8;
+  fm_replay_kernel<<<grid, 256, 0, st>>>(const_cast<fm_record*>(rec), q_cnt, q_base, heapbuf, sort_key, sort_idx, acc_cnt, mid_q,
+                                         q_off, p, (long long)cap, out, out_count, ctr);
+  if (st2) cudaStreamWaitEvent(st, ev_join, 0);
 }
 void launch_contrast(const IndexDev& ix, fm_record* rec, const int32_t* q_base, const int32_t* sort_idx,
                      const int32_t* acc_cnt, int32_t n_q, const Params& p, int64_t cap, fm_match* out, int32_t* out_count, Counters* ctr, int sm_count,
