@@ -96,10 +96,10 @@ static int ensure_spans(Workspace* w, int64_t n) {
   return FM_OK;
 }
 static int ensure_bounds(Index* ix, Workspace* w) {
-  if (w->pinfo) return FM_OK;
+  if (w->cmin_tab) return FM_OK;
   int rc;
   const int64_t t = ix->max_tokens;
-  if ((rc = dev_realloc(&w->pinfo, t + 2)) || (rc = dev_realloc(&w->cmin_tab, 2 * t * (t + 1) + 16))) return rc;
+  if ((rc = dev_realloc(&w->cmin_tab, (t + 1) << 10))) return rc;
   w->bounds_valid = false;
   return FM_OK;
 }
@@ -127,7 +127,7 @@ static int ensure_out(Workspace* w, int64_t n_q, int64_t cap) {
 }
 
 static void free_workspace(Workspace* w) {
-  cudaFree(w->d_q_tok); cudaFree(w->d_q_off); cudaFree(w->d_q_real); cudaFree(w->d_q_gap); cudaFree(w->d_itok_dist); cudaFree(w->pat); cudaFree(w->chain_q); cudaFree(w->qmeta); cudaFree(w->tbl); cudaFree(w->pinfo); cudaFree(w->cmin_tab); cudaFree(w->span_slice); cudaFree(w->qmask);
+  cudaFree(w->d_q_tok); cudaFree(w->d_q_off); cudaFree(w->d_q_real); cudaFree(w->d_q_gap); cudaFree(w->d_itok_dist); cudaFree(w->pat); cudaFree(w->chain_q); cudaFree(w->qmeta); cudaFree(w->tbl); cudaFree(w->cmin_tab); cudaFree(w->span_slice); cudaFree(w->qmask);
   cudaFree(w->sl_start); cudaFree(w->sl_rec); cudaFree(w->hkey); cudaFree(w->hlm); cudaFree(w->surv); cudaFree(w->surv_len);
   cudaFree(w->q_cnt); cudaFree(w->q_base); cudaFree(w->acc_cnt); cudaFree(w->rec); cudaFree(w->heapbuf); cudaFree(w->ctr); cudaFree(w->scan_chain);
   cudaFree(w->d_out); cudaFree(w->d_out_count); cudaFree(w->mrec); cudaFree(w->m_cnt); cudaFree(w->m_base); cudaFree(w->m_acc); cudaFree(w->m_heap); cudaFree(w->heavy_q); cudaFree(w->m_heavy); cudaFree(w->mid_q); cudaFree(w->m_mid); cudaFree(w->sort_key); cudaFree(w->sort_key2); cudaFree(w->m_key2); cudaFree(w->sort_idx); cudaFree(w->m_key); cudaFree(w->m_idx);
@@ -162,7 +162,7 @@ static int check_params(const fm_params* p, Params* out) {
 static BatchDev make_batch(Workspace* w, const int32_t* d_q_tok, const int32_t* d_q_off, int64_t n_q, int64_t n_tok) {
   BatchDev b{};
   b.q_tok_in = d_q_tok; b.q_off = d_q_off; b.n_q = (int32_t)n_q; b.n_tok = (int32_t)n_tok;
-  b.pat = w->pat; b.chain_q = w->chain_q; b.qmeta = w->qmeta; b.tbl = w->tbl; b.pinfo = w->pinfo; b.cmin_tab = w->cmin_tab; b.qmask = w->qmask;
+  b.pat = w->pat; b.chain_q = w->chain_q; b.qmeta = w->qmeta; b.tbl = w->tbl; b.cmin_tab = w->cmin_tab; b.qmask = w->qmask;
   b.span_slice = w->span_slice; b.span_cap = w->cap_spans;
   b.sl_start = w->sl_start; b.sl_rec = w->sl_rec; b.slice_cap = w->cap_slices;
   b.hkey = w->hkey; b.hlm = w->hlm; b.hmask = w->hsize - 1;

@@ -104,8 +104,7 @@ struct BatchDev {
   int32_t* chain_q;  // [n_tok] query of each chain (= pattern position)
   QMeta* qmeta;      // [n_q]
   int2* tbl;         // [4*n_tok] per-query open-addressing tables: (word, distinct_idx | count<<16)
-  const int4* pinfo;        // [max_tokens+1] per pattern length: (smin, smax, tables valid, row offset)
-  const uint16_t* cmin_tab; // per (pattern length, passing sentence length): smallest coverage that passes
+  const uint16_t* cmin_tab; // [(max_tokens+1) << 10] per (pattern length << 10 | sentence length): smallest coverage that passes
   int4* qmask;       // [2*n_q] per query: bit-sliced pattern-position counts per signature bit (B0,B1 | B2,extra)
   // search output
   long long* sl_start;  // [slice_cap+1] first flattened element of each slice (ascending)
@@ -161,7 +160,6 @@ struct Workspace {
   int32_t *pat = nullptr, *chain_q = nullptr;
   QMeta* qmeta = nullptr;
   int2* tbl = nullptr;
-  int4* pinfo = nullptr;
   uint16_t* cmin_tab = nullptr;
   int32_t* span_slice = nullptr;
   int64_t cap_spans = 0;

@@ -91,39 +91,27 @@ __device__ __forceinline__ float score_of(float cost) {
 // p; for each of them cmin = the smallest coverage the coverage bound (ngram_matches.cc:42-59) lets
 // through. Both depend only on (p, s, fuzzy, costs), so they are evaluated with the exact float/double
 // expressions once per pattern length when the parameters change, instead of once per suffix-array
-// element. pinfo[p] = (smin, smax, tables valid, offset of p's row in cmin_tab).
-__global__ void __launch_bounds__(256) fm_bounds_kernel(int max_tokens, Params pr, int4* pinfo, uint16_t* cmin_tab) {
+// element. cmin_tab[(p << 10) | s] = smallest passing coverage, kNeedReject when (p, s) can never pass,
+// kNeedNoTable when the bounds must be evaluated per element (negative costs: not monotone).
+static const int kNeedReject = 0xffff, kNeedNoTable = 0xfffe;
+__global__ void __launch_bounds__(256) fm_bounds_kernel(int max_tokens, Params pr, uint16_t* cmin_tab) {
   const int lane = threadIdx.x & 31;
   const int p = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) + 1;
   if (p > max_tokens) return;
-  int smin = 0x7fffffff, smax = 0, n_ok = 0;
-  for (int base = 1; base <= max_tokens; base += 32) {
-    const int sl = base + lane;
-    const bool ok = sl <= max_tokens && !reject_length(p, sl, pr);
-    const unsigned bal = __ballot_sync(FULL, ok);
-    if (bal) {
-      smin = min(smin, base + __ffs(bal) - 1);
-      smax = max(smax, base + 31 - __clz(bal));
-      n_ok += __popc(bal);
-    }
-  }
-  const bool fast = n_ok > 0 && n_ok == smax - smin + 1 && n_ok <= 4 * p && pr.ins >= 0.f && pr.del >= 0.f && pr.rep >= 0.f;
-  const int row = 2 * p * (p - 1);  // sum_{k<p} 4k
-  if (fast) {
-    for (int sl = smin + lane; sl <= smax; sl += 32) {
-      int need = p + 1;
-      if (!reject_cover(p, sl, p, pr)) {  // reject_cover is monotone in the coverage for costs >= 0
-        int lo = 0, hi = p;
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (!reject_cover(p, sl, mid, pr)) hi = mid; else lo = mid + 1;
-        }
-        need = lo;
+  const bool fast = pr.ins >= 0.f && pr.del >= 0.f && pr.rep >= 0.f;  // reject_cover is monotone in the coverage for costs >= 0
+  uint16_t* row = cmin_tab + (p << 10);
+  for (int sl = lane; sl < 1024; sl += 32) {
+    int need = fast ? kNeedReject : kNeedNoTable;
+    if (fast && sl >= 1 && sl <= max_tokens && !reject_length(p, sl, pr) && !reject_cover(p, sl, p, pr)) {
+      int lo = 0, hi = p;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (!reject_cover(p, sl, mid, pr)) hi = mid; else lo = mid + 1;
       }
-      cmin_tab[row + sl - smin] = (uint16_t)need;
+      need = lo;
     }
+    row[sl] = (uint16_t)need;
   }
-  if (lane == 0) pinfo[p] = make_int4(fast ? smin : 0, fast ? smax : 0, fast ? 1 : 0, row);
 }
 
 // ---------------------------------------------------------------- prepare
@@ -591,25 +579,20 @@ __global__ void __launch_bounds__(256, 8) fm_gather_kernel(IndexDev ix, BatchDev
         const int4 wr = ldg_nc_v4(ix.sa_walk + (sr.y + (el - my_start)));  // (start, slen, sig lo, sig hi)
         const int slen = wr.y;
         const int p = sr.z >> 16, lm = sr.z & 0xffff;
-        const int4 pi = __ldg(b.pinfo + p);  // (smin, smax, tables valid, row)
-        if (pi.z) {
-          if (slen >= pi.x && slen <= pi.y) {
-            const int need = __ldg(b.cmin_tab + pi.w + (slen - pi.x));
-            if (need <= p) {
-              const int4 m0 = __ldg(b.qmask + 2 * q), m1 = __ldg(b.qmask + 2 * q + 1);  // planes (B0, B1), (B2, extra)
-              const unsigned lo = (unsigned)wr.z, hi = (unsigned)wr.w;
-              int ub = __popc(lo & m0.x) + __popc(hi & m0.y) + 2 * (__popc(lo & m0.z) + __popc(hi & m0.w));
-              if (m1.x | m1.y) {  // some signature bit collects 4 or more pattern positions
-                ub += 4 * (__popc(lo & m1.x) + __popc(hi & m1.y));
-                if (m1.z) ub += m1.z * (__popc(lo & m1.x & m0.x & m0.z) + __popc(hi & m1.y & m0.y & m0.w));
-              }
-              if (ub >= need) {
-                pass = true;
-                item = make_int4(q, wr.x, slen | (need << 16), lm);
-              }
-            }
+        const int need = __ldg(b.cmin_tab + ((p << 10) | slen));  // one lookup: length window + smallest passing coverage
+        if (need <= p) {
+          const int4 m0 = __ldg(b.qmask + 2 * q), m1 = __ldg(b.qmask + 2 * q + 1);  // planes (B0, B1), (B2, extra)
+          const unsigned lo = (unsigned)wr.z, hi = (unsigned)wr.w;
+          int ub = __popc(lo & m0.x) + __popc(hi & m0.y) + 2 * (__popc(lo & m0.z) + __popc(hi & m0.w));
+          if (m1.x | m1.y) {  // some signature bit collects 4 or more pattern positions
+            ub += 4 * (__popc(lo & m1.x) + __popc(hi & m1.y));
+            if (m1.z) ub += m1.z * (__popc(lo & m1.x & m0.x & m0.z) + __popc(hi & m1.y & m0.y & m0.w));
           }
-        } else if (!reject_length(p, slen, pr)) {
+          if (ub >= need) {
+            pass = true;
+            item = make_int4(q, wr.x, slen | (need << 16), lm);
+          }
+        } else if (need == kNeedNoTable && !reject_length(p, slen, pr)) {
           pass = true;
           item = make_int4(q, wr.x, slen | (0xffff << 16), lm);
         }
@@ -1467,8 +1450,7 @@ __global__ void fm_merge_copy_kernel(ShardPtrs sp, int n_shards, const int32_t* 
 static int dp_stride(const IndexDev& ix) { return ((ix.max_tokens + 31) / 32) * 32 + 32; }
 
 void launch_bounds(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st) {
-  fm_bounds_kernel<<<(ix.max_tokens + 7) / 8, 256, 0, st>>>(ix.max_tokens, p, const_cast<int4*>(b.pinfo),
-                                                            const_cast<uint16_t*>(b.cmin_tab));
+  fm_bounds_kernel<<<(ix.max_tokens + 7) / 8, 256, 0, st>>>(ix.max_tokens, p, const_cast<uint16_t*>(b.cmin_tab));
 }
 void launch_prepare(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st) {
   const int warps_per_block = 8;
