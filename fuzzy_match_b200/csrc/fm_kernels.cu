@@ -1118,7 +1118,7 @@ __global__ void __launch_bounds__(256) fm_replay_small_kernel(fm_record* rec, co
 // longest match desc, s_id asc) by register rank sort (<= 32) or a shared-memory bitonic sort of packed
 // keys, the replay, result order, top-N output (:670-679). Larger queries are queued for
 // fm_replay_heavy_kernel.
-static const int kWarpMax = 256;
+static const int kWarpMax = 128;
 __global__ void __launch_bounds__(256) fm_replay_kernel(fm_record* rec, const int32_t* __restrict__ q_cnt,
                                                         const int32_t* __restrict__ q_base, float* heapbuf,
                                                         unsigned long long* sort_key, int32_t* sort_idx, int32_t* acc_cnt,
@@ -1499,8 +1499,10 @@ void launch_replay(const IndexDev& ix, const fm_record* rec, const int32_t* q_cn
                    int32_t* mid_q, int32_t* heavy_q, const int32_t* q_off, int32_t n_q, const Params& p, int64_t cap,
                    fm_match* out, int32_t* out_count, Counters* ctr, int sm_count, cudaStream_t st, cudaStream_t st2,
                    cudaEvent_t ev_fork, cudaEvent_t ev_join) {
+  // FM_WARP_MAX=<n> (32..kWarpMax) moves the warp / CTA boundary (tuning and tests)
+  static const int warp_max = getenv("FM_WARP_MAX") ? std::max(32, std::min(kWarpMax, atoi(getenv("FM_WARP_MAX")))) : kWarpMax;
   fm_replay_small_kernel<<<(n_q + 255) / 256, 256, 0, st>>>(const_cast<fm_record*>(rec), q_cnt, q_base, sort_idx, acc_cnt, mid_q,
-                                                            heavy_q, q_off, n_q, p, (long long)cap, out, out_count, ctr, kWarpMax);
+                                                            heavy_q, q_off, n_q, p, (long long)cap, out, out_count, ctr, warp_max);
   const size_t smem = (size_t)kHeavySmem * sizeof(unsigned long long);
   // FM_HEAVY_SMEM=<n> lowers the shared-memory sort limit so that tests reach the radix-sort path
   static const int smem_cap = getenv("FM_HEAVY_SMEM") ? std::max(64, std::min(kHeavySmem, atoi(getenv("FM_HEAVY_SMEM")))) : kHeavySmem;
