@@ -126,9 +126,10 @@ int fm_match_batch_real(fm_index* index, const int32_t* q_tokens, const int32_t*
 int fm_match_batch(fm_index* index, const int32_t* q_tokens, const int64_t* q_off, int64_t n_q,
                    const fm_params* params, int64_t cap, fm_match* out, int32_t* out_count);
 
-/* Same with device-resident buffers; q_off is int32 here ([n_q+1], device). Runs asynchronously on
- * `stream` (a cudaStream_t) unless the workspace has to grow, and leaves results in d_out/d_out_count.
- * n_query_tokens = q_off[n_q] (known to the caller). */
+/* Same with device-resident buffers; q_off is int32 here ([n_q+1], device). The batch is enqueued on
+ * `stream` (a cudaStream_t) and the call returns once that stream has finished it (the worklist
+ * overflow counters are read back; a batch that outgrew the workspace is rerun after regrowing it):
+ * on return the results are in d_out/d_out_count. n_query_tokens = q_off[n_q] (known to the caller). */
 int fm_match_batch_device(fm_index* index, const int32_t* d_q_tokens, const int32_t* d_q_off, int64_t n_q,
                           int64_t n_query_tokens, const fm_params* params, int64_t cap, fm_match* d_out,
                           int32_t* d_out_count, void* stream);
