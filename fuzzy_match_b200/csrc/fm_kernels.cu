@@ -499,24 +499,66 @@ __device__ __forceinline__ void add_survivor(const BatchDev& b, int q, int start
   }
 }
 
-// Second stage of the gather: exact coverage of a candidate that survived the signature bound.
-// item = (q, sentence start, sentence length | need << 16, match length).
-__device__ __forceinline__ void verify_candidate(const IndexDev& ix, const BatchDev& b, const Params& pr, int4 item) {
+// Second stage of the gather: exact coverage of candidates that survived the signature bound.
+// item = (q, sentence start, sentence length | need << 16, match length); lanes >= n hold nothing.
+// Patterns of up to 32 words: one candidate per lane, the set of distinct words seen is one register.
+// Longer patterns (their 64-bit signatures saturate, so many candidates get here): one candidate at a
+// time, the 32 lanes probe the sentence's tokens in parallel and mark the distinct words in a
+// shared-memory bit set (PatternCoverage::count_covered_words, src/pattern_coverage.cc:15-28).
+__device__ __forceinline__ void verify_candidates(const IndexDev& ix, const BatchDev& b, const Params& pr, int4 item, int n,
+                                                  unsigned* seen, int lane) {
+  const bool have = lane < n;
   const int q = item.x, start = item.y, slen = item.z & 0xffff, need = (int)((unsigned)item.z >> 16);
-  const QMeta qm = __ldg(b.qmeta + q);
-  const int p = qm.x;
-  const int2* tbl = b.tbl + 4ll * qm.z;
-  const int tmask = next_pow2(2 * p) - 1;
-  if (need == 0xffff) {  // no bound table for this query: evaluate the bound itself
-    const int cover = p <= 32 ? cover_sentence<1>(ix.tok + start, slen, tbl, tmask, p + 1)
-                              : cover_sentence<32>(ix.tok + start, slen, tbl, tmask, p + 1);
-    if (reject_cover(p, slen, cover, pr)) return;
-  } else {
-    const int cover = p <= 32 ? cover_sentence<1>(ix.tok + start, slen, tbl, tmask, need)
-                              : cover_sentence<32>(ix.tok + start, slen, tbl, tmask, need);
-    if (cover < need) return;
+  int p = 0, off = 0;
+  if (have) {
+    const QMeta qm = __ldg(b.qmeta + q);
+    p = qm.x;
+    off = qm.z;
   }
-  add_survivor(b, q, start, slen, item.w);
+  if (have && p <= 32) {
+    const int2* tbl = b.tbl + 4ll * off;
+    const int tmask = next_pow2(2 * p) - 1;
+    bool ok;
+    if (need == 0xffff) {  // no bound table for this query: evaluate the bound itself
+      ok = !reject_cover(p, slen, cover_sentence<1>(ix.tok + start, slen, tbl, tmask, p + 1), pr);
+    } else {
+      ok = cover_sentence<1>(ix.tok + start, slen, tbl, tmask, need) >= need;
+    }
+    if (ok) add_survivor(b, q, start, slen, item.w);
+  }
+  unsigned todo = __ballot_sync(FULL, have && p > 32);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int cq = __shfl_sync(FULL, q, src), cstart = __shfl_sync(FULL, start, src), cz = __shfl_sync(FULL, item.z, src);
+    const int clm = __shfl_sync(FULL, item.w, src), cp = __shfl_sync(FULL, p, src), coff = __shfl_sync(FULL, off, src);
+    const int cslen = cz & 0xffff, cneed = (int)((unsigned)cz >> 16);
+    const int2* tbl = b.tbl + 4ll * coff;
+    const int tmask = next_pow2(2 * cp) - 1;
+    seen[lane] = 0;
+    __syncwarp();
+    int cover = 0;
+    for (int k = lane; k < cslen; k += 32) {
+      const int w = __ldg(ix.tok + cstart + k);
+      int h = hash32((uint32_t)w) & tmask;
+      for (;;) {
+        const int2 e = __ldg(tbl + h);
+        if (e.x == w) {
+          const int d = e.y & 0xffff;
+          const unsigned bit = 1u << (d & 31);
+          if (!(atomicOr(&seen[d >> 5], bit) & bit)) cover += e.y >> 16;
+          break;
+        }
+        if (e.x == -1) break;
+        h = (h + 1) & tmask;
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cover += __shfl_xor_sync(FULL, cover, d);
+    __syncwarp();
+    const bool ok = cneed == 0xffff ? !reject_cover(cp, cslen, cover, pr) : cover >= cneed;
+    if (ok && lane == 0) add_survivor(b, cq, cstart, cslen, clm);
+  }
 }
 
 // Persistent kernel over the flattened elements of all slices: register_suffix_range_match's walk
@@ -530,6 +572,8 @@ __device__ __forceinline__ void verify_candidate(const IndexDev& ix, const Batch
 static const int kQueue = 64;
 __global__ void __launch_bounds__(256, 8) fm_gather_kernel(IndexDev ix, BatchDev b, Params pr) {
   __shared__ int4 s_queue[8][kQueue];
+  __shared__ unsigned s_seen[8][32];
+  unsigned* seen = s_seen[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   int4* queue = s_queue[threadIdx.x >> 5];
   int queued = 0;
@@ -604,13 +648,13 @@ __global__ void __launch_bounds__(256, 8) fm_gather_kernel(IndexDev ix, BatchDev
         __syncwarp();
         if (queued >= 32) {
           queued -= 32;
-          verify_candidate(ix, b, pr, queue[queued + lane]);
+          verify_candidates(ix, b, pr, queue[queued + lane], 32, seen, lane);
           __syncwarp();
         }
       }
     }
   }
-  if (lane < queued) verify_candidate(ix, b, pr, queue[lane]);
+  verify_candidates(ix, b, pr, queue[lane], queued, seen, lane);
 }
 
 // ---------------------------------------------------------------- scan (single CTA, n <= a few million)
