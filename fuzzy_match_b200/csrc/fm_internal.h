@@ -178,7 +178,7 @@ struct Workspace {
   unsigned long long *sort_key = nullptr, *m_key = nullptr, *sort_key2 = nullptr, *m_key2 = nullptr;
   int32_t *sort_idx = nullptr, *m_idx = nullptr;
   Counters* ctr = nullptr;
-  unsigned long long* scan_chain = nullptr;  // chained-scan mailboxes
+  unsigned long long* scan_chain = nullptr;  // scan mailboxes: (epoch << 32 | tile total) per CTA
   unsigned int scan_epoch = 0;
   fm_match* d_out = nullptr;
   int32_t* d_out_count = nullptr;

@@ -1,17 +1,17 @@
 // fm_kernels.cu -- hand-written sm_100a kernels of the fuzzy-match hot path.
 //
-// One batch of patterns streams through eight launches (no host round trip in between):
+// One batch of patterns streams through nine launches (no host round trip in between):
 //   prepare      per query: clamp ml, sanitise ids, build the pattern's word table and signature masks
 //   search       per (query, start position): bigram / trigram directory probes, then narrow the
 //                suffix-array range token by token; emit range slices
 //   gather       per suffix-array element of every slice: length window + signature bound from one
 //                128-bit load, exact coverage for the few that pass, dedup (query, sentence) with max
 //                match length                                          <- the "suffix-range gather"
-//   scan         exclusive scan of survivors per query (chained CTAs)
+//   scan         exclusive scan of survivors per query (co-resident CTAs, epoch-tagged tile totals)
 //   score        per surviving (query, sentence): edit-distance DP -- registers for p <= 32 (thread per
 //                pair), warp-wide wavefront in shared memory above     <- the "DP kernel"
 //   replay       per query: the reference's sequential bound heap / top-N over the scored candidates
-//                (warp per query, CTA per query for very long candidate lists)
+//                (thread per query for 0-1 candidates, warp per query, CTA per query for long lists)
 //   (+ bounds when the parameters change: per pattern length tables of the two rejection bounds;
 //    + contrast: per query warp, contrastive rerank)
 //
@@ -287,7 +287,7 @@ __device__ __forceinline__ void flush_slices(const BatchDev& b, SliceBuf& sb, in
 }
 
 // One thread per (query, start position) chain: the n-gram walk of src/fuzzy_match.cc:484-551 with
-// SuffixArray::equal_range (src/suffix_array.cc:105-212) restated as lower/upper bound on the ONE new
+// SuffixArray::equal_range (src/suffix_array.cc:105-212) restated as the equal range of the ONE new
 // token at depth k inside the previous range (every suffix there already shares k tokens).
 __global__ void __launch_bounds__(256, 8) fm_search_kernel(IndexDev ix, BatchDev b) {
   __shared__ SliceBuf sb;
