@@ -52,13 +52,31 @@ def parse():
 
 
 def measured_peak():
+    """HBM peak for the roofline: the driver-written MEASURED_PEAKS.json when present (the sustained
+    figure, since the kernel is timed inside a step), else the profiling recipe's fallback."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
         with open(path) as f:
             d = json.load(f)
-        for k in ("hbm_gbs", "hbm_gbps", "hbm_copy_gbs"):
-            if k in d:
-                return float(d[k]), "measured (MEASURED_PEAKS.json %s)" % k
+        found = []
+
+        def walk(x, trail):
+            if isinstance(x, dict):
+                for k, v in x.items():
+                    walk(v, trail + [str(k)])
+            elif isinstance(x, (int, float)) and not isinstance(x, bool):
+                name = ".".join(trail).lower()
+                if any(t in name for t in ("hbm", "dram", "copy", "mem_bw", "membw")) and not any(t in name for t in ("tflop", "tf_s", "bf16", "fp8")):
+                    found.append((name, float(x)))
+
+        walk(d, [])
+        if found:
+            found.sort(key=lambda kv: (0 if "sustain" in kv[0] else 1 if "burst" not in kv[0] else 2))
+            name, v = found[0]
+            if v < 100:  # given in TB/s
+                v *= 1000.0
+            if 1000.0 < v < 20000.0:
+                return v, "measured (MEASURED_PEAKS.json %s)" % name
     except Exception:
         pass
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
