@@ -292,7 +292,6 @@ struct HostChunk {
   int launches = 0;
 };
 
-// Enqueue H2D + the whole pipeline + D2H of one chunk; returns without waiting.
 struct RealInputs {  // Sentence API extras of a host batch (all NULL / 0 when absent)
   const int32_t* q_real = nullptr;
   const int32_t* q_gaps = nullptr;
@@ -330,6 +329,7 @@ static double now_ms() {
 }
 static const bool g_host_timing = getenv("FM_HOST_TIMING") != nullptr;
 
+// Enqueue H2D + the whole pipeline + D2H of one chunk; returns without waiting.
 static int launch_host_chunk(Index* ix, HostChunk& c, const int32_t* q_tokens, const int64_t* q_off, const Params& pr, int64_t cap,
                              fm_match* out, int32_t* out_count, const RealInputs& ri) {
   Workspace* w = c.w;
@@ -338,6 +338,7 @@ static int launch_host_chunk(Index* ix, HostChunk& c, const int32_t* q_tokens, c
   if ((rc = ensure_queries(w, c.nq, c.ntok, true)) || (rc = ensure_out(w, c.nq, cap)) || (rc = initial_worklists(ix, w, c.nq, c.ntok)))
     return rc;
   cudaStream_t st = w->stream;
+  c.in_flight = true;  // from here on the stream may hold work of this chunk: an error return must wait for it
   if (g_host_timing) cudaEventRecord(w->ev[7], st);
   // the token copy does not need the converted offsets: start it first and narrow the offsets to int32
   // on the host while it is in flight
@@ -355,7 +356,6 @@ static int launch_host_chunk(Index* ix, HostChunk& c, const int32_t* q_tokens, c
   FM_CUDA(cudaMemcpyAsync(w->h_ctr, w->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
   FM_CUDA(cudaMemcpyAsync(out + c.q0 * cap, w->d_out, c.nq * cap * sizeof(fm_match), cudaMemcpyDeviceToHost, st));
   FM_CUDA(cudaMemcpyAsync(out_count + c.q0, w->d_out_count, c.nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  c.in_flight = true;
   if (g_host_timing) {
     const double t2 = now_ms();
     cudaStreamSynchronize(st);
