@@ -12,9 +12,35 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def _cuda_devices():
+    if not os.path.exists("/dev/nvidiactl"):
+        return 0
+    try:
+        import torch
+        return torch.cuda.device_count() if torch.cuda.is_available() else 0
+    except Exception:
+        return 0
+
+
+def pytest_collection_modifyitems(config, items):
+    """A plain `pytest` on a host without a GPU skips the gpu-marked tests instead of failing them
+    (the product has no CPU fallback: load_library / fm_index_create raise there)."""
+    if not any("gpu" in item.keywords for item in items):
+        return
+    if _cuda_devices() > 0:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device: GPU parity tests run on the B200 box (-m gpu)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session", autouse=True)
 def _build_checkers():
     """The CPU checkers are test infrastructure: build them once per session."""
     from oracle import binding as ob
-    ob.build()
+    try:
+        ob.build()
+    except Exception as e:  # a missing compiler must not take the whole session down
+        pytest.skip("oracle build failed: %s" % e)
     yield

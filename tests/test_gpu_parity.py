@@ -139,35 +139,6 @@ def test_errors_are_loud():
         fmb.Index(np.array([2, 3], dtype=np.int32), np.array([0, 2], dtype=np.int64), 10, max_tokens=5000)
 
 
-def test_full_size_properties():
-    """Config-2-sized TM (1M sentences): size-independent properties instead of the slow oracle --
-    every unperturbed TM sentence finds itself with score 1.0, results are deterministic across
-    batch splits, and a sample of queries agrees with the oracle run on the same TM."""
-    tm, off, V = synth.make_tm(1000000, seed=1234)
-    index = fmb.Index(tm, off, V)
-    ids = np.arange(0, 1000000, 997)[:1000]
-    qo = np.zeros(len(ids) + 1, dtype=np.int64)
-    np.cumsum(off[ids + 1] - off[ids], out=qo[1:])
-    q = np.concatenate([tm[off[i]:off[i + 1]] for i in ids])
-    out, cnt = index.match_batch(q, qo, cap=1, fuzzy=0.7, n=1, ml=3)
-    assert (cnt == 1).all() and (out["score"][:, 0] == 1.0).all()
-    # the match is an identical sentence with the smallest s_id (ties broken by s_id asc)
-    for k in range(0, 1000, 50):
-        sid = int(out["s_id"][k, 0])
-        assert sid <= ids[k] and np.array_equal(index.sentence(sid), tm[off[ids[k]]:off[ids[k] + 1]])
-    q2, qo2 = synth.make_queries(tm, off, 20000, seed=5678)
-    a, ca = index.match_batch(q2, qo2, cap=1, fuzzy=0.7, n=1, ml=3)
-    half = 10000
-    b1, c1 = index.match_batch(q2[:qo2[half]], qo2[:half + 1], cap=1, fuzzy=0.7, n=1, ml=3)
-    b2, c2 = index.match_batch(q2[qo2[half]:], qo2[half:] - qo2[half], cap=1, fuzzy=0.7, n=1, ml=3)
-    assert (np.concatenate([c1, c2]) == ca).all()
-    assert np.concatenate([b1, b2]).tobytes() == a.tobytes()
-    oracle = ob.OracleIndex(tm, off, V)
-    ro, co = oracle.match_batch(q2[:qo2[2000]], qo2[:2001], cap=1, nthreads=8, fuzzy=0.7, n=1, ml=3)
-    assert (co == ca[:2000]).all()
-    assert [as_tuples(r, True) for r in ro] == [as_tuples(a[i, :ca[i]], True) for i in range(2000)]
-
-
 def test_sharded_tm_two_shards_one_gpu():
     """The sharded path (fm_shard_score_device per shard + fm_merge_replay_device over the union)
     must equal the unsharded oracle bit for bit: two sentence-id shards on one GPU, global IDF."""

@@ -5,7 +5,7 @@ import pytest
 
 from fuzzy_match_b200 import synth
 from oracle import binding as ob
-from tests.util import as_tuples, csr, fix_params, load_golden
+from tests.util import REALTEXT_PARAM_SETS, as_tuples, csr, fix_params, load_golden, load_realtext
 
 CASES = load_golden()
 
@@ -144,3 +144,13 @@ def test_oracle_matches_live_reference_randomised():
         rr, cr = R.match_batch_real(q, qreal, np.zeros(len(q) + len(qo) - 1, dtype=np.int32), qo, cap=4096, **params)
         assert (oc == cr).all(), (trial, params)
         assert all(as_tuples(a) == as_tuples(b) for a, b in zip(ro, rr)), (trial, params)
+
+
+def test_oracle_matches_reference_on_real_text():
+    """Realistic text (the reference's test/data/tm2.en.gz as word ids + its test-tm2.en queries,
+    tests/golden/realtext.npz): the restatement against what the unmodified reference returned."""
+    tm, off, V, q, qo, expected = load_realtext()
+    O = ob.OracleIndex(tm, off, V)
+    for params, want in zip(REALTEXT_PARAM_SETS, expected):
+        res, cnt = O.match_batch(q, qo, cap=256, nthreads=8, **params)
+        assert [as_tuples(r) for r in res] == want, params

@@ -41,3 +41,29 @@ def fix_params(p):
     if "costs" in p:
         p["costs"] = tuple(p["costs"])
     return p
+
+
+# match(Tokens) parameter sets run through the live reference (it has no no_perfect argument)
+REALTEXT_PARAM_SETS = [
+    dict(fuzzy=0.8, n=5, ml=3, mr=0.3),                       # CLI defaults
+    dict(fuzzy=0.5, n=2, ml=3, mr=0.3),                       # the reference's own tm2 test (test/test.cc:217-221)
+    dict(fuzzy=0.7, n=1, ml=3),                               # BASELINE config 2 parameters
+    dict(fuzzy=0.5, n=1, ml=3),                               # config 3
+    dict(fuzzy=0.7, n=10, ml=3, idf=1.0, contrast=0.5),       # config 5
+    dict(fuzzy=0.4, n=4, ml=2, idf=0.7, costs=(1, 0, 1), contrast=0.5, reduce=1, buffer=8),
+    dict(fuzzy=0.4, n=4, ml=2, costs=(0.5, 1.5, 1.2)),
+    dict(fuzzy=0.3, n=0, ml=2),
+]
+
+
+def load_realtext():
+    """tests/golden/realtext.npz (made by tests/golden/make_realtext.py from the live reference)."""
+    d = np.load(os.path.join(os.path.dirname(GOLDEN), "realtext.npz"))
+    expected = []
+    for k in range(int(d["n_param_sets"])):
+        cnt = d["cnt_%d" % k]
+        off = np.concatenate([[0], np.cumsum(cnt)])
+        rows = list(zip(d["s_id_%d" % k].tolist(), d["score_%d" % k].tolist(), d["penalty_%d" % k].tolist(),
+                        d["lm_%d" % k].tolist(), d["len_%d" % k].tolist()))
+        expected.append([rows[off[i]:off[i + 1]] for i in range(len(cnt))])
+    return d["tm_tok"], d["tm_off"], int(d["vocab_size"]), d["q_tok"], d["q_off"], expected
