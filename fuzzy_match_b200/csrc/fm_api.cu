@@ -66,7 +66,7 @@ static int ensure_queries(Workspace* w, int64_t n_q, int64_t n_tok, bool staging
   if (n_tok > w->cap_tok) {
     const int64_t c = round_up(n_tok + n_tok / 4 + 4096, 4096);
     if ((rc = dev_realloc(&w->pat, c)) || (rc = dev_realloc(&w->chain_q, c)) || (rc = dev_realloc(&w->tbl, 4 * c)) ||
-        (rc = dev_realloc(&w->d_q_tok, c)))
+        (rc = dev_realloc(&w->d_q_tok, c)) || (rc = dev_realloc(&w->peq64, c)))
       return rc;
     w->cap_tok = c;
   }
@@ -77,6 +77,14 @@ static int ensure_queries(Workspace* w, int64_t n_q, int64_t n_tok, bool staging
     FM_CUDA(cudaMallocHost((void**)&w->h_q_off32, c * sizeof(int32_t)));
     w->cap_hq = c;
   }
+  return FM_OK;
+}
+// per-query planes over the wide signature bits: only for an index that has wide signatures
+static int ensure_wide(Index* ix, Workspace* w) {
+  if (ix->dev.n_wide == 0 || w->cap_wq >= w->cap_q) return FM_OK;
+  int rc;
+  if ((rc = dev_realloc(&w->wq, (size_t)w->cap_q * 3 * kWideWords))) return rc;
+  w->cap_wq = w->cap_q;
   return FM_OK;
 }
 static int ensure_slices(Workspace* w, int64_t n) {
@@ -127,7 +135,7 @@ static int ensure_out(Workspace* w, int64_t n_q, int64_t cap) {
 }
 
 static void free_workspace(Workspace* w) {
-  cudaFree(w->d_q_tok); cudaFree(w->d_q_off); cudaFree(w->d_q_real); cudaFree(w->d_q_gap); cudaFree(w->d_itok_dist); cudaFree(w->pat); cudaFree(w->chain_q); cudaFree(w->qmeta); cudaFree(w->tbl); cudaFree(w->cmin_tab); cudaFree(w->span_slice); cudaFree(w->qmask);
+  cudaFree(w->d_q_tok); cudaFree(w->d_q_off); cudaFree(w->d_q_real); cudaFree(w->d_q_gap); cudaFree(w->d_itok_dist); cudaFree(w->pat); cudaFree(w->chain_q); cudaFree(w->qmeta); cudaFree(w->tbl); cudaFree(w->cmin_tab); cudaFree(w->span_slice); cudaFree(w->qmask); cudaFree(w->wq); cudaFree(w->peq64);
   cudaFree(w->sl_start); cudaFree(w->sl_rec); cudaFree(w->hkey); cudaFree(w->hlm); cudaFree(w->surv); cudaFree(w->surv_len);
   cudaFree(w->q_cnt); cudaFree(w->q_base); cudaFree(w->acc_cnt); cudaFree(w->rec); cudaFree(w->heapbuf); cudaFree(w->ctr); cudaFree(w->scan_chain);
   cudaFree(w->d_out); cudaFree(w->d_out_count); cudaFree(w->mrec); cudaFree(w->m_cnt); cudaFree(w->m_base); cudaFree(w->m_acc); cudaFree(w->m_heap); cudaFree(w->heavy_q); cudaFree(w->m_heavy); cudaFree(w->mid_q); cudaFree(w->m_mid); cudaFree(w->sort_key); cudaFree(w->sort_key2); cudaFree(w->m_key2); cudaFree(w->sort_idx); cudaFree(w->m_key); cudaFree(w->m_idx);
@@ -162,7 +170,7 @@ static int check_params(const fm_params* p, Params* out) {
 static BatchDev make_batch(Workspace* w, const int32_t* d_q_tok, const int32_t* d_q_off, int64_t n_q, int64_t n_tok) {
   BatchDev b{};
   b.q_tok_in = d_q_tok; b.q_off = d_q_off; b.n_q = (int32_t)n_q; b.n_tok = (int32_t)n_tok;
-  b.pat = w->pat; b.chain_q = w->chain_q; b.qmeta = w->qmeta; b.tbl = w->tbl; b.cmin_tab = w->cmin_tab; b.qmask = w->qmask;
+  b.pat = w->pat; b.chain_q = w->chain_q; b.qmeta = w->qmeta; b.tbl = w->tbl; b.cmin_tab = w->cmin_tab; b.qmask = w->qmask; b.wq = w->cap_wq ? w->wq : nullptr; b.peq64 = w->peq64;
   b.span_slice = w->span_slice; b.span_cap = w->cap_spans;
   b.sl_start = w->sl_start; b.sl_rec = w->sl_rec; b.slice_cap = w->cap_slices;
   b.hkey = w->hkey; b.hlm = w->hlm; b.hmask = w->hsize - 1;
@@ -205,7 +213,7 @@ static int launch_shard(Index* ix, Workspace* w, const int32_t* d_q_tok, const i
 
 static int initial_worklists(Index* ix, Workspace* w, int64_t n_q, int64_t n_tok) {
   int rc;
-  if ((rc = ensure_bounds(ix, w))) return rc;
+  if ((rc = ensure_bounds(ix, w)) || (rc = ensure_wide(ix, w))) return rc;
   if ((rc = ensure_slices(w, std::min<int64_t>((int64_t(1) << 26) - (1 << 17), std::max<int64_t>(1 << 16, 8 * n_tok + 65536))))) return rc;
   if ((rc = ensure_spans(w, std::max<int64_t>(1 << 16, 2 * n_tok + 65536)))) return rc;
   return ensure_survivors(w, std::max<int64_t>(1 << 18, 8 * n_q));

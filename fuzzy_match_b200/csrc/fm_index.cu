@@ -58,7 +58,8 @@ static int upload(const std::vector<T>& h, size_t extra, Index* ix, int blk, con
 // Boost binary archive, src/fuzzy_matcher_binarization.cc). Header, then the device blocks exactly as
 // they sit in HBM, then the host-side tables. Loading is read + upload: no sort, no hashing.
 static const char kMagic[8] = {'F', 'M', 'B', '2', '0', '0', 'I', 1};
-enum { BLK_TOK = 0, BLK_SA = 1, BLK_WALK = 2, BLK_QVA = 3, BLK_SID = 4, BLK_IDF = 5, BLK_BG = 6, BLK_TG = 7, BLK_REAL = 8, BLK_GAP = 9, BLK_NEXT = 10, N_BLK = 11 };
+static const int64_t kFileVersion = 2;  // 2: wide signatures (walk records of long sentences carry a wsig row)
+enum { BLK_TOK = 0, BLK_SA = 1, BLK_WALK = 2, BLK_QVA = 3, BLK_SID = 4, BLK_IDF = 5, BLK_BG = 6, BLK_TG = 7, BLK_REAL = 8, BLK_GAP = 9, BLK_NEXT = 10, BLK_WSIG = 11, N_BLK = 12 };
 
 static void bind_blocks(Index* ix) {
   IndexDev& d = ix->dev;
@@ -71,15 +72,17 @@ static void bind_blocks(Index* ix) {
   d.idf = static_cast<const float*>(ix->d_blocks[BLK_IDF]);
   d.bg_tab = static_cast<const int4*>(ix->d_blocks[BLK_BG]);
   d.tg_tab = static_cast<const int4*>(ix->d_blocks[BLK_TG]);
+  d.wsig = static_cast<const uint32_t*>(ix->d_blocks[BLK_WSIG]);
+  d.n_wide = (int32_t)(ix->blk_bytes[BLK_WSIG] / (kWideWords * sizeof(uint32_t)));
   d.real = ix->blk_bytes[BLK_REAL] ? static_cast<const int32_t*>(ix->d_blocks[BLK_REAL]) : nullptr;
   d.gap = ix->blk_bytes[BLK_GAP] ? static_cast<const int32_t*>(ix->d_blocks[BLK_GAP]) : nullptr;
 }
 
 int save_index(const Index* ix, const char* path) {
+  FM_CUDA(cudaSetDevice(ix->device));
   FILE* f = fopen(path, "wb");
   if (!f) { set_error(std::string("cannot open ") + path + " for writing"); return FM_ERR_INVALID; }
-  FM_CUDA(cudaSetDevice(ix->device));
-  int64_t hdr[16] = {1, ix->vocab_size, ix->max_tokens, ix->n_sent, ix->n_suf, ix->n_buf, (int64_t)ix->dev.bg_mask,
+  int64_t hdr[16] = {kFileVersion, ix->vocab_size, ix->max_tokens, ix->n_sent, ix->n_suf, ix->n_buf, (int64_t)ix->dev.bg_mask,
                      (int64_t)ix->dev.tg_mask, (int64_t)ix->dev.sid_base, ix->n_sent_global, 0, N_BLK, 0, 0, 0, 0};
   memcpy(&hdr[10], &ix->dev.idf_max, sizeof(float));
   bool ok = fwrite(kMagic, 1, 8, f) == 8 && fwrite(hdr, sizeof(int64_t), 16, f) == 16;
@@ -98,7 +101,22 @@ int save_index(const Index* ix, const char* path) {
   return FM_OK;
 }
 
-static int derive_next(Index* ix);
+// The header is untrusted input: every count is range-checked and cross-checked against the block sizes
+// before anything is allocated from it, so a truncated or corrupt file yields FM_ERR_INVALID, not a crash
+// or an out-of-bounds read in a later kernel.
+static bool header_ok(const int64_t* hdr, const int64_t* blk, int n_blk) {
+  const int64_t vocab = hdr[1], max_tok = hdr[2], n_sent = hdr[3], n_suf = hdr[4], n_buf = hdr[5], bgm = hdr[6], tgm = hdr[7];
+  auto pow2m1 = [](int64_t m) { return m >= 0 && m < (int64_t(1) << 32) && ((m + 1) & m) == 0; };
+  if (vocab < 2 || vocab > (int64_t(1) << 30) || max_tok < 1 || max_tok > FM_MAX_TOKENS) return false;
+  if (n_sent < 0 || n_suf < 0 || n_buf < 8 || n_buf >= (int64_t(1) << 31) || n_sent > n_suf || n_suf > n_buf) return false;
+  if (!pow2m1(bgm) || !pow2m1(tgm) || n_blk != N_BLK) return false;
+  if (blk[BLK_TOK] != n_buf * 4 || blk[BLK_SA] < n_suf * 4 || blk[BLK_NEXT] < n_suf * 4 || blk[BLK_WALK] < n_suf * 16) return false;
+  if (blk[BLK_QVA] != (vocab + 1) * 4 || blk[BLK_IDF] != vocab * 4 || blk[BLK_SID] != (n_buf / 4 + 1) * 4) return false;
+  if (blk[BLK_BG] != (bgm + 1) * 16 || blk[BLK_TG] != (tgm + 1) * 16) return false;
+  if (blk[BLK_WSIG] % (kWideWords * 4) != 0 || blk[BLK_WSIG] / (kWideWords * 4) > n_sent) return false;
+  if ((blk[BLK_REAL] != 0 && blk[BLK_REAL] != n_buf * 4) || blk[BLK_GAP] != blk[BLK_REAL]) return false;
+  return true;
+}
 
 int load_index(const char* path, int device, Index** out) {
   *out = nullptr;
@@ -106,44 +124,70 @@ int load_index(const char* path, int device, Index** out) {
   if (!f) { set_error(std::string("cannot open ") + path); return FM_ERR_INVALID; }
   char magic[8];
   int64_t hdr[16];
-  if (fread(magic, 1, 8, f) != 8 || memcmp(magic, kMagic, 8) != 0 || fread(hdr, sizeof(int64_t), 16, f) != 16 || hdr[0] != 1) {
+  if (fread(magic, 1, 8, f) != 8 || memcmp(magic, kMagic, 8) != 0 || fread(hdr, sizeof(int64_t), 16, f) != 16 || hdr[0] != kFileVersion) {
     fclose(f);
-    set_error(std::string(path) + " is not a fuzzy_match_b200 index (version 1)");
+    set_error(std::string(path) + " is not a fuzzy_match_b200 index (version " + std::to_string(kFileVersion) + ")");
     return FM_ERR_INVALID;
   }
-  Index* ix = new Index();
-  ix->device = device;
-  ix->vocab_size = (int32_t)hdr[1]; ix->max_tokens = (int32_t)hdr[2];
-  ix->n_sent = hdr[3]; ix->n_suf = hdr[4]; ix->n_buf = hdr[5]; ix->n_sent_global = hdr[9];
-  cudaError_t e = cudaSetDevice(device);
-  cudaDeviceProp prop;
-  if (e == cudaSuccess && cudaGetDeviceProperties(&prop, device) == cudaSuccess) ix->sm_count = prop.multiProcessorCount;
-  bool ok = e == cudaSuccess;
-  std::vector<char> buf;
-  const int n_blk = (int)std::min<int64_t>(std::max<int64_t>(hdr[11], 8), N_BLK);  // files written before the Sentence API hold 8
-  for (int k = 0; k < n_blk && ok; k++) {
-    int64_t n = 0;
-    ok = fread(&n, sizeof n, 1, f) == 1 && n >= 0 && n < (int64_t(1) << 40);
-    if (!ok) break;
-    buf.resize((size_t)n);
-    ok = n == 0 || fread(buf.data(), 1, (size_t)n, f) == (size_t)n;
-    void* d = nullptr;
-    ok = ok && cudaMalloc(&d, n ? (size_t)n : 16) == cudaSuccess;
-    ok = ok && (n == 0 || cudaMemcpy(d, buf.data(), (size_t)n, cudaMemcpyHostToDevice) == cudaSuccess);
-    ix->d_blocks[k] = d;
-    ix->blk_bytes[k] = (size_t)n;
-    ix->device_bytes += n;
-    if (k == BLK_TOK && ok) ix->h_tok.assign(reinterpret_cast<int32_t*>(buf.data()), reinterpret_cast<int32_t*>(buf.data()) + n / 4);
+  Index* ix = nullptr;
+  try {
+    // pass 1: block sizes (seek over the payloads), validated against the header
+    int64_t blk[N_BLK] = {};
+    const int n_blk = (int)hdr[11];
+    bool ok = n_blk == N_BLK;
+    const long data_pos = ftell(f);
+    for (int k = 0; k < N_BLK && ok; k++) {
+      ok = fread(&blk[k], sizeof(int64_t), 1, f) == 1 && blk[k] >= 0 && blk[k] < (int64_t(1) << 40) && fseek(f, (long)blk[k], SEEK_CUR) == 0;
+    }
+    if (ok) {  // the host tables must be there in full as well
+      const long tables_pos = ftell(f);
+      ok = fseek(f, 0, SEEK_END) == 0 && ftell(f) - tables_pos == (hdr[3] + 1) * 4 + hdr[3] * 8 + hdr[1] * 4;
+    }
+    if (!ok || !header_ok(hdr, blk, n_blk) || fseek(f, data_pos, SEEK_SET) != 0) {
+      fclose(f);
+      set_error(std::string(path) + ": corrupt or truncated index file");
+      return FM_ERR_INVALID;
+    }
+    ix = new Index();
+    ix->device = device;
+    ix->vocab_size = (int32_t)hdr[1]; ix->max_tokens = (int32_t)hdr[2];
+    ix->n_sent = hdr[3]; ix->n_suf = hdr[4]; ix->n_buf = hdr[5]; ix->n_sent_global = hdr[9];
+    cudaError_t e = cudaSetDevice(device);
+    cudaDeviceProp prop;
+    if (e == cudaSuccess && cudaGetDeviceProperties(&prop, device) == cudaSuccess) ix->sm_count = prop.multiProcessorCount;
+    ok = e == cudaSuccess;
+    std::vector<char> buf;
+    for (int k = 0; k < N_BLK && ok; k++) {
+      int64_t n = 0;
+      ok = fread(&n, sizeof n, 1, f) == 1 && n == blk[k];
+      if (!ok) break;
+      buf.resize((size_t)n);
+      ok = n == 0 || fread(buf.data(), 1, (size_t)n, f) == (size_t)n;
+      void* d = nullptr;
+      ok = ok && cudaMalloc(&d, n ? (size_t)n : 16) == cudaSuccess;
+      ok = ok && (n == 0 || cudaMemcpy(d, buf.data(), (size_t)n, cudaMemcpyHostToDevice) == cudaSuccess);
+      ix->d_blocks[k] = d;
+      ix->blk_bytes[k] = (size_t)n;
+      ix->device_bytes += n;
+      if (k == BLK_TOK && ok) ix->h_tok.assign(reinterpret_cast<int32_t*>(buf.data()), reinterpret_cast<int32_t*>(buf.data()) + n / 4);
+    }
+    ix->h_sent_start.resize((size_t)ix->n_sent + 1);
+    ix->kept.resize((size_t)ix->n_sent);
+    ix->sfreq.resize((size_t)ix->vocab_size);
+    ok = ok && fread(ix->h_sent_start.data(), sizeof(int32_t), ix->h_sent_start.size(), f) == ix->h_sent_start.size();
+    ok = ok && fread(ix->kept.data(), sizeof(int64_t), ix->kept.size(), f) == ix->kept.size();
+    ok = ok && fread(ix->sfreq.data(), sizeof(uint32_t), ix->sfreq.size(), f) == ix->sfreq.size();
+    fclose(f);
+    f = nullptr;
+    for (int64_t k = 0; ok && k <= ix->n_sent; k++)  // sentence starts index h_tok: keep them inside it
+      ok = ix->h_sent_start[k] >= 0 && ix->h_sent_start[k] < ix->n_buf && (ix->h_sent_start[k] & 3) == 0;
+    if (!ok) { free_index(ix); set_error(std::string("reading ") + path + " failed (corrupt file or CUDA error)"); return FM_ERR_INVALID; }
+  } catch (const std::exception&) {
+    if (f) fclose(f);
+    if (ix) free_index(ix);
+    set_error(std::string("out of memory while loading ") + path);
+    return FM_ERR_NOMEM;
   }
-  ix->h_sent_start.resize((size_t)ix->n_sent + 1);
-  ix->kept.resize((size_t)ix->n_sent);
-  ix->sfreq.resize((size_t)ix->vocab_size);
-  ok = ok && fread(ix->h_sent_start.data(), sizeof(int32_t), ix->h_sent_start.size(), f) == ix->h_sent_start.size();
-  ok = ok && fread(ix->kept.data(), sizeof(int64_t), ix->kept.size(), f) == ix->kept.size();
-  ok = ok && fread(ix->sfreq.data(), sizeof(uint32_t), ix->sfreq.size(), f) == ix->sfreq.size();
-  fclose(f);
-  if (!ok) { free_index(ix); set_error(std::string("reading ") + path + " failed (truncated file or CUDA error)"); return FM_ERR_INVALID; }
-  if (!ix->d_blocks[BLK_NEXT] && derive_next(ix) != FM_OK) { free_index(ix); return FM_ERR_CUDA; }  // file older than sa_next
   bind_blocks(ix);
   IndexDev& d = ix->dev;
   d.vocab_size = ix->vocab_size; d.max_tokens = ix->max_tokens; d.n_suf = ix->n_suf;
@@ -174,14 +218,28 @@ int set_idf_stats(Index* ix, const uint32_t* sf, int64_t n_sent_global) {
 // per-suffix walk records, and the bigram / trigram directories (run boundaries of the suffix array
 // inserted into open-addressing tables with 64-bit CAS).
 
+// Per sentence: length, 64-bit word signature, sid_at entry. A sentence longer than kWideMin tokens gets
+// row wide_row[s] of the 1024-bit signature table instead (the row was zeroed at allocation; one thread
+// owns a row), and its walk records carry that row number in place of the 64-bit signature.
 __global__ void fm_build_sentence_kernel(const int32_t* __restrict__ tok, const int32_t* __restrict__ sent_start, int n_sent,
-                                         unsigned long long* sig, int32_t* sent_len, int32_t* sid_at) {
+                                         const int32_t* __restrict__ wide_row, uint32_t* wsig, unsigned long long* sig,
+                                         int32_t* sent_len, int32_t* sid_at) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_sent) return;
   const int st = sent_start[s];
+  const int row = wide_row[s];
   unsigned long long sg = 0;
   int n = 0;
-  for (int t; (t = tok[st + n]) != 0; n++) sg |= 1ull << sig_bit(t);
+  if (row < 0) {
+    for (int t; (t = tok[st + n]) != 0; n++) sg |= 1ull << sig_bit(t);
+  } else {
+    uint32_t* w = wsig + (size_t)row * kWideWords;
+    for (int t; (t = tok[st + n]) != 0; n++) {
+      const unsigned b = wsig_bit(t);
+      w[b >> 5] |= 1u << (b & 31);
+    }
+    sg = (unsigned long long)(unsigned)row;
+  }
   sig[s] = sg;
   sent_len[s] = n;
   sid_at[st >> 2] = s;
@@ -318,12 +376,15 @@ static int derive_next(Index* ix) {
 }
 
 // Builds sa_walk, sa_next, sid_at and the two directories on the device from tok + sa_pos (already uploaded).
-static int build_on_device(Index* ix, const std::vector<int32_t>& sent_start) {
+static int build_on_device(Index* ix, const std::vector<int32_t>& sent_start, const std::vector<int32_t>& wide_row, int64_t n_wide) {
   IndexDev& d = ix->dev;
   const long long n_suf = ix->n_suf;
   const int n_sent = (int)ix->n_sent;
   int32_t* d_start = nullptr; int32_t* d_len = nullptr; unsigned long long* d_sig = nullptr; unsigned long long* d_counts = nullptr;
+  int32_t* d_wrow = nullptr;
   FM_CUDA(cudaMalloc((void**)&d_start, (size_t)(n_sent + 1) * 4));
+  FM_CUDA(cudaMalloc((void**)&d_wrow, (size_t)(n_sent + 1) * 4));
+  if (n_sent > 0) FM_CUDA(cudaMemcpy(d_wrow, wide_row.data(), (size_t)n_sent * 4, cudaMemcpyHostToDevice));
   FM_CUDA(cudaMalloc((void**)&d_len, (size_t)(n_sent + 1) * 4));
   FM_CUDA(cudaMalloc((void**)&d_sig, (size_t)(n_sent + 1) * 8));
   FM_CUDA(cudaMalloc((void**)&d_counts, 16));
@@ -331,13 +392,16 @@ static int build_on_device(Index* ix, const std::vector<int32_t>& sent_start) {
   FM_CUDA(cudaMemcpy(d_start, sent_start.data(), (size_t)(n_sent + 1) * 4, cudaMemcpyHostToDevice));
   int rc;
   if ((rc = dev_alloc(ix, BLK_SID, (size_t)(ix->n_buf / 4) + 1, 0xff, &d.sid_at)) ||
-      (rc = dev_alloc(ix, BLK_WALK, (size_t)n_suf + 4, 0, &d.sa_walk)) || (rc = derive_next(ix)))
+      (rc = dev_alloc(ix, BLK_WALK, (size_t)n_suf + 4, 0, &d.sa_walk)) || (rc = derive_next(ix)) ||
+      (rc = dev_alloc(ix, BLK_WSIG, (size_t)n_wide * kWideWords, 0, &d.wsig)))
     return rc;
+  d.n_wide = (int32_t)n_wide;
   d.sa_next = static_cast<const int32_t*>(ix->d_blocks[BLK_NEXT]);
   const int tb = 256;
   const unsigned gs = (unsigned)((n_suf + tb - 1) / tb);
   if (n_sent > 0)
-    fm_build_sentence_kernel<<<(n_sent + tb - 1) / tb, tb>>>(d.tok, d_start, n_sent, d_sig, d_len, const_cast<int32_t*>(d.sid_at));
+    fm_build_sentence_kernel<<<(n_sent + tb - 1) / tb, tb>>>(d.tok, d_start, n_sent, d_wrow, const_cast<uint32_t*>(d.wsig), d_sig, d_len,
+                                                             const_cast<int32_t*>(d.sid_at));
   unsigned long long counts[2] = {0, 0};
   if (n_suf > 0) {
     fm_build_walk_kernel<<<gs, tb>>>(d.sa_pos, n_suf, d_start, n_sent, d_sig, d_len, const_cast<int4*>(d.sa_walk));
@@ -359,7 +423,7 @@ static int build_on_device(Index* ix, const std::vector<int32_t>& sent_start) {
   }
   FM_CUDA(cudaDeviceSynchronize());
   FM_CUDA(cudaGetLastError());
-  cudaFree(d_start); cudaFree(d_len); cudaFree(d_sig); cudaFree(d_counts);
+  cudaFree(d_start); cudaFree(d_len); cudaFree(d_sig); cudaFree(d_counts); cudaFree(d_wrow);
   return FM_OK;
 }
 
@@ -470,6 +534,11 @@ int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_in, in
     for (int32_t w = 0; w < vocab_size; w++) cnt[w + 1] += cnt[w];
     for (int32_t w = 0; w <= vocab_size; w++) qva[w] = (int32_t)cnt[w];
   }
+  // ---- sentences that get a wide signature (kWideMin) and their row numbers
+  std::vector<int32_t> wide_row((size_t)n_keep, -1);
+  int64_t n_wide = 0;
+  for (int64_t k = 0; k < n_keep; k++)
+    if (compact_off[k + 1] - compact_off[k] > kWideMin) wide_row[k] = (int32_t)n_wide++;
   // ---- suffix sort: on the GPU (fm_sort.cu); FM_HOST_SORT=1 keeps the host-thread sort for cross-checks
   const bool host_sort = getenv("FM_HOST_SORT") != nullptr;
   std::vector<int32_t> sa;
@@ -530,7 +599,7 @@ int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_in, in
   pt.lap("suffix sort (device)");
   if (rc ||
       (rc = upload(qva, 0, ix, BLK_QVA, &d.qva)) ||
-      (rc = build_on_device(ix, ix->h_sent_start)) ||
+      (rc = build_on_device(ix, ix->h_sent_start, wide_row, n_wide)) ||
       (rc = upload(std::vector<float>((size_t)vocab_size, 0.f), 0, ix, BLK_IDF, &d.idf)) ||
       (rc = set_idf_stats(ix, sfreq_global ? sfreq_global : ix->sfreq.data(), n_sent_global > 0 ? n_sent_global : n_keep))) {
     free_index(ix);

@@ -32,6 +32,9 @@ namespace fm {
 //                         that start with that bigram, so the two widest narrowing steps of every chain
 //                         (whole array -> first word -> bigram) cost one probe instead of ~40.
 // sid_at   int32[n_buf/4] local sentence id, stored at (sentence start / 4); only read for survivors.
+// wsig     uint32[n_wide*32] 1024-bit word signatures of the sentences longer than kWideMin tokens (a 64-bit
+//                         signature saturates there); their walk records carry the row number instead of the
+//                         64-bit signature. One row = one 128-byte line.
 // idf      float[V]       logf(N / sfreq[w]) computed on the host with glibc (0 for unseen words).
 struct IndexDev {
   const int32_t* tok;
@@ -44,6 +47,8 @@ struct IndexDev {
   const int4* tg_tab;
   uint32_t tg_mask;
   const int32_t* sid_at;
+  const uint32_t* wsig;
+  int32_t n_wide;
   const float* idf;
   const int32_t* real;  // optional (Sentence API): (real form id << 1) | case class, parallel to tok
   const int32_t* gap;   // optional: penalty-token id of the gap before each token (separator slot = trailing gap)
@@ -63,6 +68,14 @@ static const int kQValid = 1;
 
 // word -> signature bit (must be identical on host and device)
 __host__ __device__ inline unsigned sig_bit(int w) { return ((unsigned)w * 0x9E3779B1u) >> 26; }
+// sentences longer than this carry a 1024-bit signature (wsig) instead of the 64-bit one
+static const int kWideMin = 48;
+static const int kWideWords = 32;  // 32-bit words per wide signature
+__host__ __device__ inline unsigned wsig_bit(int w) {
+  unsigned x = (unsigned)w * 0x85EBCA6Bu;
+  x ^= x >> 15;
+  return (x * 0xC2B2AE35u) >> 22;
+}
 // bigram -> slot hash (host build and device lookup)
 __host__ __device__ inline uint32_t bigram_hash(int w0, int w1) {
   unsigned long long k = ((unsigned long long)(unsigned)w0 << 32) | (unsigned)w1;
@@ -84,7 +97,7 @@ struct Counters {
   unsigned int n_matches;
   unsigned int n_heavy;  // queries with more than kWarpMax scored candidates (CTA each)
   unsigned int n_mid;    // queries with 2..kWarpMax scored candidates (warp each)
-  unsigned int n_long;  // != 0: some survivor's pattern is longer than 32 tokens (set by fm_score_short_kernel)
+  unsigned int n_long;  // bit0 / bit1: some survivor's pattern is too long for the first / second scoring kernel
 };
 static const int kElemBits = 38;
 
@@ -105,7 +118,9 @@ struct BatchDev {
   QMeta* qmeta;      // [n_q]
   int2* tbl;         // [4*n_tok] per-query open-addressing tables: (word, distinct_idx | count<<16)
   const uint16_t* cmin_tab; // [(max_tokens+1) << 10] per (pattern length << 10 | sentence length): smallest coverage that passes
-  int4* qmask;       // [2*n_q] per query: bit-sliced pattern-position counts per signature bit (B0,B1 | B2,extra)
+  int4* qmask;       // [2*n_q] per query: bit-sliced pattern-position counts per signature bit (B0,B1 | B2,extra,wide extra)
+  uint32_t* wq;      // [96*n_q] or NULL (index without wide signatures): the same three planes over the 1024 wide bits
+  unsigned long long* peq64;  // [n_tok] patterns of <= 64 tokens: position mask of each distinct word, at q_off + distinct index
   // search output
   long long* sl_start;  // [slice_cap+1] first flattened element of each slice (ascending)
   int4* sl_rec;         // [slice_cap] (q, sa_begin, match_len | p << 16, size)
@@ -166,6 +181,9 @@ struct Workspace {
   Params bounds_params{};
   bool bounds_valid = false;
   int4* qmask = nullptr;
+  uint32_t* wq = nullptr;
+  unsigned long long* peq64 = nullptr;
+  int64_t cap_wq = 0;
   long long* sl_start = nullptr;
   int4* sl_rec = nullptr;
   unsigned long long* hkey = nullptr;

@@ -19,6 +19,7 @@
 // result is written with __fadd_rn/__fmul_rn/__fdiv_rn in the reference's evaluation order so no
 // FMA contraction or reassociation can change a bit (the file is also compiled with -fmad=false).
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <cstdlib>
 
@@ -146,6 +147,8 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
   int2* tbl = b.tbl + 4ll * off;
   __shared__ int2 s_tbl[8][128];
   __shared__ int s_cnt[8][64];
+  __shared__ unsigned long long s_peq[8][64];
+  __shared__ uint32_t s_wcnt[8][512];  // 1024 16-bit counters per warp (wide signature bits)
   int c_lo = 0, c_hi = 0;  // pattern positions per signature bit (lane, lane + 32); unknown words excluded
   if (ts <= 128) {
     // Small pattern (p <= 64): lanes insert their words concurrently into a shared-memory table
@@ -175,6 +178,7 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
       if (e.x != -1) {
         const int d = distinct + __popc(used & ((1u << lane) - 1));
         tbl[j0 + lane] = make_int2(e.x, e.y | d);
+        wtbl[j0 + lane].y = e.y | d;
         if (e.x >= 2) atomicAdd(&cnt[sig_bit(e.x)], e.y >> 16);
       } else if (j0 + lane < ts) {
         tbl[j0 + lane] = e;
@@ -184,6 +188,20 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
     __syncwarp();
     c_lo = cnt[lane];
     c_hi = cnt[lane + 32];
+    // Position masks for the bit-parallel edit distance (p <= 64 here): peq64[off + d] has bit j set
+    // iff pattern[j] is the word with distinct index d.
+    unsigned long long* peq = s_peq[threadIdx.x >> 5];
+    peq[lane] = 0;
+    peq[lane + 32] = 0;
+    __syncwarp();
+    for (int j = lane; j < p; j += 32) {
+      const int w = b.pat[off + j];
+      int h = hash32((uint32_t)w) & (ts - 1);
+      while (wtbl[h].x != w) h = (h + 1) & (ts - 1);
+      atomicOr(&peq[wtbl[h].y & 0xffff], 1ull << j);
+    }
+    __syncwarp();
+    for (int d = lane; d < distinct; d += 32) b.peq64[off + d] = peq[d];
   } else {
     for (int j = lane; j < ts; j += 32) tbl[j] = make_int2(-1, 0);
     __syncwarp();
@@ -219,9 +237,45 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
     int extra = max(max(c_lo, c_hi) - 7, 0);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) extra = max(extra, __shfl_xor_sync(FULL, extra, d));
+    // The same three planes over the 1024 bits of the wide signatures (sentences longer than kWideMin):
+    // lane l owns signature bits [32 l, 32 l + 32), i.e. words 16 l .. 16 l + 15 of the packed counters.
+    int wextra = 0;
+    if (b.wq) {
+      uint32_t* wc = s_wcnt[threadIdx.x >> 5];
+      for (int k = lane; k < 512; k += 32) wc[k] = 0;
+      __syncwarp();
+      for (int j = lane; j < p; j += 32) {
+        const int w = b.pat[off + j];
+        if (w >= 2) {
+          const unsigned bit = wsig_bit(w);
+          atomicAdd(&wc[bit >> 1], 1u << (16 * (bit & 1)));
+        }
+      }
+      __syncwarp();
+      unsigned w0 = 0, w1 = 0, w2 = 0;
+      int mx = 0;
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        const int c = (k + lane) & 15;  // rotated: lanes hit different banks
+        const uint32_t v = wc[16 * lane + c];
+        const int c0 = (int)(v & 0xffffu), c1 = (int)(v >> 16);
+        mx = max(mx, max(c0, c1));
+        const int k0 = min(c0, 7), k1 = min(c1, 7);
+        w0 |= (unsigned)((k0 & 1) | ((k1 & 1) << 1)) << (2 * c);
+        w1 |= (unsigned)(((k0 >> 1) & 1) | (((k1 >> 1) & 1) << 1)) << (2 * c);
+        w2 |= (unsigned)(((k0 >> 2) & 1) | (((k1 >> 2) & 1) << 1)) << (2 * c);
+      }
+      uint32_t* dst = b.wq + (size_t)q * 3 * kWideWords;
+      dst[lane] = w0;
+      dst[kWideWords + lane] = w1;
+      dst[2 * kWideWords + lane] = w2;
+      wextra = max(mx - 7, 0);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) wextra = max(wextra, __shfl_xor_sync(FULL, wextra, d));
+    }
     if (lane == 0) {
       b.qmask[2 * q + 0] = make_int4(m[0], m[1], m[2], m[3]);
-      b.qmask[2 * q + 1] = make_int4(m[4], m[5], extra, 0);
+      b.qmask[2 * q + 1] = make_int4(m[4], m[5], extra, wextra);
     }
   }
 }
@@ -499,23 +553,61 @@ __device__ __forceinline__ void add_survivor(const BatchDev& b, int q, int start
   }
 }
 
-// Second stage of the gather: exact coverage of candidates that survived the signature bound.
-// item = (q, sentence start, sentence length | need << 16, match length); lanes >= n hold nothing.
-// Patterns of up to 32 words: one candidate per lane, the set of distinct words seen is one register.
-// Longer patterns (their 64-bit signatures saturate, so many candidates get here): one candidate at a
-// time, the 32 lanes probe the sentence's tokens in parallel and mark the distinct words in a
-// shared-memory bit set (PatternCoverage::count_covered_words, src/pattern_coverage.cc:15-28).
-__device__ __forceinline__ void verify_candidates(const IndexDev& ix, const BatchDev& b, const Params& pr, int4 item, int n,
+// Second stage of the gather: candidates that survived stage 1, taken from the warp's queue.
+// item = (q | match length << 20, sentence start, sentence length | need << 16, wide signature row or -1).
+//  * sentences with a wide signature (longer than kWideMin tokens): first the upper bound on the coverage
+//    from the 1024-bit signature and the query's bit-sliced planes -- 8 lanes per candidate, 128-bit loads,
+//    4 candidates per round -- so that only plausible pairs reach the exact count;
+//  * patterns of up to 32 words against short sentences: exact coverage, one candidate per lane, the set
+//    of distinct words seen is one register;
+//  * everything else: one candidate at a time, the 32 lanes probe the sentence's tokens in parallel and
+//    mark the distinct words in a shared-memory bit set (PatternCoverage::count_covered_words,
+//    src/pattern_coverage.cc:15-28).
+__device__ __forceinline__ void verify_candidates(const IndexDev& ix, const BatchDev& b, const Params& pr, const int4* queue, int n,
                                                   unsigned* seen, int lane) {
   const bool have = lane < n;
-  const int q = item.x, start = item.y, slen = item.z & 0xffff, need = (int)((unsigned)item.z >> 16);
+  const int4 item = have ? queue[lane] : make_int4(0, 0, 0, -1);
+  const int q = item.x & 0xfffff, start = item.y, slen = item.z & 0xffff, need = (int)((unsigned)item.z >> 16);
   int p = 0, off = 0;
   if (have) {
     const QMeta qm = __ldg(b.qmeta + q);
     p = qm.x;
     off = qm.z;
   }
-  if (have && p <= 32) {
+  const bool wide = have && item.w >= 0;
+  unsigned wide_pass = 0;
+  {
+    unsigned todo = __ballot_sync(FULL, wide && need != 0xffff);
+    wide_pass = __ballot_sync(FULL, wide && need == 0xffff);  // no bound table: straight to the exact count
+    const int grp = lane >> 3, sub = lane & 7;
+    const unsigned gmask = 0xffu << (8 * grp);
+    while (todo) {
+      const unsigned src = __fns(todo, 0, grp + 1);  // this group's candidate: the (grp+1)-th pending one
+      const bool valid = src < 32u;
+      int ub = 0, cneed = 0;
+      if (valid) {
+        const int4 it = queue[src];
+        const int cq = it.x & 0xfffff;
+        cneed = (int)((unsigned)it.z >> 16);
+        const uint4 sg = __ldg(reinterpret_cast<const uint4*>(ix.wsig + (size_t)it.w * kWideWords) + sub);
+        const uint4* pl = reinterpret_cast<const uint4*>(b.wq + (size_t)cq * 3 * kWideWords) + sub;
+        const uint4 b0 = __ldg(pl), b1 = __ldg(pl + kWideWords / 4), b2 = __ldg(pl + 2 * (kWideWords / 4));
+        const int extra = __ldg(&b.qmask[2 * cq + 1].w);
+        ub = __popc(sg.x & b0.x) + __popc(sg.y & b0.y) + __popc(sg.z & b0.z) + __popc(sg.w & b0.w) +
+             2 * (__popc(sg.x & b1.x) + __popc(sg.y & b1.y) + __popc(sg.z & b1.z) + __popc(sg.w & b1.w)) +
+             4 * (__popc(sg.x & b2.x) + __popc(sg.y & b2.y) + __popc(sg.z & b2.z) + __popc(sg.w & b2.w));
+        if (extra)
+          ub += extra * (__popc(sg.x & b0.x & b1.x & b2.x) + __popc(sg.y & b0.y & b1.y & b2.y) +
+                         __popc(sg.z & b0.z & b1.z & b2.z) + __popc(sg.w & b0.w & b1.w & b2.w));
+      }
+      ub = __reduce_add_sync(gmask, ub);
+      wide_pass |= __reduce_or_sync(FULL, (valid && sub == 0 && ub >= cneed) ? (1u << src) : 0u);
+      // drop the (up to) four candidates just handled
+      const unsigned done = __reduce_or_sync(FULL, valid ? (1u << src) : 0u);
+      todo &= ~done;
+    }
+  }
+  if (have && !wide && p <= 32) {
     const int2* tbl = b.tbl + 4ll * off;
     const int tmask = next_pow2(2 * p) - 1;
     bool ok;
@@ -524,15 +616,16 @@ __device__ __forceinline__ void verify_candidates(const IndexDev& ix, const Batc
     } else {
       ok = cover_sentence<1>(ix.tok + start, slen, tbl, tmask, need) >= need;
     }
-    if (ok) add_survivor(b, q, start, slen, item.w);
+    if (ok) add_survivor(b, q, start, slen, item.x >> 20);
   }
-  unsigned todo = __ballot_sync(FULL, have && p > 32);
+  unsigned todo = __ballot_sync(FULL, have && !wide && p > 32) | wide_pass;
   while (todo) {
     const int src = __ffs(todo) - 1;
     todo &= todo - 1;
-    const int cq = __shfl_sync(FULL, q, src), cstart = __shfl_sync(FULL, start, src), cz = __shfl_sync(FULL, item.z, src);
-    const int clm = __shfl_sync(FULL, item.w, src), cp = __shfl_sync(FULL, p, src), coff = __shfl_sync(FULL, off, src);
-    const int cslen = cz & 0xffff, cneed = (int)((unsigned)cz >> 16);
+    const int4 it = queue[src];
+    const int cq = it.x & 0xfffff, clm = it.x >> 20, cstart = it.y;
+    const int cslen = it.z & 0xffff, cneed = (int)((unsigned)it.z >> 16);
+    const int cp = __shfl_sync(FULL, p, src), coff = __shfl_sync(FULL, off, src);
     const int2* tbl = b.tbl + 4ll * coff;
     const int tmask = next_pow2(2 * cp) - 1;
     seen[lane] = 0;
@@ -553,8 +646,7 @@ __device__ __forceinline__ void verify_candidates(const IndexDev& ix, const Batc
         h = (h + 1) & tmask;
       }
     }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) cover += __shfl_xor_sync(FULL, cover, d);
+    cover = __reduce_add_sync(FULL, cover);
     __syncwarp();
     const bool ok = cneed == 0xffff ? !reject_cover(cp, cslen, cover, pr) : cover >= cneed;
     if (ok && lane == 0) add_survivor(b, cq, cstart, cslen, clm);
@@ -624,7 +716,10 @@ __global__ void __launch_bounds__(256, 8) fm_gather_kernel(IndexDev ix, BatchDev
         const int slen = wr.y;
         const int p = sr.z >> 16, lm = sr.z & 0xffff;
         const int need = __ldg(b.cmin_tab + ((p << 10) | slen));  // one lookup: length window + smallest passing coverage
-        if (need <= p) {
+        if (need <= p && slen > kWideMin) {  // long sentence: wr.z is its wide signature row, tested in stage 2
+          pass = true;
+          item = make_int4(q | (lm << 20), wr.x, slen | (need << 16), wr.z);
+        } else if (need <= p) {
           const int4 m0 = __ldg(b.qmask + 2 * q), m1 = __ldg(b.qmask + 2 * q + 1);  // planes (B0, B1), (B2, extra)
           const unsigned lo = (unsigned)wr.z, hi = (unsigned)wr.w;
           int ub = __popc(lo & m0.x) + __popc(hi & m0.y) + 2 * (__popc(lo & m0.z) + __popc(hi & m0.w));
@@ -634,11 +729,11 @@ __global__ void __launch_bounds__(256, 8) fm_gather_kernel(IndexDev ix, BatchDev
           }
           if (ub >= need) {
             pass = true;
-            item = make_int4(q, wr.x, slen | (need << 16), lm);
+            item = make_int4(q | (lm << 20), wr.x, slen | (need << 16), -1);
           }
         } else if (need == kNeedNoTable && !reject_length(p, slen, pr)) {
           pass = true;
-          item = make_int4(q, wr.x, slen | (0xffff << 16), lm);
+          item = make_int4(q | (lm << 20), wr.x, slen | (0xffff << 16), slen > kWideMin ? wr.z : -1);
         }
       }
       const unsigned bal = __ballot_sync(FULL, pass);
@@ -648,16 +743,16 @@ __global__ void __launch_bounds__(256, 8) fm_gather_kernel(IndexDev ix, BatchDev
         __syncwarp();
         if (queued >= 32) {
           queued -= 32;
-          verify_candidates(ix, b, pr, queue[queued + lane], 32, seen, lane);
+          verify_candidates(ix, b, pr, queue + queued, 32, seen, lane);
           __syncwarp();
         }
       }
     }
   }
-  verify_candidates(ix, b, pr, queue[lane], queued, seen, lane);
+  verify_candidates(ix, b, pr, queue, queued, seen, lane);
 }
 
-// ---------------------------------------------------------------- scan (single CTA, n <= a few million)
+// ---------------------------------------------------------------- scan (<= 128 co-resident CTAs)
 
 // Exclusive scan of the per-query survivor counts over co-resident CTAs: CTA i reduces its tile,
 // publishes the total (a flag/value pair in `chain`) and sums the totals of CTAs 0..i-1. The grid
@@ -929,7 +1024,7 @@ __global__ void __launch_bounds__(128) fm_score_short_kernel(IndexDev ix, BatchD
 // weight (src/fuzzy_match.cc:591) and the full edit distance without upper bound; writes the record
 // at the candidate's slot inside its query group.
 template <bool REAL>
-__global__ void __launch_bounds__(256) fm_score_kernel(IndexDev ix, BatchDev b, Params pr, int stride, int min_p) {
+__global__ void __launch_bounds__(256) fm_score_kernel(IndexDev ix, BatchDev b, Params pr, int stride, int min_p, unsigned long_mask) {
   extern __shared__ int smem[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -945,7 +1040,7 @@ __global__ void __launch_bounds__(256) fm_score_kernel(IndexDev ix, BatchDev b, 
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const long long n = min((long long)b.ctr->n_surv, (long long)b.surv_cap);
   if (b.ctr->overflow) return;
-  if (min_p > 32 && b.ctr->n_long == 0) return;  // nothing for the wavefront: every pattern fits the register kernel
+  if (min_p > 0 && (b.ctr->n_long & long_mask) == 0) return;  // nothing for the wavefront: the earlier kernels took every pair
   for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += n_warps) {
     const SurvRec sr = b.surv[w];
     const int slen = b.surv_len[w];
@@ -975,6 +1070,175 @@ __global__ void __launch_bounds__(256) fm_score_kernel(IndexDev ix, BatchDev b, 
     warp_edit_distance<REAL>(s_sent, slen, s_pat, p, s_pen, s_up, __fmul_rn(pr.del, wdiff), __fmul_rn(pr.ins, wdiff),
                              __fmul_rn(pr.rep, wdiff), C, K, rs);
     if (lane == 0) write_record(ix, b, sr, slen, C, K);
+  }
+}
+
+// ---------------------------------------------------------------- edit distance, bit-parallel
+//
+// When insert, delete and replace cost the same positive amount c and there are no IDF / real-token /
+// penalty-token terms, every cell of the reference's float DP (src/edit_distance.cc:41-75) is the float
+// sum of k copies of m = c * w added one at a time from 0 (each transition adds m or 0, min is exact), so
+// arr[i][j] = acc(D[i][j]) with D the integer Levenshtein distance and acc(k) = ((m + m) + m) ... k times
+// (SURVEY.md 3.1 Q3). D comes from Myers' bit-vector recurrence (Myers 1999, Hyyro 2003; global variant:
+// the top boundary grows by one per row) with the pattern along the bits: 32 (or 64) cells per ~17 integer
+// instructions. The early-exit value K = max_i min_{j>=1} arr[i][j] never exceeds the final cost for such
+// costs (row i's minimum is at most arr[i][1] <= arr[i][0] + m = arr[i+1][0] <= arr[s][p]), and the replay
+// only uses max(K, C), so K = C is recorded.
+
+__device__ __forceinline__ float chain_cost(int k, float m) {  // acc(k)
+  float v = 0.f;
+  for (int i = 0; i < k; i++) v = __fadd_rn(v, m);
+  return v;
+}
+
+// One row of the recurrence for a whole bit vector (horizontal input +1: the global top boundary);
+// returns the horizontal delta leaving at bit `high`.
+template <typename W>
+__device__ __forceinline__ int myers_row(W eq, W& pv, W& mv, W high) {
+  const W xv = eq | mv;
+  const W xh = (((eq & pv) + pv) ^ pv) | eq;
+  W ph = mv | ~(xh | pv);
+  W mh = pv & xh;
+  const int hout = (ph & high) ? 1 : ((mh & high) ? -1 : 0);
+  ph = (ph << 1) | 1;
+  mh <<= 1;
+  pv = mh | ~(xv | ph);
+  mv = ph & xv;
+  return hout;
+}
+
+// position mask of word w in the query's pattern (0 when the pattern does not contain it)
+__device__ __forceinline__ unsigned long long peq_lookup(const int2* __restrict__ tbl, int tmask,
+                                                         const unsigned long long* __restrict__ peq, int w, int2 e, int h) {
+  for (;;) {
+    if (e.x == w) return __ldg(peq + (e.y & 0xffff));
+    if (e.x == -1) return 0ull;
+    h = (h + 1) & tmask;
+    e = __ldg(tbl + h);
+  }
+}
+
+template <typename W>
+__device__ __forceinline__ int myers_thread(const int32_t* __restrict__ sent, int s, int p, const int2* __restrict__ tbl, int tmask,
+                                            const unsigned long long* __restrict__ peq) {
+  W pv = ~(W)0, mv = 0;
+  const W high = (W)1 << (p - 1);
+  int score = p;
+  const int4* s4 = reinterpret_cast<const int4*>(sent);
+  for (int i0 = 0; i0 < s; i0 += 4) {
+    const int4 t = ldg_nc_v4(s4 + (i0 >> 2));  // sentences start on 16-byte boundaries and are zero padded
+    // first probes of the four lookups in flight together
+    const int h0 = hash32((uint32_t)t.x) & tmask, h1 = hash32((uint32_t)t.y) & tmask;
+    const int h2 = hash32((uint32_t)t.z) & tmask, h3 = hash32((uint32_t)t.w) & tmask;
+    const int2 e0 = __ldg(tbl + h0), e1 = __ldg(tbl + h1), e2 = __ldg(tbl + h2), e3 = __ldg(tbl + h3);
+    const W q0 = (W)peq_lookup(tbl, tmask, peq, t.x, e0, h0);
+    const W q1 = (W)peq_lookup(tbl, tmask, peq, t.y, e1, h1);
+    const W q2 = (W)peq_lookup(tbl, tmask, peq, t.z, e2, h2);
+    const W q3 = (W)peq_lookup(tbl, tmask, peq, t.w, e3, h3);
+    score += myers_row<W>(q0, pv, mv, high);
+    if (i0 + 1 < s) score += myers_row<W>(q1, pv, mv, high);
+    if (i0 + 2 < s) score += myers_row<W>(q2, pv, mv, high);
+    if (i0 + 3 < s) score += myers_row<W>(q3, pv, mv, high);
+  }
+  return score;
+}
+
+static const int kBpThreadMax = 64;  // thread per pair up to here (one 64-bit vector)
+static const int kBpWarpMax = 320;   // warp per pair up to here (Peq table of the pair in shared memory)
+
+// One thread per surviving (query, sentence) with p <= 64.
+__global__ void __launch_bounds__(128) fm_score_bp_kernel(IndexDev ix, BatchDev b, Params pr) {
+  const long long n = min((long long)b.ctr->n_surv, (long long)b.surv_cap);
+  if (b.ctr->overflow) return;
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n) return;
+  const SurvRec sr = b.surv[w];
+  const int slen = b.surv_len[w];
+  const QMeta qm = b.qmeta[sr.q];
+  const int p = qm.x;
+  if (p > kBpThreadMax) {  // left to the warp kernels, which only scan the survivors when their flag is set
+    atomicOr(&b.ctr->n_long, p > kBpWarpMax ? 2u : 1u);
+    return;
+  }
+  const int2* tbl = b.tbl + 4ll * qm.z;
+  const int tmask = next_pow2(2 * p) - 1;
+  const unsigned long long* peq = b.peq64 + qm.z;
+  const int32_t* sent = ix.tok + sr.start;
+  const int d = p <= 32 ? myers_thread<uint32_t>(sent, slen, p, tbl, tmask, peq)
+                        : myers_thread<unsigned long long>(sent, slen, p, tbl, tmask, peq);
+  const float wdiff = __fdiv_rn(100.f, normalizer(p, slen, pr));
+  const float C = chain_cost(d, __fmul_rn(pr.del, wdiff));
+  write_record(ix, b, sr, slen, C, C);
+}
+
+// One warp per surviving pair with 64 < p <= kBpWarpMax: lane l owns pattern positions [32 l, 32 l + 32)
+// and works on row t - l at step t (a wavefront over the blocks: the horizontal delta leaving block l
+// for row i enters block l + 1 one step later, one __shfl_up per step). The pair's position masks
+// (distinct word x block) and the distinct index of every sentence token are staged in shared memory.
+__global__ void __launch_bounds__(128) fm_score_bpw_kernel(IndexDev ix, BatchDev b, Params pr, int peq_words, int didx_words) {
+  extern __shared__ uint32_t bsm[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint32_t* s_peq = bsm + (size_t)wib * (peq_words + didx_words);
+  uint16_t* s_didx = reinterpret_cast<uint16_t*>(s_peq + peq_words);
+  if (b.ctr->overflow || !(b.ctr->n_long & 1u)) return;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long n = min((long long)b.ctr->n_surv, (long long)b.surv_cap);
+  for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += n_warps) {
+    const SurvRec sr = b.surv[w];
+    const QMeta qm = b.qmeta[sr.q];
+    const int p = qm.x;
+    if (p <= kBpThreadMax || p > kBpWarpMax) continue;
+    const int slen = b.surv_len[w];
+    const int nw = (p + 31) >> 5;
+    const int2* tbl = b.tbl + 4ll * qm.z;
+    const int tmask = next_pow2(2 * p) - 1;
+    auto didx_of = [&](int word) -> int {
+      int h = hash32((uint32_t)word) & tmask;
+      for (;;) {
+        const int2 e = __ldg(tbl + h);
+        if (e.x == word) return e.y & 0xffff;
+        if (e.x == -1) return 0xffff;
+        h = (h + 1) & tmask;
+      }
+    };
+    for (int k = lane; k < p * nw; k += 32) s_peq[k] = 0;
+    __syncwarp();
+    for (int j = lane; j < p; j += 32) atomicOr(&s_peq[didx_of(b.pat[qm.z + j]) * nw + (j >> 5)], 1u << (j & 31));
+    for (int i = lane; i < slen; i += 32) s_didx[i] = (uint16_t)didx_of(__ldg(ix.tok + sr.start + i));
+    __syncwarp();
+    uint32_t pv = ~0u, mv = 0;
+    const uint32_t high = lane == nw - 1 ? 1u << ((p - 1) & 31) : 0x80000000u;
+    int hout = 0, score = p;
+    const int steps = slen + nw - 1;
+    for (int t = 1; t <= steps; t++) {
+      int hin = __shfl_up_sync(FULL, hout, 1);
+      if (lane == 0) hin = 1;
+      const int i = t - lane;
+      if (lane < nw && i >= 1 && i <= slen) {
+        const int d = s_didx[i - 1];
+        uint32_t eq = d != 0xffff ? s_peq[d * nw + lane] : 0u;
+        const uint32_t xv = eq | mv;
+        if (hin < 0) eq |= 1u;
+        const uint32_t xh = (((eq & pv) + pv) ^ pv) | eq;
+        uint32_t ph = mv | ~(xh | pv);
+        uint32_t mh = pv & xh;
+        hout = (ph & high) ? 1 : ((mh & high) ? -1 : 0);
+        ph <<= 1;
+        mh <<= 1;
+        if (hin < 0) mh |= 1u;
+        else if (hin > 0) ph |= 1u;
+        pv = mh | ~(xv | ph);
+        mv = ph & xv;
+        if (lane == nw - 1) score += hout;
+      }
+    }
+    score = __shfl_sync(FULL, score, nw - 1);
+    if (lane == 0) {
+      const float wdiff = __fdiv_rn(100.f, normalizer(p, slen, pr));
+      const float C = chain_cost(score, __fmul_rn(pr.del, wdiff));
+      write_record(ix, b, sr, slen, C, C);
+    }
+    __syncwarp();
   }
 }
 
@@ -1515,46 +1779,73 @@ void launch_scan(const int32_t* in, int32_t* out, int32_t n, unsigned long long*
   if (ctas > sm_count) ctas = sm_count;  // all CTAs must be co-resident
   fm_scan_kernel<<<ctas, 1024, 0, st>>>(in, out, n, chain, epoch);
 }
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: opt in once per (kernel, device).
+// One process may hold indexes on several GPUs and call from several host threads.
+struct SmemOptIn {
+  std::atomic<unsigned long long> done{0};
+  template <class F>
+  void ensure(F fn, int bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return;
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    done.fetch_or(bit, std::memory_order_release);
+  }
+};
+
 void launch_score(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st) {
   const int stride = dp_stride(ix);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(fm_score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(fm_score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
-  }
+  static SmemOptIn opt_f, opt_t, opt_bpw;
+  opt_f.ensure(fm_score_kernel<false>, 200 * 1024);
+  opt_t.ensure(fm_score_kernel<true>, 200 * 1024);
   if (b.q_real) {  // Sentence API: every pair through the wavefront kernel with the real-token terms
     const int warps = 4;  // 8 staging arrays per warp
-    fm_score_kernel<true><<<sm_count * 4, warps * 32, (size_t)warps * 8 * stride * sizeof(int), st>>>(ix, b, p, stride, 0);
+    fm_score_kernel<true><<<sm_count * 4, warps * 32, (size_t)warps * 8 * stride * sizeof(int), st>>>(ix, b, p, stride, 0, 0u);
     return;
   }
   const size_t smem = (size_t)8 * 4 * stride * sizeof(int);
-  // FM_SCORE_WARP_ONLY=1 forces every pair through the warp wavefront (tests exercise both paths)
+  // Environment switches (read once per process; tests/test_gpu_scale.py runs each in a fresh process):
+  // FM_SCORE_WARP_ONLY=1 sends every pair through the float warp wavefront, FM_SCORE_FLOAT_ONLY=1 disables
+  // the bit-parallel kernels so that equal costs take the float kernels too.
   static const bool warp_only = getenv("FM_SCORE_WARP_ONLY") != nullptr;
-  if (!warp_only) {
-    const int grid = (int)((b.surv_cap + 127) / 128);
-    if (p.idf_penalty != 0.f) fm_score_short_kernel<true><<<grid, 128, 0, st>>>(ix, b, p);
-    else fm_score_short_kernel<false><<<grid, 128, 0, st>>>(ix, b, p);
+  static const bool float_only = getenv("FM_SCORE_FLOAT_ONLY") != nullptr;
+  const int grid_t = (int)((b.surv_cap + 127) / 128);
+  if (warp_only) {
+    fm_score_kernel<false><<<sm_count * 4, 256, smem, st>>>(ix, b, p, stride, 0, 0u);
+    return;
   }
-  fm_score_kernel<false><<<sm_count * 4, 256, smem, st>>>(ix, b, p, stride, warp_only ? 0 : 33);
+  const bool equal_costs = p.ins == p.del && p.del == p.rep && p.ins > 0.f && p.idf_penalty == 0.f;
+  if (equal_costs && !float_only) {
+    // thread per pair (p <= 64) -> warp per pair (p <= 320) -> float wavefront (longer patterns)
+    const int mp = std::min(ix.max_tokens, kBpWarpMax);
+    const int peq_words = mp * ((mp + 31) / 32), didx_words = (ix.max_tokens + 2) / 2 + 1;
+    const size_t bsm = (size_t)4 * (peq_words + didx_words) * sizeof(uint32_t);
+    opt_bpw.ensure(fm_score_bpw_kernel, 200 * 1024);
+    fm_score_bp_kernel<<<grid_t, 128, 0, st>>>(ix, b, p);
+    if (ix.max_tokens > kBpThreadMax) fm_score_bpw_kernel<<<sm_count * 3, 128, bsm, st>>>(ix, b, p, peq_words, didx_words);
+    if (ix.max_tokens > kBpWarpMax) fm_score_kernel<false><<<sm_count * 4, 256, smem, st>>>(ix, b, p, stride, kBpWarpMax + 1, 2u);
+    return;
+  }
+  if (p.idf_penalty != 0.f) fm_score_short_kernel<true><<<grid_t, 128, 0, st>>>(ix, b, p);
+  else fm_score_short_kernel<false><<<grid_t, 128, 0, st>>>(ix, b, p);
+  if (ix.max_tokens > 32) fm_score_kernel<false><<<sm_count * 4, 256, smem, st>>>(ix, b, p, stride, 33, 1u);
 }
 void launch_replay(const IndexDev& ix, const fm_record* rec, const int32_t* q_cnt, const int32_t* q_base, float* heapbuf,
                    unsigned long long* sort_key, unsigned long long* sort_key2, int32_t* sort_idx, int32_t* acc_cnt,
                    int32_t* mid_q, int32_t* heavy_q, const int32_t* q_off, int32_t n_q, const Params& p, int64_t cap,
                    fm_match* out, int32_t* out_count, Counters* ctr, int sm_count, cudaStream_t st, cudaStream_t st2,
                    cudaEvent_t ev_fork, cudaEvent_t ev_join) {
-  // FM_WARP_MAX=<n> (32..kWarpMax) moves the warp / CTA boundary (tuning and tests)
+  // FM_WARP_MAX=<n> (32..kWarpMax) moves the warp / CTA boundary (tests/test_gpu_scale.py: fresh process per setting)
   static const int warp_max = getenv("FM_WARP_MAX") ? std::max(32, std::min(kWarpMax, atoi(getenv("FM_WARP_MAX")))) : kWarpMax;
   fm_replay_small_kernel<<<(n_q + 255) / 256, 256, 0, st>>>(const_cast<fm_record*>(rec), q_cnt, q_base, sort_idx, acc_cnt, mid_q,
                                                             heavy_q, q_off, n_q, p, (long long)cap, out, out_count, ctr, warp_max);
   const size_t smem = (size_t)kHeavySmem * sizeof(unsigned long long);
-  // FM_HEAVY_SMEM=<n> lowers the shared-memory sort limit so that tests reach the radix-sort path
+  // FM_HEAVY_SMEM=<n> lowers the shared-memory sort limit: the CTA radix sort then takes shorter lists too
+  // (tests/test_gpu_scale.py; without it lists of more than kHeavySmem candidates take that path)
   static const int smem_cap = getenv("FM_HEAVY_SMEM") ? std::max(64, std::min(kHeavySmem, atoi(getenv("FM_HEAVY_SMEM")))) : kHeavySmem;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(fm_replay_heavy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
-  }
+  static SmemOptIn opt_heavy;
+  opt_heavy.ensure(fm_replay_heavy_kernel, (int)smem);
   // The two remaining kernels work on disjoint queries (the lists the small kernel wrote). The heavy
   // one is a few long sequential replays, so it runs on a side stream next to the warp-per-query one.
   cudaStream_t sh = st2 ? st2 : st;
@@ -1576,11 +1867,8 @@ void launch_contrast(const IndexDev& ix, fm_record* rec, const int32_t* q_base, 
                      cudaStream_t st) {
   const int stride = dp_stride(ix);
   const size_t smem = (size_t)8 * 4 * stride * sizeof(int);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(fm_contrast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
-  }
+  static SmemOptIn opt_contrast;
+  opt_contrast.ensure(fm_contrast_kernel, 200 * 1024);
   int grid = (n_q + 7) / 8;
   if (grid > sm_count * 4) grid = sm_count * 4;
   fm_contrast_kernel<<<grid, 256, smem, st>>>(ix, rec, q_base, sort_idx, acc_cnt, n_q, p, (long long)cap, out, out_count, ctr, stride);
