@@ -18,7 +18,8 @@ class FuzzyMatchError(RuntimeError):
 
 
 def library_path():
-    return os.path.join(_HERE, "libfm_b200.so")
+    # FM_B200_LIB selects another build of the same library (kernel tuning experiments)
+    return os.environ.get("FM_B200_LIB") or os.path.join(_HERE, "libfm_b200.so")
 
 
 def build_library(verbose=False):
@@ -55,7 +56,7 @@ class Profile(C.Structure):
                 ("ms_score", C.c_float), ("ms_replay", C.c_float), ("ms_total", C.c_float),
                 ("n_queries", C.c_int64), ("n_query_tokens", C.c_int64), ("n_slices", C.c_int64),
                 ("n_elements", C.c_int64), ("n_survivors", C.c_int64), ("n_matches", C.c_int64),
-                ("launches", C.c_int32), ("retries", C.c_int32)]
+                ("launches", C.c_int32), ("retries", C.c_int32), ("n_stage2", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -68,7 +69,8 @@ RECORD_DTYPE = np.dtype([("s_id", np.uint32), ("longest_match", np.int32), ("len
 
 EXPORTS = ["fm_index_create", "fm_index_destroy", "fm_index_save", "fm_index_load", "fm_index_num_sentences", "fm_index_num_suffixes",
            "fm_index_max_tokens_in_pattern", "fm_index_device_bytes", "fm_index_kept_sources", "fm_index_sfreq",
-           "fm_index_sentence", "fm_index_set_idf_stats", "fm_index_set_real", "fm_match_batch", "fm_match_batch_real", "fm_match_batch_device", "fm_shard_score_device",
+           "fm_index_sentence", "fm_index_set_idf_stats", "fm_index_set_real", "fm_match_batch", "fm_match_batch_real", "fm_match_batch_device",
+           "fm_match_batch_submit", "fm_match_batch_device_submit", "fm_ticket_wait", "fm_shard_score_device",
            "fm_merge_replay_device", "fm_set_profiling", "fm_get_profile", "fm_last_error", "fm_version"]
 
 
@@ -106,6 +108,11 @@ def load_library():
                                         C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
     lib.fm_match_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(Params),
                                           C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.fm_match_batch_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Params), C.c_int64,
+                                          C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.fm_match_batch_device_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(Params),
+                                                 C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.fm_ticket_wait.argtypes = [C.c_void_p]
     lib.fm_shard_score_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(Params),
                                           C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_void_p]
     lib.fm_merge_replay_device.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p,
@@ -257,6 +264,23 @@ class Index:
         p = params if params is not None else Params.make(**kw)
         _check(self.lib, self.lib.fm_match_batch_device(self.h, d_q_tokens, d_q_off, n_q, n_tok, C.byref(p), cap, d_out,
                                                         d_out_count, stream))
+
+    def submit(self, q_tokens, q_off, out, cnt, cap, params):
+        """fm_match_batch_submit: returns a ticket; the arrays must stay alive and untouched until wait(ticket)."""
+        assert q_tokens.dtype == np.int32 and q_off.dtype == np.int64 and out.dtype == MATCH_DTYPE and cnt.dtype == np.int32
+        t = C.c_void_p()
+        _check(self.lib, self.lib.fm_match_batch_submit(self.h, _ptr(q_tokens), _ptr(q_off), len(q_off) - 1, C.byref(params), cap,
+                                                        _ptr(out), _ptr(cnt), C.byref(t)))
+        return t
+
+    def submit_device(self, d_q_tokens, d_q_off, n_q, n_tok, d_out, d_out_count, cap, stream, params):
+        t = C.c_void_p()
+        _check(self.lib, self.lib.fm_match_batch_device_submit(self.h, d_q_tokens, d_q_off, n_q, n_tok, C.byref(params), cap, d_out,
+                                                               d_out_count, stream, C.byref(t)))
+        return t
+
+    def wait(self, ticket):
+        _check(self.lib, self.lib.fm_ticket_wait(ticket))
 
     def shard_score_device(self, d_q_tokens, d_q_off, n_q, n_tok, stream=0, params=None, **kw):
         """Returns (d_rec_off ptr, d_rec ptr, n_rec) for the cross-shard replay."""

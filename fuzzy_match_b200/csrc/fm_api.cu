@@ -20,7 +20,7 @@ static int dev_realloc(T** p, size_t n) {
   return FM_OK;
 }
 
-static const int64_t kSpanHost = 256;  // == kSpan in fm_kernels.cu
+static const int64_t kSpanHost = kSpan;
 static int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
 static Workspace* acquire(Index* ix) {
@@ -45,6 +45,7 @@ static int ensure_base(Workspace* w) {
     FM_CUDA(cudaStreamCreateWithFlags(&w->stream2, cudaStreamNonBlocking));
     FM_CUDA(cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming));
     FM_CUDA(cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming));
+    FM_CUDA(cudaEventCreateWithFlags(&w->ev_done, cudaEventDisableTiming));
     FM_CUDA(cudaMalloc((void**)&w->ctr, sizeof(Counters)));
     FM_CUDA(cudaMalloc((void**)&w->scan_chain, 256 * sizeof(unsigned long long)));
     FM_CUDA(cudaMemset(w->scan_chain, 0, 256 * sizeof(unsigned long long)));
@@ -58,7 +59,7 @@ static int ensure_queries(Workspace* w, int64_t n_q, int64_t n_tok, bool staging
   if (n_q > w->cap_q) {
     const int64_t c = round_up(n_q + n_q / 4 + 1024, 1024);
     if ((rc = dev_realloc(&w->qmeta, c)) || (rc = dev_realloc(&w->q_cnt, c + 1)) || (rc = dev_realloc(&w->q_base, c + 1)) ||
-        (rc = dev_realloc(&w->acc_cnt, c)) || (rc = dev_realloc(&w->heavy_q, c)) || (rc = dev_realloc(&w->mid_q, c)) || (rc = dev_realloc(&w->qmask, 2 * c)) || (rc = dev_realloc(&w->d_q_off, c + 1)) || (rc = dev_realloc(&w->d_out_count, c + 1)))
+        (rc = dev_realloc(&w->acc_cnt, c)) || (rc = dev_realloc(&w->heavy_q, c)) || (rc = dev_realloc(&w->mid_q, c)) || (rc = dev_realloc(&w->qmask, c)) || (rc = dev_realloc(&w->d_q_off, c + 1)) || (rc = dev_realloc(&w->d_out_count, c + 1)))
       return rc;
     w->cap_q = c;
     w->cap_surv = 0;  // heapbuf depends on cap_q
@@ -83,21 +84,25 @@ static int ensure_queries(Workspace* w, int64_t n_q, int64_t n_tok, bool staging
 static int ensure_wide(Index* ix, Workspace* w) {
   if (ix->dev.n_wide == 0 || w->cap_wq >= w->cap_q) return FM_OK;
   int rc;
-  if ((rc = dev_realloc(&w->wq, (size_t)w->cap_q * 3 * kWideWords))) return rc;
+  if ((rc = dev_realloc(&w->wq, (size_t)w->cap_q * 3 * kWideWords)) || (rc = dev_realloc(&w->wextra, (size_t)w->cap_q))) return rc;
   w->cap_wq = w->cap_q;
   return FM_OK;
 }
+// (Worklists grow with a quarter of slack: batches of one stream differ a little in size, and a
+// reallocation -- cudaFree + cudaMalloc synchronise the device -- must not recur batch after batch.)
 static int ensure_slices(Workspace* w, int64_t n) {
   if (n <= w->cap_slices) return FM_OK;
+  n = std::min<int64_t>(n + n / 4, (int64_t(1) << 26) - 65537);
   // the packed (slices << 38 | elements) counter leaves 26 bits for the slice count
   if (n >= (int64_t(1) << 26) - 65536) { set_error("too many suffix-array range slices in one batch: split the batch"); return FM_ERR_NOMEM; }
   int rc;
-  if ((rc = dev_realloc(&w->sl_start, n + 1)) || (rc = dev_realloc(&w->sl_rec, n))) return rc;
+  if ((rc = dev_realloc(&w->sl_start, n + 1)) || (rc = dev_realloc(&w->sl_rec, n)) || (rc = dev_realloc(&w->sm_rec, n))) return rc;
   w->cap_slices = n;
   return FM_OK;
 }
 static int ensure_spans(Workspace* w, int64_t n) {
   if (n <= w->cap_spans) return FM_OK;
+  n += n / 4;
   int rc;
   if ((rc = dev_realloc(&w->span_slice, n))) return rc;
   w->cap_spans = n;
@@ -107,7 +112,7 @@ static int ensure_bounds(Index* ix, Workspace* w) {
   if (w->cmin_tab) return FM_OK;
   int rc;
   const int64_t t = ix->max_tokens;
-  if ((rc = dev_realloc(&w->cmin_tab, (t + 1) << 10))) return rc;
+  if ((rc = dev_realloc(&w->cmin_tab, (t + 1) << 10)) || (rc = dev_realloc(&w->cmin64, (t + 1) << 6))) return rc;
   w->bounds_valid = false;
   return FM_OK;
 }
@@ -115,6 +120,7 @@ static int ensure_survivors(Workspace* w, int64_t n) {
   if (n <= w->cap_surv) return FM_OK;
   int rc;
   if (n > (int64_t(1) << 28)) { set_error("too many surviving candidates in one batch: split the batch"); return FM_ERR_NOMEM; }
+  n = std::min<int64_t>(n + n / 4, int64_t(1) << 28);
   uint32_t hs = 1u << 20;
   while ((int64_t)hs < 4 * n) hs <<= 1;
   if ((rc = dev_realloc(&w->surv, n)) || (rc = dev_realloc(&w->surv_len, n)) || (rc = dev_realloc(&w->rec, n)) ||
@@ -128,14 +134,14 @@ static int ensure_survivors(Workspace* w, int64_t n) {
 static int ensure_out(Workspace* w, int64_t n_q, int64_t cap) {
   if (n_q * cap <= w->cap_out) return FM_OK;
   int rc;
-  const int64_t c = n_q * cap + 1024;
+  const int64_t c = n_q * cap + n_q * cap / 4 + 1024;
   if ((rc = dev_realloc(&w->d_out, c))) return rc;
   w->cap_out = c;
   return FM_OK;
 }
 
 static void free_workspace(Workspace* w) {
-  cudaFree(w->d_q_tok); cudaFree(w->d_q_off); cudaFree(w->d_q_real); cudaFree(w->d_q_gap); cudaFree(w->d_itok_dist); cudaFree(w->pat); cudaFree(w->chain_q); cudaFree(w->qmeta); cudaFree(w->tbl); cudaFree(w->cmin_tab); cudaFree(w->span_slice); cudaFree(w->qmask); cudaFree(w->wq); cudaFree(w->peq64);
+  cudaFree(w->d_q_tok); cudaFree(w->d_q_off); cudaFree(w->d_q_real); cudaFree(w->d_q_gap); cudaFree(w->d_itok_dist); cudaFree(w->pat); cudaFree(w->chain_q); cudaFree(w->qmeta); cudaFree(w->tbl); cudaFree(w->cmin_tab); cudaFree(w->span_slice); cudaFree(w->qmask); cudaFree(w->wq); cudaFree(w->peq64); cudaFree(w->cmin64); cudaFree(w->wextra); cudaFree(w->sm_rec);
   cudaFree(w->sl_start); cudaFree(w->sl_rec); cudaFree(w->hkey); cudaFree(w->hlm); cudaFree(w->surv); cudaFree(w->surv_len);
   cudaFree(w->q_cnt); cudaFree(w->q_base); cudaFree(w->acc_cnt); cudaFree(w->rec); cudaFree(w->heapbuf); cudaFree(w->ctr); cudaFree(w->scan_chain);
   cudaFree(w->d_out); cudaFree(w->d_out_count); cudaFree(w->mrec); cudaFree(w->m_cnt); cudaFree(w->m_base); cudaFree(w->m_acc); cudaFree(w->m_heap); cudaFree(w->heavy_q); cudaFree(w->m_heavy); cudaFree(w->mid_q); cudaFree(w->m_mid); cudaFree(w->sort_key); cudaFree(w->sort_key2); cudaFree(w->m_key2); cudaFree(w->sort_idx); cudaFree(w->m_key); cudaFree(w->m_idx);
@@ -146,6 +152,7 @@ static void free_workspace(Workspace* w) {
     if (w->stream2) cudaStreamDestroy(w->stream2);
     if (w->ev_fork) cudaEventDestroy(w->ev_fork);
     if (w->ev_join) cudaEventDestroy(w->ev_join);
+    if (w->ev_done) cudaEventDestroy(w->ev_done);
     for (auto& e : w->ev) cudaEventDestroy(e);
   }
   delete w;
@@ -170,11 +177,11 @@ static int check_params(const fm_params* p, Params* out) {
 static BatchDev make_batch(Workspace* w, const int32_t* d_q_tok, const int32_t* d_q_off, int64_t n_q, int64_t n_tok) {
   BatchDev b{};
   b.q_tok_in = d_q_tok; b.q_off = d_q_off; b.n_q = (int32_t)n_q; b.n_tok = (int32_t)n_tok;
-  b.pat = w->pat; b.chain_q = w->chain_q; b.qmeta = w->qmeta; b.tbl = w->tbl; b.cmin_tab = w->cmin_tab; b.qmask = w->qmask; b.wq = w->cap_wq ? w->wq : nullptr; b.peq64 = w->peq64;
+  b.pat = w->pat; b.chain_q = w->chain_q; b.qmeta = w->qmeta; b.tbl = w->tbl; b.cmin_tab = w->cmin_tab; b.cmin64 = w->cmin64; b.qmask = w->qmask; b.wq = w->cap_wq ? w->wq : nullptr; b.wextra = w->wextra; b.peq64 = w->peq64;
   b.span_slice = w->span_slice; b.span_cap = w->cap_spans;
-  b.sl_start = w->sl_start; b.sl_rec = w->sl_rec; b.slice_cap = w->cap_slices;
-  b.hkey = w->hkey; b.hlm = w->hlm; b.hmask = w->hsize - 1;
-  b.surv = w->surv; b.surv_len = w->surv_len; b.surv_cap = w->cap_surv;
+  b.sl_start = w->sl_start; b.sl_rec = w->sl_rec; b.sm_rec = w->sm_rec; b.slice_cap = w->cap_slices;
+  b.hkey = w->hkey; b.hlm = w->hlm; b.hmask = w->hs_use - 1;
+  b.surv = w->surv; b.surv_len = w->surv_len; b.surv_cap = std::min<int64_t>(w->cap_surv, w->hs_use / 4);  // load factor <= 1/4
   b.q_cnt = w->q_cnt; b.q_base = w->q_base; b.rec = w->rec; b.heapbuf = w->heapbuf; b.acc_cnt = w->acc_cnt;
   b.ctr = w->ctr;
   if (w->real_active) { b.q_real = w->d_q_real; b.q_gap = w->d_q_gap; b.itok_dist = w->d_itok_dist; b.n_itok = w->n_itok; }
@@ -186,10 +193,19 @@ static BatchDev make_batch(Workspace* w, const int32_t* d_q_tok, const int32_t* 
 // overflowed, which later kernels detect through the counters and skip).
 static int launch_shard(Index* ix, Workspace* w, const int32_t* d_q_tok, const int32_t* d_q_off, int64_t n_q, int64_t n_tok,
                         const Params& pr, cudaStream_t st, int* launches) {
+  // The dedup table is cleared per batch, so only as much of it is used as the previous batch on this
+  // workspace suggests (twice its survivors at load factor 1/4; a batch that outgrows it is rerun on the
+  // whole table by the overflow path).
+  {
+    const int64_t hint = w->surv_hint >= 0 ? w->surv_hint : n_q / 2;
+    uint32_t hs = 1u << 18;
+    while (hs < w->hsize && (int64_t)hs < 4 * (2 * hint + 32768)) hs <<= 1;
+    w->hs_use = hs;
+  }
   BatchDev b = make_batch(w, d_q_tok, d_q_off, n_q, n_tok);
   FM_CUDA(cudaMemsetAsync(w->ctr, 0, sizeof(Counters), st));
-  FM_CUDA(cudaMemsetAsync(w->hkey, 0xff, (size_t)w->hsize * sizeof(unsigned long long), st));
-  FM_CUDA(cudaMemsetAsync(w->hlm, 0, (size_t)w->hsize * sizeof(unsigned int), st));
+  FM_CUDA(cudaMemsetAsync(w->hkey, 0xff, (size_t)w->hs_use * sizeof(unsigned long long), st));
+  FM_CUDA(cudaMemsetAsync(w->hlm, 0, (size_t)w->hs_use * sizeof(unsigned int), st));
   if (ix->profiling) cudaEventRecord(w->ev[0], st);
   if (!w->bounds_valid || memcmp(&w->bounds_params, &pr, sizeof(Params)) != 0) {  // per-length bound tables follow the parameters
     launch_bounds(ix->dev, b, pr, st);
@@ -219,20 +235,33 @@ static int initial_worklists(Index* ix, Workspace* w, int64_t n_q, int64_t n_tok
   return ensure_survivors(w, std::max<int64_t>(1 << 18, 8 * n_q));
 }
 
-// Reads the counters back (one stream sync). Returns 1 if a worklist overflowed and was regrown
-// (the caller reruns the batch), 0 if the batch is complete, <0 on error (-rc).
-static int sync_and_check(Workspace* w, cudaStream_t st, int attempt, int* retries) {
-  cudaError_t e = cudaMemcpyAsync(w->h_ctr, w->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+// Behind a batch: read the counters back and mark the point with the workspace's event.
+static int enqueue_done(Workspace* w, cudaStream_t st) {
+  FM_CUDA(cudaMemcpyAsync(w->h_ctr, w->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  FM_CUDA(cudaEventRecord(w->ev_done, st));
+  return FM_OK;
+}
+
+// Waits for that point (not for anything enqueued on the stream afterwards). Returns 1 if a worklist
+// overflowed and was regrown (the caller reruns the batch), 0 if the batch is complete, <0 on error (-rc).
+static int wait_and_check(Workspace* w, int attempt, int* retries) {
+  cudaError_t e = cudaEventSynchronize(w->ev_done);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return -cuda_fail(e, "batch execution");
-  if (!w->h_ctr->overflow) return 0;
+  if (!w->h_ctr->overflow) {
+    w->surv_hint = (int64_t)w->h_ctr->n_surv;
+    return 0;
+  }
   if (attempt >= 8) { set_error("workspace overflow persists"); return -FM_ERR_NOMEM; }
   (*retries)++;
   int rc;
-  const int64_t need_slices = (int64_t)(w->h_ctr->slice_elem >> kElemBits);
+  const int64_t need_slices = std::max<int64_t>((int64_t)(w->h_ctr->slice_elem >> kElemBits), (int64_t)w->h_ctr->n_small);
   if (need_slices > w->cap_slices && (rc = ensure_slices(w, need_slices + need_slices / 8 + 1024))) return -rc;
-  if ((w->h_ctr->overflow & 2u) && (rc = ensure_survivors(w, w->cap_surv * 4))) return -rc;
+  if (w->h_ctr->overflow & 2u) {
+    if (w->hs_use < w->hsize) w->surv_hint = w->cap_surv;  // first the whole table ...
+    else if ((rc = ensure_survivors(w, w->cap_surv * 4))) return -rc;  // ... then a larger one
+    else w->surv_hint = w->cap_surv;
+  }
   const int64_t need_spans = (int64_t)((w->h_ctr->slice_elem & ((1ull << kElemBits) - 1)) / kSpanHost) + 2;
   if (need_spans > w->cap_spans && (rc = ensure_spans(w, need_spans + need_spans / 8))) return -rc;
   return 1;
@@ -265,30 +294,55 @@ static void finish_profile(Index* ix, Workspace* w, int64_t n_q, int64_t n_tok, 
   cudaEventElapsedTime(&ms, w->ev[5], w->ev[6]); p.ms_replay = ms;
   cudaEventElapsedTime(&ms, w->ev[0], w->ev[6]); p.ms_total = ms;
   p.n_queries = n_q; p.n_query_tokens = n_tok;
-  p.n_slices = (int64_t)(w->h_ctr->slice_elem >> kElemBits);
+  p.n_slices = (int64_t)(w->h_ctr->slice_elem >> kElemBits) + (int64_t)w->h_ctr->n_small;
   p.n_elements = (int64_t)(w->h_ctr->slice_elem & ((1ull << kElemBits) - 1));
   p.n_survivors = w->h_ctr->n_surv;
+  p.n_stage2 = w->h_ctr->n_stage2;
   p.n_matches = w->h_ctr->n_matches;
   p.launches = launches; p.retries = retries;
   std::lock_guard<std::mutex> g(ix->mu);
   ix->last_profile = p;
 }
 
-static int match_device(Index* ix, Workspace* w, const int32_t* d_q_tok, const int32_t* d_q_off, int64_t n_q, int64_t n_tok,
-                        const Params& pr, int64_t cap, fm_match* d_out, int32_t* d_out_count, cudaStream_t st) {
-  int rc, launches = 0, retries = 0;
-  w->real_active = false;
-  if ((rc = initial_worklists(ix, w, n_q, n_tok))) return rc;
+// Device-resident batch: enqueue the whole pipeline on the caller's stream; the ticket is completed by
+// finish_device (waits for the batch's own event, reruns after regrowing a worklist that overflowed).
+struct DeviceJob {
+  Workspace* w = nullptr;
+  const int32_t* d_q_tok = nullptr;
+  const int32_t* d_q_off = nullptr;
+  int64_t n_q = 0, n_tok = 0, cap = 0;
+  fm_match* d_out = nullptr;
+  int32_t* d_out_count = nullptr;
+  cudaStream_t st = nullptr;
+  int launches = 0;
+};
+
+static int enqueue_device(Index* ix, DeviceJob& j, const Params& pr) {
+  int rc;
+  if ((rc = launch_shard(ix, j.w, j.d_q_tok, j.d_q_off, j.n_q, j.n_tok, pr, j.st, &j.launches))) return rc;
+  if ((rc = run_replay(ix, j.w, j.w->rec, j.w->q_cnt, j.w->q_base, j.w->heapbuf, j.w->sort_key, j.w->sort_key2, j.w->sort_idx, j.w->acc_cnt,
+                       j.w->mid_q, j.w->heavy_q, j.d_q_off, j.n_q, pr, j.cap, j.d_out, j.d_out_count, j.st, &j.launches)))
+    return rc;
+  return enqueue_done(j.w, j.st);
+}
+
+static int submit_device(Index* ix, DeviceJob& j, const Params& pr) {
+  int rc;
+  j.w->real_active = false;
+  if ((rc = ensure_queries(j.w, j.n_q, j.n_tok, false)) || (rc = initial_worklists(ix, j.w, j.n_q, j.n_tok))) return rc;
+  return enqueue_device(ix, j, pr);
+}
+
+static int finish_device(Index* ix, DeviceJob& j, const Params& pr) {
+  int retries = 0;
   for (int attempt = 0;; attempt++) {
-    if ((rc = launch_shard(ix, w, d_q_tok, d_q_off, n_q, n_tok, pr, st, &launches))) return rc;
-    if ((rc = run_replay(ix, w, w->rec, w->q_cnt, w->q_base, w->heapbuf, w->sort_key, w->sort_key2, w->sort_idx, w->acc_cnt, w->mid_q, w->heavy_q, d_q_off, n_q, pr, cap, d_out, d_out_count,
-                         st, &launches)))
-      return rc;
-    const int again = sync_and_check(w, st, attempt, &retries);
+    const int again = wait_and_check(j.w, attempt, &retries);
     if (again < 0) return -again;
     if (!again) break;
+    int rc;
+    if ((rc = enqueue_device(ix, j, pr))) return rc;
   }
-  finish_profile(ix, w, n_q, n_tok, launches, retries);
+  finish_profile(ix, j.w, j.n_q, j.n_tok, j.launches, retries);
   return FM_OK;
 }
 
@@ -361,9 +415,9 @@ static int launch_host_chunk(Index* ix, HostChunk& c, const int32_t* q_tokens, c
   if ((rc = run_replay(ix, w, w->rec, w->q_cnt, w->q_base, w->heapbuf, w->sort_key, w->sort_key2, w->sort_idx, w->acc_cnt, w->mid_q, w->heavy_q, w->d_q_off,
                        c.nq, pr, cap, w->d_out, w->d_out_count, st, &c.launches)))
     return rc;
-  FM_CUDA(cudaMemcpyAsync(w->h_ctr, w->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
   FM_CUDA(cudaMemcpyAsync(out + c.q0 * cap, w->d_out, c.nq * cap * sizeof(fm_match), cudaMemcpyDeviceToHost, st));
   FM_CUDA(cudaMemcpyAsync(out_count + c.q0, w->d_out_count, c.nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if ((rc = enqueue_done(w, st))) return rc;
   if (g_host_timing) {
     const double t2 = now_ms();
     cudaStreamSynchronize(st);
@@ -381,16 +435,18 @@ static int finish_host_chunk(Index* ix, HostChunk& c, const Params& pr, int64_t 
   cudaStream_t st = w->stream;
   int retries = 0;
   for (int attempt = 0;; attempt++) {
-    const int again = sync_and_check(w, st, attempt, &retries);
+    const int again = wait_and_check(w, attempt, &retries);
     if (again < 0) return -again;
     if (!again) break;
     int rc;
+    FM_CUDA(cudaMemsetAsync(w->d_out, 0, c.nq * cap * sizeof(fm_match), st));
     if ((rc = launch_shard(ix, w, w->d_q_tok, w->d_q_off, c.nq, c.ntok, pr, st, &c.launches))) return rc;
     if ((rc = run_replay(ix, w, w->rec, w->q_cnt, w->q_base, w->heapbuf, w->sort_key, w->sort_key2, w->sort_idx, w->acc_cnt, w->mid_q, w->heavy_q,
                          w->d_q_off, c.nq, pr, cap, w->d_out, w->d_out_count, st, &c.launches)))
       return rc;
     FM_CUDA(cudaMemcpyAsync(out + c.q0 * cap, w->d_out, c.nq * cap * sizeof(fm_match), cudaMemcpyDeviceToHost, st));
     FM_CUDA(cudaMemcpyAsync(out_count + c.q0, w->d_out_count, c.nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if ((rc = enqueue_done(w, st))) return rc;
   }
   finish_profile(ix, w, c.nq, c.ntok, c.launches, retries);
   return FM_OK;
@@ -542,25 +598,98 @@ int fm_index_set_real(fm_index* index, const int32_t* real, const int32_t* gaps,
   return set_real(ix, real, gaps, sent_off, n_sent);
 }
 
-int fm_match_batch_device(fm_index* index, const int32_t* d_q_tokens, const int32_t* d_q_off, int64_t n_q,
-                          int64_t n_query_tokens, const fm_params* params, int64_t cap, fm_match* d_out, int32_t* d_out_count,
-                          void* stream) {
+// ---- submit / wait: the asynchronous form of the two batch calls. A ticket owns one workspace; several
+// tickets may be in flight on one index, so the host->device copy of batch i+1 and the device->host copy
+// of batch i-1 overlap the kernels of batch i (the reference overlaps I/O and matching the same way with
+// its queue of futures, cli/src/FuzzyMatch-cli.cc:112-193).
+struct fm_ticket {
+  Index* ix = nullptr;
+  Params pr{};
+  int64_t cap = 0;
+  bool host = false;
+  DeviceJob dev;
+  HostChunk chunk;
+  fm_match* out = nullptr;
+  int32_t* out_count = nullptr;
+};
+
+static void drop_ticket(fm_ticket* t) {  // after an error: nothing of the batch may still run on the workspace
+  Workspace* w = t->host ? t->chunk.w : t->dev.w;
+  if (w) {
+    cudaStreamSynchronize(t->host ? w->stream : t->dev.st);
+    release(t->ix, w);
+  }
+  delete t;
+}
+
+int fm_match_batch_device_submit(fm_index* index, const int32_t* d_q_tokens, const int32_t* d_q_off, int64_t n_q,
+                                 int64_t n_query_tokens, const fm_params* params, int64_t cap, fm_match* d_out,
+                                 int32_t* d_out_count, void* stream, fm_ticket** ticket) {
   Index* ix = reinterpret_cast<Index*>(index);
   Params pr;
   int rc;
-  if (!ix || n_q < 0 || cap < 1 || n_q > (1 << 20) || n_query_tokens > (int64_t(1) << 25)) {
-    set_error("bad argument (device batches hold at most 2^20 queries / 2^25 tokens)");
+  if (ticket) *ticket = nullptr;
+  if (!ix || !ticket || n_q < 1 || cap < 1 || n_q > (1 << 20) || n_query_tokens > (int64_t(1) << 25)) {
+    set_error("bad argument (device batches hold 1 .. 2^20 queries and at most 2^25 tokens)");
     return FM_ERR_INVALID;
   }
   if ((rc = check_params(params, &pr))) return rc;
-  if (n_q == 0) return FM_OK;
   FM_CUDA(cudaSetDevice(ix->device));
-  Workspace* w = acquire(ix);
-  struct Releaser { Index* ix; Workspace* w; ~Releaser() { release(ix, w); } } rel{ix, w};
-  if ((rc = ensure_base(w)) || (rc = ensure_queries(w, n_q, n_query_tokens, false))) return rc;
-  rc = match_device(ix, w, d_q_tokens, d_q_off, n_q, n_query_tokens, pr, cap, d_out, d_out_count, static_cast<cudaStream_t>(stream));
-  if (rc) cudaStreamSynchronize(static_cast<cudaStream_t>(stream));  // nothing of this call may still run on the workspace
-  return rc;
+  fm_ticket* t = new fm_ticket();
+  t->ix = ix; t->pr = pr; t->cap = cap; t->host = false;
+  DeviceJob& j = t->dev;
+  j.w = acquire(ix);
+  j.d_q_tok = d_q_tokens; j.d_q_off = d_q_off; j.n_q = n_q; j.n_tok = n_query_tokens; j.cap = cap;
+  j.d_out = d_out; j.d_out_count = d_out_count; j.st = static_cast<cudaStream_t>(stream);
+  if ((rc = ensure_base(j.w)) || (rc = submit_device(ix, j, pr))) { drop_ticket(t); return rc; }
+  *ticket = t;
+  return FM_OK;
+}
+
+int fm_match_batch_submit(fm_index* index, const int32_t* q_tokens, const int64_t* q_off, int64_t n_q, const fm_params* params,
+                          int64_t cap, fm_match* out, int32_t* out_count, fm_ticket** ticket) {
+  Index* ix = reinterpret_cast<Index*>(index);
+  Params pr;
+  int rc;
+  if (ticket) *ticket = nullptr;
+  if (!ix || !ticket || n_q < 1 || cap < 1 || !q_off || !out || !out_count) { set_error("bad argument"); return FM_ERR_INVALID; }
+  const int64_t ntok = q_off[n_q] - q_off[0];
+  if (n_q > (1 << 18) || ntok < 0 || ntok > (int64_t(1) << 22)) {
+    set_error("a submitted batch holds at most 2^18 queries / 2^22 tokens: split it or use fm_match_batch");
+    return FM_ERR_INVALID;
+  }
+  if ((rc = check_params(params, &pr))) return rc;
+  FM_CUDA(cudaSetDevice(ix->device));
+  fm_ticket* t = new fm_ticket();
+  t->ix = ix; t->pr = pr; t->cap = cap; t->host = true; t->out = out; t->out_count = out_count;
+  HostChunk& c = t->chunk;
+  c.w = acquire(ix);
+  c.q0 = 0; c.nq = n_q; c.ntok = ntok;
+  if ((rc = ensure_base(c.w)) || (rc = launch_host_chunk(ix, c, q_tokens, q_off, pr, cap, out, out_count, RealInputs()))) {
+    drop_ticket(t);
+    return rc;
+  }
+  *ticket = t;
+  return FM_OK;
+}
+
+int fm_ticket_wait(fm_ticket* t) {
+  if (!t) { set_error("NULL ticket"); return FM_ERR_INVALID; }
+  cudaSetDevice(t->ix->device);
+  const int rc = t->host ? finish_host_chunk(t->ix, t->chunk, t->pr, t->cap, t->out, t->out_count) : finish_device(t->ix, t->dev, t->pr);
+  if (rc) { drop_ticket(t); return rc; }
+  release(t->ix, t->host ? t->chunk.w : t->dev.w);
+  delete t;
+  return FM_OK;
+}
+
+int fm_match_batch_device(fm_index* index, const int32_t* d_q_tokens, const int32_t* d_q_off, int64_t n_q,
+                          int64_t n_query_tokens, const fm_params* params, int64_t cap, fm_match* d_out, int32_t* d_out_count,
+                          void* stream) {
+  if (n_q == 0 && index && cap >= 1 && params) return FM_OK;
+  fm_ticket* t = nullptr;
+  const int rc = fm_match_batch_device_submit(index, d_q_tokens, d_q_off, n_q, n_query_tokens, params, cap, d_out, d_out_count, stream, &t);
+  return rc ? rc : fm_ticket_wait(t);
 }
 
 int fm_shard_score_device(fm_index* index, const int32_t* d_q_tokens, const int32_t* d_q_off, int64_t n_q,
@@ -583,7 +712,8 @@ int fm_shard_score_device(fm_index* index, const int32_t* d_q_tokens, const int3
   for (int attempt = 0;; attempt++) {
     if ((rc = launch_shard(ix, w, d_q_tokens, d_q_off, n_q, n_query_tokens, pr, st, &launches))) return rc;
     if (ix->profiling) cudaEventRecord(w->ev[6], st);
-    const int again = sync_and_check(w, st, attempt, &retries);
+    if ((rc = enqueue_done(w, st))) return rc;
+    const int again = wait_and_check(w, attempt, &retries);
     if (again < 0) return -again;
     if (!again) break;
   }
@@ -659,7 +789,8 @@ int fm_get_profile(const fm_index* index, fm_profile* out) {
 
 // Debug hooks (not part of the public header, used while bringing the kernels up and kept for
 // stage-level inspection): fm_debug_last_slices copies the range slices of the last batch run on the
-// first workspace, rec = int4 (query, sa_begin, match_len | p << 16, size) per slice;
+// first workspace, rec = int4 (query, sa_begin, match_len | p << 10 | mult << 20, size) per slice (the flattened
+// ones first, then the small ones with start = -1);
 // fm_debug_last_survivors copies its (query, sentence start, table slot, arrival index) records and the
 // max match length recorded for each.
 extern "C" int64_t fm_debug_last_slices(fm_index* index, int32_t* rec, int64_t* start, int64_t cap) {
@@ -668,10 +799,13 @@ extern "C" int64_t fm_debug_last_slices(fm_index* index, int32_t* rec, int64_t* 
   Workspace* w = ix->pool[0];
   cudaSetDevice(ix->device);
   cudaDeviceSynchronize();
-  const int64_t n = std::min<int64_t>(cap, (int64_t)(w->h_ctr->slice_elem >> kElemBits));
-  cudaMemcpy(rec, w->sl_rec, n * sizeof(int4), cudaMemcpyDeviceToHost);
-  cudaMemcpy(start, w->sl_start, n * sizeof(long long), cudaMemcpyDeviceToHost);
-  return n;
+  const int64_t n_big = std::min<int64_t>(cap, (int64_t)(w->h_ctr->slice_elem >> kElemBits));
+  const int64_t n_small = std::min<int64_t>(cap - n_big, (int64_t)w->h_ctr->n_small);
+  cudaMemcpy(rec, w->sl_rec, n_big * sizeof(int4), cudaMemcpyDeviceToHost);
+  cudaMemcpy(start, w->sl_start, n_big * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaMemcpy(rec + 4 * n_big, w->sm_rec, n_small * sizeof(int4), cudaMemcpyDeviceToHost);  // (no flattened start)
+  for (int64_t i = 0; i < n_small; i++) start[n_big + i] = -1;
+  return n_big + n_small;
 }
 extern "C" int64_t fm_debug_last_survivors(fm_index* index, int32_t* surv, uint32_t* lm, int64_t cap) {
   Index* ix = reinterpret_cast<Index*>(index);

@@ -59,13 +59,14 @@ static int upload(const std::vector<T>& h, size_t extra, Index* ix, int blk, con
 // they sit in HBM, then the host-side tables. Loading is read + upload: no sort, no hashing.
 static const char kMagic[8] = {'F', 'M', 'B', '2', '0', '0', 'I', 1};
 static const int64_t kFileVersion = 2;  // 2: wide signatures (walk records of long sentences carry a wsig row)
-enum { BLK_TOK = 0, BLK_SA = 1, BLK_WALK = 2, BLK_QVA = 3, BLK_SID = 4, BLK_IDF = 5, BLK_BG = 6, BLK_TG = 7, BLK_REAL = 8, BLK_GAP = 9, BLK_NEXT = 10, BLK_WSIG = 11, N_BLK = 12 };
+enum { BLK_TOK = 0, BLK_SA = 1, BLK_WALK = 2, BLK_QVA = 3, BLK_SID = 4, BLK_IDF = 5, BLK_BG = 6, BLK_TG = 7, BLK_REAL = 8, BLK_GAP = 9, BLK_NEXT = 10, BLK_WSIG = 11, BLK_START = 12, N_BLK = 13 };
 
 static void bind_blocks(Index* ix) {
   IndexDev& d = ix->dev;
   d.tok = static_cast<const int32_t*>(ix->d_blocks[BLK_TOK]);
   d.sa_pos = static_cast<const int32_t*>(ix->d_blocks[BLK_SA]);
-  d.sa_walk = static_cast<const int4*>(ix->d_blocks[BLK_WALK]);
+  d.sa_rec = static_cast<const uint2*>(ix->d_blocks[BLK_WALK]);
+  d.sa_start = static_cast<const int32_t*>(ix->d_blocks[BLK_START]);
   d.sa_next = static_cast<const int32_t*>(ix->d_blocks[BLK_NEXT]);
   d.qva = static_cast<const int32_t*>(ix->d_blocks[BLK_QVA]);
   d.sid_at = static_cast<const int32_t*>(ix->d_blocks[BLK_SID]);
@@ -110,7 +111,9 @@ static bool header_ok(const int64_t* hdr, const int64_t* blk, int n_blk) {
   if (vocab < 2 || vocab > (int64_t(1) << 30) || max_tok < 1 || max_tok > FM_MAX_TOKENS) return false;
   if (n_sent < 0 || n_suf < 0 || n_buf < 8 || n_buf >= (int64_t(1) << 31) || n_sent > n_suf || n_suf > n_buf) return false;
   if (!pow2m1(bgm) || !pow2m1(tgm) || n_blk != N_BLK) return false;
-  if (blk[BLK_TOK] != n_buf * 4 || blk[BLK_SA] < n_suf * 4 || blk[BLK_NEXT] < n_suf * 4 || blk[BLK_WALK] < n_suf * 16) return false;
+  if (blk[BLK_TOK] != n_buf * 4 || blk[BLK_SA] < n_suf * 4 || blk[BLK_NEXT] < n_suf * 4 || blk[BLK_WALK] < (n_suf + 8) * 8 ||
+      blk[BLK_START] < n_suf * 4)
+    return false;
   if (blk[BLK_QVA] != (vocab + 1) * 4 || blk[BLK_IDF] != vocab * 4 || blk[BLK_SID] != (n_buf / 4 + 1) * 4) return false;
   if (blk[BLK_BG] != (bgm + 1) * 16 || blk[BLK_TG] != (tgm + 1) * 16) return false;
   if (blk[BLK_WSIG] % (kWideWords * 4) != 0 || blk[BLK_WSIG] / (kWideWords * 4) > n_sent) return false;
@@ -232,22 +235,23 @@ __global__ void fm_build_sentence_kernel(const int32_t* __restrict__ tok, const 
   int n = 0;
   if (row < 0) {
     for (int t; (t = tok[st + n]) != 0; n++) sg |= 1ull << sig_bit(t);
+    sg |= (unsigned long long)n;  // bits 0-5: the length (<= kWideMin < 63)
   } else {
     uint32_t* w = wsig + (size_t)row * kWideWords;
     for (int t; (t = tok[st + n]) != 0; n++) {
       const unsigned b = wsig_bit(t);
       w[b >> 5] |= 1u << (b & 31);
     }
-    sg = (unsigned long long)(unsigned)row;
+    sg = ((unsigned long long)(unsigned)row << 32) | ((unsigned long long)n << 6) | 63ull;
   }
-  sig[s] = sg;
+  sig[s] = sg;  // the walk record of every suffix of this sentence
   sent_len[s] = n;
   sid_at[st >> 2] = s;
 }
 
 __global__ void fm_build_walk_kernel(const int32_t* __restrict__ sa_pos, long long n_suf, const int32_t* __restrict__ sent_start,
                                      int n_sent, const unsigned long long* __restrict__ sig,
-                                     const int32_t* __restrict__ sent_len, int4* sa_walk) {
+                                     uint2* sa_rec, int32_t* sa_start) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_suf) return;
   const int pos = sa_pos[i];
@@ -257,7 +261,8 @@ __global__ void fm_build_walk_kernel(const int32_t* __restrict__ sa_pos, long lo
     if (sent_start[mid] <= pos) a = mid; else e = mid;
   }
   const unsigned long long sg = sig[a];
-  sa_walk[i] = make_int4(sent_start[a], sent_len[a], (int)(unsigned)sg, (int)(unsigned)(sg >> 32));
+  sa_rec[i] = make_uint2((unsigned)sg, (unsigned)(sg >> 32));
+  sa_start[i] = sent_start[a];
 }
 
 // sa_next[i] = token at depth 3 of suffix i (0 if it has fewer than four tokens)
@@ -375,7 +380,7 @@ static int derive_next(Index* ix) {
   return FM_OK;
 }
 
-// Builds sa_walk, sa_next, sid_at and the two directories on the device from tok + sa_pos (already uploaded).
+// Builds sa_rec, sa_start, sa_next, sid_at and the two directories on the device from tok + sa_pos (already uploaded).
 static int build_on_device(Index* ix, const std::vector<int32_t>& sent_start, const std::vector<int32_t>& wide_row, int64_t n_wide) {
   IndexDev& d = ix->dev;
   const long long n_suf = ix->n_suf;
@@ -392,7 +397,8 @@ static int build_on_device(Index* ix, const std::vector<int32_t>& sent_start, co
   FM_CUDA(cudaMemcpy(d_start, sent_start.data(), (size_t)(n_sent + 1) * 4, cudaMemcpyHostToDevice));
   int rc;
   if ((rc = dev_alloc(ix, BLK_SID, (size_t)(ix->n_buf / 4) + 1, 0xff, &d.sid_at)) ||
-      (rc = dev_alloc(ix, BLK_WALK, (size_t)n_suf + 4, 0, &d.sa_walk)) || (rc = derive_next(ix)) ||
+      (rc = dev_alloc(ix, BLK_WALK, (size_t)n_suf + 8, 0, &d.sa_rec)) || (rc = dev_alloc(ix, BLK_START, (size_t)n_suf + 4, 0, &d.sa_start)) ||
+      (rc = derive_next(ix)) ||
       (rc = dev_alloc(ix, BLK_WSIG, (size_t)n_wide * kWideWords, 0, &d.wsig)))
     return rc;
   d.n_wide = (int32_t)n_wide;
@@ -404,7 +410,7 @@ static int build_on_device(Index* ix, const std::vector<int32_t>& sent_start, co
                                                              const_cast<int32_t*>(d.sid_at));
   unsigned long long counts[2] = {0, 0};
   if (n_suf > 0) {
-    fm_build_walk_kernel<<<gs, tb>>>(d.sa_pos, n_suf, d_start, n_sent, d_sig, d_len, const_cast<int4*>(d.sa_walk));
+    fm_build_walk_kernel<<<gs, tb>>>(d.sa_pos, n_suf, d_start, n_sent, d_sig, const_cast<uint2*>(d.sa_rec), const_cast<int32_t*>(d.sa_start));
     fm_count_runs_kernel<<<gs, tb>>>(d.tok, d.sa_pos, n_suf, d_counts);
   }
   FM_CUDA(cudaMemcpy(counts, d_counts, 16, cudaMemcpyDeviceToHost));

@@ -17,10 +17,12 @@ namespace fm {
 //                         (multiple of 4 tokens) and is followed by >= 1 zero (the separator); the zero
 //                         sorts before every word id, so "shorter suffix first" needs no length check.
 // sa_pos   int32[n_suf]   suffix array: absolute offset into tok of each suffix, sorted.
-// sa_walk  int4[n_suf]    what the range walk needs per suffix, one 128-bit load: (sentence start in tok,
-//                         sentence length, 64-bit word signature of the sentence: bit sig_bit(w) set for
-//                         every word w). The signature gives an upper bound on the coverage without
-//                         touching the sentence.
+// sa_rec   uint2[n_suf]   what the range walk tests per suffix, 8 bytes so that one 256-bit load brings four:
+//                         bits 0-5 = sentence length (<= kWideMin), bits 6-63 = 58-bit word signature of the
+//                         sentence (bit sig_bit(w) set for every word w): an upper bound on the coverage
+//                         without touching the sentence. Long sentences: bits 0-5 = 63, bits 6-15 = length,
+//                         high word = row of the sentence's wide signature (wsig).
+// sa_start int32[n_suf]   sentence start in tok of each suffix; read only for elements that pass the test.
 // sa_next  int32[n_suf]   token at depth 3 of each suffix (tok[sa_pos[k] + 3], 0 when the suffix is shorter):
 //                         the binary search that narrows a trigram range -- the only level where ranges are
 //                         still wide -- reads ONE array instead of sa_pos -> tok (two dependent misses).
@@ -39,7 +41,8 @@ namespace fm {
 struct IndexDev {
   const int32_t* tok;
   const int32_t* sa_pos;
-  const int4* sa_walk;
+  const uint2* sa_rec;
+  const int32_t* sa_start;
   const int32_t* sa_next;
   const int32_t* qva;
   const int4* bg_tab;
@@ -62,12 +65,12 @@ struct IndexDev {
 // per-query metadata written by the prepare kernel
 //   x = pattern length p (0 if the query is skipped), y = effective min_subseq_length,
 //   z = offset of the pattern in the token arrays,
-//   w = bit0: query takes part
+//   w = bit0: query takes part; bits 8..: max(0, (largest number of pattern positions on one signature bit) - 3)
 typedef int4 QMeta;
 static const int kQValid = 1;
 
-// word -> signature bit (must be identical on host and device)
-__host__ __device__ inline unsigned sig_bit(int w) { return ((unsigned)w * 0x9E3779B1u) >> 26; }
+// word -> signature bit 6..63 (must be identical on host and device); bits 0-5 of a record hold the length
+__host__ __device__ inline unsigned sig_bit(int w) { return 6u + (((((unsigned)w * 0x9E3779B1u) >> 16) * 58u) >> 16); }
 // sentences longer than this carry a 1024-bit signature (wsig) instead of the 64-bit one
 static const int kWideMin = 48;
 static const int kWideWords = 32;  // 32-bit words per wide signature
@@ -97,9 +100,13 @@ struct Counters {
   unsigned int n_matches;
   unsigned int n_heavy;  // queries with more than kWarpMax scored candidates (CTA each)
   unsigned int n_mid;    // queries with 2..kWarpMax scored candidates (warp each)
+  unsigned int n_stage2;  // elements that passed stage 1 of the gather (profiling)
+  unsigned int n_small;  // slices of at most kSmallSlice elements (their own list, a lane each)
   unsigned int n_long;  // bit0 / bit1: some survivor's pattern is too long for the first / second scoring kernel
 };
 static const int kElemBits = 38;
+static const int kSmallSlice = 4;
+static const int kSpan = 512;  // flattened elements per gather work unit
 
 // per-batch workspace pointers (device)
 struct BatchDev {
@@ -118,12 +125,15 @@ struct BatchDev {
   QMeta* qmeta;      // [n_q]
   int2* tbl;         // [4*n_tok] per-query open-addressing tables: (word, distinct_idx | count<<16)
   const uint16_t* cmin_tab; // [(max_tokens+1) << 10] per (pattern length << 10 | sentence length): smallest coverage that passes
-  int4* qmask;       // [2*n_q] per query: bit-sliced pattern-position counts per signature bit (B0,B1 | B2,extra,wide extra)
+  const uint16_t* cmin64;   // [(max_tokens+1) << 6] the same for the 6-bit length field of a walk record (stage 1 of the gather)
+  int4* qmask;       // [n_q] per query, in record layout: planes (B0 lo, B0 hi, B1 lo, B1 hi) of min(pattern positions per signature bit, 3)
+  int32_t* wextra;   // [n_q] wide planes: (largest count on one wide bit) - 7, at least 0
   uint32_t* wq;      // [96*n_q] or NULL (index without wide signatures): the same three planes over the 1024 wide bits
   unsigned long long* peq64;  // [n_tok] patterns of <= 64 tokens: position mask of each distinct word, at q_off + distinct index
-  // search output
+  // search output: slices of more than kSmallSlice elements, flattened, and the small ones
   long long* sl_start;  // [slice_cap+1] first flattened element of each slice (ascending)
-  int4* sl_rec;         // [slice_cap] (q, sa_begin, match_len | p << 16, size)
+  int4* sl_rec;         // [slice_cap] (q, sa_begin, match_len | p << 10 | mult << 20, size)
+  int4* sm_rec;         // [slice_cap] same record, slices of <= kSmallSlice elements
   int64_t slice_cap;
   int32_t* span_slice;  // [span_cap] slice holding flattened element k*kSpan
   int64_t span_cap;
@@ -163,6 +173,9 @@ struct Workspace {
   cudaStream_t stream = nullptr;  // owned stream for the host-buffer API
   cudaStream_t stream2 = nullptr;  // side stream: the CTA-per-query replay runs next to the warp-per-query one
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_done = nullptr;  // recorded behind the counter read-back of a submitted batch
+  int64_t surv_hint = -1;         // survivors of the previous batch on this workspace: sizes the dedup table
+  uint32_t hs_use = 0;            // dedup-table slots cleared and used by the batch in flight (power of two <= hsize)
   // capacities
   int64_t cap_q = 0, cap_tok = 0, cap_slices = 0, cap_surv = 0, cap_out = 0;
   uint32_t hsize = 0;
@@ -176,6 +189,9 @@ struct Workspace {
   QMeta* qmeta = nullptr;
   int2* tbl = nullptr;
   uint16_t* cmin_tab = nullptr;
+  uint16_t* cmin64 = nullptr;
+  int32_t* wextra = nullptr;
+  int4* sm_rec = nullptr;
   int32_t* span_slice = nullptr;
   int64_t cap_spans = 0;
   Params bounds_params{};
@@ -225,8 +241,8 @@ struct Index {
   int64_t n_sent = 0, n_suf = 0, n_buf = 0;
   int64_t device_bytes = 0;
   int32_t vocab_size = 0, max_tokens = 0;
-  void* d_blocks[12] = {};
-  size_t blk_bytes[12] = {};
+  void* d_blocks[16] = {};
+  size_t blk_bytes[16] = {};
   int64_t n_sent_global = 0;
   int sm_count = 148;
   // workspaces

@@ -28,7 +28,6 @@
 namespace fm {
 
 #define FULL 0xffffffffu
-static const int kSpan = 256;  // flattened elements per gather work unit
 
 // ---------------------------------------------------------------- small device helpers
 
@@ -95,7 +94,11 @@ __device__ __forceinline__ float score_of(float cost) {
 // element. cmin_tab[(p << 10) | s] = smallest passing coverage, kNeedReject when (p, s) can never pass,
 // kNeedNoTable when the bounds must be evaluated per element (negative costs: not monotone).
 static const int kNeedReject = 0xffff, kNeedNoTable = 0xfffe;
-__global__ void __launch_bounds__(256) fm_bounds_kernel(int max_tokens, Params pr, uint16_t* cmin_tab) {
+// cmin64[(p << 6) | l] is the same table over the 6-bit length field of a walk record, in the form stage 1
+// of the gather compares against: the smallest passing coverage, kNeedReject, or 0 = "goes to stage 2"
+// for l = 63 (a long sentence: its real length and wide signature are looked at there) and when there is
+// no table.
+__global__ void __launch_bounds__(256) fm_bounds_kernel(int max_tokens, Params pr, uint16_t* cmin_tab, uint16_t* cmin64) {
   const int lane = threadIdx.x & 31;
   const int p = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) + 1;
   if (p > max_tokens) return;
@@ -112,6 +115,7 @@ __global__ void __launch_bounds__(256) fm_bounds_kernel(int max_tokens, Params p
       need = lo;
     }
     row[sl] = (uint16_t)need;
+    if (sl < 64) cmin64[(p << 6) | sl] = (uint16_t)(sl == 63 || need == kNeedNoTable ? 0 : (sl > kWideMin ? kNeedReject : need));
   }
 }
 
@@ -132,7 +136,7 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
   const int by_ratio = (int)__fmul_rn(pr.mr, (float)p);
   if (by_ratio > ml) ml = by_ratio;
   if (lane == 0) {
-    b.qmeta[q] = make_int4(valid ? p : 0, ml, off, valid ? kQValid : 0);
+    if (!valid) b.qmeta[q] = make_int4(0, ml, off, 0);
     b.q_cnt[q] = 0;
     if (q == 0) b.q_cnt[b.n_q] = 0;
   }
@@ -188,20 +192,23 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
     __syncwarp();
     c_lo = cnt[lane];
     c_hi = cnt[lane + 32];
-    // Position masks for the bit-parallel edit distance (p <= 64 here): peq64[off + d] has bit j set
-    // iff pattern[j] is the word with distinct index d.
-    unsigned long long* peq = s_peq[threadIdx.x >> 5];
-    peq[lane] = 0;
-    peq[lane + 32] = 0;
-    __syncwarp();
-    for (int j = lane; j < p; j += 32) {
-      const int w = b.pat[off + j];
-      int h = hash32((uint32_t)w) & (ts - 1);
-      while (wtbl[h].x != w) h = (h + 1) & (ts - 1);
-      atomicOr(&peq[wtbl[h].y & 0xffff], 1ull << j);
+    // Position masks for the bit-parallel edit distance of patterns of 33..64 tokens (shorter ones compare
+    // against the pattern in registers): peq64[off + d] has bit j set iff pattern[j] is the word with
+    // distinct index d.
+    if (p > 32) {
+      unsigned long long* peq = s_peq[threadIdx.x >> 5];
+      peq[lane] = 0;
+      peq[lane + 32] = 0;
+      __syncwarp();
+      for (int j = lane; j < p; j += 32) {
+        const int w = b.pat[off + j];
+        int h = hash32((uint32_t)w) & (ts - 1);
+        while (wtbl[h].x != w) h = (h + 1) & (ts - 1);
+        atomicOr(&peq[wtbl[h].y & 0xffff], 1ull << j);
+      }
+      __syncwarp();
+      for (int d = lane; d < distinct; d += 32) b.peq64[off + d] = peq[d];
     }
-    __syncwarp();
-    for (int d = lane; d < distinct; d += 32) b.peq64[off + d] = peq[d];
   } else {
     for (int j = lane; j < ts; j += 32) tbl[j] = make_int2(-1, 0);
     __syncwarp();
@@ -223,20 +230,17 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
       c_hi += bit == (unsigned)(lane + 32);
     }
   }
-  // Signature masks, bit-sliced: plane k holds bit k of the number of pattern positions that hash to
-  // each signature bit, so coverage <= popc(sig & B0) + 2 popc(sig & B1) + 4 popc(sig & B2); a bit with
-  // 8 or more positions (long patterns) is stored as 7 and `extra` covers the rest.
+  // Signature masks in the layout of a walk record (bits 6..63), bit-sliced: plane k holds bit k of
+  // min(count, 3), count = pattern positions on that signature bit, and mult = (largest count) - 3 (>= 0):
+  //   coverage <= popc(sig & B0) + 2 popc(sig & B1) + mult * popc(sig & B0 & B1)
+  // (exact while no bit collects more than three positions).
   {
-    const int k_lo = min(c_lo, 7), k_hi = min(c_hi, 7);
-    unsigned m[6];
+    const int k_lo = min(c_lo, 3), k_hi = min(c_hi, 3);
+    const unsigned a_lo = __ballot_sync(FULL, k_lo & 1), a_hi = __ballot_sync(FULL, k_hi & 1);
+    const unsigned a2_lo = __ballot_sync(FULL, k_lo & 2), a2_hi = __ballot_sync(FULL, k_hi & 2);
+    int mult = max(max(c_lo, c_hi) - 3, 0);
 #pragma unroll
-    for (int l = 0; l < 3; l++) {
-      m[2 * l] = __ballot_sync(FULL, (k_lo >> l) & 1);
-      m[2 * l + 1] = __ballot_sync(FULL, (k_hi >> l) & 1);
-    }
-    int extra = max(max(c_lo, c_hi) - 7, 0);
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) extra = max(extra, __shfl_xor_sync(FULL, extra, d));
+    for (int d = 16; d > 0; d >>= 1) mult = max(mult, __shfl_xor_sync(FULL, mult, d));
     // The same three planes over the 1024 bits of the wide signatures (sentences longer than kWideMin):
     // lane l owns signature bits [32 l, 32 l + 32), i.e. words 16 l .. 16 l + 15 of the packed counters.
     int wextra = 0;
@@ -274,8 +278,9 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
       for (int d = 16; d > 0; d >>= 1) wextra = max(wextra, __shfl_xor_sync(FULL, wextra, d));
     }
     if (lane == 0) {
-      b.qmask[2 * q + 0] = make_int4(m[0], m[1], m[2], m[3]);
-      b.qmask[2 * q + 1] = make_int4(m[4], m[5], extra, wextra);
+      b.qmask[q] = make_int4((int)a_lo, (int)a_hi, (int)a2_lo, (int)a2_hi);
+      b.qmeta[q] = make_int4(p, ml, off, kQValid | (mult << 8));
+      if (b.wq) b.wextra[q] = wextra;
     }
   }
 }
@@ -305,10 +310,18 @@ __device__ __forceinline__ void push_slice(SliceBuf& sb, int& nbuf, int beg, int
   sb.lm[nbuf][threadIdx.x] = lm;
   nbuf++;
 }
-__device__ __forceinline__ void flush_slices(const BatchDev& b, SliceBuf& sb, int& nbuf, int lane, int q, int p) {
-  int elems = 0;
-  for (int k = 0; k < nbuf; k++) elems += sb.sz[k][threadIdx.x];
-  const unsigned long long mine = ((unsigned long long)nbuf << kElemBits) | (unsigned long long)(unsigned)elems;
+// Slices of more than kSmallSlice elements go to the flattened list (the gather walks them with whole
+// warps); the many tiny ones -- three quarters of all slices hold a single suffix -- go to their own
+// list, where a lane takes a slice. `tag` = p << 10 | mult << 20 of the query.
+__device__ __forceinline__ void flush_slices(const BatchDev& b, SliceBuf& sb, int& nbuf, int lane, int q, int tag) {
+  int elems = 0, n_big = 0;
+  for (int k = 0; k < nbuf; k++) {
+    const int sz = sb.sz[k][threadIdx.x];
+    if (sz > kSmallSlice) { elems += sz; n_big++; }
+  }
+  // one scan for three counts: small slices << 54 | big slices << kElemBits | elements of big slices
+  const unsigned long long mine = ((unsigned long long)(nbuf - n_big) << 54) | ((unsigned long long)n_big << kElemBits) |
+                                  (unsigned long long)(unsigned)elems;
   unsigned long long incl = mine;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -317,23 +330,34 @@ __device__ __forceinline__ void flush_slices(const BatchDev& b, SliceBuf& sb, in
   }
   const unsigned long long total = __shfl_sync(FULL, incl, 31);
   if (total == 0) return;
+  const unsigned long long low54 = (1ull << 54) - 1;
   unsigned long long base = 0;
-  if (lane == 31) base = atomicAdd(&b.ctr->slice_elem, total);
+  unsigned int sbase = 0;
+  if (lane == 31 && (total & low54)) base = atomicAdd(&b.ctr->slice_elem, total & low54);
+  if (lane == 30 && (total >> 54)) sbase = atomicAdd(&b.ctr->n_small, (unsigned)(total >> 54));
   base = __shfl_sync(FULL, base, 31);
-  const unsigned long long excl = base + incl - mine;
-  long long slot = (long long)(excl >> kElemBits);
-  long long start = (long long)(excl & ((1ull << kElemBits) - 1));
+  sbase = __shfl_sync(FULL, sbase, 30);
+  const unsigned long long excl = incl - mine;
+  const unsigned long long big_excl = base + (excl & low54);
+  long long slot = (long long)(big_excl >> kElemBits);
+  long long start = (long long)(big_excl & ((1ull << kElemBits) - 1));
+  long long sslot = (long long)sbase + (long long)(excl >> 54);
   if (nbuf > 0) {
-    if (slot + nbuf > b.slice_cap) {
+    if (slot + n_big > b.slice_cap || sslot + (nbuf - n_big) > b.slice_cap) {
       atomicOr(&b.ctr->overflow, 1u);
     } else {
       for (int k = 0; k < nbuf; k++) {
         const int sz = sb.sz[k][threadIdx.x];
-        b.sl_start[slot] = start;
-        b.sl_rec[slot] = make_int4(q, sb.beg[k][threadIdx.x], sb.lm[k][threadIdx.x] | (p << 16), sz);
-        note_spans(b, slot, start, sz);
-        slot++;
-        start += sz;
+        const int4 rec = make_int4(q, sb.beg[k][threadIdx.x], sb.lm[k][threadIdx.x] | tag, sz);
+        if (sz > kSmallSlice) {
+          b.sl_start[slot] = start;
+          b.sl_rec[slot] = rec;
+          note_spans(b, slot, start, sz);
+          slot++;
+          start += sz;
+        } else {
+          b.sm_rec[sslot++] = rec;
+        }
       }
     }
   }
@@ -348,7 +372,7 @@ __global__ void __launch_bounds__(256, 8) fm_search_kernel(IndexDev ix, BatchDev
   int nbuf = 0;
   const int lane = threadIdx.x & 31;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  int q = 0, it = 0, p = 0, ml = 0;
+  int q = 0, it = 0, p = 0, ml = 0, tag = 0;
   const int32_t* pat = b.pat;
   bool live = c < b.n_tok;
   if (live) {
@@ -356,6 +380,7 @@ __global__ void __launch_bounds__(256, 8) fm_search_kernel(IndexDev ix, BatchDev
     const QMeta m = b.qmeta[q];
     p = m.x; ml = m.y; it = c - m.z; pat = b.pat + m.z;
     live = (m.w & kQValid) != 0;
+    tag = (p << 10) | ((m.w >> 8) << 20);
   }
   int lo = 0, hi = 0, len = 0;
   uint32_t bslot = 0;  // slot of the chain's bigram in the bigram directory
@@ -386,7 +411,7 @@ __global__ void __launch_bounds__(256, 8) fm_search_kernel(IndexDev ix, BatchDev
   bool extending = live && it + len < p;
   int pos1 = -1;  // sa_pos[lo] once the range has shrunk to one suffix
   while (__any_sync(FULL, extending)) {
-    if (__any_sync(FULL, nbuf > kSliceBuf - 2)) flush_slices(b, sb, nbuf, lane, q, p);  // room for two more
+    if (__any_sync(FULL, nbuf > kSliceBuf - 2)) flush_slices(b, sb, nbuf, lane, q, tag);  // room for two more
     if (extending) {
       const int t = pat[it + len];  // token at depth len
       int nlo = lo, nhi = lo, npos1 = -1;
@@ -476,9 +501,9 @@ __global__ void __launch_bounds__(256, 8) fm_search_kernel(IndexDev ix, BatchDev
       }
     }
   }
-  if (__any_sync(FULL, nbuf > kSliceBuf - 1)) flush_slices(b, sb, nbuf, lane, q, p);
+  if (__any_sync(FULL, nbuf > kSliceBuf - 1)) flush_slices(b, sb, nbuf, lane, q, tag);
   if (live && len >= 2 && len >= ml) push_slice(sb, nbuf, lo, hi - lo, len);
-  flush_slices(b, sb, nbuf, lane, q, p);
+  flush_slices(b, sb, nbuf, lane, q, tag);
 }
 
 // ---------------------------------------------------------------- gather
@@ -524,12 +549,12 @@ __device__ __forceinline__ int cover_sentence(const int32_t* __restrict__ sent, 
 
 // Insert (q, start) into the dedup table keeping the max match length: NGramMatches::_longest_matches
 // (src/ngram_matches.cc:79-81). The first inserter also claims the candidate's slot inside its query.
-__device__ __forceinline__ void add_survivor(const BatchDev& b, int q, int start, int slen, int lm) {
+__device__ __forceinline__ int add_survivor(const BatchDev& b, int q, int start, int slen, int lm) {
   const unsigned long long key = ((unsigned long long)(unsigned)q << 32) | (unsigned)start;
   uint32_t h = hash64(key) & b.hmask;
   if (*(volatile unsigned int*)&b.ctr->n_surv >= (unsigned long long)b.surv_cap) {  // table (4x cap) must never fill up
     atomicOr(&b.ctr->overflow, 2u);
-    return;
+    return -1;
   }
   for (;;) {
     const unsigned long long prev = atomicCAS(&b.hkey[h], ~0ull, key);
@@ -537,24 +562,38 @@ __device__ __forceinline__ void add_survivor(const BatchDev& b, int q, int start
       const unsigned idx = atomicAdd(&b.ctr->n_surv, 1u);
       if ((long long)idx >= b.surv_cap) {
         atomicOr(&b.ctr->overflow, 2u);
-        return;
+        return -1;
       }
       const int j = atomicAdd(&b.q_cnt[q], 1);
       atomicMax(&b.hlm[h], (unsigned)lm);
       b.surv[idx] = SurvRec{q, start, (int32_t)h, j};
       b.surv_len[idx] = (uint16_t)slen;
-      return;
+      return (int)h;
     }
     if (prev == key) {
       atomicMax(&b.hlm[h], (unsigned)lm);
-      return;
+      return (int)h;
     }
+    h = (h + 1) & b.hmask;
+  }
+}
+// Slot of (q, start) if it already is a survivor, else -1 (a concurrent insert may be missed: the caller
+// then verifies the pair again, which is harmless).
+__device__ __forceinline__ int find_survivor(const BatchDev& b, int q, int start) {
+  const unsigned long long key = ((unsigned long long)(unsigned)q << 32) | (unsigned)start;
+  uint32_t h = hash64(key) & b.hmask;
+  for (;;) {
+    const unsigned long long k = *(volatile const unsigned long long*)&b.hkey[h];
+    if (k == key) return (int)h;
+    if (k == ~0ull) return -1;
     h = (h + 1) & b.hmask;
   }
 }
 
 // Second stage of the gather: candidates that survived stage 1, taken from the warp's queue.
-// item = (q | match length << 20, sentence start, sentence length | need << 16, wide signature row or -1).
+// item = (q | match length << 20, suffix-array index). Each lane resolves one item -- walk record,
+// sentence start, the query's length / table offset, the smallest passing coverage for this length pair --
+// and then:
 //  * sentences with a wide signature (longer than kWideMin tokens): first the upper bound on the coverage
 //    from the 1024-bit signature and the query's bit-sliced planes -- 8 lanes per candidate, 128-bit loads,
 //    4 candidates per round -- so that only plausible pairs reach the exact count;
@@ -563,22 +602,61 @@ __device__ __forceinline__ void add_survivor(const BatchDev& b, int q, int start
 //  * everything else: one candidate at a time, the 32 lanes probe the sentence's tokens in parallel and
 //    mark the distinct words in a shared-memory bit set (PatternCoverage::count_covered_words,
 //    src/pattern_coverage.cc:15-28).
-__device__ __forceinline__ void verify_candidates(const IndexDev& ix, const BatchDev& b, const Params& pr, const int4* queue, int n,
-                                                  unsigned* seen, int lane) {
-  const bool have = lane < n;
-  const int4 item = have ? queue[lane] : make_int4(0, 0, 0, -1);
-  const int q = item.x & 0xfffff, start = item.y, slen = item.z & 0xffff, need = (int)((unsigned)item.z >> 16);
-  int p = 0, off = 0;
+struct Cand {  // a resolved queue item, exchanged between lanes through shared memory
+  int q_lm;    // q | match length << 20
+  int start;   // sentence start in tok
+  int len_need;  // sentence length | need << 16 (need = 0xffff: no bound table, evaluate the bounds)
+  int wrow;    // wide signature row or -1
+};
+__device__ __forceinline__ void verify_candidates(const IndexDev& ix, const BatchDev& b, const Params& pr, const int2* queue, int n,
+                                                  Cand* cand, unsigned* seen, int lane) {
+  bool have = lane < n;
+  int q = 0, lm = 0, start = 0, slen = 0, need = 0, wrow = -1, p = 0, off = 0;
   if (have) {
+    const int2 item = queue[lane];
+    q = item.x & 0xfffff;
+    lm = item.x >> 20;
+    const uint2 rec = __ldg(ix.sa_rec + item.y);
+    start = __ldg(ix.sa_start + item.y);
     const QMeta qm = __ldg(b.qmeta + q);
     p = qm.x;
     off = qm.z;
+    slen = (int)(rec.x & 63u);
+    if (slen == 63) {
+      slen = (int)((rec.x >> 6) & 1023u);
+      wrow = (int)rec.y;
+    }
+    need = __ldg(b.cmin_tab + ((p << 10) | slen));
+    if (need == kNeedReject) have = false;  // (a long sentence outside the length window)
+    else if (need == kNeedNoTable) {
+      need = 0xffff;
+      if (reject_length(p, slen, pr)) have = false;
+    }
   }
-  const bool wide = have && item.w >= 0;
-  unsigned wide_pass = 0;
+  // The sentence a query really matches is reached through many of its n-grams, so most candidates are
+  // repeats of a pair that has been verified already: those only raise the recorded match length
+  // (NGramMatches::_longest_matches keeps the maximum, src/ngram_matches.cc:79-81). Repeats inside this
+  // batch are verified once, by their lowest lane.
+  int slot = -1;
+  if (have) {
+    slot = find_survivor(b, q, start);
+    if (slot >= 0) {
+      atomicMax(&b.hlm[slot], (unsigned)lm);
+      have = false;
+    }
+  }
+  const unsigned long long pair_key = have ? (((unsigned long long)(unsigned)q << 32) | (unsigned)start) : ~(unsigned long long)lane;
+  const int leader = __ffs(__match_any_sync(FULL, pair_key)) - 1;
+  const bool repeat = have && leader != lane;
+  if (repeat) have = false;
+  slot = -1;
+  __syncwarp();
+  cand[lane] = Cand{q | (lm << 20), start, slen | (need << 16), wrow};
+  __syncwarp();
+  const bool wide = have && wrow >= 0;
+  unsigned wide_pass = __ballot_sync(FULL, wide && need == 0xffff);  // no bound table: straight to the exact count
   {
     unsigned todo = __ballot_sync(FULL, wide && need != 0xffff);
-    wide_pass = __ballot_sync(FULL, wide && need == 0xffff);  // no bound table: straight to the exact count
     const int grp = lane >> 3, sub = lane & 7;
     const unsigned gmask = 0xffu << (8 * grp);
     while (todo) {
@@ -586,13 +664,13 @@ __device__ __forceinline__ void verify_candidates(const IndexDev& ix, const Batc
       const bool valid = src < 32u;
       int ub = 0, cneed = 0;
       if (valid) {
-        const int4 it = queue[src];
-        const int cq = it.x & 0xfffff;
-        cneed = (int)((unsigned)it.z >> 16);
-        const uint4 sg = __ldg(reinterpret_cast<const uint4*>(ix.wsig + (size_t)it.w * kWideWords) + sub);
+        const Cand c = cand[src];
+        const int cq = c.q_lm & 0xfffff;
+        cneed = (int)((unsigned)c.len_need >> 16);
+        const uint4 sg = __ldg(reinterpret_cast<const uint4*>(ix.wsig + (size_t)c.wrow * kWideWords) + sub);
         const uint4* pl = reinterpret_cast<const uint4*>(b.wq + (size_t)cq * 3 * kWideWords) + sub;
         const uint4 b0 = __ldg(pl), b1 = __ldg(pl + kWideWords / 4), b2 = __ldg(pl + 2 * (kWideWords / 4));
-        const int extra = __ldg(&b.qmask[2 * cq + 1].w);
+        const int extra = __ldg(b.wextra + cq);
         ub = __popc(sg.x & b0.x) + __popc(sg.y & b0.y) + __popc(sg.z & b0.z) + __popc(sg.w & b0.w) +
              2 * (__popc(sg.x & b1.x) + __popc(sg.y & b1.y) + __popc(sg.z & b1.z) + __popc(sg.w & b1.w)) +
              4 * (__popc(sg.x & b2.x) + __popc(sg.y & b2.y) + __popc(sg.z & b2.z) + __popc(sg.w & b2.w));
@@ -602,9 +680,7 @@ __device__ __forceinline__ void verify_candidates(const IndexDev& ix, const Batc
       }
       ub = __reduce_add_sync(gmask, ub);
       wide_pass |= __reduce_or_sync(FULL, (valid && sub == 0 && ub >= cneed) ? (1u << src) : 0u);
-      // drop the (up to) four candidates just handled
-      const unsigned done = __reduce_or_sync(FULL, valid ? (1u << src) : 0u);
-      todo &= ~done;
+      todo &= ~__reduce_or_sync(FULL, valid ? (1u << src) : 0u);  // the (up to) four candidates just handled
     }
   }
   if (have && !wide && p <= 32) {
@@ -616,15 +692,15 @@ __device__ __forceinline__ void verify_candidates(const IndexDev& ix, const Batc
     } else {
       ok = cover_sentence<1>(ix.tok + start, slen, tbl, tmask, need) >= need;
     }
-    if (ok) add_survivor(b, q, start, slen, item.x >> 20);
+    if (ok) slot = add_survivor(b, q, start, slen, lm);
   }
   unsigned todo = __ballot_sync(FULL, have && !wide && p > 32) | wide_pass;
   while (todo) {
     const int src = __ffs(todo) - 1;
     todo &= todo - 1;
-    const int4 it = queue[src];
-    const int cq = it.x & 0xfffff, clm = it.x >> 20, cstart = it.y;
-    const int cslen = it.z & 0xffff, cneed = (int)((unsigned)it.z >> 16);
+    const Cand c = cand[src];
+    const int cq = c.q_lm & 0xfffff, clm = c.q_lm >> 20, cstart = c.start;
+    const int cslen = c.len_need & 0xffff, cneed = (int)((unsigned)c.len_need >> 16);
     const int cp = __shfl_sync(FULL, p, src), coff = __shfl_sync(FULL, off, src);
     const int2* tbl = b.tbl + 4ll * coff;
     const int tmask = next_pow2(2 * cp) - 1;
@@ -649,107 +725,161 @@ __device__ __forceinline__ void verify_candidates(const IndexDev& ix, const Batc
     cover = __reduce_add_sync(FULL, cover);
     __syncwarp();
     const bool ok = cneed == 0xffff ? !reject_cover(cp, cslen, cover, pr) : cover >= cneed;
-    if (ok && lane == 0) add_survivor(b, cq, cstart, cslen, clm);
+    int hs = -1;
+    if (ok && lane == 0) hs = add_survivor(b, cq, cstart, cslen, clm);
+    hs = __shfl_sync(FULL, hs, 0);
+    if (lane == src) slot = hs;
   }
+  const int lslot = __shfl_sync(FULL, slot, leader);
+  if (repeat && lslot >= 0) atomicMax(&b.hlm[lslot], (unsigned)lm);
 }
 
-// Persistent kernel over the flattened elements of all slices: register_suffix_range_match's walk
-// (src/ngram_matches.cc:62-84) fused with the candidate filter of src/fuzzy_match.cc:576-581.
-// Each warp takes spans of kSpan consecutive elements; element -> slice by one binary search per
-// span plus a 6-step shuffle search per 32 elements (every slice holds >= 1 element, so the 32
-// elements of a group touch at most the 32 slices after the previous group's last slice).
-// Stage 1 (every element, one 128-bit load): length window + signature upper bound on the coverage.
-// Stage 2 (the few that pass): queued per warp in shared memory and verified 32 at a time against
-// the sentence tokens, so the expensive path runs with full warps.
-static const int kQueue = 64;
-__global__ void __launch_bounds__(256, 8) fm_gather_kernel(IndexDev ix, BatchDev b, Params pr) {
-  __shared__ int4 s_queue[8][kQueue];
+__device__ __forceinline__ void ldg_nc_v8(const void* p, unsigned (&r)[8]) {  // one 256-bit load (32-byte aligned)
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+
+// Warp-level queue of stage-1 survivors in shared memory; drained 32 at a time so that stage 2 runs with
+// full warps.
+static const int kQueue = 160;  // 31 left over + up to 128 new ones per round
+struct WarpQueue {
+  int2* items;
+  Cand* cand;
+  unsigned* seen;
+  int n;
+};
+__device__ __forceinline__ void queue_push(WarpQueue& wq, bool pass, int2 item, int lane) {
+  const unsigned bal = __ballot_sync(FULL, pass);
+  if (pass) wq.items[wq.n + __popc(bal & ((1u << lane) - 1))] = item;
+  wq.n += __popc(bal);
+}
+
+// Stage 1 for one walk record: upper bound on the coverage from the signature against the smallest
+// coverage that passes for this (pattern length, sentence length). row = cmin64 + (p << 6); m = the
+// query's planes (B0 lo, B0 hi, B1 lo, B1 hi). Branch-free; the rare correction for signature bits that
+// collect more than three pattern positions (mult != 0, uniform over a slice) is added by the caller.
+__device__ __forceinline__ int stage1_margin(unsigned lo, unsigned hi, const int4& m, const uint16_t* __restrict__ row) {
+  const int need = __ldg(row + (lo & 63u));
+  return __popc(lo & (unsigned)m.x) + __popc(hi & (unsigned)m.y) + 2 * (__popc(lo & (unsigned)m.z) + __popc(hi & (unsigned)m.w)) - need;
+}
+__device__ __forceinline__ int stage1_extra(unsigned lo, unsigned hi, const int4& m, int mult) {
+  return mult * (__popc(lo & (unsigned)m.x & (unsigned)m.z) + __popc(hi & (unsigned)m.y & (unsigned)m.w));
+}
+
+// Persistent kernel over all range slices: register_suffix_range_match's walk (src/ngram_matches.cc:62-84)
+// fused with the candidate filter of src/fuzzy_match.cc:576-581.
+// Stage 1 (every element): one 8-byte walk record -- length and 58-bit signature -- against the query's
+// masks and the per-length bound table; no sentence is touched.
+//  * Slices of more than kSmallSlice elements (94 % of the elements sit in slices of 33 or more) are
+//    flattened; a warp takes spans of kSpan consecutive elements and walks them slice by slice with the
+//    slice's query constants in registers, four records per lane from one 256-bit load.
+//  * Small slices (three quarters of all slices hold one suffix): one slice per lane.
+// Stage 2 (the few that pass): queued per warp in shared memory and verified 32 at a time. The warp
+// alternates between producing (stage 1, until 32 candidates are queued or the work is done) and
+// consuming (one call site of the stage-2 code).
+#ifndef FM_GATHER_CTAS
+#define FM_GATHER_CTAS 5
+#endif
+__global__ void __launch_bounds__(256, FM_GATHER_CTAS) fm_gather_kernel(IndexDev ix, BatchDev b, Params pr) {
+  __shared__ int2 s_queue[8][kQueue];
+  __shared__ Cand s_cand[8][32];
   __shared__ unsigned s_seen[8][32];
-  unsigned* seen = s_seen[threadIdx.x >> 5];
-  const int lane = threadIdx.x & 31;
-  int4* queue = s_queue[threadIdx.x >> 5];
-  int queued = 0;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  WarpQueue wq{s_queue[wib], s_cand[wib], s_seen[wib], 0};
   const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const unsigned long long packed = b.ctr->slice_elem;
   const long long total = (long long)(packed & ((1ull << kElemBits) - 1));
-  long long n_slices = (long long)(packed >> kElemBits);
+  const long long n_small = (long long)b.ctr->n_small;
   if (b.ctr->overflow) return;  // a worklist overflowed: the host regrows and reruns
-  for (long long span = warp_id * kSpan; span < total; span += n_warps * kSpan) {
-    // slice containing the first element of the span (written by the search kernel)
-    long long k0 = __ldg(b.span_slice + span / kSpan);  // a slice at or one before the slice of the group's first element
-    // starts relative to the span: window starts are > span - 1, the current slice may begin earlier
-    int s0 = (int)max(__ldg(b.sl_start + k0) - span, -0x7fffffffll);
-    int z0 = __ldg(&b.sl_rec[k0].w);  // size of slice k0
-    for (int u = 0; u < kSpan; u += 32) {
-      if (span + u >= total) break;
-      const int el = u + lane;
-      int my_start = s0;
-      long long my_slice = k0;
-      if (u + 31 >= s0 + z0) {  // (uniform) the group reaches past slice k0: find each lane's slice
-        // window = the 32 slices after k0; slice(el) = k0 + #{window starts <= el}
-        const long long ks = k0 + 1 + lane;
-        const int wst = ks < n_slices ? (int)min(__ldg(b.sl_start + ks) - span, 0x7fffffffll) : 0x7fffffff;
-        int c = 0;
+
+  // producer state: the small slices first (phase 0), then the flattened spans (phase 1). The sentence a
+  // query really matches sits at the deep end of most of its chains, i.e. in small slices that are adjacent
+  // in the list (chains of one query are searched by neighbouring threads): taking them first puts those
+  // pairs into the dedup table once, and the repeats among the flattened elements skip stage 2.
+  int phase = 0;
+  long long span = warp_id * kSpan, pos = 0, span_end = 0, k = 0;  // current span / position / slice
+  int g = 0, a0 = 0, a1 = 0, qlm = 0, mult = 0;                   // current segment: suffix-array indices [a0, a1), next group g
+  int4 m = make_int4(0, 0, 0, 0);
+  const uint16_t* row = b.cmin64;
+  long long s0 = warp_id * 32;
+  bool in_span = false;
+  unsigned stage2 = 0;
+  for (;;) {
+    // ---- produce until a full batch of candidates is queued
+    while (phase < 2 && wq.n < 32) {
+      if (phase == 1) {
+        if (g >= a1) {  // next segment
+          if (!in_span || pos >= span_end) {  // next span
+            if (in_span) span += n_warps * kSpan;
+            if (span >= total) { phase = 2; continue; }
+            in_span = true;
+            span_end = min(span + kSpan, total);
+            pos = span;
+            k = __ldg(b.span_slice + span / kSpan);  // slice that holds the first element of the span
+          }
+          const int4 sr = __ldg(b.sl_rec + k);  // (q, sa_begin, lm | p << 10 | mult << 20, size), same for all lanes
+          const long long st = __ldg(b.sl_start + k);
+          const long long seg_end = min(st + sr.w, span_end);
+          m = __ldg(b.qmask + sr.x);
+          mult = sr.z >> 20;
+          row = b.cmin64 + (((sr.z >> 10) & 1023) << 6);
+          qlm = sr.x | ((sr.z & 1023) << 20);
+          a0 = sr.y + (int)(pos - st);
+          a1 = sr.y + (int)(seg_end - st);
+          g = a0 & ~3;  // 256-bit loads cover aligned groups of four records
+          pos = seg_end;
+          k++;
+        }
+        const int base = g + 4 * lane;
+        unsigned r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (base < a1) ldg_nc_v8(ix.sa_rec + base, r);
+        int d0 = stage1_margin(r[0], r[1], m, row), d1 = stage1_margin(r[2], r[3], m, row);
+        int d2 = stage1_margin(r[4], r[5], m, row), d3 = stage1_margin(r[6], r[7], m, row);
+        if (mult) {  // (uniform)
+          d0 += stage1_extra(r[0], r[1], m, mult); d1 += stage1_extra(r[2], r[3], m, mult);
+          d2 += stage1_extra(r[4], r[5], m, mult); d3 += stage1_extra(r[6], r[7], m, mult);
+        }
+        const unsigned len = (unsigned)(a1 - a0), rel = (unsigned)(base - a0);  // element base + i is inside iff rel + i < len (unsigned)
+        const bool p0 = (d0 >= 0) & (rel < len), p1 = (d1 >= 0) & (rel + 1u < len);
+        const bool p2 = (d2 >= 0) & (rel + 2u < len), p3 = (d3 >= 0) & (rel + 3u < len);
+        if (__any_sync(FULL, p0 | p1 | p2 | p3)) {
+          queue_push(wq, p0, make_int2(qlm, base), lane);
+          queue_push(wq, p1, make_int2(qlm, base + 1), lane);
+          queue_push(wq, p2, make_int2(qlm, base + 2), lane);
+          queue_push(wq, p3, make_int2(qlm, base + 3), lane);
+        }
+        g += 128;
+      } else {
+        if (s0 >= n_small) { phase = 1; continue; }
+        const long long si = s0 + lane;
+        int4 sr = make_int4(0, 0, 0, 0);
+        if (si < n_small) sr = __ldg(b.sm_rec + si);
+        const int4 sm = __ldg(b.qmask + sr.x);
+        const uint16_t* srow = b.cmin64 + (((sr.z >> 10) & 1023) << 6);
+        const int smult = sr.z >> 20, sqlm = sr.x | ((sr.z & 1023) << 20);
+        uint2 rec[kSmallSlice];
 #pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-          const int v = __shfl_sync(FULL, wst, c + step - 1);
-          if (v <= el) c += step;
+        for (int e = 0; e < kSmallSlice; e++) rec[e] = e < sr.w ? __ldg(ix.sa_rec + sr.y + e) : make_uint2(0u, 0u);
+#pragma unroll
+        for (int e = 0; e < kSmallSlice; e++) {
+          const bool pass = (e < sr.w) & (stage1_margin(rec[e].x, rec[e].y, sm, srow) + stage1_extra(rec[e].x, rec[e].y, sm, smult) >= 0);
+          if (__any_sync(FULL, pass)) queue_push(wq, pass, make_int2(sqlm, sr.y + e), lane);
         }
-        {
-          const int v = __shfl_sync(FULL, wst, c);  // c <= 31
-          if (v <= el) c += 1;
-        }
-        const int prev_start = __shfl_sync(FULL, wst, c > 0 ? c - 1 : 0);
-        my_start = c > 0 ? prev_start : s0;
-        my_slice = k0 + c;
-        k0 = __shfl_sync(FULL, my_slice, 31);
-        s0 = __shfl_sync(FULL, my_start, 31);
-        z0 = __ldg(&b.sl_rec[k0].w);
-      }
-      bool pass = false;
-      int4 item = make_int4(0, 0, 0, 0);
-      if (span + el < total) {
-        const int4 sr = __ldg(b.sl_rec + my_slice);
-        const int q = sr.x;
-        const int4 wr = ldg_nc_v4(ix.sa_walk + (sr.y + (el - my_start)));  // (start, slen, sig lo, sig hi)
-        const int slen = wr.y;
-        const int p = sr.z >> 16, lm = sr.z & 0xffff;
-        const int need = __ldg(b.cmin_tab + ((p << 10) | slen));  // one lookup: length window + smallest passing coverage
-        if (need <= p && slen > kWideMin) {  // long sentence: wr.z is its wide signature row, tested in stage 2
-          pass = true;
-          item = make_int4(q | (lm << 20), wr.x, slen | (need << 16), wr.z);
-        } else if (need <= p) {
-          const int4 m0 = __ldg(b.qmask + 2 * q), m1 = __ldg(b.qmask + 2 * q + 1);  // planes (B0, B1), (B2, extra)
-          const unsigned lo = (unsigned)wr.z, hi = (unsigned)wr.w;
-          int ub = __popc(lo & m0.x) + __popc(hi & m0.y) + 2 * (__popc(lo & m0.z) + __popc(hi & m0.w));
-          if (m1.x | m1.y) {  // some signature bit collects 4 or more pattern positions
-            ub += 4 * (__popc(lo & m1.x) + __popc(hi & m1.y));
-            if (m1.z) ub += m1.z * (__popc(lo & m1.x & m0.x & m0.z) + __popc(hi & m1.y & m0.y & m0.w));
-          }
-          if (ub >= need) {
-            pass = true;
-            item = make_int4(q | (lm << 20), wr.x, slen | (need << 16), -1);
-          }
-        } else if (need == kNeedNoTable && !reject_length(p, slen, pr)) {
-          pass = true;
-          item = make_int4(q | (lm << 20), wr.x, slen | (0xffff << 16), slen > kWideMin ? wr.z : -1);
-        }
-      }
-      const unsigned bal = __ballot_sync(FULL, pass);
-      if (bal) {
-        if (pass) queue[queued + __popc(bal & ((1u << lane) - 1))] = item;
-        queued += __popc(bal);
-        __syncwarp();
-        if (queued >= 32) {
-          queued -= 32;
-          verify_candidates(ix, b, pr, queue + queued, 32, seen, lane);
-          __syncwarp();
-        }
+        s0 += n_warps * 32;
       }
     }
+    // ---- consume one batch
+    if (wq.n == 0) break;  // (phase == 2)
+    __syncwarp();
+    const int take = min(wq.n, 32);
+    wq.n -= take;
+    stage2 += take;
+    verify_candidates(ix, b, pr, wq.items + wq.n, take, wq.cand, wq.seen, lane);
+    __syncwarp();
   }
-  verify_candidates(ix, b, pr, queue, queued, seen, lane);
+  if (lane == 0 && stage2) atomicAdd(&b.ctr->n_stage2, stage2);
 }
 
 // ---------------------------------------------------------------- scan (<= 128 co-resident CTAs)
@@ -1118,23 +1248,56 @@ __device__ __forceinline__ unsigned long long peq_lookup(const int2* __restrict_
   }
 }
 
-template <typename W>
-__device__ __forceinline__ int myers_thread(const int32_t* __restrict__ sent, int s, int p, const int2* __restrict__ tbl, int tmask,
-                                            const unsigned long long* __restrict__ peq) {
+// p <= 32: the pattern sits in registers and the match vector of a sentence token is built by comparing
+// against all of it (no table lookups, no dependent loads: the only memory traffic is the sentence).
+__device__ __forceinline__ int myers_thread32(const int32_t* __restrict__ sent, int s, const int32_t* __restrict__ pat, int p) {
+  int pt[32];
+#pragma unroll
+  for (int j = 0; j < 32; j++) pt[j] = j < p ? __ldg(pat + j) : -1;
+  uint32_t pv = ~0u, mv = 0;
+  const uint32_t high = 1u << (p - 1);
+  int score = p;
+  const int4* s4 = reinterpret_cast<const int4*>(sent);
+  int4 t = ldg_nc_v4(s4);  // sentences start on 16-byte boundaries and are zero padded
+  for (int i0 = 0; i0 < s; i0 += 4) {
+    const int4 cur = t;
+    if (i0 + 4 < s) t = ldg_nc_v4(s4 + (i0 >> 2) + 1);
+    uint32_t e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+      const uint32_t bit = 1u << j;
+      if (cur.x == pt[j]) e0 |= bit;
+      if (cur.y == pt[j]) e1 |= bit;
+      if (cur.z == pt[j]) e2 |= bit;
+      if (cur.w == pt[j]) e3 |= bit;
+    }
+    score += myers_row<uint32_t>(e0, pv, mv, high);
+    if (i0 + 1 < s) score += myers_row<uint32_t>(e1, pv, mv, high);
+    if (i0 + 2 < s) score += myers_row<uint32_t>(e2, pv, mv, high);
+    if (i0 + 3 < s) score += myers_row<uint32_t>(e3, pv, mv, high);
+  }
+  return score;
+}
+
+// 32 < p <= 64: one 64-bit vector; the match vectors come from the query's position masks (peq64, built
+// by the prepare kernel) through its word table.
+__device__ __forceinline__ int myers_thread64(const int32_t* __restrict__ sent, int s, int p, const int2* __restrict__ tbl, int tmask,
+                                              const unsigned long long* __restrict__ peq) {
+  typedef unsigned long long W;
   W pv = ~(W)0, mv = 0;
   const W high = (W)1 << (p - 1);
   int score = p;
   const int4* s4 = reinterpret_cast<const int4*>(sent);
   for (int i0 = 0; i0 < s; i0 += 4) {
-    const int4 t = ldg_nc_v4(s4 + (i0 >> 2));  // sentences start on 16-byte boundaries and are zero padded
+    const int4 t = ldg_nc_v4(s4 + (i0 >> 2));
     // first probes of the four lookups in flight together
     const int h0 = hash32((uint32_t)t.x) & tmask, h1 = hash32((uint32_t)t.y) & tmask;
     const int h2 = hash32((uint32_t)t.z) & tmask, h3 = hash32((uint32_t)t.w) & tmask;
     const int2 e0 = __ldg(tbl + h0), e1 = __ldg(tbl + h1), e2 = __ldg(tbl + h2), e3 = __ldg(tbl + h3);
-    const W q0 = (W)peq_lookup(tbl, tmask, peq, t.x, e0, h0);
-    const W q1 = (W)peq_lookup(tbl, tmask, peq, t.y, e1, h1);
-    const W q2 = (W)peq_lookup(tbl, tmask, peq, t.z, e2, h2);
-    const W q3 = (W)peq_lookup(tbl, tmask, peq, t.w, e3, h3);
+    const W q0 = peq_lookup(tbl, tmask, peq, t.x, e0, h0);
+    const W q1 = peq_lookup(tbl, tmask, peq, t.y, e1, h1);
+    const W q2 = peq_lookup(tbl, tmask, peq, t.z, e2, h2);
+    const W q3 = peq_lookup(tbl, tmask, peq, t.w, e3, h3);
     score += myers_row<W>(q0, pv, mv, high);
     if (i0 + 1 < s) score += myers_row<W>(q1, pv, mv, high);
     if (i0 + 2 < s) score += myers_row<W>(q2, pv, mv, high);
@@ -1160,12 +1323,9 @@ __global__ void __launch_bounds__(128) fm_score_bp_kernel(IndexDev ix, BatchDev 
     atomicOr(&b.ctr->n_long, p > kBpWarpMax ? 2u : 1u);
     return;
   }
-  const int2* tbl = b.tbl + 4ll * qm.z;
-  const int tmask = next_pow2(2 * p) - 1;
-  const unsigned long long* peq = b.peq64 + qm.z;
   const int32_t* sent = ix.tok + sr.start;
-  const int d = p <= 32 ? myers_thread<uint32_t>(sent, slen, p, tbl, tmask, peq)
-                        : myers_thread<unsigned long long>(sent, slen, p, tbl, tmask, peq);
+  const int d = p <= 32 ? myers_thread32(sent, slen, b.pat + qm.z, p)
+                        : myers_thread64(sent, slen, p, b.tbl + 4ll * qm.z, next_pow2(2 * p) - 1, b.peq64 + qm.z);
   const float wdiff = __fdiv_rn(100.f, normalizer(p, slen, pr));
   const float C = chain_cost(d, __fmul_rn(pr.del, wdiff));
   write_record(ix, b, sr, slen, C, C);
@@ -1758,7 +1918,8 @@ __global__ void fm_merge_copy_kernel(ShardPtrs sp, int n_shards, const int32_t* 
 static int dp_stride(const IndexDev& ix) { return ((ix.max_tokens + 31) / 32) * 32 + 32; }
 
 void launch_bounds(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st) {
-  fm_bounds_kernel<<<(ix.max_tokens + 7) / 8, 256, 0, st>>>(ix.max_tokens, p, const_cast<uint16_t*>(b.cmin_tab));
+  fm_bounds_kernel<<<(ix.max_tokens + 7) / 8, 256, 0, st>>>(ix.max_tokens, p, const_cast<uint16_t*>(b.cmin_tab),
+                                                            const_cast<uint16_t*>(b.cmin64));
 }
 void launch_prepare(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st) {
   const int warps_per_block = 8;
@@ -1770,7 +1931,7 @@ void launch_search(const IndexDev& ix, const BatchDev& b, const Params&, cudaStr
   if (grid > 0) fm_search_kernel<<<grid, 256, 0, st>>>(ix, b);
 }
 void launch_gather(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st) {
-  fm_gather_kernel<<<sm_count * 8, 256, 0, st>>>(ix, b, p);
+  fm_gather_kernel<<<sm_count * FM_GATHER_CTAS, 256, 0, st>>>(ix, b, p);
 }
 void launch_scan(const int32_t* in, int32_t* out, int32_t n, unsigned long long* chain, unsigned int epoch, int sm_count,
                  cudaStream_t st) {

@@ -79,6 +79,7 @@ typedef struct fm_profile {
   int64_t n_queries, n_query_tokens, n_slices, n_elements, n_survivors, n_matches;
   int32_t launches; /* kernels launched for the batch */
   int32_t retries;  /* workspace regrowths */
+  int64_t n_stage2; /* suffix-array elements that passed the signature test of the gather */
 } fm_profile;
 
 /* Build the device index for one GPU from a CSR translation memory.
@@ -133,6 +134,22 @@ int fm_match_batch(fm_index* index, const int32_t* q_tokens, const int64_t* q_of
 int fm_match_batch_device(fm_index* index, const int32_t* d_q_tokens, const int32_t* d_q_off, int64_t n_q,
                           int64_t n_query_tokens, const fm_params* params, int64_t cap, fm_match* d_out,
                           int32_t* d_out_count, void* stream);
+
+/* Asynchronous form of the two calls above: submit enqueues the copies and kernels of one batch and
+ * returns a ticket; fm_ticket_wait blocks until that batch (not later ones) has finished, reruns it if
+ * a worklist overflowed, and frees the ticket (also on error). Several tickets may be in flight on one
+ * index -- each owns a workspace -- so the host<->device copies of neighbouring batches overlap the
+ * kernels, as the reference's CLI overlaps I/O and matching through its queue of futures
+ * (cli/src/FuzzyMatch-cli.cc:112-193). The buffers of a submitted batch must stay valid and untouched until
+ * its wait returns; host buffers should be pinned for the copies to be asynchronous. A submitted host
+ * batch holds at most 2^18 queries / 2^22 tokens. */
+typedef struct fm_ticket fm_ticket;
+int fm_match_batch_submit(fm_index* index, const int32_t* q_tokens, const int64_t* q_off, int64_t n_q,
+                          const fm_params* params, int64_t cap, fm_match* out, int32_t* out_count, fm_ticket** ticket);
+int fm_match_batch_device_submit(fm_index* index, const int32_t* d_q_tokens, const int32_t* d_q_off, int64_t n_q,
+                                 int64_t n_query_tokens, const fm_params* params, int64_t cap, fm_match* d_out,
+                                 int32_t* d_out_count, void* stream, fm_ticket** ticket);
+int fm_ticket_wait(fm_ticket* ticket);
 
 /* Sharded TM: per-shard half. Scores every surviving candidate of this shard and returns them grouped
  * by query: d_rec_off[n_q+1] (exclusive offsets) and d_rec[*n_rec] (device pointers owned by the index,

@@ -20,13 +20,12 @@ def test_fallback_peak_when_file_absent(tmp_path, monkeypatch):
     assert v == bench.FALLBACK_HBM_GBS and src.startswith("fallback")
 
 
-def test_measured_peak_prefers_sustained_hbm_figure(tmp_path, monkeypatch):
-    v, src = _with_peaks(tmp_path, monkeypatch, {"hbm": {"burst_gbs": 7400, "sustained_gbs": 6900}, "bf16_tflops": 1800})
-    assert v == 6900 and "sustained" in src
+def test_measured_peak_reads_hbm_gbs(tmp_path, monkeypatch):
+    v, src = _with_peaks(tmp_path, monkeypatch, {"hbm_gbs": 6551.0, "bf16_tflops": 1686.7})
+    assert v == 6551.0 and src.startswith("measured")
 
 
-def test_measured_peak_accepts_tb_per_s_and_ignores_nonsense(tmp_path, monkeypatch):
-    assert _with_peaks(tmp_path, monkeypatch, {"hbm_copy_tb_s": 6.8})[0] == 6800
+def test_measured_peak_falls_back_on_a_file_without_the_key(tmp_path, monkeypatch):
     assert _with_peaks(tmp_path, monkeypatch, {"bf16_tflops": 1800})[0] == bench.FALLBACK_HBM_GBS
     (tmp_path / "MEASURED_PEAKS.json").write_text("not json")
     assert bench.measured_peak()[0] == bench.FALLBACK_HBM_GBS

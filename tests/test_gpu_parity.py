@@ -399,3 +399,45 @@ def test_degenerate_inputs():
     assert len(cnt) == 0
     out, cnt = index.match_batch(np.array([2, 3, 4], dtype=np.int32), np.array([0, 0, 3, 3], dtype=np.int64), cap=1, fuzzy=0.5, n=1)
     assert cnt.tolist() == [0, 1, 0] and out[1, 0]["score"] == 1.0
+
+
+def test_submit_wait_pipeline(medium):
+    """fm_match_batch_submit / fm_ticket_wait: several batches in flight on one index (each ticket owns a
+    workspace) give the same bytes as the synchronous call, in any wait order; same for device buffers."""
+    import torch
+    from fuzzy_match_b200 import capi
+    index, _, q, qo = medium
+    params = capi.Params.make(fuzzy=0.5, n=4, ml=2)
+    cap, n_q = 4, len(qo) - 1
+    parts = [(0, 500), (500, 1100), (1100, n_q)]
+    want, wcnt = index.match_batch(q, qo, cap=cap, params=params)
+    bufs, tickets = [], []
+    for a, b in parts:
+        pq = np.ascontiguousarray(q[qo[a]:qo[b]])
+        po = np.ascontiguousarray(qo[a:b + 1] - qo[a])
+        out = np.zeros((b - a, cap), dtype=capi.MATCH_DTYPE)
+        cnt = np.zeros(b - a, dtype=np.int32)
+        bufs.append((pq, po, out, cnt))
+        tickets.append(index.submit(pq, po, out, cnt, cap, params))
+    for k in (1, 0, 2):
+        index.wait(tickets[k])
+    for (a, b), (_, _, out, cnt) in zip(parts, bufs):
+        assert (cnt == wcnt[a:b]).all() and out.tobytes() == want[a:b].tobytes()
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(dev)
+    dbufs, tickets = [], []
+    for a, b in parts:
+        d_tok = torch.as_tensor(q[qo[a]:qo[b]], device=dev)
+        d_off = torch.as_tensor((qo[a:b + 1] - qo[a]).astype(np.int32), device=dev)
+        d_out = torch.zeros((b - a) * cap * 24, dtype=torch.uint8, device=dev)
+        d_cnt = torch.zeros(b - a, dtype=torch.int32, device=dev)
+        dbufs.append((d_tok, d_off, d_out, d_cnt))
+        tickets.append(index.submit_device(d_tok.data_ptr(), d_off.data_ptr(), b - a, int(qo[b] - qo[a]), d_out.data_ptr(),
+                                           d_cnt.data_ptr(), cap, stream.cuda_stream, params))
+    for t in tickets:
+        index.wait(t)
+    for (a, b), (_, _, d_out, d_cnt) in zip(parts, dbufs):
+        cnt = d_cnt.cpu().numpy()
+        got = d_out.cpu().numpy().view(capi.MATCH_DTYPE).reshape(b - a, cap)
+        assert (cnt == wcnt[a:b]).all()
+        assert all(got[i, :cnt[i]].tobytes() == want[a + i, :cnt[i]].tobytes() for i in range(b - a))

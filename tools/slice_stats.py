@@ -28,14 +28,14 @@ def main():
     index.match_batch(q, qo, cap=1, fuzzy=args.fuzzy, n=1, ml=3)
     prof = index.profile()
     lib = capi.load_library()
-    cap = int(prof["n_slices"]) + 16
+    cap = 4 * int(prof["n_slices"]) + (1 << 21)
     rec = np.zeros((cap, 4), dtype=np.int32)
     start = np.zeros(cap, dtype=np.int64)
     lib.fm_debug_last_slices.restype = C.c_int64
     n = lib.fm_debug_last_slices(index.h, C.c_void_p(rec.ctypes.data), C.c_void_p(start.ctypes.data), C.c_int64(cap))
     rec = rec[:n]
     size = rec[:, 3].astype(np.int64)
-    lm = rec[:, 2] & 0xffff
+    lm = rec[:, 2] & 1023
     total = size.sum()
     print("slices %d elements %d (profile: %d / %d) survivors %d" % (n, total, prof["n_slices"], prof["n_elements"], prof["n_survivors"]))
     edges = [1, 2, 3, 5, 9, 17, 33, 65, 129, 257, 513, 1025, 4097, 16385, 1 << 30]
