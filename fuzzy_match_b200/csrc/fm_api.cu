@@ -96,7 +96,7 @@ static int ensure_slices(Workspace* w, int64_t n) {
   // the packed (slices << 38 | elements) counter leaves 26 bits for the slice count
   if (n >= (int64_t(1) << 26) - 65536) { set_error("too many suffix-array range slices in one batch: split the batch"); return FM_ERR_NOMEM; }
   int rc;
-  if ((rc = dev_realloc(&w->sl_start, n + 1)) || (rc = dev_realloc(&w->sl_rec, n)) || (rc = dev_realloc(&w->sm_rec, n))) return rc;
+  if ((rc = dev_realloc(&w->sl_start, n + 1)) || (rc = dev_realloc(&w->sl_rec, 2 * n)) || (rc = dev_realloc(&w->sm_rec, 2 * n))) return rc;
   w->cap_slices = n;
   return FM_OK;
 }
@@ -114,6 +114,16 @@ static int ensure_bounds(Index* ix, Workspace* w) {
   const int64_t t = ix->max_tokens;
   if ((rc = dev_realloc(&w->cmin_tab, (t + 1) << 10)) || (rc = dev_realloc(&w->cmin64, (t + 1) << 6))) return rc;
   w->bounds_valid = false;
+  return FM_OK;
+}
+// stage-1 survivors handed from the walk kernel to the verify kernel
+static int ensure_cand(Workspace* w, int64_t n) {
+  if (n <= w->cap_cand) return FM_OK;
+  int rc;
+  if (n > (int64_t(1) << 31)) { set_error("too many candidates in one batch: split the batch"); return FM_ERR_NOMEM; }
+  n = std::min<int64_t>(n + n / 4, int64_t(1) << 31);
+  if ((rc = dev_realloc(&w->cand, n))) return rc;
+  w->cap_cand = n;
   return FM_OK;
 }
 static int ensure_survivors(Workspace* w, int64_t n) {
@@ -142,7 +152,7 @@ static int ensure_out(Workspace* w, int64_t n_q, int64_t cap) {
 
 static void free_workspace(Workspace* w) {
   cudaFree(w->d_q_tok); cudaFree(w->d_q_off); cudaFree(w->d_q_real); cudaFree(w->d_q_gap); cudaFree(w->d_itok_dist); cudaFree(w->pat); cudaFree(w->chain_q); cudaFree(w->qmeta); cudaFree(w->tbl); cudaFree(w->cmin_tab); cudaFree(w->span_slice); cudaFree(w->qmask); cudaFree(w->wq); cudaFree(w->peq64); cudaFree(w->cmin64); cudaFree(w->wextra); cudaFree(w->sm_rec);
-  cudaFree(w->sl_start); cudaFree(w->sl_rec); cudaFree(w->hkey); cudaFree(w->hlm); cudaFree(w->surv); cudaFree(w->surv_len);
+  cudaFree(w->sl_start); cudaFree(w->sl_rec); cudaFree(w->hkey); cudaFree(w->hlm); cudaFree(w->surv); cudaFree(w->cand); cudaFree(w->surv_len);
   cudaFree(w->q_cnt); cudaFree(w->q_base); cudaFree(w->acc_cnt); cudaFree(w->rec); cudaFree(w->heapbuf); cudaFree(w->ctr); cudaFree(w->scan_chain);
   cudaFree(w->d_out); cudaFree(w->d_out_count); cudaFree(w->mrec); cudaFree(w->m_cnt); cudaFree(w->m_base); cudaFree(w->m_acc); cudaFree(w->m_heap); cudaFree(w->heavy_q); cudaFree(w->m_heavy); cudaFree(w->mid_q); cudaFree(w->m_mid); cudaFree(w->sort_key); cudaFree(w->sort_key2); cudaFree(w->m_key2); cudaFree(w->sort_idx); cudaFree(w->m_key); cudaFree(w->m_idx);
   if (w->h_ctr) cudaFreeHost(w->h_ctr);
@@ -174,6 +184,16 @@ static int check_params(const fm_params* p, Params* out) {
   return FM_OK;
 }
 
+// FM_DEBUG_SYNC=1: wait after every stage and name the one that failed (diagnostics only)
+static const bool g_debug_sync = getenv("FM_DEBUG_SYNC") != nullptr;
+static int stage_check(cudaStream_t st, const char* what) {
+  if (!g_debug_sync) return FM_OK;
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, what);
+  return FM_OK;
+}
+
 static BatchDev make_batch(Workspace* w, const int32_t* d_q_tok, const int32_t* d_q_off, int64_t n_q, int64_t n_tok) {
   BatchDev b{};
   b.q_tok_in = d_q_tok; b.q_off = d_q_off; b.n_q = (int32_t)n_q; b.n_tok = (int32_t)n_tok;
@@ -181,6 +201,7 @@ static BatchDev make_batch(Workspace* w, const int32_t* d_q_tok, const int32_t* 
   b.span_slice = w->span_slice; b.span_cap = w->cap_spans;
   b.sl_start = w->sl_start; b.sl_rec = w->sl_rec; b.sm_rec = w->sm_rec; b.slice_cap = w->cap_slices;
   b.hkey = w->hkey; b.hlm = w->hlm; b.hmask = w->hs_use - 1;
+  b.cand = w->cand; b.cand_cap = w->cap_cand;
   b.surv = w->surv; b.surv_len = w->surv_len; b.surv_cap = std::min<int64_t>(w->cap_surv, w->hs_use / 4);  // load factor <= 1/4
   b.q_cnt = w->q_cnt; b.q_base = w->q_base; b.rec = w->rec; b.heapbuf = w->heapbuf; b.acc_cnt = w->acc_cnt;
   b.ctr = w->ctr;
@@ -213,17 +234,24 @@ static int launch_shard(Index* ix, Workspace* w, const int32_t* d_q_tok, const i
     w->bounds_valid = true;
     (*launches)++;
   }
+  int rc;
+  if ((rc = stage_check(st, "memsets / bounds"))) return rc;
   launch_prepare(ix->dev, b, pr, st);
   if (ix->profiling) cudaEventRecord(w->ev[1], st);
+  if ((rc = stage_check(st, "prepare kernel"))) return rc;
   launch_search(ix->dev, b, pr, st);
   if (ix->profiling) cudaEventRecord(w->ev[2], st);
+  if ((rc = stage_check(st, "search kernel"))) return rc;
   launch_gather(ix->dev, b, pr, ix->sm_count, st);
   if (ix->profiling) cudaEventRecord(w->ev[3], st);
+  if ((rc = stage_check(st, "gather kernels"))) return rc;
   launch_scan(w->q_cnt, w->q_base, (int32_t)n_q, w->scan_chain, ++w->scan_epoch, ix->sm_count, st);
   if (ix->profiling) cudaEventRecord(w->ev[4], st);
+  if ((rc = stage_check(st, "scan kernel"))) return rc;
   launch_score(ix->dev, b, pr, ix->sm_count, st);
   if (ix->profiling) cudaEventRecord(w->ev[5], st);
-  *launches += w->real_active ? 5 : 6;  // prepare, search, gather, scan, score (short + wavefront kernels)
+  if ((rc = stage_check(st, "score kernels"))) return rc;
+  *launches += w->real_active ? 6 : 7;  // prepare, search, gather (walk + verify), scan, score (short + wavefront kernels)
   return FM_OK;
 }
 
@@ -232,6 +260,7 @@ static int initial_worklists(Index* ix, Workspace* w, int64_t n_q, int64_t n_tok
   if ((rc = ensure_bounds(ix, w)) || (rc = ensure_wide(ix, w))) return rc;
   if ((rc = ensure_slices(w, std::min<int64_t>((int64_t(1) << 26) - (1 << 17), std::max<int64_t>(1 << 16, 8 * n_tok + 65536))))) return rc;
   if ((rc = ensure_spans(w, std::max<int64_t>(1 << 16, 2 * n_tok + 65536)))) return rc;
+  if ((rc = ensure_cand(w, std::max<int64_t>(1 << 20, 16 * n_q)))) return rc;
   return ensure_survivors(w, std::max<int64_t>(1 << 18, 8 * n_q));
 }
 
@@ -262,6 +291,8 @@ static int wait_and_check(Workspace* w, int attempt, int* retries) {
     else if ((rc = ensure_survivors(w, w->cap_surv * 4))) return -rc;  // ... then a larger one
     else w->surv_hint = w->cap_surv;
   }
+  // the walk kernel counts every candidate, also those that did not fit: the list is regrown to the exact need
+  if ((w->h_ctr->overflow & 8u) && (rc = ensure_cand(w, (int64_t)w->h_ctr->n_cand + 1024))) return -rc;
   const int64_t need_spans = (int64_t)((w->h_ctr->slice_elem & ((1ull << kElemBits) - 1)) / kSpanHost) + 2;
   if (need_spans > w->cap_spans && (rc = ensure_spans(w, need_spans + need_spans / 8))) return -rc;
   return 1;
@@ -274,6 +305,10 @@ static int run_replay(Index* ix, Workspace* w, fm_record* rec, const int32_t* q_
   launch_replay(ix->dev, rec, q_cnt, q_base, heapbuf, sort_key, sort_key2, sort_idx, acc_cnt, mid_q, heavy_q, d_q_off, (int32_t)n_q, pr, cap, d_out,
                 d_out_count, w->ctr, ix->sm_count, st, w->stream2, w->ev_fork, w->ev_join);
   (*launches) += 3;
+  {
+    int rc;
+    if ((rc = stage_check(st, "replay kernels"))) return rc;
+  }
   if (pr.contrast > 0.f) {
     launch_contrast(ix->dev, rec, q_base, sort_idx, acc_cnt, (int32_t)n_q, pr, cap, d_out, d_out_count, w->ctr, ix->sm_count, st);
     (*launches)++;
@@ -297,7 +332,8 @@ static void finish_profile(Index* ix, Workspace* w, int64_t n_q, int64_t n_tok, 
   p.n_slices = (int64_t)(w->h_ctr->slice_elem >> kElemBits) + (int64_t)w->h_ctr->n_small;
   p.n_elements = (int64_t)(w->h_ctr->slice_elem & ((1ull << kElemBits) - 1));
   p.n_survivors = w->h_ctr->n_surv;
-  p.n_stage2 = w->h_ctr->n_stage2;
+  p.n_stage2 = w->h_ctr->n_cand;
+  p.n_verified = w->h_ctr->n_verified;
   p.n_matches = w->h_ctr->n_matches;
   p.launches = launches; p.retries = retries;
   std::lock_guard<std::mutex> g(ix->mu);
@@ -801,9 +837,9 @@ extern "C" int64_t fm_debug_last_slices(fm_index* index, int32_t* rec, int64_t* 
   cudaDeviceSynchronize();
   const int64_t n_big = std::min<int64_t>(cap, (int64_t)(w->h_ctr->slice_elem >> kElemBits));
   const int64_t n_small = std::min<int64_t>(cap - n_big, (int64_t)w->h_ctr->n_small);
-  cudaMemcpy(rec, w->sl_rec, n_big * sizeof(int4), cudaMemcpyDeviceToHost);
+  cudaMemcpy2D(rec, sizeof(int4), w->sl_rec, 2 * sizeof(int4), sizeof(int4), n_big, cudaMemcpyDeviceToHost);  // first half of each record
   cudaMemcpy(start, w->sl_start, n_big * sizeof(long long), cudaMemcpyDeviceToHost);
-  cudaMemcpy(rec + 4 * n_big, w->sm_rec, n_small * sizeof(int4), cudaMemcpyDeviceToHost);  // (no flattened start)
+  cudaMemcpy2D(rec + 4 * n_big, sizeof(int4), w->sm_rec, 2 * sizeof(int4), sizeof(int4), n_small, cudaMemcpyDeviceToHost);  // (no flattened start)
   for (int64_t i = 0; i < n_small; i++) start[n_big + i] = -1;
   return n_big + n_small;
 }

@@ -96,13 +96,15 @@ struct SurvRec {  // one distinct (query, sentence) that passed both rejection b
 struct Counters {
   unsigned long long slice_elem;  // (n_slices << 38) | n_elements, one packed atomic
   unsigned int n_surv;
-  unsigned int overflow;  // bit0 slices, bit1 survivors, bit2 span index
+  unsigned int overflow;  // bit0 slices, bit1 survivors, bit2 span index, bit3 candidate list
   unsigned int n_matches;
   unsigned int n_heavy;  // queries with more than kWarpMax scored candidates (CTA each)
   unsigned int n_mid;    // queries with 2..kWarpMax scored candidates (warp each)
-  unsigned int n_stage2;  // elements that passed stage 1 of the gather (profiling)
+  unsigned int n_stage2;  // (unused)
   unsigned int n_small;  // slices of at most kSmallSlice elements (their own list, a lane each)
   unsigned int n_long;  // bit0 / bit1: some survivor's pattern is too long for the first / second scoring kernel
+  unsigned int n_cand;   // suffix-array elements that passed stage 1 of the gather (the candidate list)
+  unsigned int n_verified;  // exact coverage counts (profiling)
 };
 static const int kElemBits = 38;
 static const int kSmallSlice = 4;
@@ -132,8 +134,9 @@ struct BatchDev {
   unsigned long long* peq64;  // [n_tok] patterns of <= 64 tokens: position mask of each distinct word, at q_off + distinct index
   // search output: slices of more than kSmallSlice elements, flattened, and the small ones
   long long* sl_start;  // [slice_cap+1] first flattened element of each slice (ascending)
-  int4* sl_rec;         // [slice_cap] (q, sa_begin, match_len | p << 10 | mult << 20, size)
-  int4* sm_rec;         // [slice_cap] same record, slices of <= kSmallSlice elements
+  int4* sl_rec;         // [2*slice_cap] per slice (q, sa_begin, match_len | p << 10 | mult << 20, size) and the query's
+                        //               signature planes (qmask[q]): everything stage 1 needs in one 32-byte record
+  int4* sm_rec;         // [2*slice_cap] same records, slices of <= kSmallSlice elements
   int64_t slice_cap;
   int32_t* span_slice;  // [span_cap] slice holding flattened element k*kSpan
   int64_t span_cap;
@@ -141,6 +144,8 @@ struct BatchDev {
   unsigned long long* hkey;  // [hsize] (q<<32 | start), ~0 = empty
   unsigned int* hlm;         // [hsize] max match length
   uint32_t hmask;
+  int2* cand;         // [cand_cap] walk kernel -> verify kernel: (q | match length << 20, suffix-array index)
+  int64_t cand_cap;
   SurvRec* surv;      // [surv_cap]
   uint16_t* surv_len; // [surv_cap]
   int64_t surv_cap;
@@ -177,7 +182,7 @@ struct Workspace {
   int64_t surv_hint = -1;         // survivors of the previous batch on this workspace: sizes the dedup table
   uint32_t hs_use = 0;            // dedup-table slots cleared and used by the batch in flight (power of two <= hsize)
   // capacities
-  int64_t cap_q = 0, cap_tok = 0, cap_slices = 0, cap_surv = 0, cap_out = 0;
+  int64_t cap_q = 0, cap_tok = 0, cap_slices = 0, cap_surv = 0, cap_out = 0, cap_cand = 0;
   uint32_t hsize = 0;
   // device buffers
   int32_t *d_q_tok = nullptr, *d_q_off = nullptr;  // staging for host inputs
@@ -205,6 +210,7 @@ struct Workspace {
   unsigned long long* hkey = nullptr;
   unsigned int* hlm = nullptr;
   SurvRec* surv = nullptr;
+  int2* cand = nullptr;
   uint16_t* surv_len = nullptr;
   int32_t *q_cnt = nullptr, *q_base = nullptr, *acc_cnt = nullptr, *heavy_q = nullptr, *m_heavy = nullptr, *mid_q = nullptr, *m_mid = nullptr;
   fm_record* rec = nullptr;
@@ -278,7 +284,7 @@ int gpu_suffix_sort(const int32_t* d_tok, int64_t n_buf, const std::vector<int32
 void launch_bounds(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st);
 void launch_prepare(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st);
 void launch_search(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st);
-void launch_gather(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st);
+void launch_gather(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st);  // walk + verify
 void launch_scan(const int32_t* in, int32_t* out, int32_t n, unsigned long long* chain, unsigned int epoch, int sm_count,
                  cudaStream_t st);
 void launch_score(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st);

@@ -100,7 +100,7 @@ static const int kNeedReject = 0xffff, kNeedNoTable = 0xfffe;
 // no table.
 __global__ void __launch_bounds__(256) fm_bounds_kernel(int max_tokens, Params pr, uint16_t* cmin_tab, uint16_t* cmin64) {
   const int lane = threadIdx.x & 31;
-  const int p = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) + 1;
+  const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // row 0 exists for idle lanes of the walk
   if (p > max_tokens) return;
   const bool fast = pr.ins >= 0.f && pr.del >= 0.f && pr.rep >= 0.f;  // reject_cover is monotone in the coverage for costs >= 0
   uint16_t* row = cmin_tab + (p << 10);
@@ -346,17 +346,21 @@ __device__ __forceinline__ void flush_slices(const BatchDev& b, SliceBuf& sb, in
     if (slot + n_big > b.slice_cap || sslot + (nbuf - n_big) > b.slice_cap) {
       atomicOr(&b.ctr->overflow, 1u);
     } else {
+      const int4 planes = __ldg(b.qmask + q);  // travels with every slice: the walk needs no per-query load
       for (int k = 0; k < nbuf; k++) {
         const int sz = sb.sz[k][threadIdx.x];
         const int4 rec = make_int4(q, sb.beg[k][threadIdx.x], sb.lm[k][threadIdx.x] | tag, sz);
         if (sz > kSmallSlice) {
           b.sl_start[slot] = start;
-          b.sl_rec[slot] = rec;
+          b.sl_rec[2 * slot] = rec;
+          b.sl_rec[2 * slot + 1] = planes;
           note_spans(b, slot, start, sz);
           slot++;
           start += sz;
         } else {
-          b.sm_rec[sslot++] = rec;
+          b.sm_rec[2 * sslot] = rec;
+          b.sm_rec[2 * sslot + 1] = planes;
+          sslot++;
         }
       }
     }
@@ -547,27 +551,194 @@ __device__ __forceinline__ int cover_sentence(const int32_t* __restrict__ sent, 
   return cover;
 }
 
+__device__ __forceinline__ void ldg_nc_v8(const void* p, unsigned (&r)[8]) {  // one 256-bit load (32-byte aligned)
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Stage 1 for one walk record: upper bound on the coverage from the signature against the smallest
+// coverage that passes for this (pattern length, sentence length). row = cmin64 + (p << 6); m = the
+// query's planes (B0 lo, B0 hi, B1 lo, B1 hi). Branch-free; the rare correction for signature bits that
+// collect more than three pattern positions (mult != 0, uniform over a slice) is added by the caller.
+__device__ __forceinline__ int stage1_margin(unsigned lo, unsigned hi, const int4& m, const uint16_t* __restrict__ row) {
+  const int need = __ldg(row + (lo & 63u));
+  return __popc(lo & (unsigned)m.x) + __popc(hi & (unsigned)m.y) + 2 * (__popc(lo & (unsigned)m.z) + __popc(hi & (unsigned)m.w)) - need;
+}
+__device__ __forceinline__ int stage1_extra(unsigned lo, unsigned hi, const int4& m, int mult) {
+  return mult * (__popc(lo & (unsigned)m.x & (unsigned)m.z) + __popc(hi & (unsigned)m.y & (unsigned)m.w));
+}
+
+// "Suffix-range gather", first kernel: register_suffix_range_match's walk (src/ngram_matches.cc:62-84) with
+// the signature form of the coverage filter (src/fuzzy_match.cc:576-581) evaluated per element: one 8-byte
+// walk record -- length and 58-bit signature -- against the query's planes and the per-length bound table;
+// no sentence is touched. A pure streaming filter: the elements that pass go to the candidate list
+// (q | match length << 20, suffix-array index) and are looked at by fm_verify_kernel.
+// A CTA takes blocks of work in turn (the grid is larger than what is resident, so the hardware balances
+// the CTAs):
+//  * a block of flattened elements, kSpan per warp. Slices of more than kSmallSlice elements (94 % of the
+//    elements sit in slices of 33 or more) are flattened; a warp walks its span slice by slice, four records
+//    per lane from one 256-bit load. The 32-byte slice records of the span (query, range, planes) are
+//    fetched by the lanes in one go into shared memory and every line of the span is prefetched into L2
+//    before the walk starts;
+//  * or a block of small slices (three quarters of all slices hold one suffix), one slice per thread.
+// Candidates are collected per CTA in shared memory; one atomic per block reserves their place in the list.
+#ifndef FM_GATHER_CTAS
+#define FM_GATHER_CTAS 5
+#endif
+static const int kWalkQueue = 8 * kSpan;  // every element of a block may pass
+struct SliceWin {  // the slice records of the span a warp is walking
+  int4 rec[32];
+  int4 planes[32];
+  int st[32];  // first flattened element of the slice, relative to the span start
+};
+__device__ __forceinline__ void block_push(int2* queue, int* n, bool pass, int2 item, int lane) {
+  const unsigned bal = __ballot_sync(FULL, pass);
+  if (!bal) return;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(n, __popc(bal));
+  base = __shfl_sync(FULL, base, 0);
+  if (pass) queue[base + __popc(bal & ((1u << lane) - 1))] = item;
+}
+__global__ void __launch_bounds__(256, FM_GATHER_CTAS) fm_gather_kernel(IndexDev ix, BatchDev b) {
+  __shared__ int2 s_queue[kWalkQueue];
+  __shared__ SliceWin s_win[8];
+  __shared__ int s_n, s_base;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  SliceWin& win = s_win[wib];
+  // A worklist of the search overflowed: the host regrows and reruns. One decision per CTA (the CTA's warps
+  // work together below). An overflow of the candidate list itself (bit 3, set by other CTAs of this kernel)
+  // does not stop the walk: the count goes on, so that the host learns the size to regrow to.
+  if (threadIdx.x == 0) s_n = (int)(b.ctr->overflow & 5u);
+  __syncthreads();
+  const bool stop = s_n != 0;
+  __syncthreads();
+  if (stop) return;
+  const unsigned long long packed = b.ctr->slice_elem;
+  const long long total = (long long)(packed & ((1ull << kElemBits) - 1));
+  const int n_big = (int)(packed >> kElemBits);
+  const int n_small = (int)b.ctr->n_small;
+  const int n_spans = (int)((total + kSpan - 1) / kSpan);
+  const int span_blocks = (n_spans + 7) >> 3, small_blocks = (n_small + 255) >> 8;
+  for (int blk = blockIdx.x; blk < span_blocks + small_blocks; blk += gridDim.x) {
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    if (blk < span_blocks) {
+      const int sp = blk * 8 + wib;
+      if (sp < n_spans) {
+        const long long span_base = (long long)sp * kSpan;
+        const int span_len = (int)min((long long)kSpan, total - span_base);
+        int k = __ldg(b.span_slice + sp);  // slice that holds the first element of the span
+        int kwin = k - 32;
+        int pos = 0;
+        while (pos < span_len) {
+          if (k >= kwin + 32) {  // fetch the records of slices k .. k+31, one per lane, and prefetch their elements
+            kwin = k;
+            __syncwarp();
+            int4 r0 = make_int4(0, 0, 0, 0);
+            int st = 1 << 30;
+            if (k + lane < n_big) {
+              r0 = __ldg(b.sl_rec + 2 * (k + lane));
+              win.rec[lane] = r0;
+              win.planes[lane] = __ldg(b.sl_rec + 2 * (k + lane) + 1);
+              st = (int)max(-(1ll << 31), min(1ll << 30, __ldg(b.sl_start + k + lane) - span_base));
+              win.st[lane] = st;
+            }
+            // lane l: the part of slice k + l inside the rest of the span, as 128-byte lines of walk records
+            const int e0 = max(st, pos), e1 = min((int)min((long long)st + r0.w, (long long)span_len), span_len);
+            if (e0 < e1) {
+              const uint2* p0 = ix.sa_rec + (r0.y + (e0 - st));
+              const uint2* p1 = ix.sa_rec + (r0.y + (e1 - st) - 1);
+              for (uintptr_t a = (uintptr_t)p0 & ~(uintptr_t)127; a <= (uintptr_t)p1; a += 128) prefetch_l2((const void*)a);
+            }
+            __syncwarp();
+          }
+          const int4 sr = win.rec[k - kwin];  // (q, sa_begin, lm | p << 10 | mult << 20, size), same for all lanes
+          const int4 m = win.planes[k - kwin];
+          const int st = win.st[k - kwin];
+          const int seg_end = (int)min((long long)st + sr.w, (long long)span_len);
+          const int mult = sr.z >> 20;
+          const uint16_t* row = b.cmin64 + (((sr.z >> 10) & 1023) << 6);
+          const int qlm = sr.x | ((sr.z & 1023) << 20);
+          const int a0 = sr.y + (pos - st), a1 = sr.y + (seg_end - st);  // suffix-array indices [a0, a1)
+          const unsigned len = (unsigned)(a1 - a0);
+          pos = seg_end;
+          k++;
+          for (int g = a0 & ~3; g < a1; g += 128) {  // 256-bit loads cover aligned groups of four records
+            const int base = g + 4 * lane;
+            unsigned r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (base < a1) ldg_nc_v8(ix.sa_rec + base, r);
+            int d0 = stage1_margin(r[0], r[1], m, row), d1 = stage1_margin(r[2], r[3], m, row);
+            int d2 = stage1_margin(r[4], r[5], m, row), d3 = stage1_margin(r[6], r[7], m, row);
+            if (mult) {  // (uniform)
+              d0 += stage1_extra(r[0], r[1], m, mult); d1 += stage1_extra(r[2], r[3], m, mult);
+              d2 += stage1_extra(r[4], r[5], m, mult); d3 += stage1_extra(r[6], r[7], m, mult);
+            }
+            const unsigned rel = (unsigned)(base - a0);  // element base + i is inside iff rel + i < len (unsigned)
+            const bool p0 = (d0 >= 0) & (rel < len), p1 = (d1 >= 0) & (rel + 1u < len);
+            const bool p2 = (d2 >= 0) & (rel + 2u < len), p3 = (d3 >= 0) & (rel + 3u < len);
+            if (__any_sync(FULL, p0 | p1 | p2 | p3)) {
+              block_push(s_queue, &s_n, p0, make_int2(qlm, base), lane);
+              block_push(s_queue, &s_n, p1, make_int2(qlm, base + 1), lane);
+              block_push(s_queue, &s_n, p2, make_int2(qlm, base + 2), lane);
+              block_push(s_queue, &s_n, p3, make_int2(qlm, base + 3), lane);
+            }
+          }
+        }
+      }
+    } else {
+      const int si = (blk - span_blocks) * 256 + threadIdx.x;
+      int4 sr = make_int4(0, 0, 0, 0), sm = make_int4(0, 0, 0, 0);
+      if (si < n_small) {
+        sr = __ldg(b.sm_rec + 2 * si);
+        sm = __ldg(b.sm_rec + 2 * si + 1);
+      }
+      const uint16_t* srow = b.cmin64 + (((sr.z >> 10) & 1023) << 6);
+      const int smult = sr.z >> 20, sqlm = sr.x | ((sr.z & 1023) << 20);
+      uint2 rec[kSmallSlice];
+#pragma unroll
+      for (int e = 0; e < kSmallSlice; e++) rec[e] = e < sr.w ? __ldg(ix.sa_rec + sr.y + e) : make_uint2(0u, 0u);
+#pragma unroll
+      for (int e = 0; e < kSmallSlice; e++) {
+        const bool pass = (e < sr.w) & (stage1_margin(rec[e].x, rec[e].y, sm, srow) + stage1_extra(rec[e].x, rec[e].y, sm, smult) >= 0);
+        block_push(s_queue, &s_n, pass, make_int2(sqlm, sr.y + e), lane);
+      }
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (n) {  // (uniform)
+      if (threadIdx.x == 0) s_base = (int)atomicAdd(&b.ctr->n_cand, (unsigned)n);
+      __syncthreads();
+      const long long base = (unsigned)s_base;
+      if (base + n <= b.cand_cap) {
+        for (int i = threadIdx.x; i < n; i += 256) b.cand[base + i] = s_queue[i];
+      } else if (threadIdx.x == 0) {
+        atomicOr(&b.ctr->overflow, 8u);  // the count goes on, so that the host knows the size to regrow to
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // Insert (q, start) into the dedup table keeping the max match length: NGramMatches::_longest_matches
-// (src/ngram_matches.cc:79-81). The first inserter also claims the candidate's slot inside its query.
-__device__ __forceinline__ int add_survivor(const BatchDev& b, int q, int start, int slen, int lm) {
+// (src/ngram_matches.cc:79-81). The survivor's slot in the compact list comes from the caller (reserved per
+// CTA); the first inserter also claims the candidate's slot inside its query.
+struct SurvStage {  // survivors of one CTA block, staged in shared memory
+  SurvRec rec[512];
+  uint16_t len[512];
+};
+__device__ __forceinline__ int add_survivor(const BatchDev& b, SurvStage& stage, int* n_stage, int q, int start, int slen, int lm) {
   const unsigned long long key = ((unsigned long long)(unsigned)q << 32) | (unsigned)start;
   uint32_t h = hash64(key) & b.hmask;
-  if (*(volatile unsigned int*)&b.ctr->n_surv >= (unsigned long long)b.surv_cap) {  // table (4x cap) must never fill up
-    atomicOr(&b.ctr->overflow, 2u);
-    return -1;
-  }
-  for (;;) {
+  for (int probes = 0; probes < 4096; probes++) {
     const unsigned long long prev = atomicCAS(&b.hkey[h], ~0ull, key);
     if (prev == ~0ull) {
-      const unsigned idx = atomicAdd(&b.ctr->n_surv, 1u);
-      if ((long long)idx >= b.surv_cap) {
-        atomicOr(&b.ctr->overflow, 2u);
-        return -1;
-      }
       const int j = atomicAdd(&b.q_cnt[q], 1);
       atomicMax(&b.hlm[h], (unsigned)lm);
-      b.surv[idx] = SurvRec{q, start, (int32_t)h, j};
-      b.surv_len[idx] = (uint16_t)slen;
+      const int i = atomicAdd(n_stage, 1);
+      stage.rec[i] = SurvRec{q, start, (int32_t)h, j};
+      stage.len[i] = (uint16_t)slen;
       return (int)h;
     }
     if (prev == key) {
@@ -576,44 +747,49 @@ __device__ __forceinline__ int add_survivor(const BatchDev& b, int q, int start,
     }
     h = (h + 1) & b.hmask;
   }
+  atomicOr(&b.ctr->overflow, 2u);  // (a probe sequence this long: the table is all but full)
+  return -1;
 }
 // Slot of (q, start) if it already is a survivor, else -1 (a concurrent insert may be missed: the caller
 // then verifies the pair again, which is harmless).
 __device__ __forceinline__ int find_survivor(const BatchDev& b, int q, int start) {
   const unsigned long long key = ((unsigned long long)(unsigned)q << 32) | (unsigned)start;
   uint32_t h = hash64(key) & b.hmask;
-  for (;;) {
+  for (int probes = 0; probes < 4096; probes++) {
     const unsigned long long k = *(volatile const unsigned long long*)&b.hkey[h];
     if (k == key) return (int)h;
     if (k == ~0ull) return -1;
     h = (h + 1) & b.hmask;
   }
+  return -1;
 }
 
-// Second stage of the gather: candidates that survived stage 1, taken from the warp's queue.
-// item = (q | match length << 20, suffix-array index). Each lane resolves one item -- walk record,
-// sentence start, the query's length / table offset, the smallest passing coverage for this length pair --
-// and then:
+// "Suffix-range gather", second kernel: the candidates of the walk, 32 per warp and round. Each lane
+// resolves one item -- walk record, sentence start, the query's length / table offset, the smallest passing
+// coverage for this length pair -- and then:
 //  * sentences with a wide signature (longer than kWideMin tokens): first the upper bound on the coverage
 //    from the 1024-bit signature and the query's bit-sliced planes -- 8 lanes per candidate, 128-bit loads,
 //    4 candidates per round -- so that only plausible pairs reach the exact count;
 //  * patterns of up to 32 words against short sentences: exact coverage, one candidate per lane, the set
-//    of distinct words seen is one register;
+//    of distinct words seen is one register, the count stops as soon as the bound is met;
 //  * everything else: one candidate at a time, the 32 lanes probe the sentence's tokens in parallel and
 //    mark the distinct words in a shared-memory bit set (PatternCoverage::count_covered_words,
 //    src/pattern_coverage.cc:15-28).
-struct Cand {  // a resolved queue item, exchanged between lanes through shared memory
+// A pair that passes the coverage bound (theoretical_rejection_cover, src/ngram_matches.cc:42-59) enters the
+// dedup table with its match length; survivors are staged per CTA and appended to the compact list with
+// one atomic per block of 512 candidates.
+struct Cand {  // a resolved candidate, exchanged between lanes through shared memory
   int q_lm;    // q | match length << 20
   int start;   // sentence start in tok
   int len_need;  // sentence length | need << 16 (need = 0xffff: no bound table, evaluate the bounds)
   int wrow;    // wide signature row or -1
 };
-__device__ __forceinline__ void verify_candidates(const IndexDev& ix, const BatchDev& b, const Params& pr, const int2* queue, int n,
-                                                  Cand* cand, unsigned* seen, int lane) {
+__device__ __forceinline__ int verify_candidates(const IndexDev& ix, const BatchDev& b, const Params& pr, const int2* items, int n,
+                                                 Cand* cand, unsigned* seen, SurvStage& stage, int* n_stage, int lane) {
   bool have = lane < n;
   int q = 0, lm = 0, start = 0, slen = 0, need = 0, wrow = -1, p = 0, off = 0;
   if (have) {
-    const int2 item = queue[lane];
+    const int2 item = items[lane];
     q = item.x & 0xfffff;
     lm = item.x >> 20;
     const uint2 rec = __ldg(ix.sa_rec + item.y);
@@ -633,10 +809,10 @@ __device__ __forceinline__ void verify_candidates(const IndexDev& ix, const Batc
       if (reject_length(p, slen, pr)) have = false;
     }
   }
-  // The sentence a query really matches is reached through many of its n-grams, so most candidates are
-  // repeats of a pair that has been verified already: those only raise the recorded match length
+  // The sentence a query really matches is reached through many of its n-grams, so many candidates are
+  // repeats of a pair that is a survivor already: those only raise the recorded match length
   // (NGramMatches::_longest_matches keeps the maximum, src/ngram_matches.cc:79-81). Repeats inside this
-  // batch are verified once, by their lowest lane.
+  // round are verified once, by their lowest lane.
   int slot = -1;
   if (have) {
     slot = find_survivor(b, q, start);
@@ -650,12 +826,16 @@ __device__ __forceinline__ void verify_candidates(const IndexDev& ix, const Batc
   const bool repeat = have && leader != lane;
   if (repeat) have = false;
   slot = -1;
-  __syncwarp();
-  cand[lane] = Cand{q | (lm << 20), start, slen | (need << 16), wrow};
-  __syncwarp();
+  const int n_verified = __popc(__ballot_sync(FULL, have));
   const bool wide = have && wrow >= 0;
-  unsigned wide_pass = __ballot_sync(FULL, wide && need == 0xffff);  // no bound table: straight to the exact count
-  {
+  unsigned wide_pass = 0;
+  if (__any_sync(FULL, (have && p > 32) || wide)) {
+    __syncwarp();
+    cand[lane] = Cand{q | (lm << 20), start, slen | (need << 16), wrow};
+    __syncwarp();
+  }
+  if (__any_sync(FULL, wide)) {
+    wide_pass = __ballot_sync(FULL, wide && need == 0xffff);  // no bound table: straight to the exact count
     unsigned todo = __ballot_sync(FULL, wide && need != 0xffff);
     const int grp = lane >> 3, sub = lane & 7;
     const unsigned gmask = 0xffu << (8 * grp);
@@ -692,7 +872,7 @@ __device__ __forceinline__ void verify_candidates(const IndexDev& ix, const Batc
     } else {
       ok = cover_sentence<1>(ix.tok + start, slen, tbl, tmask, need) >= need;
     }
-    if (ok) slot = add_survivor(b, q, start, slen, lm);
+    if (ok) slot = add_survivor(b, stage, n_stage, q, start, slen, lm);
   }
   unsigned todo = __ballot_sync(FULL, have && !wide && p > 32) | wide_pass;
   while (todo) {
@@ -726,160 +906,56 @@ __device__ __forceinline__ void verify_candidates(const IndexDev& ix, const Batc
     __syncwarp();
     const bool ok = cneed == 0xffff ? !reject_cover(cp, cslen, cover, pr) : cover >= cneed;
     int hs = -1;
-    if (ok && lane == 0) hs = add_survivor(b, cq, cstart, cslen, clm);
+    if (ok && lane == 0) hs = add_survivor(b, stage, n_stage, cq, cstart, cslen, clm);
     hs = __shfl_sync(FULL, hs, 0);
     if (lane == src) slot = hs;
   }
   const int lslot = __shfl_sync(FULL, slot, leader);
   if (repeat && lslot >= 0) atomicMax(&b.hlm[lslot], (unsigned)lm);
+  return n_verified;
 }
 
-__device__ __forceinline__ void ldg_nc_v8(const void* p, unsigned (&r)[8]) {  // one 256-bit load (32-byte aligned)
-  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "l"(p));
-}
-
-// Warp-level queue of stage-1 survivors in shared memory; drained 32 at a time so that stage 2 runs with
-// full warps.
-static const int kQueue = 160;  // 31 left over + up to 128 new ones per round
-struct WarpQueue {
-  int2* items;
-  Cand* cand;
-  unsigned* seen;
-  int n;
-};
-__device__ __forceinline__ void queue_push(WarpQueue& wq, bool pass, int2 item, int lane) {
-  const unsigned bal = __ballot_sync(FULL, pass);
-  if (pass) wq.items[wq.n + __popc(bal & ((1u << lane) - 1))] = item;
-  wq.n += __popc(bal);
-}
-
-// Stage 1 for one walk record: upper bound on the coverage from the signature against the smallest
-// coverage that passes for this (pattern length, sentence length). row = cmin64 + (p << 6); m = the
-// query's planes (B0 lo, B0 hi, B1 lo, B1 hi). Branch-free; the rare correction for signature bits that
-// collect more than three pattern positions (mult != 0, uniform over a slice) is added by the caller.
-__device__ __forceinline__ int stage1_margin(unsigned lo, unsigned hi, const int4& m, const uint16_t* __restrict__ row) {
-  const int need = __ldg(row + (lo & 63u));
-  return __popc(lo & (unsigned)m.x) + __popc(hi & (unsigned)m.y) + 2 * (__popc(lo & (unsigned)m.z) + __popc(hi & (unsigned)m.w)) - need;
-}
-__device__ __forceinline__ int stage1_extra(unsigned lo, unsigned hi, const int4& m, int mult) {
-  return mult * (__popc(lo & (unsigned)m.x & (unsigned)m.z) + __popc(hi & (unsigned)m.y & (unsigned)m.w));
-}
-
-// Persistent kernel over all range slices: register_suffix_range_match's walk (src/ngram_matches.cc:62-84)
-// fused with the candidate filter of src/fuzzy_match.cc:576-581.
-// Stage 1 (every element): one 8-byte walk record -- length and 58-bit signature -- against the query's
-// masks and the per-length bound table; no sentence is touched.
-//  * Slices of more than kSmallSlice elements (94 % of the elements sit in slices of 33 or more) are
-//    flattened; a warp takes spans of kSpan consecutive elements and walks them slice by slice with the
-//    slice's query constants in registers, four records per lane from one 256-bit load.
-//  * Small slices (three quarters of all slices hold one suffix): one slice per lane.
-// Stage 2 (the few that pass): queued per warp in shared memory and verified 32 at a time. The warp
-// alternates between producing (stage 1, until 32 candidates are queued or the work is done) and
-// consuming (one call site of the stage-2 code).
-#ifndef FM_GATHER_CTAS
-#define FM_GATHER_CTAS 5
-#endif
-__global__ void __launch_bounds__(256, FM_GATHER_CTAS) fm_gather_kernel(IndexDev ix, BatchDev b, Params pr) {
-  __shared__ int2 s_queue[8][kQueue];
+__global__ void __launch_bounds__(256) fm_verify_kernel(IndexDev ix, BatchDev b, Params pr) {
+  __shared__ SurvStage s_stage;
   __shared__ Cand s_cand[8][32];
   __shared__ unsigned s_seen[8][32];
+  __shared__ int s_n, s_base;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  WarpQueue wq{s_queue[wib], s_cand[wib], s_seen[wib], 0};
-  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const unsigned long long packed = b.ctr->slice_elem;
-  const long long total = (long long)(packed & ((1ull << kElemBits) - 1));
-  const long long n_small = (long long)b.ctr->n_small;
-  if (b.ctr->overflow) return;  // a worklist overflowed: the host regrows and reruns
-
-  // producer state: the small slices first (phase 0), then the flattened spans (phase 1). The sentence a
-  // query really matches sits at the deep end of most of its chains, i.e. in small slices that are adjacent
-  // in the list (chains of one query are searched by neighbouring threads): taking them first puts those
-  // pairs into the dedup table once, and the repeats among the flattened elements skip stage 2.
-  int phase = 0;
-  long long span = warp_id * kSpan, pos = 0, span_end = 0, k = 0;  // current span / position / slice
-  int g = 0, a0 = 0, a1 = 0, qlm = 0, mult = 0;                   // current segment: suffix-array indices [a0, a1), next group g
-  int4 m = make_int4(0, 0, 0, 0);
-  const uint16_t* row = b.cmin64;
-  long long s0 = warp_id * 32;
-  bool in_span = false;
-  unsigned stage2 = 0;
-  for (;;) {
-    // ---- produce until a full batch of candidates is queued
-    while (phase < 2 && wq.n < 32) {
-      if (phase == 1) {
-        if (g >= a1) {  // next segment
-          if (!in_span || pos >= span_end) {  // next span
-            if (in_span) span += n_warps * kSpan;
-            if (span >= total) { phase = 2; continue; }
-            in_span = true;
-            span_end = min(span + kSpan, total);
-            pos = span;
-            k = __ldg(b.span_slice + span / kSpan);  // slice that holds the first element of the span
-          }
-          const int4 sr = __ldg(b.sl_rec + k);  // (q, sa_begin, lm | p << 10 | mult << 20, size), same for all lanes
-          const long long st = __ldg(b.sl_start + k);
-          const long long seg_end = min(st + sr.w, span_end);
-          m = __ldg(b.qmask + sr.x);
-          mult = sr.z >> 20;
-          row = b.cmin64 + (((sr.z >> 10) & 1023) << 6);
-          qlm = sr.x | ((sr.z & 1023) << 20);
-          a0 = sr.y + (int)(pos - st);
-          a1 = sr.y + (int)(seg_end - st);
-          g = a0 & ~3;  // 256-bit loads cover aligned groups of four records
-          pos = seg_end;
-          k++;
-        }
-        const int base = g + 4 * lane;
-        unsigned r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (base < a1) ldg_nc_v8(ix.sa_rec + base, r);
-        int d0 = stage1_margin(r[0], r[1], m, row), d1 = stage1_margin(r[2], r[3], m, row);
-        int d2 = stage1_margin(r[4], r[5], m, row), d3 = stage1_margin(r[6], r[7], m, row);
-        if (mult) {  // (uniform)
-          d0 += stage1_extra(r[0], r[1], m, mult); d1 += stage1_extra(r[2], r[3], m, mult);
-          d2 += stage1_extra(r[4], r[5], m, mult); d3 += stage1_extra(r[6], r[7], m, mult);
-        }
-        const unsigned len = (unsigned)(a1 - a0), rel = (unsigned)(base - a0);  // element base + i is inside iff rel + i < len (unsigned)
-        const bool p0 = (d0 >= 0) & (rel < len), p1 = (d1 >= 0) & (rel + 1u < len);
-        const bool p2 = (d2 >= 0) & (rel + 2u < len), p3 = (d3 >= 0) & (rel + 3u < len);
-        if (__any_sync(FULL, p0 | p1 | p2 | p3)) {
-          queue_push(wq, p0, make_int2(qlm, base), lane);
-          queue_push(wq, p1, make_int2(qlm, base + 1), lane);
-          queue_push(wq, p2, make_int2(qlm, base + 2), lane);
-          queue_push(wq, p3, make_int2(qlm, base + 3), lane);
-        }
-        g += 128;
-      } else {
-        if (s0 >= n_small) { phase = 1; continue; }
-        const long long si = s0 + lane;
-        int4 sr = make_int4(0, 0, 0, 0);
-        if (si < n_small) sr = __ldg(b.sm_rec + si);
-        const int4 sm = __ldg(b.qmask + sr.x);
-        const uint16_t* srow = b.cmin64 + (((sr.z >> 10) & 1023) << 6);
-        const int smult = sr.z >> 20, sqlm = sr.x | ((sr.z & 1023) << 20);
-        uint2 rec[kSmallSlice];
-#pragma unroll
-        for (int e = 0; e < kSmallSlice; e++) rec[e] = e < sr.w ? __ldg(ix.sa_rec + sr.y + e) : make_uint2(0u, 0u);
-#pragma unroll
-        for (int e = 0; e < kSmallSlice; e++) {
-          const bool pass = (e < sr.w) & (stage1_margin(rec[e].x, rec[e].y, sm, srow) + stage1_extra(rec[e].x, rec[e].y, sm, smult) >= 0);
-          if (__any_sync(FULL, pass)) queue_push(wq, pass, make_int2(sqlm, sr.y + e), lane);
-        }
-        s0 += n_warps * 32;
-      }
+  // one decision per CTA: other CTAs of this kernel may raise the flag while this one starts
+  if (threadIdx.x == 0) s_n = (int)b.ctr->overflow;
+  __syncthreads();
+  const bool stop = s_n != 0;
+  __syncthreads();
+  if (stop) return;
+  const long long n_cand = (long long)b.ctr->n_cand;
+  const int n_blocks = (int)((n_cand + 511) >> 9);
+  int verified = 0;
+  for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int r = 0; r < 2; r++) {
+      const long long first = (long long)blk * 512 + (r * 8 + wib) * 32;
+      const int n = (int)min(32ll, n_cand - first);
+      if (n > 0) verified += verify_candidates(ix, b, pr, b.cand + first, n, s_cand[wib], s_seen[wib], s_stage, &s_n, lane);
     }
-    // ---- consume one batch
-    if (wq.n == 0) break;  // (phase == 2)
-    __syncwarp();
-    const int take = min(wq.n, 32);
-    wq.n -= take;
-    stage2 += take;
-    verify_candidates(ix, b, pr, wq.items + wq.n, take, wq.cand, wq.seen, lane);
-    __syncwarp();
+    __syncthreads();
+    const int n = s_n;
+    if (n) {  // (uniform)
+      if (threadIdx.x == 0) s_base = (int)atomicAdd(&b.ctr->n_surv, (unsigned)n);
+      __syncthreads();
+      const long long base = (unsigned)s_base;
+      if (base + n <= b.surv_cap) {
+        for (int i = threadIdx.x; i < n; i += 256) {
+          b.surv[base + i] = s_stage.rec[i];
+          b.surv_len[base + i] = s_stage.len[i];
+        }
+      } else if (threadIdx.x == 0) {
+        atomicOr(&b.ctr->overflow, 2u);
+      }
+      __syncthreads();
+    }
   }
-  if (lane == 0 && stage2) atomicAdd(&b.ctr->n_stage2, stage2);
+  if (lane == 0 && verified) atomicAdd(&b.ctr->n_verified, (unsigned)verified);
 }
 
 // ---------------------------------------------------------------- scan (<= 128 co-resident CTAs)
@@ -1918,7 +1994,7 @@ __global__ void fm_merge_copy_kernel(ShardPtrs sp, int n_shards, const int32_t* 
 static int dp_stride(const IndexDev& ix) { return ((ix.max_tokens + 31) / 32) * 32 + 32; }
 
 void launch_bounds(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st) {
-  fm_bounds_kernel<<<(ix.max_tokens + 7) / 8, 256, 0, st>>>(ix.max_tokens, p, const_cast<uint16_t*>(b.cmin_tab),
+  fm_bounds_kernel<<<(ix.max_tokens + 8) / 8, 256, 0, st>>>(ix.max_tokens, p, const_cast<uint16_t*>(b.cmin_tab),
                                                             const_cast<uint16_t*>(b.cmin64));
 }
 void launch_prepare(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st) {
@@ -1931,7 +2007,9 @@ void launch_search(const IndexDev& ix, const BatchDev& b, const Params&, cudaStr
   if (grid > 0) fm_search_kernel<<<grid, 256, 0, st>>>(ix, b);
 }
 void launch_gather(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st) {
-  fm_gather_kernel<<<sm_count * FM_GATHER_CTAS, 256, 0, st>>>(ix, b, p);
+  // grids several times what is resident: CTAs that finish early make room for the next ones
+  fm_gather_kernel<<<sm_count * FM_GATHER_CTAS * 8, 256, 0, st>>>(ix, b);
+  fm_verify_kernel<<<sm_count * 4 * 4, 256, 0, st>>>(ix, b, p);
 }
 void launch_scan(const int32_t* in, int32_t* out, int32_t n, unsigned long long* chain, unsigned int epoch, int sm_count,
                  cudaStream_t st) {

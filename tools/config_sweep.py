@@ -31,7 +31,7 @@ def run(name, index, oracle, q, qo, cap, sample, **params):
     stages = {k[3:]: round(prof[k], 3) for k in prof if k.startswith("ms_")}
     print("%s: %d queries in %.1f ms e2e (%.0f q/s), found %d; oracle sample %d in %.2f s (%.0f q/s, %d threads); identical=%s"
           % (name, n_q, dt * 1e3, n_q / dt, int((cnt > 0).sum()), sample, cpu, sample / cpu, os.cpu_count(), same))
-    print("   stages(ms, last chunk):", stages, "elements", prof["n_elements"], "stage2", prof["n_stage2"], "survivors", prof["n_survivors"], "retries", prof["retries"])
+    print("   stages(ms, last chunk):", stages, "elements", prof["n_elements"], "stage2", prof["n_stage2"], "verified", prof["n_verified"], "survivors", prof["n_survivors"], "retries", prof["retries"])
     return same
 
 
