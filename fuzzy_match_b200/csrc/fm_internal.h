@@ -108,7 +108,7 @@ struct Counters {
 };
 static const int kElemBits = 38;
 static const int kSmallSlice = 4;
-static const int kSpan = 512;  // flattened elements per gather work unit
+static const int kSpan = 1024;  // flattened elements per gather work unit (one warp)
 
 // per-batch workspace pointers (device)
 struct BatchDev {

@@ -512,14 +512,15 @@ __global__ void __launch_bounds__(256, 8) fm_search_kernel(IndexDev ix, BatchDev
 
 // ---------------------------------------------------------------- gather
 
-// PatternCoverage::count_covered_words (src/pattern_coverage.cc:15-28) for one sentence token:
-// look the word up in the query's table; the first time a distinct pattern word is seen, add its
-// multiplicity. `seen` is a bitmask over distinct-word indices.
+// PatternCoverage::count_covered_words (src/pattern_coverage.cc:15-28): every sentence token is looked up in
+// the query's table; the first time a distinct pattern word is seen, its multiplicity is added. `seen` is
+// a bitmask over distinct-word indices.
+// Exact coverage of one sentence, stopping as soon as `need` is reached (the caller only compares
+// the result with `need`; pass need > p to get the exact count). The first probes of the four words of a
+// 128-bit load are issued together: the count is a chain of dependent table reads otherwise.
 template <int MW>
-__device__ __forceinline__ void cover_token(const int2* __restrict__ tbl, int tmask, int w, unsigned* seen, int& cover) {
-  int h = hash32((uint32_t)w) & tmask;
+__device__ __forceinline__ void cover_resolve(const int2* __restrict__ tbl, int tmask, int w, int h, int2 e, unsigned* seen, int& cover) {
   for (;;) {
-    const int2 e = __ldg(tbl + h);
     if (e.x == w) {
       const int d = e.y & 0xffff;
       const unsigned bit = 1u << (d & 31);
@@ -529,11 +530,9 @@ __device__ __forceinline__ void cover_token(const int2* __restrict__ tbl, int tm
     }
     if (e.x == -1) return;
     h = (h + 1) & tmask;
+    e = __ldg(tbl + h);
   }
 }
-
-// Exact coverage of one sentence, stopping as soon as `need` is reached (the caller only compares
-// the result with `need`; pass need > p to get the exact count).
 template <int MW>
 __device__ __forceinline__ int cover_sentence(const int32_t* __restrict__ sent, int slen, const int2* tbl, int tmask, int need) {
   unsigned seen[MW];
@@ -541,12 +540,17 @@ __device__ __forceinline__ int cover_sentence(const int32_t* __restrict__ sent, 
   for (int i = 0; i < MW; i++) seen[i] = 0;
   int cover = 0;
   const int4* s4 = reinterpret_cast<const int4*>(sent);
+  int4 t = ldg_nc_v4(s4);  // sentences start on 16-byte boundaries and are zero padded
   for (int k = 0; k < slen && cover < need; k += 4) {
-    const int4 t = ldg_nc_v4(s4 + (k >> 2));
-    cover_token<MW>(tbl, tmask, t.x, seen, cover);
-    if (k + 1 < slen) cover_token<MW>(tbl, tmask, t.y, seen, cover);
-    if (k + 2 < slen) cover_token<MW>(tbl, tmask, t.z, seen, cover);
-    if (k + 3 < slen) cover_token<MW>(tbl, tmask, t.w, seen, cover);
+    const int4 cur = t;
+    if (k + 4 < slen) t = ldg_nc_v4(s4 + (k >> 2) + 1);
+    const int h0 = hash32((uint32_t)cur.x) & tmask, h1 = hash32((uint32_t)cur.y) & tmask;
+    const int h2 = hash32((uint32_t)cur.z) & tmask, h3 = hash32((uint32_t)cur.w) & tmask;
+    const int2 e0 = __ldg(tbl + h0), e1 = __ldg(tbl + h1), e2 = __ldg(tbl + h2), e3 = __ldg(tbl + h3);
+    cover_resolve<MW>(tbl, tmask, cur.x, h0, e0, seen, cover);
+    if (k + 1 < slen) cover_resolve<MW>(tbl, tmask, cur.y, h1, e1, seen, cover);
+    if (k + 2 < slen) cover_resolve<MW>(tbl, tmask, cur.z, h2, e2, seen, cover);
+    if (k + 3 < slen) cover_resolve<MW>(tbl, tmask, cur.w, h3, e3, seen, cover);
   }
   return cover;
 }
@@ -587,32 +591,47 @@ __device__ __forceinline__ int stage1_extra(unsigned lo, unsigned hi, const int4
 #ifndef FM_GATHER_CTAS
 #define FM_GATHER_CTAS 5
 #endif
-static const int kWalkQueue = 8 * kSpan;  // every element of a block may pass
+static const int kWalkQueue = 3072;  // candidates of a block staged in shared memory (8 * kSpan elements; beyond: straight to the list)
 struct SliceWin {  // the slice records of the span a warp is walking
   int4 rec[32];
   int4 planes[32];
   int st[32];  // first flattened element of the slice, relative to the span start
 };
-__device__ __forceinline__ void block_push(int2* queue, int* n, bool pass, int2 item, int lane) {
+// nfill[0] = slots reserved so far, nfill[1] = end of the last reservation that fitted the shared-memory queue
+__device__ __forceinline__ void block_push(const BatchDev& b, int2* queue, int* nfill, bool pass, int2 item, int lane) {
   const unsigned bal = __ballot_sync(FULL, pass);
   if (!bal) return;
+  const int cnt = __popc(bal);
   int base = 0;
-  if (lane == 0) base = atomicAdd(n, __popc(bal));
+  if (lane == 0) base = atomicAdd(&nfill[0], cnt);
   base = __shfl_sync(FULL, base, 0);
-  if (pass) queue[base + __popc(bal & ((1u << lane) - 1))] = item;
+  const int rank = __popc(bal & ((1u << lane) - 1));
+  if (base + cnt <= kWalkQueue) {
+    if (pass) queue[base + rank] = item;
+    if (lane == 0) atomicMax(&nfill[1], base + cnt);
+  } else {  // the block's queue is full (dense candidates): this push goes straight to the list
+    unsigned g = 0;
+    if (lane == 0) g = atomicAdd(&b.ctr->n_cand, (unsigned)cnt);
+    g = __shfl_sync(FULL, g, 0);
+    if ((long long)g + cnt <= b.cand_cap) {
+      if (pass) b.cand[(long long)g + rank] = item;
+    } else if (lane == 0) {
+      atomicOr(&b.ctr->overflow, 8u);
+    }
+  }
 }
 __global__ void __launch_bounds__(256, FM_GATHER_CTAS) fm_gather_kernel(IndexDev ix, BatchDev b) {
   __shared__ int2 s_queue[kWalkQueue];
   __shared__ SliceWin s_win[8];
-  __shared__ int s_n, s_base;
+  __shared__ int s_n[2], s_base;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   SliceWin& win = s_win[wib];
   // A worklist of the search overflowed: the host regrows and reruns. One decision per CTA (the CTA's warps
   // work together below). An overflow of the candidate list itself (bit 3, set by other CTAs of this kernel)
   // does not stop the walk: the count goes on, so that the host learns the size to regrow to.
-  if (threadIdx.x == 0) s_n = (int)(b.ctr->overflow & 5u);
+  if (threadIdx.x == 0) s_n[0] = (int)(b.ctr->overflow & 5u);
   __syncthreads();
-  const bool stop = s_n != 0;
+  const bool stop = s_n[0] != 0;
   __syncthreads();
   if (stop) return;
   const unsigned long long packed = b.ctr->slice_elem;
@@ -622,7 +641,7 @@ __global__ void __launch_bounds__(256, FM_GATHER_CTAS) fm_gather_kernel(IndexDev
   const int n_spans = (int)((total + kSpan - 1) / kSpan);
   const int span_blocks = (n_spans + 7) >> 3, small_blocks = (n_small + 255) >> 8;
   for (int blk = blockIdx.x; blk < span_blocks + small_blocks; blk += gridDim.x) {
-    if (threadIdx.x == 0) s_n = 0;
+    if (threadIdx.x == 0) s_n[0] = s_n[1] = 0;
     __syncthreads();
     if (blk < span_blocks) {
       const int sp = blk * 8 + wib;
@@ -645,13 +664,10 @@ __global__ void __launch_bounds__(256, FM_GATHER_CTAS) fm_gather_kernel(IndexDev
               st = (int)max(-(1ll << 31), min(1ll << 30, __ldg(b.sl_start + k + lane) - span_base));
               win.st[lane] = st;
             }
-            // lane l: the part of slice k + l inside the rest of the span, as 128-byte lines of walk records
-            const int e0 = max(st, pos), e1 = min((int)min((long long)st + r0.w, (long long)span_len), span_len);
-            if (e0 < e1) {
-              const uint2* p0 = ix.sa_rec + (r0.y + (e0 - st));
-              const uint2* p1 = ix.sa_rec + (r0.y + (e1 - st) - 1);
-              for (uintptr_t a = (uintptr_t)p0 & ~(uintptr_t)127; a <= (uintptr_t)p1; a += 128) prefetch_l2((const void*)a);
-            }
+            // lane l: the first line of walk records of slice k + l inside the rest of the span (the walk itself
+            // prefetches two groups ahead inside a slice)
+            const int e0 = max(st, pos);
+            if (e0 < span_len && e0 < st + r0.w) prefetch_l2(ix.sa_rec + (r0.y + (e0 - st)));
             __syncwarp();
           }
           const int4 sr = win.rec[k - kwin];  // (q, sa_begin, lm | p << 10 | mult << 20, size), same for all lanes
@@ -669,6 +685,7 @@ __global__ void __launch_bounds__(256, FM_GATHER_CTAS) fm_gather_kernel(IndexDev
             const int base = g + 4 * lane;
             unsigned r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             if (base < a1) ldg_nc_v8(ix.sa_rec + base, r);
+            if (base + 256 < a1) prefetch_l2(ix.sa_rec + base + 256);
             int d0 = stage1_margin(r[0], r[1], m, row), d1 = stage1_margin(r[2], r[3], m, row);
             int d2 = stage1_margin(r[4], r[5], m, row), d3 = stage1_margin(r[6], r[7], m, row);
             if (mult) {  // (uniform)
@@ -679,10 +696,10 @@ __global__ void __launch_bounds__(256, FM_GATHER_CTAS) fm_gather_kernel(IndexDev
             const bool p0 = (d0 >= 0) & (rel < len), p1 = (d1 >= 0) & (rel + 1u < len);
             const bool p2 = (d2 >= 0) & (rel + 2u < len), p3 = (d3 >= 0) & (rel + 3u < len);
             if (__any_sync(FULL, p0 | p1 | p2 | p3)) {
-              block_push(s_queue, &s_n, p0, make_int2(qlm, base), lane);
-              block_push(s_queue, &s_n, p1, make_int2(qlm, base + 1), lane);
-              block_push(s_queue, &s_n, p2, make_int2(qlm, base + 2), lane);
-              block_push(s_queue, &s_n, p3, make_int2(qlm, base + 3), lane);
+              block_push(b, s_queue, s_n, p0, make_int2(qlm, base), lane);
+              block_push(b, s_queue, s_n, p1, make_int2(qlm, base + 1), lane);
+              block_push(b, s_queue, s_n, p2, make_int2(qlm, base + 2), lane);
+              block_push(b, s_queue, s_n, p3, make_int2(qlm, base + 3), lane);
             }
           }
         }
@@ -702,11 +719,11 @@ __global__ void __launch_bounds__(256, FM_GATHER_CTAS) fm_gather_kernel(IndexDev
 #pragma unroll
       for (int e = 0; e < kSmallSlice; e++) {
         const bool pass = (e < sr.w) & (stage1_margin(rec[e].x, rec[e].y, sm, srow) + stage1_extra(rec[e].x, rec[e].y, sm, smult) >= 0);
-        block_push(s_queue, &s_n, pass, make_int2(sqlm, sr.y + e), lane);
+        block_push(b, s_queue, s_n, pass, make_int2(sqlm, sr.y + e), lane);
       }
     }
     __syncthreads();
-    const int n = s_n;
+    const int n = s_n[1];
     if (n) {  // (uniform)
       if (threadIdx.x == 0) s_base = (int)atomicAdd(&b.ctr->n_cand, (unsigned)n);
       __syncthreads();
@@ -915,7 +932,7 @@ __device__ __forceinline__ int verify_candidates(const IndexDev& ix, const Batch
   return n_verified;
 }
 
-__global__ void __launch_bounds__(256) fm_verify_kernel(IndexDev ix, BatchDev b, Params pr) {
+__global__ void __launch_bounds__(256, 4) fm_verify_kernel(IndexDev ix, BatchDev b, Params pr) {
   __shared__ SurvStage s_stage;
   __shared__ Cand s_cand[8][32];
   __shared__ unsigned s_seen[8][32];
