@@ -8,6 +8,6 @@
 
 There is no CPU fallback: every entry point raises if libfm_b200.so is missing or CUDA fails.
 """
-from .capi import (FuzzyMatchError, Index, MATCH_DTYPE, RECORD_DTYPE, Params, build_library, library_path,  # noqa: F401
+from .capi import (FuzzyMatchError, Index, MATCH_DTYPE, WIRE_DTYPE, Params, build_library, library_path,  # noqa: F401
                    load_library)
 from .fuzzy_match import ContrastReduce, EditCosts, FuzzyMatch, Match  # noqa: F401

@@ -64,14 +64,14 @@ class Profile(C.Structure):
 
 MATCH_DTYPE = np.dtype([("s_id", np.uint32), ("score", np.float32), ("penalty", np.float32),
                         ("max_subseq", np.int32), ("length", np.int32), ("cost", np.float32)])
-RECORD_DTYPE = np.dtype([("s_id", np.uint32), ("longest_match", np.int32), ("length", np.int32),
-                         ("cost", np.float32), ("rowmin_max", np.float32), ("reserved", np.int32, (3,))])
+WIRE_DTYPE = np.dtype([("s_id", np.uint32), ("lm_len", np.uint32), ("cost", np.float32), ("rowmin_max", np.float32)])
 
 EXPORTS = ["fm_index_create", "fm_index_destroy", "fm_index_save", "fm_index_load", "fm_index_num_sentences", "fm_index_num_suffixes",
            "fm_index_max_tokens_in_pattern", "fm_index_device_bytes", "fm_index_kept_sources", "fm_index_sfreq",
            "fm_index_sentence", "fm_index_set_idf_stats", "fm_index_set_real", "fm_match_batch", "fm_match_batch_real", "fm_match_batch_device",
-           "fm_match_batch_submit", "fm_match_batch_device_submit", "fm_ticket_wait", "fm_shard_score_device",
-           "fm_merge_replay_device", "fm_set_profiling", "fm_get_profile", "fm_last_error", "fm_version"]
+           "fm_match_batch_submit", "fm_match_batch_device_submit", "fm_ticket_wait", "fm_wire_block_bytes", "fm_shard_accept_device",
+           "fm_merge_accepted_device", "fm_comm_unique_id", "fm_comm_create", "fm_comm_destroy", "fm_match_batch_sharded_device",
+           "fm_comm_last_gather_bytes", "fm_comm_block_capacity", "fm_set_profiling", "fm_get_profile", "fm_last_error", "fm_version"]
 
 
 def load_library():
@@ -113,10 +113,22 @@ def load_library():
     lib.fm_match_batch_device_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(Params),
                                                  C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
     lib.fm_ticket_wait.argtypes = [C.c_void_p]
-    lib.fm_shard_score_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(Params),
-                                          C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_void_p]
-    lib.fm_merge_replay_device.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p,
-                                           C.c_int64, C.POINTER(Params), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.fm_wire_block_bytes.restype = C.c_int64
+    lib.fm_wire_block_bytes.argtypes = [C.c_int64, C.c_int64]
+    lib.fm_shard_accept_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(Params), C.c_int64,
+                                           C.c_void_p, C.c_void_p]
+    lib.fm_merge_accepted_device.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int64, C.c_void_p, C.c_int64, C.POINTER(Params),
+                                             C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]
+    lib.fm_comm_unique_id.argtypes = [C.c_void_p]
+    lib.fm_comm_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    lib.fm_comm_destroy.argtypes = [C.c_void_p]
+    lib.fm_comm_destroy.restype = None
+    lib.fm_match_batch_sharded_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(Params),
+                                                  C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.fm_comm_last_gather_bytes.restype = C.c_int64
+    lib.fm_comm_last_gather_bytes.argtypes = [C.c_void_p]
+    lib.fm_comm_block_capacity.restype = C.c_int64
+    lib.fm_comm_block_capacity.argtypes = [C.c_void_p]
     lib.fm_set_profiling.argtypes = [C.c_void_p, C.c_int]
     lib.fm_get_profile.argtypes = [C.c_void_p, C.POINTER(Profile)]
     _LIB = lib
@@ -282,21 +294,25 @@ class Index:
     def wait(self, ticket):
         _check(self.lib, self.lib.fm_ticket_wait(ticket))
 
-    def shard_score_device(self, d_q_tokens, d_q_off, n_q, n_tok, stream=0, params=None, **kw):
-        """Returns (d_rec_off ptr, d_rec ptr, n_rec) for the cross-shard replay."""
+    def shard_accept_device(self, d_q_tokens, d_q_off, n_q, n_tok, capacity, d_block, stream=0, params=None, **kw):
+        """fm_shard_accept_device: this shard's accepted records into d_block (fm_wire_block_bytes(n_q, capacity) device bytes)."""
         p = params if params is not None else Params.make(**kw)
-        off, rec, n = C.c_void_p(), C.c_void_p(), C.c_int64()
-        _check(self.lib, self.lib.fm_shard_score_device(self.h, d_q_tokens, d_q_off, n_q, n_tok, C.byref(p), C.byref(off),
-                                                        C.byref(rec), C.byref(n), stream))
-        return off.value, rec.value, n.value
+        _check(self.lib, self.lib.fm_shard_accept_device(self.h, d_q_tokens, d_q_off, n_q, n_tok, C.byref(p), capacity, d_block, stream))
 
-    def merge_replay_device(self, d_rec_offs, d_recs, d_q_off, n_q, d_out, d_out_count, cap, stream=0, params=None, **kw):
+    def merge_accepted_device(self, d_blocks, total_capacity, d_q_off, n_q, d_out, d_out_count, cap, stream=0, params=None, **kw):
+        """fm_merge_accepted_device over the blocks of all shards; returns the block capacity a rerun needs (0: complete)."""
         p = params if params is not None else Params.make(**kw)
-        k = len(d_rec_offs)
-        offs = (C.c_void_p * k)(*d_rec_offs)
-        recs = (C.c_void_p * k)(*d_recs)
-        _check(self.lib, self.lib.fm_merge_replay_device(self.h, k, offs, recs, d_q_off, n_q, C.byref(p), cap, d_out,
-                                                         d_out_count, stream))
+        k = len(d_blocks)
+        blocks = (C.c_void_p * k)(*d_blocks)
+        need = C.c_int64(0)
+        _check(self.lib, self.lib.fm_merge_accepted_device(self.h, k, blocks, total_capacity, d_q_off, n_q, C.byref(p), cap, d_out,
+                                                           d_out_count, C.byref(need), stream))
+        return need.value
+
+    def match_batch_sharded_device(self, comm, d_q_tokens, d_q_off, n_q, n_tok, d_out, d_out_count, cap, stream=0, params=None, **kw):
+        p = params if params is not None else Params.make(**kw)
+        _check(self.lib, self.lib.fm_match_batch_sharded_device(self.h, comm, d_q_tokens, d_q_off, n_q, n_tok, C.byref(p), cap, d_out,
+                                                                d_out_count, stream))
 
     def set_profiling(self, enabled=True):
         _check(self.lib, self.lib.fm_set_profiling(self.h, int(enabled)))
@@ -305,3 +321,44 @@ class Index:
         p = Profile()
         _check(self.lib, self.lib.fm_get_profile(self.h, C.byref(p)))
         return p.as_dict()
+
+
+def wire_block_bytes(n_q, capacity):
+    return int(load_library().fm_wire_block_bytes(n_q, capacity))
+
+
+def comm_unique_id():
+    """fm_comm_unique_id: 128 bytes that rank 0 hands to every rank."""
+    lib = load_library()
+    buf = (C.c_char * 128)()
+    _check(lib, lib.fm_comm_unique_id(buf))
+    return bytes(buf)
+
+
+class Comm:
+    """fm_comm: the NCCL communicator of a sharded TM (one rank per GPU)."""
+
+    def __init__(self, unique_id, rank, world, device):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        assert len(unique_id) == 128
+        _check(self.lib, self.lib.fm_comm_create(unique_id, rank, world, device, C.byref(self.h)))
+
+    @property
+    def last_gather_bytes(self):
+        return int(self.lib.fm_comm_last_gather_bytes(self.h))
+
+    @property
+    def block_capacity(self):
+        return int(self.lib.fm_comm_block_capacity(self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.fm_comm_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

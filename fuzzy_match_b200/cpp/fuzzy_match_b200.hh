@@ -127,7 +127,7 @@ public:
     std::vector<std::vector<Match>> out(1);
     match_batch({pattern}, fuzzy, number_of_matches, out, min_subseq_length, min_subseq_ratio, vocab_idf_penalty, edit_costs,
                 contrastive_factor, reduce, contrast_buffer, no_perfect);
-    matches.insert(matches.end(), out[0].begin(), out[0].end());
+    append_results(matches, out[0], number_of_matches, contrastive_factor);
     return matches.size() > 0;
   }
 
@@ -141,7 +141,7 @@ public:
     const std::vector<Sentence> reals(1, real);
     run_batch({pattern}, &reals, fuzzy, number_of_matches, out, min_subseq_length, min_subseq_ratio, vocab_idf_penalty, edit_costs,
               contrastive_factor, reduce, contrast_buffer, no_perfect);
-    matches.insert(matches.end(), out[0].begin(), out[0].end());
+    append_results(matches, out[0], number_of_matches, contrastive_factor);
     return matches.size() > 0;
   }
 
@@ -155,6 +155,20 @@ public:
   }
 
 private:
+  // The reference APPENDS to `matches` and stops at number_of_matches entries in total, so entries that are
+  // already there shorten what a call adds (src/fuzzy_match.cc:670-679). Its contrastive rerank also penalises
+  // the candidates against entries that were there before the call (:634-652); that needs the earlier matches
+  // on the device and is not offered: refused instead of answered differently.
+  static void append_results(std::vector<Match>& matches, const std::vector<Match>& found, unsigned number_of_matches,
+                             float contrastive_factor) {
+    if (contrastive_factor > 0 && !matches.empty())
+      throw std::logic_error("contrastive match() into a non-empty result vector is not supported: clear it first");
+    for (const Match& m : found) {
+      if (number_of_matches != 0 && matches.size() >= number_of_matches) break;
+      matches.push_back(m);
+    }
+  }
+
   // reals == nullptr: the real sentence of every pattern is the pattern itself (Tokens overload)
   void run_batch(const std::vector<Tokens>& patterns, const std::vector<Sentence>* reals, float fuzzy, unsigned number_of_matches,
                  std::vector<std::vector<Match>>& out, int min_subseq_length, float min_subseq_ratio, float vocab_idf_penalty,

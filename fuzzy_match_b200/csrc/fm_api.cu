@@ -50,6 +50,8 @@ static int ensure_base(Workspace* w) {
     FM_CUDA(cudaMalloc((void**)&w->scan_chain, 256 * sizeof(unsigned long long)));
     FM_CUDA(cudaMemset(w->scan_chain, 0, 256 * sizeof(unsigned long long)));
     FM_CUDA(cudaMallocHost((void**)&w->h_ctr, sizeof(Counters)));
+    FM_CUDA(cudaMalloc((void**)&w->mctr, sizeof(Counters)));
+    FM_CUDA(cudaMallocHost((void**)&w->h_mctr, sizeof(Counters)));
   }
   return FM_OK;
 }
@@ -137,9 +139,17 @@ static int ensure_survivors(Workspace* w, int64_t n) {
       (rc = dev_realloc(&w->heapbuf, n + w->cap_q + 1)) || (rc = dev_realloc(&w->sort_key, n)) || (rc = dev_realloc(&w->sort_key2, n)) || (rc = dev_realloc(&w->sort_idx, n)) || (rc = dev_realloc(&w->hkey, (size_t)hs)) ||
       (rc = dev_realloc(&w->hlm, (size_t)hs)))
     return rc;
+  if (w->want_stage && (rc = dev_realloc(&w->wire_stage, n))) return rc;
   w->hsize = hs;
   w->cap_surv = n;
   return FM_OK;
+}
+// sharded TM: the staging buffer for accepted records follows the survivor capacity
+static int ensure_stage(Workspace* w) {
+  if (w->want_stage && w->wire_stage) return FM_OK;
+  w->want_stage = true;
+  if (w->cap_surv == 0) return FM_OK;  // allocated with the survivor arrays
+  return dev_realloc(&w->wire_stage, (size_t)w->cap_surv);
 }
 static int ensure_out(Workspace* w, int64_t n_q, int64_t cap) {
   if (n_q * cap <= w->cap_out) return FM_OK;
@@ -153,9 +163,10 @@ static int ensure_out(Workspace* w, int64_t n_q, int64_t cap) {
 static void free_workspace(Workspace* w) {
   cudaFree(w->d_q_tok); cudaFree(w->d_q_off); cudaFree(w->d_q_real); cudaFree(w->d_q_gap); cudaFree(w->d_itok_dist); cudaFree(w->pat); cudaFree(w->chain_q); cudaFree(w->qmeta); cudaFree(w->tbl); cudaFree(w->cmin_tab); cudaFree(w->span_slice); cudaFree(w->qmask); cudaFree(w->wq); cudaFree(w->peq64); cudaFree(w->cmin64); cudaFree(w->wextra); cudaFree(w->sm_rec);
   cudaFree(w->sl_start); cudaFree(w->sl_rec); cudaFree(w->hkey); cudaFree(w->hlm); cudaFree(w->surv); cudaFree(w->cand); cudaFree(w->surv_len);
-  cudaFree(w->q_cnt); cudaFree(w->q_base); cudaFree(w->acc_cnt); cudaFree(w->rec); cudaFree(w->heapbuf); cudaFree(w->ctr); cudaFree(w->scan_chain);
+  cudaFree(w->q_cnt); cudaFree(w->q_base); cudaFree(w->acc_cnt); cudaFree(w->rec); cudaFree(w->heapbuf); cudaFree(w->ctr); cudaFree(w->mctr); cudaFree(w->wire_stage); cudaFree(w->scan_chain);
   cudaFree(w->d_out); cudaFree(w->d_out_count); cudaFree(w->mrec); cudaFree(w->m_cnt); cudaFree(w->m_base); cudaFree(w->m_acc); cudaFree(w->m_heap); cudaFree(w->heavy_q); cudaFree(w->m_heavy); cudaFree(w->mid_q); cudaFree(w->m_mid); cudaFree(w->sort_key); cudaFree(w->sort_key2); cudaFree(w->m_key2); cudaFree(w->sort_idx); cudaFree(w->m_key); cudaFree(w->m_idx);
   if (w->h_ctr) cudaFreeHost(w->h_ctr);
+  if (w->h_mctr) cudaFreeHost(w->h_mctr);
   if (w->h_q_off32) cudaFreeHost(w->h_q_off32);
   if (w->stream) {
     cudaStreamDestroy(w->stream);
@@ -301,16 +312,17 @@ static int wait_and_check(Workspace* w, int attempt, int* retries) {
 static int run_replay(Index* ix, Workspace* w, fm_record* rec, const int32_t* q_cnt, const int32_t* q_base, float* heapbuf,
                       unsigned long long* sort_key, unsigned long long* sort_key2, int32_t* sort_idx, int32_t* acc_cnt,
                       int32_t* mid_q, int32_t* heavy_q, const int32_t* d_q_off, int64_t n_q, const Params& pr, int64_t cap, fm_match* d_out, int32_t* d_out_count,
-                      cudaStream_t st, int* launches) {
+                      cudaStream_t st, int* launches, Counters* ctr = nullptr, int32_t* wire_cnt = nullptr, fm_wire* wire_stage = nullptr) {
+  if (!ctr) ctr = w->ctr;
   launch_replay(ix->dev, rec, q_cnt, q_base, heapbuf, sort_key, sort_key2, sort_idx, acc_cnt, mid_q, heavy_q, d_q_off, (int32_t)n_q, pr, cap, d_out,
-                d_out_count, w->ctr, ix->sm_count, st, w->stream2, w->ev_fork, w->ev_join);
+                d_out_count, ctr, ix->sm_count, st, w->stream2, w->ev_fork, w->ev_join, wire_cnt, wire_stage);
   (*launches) += 3;
   {
     int rc;
     if ((rc = stage_check(st, "replay kernels"))) return rc;
   }
-  if (pr.contrast > 0.f) {
-    launch_contrast(ix->dev, rec, q_base, sort_idx, acc_cnt, (int32_t)n_q, pr, cap, d_out, d_out_count, w->ctr, ix->sm_count, st);
+  if (pr.contrast > 0.f && !wire_cnt) {
+    launch_contrast(ix->dev, rec, q_base, sort_idx, acc_cnt, (int32_t)n_q, pr, cap, d_out, d_out_count, ctr, ix->sm_count, st);
     (*launches)++;
   }
   if (ix->profiling) cudaEventRecord(w->ev[6], st);
@@ -728,55 +740,30 @@ int fm_match_batch_device(fm_index* index, const int32_t* d_q_tokens, const int3
   return rc ? rc : fm_ticket_wait(t);
 }
 
-int fm_shard_score_device(fm_index* index, const int32_t* d_q_tokens, const int32_t* d_q_off, int64_t n_q,
-                          int64_t n_query_tokens, const fm_params* params, const int32_t** d_rec_off, const fm_record** d_rec,
-                          int64_t* n_rec, void* stream) {
-  Index* ix = reinterpret_cast<Index*>(index);
-  Params pr;
+// ---------------------------------------------------------------- sharded TM
+
+int64_t fm_wire_block_bytes(int64_t n_q, int64_t capacity) { return n_q < 0 || capacity < 0 ? -1 : wire_block_bytes(n_q, capacity); }
+
+// Enqueue the shard half of a batch on st: the whole pipeline with the replay in shard mode (accepted records
+// staged per query), their offsets scanned straight into the block, then packed behind them with the header.
+static int enqueue_accept(Index* ix, Workspace* w, const int32_t* d_q_tok, const int32_t* d_q_off, int64_t n_q, int64_t n_tok,
+                          const Params& pr, int64_t capacity, void* d_block, cudaStream_t st, int* launches) {
   int rc;
-  if (!ix || n_q < 1 || !d_rec_off || !d_rec || !n_rec) { set_error("bad argument"); return FM_ERR_INVALID; }
-  if ((rc = check_params(params, &pr))) return rc;
-  FM_CUDA(cudaSetDevice(ix->device));
-  // the shard workspace stays reserved for this index: pool[0] is dedicated to the sharded path
-  Workspace* w = acquire(ix);
-  struct Releaser { Index* ix; Workspace* w; ~Releaser() { release(ix, w); } } rel{ix, w};
-  if ((rc = ensure_base(w)) || (rc = ensure_queries(w, n_q, n_query_tokens, false))) return rc;
-  int launches = 0, retries = 0;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  w->real_active = false;
-  if ((rc = initial_worklists(ix, w, n_q, n_query_tokens))) return rc;
-  for (int attempt = 0;; attempt++) {
-    if ((rc = launch_shard(ix, w, d_q_tokens, d_q_off, n_q, n_query_tokens, pr, st, &launches))) return rc;
-    if (ix->profiling) cudaEventRecord(w->ev[6], st);
-    if ((rc = enqueue_done(w, st))) return rc;
-    const int again = wait_and_check(w, attempt, &retries);
-    if (again < 0) return -again;
-    if (!again) break;
-  }
-  finish_profile(ix, w, n_q, n_query_tokens, launches, retries);
-  *d_rec_off = w->q_base;
-  *d_rec = w->rec;
-  *n_rec = (int64_t)w->h_ctr->n_surv;
-  return FM_OK;
+  int32_t* blk = static_cast<int32_t*>(d_block);
+  FM_CUDA(cudaMemsetAsync(w->acc_cnt, 0, n_q * sizeof(int32_t), st));  // queries the replay skips count 0
+  if ((rc = launch_shard(ix, w, d_q_tok, d_q_off, n_q, n_tok, pr, st, launches))) return rc;
+  if ((rc = run_replay(ix, w, w->rec, w->q_cnt, w->q_base, w->heapbuf, w->sort_key, w->sort_key2, w->sort_idx, nullptr, w->mid_q,
+                       w->heavy_q, d_q_off, n_q, pr, 1, nullptr, nullptr, st, launches, nullptr, w->acc_cnt, w->wire_stage)))
+    return rc;
+  launch_scan(w->acc_cnt, blk + 4, (int32_t)n_q, w->scan_chain, ++w->scan_epoch, ix->sm_count, st);
+  launch_wire_pack(blk, w->ctr, w->wire_stage, w->q_base, (int32_t)n_q, (int)capacity, st);
+  *launches += 2;
+  return stage_check(st, "wire pack");
 }
 
-int fm_merge_replay_device(fm_index* index, int n_shards, const int32_t* const* d_rec_off, const fm_record* const* d_rec,
-                           const int32_t* d_q_off, int64_t n_q, const fm_params* params, int64_t cap, fm_match* d_out,
-                           int32_t* d_out_count, void* stream) {
-  Index* ix = reinterpret_cast<Index*>(index);
-  Params pr;
+// Enqueue the cross-shard half: counts -> scan -> unpack -> the ordinary replay of the union.
+static int ensure_merge(Workspace* w, int64_t n_q, int64_t total) {
   int rc;
-  if (!ix || n_shards < 1 || n_shards > 16 || n_q < 1 || !d_rec_off || !d_rec) { set_error("bad argument"); return FM_ERR_INVALID; }
-  if ((rc = check_params(params, &pr))) return rc;
-  if (pr.contrast > 0.f && n_shards > 1) {
-    set_error("contrastive rerank needs the sentences of every shard; not supported on a sharded TM");
-    return FM_ERR_INVALID;
-  }
-  FM_CUDA(cudaSetDevice(ix->device));
-  Workspace* w = acquire(ix);
-  struct Releaser { Index* ix; Workspace* w; ~Releaser() { release(ix, w); } } rel{ix, w};
-  if ((rc = ensure_base(w))) return rc;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (n_q > w->cap_mq) {
     if ((rc = dev_realloc(&w->m_cnt, n_q + 1)) || (rc = dev_realloc(&w->m_base, n_q + 1)) || (rc = dev_realloc(&w->m_acc, n_q + 1)) ||
         (rc = dev_realloc(&w->m_heavy, n_q + 1)) || (rc = dev_realloc(&w->m_mid, n_q + 1)))
@@ -784,26 +771,239 @@ int fm_merge_replay_device(fm_index* index, int n_shards, const int32_t* const* 
     w->cap_mq = n_q;
     w->cap_mrec = 0;  // m_heap depends on cap_mq
   }
-  int launches = 0;
-  launch_merge_count(n_shards, d_rec_off, w->m_cnt, (int32_t)n_q, st);
-  launch_scan(w->m_cnt, w->m_base, (int32_t)n_q, w->scan_chain, ++w->scan_epoch, ix->sm_count, st);
-  int32_t total = 0;
-  FM_CUDA(cudaMemcpyAsync(&total, w->m_base + n_q, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  FM_CUDA(cudaStreamSynchronize(st));
   if (total + n_q + 1 > w->cap_mrec) {
     const int64_t c = total + total / 4 + n_q + 1024;
-    if ((rc = dev_realloc(&w->mrec, c)) || (rc = dev_realloc(&w->m_heap, c + w->cap_mq + 1)) || (rc = dev_realloc(&w->m_key, c)) || (rc = dev_realloc(&w->m_key2, c)) ||
-        (rc = dev_realloc(&w->m_idx, c)))
+    if ((rc = dev_realloc(&w->mrec, c)) || (rc = dev_realloc(&w->m_heap, c + w->cap_mq + 1)) || (rc = dev_realloc(&w->m_key, c)) ||
+        (rc = dev_realloc(&w->m_key2, c)) || (rc = dev_realloc(&w->m_idx, c)))
       return rc;
     w->cap_mrec = c;
   }
-  launch_merge_copy(n_shards, d_rec_off, d_rec, w->m_base, w->mrec, (int32_t)n_q, st);
-  launches += 3;
-  FM_CUDA(cudaMemsetAsync(w->ctr, 0, sizeof(Counters), st));
-  if ((rc = run_replay(ix, w, w->mrec, w->m_cnt, w->m_base, w->m_heap, w->m_key, w->m_key2, w->m_idx, w->m_acc, w->m_mid, w->m_heavy, d_q_off, n_q, pr, cap, d_out, d_out_count, st, &launches)))
+  return FM_OK;
+}
+// total_capacity = sum of the blocks' capacities (an upper bound on the records of the union)
+static int enqueue_merge(Index* ix, Workspace* w, int n_shards, const int32_t* const* blocks, int64_t total_capacity, const int32_t* d_q_off,
+                         int64_t n_q, const Params& pr, int64_t cap, fm_match* d_out, int32_t* d_out_count, cudaStream_t st, int* launches) {
+  int rc;
+  if ((rc = ensure_merge(w, n_q, total_capacity))) return rc;
+  FM_CUDA(cudaMemsetAsync(w->mctr, 0, sizeof(Counters), st));
+  launch_wire_count(n_shards, blocks, w->m_cnt, (int32_t)n_q, w->mctr, st);
+  launch_scan(w->m_cnt, w->m_base, (int32_t)n_q, w->scan_chain, ++w->scan_epoch, ix->sm_count, st);
+  launch_wire_copy(n_shards, blocks, w->m_base, w->mrec, (int32_t)n_q, w->mctr, st);
+  *launches += 3;
+  if ((rc = stage_check(st, "wire merge"))) return rc;
+  if ((rc = run_replay(ix, w, w->mrec, w->m_cnt, w->m_base, w->m_heap, w->m_key, w->m_key2, w->m_idx, w->m_acc, w->m_mid, w->m_heavy, d_q_off,
+                       n_q, pr, cap, d_out, d_out_count, st, launches, w->mctr)))
     return rc;
+  FM_CUDA(cudaMemcpyAsync(w->h_mctr, w->mctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  return FM_OK;
+}
+
+int fm_shard_accept_device(fm_index* index, const int32_t* d_q_tokens, const int32_t* d_q_off, int64_t n_q, int64_t n_query_tokens,
+                           const fm_params* params, int64_t capacity, void* d_block, void* stream) {
+  Index* ix = reinterpret_cast<Index*>(index);
+  Params pr;
+  int rc;
+  if (!ix || n_q < 1 || n_q > (1 << 20) || capacity < 0 || capacity > (int64_t(1) << 30) || !d_block) { set_error("bad argument"); return FM_ERR_INVALID; }
+  if ((rc = check_params(params, &pr))) return rc;
+  FM_CUDA(cudaSetDevice(ix->device));
+  Workspace* w = acquire(ix);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  struct Releaser { Index* ix; Workspace* w; cudaStream_t st; ~Releaser() { cudaStreamSynchronize(st); release(ix, w); } } rel{ix, w, st};
+  if ((rc = ensure_base(w)) || (rc = ensure_queries(w, n_q, n_query_tokens, false))) return rc;
+  int launches = 0, retries = 0;
+  w->real_active = false;
+  if ((rc = ensure_stage(w)) || (rc = initial_worklists(ix, w, n_q, n_query_tokens))) return rc;
+  for (int attempt = 0;; attempt++) {
+    if ((rc = enqueue_accept(ix, w, d_q_tokens, d_q_off, n_q, n_query_tokens, pr, capacity, d_block, st, &launches))) return rc;
+    if (ix->profiling) cudaEventRecord(w->ev[6], st);
+    if ((rc = enqueue_done(w, st))) return rc;
+    const int again = wait_and_check(w, attempt, &retries);
+    if (again < 0) return -again;
+    if (!again) break;
+  }
+  finish_profile(ix, w, n_q, n_query_tokens, launches, retries);
+  return FM_OK;
+}
+
+int fm_merge_accepted_device(fm_index* index, int n_shards, const void* const* d_blocks, int64_t total_capacity, const int32_t* d_q_off,
+                             int64_t n_q, const fm_params* params, int64_t cap, fm_match* d_out, int32_t* d_out_count,
+                             int64_t* need_capacity, void* stream) {
+  Index* ix = reinterpret_cast<Index*>(index);
+  Params pr;
+  int rc;
+  if (need_capacity) *need_capacity = 0;
+  if (!ix || n_shards < 1 || n_shards > 16 || n_q < 1 || total_capacity < 0 || !d_blocks || cap < 1) { set_error("bad argument"); return FM_ERR_INVALID; }
+  if ((rc = check_params(params, &pr))) return rc;
+  if (pr.contrast > 0.f) {
+    set_error("contrastive rerank needs the sentences behind the records; not supported on accepted-record blocks");
+    return FM_ERR_INVALID;
+  }
+  FM_CUDA(cudaSetDevice(ix->device));
+  Workspace* w = acquire(ix);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  struct Releaser { Index* ix; Workspace* w; cudaStream_t st; ~Releaser() { cudaStreamSynchronize(st); release(ix, w); } } rel{ix, w, st};
+  if ((rc = ensure_base(w))) return rc;
+  int launches = 0;
+  const int32_t* blocks[16];
+  for (int k = 0; k < n_shards; k++) blocks[k] = static_cast<const int32_t*>(d_blocks[k]);
+  if ((rc = enqueue_merge(ix, w, n_shards, blocks, total_capacity, d_q_off, n_q, pr, cap, d_out, d_out_count, st, &launches))) return rc;
   FM_CUDA(cudaStreamSynchronize(st));
   FM_CUDA(cudaGetLastError());
+  if (w->h_mctr->overflow & 0x200u) { set_error("the blocks were made for another batch size"); return FM_ERR_INVALID; }
+  if (w->h_mctr->overflow & 0x100u) { set_error("a shard block is marked incomplete (workspace overflow in fm_shard_accept_device)"); return FM_ERR_INVALID; }
+  if ((w->h_mctr->overflow & 0x400u) && need_capacity) *need_capacity = (int64_t)w->h_mctr->wire_need;
+  if ((w->h_mctr->overflow & 0x400u) && !need_capacity) { set_error("a shard accepted more records than its block holds"); return FM_ERR_NOMEM; }
+  return FM_OK;
+}
+
+// ---- NCCL, opened at run time (the library has no link-time dependency on it)
+}  // extern "C"
+#include <dlfcn.h>
+namespace fm {
+struct NcclId { char internal[128]; };
+struct Nccl {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(void** comm, int nranks, NcclId id, int rank) = nullptr;
+  int (*CommDestroy)(void* comm) = nullptr;
+  int (*AllGather)(const void* send, void* recv, size_t count, int dtype, void* comm, cudaStream_t st) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+static Nccl& nccl() {
+  static Nccl n;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* names[] = {getenv("FM_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      if (!nm) continue;
+      n.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (n.lib) break;
+    }
+    if (!n.lib) return;
+    n.GetUniqueId = reinterpret_cast<int (*)(NcclId*)>(dlsym(n.lib, "ncclGetUniqueId"));
+    n.CommInitRank = reinterpret_cast<int (*)(void**, int, NcclId, int)>(dlsym(n.lib, "ncclCommInitRank"));
+    n.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(n.lib, "ncclCommDestroy"));
+    n.AllGather = reinterpret_cast<int (*)(const void*, void*, size_t, int, void*, cudaStream_t)>(dlsym(n.lib, "ncclAllGather"));
+    n.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(n.lib, "ncclGetErrorString"));
+    n.ok = n.GetUniqueId && n.CommInitRank && n.CommDestroy && n.AllGather;
+  });
+  return n;
+}
+static int nccl_fail(int r, const char* what) {
+  set_error(std::string("NCCL error in ") + what + ": " + (nccl().GetErrorString ? nccl().GetErrorString(r) : "?"));
+  return FM_ERR_CUDA;
+}
+}  // namespace fm
+
+struct fm_comm {
+  void* comm = nullptr;
+  int rank = 0, world = 1, device = 0;
+  double rate = 0.5;  // accepted records per query of the fullest shard (recent batches): sizes the blocks
+  int64_t last_capacity = 0;
+  char* d_send = nullptr;
+  char* d_recv = nullptr;
+  int64_t cap_block = 0;
+  int64_t last_gather_bytes = 0;
+};
+
+extern "C" {
+
+int fm_comm_unique_id(void* id_out) {
+  if (!id_out) { set_error("NULL argument"); return FM_ERR_INVALID; }
+  if (!nccl().ok) { set_error("libnccl.so.2 not found (set FM_NCCL_LIB)"); return FM_ERR_INVALID; }
+  NcclId id;
+  const int r = nccl().GetUniqueId(&id);
+  if (r) return nccl_fail(r, "ncclGetUniqueId");
+  memcpy(id_out, &id, sizeof(id));
+  return FM_OK;
+}
+int fm_comm_create(const void* id, int rank, int world, int device, fm_comm** out) {
+  if (out) *out = nullptr;
+  if (!id || !out || world < 1 || world > 16 || rank < 0 || rank >= world) { set_error("bad argument (1..16 ranks)"); return FM_ERR_INVALID; }
+  if (!nccl().ok) { set_error("libnccl.so.2 not found (set FM_NCCL_LIB)"); return FM_ERR_INVALID; }
+  FM_CUDA(cudaSetDevice(device));
+  NcclId nid;
+  memcpy(&nid, id, sizeof(nid));
+  fm_comm* c = new fm_comm();
+  c->rank = rank; c->world = world; c->device = device;
+  const int r = nccl().CommInitRank(&c->comm, world, nid, rank);
+  if (r) { delete c; return nccl_fail(r, "ncclCommInitRank"); }
+  *out = c;
+  return FM_OK;
+}
+void fm_comm_destroy(fm_comm* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->comm) nccl().CommDestroy(c->comm);
+  cudaFree(c->d_send);
+  cudaFree(c->d_recv);
+  delete c;
+}
+int64_t fm_comm_last_gather_bytes(const fm_comm* c) { return c ? c->last_gather_bytes : 0; }
+int64_t fm_comm_block_capacity(const fm_comm* c) { return c ? c->last_capacity : 0; }
+
+int fm_match_batch_sharded_device(fm_index* index, fm_comm* c, const int32_t* d_q_tokens, const int32_t* d_q_off, int64_t n_q,
+                                  int64_t n_query_tokens, const fm_params* params, int64_t cap, fm_match* d_out, int32_t* d_out_count,
+                                  void* stream) {
+  Index* ix = reinterpret_cast<Index*>(index);
+  Params pr;
+  int rc;
+  if (!ix || !c || n_q < 1 || n_q > (1 << 20) || cap < 1) { set_error("bad argument"); return FM_ERR_INVALID; }
+  if (ix->device != c->device) { set_error("index and communicator live on different devices"); return FM_ERR_INVALID; }
+  if ((rc = check_params(params, &pr))) return rc;
+  if (c->world == 1)  // one shard is the whole TM
+    return fm_match_batch_device(index, d_q_tokens, d_q_off, n_q, n_query_tokens, params, cap, d_out, d_out_count, stream);
+  if (pr.contrast > 0.f) {
+    set_error("contrastive rerank needs the sentences of every shard; not supported on a sharded TM");
+    return FM_ERR_INVALID;
+  }
+  FM_CUDA(cudaSetDevice(ix->device));
+  std::lock_guard<std::mutex> coll(ix->shard_mu);  // collectives of one communicator must not interleave
+  Workspace* w = acquire(ix);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  struct Releaser { Index* ix; Workspace* w; cudaStream_t st; ~Releaser() { cudaStreamSynchronize(st); release(ix, w); } } rel{ix, w, st};
+  if ((rc = ensure_base(w)) || (rc = ensure_queries(w, n_q, n_query_tokens, false))) return rc;
+  w->real_active = false;
+  if ((rc = initial_worklists(ix, w, n_q, n_query_tokens))) return rc;
+  int launches = 0, retries = 0;
+  // Every rank takes the same decisions from the same gathered data, so the collectives stay matched: a
+  // batch is rerun by all ranks when any shard overflowed its workspace (flag in its block header) or accepted
+  // more records than a block holds (its total travels in the header; the next size follows the largest).
+  if ((rc = ensure_stage(w))) return rc;
+  for (int attempt = 0;; attempt++) {
+    if (attempt >= 10) { set_error("sharded batch does not settle (workspace / block size keep growing)"); return FM_ERR_NOMEM; }
+    const int64_t capacity = std::max<int64_t>(1024, ((int64_t)(c->rate * 1.25 * (double)n_q) + 1023) / 1024 * 1024);
+    const int64_t bytes = wire_block_bytes(n_q, capacity);
+    if (bytes > c->cap_block) {
+      cudaFree(c->d_send); cudaFree(c->d_recv);
+      c->d_send = c->d_recv = nullptr;
+      c->cap_block = 0;
+      const int64_t cb = bytes + bytes / 4;
+      FM_CUDA(cudaMalloc((void**)&c->d_send, cb));
+      FM_CUDA(cudaMalloc((void**)&c->d_recv, cb * c->world));
+      c->cap_block = cb;
+    }
+    c->last_capacity = capacity;
+    if ((rc = enqueue_accept(ix, w, d_q_tokens, d_q_off, n_q, n_query_tokens, pr, capacity, c->d_send, st, &launches))) return rc;
+    if (ix->profiling) cudaEventRecord(w->ev[6], st);
+    const int nr = nccl().AllGather(c->d_send, c->d_recv, (size_t)bytes, /*ncclInt8*/ 0, c->comm, st);
+    if (nr) return nccl_fail(nr, "ncclAllGather");
+    c->last_gather_bytes = bytes * c->world;
+    const int32_t* blocks[16];
+    for (int k = 0; k < c->world; k++) blocks[k] = reinterpret_cast<const int32_t*>(c->d_recv + (size_t)k * bytes);
+    if ((rc = enqueue_merge(ix, w, c->world, blocks, capacity * c->world, d_q_off, n_q, pr, cap, d_out, d_out_count, st, &launches))) return rc;
+    if ((rc = enqueue_done(w, st))) return rc;
+    // own overflow: regrow (wait_and_check); the gathered flags say whether anybody has to rerun
+    const int mine = wait_and_check(w, attempt, &retries);
+    if (mine < 0) return -mine;
+    const unsigned flags = w->h_mctr->overflow;
+    if (flags & 0x200u) { set_error("ranks disagree on the batch (number of queries)"); return FM_ERR_INVALID; }
+    const double seen = (double)w->h_mctr->wire_need / (double)n_q;
+    if (!(flags & 0x100u)) c->rate = std::max(c->rate * 0.98, seen);  // (totals of an overflowed pipeline mean nothing)
+    if (!(flags & (0x100u | 0x400u))) break;
+  }
+  finish_profile(ix, w, n_q, n_query_tokens, launches, retries);
   return FM_OK;
 }
 

@@ -86,6 +86,18 @@ __host__ __device__ inline uint32_t bigram_hash(int w0, int w1) {
   return (uint32_t)k;
 }
 
+// A scored candidate: what the replay of the candidate loop needs. rowmin_max = max over DP rows of the row
+// minimum (reproduces the reference's early exit); reserved[0] = sentence start in tok (contrastive rerank),
+// reserved[1..2] = scratch of the rerank.
+struct fm_record {
+  uint32_t s_id;  // global sentence id
+  int32_t longest_match;
+  int32_t length;
+  float cost;
+  float rowmin_max;
+  int32_t reserved[3];
+};
+
 struct SurvRec {  // one distinct (query, sentence) that passed both rejection bounds
   int32_t q;
   int32_t start;  // sentence start in tok (unique per sentence, ascending with s_id)
@@ -105,6 +117,7 @@ struct Counters {
   unsigned int n_long;  // bit0 / bit1: some survivor's pattern is too long for the first / second scoring kernel
   unsigned int n_cand;   // suffix-array elements that passed stage 1 of the gather (the candidate list)
   unsigned int n_verified;  // exact coverage counts (profiling)
+  unsigned int wire_need;   // merge stage: largest number of accepted records of one shard
 };
 static const int kElemBits = 38;
 static const int kSmallSlice = 4;
@@ -222,7 +235,12 @@ struct Workspace {
   unsigned int scan_epoch = 0;
   fm_match* d_out = nullptr;
   int32_t* d_out_count = nullptr;
+  // sharded TM: accepted records of the batch before they are packed (sized like the survivor arrays)
+  fm_wire* wire_stage = nullptr;
+  bool want_stage = false;
   // merged-shard buffers
+  Counters* mctr = nullptr;    // counters of the merge stage (the shard stage's stay intact for the overflow check)
+  Counters* h_mctr = nullptr;  // pinned
   fm_record* mrec = nullptr;
   int32_t *m_cnt = nullptr, *m_base = nullptr, *m_acc = nullptr;
   float* m_heap = nullptr;
@@ -254,6 +272,7 @@ struct Index {
   // workspaces
   std::mutex mu;
   std::vector<Workspace*> pool;
+  std::mutex shard_mu;  // the sharded calls of one index run one at a time (collectives must not interleave)
   bool profiling = false;
   fm_profile last_profile{};
 };
@@ -291,12 +310,18 @@ void launch_score(const IndexDev& ix, const BatchDev& b, const Params& p, int sm
 void launch_replay(const IndexDev& ix, const fm_record* rec, const int32_t* q_cnt, const int32_t* q_base, float* heapbuf,
                    unsigned long long* sort_key, unsigned long long* sort_key2, int32_t* sort_idx, int32_t* acc_cnt,
                    int32_t* mid_q, int32_t* heavy_q, const int32_t* q_off, int32_t n_q, const Params& p, int64_t cap,
-                   fm_match* out, int32_t* out_count, Counters* ctr, int sm_count, cudaStream_t st, cudaStream_t st2, cudaEvent_t ev_fork, cudaEvent_t ev_join);
+                   fm_match* out, int32_t* out_count, Counters* ctr, int sm_count, cudaStream_t st, cudaStream_t st2, cudaEvent_t ev_fork, cudaEvent_t ev_join,
+                   int32_t* wire_cnt = nullptr, fm_wire* wire_stage = nullptr);  // wire_cnt != NULL: shard mode (accepted records out)
 void launch_contrast(const IndexDev& ix, fm_record* rec, const int32_t* q_base, const int32_t* sort_idx,
                      const int32_t* acc_cnt, int32_t n_q, const Params& p, int64_t cap, fm_match* out, int32_t* out_count,
                      Counters* ctr, int sm_count, cudaStream_t st);
-void launch_merge_count(int n_shards, const int32_t* const* d_rec_off_dev, int32_t* m_cnt, int32_t n_q, cudaStream_t st);
-void launch_merge_copy(int n_shards, const int32_t* const* d_rec_off_dev, const fm_record* const* d_rec_dev,
-                       const int32_t* m_base, fm_record* mrec, int32_t n_q, cudaStream_t st);
+// wire blocks (one shard's accepted records of a batch; layout in fm_kernels.cu / include/fuzzy_match_b200.h)
+inline long long wire_off_words_host(long long n_q) { return (n_q + 1 + 3) / 4 * 4; }
+inline long long wire_block_bytes(long long n_q, long long capacity) { return 4 * (4 + wire_off_words_host(n_q)) + (long long)sizeof(fm_wire) * capacity; }
+void launch_wire_pack(int32_t* block, const Counters* ctr, const fm_wire* stage, const int32_t* q_base, int32_t n_q, int capacity,
+                      cudaStream_t st);
+void launch_wire_count(int n_shards, const int32_t* const* blocks, int32_t* m_cnt, int32_t n_q, Counters* mctr, cudaStream_t st);
+void launch_wire_copy(int n_shards, const int32_t* const* blocks, const int32_t* m_base, fm_record* mrec, int32_t n_q,
+                      const Counters* mctr, cudaStream_t st);
 
 }  // namespace fm

@@ -1561,10 +1561,22 @@ __device__ void block_sort_pairs(unsigned long long* keys, int32_t* idx, int n) 
 // bounded edit distance would have exited early or exceeded the bound: max(K, C) > bound.
 // On return idx[0..nacc) / keys[0..nacc) hold the accepted records and their result keys
 // (score desc, s_id asc; CompareMatch :25-33); rowmin_max of an accepted record now holds its score.
+struct WireOut {   // shard mode of the replay kernels: where the locally accepted records go (cnt == NULL: off)
+  int32_t* cnt;    // [n_q] accepted records of each query
+  fm_wire* stage;  // accepted records of query q at stage[q_base[q] ...] (never more than its scored candidates)
+};
+__device__ __forceinline__ fm_wire to_wire(const fm_record& r) {
+  fm_wire w;
+  w.s_id = r.s_id;
+  w.lm_len = (uint32_t)r.longest_match | ((uint32_t)r.length << 16);
+  w.cost = r.cost;
+  w.rowmin_max = r.rowmin_max;
+  return w;
+}
 __device__ int replay_sequence(fm_record* seg, int n, int p, int32_t* idx, unsigned long long* keys, float* heap,
-                               const Params& pr) {
+                               const Params& pr, fm_wire* wire = nullptr, int wire_cap = 0, int* wire_n = nullptr) {
   const int lane = threadIdx.x & 31;
-  int hn = 0, nacc = 0;
+  int hn = 0, nacc = 0, nwire = 0;
   if (lane == 0) heap_push(heap, hn, FLT_MAX);
   float bound = FLT_MAX;
   for (int c0 = 0; c0 < n; c0 += 32) {
@@ -1588,7 +1600,10 @@ __device__ int replay_sequence(fm_record* seg, int n, int p, int32_t* idx, unsig
         const float score = score_of(cost);
         heap_push(heap, hn, cost);
         if (score < pr.fuzzy || (pr.buffer > 0 && hn > pr.buffer)) heap_pop(heap, hn);
-        if (score >= pr.fuzzy) {
+        if (wire) {  // shard mode: every candidate the loop accepts, in the order it accepts them; nothing else is kept
+          if (nwire < wire_cap) wire[nwire] = to_wire(seg[id]);
+          nwire++;
+        } else if (score >= pr.fuzzy) {
           seg[id].rowmin_max = score;  // slot reused: score
           seg[id].reserved[1] = 0;     // contrastive accumulator
           seg[id].reserved[2] = 0;     // contrastive "selected" flag
@@ -1605,6 +1620,7 @@ __device__ int replay_sequence(fm_record* seg, int n, int p, int32_t* idx, unsig
     }
     __syncwarp();
   }
+  if (wire_n && lane == 0) *wire_n = nwire;
   return __shfl_sync(FULL, nacc, 0);
 }
 
@@ -1636,7 +1652,7 @@ __global__ void __launch_bounds__(256) fm_replay_small_kernel(fm_record* rec, co
                                                               const int32_t* __restrict__ q_base, int32_t* sort_idx,
                                                               int32_t* acc_cnt, int32_t* mid_q, int32_t* heavy_q,
                                                               const int32_t* __restrict__ q_off, int n_q, Params pr, long long cap,
-                                                              fm_match* out, int32_t* out_count, Counters* ctr, int warp_max) {
+                                                              fm_match* out, int32_t* out_count, Counters* ctr, int warp_max, WireOut wo) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n_q) return;
   if (ctr->overflow) return;
@@ -1647,6 +1663,19 @@ __global__ void __launch_bounds__(256) fm_replay_small_kernel(fm_record* rec, co
     return;
   }
   int nacc = 0;
+  if (wo.cnt) {  // shard mode: the single candidate is accepted unless no_perfect skips it (the bound is still FLT_MAX)
+    int c = 0;
+    if (n == 1) {
+      const fm_record r = rec[q_base[q]];
+      const int p = q_off[q + 1] - q_off[q];
+      if (!(r.rowmin_max > FLT_MAX || r.cost > FLT_MAX) && !(pr.no_perfect && r.cost == 0.f && r.length == p)) {
+        wo.stage[q_base[q]] = to_wire(r);
+        c = 1;
+      }
+    }
+    wo.cnt[q] = c;
+    return;
+  }
   if (n == 1) {
     const int base = q_base[q];
     fm_record r = rec[base];
@@ -1685,7 +1714,7 @@ __global__ void __launch_bounds__(256) fm_replay_kernel(fm_record* rec, const in
                                                         unsigned long long* sort_key, int32_t* sort_idx, int32_t* acc_cnt,
                                                         const int32_t* __restrict__ mid_q, const int32_t* __restrict__ q_off,
                                                         Params pr, long long cap, fm_match* out, int32_t* out_count,
-                                                        Counters* ctr) {
+                                                        Counters* ctr, WireOut wo) {
   __shared__ float s_heap[8][64];
   __shared__ unsigned long long s_keys[8][kWarpMax];
   const int lane = threadIdx.x & 31;
@@ -1716,6 +1745,11 @@ __global__ void __launch_bounds__(256) fm_replay_kernel(fm_record* rec, const in
   }
   __syncwarp();
   float* heap = (pr.buffer > 0 && pr.buffer <= 62) ? s_heap[threadIdx.x >> 5] : heapbuf + base + q;
+  if (wo.cnt) {  // shard mode: only the accepted records travel; the result order is made after the merge
+    replay_sequence(seg, n, p, idx, keys, heap, pr, wo.stage + base, n, wo.cnt + q);
+    __syncwarp();
+    continue;
+  }
   const int nacc = replay_sequence(seg, n, p, idx, keys, heap, pr);
   if (nacc > 1) {
     if (nacc <= 32) {
@@ -1847,7 +1881,8 @@ __global__ void __launch_bounds__(256) fm_replay_heavy_kernel(fm_record* rec, co
                                                               int32_t* sort_idx, int32_t* acc_cnt,
                                                               const int32_t* __restrict__ heavy_q,
                                                               const int32_t* __restrict__ q_off, Params pr, long long cap,
-                                                              fm_match* out, int32_t* out_count, Counters* ctr, int smem_cap) {
+                                                              fm_match* out, int32_t* out_count, Counters* ctr, int smem_cap,
+                                                              WireOut wo) {
   extern __shared__ unsigned long long s_keys[];
   __shared__ float s_heap[64];
   __shared__ int s_nacc;
@@ -1881,10 +1916,12 @@ __global__ void __launch_bounds__(256) fm_replay_heavy_kernel(fm_record* rec, co
     __syncthreads();
     if (threadIdx.x < 32) {
       float* heap = (pr.buffer > 0 && pr.buffer <= 62) ? s_heap : heapbuf + base + q;
-      const int nacc = replay_sequence(seg, n, p, idx, gkeys, heap, pr);
+      const int nacc = wo.cnt ? replay_sequence(seg, n, p, idx, gkeys, heap, pr, wo.stage + base, n, wo.cnt + q)
+                              : replay_sequence(seg, n, p, idx, gkeys, heap, pr);
       if (threadIdx.x == 0) s_nacc = nacc;
     }
     __syncthreads();
+    if (wo.cnt) continue;  // shard mode (uniform)
     const int nacc = s_nacc;
     block_sort_pairs(gkeys, idx, nacc);
     if (pr.contrast > 0.f) {
@@ -1980,29 +2017,77 @@ __global__ void __launch_bounds__(256) fm_contrast_kernel(IndexDev ix, fm_record
 }
 
 // ---------------------------------------------------------------- cross-shard merge helpers
-
-struct ShardPtrs {
-  const int32_t* off[16];
-  const fm_record* rec[16];
+//
+// One shard's block for n_q queries with room for `capacity` records (what travels in the all-gather):
+//   int32 header[4]     = (overflow flags of the shard's own pipeline, n_q, capacity, accepted records in total)
+//   int32 off[n_q + 1]  exclusive offsets of the queries' records (padded to a multiple of 4 words)
+//   fm_wire rec[capacity]   the accepted records, query after query, each in the order its loop accepted them
+struct WireBlocks {
+  const int32_t* blk[16];
 };
-__global__ void fm_merge_count_kernel(ShardPtrs sp, int n_shards, int32_t* m_cnt, int n_q) {
+__host__ __device__ inline long long wire_off_words(long long n_q) { return (n_q + 1 + 3) / 4 * 4; }
+// Compacts the staged records into the block (one thread per query) and writes the header.
+__global__ void fm_wire_pack_kernel(int32_t* block, const Counters* ctr, const fm_wire* __restrict__ stage,
+                                    const int32_t* __restrict__ q_base, int n_q, int capacity) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int32_t* off = block + 4;
+  if (q == 0) {
+    block[0] = (int32_t)ctr->overflow;
+    block[1] = n_q;
+    block[2] = capacity;
+    block[3] = off[n_q];
+  }
+  if (q >= n_q || ctr->overflow) return;
+  fm_wire* rec = reinterpret_cast<fm_wire*>(block + 4 + wire_off_words(n_q));
+  const int o0 = off[q], o1 = off[q + 1];
+  const fm_wire* src = stage + q_base[q];
+  for (int i = o0; i < o1 && i < capacity; i++) rec[i] = src[i - o0];
+}
+// m_cnt[q] = records of query q over all shards. mctr->wire_need = the largest total of one shard (the callers
+// size the next blocks from it); mctr->overflow: 0x100 a shard's own pipeline overflowed, 0x200 blocks of another
+// batch shape, 0x400 a shard accepted more records than its block holds.
+__global__ void fm_wire_count_kernel(WireBlocks wb, int n_shards, int32_t* m_cnt, int n_q, Counters* mctr) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q == 0) {
+    unsigned bad = 0, mx = 0;
+    for (int k = 0; k < n_shards; k++) {
+      const int32_t* h = wb.blk[k];
+      if (h[0]) bad |= 0x100u;
+      if (h[1] != n_q) bad |= 0x200u;
+      if (h[3] > h[2]) bad |= 0x400u;
+      mx = max(mx, (unsigned)h[3]);
+    }
+    if (bad) atomicOr(&mctr->overflow, bad);
+    mctr->wire_need = mx;
+  }
   if (q > n_q) return;
   int c = 0;
   if (q < n_q)
-    for (int k = 0; k < n_shards; k++) c += sp.off[k][q + 1] - sp.off[k][q];
+    for (int k = 0; k < n_shards; k++) c += wb.blk[k][4 + q + 1] - wb.blk[k][4 + q];
   m_cnt[q] = c;
 }
-__global__ void fm_merge_copy_kernel(ShardPtrs sp, int n_shards, const int32_t* __restrict__ m_base, fm_record* mrec,
-                                     int n_q) {
-  const int lane = threadIdx.x & 31;
-  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (q >= n_q) return;
+__global__ void fm_wire_copy_kernel(WireBlocks wb, int n_shards, const int32_t* __restrict__ m_base, fm_record* mrec, int n_q,
+                                    const Counters* mctr) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_q || mctr->overflow) return;
   int dst = m_base[q];
+  const long long ow = wire_off_words(n_q);
   for (int k = 0; k < n_shards; k++) {
-    const int b0 = sp.off[k][q], b1 = sp.off[k][q + 1];
-    for (int i = b0 + lane; i < b1; i += 32) mrec[dst + (i - b0)] = sp.rec[k][i];
-    dst += b1 - b0;
+    const int o0 = wb.blk[k][4 + q], o1 = wb.blk[k][4 + q + 1];
+    const fm_wire* src = reinterpret_cast<const fm_wire*>(wb.blk[k] + 4 + ow);
+    for (int i = o0; i < o1; i++) {
+      const fm_wire w = src[i];
+      fm_record r;
+      r.s_id = w.s_id;
+      r.longest_match = (int32_t)(w.lm_len & 0xffffu);
+      r.length = (int32_t)(w.lm_len >> 16);
+      r.cost = w.cost;
+      r.rowmin_max = w.rowmin_max;
+      r.reserved[0] = -1;
+      r.reserved[1] = 0;
+      r.reserved[2] = 0;
+      mrec[dst++] = r;
+    }
   }
 }
 
@@ -2091,11 +2176,12 @@ void launch_replay(const IndexDev& ix, const fm_record* rec, const int32_t* q_cn
                    unsigned long long* sort_key, unsigned long long* sort_key2, int32_t* sort_idx, int32_t* acc_cnt,
                    int32_t* mid_q, int32_t* heavy_q, const int32_t* q_off, int32_t n_q, const Params& p, int64_t cap,
                    fm_match* out, int32_t* out_count, Counters* ctr, int sm_count, cudaStream_t st, cudaStream_t st2,
-                   cudaEvent_t ev_fork, cudaEvent_t ev_join) {
+                   cudaEvent_t ev_fork, cudaEvent_t ev_join, int32_t* wire_cnt, fm_wire* wire_stage) {
+  const WireOut wo{wire_cnt, wire_stage};
   // FM_WARP_MAX=<n> (32..kWarpMax) moves the warp / CTA boundary (tests/test_gpu_scale.py: fresh process per setting)
   static const int warp_max = getenv("FM_WARP_MAX") ? std::max(32, std::min(kWarpMax, atoi(getenv("FM_WARP_MAX")))) : kWarpMax;
   fm_replay_small_kernel<<<(n_q + 255) / 256, 256, 0, st>>>(const_cast<fm_record*>(rec), q_cnt, q_base, sort_idx, acc_cnt, mid_q,
-                                                            heavy_q, q_off, n_q, p, (long long)cap, out, out_count, ctr, warp_max);
+                                                            heavy_q, q_off, n_q, p, (long long)cap, out, out_count, ctr, warp_max, wo);
   const size_t smem = (size_t)kHeavySmem * sizeof(unsigned long long);
   // FM_HEAVY_SMEM=<n> lowers the shared-memory sort limit: the CTA radix sort then takes shorter lists too
   // (tests/test_gpu_scale.py; without it lists of more than kHeavySmem candidates take that path)
@@ -2110,12 +2196,12 @@ void launch_replay(const IndexDev& ix, const fm_record* rec, const int32_t* q_cn
     cudaStreamWaitEvent(st2, ev_fork, 0);
   }
   fm_replay_heavy_kernel<<<sm_count * 2, 256, smem, sh>>>(const_cast<fm_record*>(rec), q_cnt, q_base, heapbuf, sort_key, sort_key2,
-                                                          sort_idx, acc_cnt, heavy_q, q_off, p, (long long)cap, out, out_count, ctr, smem_cap);
+                                                          sort_idx, acc_cnt, heavy_q, q_off, p, (long long)cap, out, out_count, ctr, smem_cap, wo);
   if (st2) cudaEventRecord(ev_join, st2);
   int grid = (n_q + 7) / 8;
   if (grid > sm_count * 8) grid = sm_count * 8;
   fm_replay_kernel<<<grid, 256, 0, st>>>(const_cast<fm_record*>(rec), q_cnt, q_base, heapbuf, sort_key, sort_idx, acc_cnt, mid_q,
-                                         q_off, p, (long long)cap, out, out_count, ctr);
+                                         q_off, p, (long long)cap, out, out_count, ctr, wo);
   if (st2) cudaStreamWaitEvent(st, ev_join, 0);
 }
 void launch_contrast(const IndexDev& ix, fm_record* rec, const int32_t* q_base, const int32_t* sort_idx,
@@ -2130,16 +2216,20 @@ void launch_contrast(const IndexDev& ix, fm_record* rec, const int32_t* q_base, 
   fm_contrast_kernel<<<grid, 256, smem, st>>>(ix, rec, q_base, sort_idx, acc_cnt, n_q, p, (long long)cap, out, out_count, ctr, stride);
 }
 
-void launch_merge_count(int n_shards, const int32_t* const* off, int32_t* m_cnt, int32_t n_q, cudaStream_t st) {
-  ShardPtrs sp{};
-  for (int k = 0; k < n_shards; k++) sp.off[k] = off[k];
-  fm_merge_count_kernel<<<(n_q + 256) / 256, 256, 0, st>>>(sp, n_shards, m_cnt, n_q);
+void launch_wire_pack(int32_t* block, const Counters* ctr, const fm_wire* stage, const int32_t* q_base, int32_t n_q, int capacity,
+                      cudaStream_t st) {
+  fm_wire_pack_kernel<<<(n_q + 255) / 256, 256, 0, st>>>(block, ctr, stage, q_base, n_q, capacity);
 }
-void launch_merge_copy(int n_shards, const int32_t* const* off, const fm_record* const* rec, const int32_t* m_base,
-                       fm_record* mrec, int32_t n_q, cudaStream_t st) {
-  ShardPtrs sp{};
-  for (int k = 0; k < n_shards; k++) { sp.off[k] = off[k]; sp.rec[k] = rec[k]; }
-  fm_merge_copy_kernel<<<(n_q + 7) / 8, 256, 0, st>>>(sp, n_shards, m_base, mrec, n_q);
+void launch_wire_count(int n_shards, const int32_t* const* blocks, int32_t* m_cnt, int32_t n_q, Counters* mctr, cudaStream_t st) {
+  WireBlocks wb{};
+  for (int k = 0; k < n_shards; k++) wb.blk[k] = blocks[k];
+  fm_wire_count_kernel<<<(n_q + 256) / 256, 256, 0, st>>>(wb, n_shards, m_cnt, n_q, mctr);
+}
+void launch_wire_copy(int n_shards, const int32_t* const* blocks, const int32_t* m_base, fm_record* mrec, int32_t n_q,
+                      const Counters* mctr, cudaStream_t st) {
+  WireBlocks wb{};
+  for (int k = 0; k < n_shards; k++) wb.blk[k] = blocks[k];
+  fm_wire_copy_kernel<<<(n_q + 255) / 256, 256, 0, st>>>(wb, n_shards, m_base, mrec, n_q, mctr);
 }
 
 }  // namespace fm

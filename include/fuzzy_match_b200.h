@@ -8,8 +8,8 @@
  *   fm_index_create      <- FuzzyMatch::add_tm(id, Tokens) x N + FuzzyMatch::sort()
  *   fm_match_batch       <- FuzzyMatch::match(Tokens, ...) for a batch of patterns (host buffers)
  *   fm_match_batch_device<- same, device-resident inputs/outputs on a caller stream
- *   fm_shard_score_device + fm_merge_replay_device <- the same path split at the per-shard / cross-shard boundary for a TM
- *                           sharded by sentence-id range over several GPUs
+ *   fm_match_batch_sharded_device (fm_shard_accept_device + NCCL all-gather + fm_merge_accepted_device)
+ *                        <- the same path for a TM sharded by sentence-id range over several GPUs
  * Plain pointers and sizes only; status codes, no exceptions; every function is safe to call from
  * several host threads on one shared index (like the reference's const match()).
  *
@@ -60,17 +60,6 @@ typedef struct fm_match {
   int32_t length;
   float cost;
 } fm_match;
-
-/* A scored candidate of one (query, shard): everything the cross-shard replay needs.
- * rowmin_max = max over DP rows of the row minimum (reproduces the reference's early exit). */
-typedef struct fm_record {
-  uint32_t s_id; /* global sentence id */
-  int32_t longest_match;
-  int32_t length;
-  float cost;
-  float rowmin_max;
-  int32_t reserved[3];
-} fm_record;
 
 /* Per-stage device times of the last completed batch on this index (milliseconds, CUDA events on
  * the stream the kernels ran on) and the work it did. Filled only when profiling is enabled. */
@@ -152,19 +141,59 @@ int fm_match_batch_device_submit(fm_index* index, const int32_t* d_q_tokens, con
                                  int32_t* d_out_count, void* stream, fm_ticket** ticket);
 int fm_ticket_wait(fm_ticket* ticket);
 
-/* Sharded TM: per-shard half. Scores every surviving candidate of this shard and returns them grouped
- * by query: d_rec_off[n_q+1] (exclusive offsets) and d_rec[*n_rec] (device pointers owned by the index,
- * valid until its next call). */
-int fm_shard_score_device(fm_index* index, const int32_t* d_q_tokens, const int32_t* d_q_off, int64_t n_q,
-                          int64_t n_query_tokens, const fm_params* params, const int32_t** d_rec_off,
-                          const fm_record** d_rec, int64_t* n_rec, void* stream);
-/* Sharded TM: cross-shard half. Replays the union of n_shards record sets (each grouped by query,
- * shards in ascending s_id order: d_rec_off[k] -> [n_q+1], d_rec[k]) exactly like the single-index
- * candidate loop (bound heap, top-N, contrastive rerank). Device pointers; host arrays of pointers. */
-int fm_merge_replay_device(fm_index* index, int n_shards, const int32_t* const* d_rec_off,
-                           const fm_record* const* d_rec, const int32_t* d_q_off, int64_t n_q,
-                           const fm_params* params, int64_t cap, fm_match* d_out, int32_t* d_out_count,
-                           void* stream);
+/* ---- TM sharded by sentence-id range over several GPUs (BASELINE.json north_star; no counterpart in the
+ * reference, which is single-process). Each shard is an fm_index built over its sentence range with the global
+ * IDF statistics (fm_index_create: sfreq_global, n_sent_global, s_id_base). Per batch every shard runs the
+ * whole pipeline on its own sentences INCLUDING the candidate loop of src/fuzzy_match.cc:567-611 and keeps
+ * the records that loop accepts (its bound is never tighter than the global one, so this is a superset of
+ * what the global loop accepts in that shard); ONE all-gather moves those records (16 bytes each) in blocks of
+ * one size;
+ * every rank then replays the union in the reference's candidate order -- bit-identical to one index.
+ *
+ * One accepted record on the wire (16 bytes). */
+typedef struct fm_wire {
+  uint32_t s_id;    /* global sentence id */
+  uint32_t lm_len;  /* longest n-gram match | sentence length << 16 */
+  float cost;
+  float rowmin_max;
+} fm_wire;
+/* Size of one shard's block for n_q queries with room for `capacity` records:
+ * int32 header[4] (overflow flags, n_q, capacity, accepted records in total) | int32 off[n_q + 1, padded to 4] |
+ * fm_wire rec[capacity] -- the accepted records query after query, each in the order its loop accepted them. */
+int64_t fm_wire_block_bytes(int64_t n_q, int64_t capacity);
+/* Per-shard half: fills d_block (device, caller-owned, fm_wire_block_bytes) with the records the shard's own
+ * candidate loop accepts (the header says how many there were; records beyond the capacity are dropped). Returns
+ * after the stream has finished; a workspace overflow of this shard is handled inside (rerun). */
+int fm_shard_accept_device(fm_index* shard, const int32_t* d_q_tokens, const int32_t* d_q_off, int64_t n_q,
+                           int64_t n_query_tokens, const fm_params* params, int64_t capacity, void* d_block, void* stream);
+/* Cross-shard half: replays the union of n_shards blocks (ascending s_id order) exactly like the single-index
+ * candidate loop (bound heap, top-N). total_capacity = sum of the blocks' capacities. If a shard accepted more
+ * records than its block holds, *need_capacity = the largest total of one shard and the results are not written:
+ * rerun both halves with blocks of at least that capacity (otherwise 0). `index` only provides the device and a
+ * workspace (any shard). Contrastive rerank needs the sentences behind the records: FM_ERR_INVALID. */
+int fm_merge_accepted_device(fm_index* index, int n_shards, const void* const* d_blocks, int64_t total_capacity,
+                             const int32_t* d_q_off, int64_t n_q, const fm_params* params, int64_t cap, fm_match* d_out,
+                             int32_t* d_out_count, int64_t* need_capacity, void* stream);
+
+/* The two halves around one NCCL all-gather, one process per GPU: the communicator is NCCL's own
+ * (libnccl.so.2 is opened at run time; FM_ERR_INVALID if it is missing). Rank 0 calls fm_comm_unique_id and
+ * hands the 128 bytes to every rank by any means (the Python mirror broadcasts them with torch.distributed);
+ * fm_comm_create is collective. */
+#define FM_COMM_ID_BYTES 128
+typedef struct fm_comm fm_comm;
+int fm_comm_unique_id(void* id_out);
+int fm_comm_create(const void* id, int rank, int world, int device, fm_comm** out);
+void fm_comm_destroy(fm_comm* comm);
+/* One batch against the sharded TM: every rank passes the same queries (device) and gets the complete result
+ * in d_out / d_out_count. Collective; returns after the stream has finished. The block capacity follows the
+ * number of records recent batches accepted; a batch that needs more is rerun by all ranks together, as is a
+ * batch during which some rank had to regrow its workspace. */
+int fm_match_batch_sharded_device(fm_index* shard, fm_comm* comm, const int32_t* d_q_tokens, const int32_t* d_q_off,
+                                  int64_t n_q, int64_t n_query_tokens, const fm_params* params, int64_t cap,
+                                  fm_match* d_out, int32_t* d_out_count, void* stream);
+/* Bytes received by the last all-gather of this communicator and the record capacity of its blocks. */
+int64_t fm_comm_last_gather_bytes(const fm_comm* comm);
+int64_t fm_comm_block_capacity(const fm_comm* comm);
 
 int fm_set_profiling(fm_index* index, int enabled);
 int fm_get_profile(const fm_index* index, fm_profile* out);

@@ -126,9 +126,18 @@ static void batch_and_append() {
   fm.match_batch({split("a b c d e"), split("x y z"), split("q q q"), {}}, 0.5, 2, out);
   EXPECT(out.size() == 4 && out[0].size() == 2 && out[1].size() == 1 && out[2].empty() && out[3].empty());
   if (out[0].size() == 2) EXPECT(out[0][0].s_id == 0 && out[0][0].score == 1.f && out[0][0].id == "");
-  std::vector<fuzzy::FuzzyMatch::Match> m(1);  // match() appends to what is already there
+  // match() appends to what is already there and stops at number_of_matches entries IN TOTAL
+  // (reference src/fuzzy_match.cc:670-679: `matches.size() < number_of_matches`)
+  std::vector<fuzzy::FuzzyMatch::Match> m(1);
   EXPECT(fm.match(split("x y z"), 0.5, 1, m));
-  EXPECT(m.size() == 2);
+  EXPECT(m.size() == 1);
+  EXPECT(fm.match(split("x y z"), 0.5, 2, m));
+  EXPECT(m.size() == 2 && m[1].s_id == 2);
+  EXPECT(fm.match(split("a b c d e"), 0.5, 0, m));  // 0 = all
+  EXPECT(m.size() == 4);
+  bool refused = false;
+  try { fm.match(split("a b c d e"), 0.5, 0, m, 2, 0, 0, fuzzy::EditCosts(), 0.5f); } catch (const std::logic_error&) { refused = true; }
+  EXPECT(refused);  // contrastive rerank against earlier entries is refused, not answered differently
 }
 
 static void sentence_api() {

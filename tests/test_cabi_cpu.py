@@ -31,7 +31,7 @@ def test_every_declared_symbol_is_exported(lib):
 def test_struct_layouts_match_header():
     assert C.sizeof(capi.Params) == 12 * 4
     assert capi.MATCH_DTYPE.itemsize == 24
-    assert capi.RECORD_DTYPE.itemsize == 32
+    assert capi.WIRE_DTYPE.itemsize == 16
 
 
 def test_version_and_error_strings(lib):

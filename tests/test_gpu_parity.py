@@ -139,46 +139,62 @@ def test_errors_are_loud():
         fmb.Index(np.array([2, 3], dtype=np.int32), np.array([0, 2], dtype=np.int64), 10, max_tokens=5000)
 
 
-def test_sharded_tm_two_shards_one_gpu():
-    """The sharded path (fm_shard_score_device per shard + fm_merge_replay_device over the union)
-    must equal the unsharded oracle bit for bit: two sentence-id shards on one GPU, global IDF."""
+def test_sharded_tm_shards_one_gpu():
+    """The sharded path without the collective: fm_shard_accept_device per shard (the shard's own candidate loop,
+    accepted records in one block per shard) + fm_merge_accepted_device over the blocks must equal the unsharded
+    oracle bit for bit -- two and three sentence-id shards on one GPU, global IDF; a block that is too small is
+    reported and the rerun with the reported capacity is complete."""
     import torch
     from fuzzy_match_b200 import capi, sharded
     tm, off, V = synth.make_tm(6000, vocab=700, len_lo=0, len_hi=30, seed=101)
     q, qo = synth.make_queries(tm, off, 400, vocab=700, seed=102, len_lo=1, len_hi=30)
     oracle = ob.OracleIndex(tm, off, V, max_tokens=28)
     n_sent = len(off) - 1
-    shards, base = [], 0
-    for r in range(2):
-        lo, hi = sharded.shard_range(n_sent, r, 2)
-        ix = fmb.Index(tm[off[lo]:off[hi]], off[lo:hi + 1] - off[lo], V, max_tokens=28, s_id_base=base)
-        base += ix.num_sentences
-        shards.append(ix)
-    sf = sum(ix.sfreq().astype(np.int64) for ix in shards).astype(np.uint32)
-    assert (sf == oracle.sfreq).all() and base == oracle.num_sentences
-    for ix in shards:
-        ix.set_idf_stats(sf, base)
     dev = torch.device("cuda", 0)
     d_tok = torch.as_tensor(q, device=dev)
     d_off = torch.as_tensor(qo.astype(np.int32), device=dev)
     n_q, n_tok, cap = len(qo) - 1, int(qo[-1]), 8
     st = torch.cuda.current_stream(dev).cuda_stream
-    for params in (dict(fuzzy=0.5, n=4, ml=2), dict(fuzzy=0.4, n=3, ml=3, idf=1.0, costs=(1, 0, 1)), dict(fuzzy=0.6, n=1, ml=3, mr=0.3)):
-        p = capi.Params.make(**params)
-        offs, recs = [], []
+    for n_shards in (2, 3):
+        shards, base = [], 0
+        for r in range(n_shards):
+            lo, hi = sharded.shard_range(n_sent, r, n_shards)
+            ix = fmb.Index(tm[off[lo]:off[hi]], off[lo:hi + 1] - off[lo], V, max_tokens=28, s_id_base=base)
+            base += ix.num_sentences
+            shards.append(ix)
+        sf = sum(ix.sfreq().astype(np.int64) for ix in shards).astype(np.uint32)
+        assert (sf == oracle.sfreq).all() and base == oracle.num_sentences
         for ix in shards:
-            o, r, n = ix.shard_score_device(d_tok.data_ptr(), d_off.data_ptr(), n_q, n_tok, stream=st, params=p)
-            offs.append(o)
-            recs.append(r)
-        d_out = torch.zeros(n_q * cap * 24, dtype=torch.uint8, device=dev)
-        d_cnt = torch.zeros(n_q, dtype=torch.int32, device=dev)
-        shards[0].merge_replay_device(offs, recs, d_off.data_ptr(), n_q, d_out.data_ptr(), d_cnt.data_ptr(), cap, stream=st, params=p)
-        torch.cuda.synchronize()
-        out = d_out.cpu().numpy().view(capi.MATCH_DTYPE).reshape(n_q, cap)
-        cnt = d_cnt.cpu().numpy()
-        ro, oc = oracle.match_batch(q, qo, cap=cap, **params)
-        assert (cnt == oc).all()
-        assert [as_tuples(out[i, :cnt[i]], True) for i in range(n_q)] == [as_tuples(r, True) for r in ro]
+            ix.set_idf_stats(sf, base)
+        grew = 0
+        for params in (dict(fuzzy=0.5, n=4, ml=2), dict(fuzzy=0.4, n=3, ml=3, idf=1.0, costs=(1, 0, 1)), dict(fuzzy=0.6, n=1, ml=3, mr=0.3),
+                       dict(fuzzy=0.3, n=0, ml=2), dict(fuzzy=0.5, n=2, ml=2, no_perfect=True)):
+            p = capi.Params.make(**params)
+            capacity = 64
+            for attempt in range(8):
+                blocks = [torch.zeros(capi.wire_block_bytes(n_q, capacity), dtype=torch.uint8, device=dev) for _ in shards]
+                for ix, blk in zip(shards, blocks):
+                    ix.shard_accept_device(d_tok.data_ptr(), d_off.data_ptr(), n_q, n_tok, capacity, blk.data_ptr(), stream=st, params=p)
+                d_out = torch.zeros(n_q * cap * 24, dtype=torch.uint8, device=dev)
+                d_cnt = torch.zeros(n_q, dtype=torch.int32, device=dev)
+                need = shards[0].merge_accepted_device([b.data_ptr() for b in blocks], capacity * n_shards, d_off.data_ptr(), n_q,
+                                                       d_out.data_ptr(), d_cnt.data_ptr(), cap, stream=st, params=p)
+                torch.cuda.synchronize()
+                if need == 0:
+                    break
+                assert need > capacity
+                capacity, grew = need, grew + 1
+            out = d_out.cpu().numpy().view(capi.MATCH_DTYPE).reshape(n_q, cap)
+            cnt = d_cnt.cpu().numpy()
+            ro, oc = oracle.match_batch(q, qo, cap=cap, **params)
+            assert (cnt == oc).all()
+            assert [as_tuples(out[i, :min(cnt[i], cap)], True) for i in range(n_q)] == [as_tuples(r, True) for r in ro]
+            # the blocks carry only what the shard's own loop accepted: far fewer records than scored candidates
+            hdr = blocks[0][:16].cpu().numpy().view(np.int32)
+            assert hdr[0] == 0 and hdr[1] == n_q and hdr[2] == capacity and 0 < hdr[3] <= capacity
+        assert grew >= 1  # (64 records are not enough for 400 queries: the first attempt reports the size it needs)
+        for ix in shards:
+            ix.close()
 
 
 def test_device_resident_api_matches_host_api(medium):

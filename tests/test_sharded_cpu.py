@@ -1,5 +1,6 @@
 """world_size-2 gloo tests (CPU) of the host-side logic of the sharded path: shard ranges and s_id
-bases, the sfreq all-reduce, and the pack / all-gather / unpack of per-shard record buffers."""
+bases, the sfreq all-reduce, handing the communicator id to the ranks, and the wire-block layout the
+ranks exchange (include/fuzzy_match_b200.h: fm_wire_block_bytes)."""
 import os
 import socket
 
@@ -34,23 +35,10 @@ def _worker(rank, world, port, ret):
             if 0 < len(sent) <= max_tokens:
                 sf[np.unique(sent)] += 1
         sf_global = sharded.allreduce_sfreq(sf, "cpu")
-        # per-shard record buffers of different sizes
-        n_q = 37
-        rng = np.random.default_rng(100 + rank)
-        cnt = rng.integers(0, 4 + 3 * rank, size=n_q)
-        rec_off = torch.zeros(n_q + 1, dtype=torch.int32)
-        rec_off[1:] = torch.as_tensor(np.cumsum(cnt).astype(np.int32))
-        n_rec = int(rec_off[-1])
-        rec_words = torch.as_tensor(rng.integers(0, 1 << 30, size=n_rec * 8).astype(np.int32))
-        allc = torch.empty(world, dtype=torch.int64)
-        dist.all_gather_into_tensor(allc, torch.tensor([n_rec], dtype=torch.int64))
-        max_rec = int(allc.max())
-        buf = sharded.pack_records(rec_off, rec_words, n_q, max_rec)
-        recv = sharded.gather_records(buf)
-        hw = sharded.header_words(n_q)
-        ret[rank] = dict(lo=lo, hi=hi, n_kept=n_kept, base=base, n_global=n_global, sf_global=sf_global,
-                         rec_off=rec_off.numpy().copy(), rec_words=rec_words.numpy().copy(),
-                         recv=recv.numpy().copy(), hw=hw, counts=allc.numpy().copy())
+        # the 128-byte communicator id travels from rank 0 to everybody
+        secret = bytes((7 * i + 3) % 256 for i in range(128))
+        got = sharded.broadcast_bytes(secret if rank == 0 else b"", 128, "cpu")
+        ret[rank] = dict(lo=lo, hi=hi, n_kept=n_kept, base=base, n_global=n_global, sf_global=sf_global, uid=got, secret=secret)
     finally:
         dist.destroy_process_group()
 
@@ -73,12 +61,13 @@ def test_sharded_host_logic_world2():
     for s in np.nonzero(kept)[0]:
         sf[np.unique(tm[off[s]:off[s + 1]])] += 1
     assert (r[0]["sf_global"] == sf).all() and (r[1]["sf_global"] == sf).all()
-    # every rank received every shard's offsets and records at the documented positions
-    for me in range(world):
-        recv, hw = r[me]["recv"], r[me]["hw"]
-        for k in range(world):
-            n_q = len(r[k]["rec_off"]) - 1
-            assert (recv[k, :n_q + 1] == r[k]["rec_off"]).all()
-            nw = len(r[k]["rec_words"])
-            assert (recv[k, hw:hw + nw] == r[k]["rec_words"]).all()
-        assert hw % 8 == 0 and recv.shape[1] == hw + 8 * int(r[me]["counts"].max())
+    assert r[0]["uid"] == r[1]["uid"] == r[0]["secret"]
+
+
+def test_wire_block_layout():
+    """header (4 int32) | offsets (n_q + 1, padded to 4) | 16-byte records: the size every rank computes for the all-gather."""
+    from fuzzy_match_b200 import capi
+    assert capi.WIRE_DTYPE.itemsize == 16
+    for n_q, cap in ((1, 1), (37, 2), (100000, 65536), (4096, 0)):
+        assert capi.wire_block_bytes(n_q, cap) == 4 * (4 + (n_q + 1 + 3) // 4 * 4) + 16 * cap
+        assert capi.wire_block_bytes(n_q, cap) % 16 == 0
