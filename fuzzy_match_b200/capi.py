@@ -56,7 +56,8 @@ class Profile(C.Structure):
                 ("ms_score", C.c_float), ("ms_replay", C.c_float), ("ms_total", C.c_float),
                 ("n_queries", C.c_int64), ("n_query_tokens", C.c_int64), ("n_slices", C.c_int64),
                 ("n_elements", C.c_int64), ("n_survivors", C.c_int64), ("n_matches", C.c_int64),
-                ("launches", C.c_int32), ("retries", C.c_int32), ("n_stage2", C.c_int64), ("n_verified", C.c_int64)]
+                ("launches", C.c_int32), ("retries", C.c_int32), ("n_stage2", C.c_int64), ("n_verified", C.c_int64),
+                ("ms_walk", C.c_float), ("ms_verify", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

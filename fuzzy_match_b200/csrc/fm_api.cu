@@ -86,7 +86,7 @@ static int ensure_queries(Workspace* w, int64_t n_q, int64_t n_tok, bool staging
 static int ensure_wide(Index* ix, Workspace* w) {
   if (ix->dev.n_wide == 0 || w->cap_wq >= w->cap_q) return FM_OK;
   int rc;
-  if ((rc = dev_realloc(&w->wq, (size_t)w->cap_q * 3 * kWideWords)) || (rc = dev_realloc(&w->wextra, (size_t)w->cap_q))) return rc;
+  if ((rc = dev_realloc(&w->wq, (size_t)w->cap_q * kWideStride))) return rc;
   w->cap_wq = w->cap_q;
   return FM_OK;
 }
@@ -161,7 +161,7 @@ static int ensure_out(Workspace* w, int64_t n_q, int64_t cap) {
 }
 
 static void free_workspace(Workspace* w) {
-  cudaFree(w->d_q_tok); cudaFree(w->d_q_off); cudaFree(w->d_q_real); cudaFree(w->d_q_gap); cudaFree(w->d_itok_dist); cudaFree(w->pat); cudaFree(w->chain_q); cudaFree(w->qmeta); cudaFree(w->tbl); cudaFree(w->cmin_tab); cudaFree(w->span_slice); cudaFree(w->qmask); cudaFree(w->wq); cudaFree(w->peq64); cudaFree(w->cmin64); cudaFree(w->wextra); cudaFree(w->sm_rec);
+  cudaFree(w->d_q_tok); cudaFree(w->d_q_off); cudaFree(w->d_q_real); cudaFree(w->d_q_gap); cudaFree(w->d_itok_dist); cudaFree(w->pat); cudaFree(w->chain_q); cudaFree(w->qmeta); cudaFree(w->tbl); cudaFree(w->cmin_tab); cudaFree(w->span_slice); cudaFree(w->qmask); cudaFree(w->wq); cudaFree(w->peq64); cudaFree(w->cmin64); cudaFree(w->sm_rec);
   cudaFree(w->sl_start); cudaFree(w->sl_rec); cudaFree(w->hkey); cudaFree(w->hlm); cudaFree(w->surv); cudaFree(w->cand); cudaFree(w->surv_len);
   cudaFree(w->q_cnt); cudaFree(w->q_base); cudaFree(w->acc_cnt); cudaFree(w->rec); cudaFree(w->heapbuf); cudaFree(w->ctr); cudaFree(w->mctr); cudaFree(w->wire_stage); cudaFree(w->scan_chain);
   cudaFree(w->d_out); cudaFree(w->d_out_count); cudaFree(w->mrec); cudaFree(w->m_cnt); cudaFree(w->m_base); cudaFree(w->m_acc); cudaFree(w->m_heap); cudaFree(w->heavy_q); cudaFree(w->m_heavy); cudaFree(w->mid_q); cudaFree(w->m_mid); cudaFree(w->sort_key); cudaFree(w->sort_key2); cudaFree(w->m_key2); cudaFree(w->sort_idx); cudaFree(w->m_key); cudaFree(w->m_idx);
@@ -208,7 +208,7 @@ static int stage_check(cudaStream_t st, const char* what) {
 static BatchDev make_batch(Workspace* w, const int32_t* d_q_tok, const int32_t* d_q_off, int64_t n_q, int64_t n_tok) {
   BatchDev b{};
   b.q_tok_in = d_q_tok; b.q_off = d_q_off; b.n_q = (int32_t)n_q; b.n_tok = (int32_t)n_tok;
-  b.pat = w->pat; b.chain_q = w->chain_q; b.qmeta = w->qmeta; b.tbl = w->tbl; b.cmin_tab = w->cmin_tab; b.cmin64 = w->cmin64; b.qmask = w->qmask; b.wq = w->cap_wq ? w->wq : nullptr; b.wextra = w->wextra; b.peq64 = w->peq64;
+  b.pat = w->pat; b.chain_q = w->chain_q; b.qmeta = w->qmeta; b.tbl = w->tbl; b.cmin_tab = w->cmin_tab; b.cmin64 = w->cmin64; b.qmask = w->qmask; b.wq = w->cap_wq ? w->wq : nullptr; b.peq64 = w->peq64;
   b.span_slice = w->span_slice; b.span_cap = w->cap_spans;
   b.sl_start = w->sl_start; b.sl_rec = w->sl_rec; b.sm_rec = w->sm_rec; b.slice_cap = w->cap_slices;
   b.hkey = w->hkey; b.hlm = w->hlm; b.hmask = w->hs_use - 1;
@@ -253,7 +253,7 @@ static int launch_shard(Index* ix, Workspace* w, const int32_t* d_q_tok, const i
   launch_search(ix->dev, b, pr, st);
   if (ix->profiling) cudaEventRecord(w->ev[2], st);
   if ((rc = stage_check(st, "search kernel"))) return rc;
-  launch_gather(ix->dev, b, pr, ix->sm_count, st);
+  launch_gather(ix->dev, b, pr, ix->sm_count, st, ix->profiling ? w->ev[8] : nullptr);
   if (ix->profiling) cudaEventRecord(w->ev[3], st);
   if ((rc = stage_check(st, "gather kernels"))) return rc;
   launch_scan(w->q_cnt, w->q_base, (int32_t)n_q, w->scan_chain, ++w->scan_epoch, ix->sm_count, st);
@@ -336,6 +336,8 @@ static void finish_profile(Index* ix, Workspace* w, int64_t n_q, int64_t n_tok, 
   cudaEventElapsedTime(&ms, w->ev[0], w->ev[1]); p.ms_prepare = ms;
   cudaEventElapsedTime(&ms, w->ev[1], w->ev[2]); p.ms_search = ms;
   cudaEventElapsedTime(&ms, w->ev[2], w->ev[3]); p.ms_gather = ms;
+  cudaEventElapsedTime(&ms, w->ev[2], w->ev[8]); p.ms_walk = ms;
+  cudaEventElapsedTime(&ms, w->ev[8], w->ev[3]); p.ms_verify = ms;
   cudaEventElapsedTime(&ms, w->ev[3], w->ev[4]); p.ms_scan = ms;
   cudaEventElapsedTime(&ms, w->ev[4], w->ev[5]); p.ms_score = ms;
   cudaEventElapsedTime(&ms, w->ev[5], w->ev[6]); p.ms_replay = ms;

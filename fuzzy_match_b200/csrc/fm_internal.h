@@ -74,6 +74,11 @@ __host__ __device__ inline unsigned sig_bit(int w) { return 6u + (((((unsigned)w
 // sentences longer than this carry a 1024-bit signature (wsig) instead of the 64-bit one
 static const int kWideMin = 48;
 static const int kWideWords = 32;  // 32-bit words per wide signature
+// Per query, for the wide signatures: three bit-sliced planes of min(pattern positions per wide bit, 7), then up to
+// kWideBig entries (bit | excess << 16) for the bits that collect more than 7 positions, then one word: the excess
+// of further such bits (counted as present).
+static const int kWideBig = 8;
+static const int kWideStride = 3 * kWideWords + 16;
 __host__ __device__ inline unsigned wsig_bit(int w) {
   unsigned x = (unsigned)w * 0x85EBCA6Bu;
   x ^= x >> 15;
@@ -142,8 +147,7 @@ struct BatchDev {
   const uint16_t* cmin_tab; // [(max_tokens+1) << 10] per (pattern length << 10 | sentence length): smallest coverage that passes
   const uint16_t* cmin64;   // [(max_tokens+1) << 6] the same for the 6-bit length field of a walk record (stage 1 of the gather)
   int4* qmask;       // [n_q] per query, in record layout: planes (B0 lo, B0 hi, B1 lo, B1 hi) of min(pattern positions per signature bit, 3)
-  int32_t* wextra;   // [n_q] wide planes: (largest count on one wide bit) - 7, at least 0
-  uint32_t* wq;      // [96*n_q] or NULL (index without wide signatures): the same three planes over the 1024 wide bits
+  uint32_t* wq;      // [kWideStride*n_q] or NULL (index without wide signatures): planes and excess list over the 1024 wide bits
   unsigned long long* peq64;  // [n_tok] patterns of <= 64 tokens: position mask of each distinct word, at q_off + distinct index
   // search output: slices of more than kSmallSlice elements, flattened, and the small ones
   long long* sl_start;  // [slice_cap+1] first flattened element of each slice (ascending)
@@ -208,7 +212,6 @@ struct Workspace {
   int2* tbl = nullptr;
   uint16_t* cmin_tab = nullptr;
   uint16_t* cmin64 = nullptr;
-  int32_t* wextra = nullptr;
   int4* sm_rec = nullptr;
   int32_t* span_slice = nullptr;
   int64_t cap_spans = 0;
@@ -250,7 +253,7 @@ struct Workspace {
   int32_t* h_q_off32 = nullptr;
   int64_t cap_hq = 0;
   // profiling
-  cudaEvent_t ev[8] = {};
+  cudaEvent_t ev[10] = {};  // 0..6 stage boundaries, 7 host timing, 8 between the two gather kernels
   bool in_use = false;
 };
 
@@ -303,7 +306,7 @@ int gpu_suffix_sort(const int32_t* d_tok, int64_t n_buf, const std::vector<int32
 void launch_bounds(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st);
 void launch_prepare(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st);
 void launch_search(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st);
-void launch_gather(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st);  // walk + verify
+void launch_gather(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st, cudaEvent_t between);  // walk + verify
 void launch_scan(const int32_t* in, int32_t* out, int32_t n, unsigned long long* chain, unsigned int epoch, int sm_count,
                  cudaStream_t st);
 void launch_score(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st);

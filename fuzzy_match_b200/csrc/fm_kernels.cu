@@ -153,82 +153,59 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
   __shared__ int s_cnt[8][64];
   __shared__ unsigned long long s_peq[8][64];
   __shared__ uint32_t s_wcnt[8][512];  // 1024 16-bit counters per warp (wide signature bits)
-  int c_lo = 0, c_hi = 0;  // pattern positions per signature bit (lane, lane + 32); unknown words excluded
-  if (ts <= 128) {
-    // Small pattern (p <= 64): lanes insert their words concurrently into a shared-memory table
-    // (CAS on the key, atomic add on the multiplicity), distinct indices are then handed out in slot
-    // order, and the per-bit position counts come from the table's (word, multiplicity) entries.
-    int2* wtbl = s_tbl[threadIdx.x >> 5];
-    int* cnt = s_cnt[threadIdx.x >> 5];
-    for (int j = lane; j < ts; j += 32) wtbl[j] = make_int2(-1, 0);
-    cnt[lane] = 0;
-    cnt[lane + 32] = 0;
+  // Lanes insert their words concurrently (CAS on the key, atomic add on the multiplicity) -- into a
+  // shared-memory table for patterns of up to 64 words, straight into the query's table in global memory for
+  // longer ones; distinct indices are then handed out in slot order.
+  const bool small = ts <= 128;
+  int2* wtbl = small ? s_tbl[threadIdx.x >> 5] : tbl;
+  int* cnt = s_cnt[threadIdx.x >> 5];
+  for (int j = lane; j < ts; j += 32) wtbl[j] = make_int2(-1, 0);
+  cnt[lane] = 0;
+  cnt[lane + 32] = 0;
+  __syncwarp();
+  for (int j = lane; j < p; j += 32) {
+    const int w = b.pat[off + j];
+    int h = hash32((uint32_t)w) & (ts - 1);
+    for (;;) {
+      const int prev = atomicCAS(&wtbl[h].x, -1, w);
+      if (prev == -1 || prev == w) break;
+      h = (h + 1) & (ts - 1);
+    }
+    atomicAdd(&wtbl[h].y, 1 << 16);
+    if (w >= 2) atomicAdd(&cnt[sig_bit(w)], 1);  // pattern positions per signature bit; unknown words excluded
+  }
+  __syncwarp();
+  int distinct = 0;
+  for (int j0 = 0; j0 < ts; j0 += 32) {
+    const int2 e = j0 + lane < ts ? wtbl[j0 + lane] : make_int2(-1, 0);
+    const unsigned used = __ballot_sync(FULL, e.x != -1);
+    if (e.x != -1) {
+      const int d = distinct + __popc(used & ((1u << lane) - 1));
+      wtbl[j0 + lane].y = e.y | d;
+      if (small) tbl[j0 + lane] = make_int2(e.x, e.y | d);
+    } else if (small && j0 + lane < ts) {
+      tbl[j0 + lane] = e;
+    }
+    distinct += __popc(used);
+  }
+  __syncwarp();
+  const int c_lo = cnt[lane], c_hi = cnt[lane + 32];  // pattern positions per signature bit (lane, lane + 32)
+  // Position masks for the bit-parallel edit distance of patterns of 33..64 tokens (shorter ones compare
+  // against the pattern in registers): peq64[off + d] has bit j set iff pattern[j] is the word with
+  // distinct index d.
+  if (small && p > 32) {
+    unsigned long long* peq = s_peq[threadIdx.x >> 5];
+    peq[lane] = 0;
+    peq[lane + 32] = 0;
     __syncwarp();
     for (int j = lane; j < p; j += 32) {
       const int w = b.pat[off + j];
       int h = hash32((uint32_t)w) & (ts - 1);
-      for (;;) {
-        const int prev = atomicCAS(&wtbl[h].x, -1, w);
-        if (prev == -1 || prev == w) break;
-        h = (h + 1) & (ts - 1);
-      }
-      atomicAdd(&wtbl[h].y, 1 << 16);
+      while (wtbl[h].x != w) h = (h + 1) & (ts - 1);
+      atomicOr(&peq[wtbl[h].y & 0xffff], 1ull << j);
     }
     __syncwarp();
-    int distinct = 0;
-    for (int j0 = 0; j0 < ts; j0 += 32) {
-      const int2 e = j0 + lane < ts ? wtbl[j0 + lane] : make_int2(-1, 0);
-      const unsigned used = __ballot_sync(FULL, e.x != -1);
-      if (e.x != -1) {
-        const int d = distinct + __popc(used & ((1u << lane) - 1));
-        tbl[j0 + lane] = make_int2(e.x, e.y | d);
-        wtbl[j0 + lane].y = e.y | d;
-        if (e.x >= 2) atomicAdd(&cnt[sig_bit(e.x)], e.y >> 16);
-      } else if (j0 + lane < ts) {
-        tbl[j0 + lane] = e;
-      }
-      distinct += __popc(used);
-    }
-    __syncwarp();
-    c_lo = cnt[lane];
-    c_hi = cnt[lane + 32];
-    // Position masks for the bit-parallel edit distance of patterns of 33..64 tokens (shorter ones compare
-    // against the pattern in registers): peq64[off + d] has bit j set iff pattern[j] is the word with
-    // distinct index d.
-    if (p > 32) {
-      unsigned long long* peq = s_peq[threadIdx.x >> 5];
-      peq[lane] = 0;
-      peq[lane + 32] = 0;
-      __syncwarp();
-      for (int j = lane; j < p; j += 32) {
-        const int w = b.pat[off + j];
-        int h = hash32((uint32_t)w) & (ts - 1);
-        while (wtbl[h].x != w) h = (h + 1) & (ts - 1);
-        atomicOr(&peq[wtbl[h].y & 0xffff], 1ull << j);
-      }
-      __syncwarp();
-      for (int d = lane; d < distinct; d += 32) b.peq64[off + d] = peq[d];
-    }
-  } else {
-    for (int j = lane; j < ts; j += 32) tbl[j] = make_int2(-1, 0);
-    __syncwarp();
-    if (lane == 0) {
-      int distinct = 0;
-      for (int j = 0; j < p; j++) {
-        const int w = b.pat[off + j];
-        int h = hash32((uint32_t)w) & (ts - 1);
-        while (tbl[h].x != -1 && tbl[h].x != w) h = (h + 1) & (ts - 1);
-        if (tbl[h].x == -1) tbl[h] = make_int2(w, (distinct++) | (1 << 16));
-        else tbl[h].y += 1 << 16;
-      }
-    }
-    for (int j = 0; j < p; j++) {
-      const int w = b.pat[off + j];
-      if (w < 2) continue;
-      const unsigned bit = sig_bit(w);
-      c_lo += bit == (unsigned)lane;
-      c_hi += bit == (unsigned)(lane + 32);
-    }
+    for (int d = lane; d < distinct; d += 32) b.peq64[off + d] = peq[d];
   }
   // Signature masks in the layout of a walk record (bits 6..63), bit-sliced: plane k holds bit k of
   // min(count, 3), count = pattern positions on that signature bit, and mult = (largest count) - 3 (>= 0):
@@ -241,9 +218,11 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
     int mult = max(max(c_lo, c_hi) - 3, 0);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) mult = max(mult, __shfl_xor_sync(FULL, mult, d));
-    // The same three planes over the 1024 bits of the wide signatures (sentences longer than kWideMin):
-    // lane l owns signature bits [32 l, 32 l + 32), i.e. words 16 l .. 16 l + 15 of the packed counters.
-    int wextra = 0;
+    // The same over the 1024 bits of the wide signatures (sentences longer than kWideMin), exactly: three planes
+    // of min(count, 7) and a short list of the bits that collect more (frequent words of a long pattern), so that
+    //   coverage <= sum over the signature's bits of count(bit)
+    // is evaluated without slack. Lane l owns signature bits [32 l, 32 l + 32), i.e. words 16 l .. 16 l + 15 of
+    // the packed counters.
     if (b.wq) {
       uint32_t* wc = s_wcnt[threadIdx.x >> 5];
       for (int k = lane; k < 512; k += 32) wc[k] = 0;
@@ -256,31 +235,43 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
         }
       }
       __syncwarp();
+      uint32_t* dst = b.wq + (size_t)q * kWideStride;
+      if (lane < 16) dst[3 * kWideWords + lane] = 0;
+      __syncwarp();
       unsigned w0 = 0, w1 = 0, w2 = 0;
-      int mx = 0;
+      int n_big = 0, rest = 0;  // entries written so far (warp-uniform) / excess that found no entry (this lane)
 #pragma unroll
       for (int k = 0; k < 16; k++) {
         const int c = (k + lane) & 15;  // rotated: lanes hit different banks
         const uint32_t v = wc[16 * lane + c];
         const int c0 = (int)(v & 0xffffu), c1 = (int)(v >> 16);
-        mx = max(mx, max(c0, c1));
         const int k0 = min(c0, 7), k1 = min(c1, 7);
         w0 |= (unsigned)((k0 & 1) | ((k1 & 1) << 1)) << (2 * c);
         w1 |= (unsigned)(((k0 >> 1) & 1) | (((k1 >> 1) & 1) << 1)) << (2 * c);
         w2 |= (unsigned)(((k0 >> 2) & 1) | (((k1 >> 2) & 1) << 1)) << (2 * c);
+        if (__any_sync(FULL, max(c0, c1) > 7)) {
+#pragma unroll
+          for (int half = 0; half < 2; half++) {
+            const int cc = half ? c1 : c0;
+            const unsigned bal = __ballot_sync(FULL, cc > 7);
+            if (cc > 7) {
+              const int slot = n_big + __popc(bal & ((1u << lane) - 1));
+              if (slot < kWideBig) dst[3 * kWideWords + slot] = (uint32_t)(32 * lane + 2 * c + half) | ((uint32_t)(cc - 7) << 16);
+              else rest += cc - 7;
+            }
+            n_big += __popc(bal);
+          }
+        }
       }
-      uint32_t* dst = b.wq + (size_t)q * 3 * kWideWords;
       dst[lane] = w0;
       dst[kWideWords + lane] = w1;
       dst[2 * kWideWords + lane] = w2;
-      wextra = max(mx - 7, 0);
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) wextra = max(wextra, __shfl_xor_sync(FULL, wextra, d));
+      rest = __reduce_add_sync(FULL, rest);
+      if (lane == 0) dst[3 * kWideWords + kWideBig] = (uint32_t)rest;
     }
     if (lane == 0) {
       b.qmask[q] = make_int4((int)a_lo, (int)a_hi, (int)a2_lo, (int)a2_hi);
       b.qmeta[q] = make_int4(p, ml, off, kQValid | (mult << 8));
-      if (b.wq) b.wextra[q] = wextra;
     }
   }
 }
@@ -857,27 +848,39 @@ __device__ __forceinline__ int verify_candidates(const IndexDev& ix, const Batch
     const int grp = lane >> 3, sub = lane & 7;
     const unsigned gmask = 0xffu << (8 * grp);
     while (todo) {
-      const unsigned src = __fns(todo, 0, grp + 1);  // this group's candidate: the (grp+1)-th pending one
-      const bool valid = src < 32u;
+      // the next (up to) four pending candidates, one per group of eight lanes
+      unsigned t = todo;
+      int src = -1;
+#pragma unroll
+      for (int g = 0; g < 4; g++) {
+        const int s0 = t ? __ffs(t) - 1 : -1;
+        if (g == grp) src = s0;
+        t &= t - 1;
+      }
+      todo = t;
+      const bool valid = src >= 0;
       int ub = 0, cneed = 0;
       if (valid) {
         const Cand c = cand[src];
         const int cq = c.q_lm & 0xfffff;
         cneed = (int)((unsigned)c.len_need >> 16);
-        const uint4 sg = __ldg(reinterpret_cast<const uint4*>(ix.wsig + (size_t)c.wrow * kWideWords) + sub);
-        const uint4* pl = reinterpret_cast<const uint4*>(b.wq + (size_t)cq * 3 * kWideWords) + sub;
+        const uint32_t* sig = ix.wsig + (size_t)c.wrow * kWideWords;
+        const uint32_t* wq = b.wq + (size_t)cq * kWideStride;
+        const uint4 sg = __ldg(reinterpret_cast<const uint4*>(sig) + sub);
+        const uint4* pl = reinterpret_cast<const uint4*>(wq) + sub;
         const uint4 b0 = __ldg(pl), b1 = __ldg(pl + kWideWords / 4), b2 = __ldg(pl + 2 * (kWideWords / 4));
-        const int extra = __ldg(b.wextra + cq);
+        const uint32_t big = __ldg(wq + 3 * kWideWords + sub);  // (bit | excess << 16) of a bit with more than 7 positions
         ub = __popc(sg.x & b0.x) + __popc(sg.y & b0.y) + __popc(sg.z & b0.z) + __popc(sg.w & b0.w) +
              2 * (__popc(sg.x & b1.x) + __popc(sg.y & b1.y) + __popc(sg.z & b1.z) + __popc(sg.w & b1.w)) +
              4 * (__popc(sg.x & b2.x) + __popc(sg.y & b2.y) + __popc(sg.z & b2.z) + __popc(sg.w & b2.w));
-        if (extra)
-          ub += extra * (__popc(sg.x & b0.x & b1.x & b2.x) + __popc(sg.y & b0.y & b1.y & b2.y) +
-                         __popc(sg.z & b0.z & b1.z & b2.z) + __popc(sg.w & b0.w & b1.w & b2.w));
+        if (big >> 16) {
+          const unsigned bit = big & 0x3ffu;
+          if ((__ldg(sig + (bit >> 5)) >> (bit & 31u)) & 1u) ub += (int)(big >> 16);
+        }
+        if (sub == 0) ub += (int)__ldg(wq + 3 * kWideWords + kWideBig);
       }
       ub = __reduce_add_sync(gmask, ub);
       wide_pass |= __reduce_or_sync(FULL, (valid && sub == 0 && ub >= cneed) ? (1u << src) : 0u);
-      todo &= ~__reduce_or_sync(FULL, valid ? (1u << src) : 0u);  // the (up to) four candidates just handled
     }
   }
   if (have && !wide && p <= 32) {
@@ -2108,9 +2111,10 @@ void launch_search(const IndexDev& ix, const BatchDev& b, const Params&, cudaStr
   const int grid = (b.n_tok + 255) / 256;
   if (grid > 0) fm_search_kernel<<<grid, 256, 0, st>>>(ix, b);
 }
-void launch_gather(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st) {
+void launch_gather(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st, cudaEvent_t between) {
   // grids several times what is resident: CTAs that finish early make room for the next ones
   fm_gather_kernel<<<sm_count * FM_GATHER_CTAS * 8, 256, 0, st>>>(ix, b);
+  if (between) cudaEventRecord(between, st);
   fm_verify_kernel<<<sm_count * 4 * 4, 256, 0, st>>>(ix, b, p);
 }
 void launch_scan(const int32_t* in, int32_t* out, int32_t n, unsigned long long* chain, unsigned int epoch, int sm_count,

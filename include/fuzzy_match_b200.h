@@ -70,6 +70,7 @@ typedef struct fm_profile {
   int32_t retries;  /* workspace regrowths */
   int64_t n_stage2; /* suffix-array elements that passed the signature test of the gather */
   int64_t n_verified; /* exact coverage counts done for them (repeats of a known pair are skipped) */
+  float ms_walk, ms_verify; /* the two kernels of ms_gather: range walk with the signature test / exact coverage */
 } fm_profile;
 
 /* Build the device index for one GPU from a CSR translation memory.

@@ -39,7 +39,17 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sentences", type=int, default=1000000)
     ap.add_argument("--queries", type=int, default=100000)
+    ap.add_argument("--only-config4", action="store_true", help="only the long-pattern configuration (for profiling)")
     args = ap.parse_args()
+    ok = True
+    if not args.only_config4:
+        ok &= short_configs(args)
+    ok &= long_config(args)
+    print("ALL IDENTICAL" if ok else "MISMATCH")
+    sys.exit(0 if ok else 1)
+
+
+def short_configs(args):
     ok = True
     tm, off, V = synth.make_tm(args.sentences, seed=1234)
     q, qo = synth.make_queries(tm, off, args.queries, seed=5678)
@@ -48,7 +58,10 @@ def main():
     ok &= run("config2' CLI defaults f=0.8 n=5 ml=3 mr=0.3", index, oracle, q, qo, 5, 3000, fuzzy=0.8, n=5, ml=3, mr=0.3)
     ok &= run("config3-shape f=0.5 n=1 ml=3", index, oracle, q, qo, 1, 2000, fuzzy=0.5, n=1, ml=3)
     ok &= run("config5 contrastive n=10 c=0.5 idf=1", index, oracle, q, qo, 10, 2000, fuzzy=0.7, n=10, ml=3, idf=1.0, contrast=0.5)
-    del index, oracle
+    return ok
+
+
+def long_config(args):
     # config 4: 980k short + 20k long sentences, queries = perturbed long sentences
     n_long = max(200, args.sentences // 50)
     tm, off, V = synth.make_tm(args.sentences, seed=1234, n_long=n_long)
@@ -56,9 +69,7 @@ def main():
     nq4 = max(100, args.queries // 50)
     q, qo = synth.make_queries(tm, off, nq4, seed=5678, source_ids=src, frac_random=0.2, len_lo=200, len_hi=300)
     index, oracle = fmb.Index(tm, off, V), ob.OracleIndex(tm, off, V)
-    ok &= run("config4 long patterns f=0.7 n=1 ml=3", index, oracle, q, qo, 1, min(nq4, 300), fuzzy=0.7, n=1, ml=3)
-    print("ALL IDENTICAL" if ok else "MISMATCH")
-    sys.exit(0 if ok else 1)
+    return run("config4 long patterns f=0.7 n=1 ml=3", index, oracle, q, qo, 1, min(nq4, 300), fuzzy=0.7, n=1, ml=3)
 
 
 if __name__ == "__main__":

@@ -44,5 +44,28 @@ def full(path):
                                       (rd * scale[units[idx["dram__bytes_read.sum"]]] + wr * scale[units[idx["dram__bytes_write.sum"]]]) / 1e6))
 
 
+def traffic(path):
+    """JSON for profiles/ncu_traffic.json: per kernel DRAM bytes, issue-slot utilisation and warp instructions per launch."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}
+    acc = defaultdict(lambda: defaultdict(list))
+    for r in rows[2:]:
+        k = r[idx["Kernel Name"]].split("(")[0].split("<")[0]
+        rd = float(r[idx["dram__bytes_read.sum"]]) * scale[units[idx["dram__bytes_read.sum"]]]
+        wr = float(r[idx["dram__bytes_write.sum"]]) * scale[units[idx["dram__bytes_write.sum"]]]
+        acc[k]["traffic_bytes_per_launch"].append(rd + wr)
+        acc[k]["issue_active_pct"].append(float(r[idx["smsp__issue_active.avg.pct_of_peak_sustained_active"]]))
+        acc[k]["inst_executed"].append(float(r[idx["smsp__inst_executed.sum"]]))
+        acc[k]["duration_us"].append(float(r[idx["gpu__time_duration.sum"]]) * (1e-3 if units[idx["gpu__time_duration.sum"]] == "ns" else 1.0))
+        acc[k]["l2_hit_pct"].append(float(r[idx["lts__t_sector_hit_rate.pct"]]))
+    res = {k: dict({m: sum(v) / len(v) for m, v in d.items()}, launches_sampled=len(d["inst_executed"])) for k, d in acc.items()}
+    res["_source"] = "ncu --set full --clock-control none (%s): per launch, config 2 (1M sentences, 100k queries/step)" % path
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
