@@ -362,7 +362,10 @@ __device__ __forceinline__ void flush_slices(const BatchDev& b, SliceBuf& sb, in
 // One thread per (query, start position) chain: the n-gram walk of src/fuzzy_match.cc:484-551 with
 // SuffixArray::equal_range (src/suffix_array.cc:105-212) restated as the equal range of the ONE new
 // token at depth k inside the previous range (every suffix there already shares k tokens).
-__global__ void __launch_bounds__(256, 8) fm_search_kernel(IndexDev ix, BatchDev b) {
+#ifndef FM_SEARCH_CTAS
+#define FM_SEARCH_CTAS 6
+#endif
+__global__ void __launch_bounds__(256, FM_SEARCH_CTAS) fm_search_kernel(IndexDev ix, BatchDev b) {
   __shared__ SliceBuf sb;
   int nbuf = 0;
   const int lane = threadIdx.x & 31;
@@ -498,7 +501,64 @@ __global__ void __launch_bounds__(256, 8) fm_search_kernel(IndexDev ix, BatchDev
   }
   if (__any_sync(FULL, nbuf > kSliceBuf - 1)) flush_slices(b, sb, nbuf, lane, q, tag);
   if (live && len >= 2 && len >= ml) push_slice(sb, nbuf, lo, hi - lo, len);
-  flush_slices(b, sb, nbuf, lane, q, tag);
+  // The last flush -- for most chains the only one -- is made by the whole CTA: one pair of atomics on the
+  // global counters per CTA instead of one per warp (same-address atomics serialise in L2).
+  {
+    __shared__ unsigned long long s_wtot[8], s_base;
+    __shared__ unsigned int s_sbase;
+    int elems = 0, n_big = 0;
+    for (int k = 0; k < nbuf; k++) {
+      const int sz = sb.sz[k][threadIdx.x];
+      if (sz > kSmallSlice) { elems += sz; n_big++; }
+    }
+    const unsigned long long mine = ((unsigned long long)(nbuf - n_big) << 54) | ((unsigned long long)n_big << kElemBits) |
+                                    (unsigned long long)(unsigned)elems;
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long o = __shfl_up_sync(FULL, incl, d);
+      if (lane >= d) incl += o;
+    }
+    const int wib = threadIdx.x >> 5;
+    if (lane == 31) s_wtot[wib] = incl;
+    __syncthreads();
+    const unsigned long long low54 = (1ull << 54) - 1;
+    if (threadIdx.x == 0) {
+      unsigned long long tot = 0;
+      for (int k = 0; k < 8; k++) { const unsigned long long v = s_wtot[k]; s_wtot[k] = tot; tot += v; }
+      s_base = (tot & low54) ? atomicAdd(&b.ctr->slice_elem, tot & low54) : 0ull;
+      s_sbase = (tot >> 54) ? atomicAdd(&b.ctr->n_small, (unsigned)(tot >> 54)) : 0u;
+    }
+    __syncthreads();
+    if (nbuf > 0) {
+      const unsigned long long excl = s_wtot[wib] + incl - mine;
+      const unsigned long long big_excl = s_base + (excl & low54);
+      long long slot = (long long)(big_excl >> kElemBits);
+      long long start = (long long)(big_excl & ((1ull << kElemBits) - 1));
+      long long sslot = (long long)s_sbase + (long long)(excl >> 54);
+      if (slot + n_big > b.slice_cap || sslot + (nbuf - n_big) > b.slice_cap) {
+        atomicOr(&b.ctr->overflow, 1u);
+      } else {
+        const int4 planes = __ldg(b.qmask + q);
+        for (int k = 0; k < nbuf; k++) {
+          const int sz = sb.sz[k][threadIdx.x];
+          const int4 rec = make_int4(q, sb.beg[k][threadIdx.x], sb.lm[k][threadIdx.x] | tag, sz);
+          if (sz > kSmallSlice) {
+            b.sl_start[slot] = start;
+            b.sl_rec[2 * slot] = rec;
+            b.sl_rec[2 * slot + 1] = planes;
+            note_spans(b, slot, start, sz);
+            slot++;
+            start += sz;
+          } else {
+            b.sm_rec[2 * sslot] = rec;
+            b.sm_rec[2 * sslot + 1] = planes;
+            sslot++;
+          }
+        }
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------- gather
@@ -1627,6 +1687,66 @@ __device__ int replay_sequence(fm_record* seg, int n, int p, int32_t* idx, unsig
   return __shfl_sync(FULL, nacc, 0);
 }
 
+// The same loop over a list prepared for it: packed[i] = (bits of max(K, C), or +inf for a candidate that
+// no_perfect skips) << 32 | record index, in the reference's candidate order, in shared memory or as one
+// coalesced global array. The bound test of 32 candidates is then one read and one compare per lane -- no
+// dependent record fetch per block (what made long lists slow) -- and only accepted candidates touch their record.
+// packed may alias keys_out / idx_out is written at positions already consumed, as above.
+__device__ __forceinline__ unsigned long long pack_candidate(const fm_record& r, int id, int p, const Params& pr) {
+  float m = fmaxf(r.rowmin_max, r.cost);
+  if (pr.no_perfect && r.cost == 0.f && r.length == p) m = __int_as_float(0x7f800000);  // never passes
+  return ((unsigned long long)__float_as_uint(m) << 32) | (unsigned)id;
+}
+__device__ int replay_sequence_packed(fm_record* seg, int n, const unsigned long long* packed, int32_t* idx_out,
+                                      unsigned long long* keys_out, float* heap, const Params& pr, fm_wire* wire = nullptr,
+                                      int wire_cap = 0, int* wire_n = nullptr) {
+  const int lane = threadIdx.x & 31;
+  int hn = 0, nacc = 0, nwire = 0;
+  if (lane == 0) heap_push(heap, hn, FLT_MAX);
+  float bound = FLT_MAX;
+  unsigned long long nxt = lane < n ? packed[lane] : 0ull;
+  for (int c0 = 0; c0 < n; c0 += 32) {
+    const bool have = c0 + lane < n;
+    const unsigned long long pk = nxt;
+    if (c0 + 32 + lane < n) nxt = packed[c0 + 32 + lane];  // next block in flight while this one is replayed
+    const float m = __uint_as_float((unsigned)(pk >> 32));
+    __syncwarp();
+    int pos = 0;  // candidates before pos are done
+    for (;;) {
+      const bool pass = have && lane >= pos && !(m > bound);
+      const unsigned bal = __ballot_sync(FULL, pass);
+      if (!bal) break;
+      const int t = __ffs(bal) - 1;
+      const int id = (int)__shfl_sync(FULL, (unsigned)pk, t);
+      if (lane == 0) {
+        const fm_record r = seg[id];
+        const float score = score_of(r.cost);
+        heap_push(heap, hn, r.cost);
+        if (score < pr.fuzzy || (pr.buffer > 0 && hn > pr.buffer)) heap_pop(heap, hn);
+        if (wire) {
+          if (nwire < wire_cap) wire[nwire] = to_wire(r);
+          nwire++;
+        } else if (score >= pr.fuzzy) {
+          seg[id].rowmin_max = score;  // slot reused: score
+          seg[id].reserved[1] = 0;     // contrastive accumulator
+          seg[id].reserved[2] = 0;     // contrastive "selected" flag
+          const unsigned u = __float_as_uint(score);
+          const unsigned ord = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+          keys_out[nacc] = ((unsigned long long)(~ord) << 32) | r.s_id;
+          idx_out[nacc] = id;
+          nacc++;
+        }
+        bound = heap[0];
+      }
+      bound = __shfl_sync(FULL, bound, 0);
+      pos = t + 1;
+    }
+    __syncwarp();
+  }
+  if (wire_n && lane == 0) *wire_n = nwire;
+  return __shfl_sync(FULL, nacc, 0);
+}
+
 // Warp-cooperative ascending bitonic sort of 64-bit keys in shared memory (ascending comparators only,
 // so the virtual +inf padding up to the next power of two never moves).
 __device__ void warp_sort_keys(unsigned long long* keys, int n) {
@@ -1744,16 +1864,21 @@ __global__ void __launch_bounds__(256) fm_replay_kernel(fm_record* rec, const in
     }
     __syncwarp();
     warp_sort_keys(sk, n);
-    for (int i = lane; i < n; i += 32) idx[i] = (int)(sk[i] & 0xfffffu);
+    for (int i = lane; i < n; i += 32) {  // in place: sorted key -> (bound-test value, record index)
+      const int id = (int)(sk[i] & 0xfffffu);
+      sk[i] = pack_candidate(seg[id], id, p, pr);
+    }
   }
   __syncwarp();
+  const unsigned long long* packed = n > 32 ? s_keys[threadIdx.x >> 5] : nullptr;
   float* heap = (pr.buffer > 0 && pr.buffer <= 62) ? s_heap[threadIdx.x >> 5] : heapbuf + base + q;
   if (wo.cnt) {  // shard mode: only the accepted records travel; the result order is made after the merge
-    replay_sequence(seg, n, p, idx, keys, heap, pr, wo.stage + base, n, wo.cnt + q);
+    if (packed) replay_sequence_packed(seg, n, packed, idx, keys, heap, pr, wo.stage + base, n, wo.cnt + q);
+    else replay_sequence(seg, n, p, idx, keys, heap, pr, wo.stage + base, n, wo.cnt + q);
     __syncwarp();
     continue;
   }
-  const int nacc = replay_sequence(seg, n, p, idx, keys, heap, pr);
+  const int nacc = packed ? replay_sequence_packed(seg, n, packed, idx, keys, heap, pr) : replay_sequence(seg, n, p, idx, keys, heap, pr);
   if (nacc > 1) {
     if (nacc <= 32) {
       const unsigned long long k = lane < nacc ? keys[lane] : ~0ull;
@@ -1877,7 +2002,7 @@ __device__ unsigned long long* block_radix_sort_keys(unsigned long long* a, unsi
 // One CTA per query with more than kWarpMax scored candidates. The candidate order is sorted as ONE packed
 // 64-bit key per record -- (1023 - match length) << 52 | s_id << 20 | record index -- in shared
 // memory (up to kHeavySmem records, else in global scratch); warp 0 then runs the replay.
-static const int kHeavySmem = 24576;
+static const int kHeavySmem = 4096;  // 32 KB of sort keys per CTA: several CTAs per SM; longer lists are sorted in global memory
 __global__ void __launch_bounds__(256) fm_replay_heavy_kernel(fm_record* rec, const int32_t* __restrict__ q_cnt,
                                                               const int32_t* __restrict__ q_base, float* heapbuf,
                                                               unsigned long long* sort_key, unsigned long long* sort_key2,
@@ -1901,6 +2026,7 @@ __global__ void __launch_bounds__(256) fm_replay_heavy_kernel(fm_record* rec, co
     fm_record* seg = rec + base;
     unsigned long long* gkeys = sort_key + base;
     int32_t* idx = sort_idx + base;
+    const unsigned long long* packed = nullptr;  // the list in replay order when it was sorted as packed keys
     if (n < (1 << 20)) {
       unsigned long long* keys = n <= smem_cap ? s_keys : gkeys;
       for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -1910,7 +2036,12 @@ __global__ void __launch_bounds__(256) fm_replay_heavy_kernel(fm_record* rec, co
       __syncthreads();
       if (n <= smem_cap) block_sort_keys(keys, n);
       else keys = block_radix_sort_keys(gkeys, sort_key2 + base, n, 20, 62, reinterpret_cast<int(*)[256]>(s_keys), s_tot, &s_flag);
-      for (int i = threadIdx.x; i < n; i += blockDim.x) idx[i] = (int)(keys[i] & 0xfffffu);
+      // in place: sorted key -> (bound-test value, record index); every thread fetches the records of its slots
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int id = (int)(keys[i] & 0xfffffu);
+        keys[i] = pack_candidate(seg[id], id, p, pr);
+      }
+      packed = keys;
     } else {
       for (int i = threadIdx.x; i < n; i += blockDim.x) { gkeys[i] = order_key(seg[i]); idx[i] = i; }
       __syncthreads();
@@ -1919,8 +2050,11 @@ __global__ void __launch_bounds__(256) fm_replay_heavy_kernel(fm_record* rec, co
     __syncthreads();
     if (threadIdx.x < 32) {
       float* heap = (pr.buffer > 0 && pr.buffer <= 62) ? s_heap : heapbuf + base + q;
-      const int nacc = wo.cnt ? replay_sequence(seg, n, p, idx, gkeys, heap, pr, wo.stage + base, n, wo.cnt + q)
-                              : replay_sequence(seg, n, p, idx, gkeys, heap, pr);
+      int nacc;
+      if (packed) nacc = wo.cnt ? replay_sequence_packed(seg, n, packed, idx, gkeys, heap, pr, wo.stage + base, n, wo.cnt + q)
+                                : replay_sequence_packed(seg, n, packed, idx, gkeys, heap, pr);
+      else nacc = wo.cnt ? replay_sequence(seg, n, p, idx, gkeys, heap, pr, wo.stage + base, n, wo.cnt + q)
+                         : replay_sequence(seg, n, p, idx, gkeys, heap, pr);
       if (threadIdx.x == 0) s_nacc = nacc;
     }
     __syncthreads();
@@ -2199,7 +2333,7 @@ void launch_replay(const IndexDev& ix, const fm_record* rec, const int32_t* q_cn
     cudaEventRecord(ev_fork, st);
     cudaStreamWaitEvent(st2, ev_fork, 0);
   }
-  fm_replay_heavy_kernel<<<sm_count * 2, 256, smem, sh>>>(const_cast<fm_record*>(rec), q_cnt, q_base, heapbuf, sort_key, sort_key2,
+  fm_replay_heavy_kernel<<<sm_count * 6, 256, smem, sh>>>(const_cast<fm_record*>(rec), q_cnt, q_base, heapbuf, sort_key, sort_key2,
                                                           sort_idx, acc_cnt, heavy_q, q_off, p, (long long)cap, out, out_count, ctr, smem_cap, wo);
   if (st2) cudaEventRecord(ev_join, st2);
   int grid = (n_q + 7) / 8;
