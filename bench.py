@@ -458,27 +458,41 @@ def config3_leg(args, world, rank, dev, torch, dist, capi, fmb):
         sidx = ShardedIndex(tm, off, V, device=dev)
         barrier()
         build_sh = time.time() - t0
-        stream = torch.cuda.Stream(dev)
+        depth = int(os.environ.get("FM_BENCH_DEPTH", "3"))
+        streams = [torch.cuda.Stream(dev) for _ in range(depth)]
         dbat = [(torch.as_tensor(q, device=dev), torch.as_tensor(qo.astype(np.int32), device=dev), len(qo) - 1, int(qo[-1])) for q, qo in batches]
-        d_out = torch.zeros(args.queries * 24, dtype=torch.uint8, device=dev)
-        d_cnt = torch.zeros(args.queries, dtype=torch.int32, device=dev)
-        for i in range(3):
-            dq, dqo, nq, ntok = dbat[i % n_batches]
-            sidx.match_batch_device(dq, dqo, nq, ntok, d_out, d_cnt, 1, params, stream=stream)
+        d_out = [torch.zeros(args.queries * 24, dtype=torch.uint8, device=dev) for _ in range(depth)]
+        d_cnt = [torch.zeros(args.queries, dtype=torch.int32, device=dev) for _ in range(depth)]
+
+        def sharded_loop(n):  # `depth` batches in flight, each on its own stream; every rank in the same order
+            tickets = []
+            for i in range(n):
+                dq, dqo, nq, ntok = dbat[i % n_batches]
+                s = i % depth
+                if len(tickets) >= depth:
+                    sidx.wait(tickets.pop(0))
+                tickets.append(sidx.submit_device(dq, dqo, nq, ntok, d_out[s], d_cnt[s], 1, params, streams[s]))
+            for t in tickets:
+                sidx.wait(t)
+
+        sharded_loop(max(3, depth))
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(stream):
-            e0.record(stream)
-            for i in range(steps):
-                dq, dqo, nq, ntok = dbat[i % n_batches]
-                sidx.match_batch_device(dq, dqo, nq, ntok, d_out, d_cnt, 1, params, stream=stream)
-            e1.record(stream)
+        e0.record(streams[0])
+        for st in streams[1:]:
+            st.wait_event(e0)
+        sharded_loop(steps)
+        for st in streams[1:]:
+            streams[0].wait_stream(st)
+        e1.record(streams[0])
         barrier()
         ms = max_ms(e0.elapsed_time(e1))
+        last = (steps - 1) % depth
         out["tm_sharded"] = {"value": args.queries * steps / (ms / 1e3), "unit": "queries/s", "ms_per_step": ms / steps,
                              "scaling": "strong", "shard_device_bytes": int(sidx.index.device_bytes), "shard_build_s": round(build_sh, 2),
                              "allgather_bytes_per_step": int(sidx.last_gather_bytes),
-                             "found_fraction": float((d_cnt[:dbat[(steps - 1) % n_batches][2]] > 0).float().mean().item()),
+                             "found_fraction": float((d_cnt[last][:dbat[(steps - 1) % n_batches][2]] > 0).float().mean().item()),
+                             "batches_in_flight": depth, "block_capacity_records": int(sidx.block_capacity),
                              "layout": "%d sentence-id shards, queries replicated, local replay per shard, one NCCL all-gather of the "
                                        "locally accepted records per batch, merged replay" % world}
     return out

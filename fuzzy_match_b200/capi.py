@@ -71,7 +71,7 @@ EXPORTS = ["fm_index_create", "fm_index_destroy", "fm_index_save", "fm_index_loa
            "fm_index_max_tokens_in_pattern", "fm_index_device_bytes", "fm_index_kept_sources", "fm_index_sfreq",
            "fm_index_sentence", "fm_index_set_idf_stats", "fm_index_set_real", "fm_match_batch", "fm_match_batch_real", "fm_match_batch_device",
            "fm_match_batch_submit", "fm_match_batch_device_submit", "fm_ticket_wait", "fm_wire_block_bytes", "fm_shard_accept_device",
-           "fm_merge_accepted_device", "fm_comm_unique_id", "fm_comm_create", "fm_comm_destroy", "fm_match_batch_sharded_device",
+           "fm_merge_accepted_device", "fm_comm_unique_id", "fm_comm_create", "fm_comm_destroy", "fm_match_batch_sharded_device", "fm_match_batch_sharded_submit",
            "fm_comm_last_gather_bytes", "fm_comm_block_capacity", "fm_set_profiling", "fm_get_profile", "fm_last_error", "fm_version"]
 
 
@@ -126,6 +126,8 @@ def load_library():
     lib.fm_comm_destroy.restype = None
     lib.fm_match_batch_sharded_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(Params),
                                                   C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.fm_match_batch_sharded_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(Params),
+                                                  C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
     lib.fm_comm_last_gather_bytes.restype = C.c_int64
     lib.fm_comm_last_gather_bytes.argtypes = [C.c_void_p]
     lib.fm_comm_block_capacity.restype = C.c_int64
@@ -309,6 +311,13 @@ class Index:
         _check(self.lib, self.lib.fm_merge_accepted_device(self.h, k, blocks, total_capacity, d_q_off, n_q, C.byref(p), cap, d_out,
                                                            d_out_count, C.byref(need), stream))
         return need.value
+
+    def submit_sharded_device(self, comm, d_q_tokens, d_q_off, n_q, n_tok, d_out, d_out_count, cap, stream, params):
+        """fm_match_batch_sharded_submit: returns a ticket for wait(); collective -- every rank in the same order."""
+        t = C.c_void_p()
+        _check(self.lib, self.lib.fm_match_batch_sharded_submit(self.h, comm, d_q_tokens, d_q_off, n_q, n_tok, C.byref(params), cap, d_out,
+                                                                d_out_count, stream, C.byref(t)))
+        return t
 
     def match_batch_sharded_device(self, comm, d_q_tokens, d_q_off, n_q, n_tok, d_out, d_out_count, cap, stream=0, params=None, **kw):
         p = params if params is not None else Params.make(**kw)

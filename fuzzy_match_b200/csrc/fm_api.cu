@@ -163,7 +163,7 @@ static int ensure_out(Workspace* w, int64_t n_q, int64_t cap) {
 static void free_workspace(Workspace* w) {
   cudaFree(w->d_q_tok); cudaFree(w->d_q_off); cudaFree(w->d_q_real); cudaFree(w->d_q_gap); cudaFree(w->d_itok_dist); cudaFree(w->pat); cudaFree(w->chain_q); cudaFree(w->qmeta); cudaFree(w->tbl); cudaFree(w->cmin_tab); cudaFree(w->span_slice); cudaFree(w->qmask); cudaFree(w->wq); cudaFree(w->peq64); cudaFree(w->cmin64); cudaFree(w->sm_rec);
   cudaFree(w->sl_start); cudaFree(w->sl_rec); cudaFree(w->hkey); cudaFree(w->hlm); cudaFree(w->surv); cudaFree(w->cand); cudaFree(w->surv_len);
-  cudaFree(w->q_cnt); cudaFree(w->q_base); cudaFree(w->acc_cnt); cudaFree(w->rec); cudaFree(w->heapbuf); cudaFree(w->ctr); cudaFree(w->mctr); cudaFree(w->wire_stage); cudaFree(w->scan_chain);
+  cudaFree(w->q_cnt); cudaFree(w->q_base); cudaFree(w->acc_cnt); cudaFree(w->rec); cudaFree(w->heapbuf); cudaFree(w->ctr); cudaFree(w->mctr); cudaFree(w->wire_stage); cudaFree(w->wire_send); cudaFree(w->wire_recv); cudaFree(w->scan_chain);
   cudaFree(w->d_out); cudaFree(w->d_out_count); cudaFree(w->mrec); cudaFree(w->m_cnt); cudaFree(w->m_base); cudaFree(w->m_acc); cudaFree(w->m_heap); cudaFree(w->heavy_q); cudaFree(w->m_heavy); cudaFree(w->mid_q); cudaFree(w->m_mid); cudaFree(w->sort_key); cudaFree(w->sort_key2); cudaFree(w->m_key2); cudaFree(w->sort_idx); cudaFree(w->m_key); cudaFree(w->m_idx);
   if (w->h_ctr) cudaFreeHost(w->h_ctr);
   if (w->h_mctr) cudaFreeHost(w->h_mctr);
@@ -661,7 +661,11 @@ struct fm_ticket {
   HostChunk chunk;
   fm_match* out = nullptr;
   int32_t* out_count = nullptr;
+  fm_comm* comm = nullptr;  // sharded batch (dev holds the job)
+  int64_t capacity = 0;     // record capacity of the blocks of the attempt in flight
+  int attempts = 0;
 };
+static int finish_sharded(fm_ticket* t);
 
 static void drop_ticket(fm_ticket* t) {  // after an error: nothing of the batch may still run on the workspace
   Workspace* w = t->host ? t->chunk.w : t->dev.w;
@@ -726,7 +730,8 @@ int fm_match_batch_submit(fm_index* index, const int32_t* q_tokens, const int64_
 int fm_ticket_wait(fm_ticket* t) {
   if (!t) { set_error("NULL ticket"); return FM_ERR_INVALID; }
   cudaSetDevice(t->ix->device);
-  const int rc = t->host ? finish_host_chunk(t->ix, t->chunk, t->pr, t->cap, t->out, t->out_count) : finish_device(t->ix, t->dev, t->pr);
+  const int rc = t->comm ? finish_sharded(t)
+                 : t->host ? finish_host_chunk(t->ix, t->chunk, t->pr, t->cap, t->out, t->out_count) : finish_device(t->ix, t->dev, t->pr);
   if (rc) { drop_ticket(t); return rc; }
   release(t->ix, t->host ? t->chunk.w : t->dev.w);
   delete t;
@@ -903,9 +908,6 @@ struct fm_comm {
   int rank = 0, world = 1, device = 0;
   double rate = 0.5;  // accepted records per query of the fullest shard (recent batches): sizes the blocks
   int64_t last_capacity = 0;
-  char* d_send = nullptr;
-  char* d_recv = nullptr;
-  int64_t cap_block = 0;
   int64_t last_gather_bytes = 0;
 };
 
@@ -938,75 +940,111 @@ void fm_comm_destroy(fm_comm* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->comm) nccl().CommDestroy(c->comm);
-  cudaFree(c->d_send);
-  cudaFree(c->d_recv);
   delete c;
 }
 int64_t fm_comm_last_gather_bytes(const fm_comm* c) { return c ? c->last_gather_bytes : 0; }
 int64_t fm_comm_block_capacity(const fm_comm* c) { return c ? c->last_capacity : 0; }
 
-int fm_match_batch_sharded_device(fm_index* index, fm_comm* c, const int32_t* d_q_tokens, const int32_t* d_q_off, int64_t n_q,
+}  // extern "C"
+
+// One attempt of a sharded batch on the ticket's stream: shard half -> all-gather -> cross-shard half.
+static int enqueue_sharded(fm_ticket* t) {
+  Index* ix = t->ix;
+  fm_comm* c = t->comm;
+  DeviceJob& j = t->dev;
+  Workspace* w = j.w;
+  int rc;
+  const int64_t capacity = std::max<int64_t>(1024, ((int64_t)(c->rate * 1.25 * (double)j.n_q) + 1023) / 1024 * 1024);
+  const int64_t bytes = wire_block_bytes(j.n_q, capacity);
+  if (bytes > w->cap_wire_block) {
+    cudaFree(w->wire_send); cudaFree(w->wire_recv);
+    w->wire_send = w->wire_recv = nullptr;
+    w->cap_wire_block = 0;
+    const int64_t cb = bytes + bytes / 4;
+    FM_CUDA(cudaMalloc((void**)&w->wire_send, cb));
+    FM_CUDA(cudaMalloc((void**)&w->wire_recv, cb * c->world));
+    w->cap_wire_block = cb;
+  }
+  t->capacity = c->last_capacity = capacity;
+  if ((rc = enqueue_accept(ix, w, j.d_q_tok, j.d_q_off, j.n_q, j.n_tok, t->pr, capacity, w->wire_send, j.st, &j.launches))) return rc;
+  if (ix->profiling) cudaEventRecord(w->ev[6], j.st);
+  const int nr = nccl().AllGather(w->wire_send, w->wire_recv, (size_t)bytes, /*ncclInt8*/ 0, c->comm, j.st);
+  if (nr) return nccl_fail(nr, "ncclAllGather");
+  c->last_gather_bytes = bytes * c->world;
+  const int32_t* blocks[16];
+  for (int k = 0; k < c->world; k++) blocks[k] = reinterpret_cast<const int32_t*>(w->wire_recv + (size_t)k * bytes);
+  if ((rc = enqueue_merge(ix, w, c->world, blocks, capacity * c->world, j.d_q_off, j.n_q, t->pr, j.cap, j.d_out, j.d_out_count, j.st, &j.launches)))
+    return rc;
+  return enqueue_done(w, j.st);
+}
+
+// Every rank takes the same decisions from the same gathered data, so the collectives stay matched: a batch
+// is rerun by all ranks when any shard overflowed its workspace (flag in its block header) or accepted more
+// records than a block holds (its total travels in the header; the next size follows the largest).
+static int finish_sharded(fm_ticket* t) {
+  Index* ix = t->ix;
+  fm_comm* c = t->comm;
+  DeviceJob& j = t->dev;
+  Workspace* w = j.w;
+  int retries = 0, rc;
+  std::lock_guard<std::mutex> coll(ix->shard_mu);
+  for (;;) {
+    const int mine = wait_and_check(w, t->attempts, &retries);  // own overflow: regrown here
+    if (mine < 0) return -mine;
+    const unsigned flags = w->h_mctr->overflow;
+    if (flags & 0x200u) { set_error("ranks disagree on the batch (number of queries)"); return FM_ERR_INVALID; }
+    const double seen = (double)w->h_mctr->wire_need / (double)j.n_q;
+    if (!(flags & 0x100u)) c->rate = std::max(c->rate * 0.98, seen);  // (totals of an overflowed pipeline mean nothing)
+    if (!(flags & (0x100u | 0x400u))) break;
+    if (++t->attempts >= 10) { set_error("sharded batch does not settle (workspace / block size keep growing)"); return FM_ERR_NOMEM; }
+    if ((rc = enqueue_sharded(t))) return rc;
+  }
+  finish_profile(ix, w, j.n_q, j.n_tok, j.launches, retries);
+  return FM_OK;
+}
+
+extern "C" {
+
+int fm_match_batch_sharded_submit(fm_index* index, fm_comm* c, const int32_t* d_q_tokens, const int32_t* d_q_off, int64_t n_q,
                                   int64_t n_query_tokens, const fm_params* params, int64_t cap, fm_match* d_out, int32_t* d_out_count,
-                                  void* stream) {
+                                  void* stream, fm_ticket** ticket) {
   Index* ix = reinterpret_cast<Index*>(index);
   Params pr;
   int rc;
-  if (!ix || !c || n_q < 1 || n_q > (1 << 20) || cap < 1) { set_error("bad argument"); return FM_ERR_INVALID; }
+  if (ticket) *ticket = nullptr;
+  if (!ix || !c || !ticket || n_q < 1 || n_q > (1 << 20) || cap < 1) { set_error("bad argument"); return FM_ERR_INVALID; }
   if (ix->device != c->device) { set_error("index and communicator live on different devices"); return FM_ERR_INVALID; }
   if ((rc = check_params(params, &pr))) return rc;
   if (c->world == 1)  // one shard is the whole TM
-    return fm_match_batch_device(index, d_q_tokens, d_q_off, n_q, n_query_tokens, params, cap, d_out, d_out_count, stream);
+    return fm_match_batch_device_submit(index, d_q_tokens, d_q_off, n_q, n_query_tokens, params, cap, d_out, d_out_count, stream, ticket);
   if (pr.contrast > 0.f) {
     set_error("contrastive rerank needs the sentences of every shard; not supported on a sharded TM");
     return FM_ERR_INVALID;
   }
   FM_CUDA(cudaSetDevice(ix->device));
-  std::lock_guard<std::mutex> coll(ix->shard_mu);  // collectives of one communicator must not interleave
-  Workspace* w = acquire(ix);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  struct Releaser { Index* ix; Workspace* w; cudaStream_t st; ~Releaser() { cudaStreamSynchronize(st); release(ix, w); } } rel{ix, w, st};
-  if ((rc = ensure_base(w)) || (rc = ensure_queries(w, n_q, n_query_tokens, false))) return rc;
-  w->real_active = false;
-  if ((rc = initial_worklists(ix, w, n_q, n_query_tokens))) return rc;
-  int launches = 0, retries = 0;
-  // Every rank takes the same decisions from the same gathered data, so the collectives stay matched: a
-  // batch is rerun by all ranks when any shard overflowed its workspace (flag in its block header) or accepted
-  // more records than a block holds (its total travels in the header; the next size follows the largest).
-  if ((rc = ensure_stage(w))) return rc;
-  for (int attempt = 0;; attempt++) {
-    if (attempt >= 10) { set_error("sharded batch does not settle (workspace / block size keep growing)"); return FM_ERR_NOMEM; }
-    const int64_t capacity = std::max<int64_t>(1024, ((int64_t)(c->rate * 1.25 * (double)n_q) + 1023) / 1024 * 1024);
-    const int64_t bytes = wire_block_bytes(n_q, capacity);
-    if (bytes > c->cap_block) {
-      cudaFree(c->d_send); cudaFree(c->d_recv);
-      c->d_send = c->d_recv = nullptr;
-      c->cap_block = 0;
-      const int64_t cb = bytes + bytes / 4;
-      FM_CUDA(cudaMalloc((void**)&c->d_send, cb));
-      FM_CUDA(cudaMalloc((void**)&c->d_recv, cb * c->world));
-      c->cap_block = cb;
-    }
-    c->last_capacity = capacity;
-    if ((rc = enqueue_accept(ix, w, d_q_tokens, d_q_off, n_q, n_query_tokens, pr, capacity, c->d_send, st, &launches))) return rc;
-    if (ix->profiling) cudaEventRecord(w->ev[6], st);
-    const int nr = nccl().AllGather(c->d_send, c->d_recv, (size_t)bytes, /*ncclInt8*/ 0, c->comm, st);
-    if (nr) return nccl_fail(nr, "ncclAllGather");
-    c->last_gather_bytes = bytes * c->world;
-    const int32_t* blocks[16];
-    for (int k = 0; k < c->world; k++) blocks[k] = reinterpret_cast<const int32_t*>(c->d_recv + (size_t)k * bytes);
-    if ((rc = enqueue_merge(ix, w, c->world, blocks, capacity * c->world, d_q_off, n_q, pr, cap, d_out, d_out_count, st, &launches))) return rc;
-    if ((rc = enqueue_done(w, st))) return rc;
-    // own overflow: regrow (wait_and_check); the gathered flags say whether anybody has to rerun
-    const int mine = wait_and_check(w, attempt, &retries);
-    if (mine < 0) return -mine;
-    const unsigned flags = w->h_mctr->overflow;
-    if (flags & 0x200u) { set_error("ranks disagree on the batch (number of queries)"); return FM_ERR_INVALID; }
-    const double seen = (double)w->h_mctr->wire_need / (double)n_q;
-    if (!(flags & 0x100u)) c->rate = std::max(c->rate * 0.98, seen);  // (totals of an overflowed pipeline mean nothing)
-    if (!(flags & (0x100u | 0x400u))) break;
+  std::lock_guard<std::mutex> coll(ix->shard_mu);  // collectives of one communicator are issued one call at a time
+  fm_ticket* t = new fm_ticket();
+  t->ix = ix; t->pr = pr; t->cap = cap; t->host = false; t->comm = c;
+  DeviceJob& j = t->dev;
+  j.w = acquire(ix);
+  j.d_q_tok = d_q_tokens; j.d_q_off = d_q_off; j.n_q = n_q; j.n_tok = n_query_tokens; j.cap = cap;
+  j.d_out = d_out; j.d_out_count = d_out_count; j.st = static_cast<cudaStream_t>(stream);
+  j.w->real_active = false;
+  if ((rc = ensure_base(j.w)) || (rc = ensure_queries(j.w, n_q, n_query_tokens, false)) || (rc = ensure_stage(j.w)) ||
+      (rc = initial_worklists(ix, j.w, n_q, n_query_tokens)) || (rc = enqueue_sharded(t))) {
+    drop_ticket(t);
+    return rc;
   }
-  finish_profile(ix, w, n_q, n_query_tokens, launches, retries);
+  *ticket = t;
   return FM_OK;
+}
+
+int fm_match_batch_sharded_device(fm_index* index, fm_comm* c, const int32_t* d_q_tokens, const int32_t* d_q_off, int64_t n_q,
+                                  int64_t n_query_tokens, const fm_params* params, int64_t cap, fm_match* d_out, int32_t* d_out_count,
+                                  void* stream) {
+  fm_ticket* t = nullptr;
+  const int rc = fm_match_batch_sharded_submit(index, c, d_q_tokens, d_q_off, n_q, n_query_tokens, params, cap, d_out, d_out_count, stream, &t);
+  return rc ? rc : fm_ticket_wait(t);
 }
 
 int fm_set_profiling(fm_index* index, int enabled) {

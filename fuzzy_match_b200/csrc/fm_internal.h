@@ -238,9 +238,13 @@ struct Workspace {
   unsigned int scan_epoch = 0;
   fm_match* d_out = nullptr;
   int32_t* d_out_count = nullptr;
-  // sharded TM: accepted records of the batch before they are packed (sized like the survivor arrays)
+  // sharded TM: accepted records of the batch before they are packed (sized like the survivor arrays), this
+  // rank's block and the gathered blocks of all ranks
   fm_wire* wire_stage = nullptr;
   bool want_stage = false;
+  char* wire_send = nullptr;
+  char* wire_recv = nullptr;
+  int64_t cap_wire_block = 0;
   // merged-shard buffers
   Counters* mctr = nullptr;    // counters of the merge stage (the shard stage's stay intact for the overflow check)
   Counters* h_mctr = nullptr;  // pinned

@@ -95,6 +95,15 @@ class ShardedIndex:
         self.index.match_batch_sharded_device(self.comm.h, d_q_tok.data_ptr(), d_q_off.data_ptr(), n_q, n_tok, d_out.data_ptr(),
                                               d_out_count.data_ptr(), cap, stream=st.cuda_stream, params=params)
 
+    def submit_device(self, d_q_tok, d_q_off, n_q, n_tok, d_out, d_out_count, cap, params, stream):
+        """Asynchronous form: returns a ticket for wait(); several batches may be in flight, each on its own stream
+        (their kernels and all-gathers overlap). Every rank submits and waits in the same order."""
+        return self.index.submit_sharded_device(self.comm.h, d_q_tok.data_ptr(), d_q_off.data_ptr(), n_q, n_tok, d_out.data_ptr(),
+                                                d_out_count.data_ptr(), cap, stream.cuda_stream, params)
+
+    def wait(self, ticket):
+        self.index.wait(ticket)
+
     def match_batch(self, q_tokens, q_off, cap, **kw):
         """Host CSR in, numpy (matches[n_q, cap], counts[n_q]) out -- convenience for tests."""
         params = capi.Params.make(**kw)

@@ -192,6 +192,12 @@ void fm_comm_destroy(fm_comm* comm);
 int fm_match_batch_sharded_device(fm_index* shard, fm_comm* comm, const int32_t* d_q_tokens, const int32_t* d_q_off,
                                   int64_t n_q, int64_t n_query_tokens, const fm_params* params, int64_t cap,
                                   fm_match* d_out, int32_t* d_out_count, void* stream);
+/* Asynchronous form (see fm_match_batch_device_submit): several batches in flight, each on its own stream, so
+ * that the kernels and the all-gathers of neighbouring batches overlap. Every rank must submit and wait in the
+ * same order. The buffers stay untouched until fm_ticket_wait returns. */
+int fm_match_batch_sharded_submit(fm_index* shard, fm_comm* comm, const int32_t* d_q_tokens, const int32_t* d_q_off,
+                                  int64_t n_q, int64_t n_query_tokens, const fm_params* params, int64_t cap,
+                                  fm_match* d_out, int32_t* d_out_count, void* stream, fm_ticket** ticket);
 /* Bytes received by the last all-gather of this communicator and the record capacity of its blocks. */
 int64_t fm_comm_last_gather_bytes(const fm_comm* comm);
 int64_t fm_comm_block_capacity(const fm_comm* comm);
