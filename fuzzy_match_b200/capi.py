@@ -65,11 +65,14 @@ class Profile(C.Structure):
 
 MATCH_DTYPE = np.dtype([("s_id", np.uint32), ("score", np.float32), ("penalty", np.float32),
                         ("max_subseq", np.int32), ("length", np.int32), ("cost", np.float32)])
+SUBSEQ_DTYPE = np.dtype([("s_id", np.uint32), ("score", np.float32), ("cost", np.float32), ("position", np.int32),
+                         ("length", np.int32), ("found", np.int32)])
 WIRE_DTYPE = np.dtype([("s_id", np.uint32), ("lm_len", np.uint32), ("cost", np.float32), ("rowmin_max", np.float32)])
 
 EXPORTS = ["fm_index_create", "fm_index_destroy", "fm_index_save", "fm_index_load", "fm_index_num_sentences", "fm_index_num_suffixes",
            "fm_index_max_tokens_in_pattern", "fm_index_device_bytes", "fm_index_kept_sources", "fm_index_sfreq",
            "fm_index_sentence", "fm_index_set_idf_stats", "fm_index_set_real", "fm_match_batch", "fm_match_batch_real", "fm_match_batch_device",
+           "fm_subsequence_batch",
            "fm_match_batch_submit", "fm_match_batch_device_submit", "fm_ticket_wait", "fm_wire_block_bytes", "fm_shard_accept_device",
            "fm_merge_accepted_device", "fm_comm_unique_id", "fm_comm_create", "fm_comm_destroy", "fm_match_batch_sharded_device", "fm_match_batch_sharded_submit",
            "fm_comm_last_gather_bytes", "fm_comm_block_capacity", "fm_set_profiling", "fm_get_profile", "fm_last_error", "fm_version"]
@@ -104,6 +107,8 @@ def load_library():
     lib.fm_index_sentence.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32)]
     lib.fm_match_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Params), C.c_int64,
                                    C.c_void_p, C.c_void_p]
+    lib.fm_subsequence_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                         C.c_int32, C.c_void_p]
     lib.fm_index_set_real.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
     lib.fm_match_batch_real.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Params),
                                         C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
@@ -248,6 +253,16 @@ class Index:
         _check(self.lib, self.lib.fm_match_batch(self.h, _ptr(q_tokens), _ptr(q_off), n_q, C.byref(p), cap, _ptr(out),
                                                  _ptr(cnt)))
         return out, cnt
+
+    def subsequence_batch(self, q_tokens, q_off, n=1, no_perfect=False, ml=3, mr=0.3, idf_weighting=False):
+        """fm_subsequence_batch: FuzzyMatch::subsequence per pattern -> records[n_q] of SUBSEQ_DTYPE."""
+        q_tokens = np.ascontiguousarray(q_tokens, dtype=np.int32)
+        q_off = np.ascontiguousarray(q_off, dtype=np.int64)
+        n_q = len(q_off) - 1
+        out = np.zeros(n_q, dtype=SUBSEQ_DTYPE)
+        _check(self.lib, self.lib.fm_subsequence_batch(self.h, _ptr(q_tokens), _ptr(q_off), n_q, int(n), int(no_perfect), int(ml),
+                                                       float(mr), int(idf_weighting), _ptr(out)))
+        return out
 
     def set_real(self, real, gaps, sent_off):
         """fm_index_set_real: real tokens ((form id << 1) | case class) and gap penalty-token ids of the TM."""

@@ -154,6 +154,32 @@ public:
               contrastive_factor, reduce, contrast_buffer, no_perfect);
   }
 
+  // subsequence(sentence, ...): include/fuzzy/fuzzy_match.hh:96-102, src/fuzzy_match.cc:238-365, behind its tokenizer --
+  // the pattern arrives tokenised. Appends at most one Match; Match::id = "<tm id>\t<sub-sequence>" with the tokens
+  // of the sub-sequence joined by blanks (what detokenize gives for pt_none).
+  bool subsequence(const Tokens& pattern, unsigned number_of_matches, bool no_perfect, std::vector<Match>& matches,
+                   int min_subseq_length = 3, float min_subseq_ratio = 0.3f, bool idf_weighting = false) const {
+    if (!_index || _dirty) throw std::logic_error("FuzzyMatch::sort() must be called before subsequence()");
+    std::vector<int32_t> q_tok;
+    for (const auto& w : pattern) {
+      auto it = _form2index.find(w);
+      q_tok.push_back(it == _form2index.end() ? 1 : (int32_t)it->second);
+    }
+    const int64_t q_off[2] = {0, (int64_t)q_tok.size()};
+    fm_subseq r;
+    check(fm_subsequence_batch(_index, q_tok.data(), q_off, 1, (int32_t)number_of_matches, no_perfect, min_subseq_length, min_subseq_ratio,
+                               idf_weighting, &r));
+    if (r.found != 1) return false;
+    const int32_t* toks = nullptr;
+    int32_t len = 0;
+    check(fm_index_sentence(_index, r.s_id, &toks, &len));
+    Match m;  // the reference leaves length / s unset here (best_match is default-constructed, :295)
+    m.score = r.score; m.max_subseq = r.length; m.s_id = r.s_id; m.id = _ids[r.s_id] + "\t";
+    for (int32_t k = 0; k < r.length; k++) m.id += (k ? " " : "") + pattern[(size_t)(r.position + k)];
+    matches.push_back(m);
+    return true;
+  }
+
 private:
   // The reference APPENDS to `matches` and stops at number_of_matches entries in total, so entries that are
   // already there shorten what a call adds (src/fuzzy_match.cc:670-679). Its contrastive rerank also penalises

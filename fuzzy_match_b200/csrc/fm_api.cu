@@ -648,6 +648,47 @@ int fm_index_set_real(fm_index* index, const int32_t* real, const int32_t* gaps,
   return set_real(ix, real, gaps, sent_off, n_sent);
 }
 
+int fm_subsequence_batch(fm_index* index, const int32_t* q_tokens, const int64_t* q_off, int64_t n_q, int32_t number_of_matches,
+                         int32_t no_perfect, int32_t min_subseq_length, float min_subseq_ratio, int32_t idf_weighting, fm_subseq* out) {
+  Index* ix = reinterpret_cast<Index*>(index);
+  if (!ix || n_q < 0 || number_of_matches < 0 || number_of_matches > 4096 || (n_q > 0 && (!q_off || !out))) {
+    set_error("bad argument (number_of_matches 0..4096)");
+    return FM_ERR_INVALID;
+  }
+  if (n_q == 0) return FM_OK;
+  const int64_t ntok = q_off[n_q] - q_off[0];
+  if (n_q > (1 << 20) || ntok < 0 || ntok > (int64_t(1) << 28)) { set_error("batch too large: split it"); return FM_ERR_INVALID; }
+  for (int64_t i = 0; i < n_q; i++)
+    if (q_off[i + 1] < q_off[i] || q_off[i + 1] - q_off[i] > ix->max_tokens) {
+      // the reference has no cap here (only match() ignores such patterns); the kernel's staging buffers do
+      set_error("subsequence: pattern longer than max_tokens_in_pattern (or q_off not ascending)");
+      return FM_ERR_INVALID;
+    }
+  FM_CUDA(cudaSetDevice(ix->device));
+  Workspace* w = acquire(ix);
+  struct Releaser { Index* ix; Workspace* w; ~Releaser() { if (w->stream) cudaStreamSynchronize(w->stream); release(ix, w); } } rel{ix, w};
+  int rc;
+  if ((rc = ensure_base(w)) || (rc = ensure_queries(w, n_q, ntok, true))) return rc;
+  cudaStream_t st = w->stream;
+  const int seen_cap = number_of_matches + 64;  // candidates + sentences skipped as perfect
+  uint32_t* d_seen = nullptr;
+  fm_subseq* d_out = nullptr;
+  FM_CUDA(cudaMalloc((void**)&d_seen, (size_t)n_q * seen_cap * sizeof(uint32_t)));
+  if (cudaMalloc((void**)&d_out, (size_t)n_q * sizeof(fm_subseq)) != cudaSuccess) { cudaFree(d_seen); set_error("out of device memory"); return FM_ERR_NOMEM; }
+  struct Freer { void* a; void* b; ~Freer() { cudaFree(a); cudaFree(b); } } fr{d_seen, d_out};
+  if (ntok) FM_CUDA(cudaMemcpyAsync(w->d_q_tok, q_tokens + q_off[0], ntok * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  for (int64_t i = 0; i <= n_q; i++) w->h_q_off32[i] = (int32_t)(q_off[i] - q_off[0]);
+  FM_CUDA(cudaMemcpyAsync(w->d_q_off, w->h_q_off32, (n_q + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  launch_subseq(ix->dev, w->d_q_tok, w->d_q_off, (int32_t)n_q, number_of_matches, no_perfect != 0, min_subseq_length, min_subseq_ratio,
+                idf_weighting != 0, d_seen, seen_cap, d_out, st);
+  FM_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n_q * sizeof(fm_subseq), cudaMemcpyDeviceToHost, st));
+  FM_CUDA(cudaStreamSynchronize(st));
+  FM_CUDA(cudaGetLastError());
+  for (int64_t i = 0; i < n_q; i++)
+    if (out[i].found < 0) { set_error("more than 64 perfect matches skipped for one pattern (no_perfect)"); return FM_ERR_NOMEM; }
+  return FM_OK;
+}
+
 // ---- submit / wait: the asynchronous form of the two batch calls. A ticket owns one workspace; several
 // tickets may be in flight on one index, so the host->device copy of batch i+1 and the device->host copy
 // of batch i-1 overlap the kernels of batch i (the reference overlaps I/O and matching the same way with

@@ -322,6 +322,8 @@ void launch_replay(const IndexDev& ix, const fm_record* rec, const int32_t* q_cn
 void launch_contrast(const IndexDev& ix, fm_record* rec, const int32_t* q_base, const int32_t* sort_idx,
                      const int32_t* acc_cnt, int32_t n_q, const Params& p, int64_t cap, fm_match* out, int32_t* out_count,
                      Counters* ctr, int sm_count, cudaStream_t st);
+void launch_subseq(const IndexDev& ix, const int32_t* q_tok, const int32_t* q_off, int32_t n_q, int n_matches, int no_perfect, int ml, float mr,
+                   int idf_weighting, uint32_t* seen, int seen_cap, fm_subseq* out, cudaStream_t st);
 // wire blocks (one shard's accepted records of a batch; layout in fm_kernels.cu / include/fuzzy_match_b200.h)
 inline long long wire_off_words_host(long long n_q) { return (n_q + 1 + 3) / 4 * 4; }
 inline long long wire_block_bytes(long long n_q, long long capacity) { return 4 * (4 + wire_off_words_host(n_q)) + (long long)sizeof(fm_wire) * capacity; }

@@ -2153,6 +2153,203 @@ __global__ void __launch_bounds__(256) fm_contrast_kernel(IndexDev ix, fm_record
   }
 }
 
+// ---------------------------------------------------------------- subsequence()
+//
+// FuzzyMatch::subsequence (reference src/fuzzy_match.cc:238-365) behind its tokenizer, one warp per pattern:
+// the sub-sequences of the pattern are tried by weight (length, or summed IDF) until one occurs in a sentence
+// that is not skipped as perfect; the suffix-array range of that sub-sequence is walked in order for at most
+// number_of_matches distinct sentences, each scored with the full edit distance (unit costs), and the best
+// under the reference's integer-truncated running bound is returned. Nothing here is throughput critical
+// (a handful of dependent lookups and one or two edit distances per pattern); the batch gives the parallelism.
+
+// suffixes that start with the bigram / extend a bigram slot by one word (the directories of the search kernel)
+__device__ __forceinline__ bool dir_bigram(const IndexDev& ix, int t0, int t1, int& lo, int& hi, uint32_t& slot) {
+  if (t0 < 2 || t1 < 2) return false;
+  uint32_t h = bigram_hash(t0, t1) & ix.bg_mask;
+  for (;;) {
+    const int4 e = __ldg(ix.bg_tab + h);
+    if (e.x == t0 && e.y == t1) { lo = e.z; hi = e.w; slot = h; return true; }
+    if (e.x == -1) return false;
+    h = (h + 1) & ix.bg_mask;
+  }
+}
+__device__ __forceinline__ bool dir_trigram(const IndexDev& ix, uint32_t bslot, int t2, int& lo, int& hi) {
+  if (t2 < 2) return false;
+  uint32_t h = bigram_hash((int)bslot, t2) & ix.tg_mask;
+  for (;;) {
+    const int4 e = __ldg(ix.tg_tab + h);
+    if (e.x == (int)bslot && e.y == t2) { lo = e.z; hi = e.w < 0 ? e.z + 1 : e.w; return true; }
+    if (e.x == -1) return false;
+    h = (h + 1) & ix.tg_mask;
+  }
+}
+// equal range of word t at depth `depth` inside [lo, hi) (all suffixes there share `depth` words)
+__device__ __forceinline__ void narrow_range(const IndexDev& ix, int depth, int t, int& lo, int& hi) {
+  if (t < 2) { hi = lo; return; }
+  auto key = [&](int k) { return depth == 3 ? __ldg(ix.sa_next + k) : __ldg(ix.tok + (__ldg(ix.sa_pos + k) + depth)); };
+  int a = lo, e = hi;
+  while (a < e) {  // first suffix whose word is not < t
+    const int m = (int)(((unsigned)a + (unsigned)e) >> 1);
+    if (key(m) < t) a = m + 1; else e = m;
+  }
+  const int first = a;
+  e = hi;
+  while (a < e) {  // first suffix whose word is > t
+    const int m = (int)(((unsigned)a + (unsigned)e) >> 1);
+    if (key(m) <= t) a = m + 1; else e = m;
+  }
+  lo = first;
+  hi = a;
+}
+// SuffixArray::equal_range of pat[0..len) (src/suffix_array.cc:105-212); returns false when no suffix starts with it
+__device__ bool ngram_range(const IndexDev& ix, const int32_t* pat, int len, int& lo, int& hi) {
+  const int t0 = pat[0];
+  if (t0 < 2 || t0 >= ix.vocab_size) return false;
+  if (len == 1) { lo = __ldg(ix.qva + t0); hi = __ldg(ix.qva + t0 + 1); return hi > lo; }
+  uint32_t slot = 0;
+  if (!dir_bigram(ix, t0, pat[1], lo, hi, slot)) return false;
+  if (len >= 3 && !dir_trigram(ix, slot, pat[2], lo, hi)) return false;
+  for (int d = 3; d < len; d++) {
+    narrow_range(ix, d, pat[d], lo, hi);
+    if (hi <= lo) return false;
+  }
+  return true;
+}
+// longest prefix of pat[0..n) that occurs in the TM
+__device__ int longest_prefix(const IndexDev& ix, const int32_t* pat, int n) {
+  int lo = 0, hi = 0;
+  if (n < 1 || !ngram_range(ix, pat, 1, lo, hi)) return 0;
+  if (n < 2) return 1;
+  uint32_t slot = 0;
+  if (!dir_bigram(ix, pat[0], pat[1], lo, hi, slot)) return 1;
+  if (n < 3 || !dir_trigram(ix, slot, pat[2], lo, hi)) return 2;
+  int len = 3;
+  while (len < n) {
+    narrow_range(ix, len, pat[len], lo, hi);
+    if (hi <= lo) break;
+    len++;
+  }
+  return len;
+}
+
+struct SubseqKey {  // priority of a sub-sequence: weight desc, position asc (Subseq::operator<, :238-248), then length desc
+  float w;
+  int pos, len;
+};
+__device__ __forceinline__ bool subseq_before(const SubseqKey& a, const SubseqKey& b) {  // a is tried before b
+  if (a.w != b.w) return a.w > b.w;
+  if (a.pos != b.pos) return a.pos < b.pos;
+  return a.len > b.len;
+}
+
+__global__ void __launch_bounds__(128) fm_subseq_kernel(IndexDev ix, const int32_t* __restrict__ q_tok, const int32_t* __restrict__ q_off,
+                                                        int n_q, int n_matches, int no_perfect, int ml_in, float mr, int idf_weighting,
+                                                        int stride, uint32_t* seen_buf, int seen_cap, fm_subseq* out) {
+  extern __shared__ int smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  int32_t* s_sent = smem + wib * 5 * stride;
+  int32_t* s_pat = s_sent + stride;
+  float* s_pen = reinterpret_cast<float*>(s_pat + stride);
+  float* s_up = s_pen + stride;
+  int32_t* s_lmax = reinterpret_cast<int32_t*>(s_up + stride);
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= n_q) return;
+  fm_subseq res;
+  res.s_id = 0; res.score = 0.f; res.cost = 0.f; res.position = 0; res.length = 0; res.found = 0;
+  const int off = q_off[q], p = q_off[q + 1] - off;
+  int ml = ml_in;
+  if ((int)__fmul_rn(mr, (float)p) > ml) ml = (int)__fmul_rn(mr, (float)p);  // :263-264
+  if (p < ml || p < 1 || p > ix.max_tokens) {  // :266-267 (patterns beyond max_tokens_in_pattern are not searched)
+    if (lane == 0) out[q] = res;
+    return;
+  }
+  // words the TM does not know are VOCAB_UNK: no sub-sequence runs over them (:281-283)
+  for (int j = lane; j < p; j += 32) {
+    const int t = q_tok[off + j];
+    const bool known = t >= 2 && t < ix.vocab_size && __ldg(ix.qva + t + 1) > __ldg(ix.qva + t);
+    s_pat[j] = known ? t : 1;
+    s_pen[j] = 0.f;  // the edit distance runs with idf_weight 0 (:321-326)
+  }
+  __syncwarp();
+  for (int it = lane; it < p; it += 32) s_lmax[it] = longest_prefix(ix, s_pat + it, p - it);
+  __syncwarp();
+  uint32_t* seen = seen_buf + (size_t)q * seen_cap;  // candidates first, then the perfect sentences
+  int n_cand = 0, n_perfect = 0;
+  int max_distance = 10000;
+  SubseqKey prev;
+  prev.w = __int_as_float(0x7f800000); prev.pos = -1; prev.len = 0;  // before everything
+  while (max_distance == 10000) {
+    // the next sub-sequence in priority order among those that occur in the TM (the others have empty ranges)
+    SubseqKey best;
+    best.w = -1.f; best.pos = 0; best.len = 0;
+    for (int it = lane; it < p; it += 32) {
+      float w = 0.f;
+      const int lm = s_lmax[it];
+      for (int len = 1; len <= lm; len++) {
+        w = idf_weighting ? __fadd_rn(w, __ldg(ix.idf + s_pat[it + len - 1])) : __fadd_rn(w, 1.f);
+        if (len < ml) continue;
+        SubseqKey k;
+        k.w = w; k.pos = it; k.len = len;
+        if (subseq_before(prev, k) && (best.len == 0 || subseq_before(k, best))) best = k;
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      SubseqKey o;
+      o.w = __shfl_xor_sync(FULL, best.w, d); o.pos = __shfl_xor_sync(FULL, best.pos, d); o.len = __shfl_xor_sync(FULL, best.len, d);
+      if (o.len != 0 && (best.len == 0 || subseq_before(o, best))) best = o;
+    }
+    if (best.len == 0) break;  // nothing left
+    prev = best;
+    int lo = 0, hi = 0;
+    if (lane == 0) ngram_range(ix, s_pat + best.pos, best.len, lo, hi);
+    lo = __shfl_sync(FULL, lo, 0);
+    hi = __shfl_sync(FULL, hi, 0);
+    for (int su = lo; su < hi && n_cand < n_matches; su++) {  // :308-309
+      const int start = __ldg(ix.sa_start + su);
+      const uint32_t sid = (uint32_t)__ldg(ix.sid_at + (start >> 2));
+      bool dup = false;
+      for (int i = lane; i < n_cand + n_perfect; i += 32) dup |= seen[i < n_cand ? i : n_matches + (i - n_cand)] == sid;
+      if (__any_sync(FULL, dup)) continue;
+      int slen = 0;
+      for (int k0 = 0;; k0 += 32) {  // stage the sentence (it ends at the separator)
+        const int t = __ldg(ix.tok + start + k0 + lane);
+        const unsigned z = __ballot_sync(FULL, t == 0);
+        s_sent[k0 + lane] = t;
+        if (z) { slen = k0 + __ffs(z) - 1; break; }
+      }
+      __syncwarp();
+      Params unit;
+      unit.ins = unit.del = unit.rep = 1.f;
+      const float wdiff = __fdiv_rn(100.f, normalizer(p, slen, unit));  // Costs(p, s, EditCosts()) :317-318
+      float C, K;
+      warp_edit_distance<false>(s_sent, slen, s_pat, p, s_pen, s_up, __fmul_rn(1.f, wdiff), __fmul_rn(1.f, wdiff), __fmul_rn(1.f, wdiff), C,
+                                K, RealSide{});
+      if (C == 0.f && no_perfect) {  // :327-330
+        if (n_matches + n_perfect >= seen_cap) { res.found = -1; max_distance = -1; break; }
+        if (lane == 0) seen[n_matches + n_perfect] = sid;
+        n_perfect++;
+        __syncwarp();
+        continue;
+      }
+      if (C < (float)max_distance) {  // :331-350
+        res.found = 1;
+        res.score = score_of(C);
+        res.cost = C;
+        res.length = best.len;
+        res.position = best.pos;
+        res.s_id = sid + ix.sid_base;
+        max_distance = (int)C;  // int max_distance = cost
+        if (C == 0.f) break;
+      }
+      if (lane == 0) seen[n_cand] = sid;
+      n_cand++;
+      __syncwarp();
+    }
+  }
+  if (lane == 0) out[q] = res;
+}
+
 // ---------------------------------------------------------------- cross-shard merge helpers
 //
 // One shard's block for n_q queries with room for `capacity` records (what travels in the all-gather):
@@ -2354,6 +2551,14 @@ void launch_contrast(const IndexDev& ix, fm_record* rec, const int32_t* q_base, 
   fm_contrast_kernel<<<grid, 256, smem, st>>>(ix, rec, q_base, sort_idx, acc_cnt, n_q, p, (long long)cap, out, out_count, ctr, stride);
 }
 
+void launch_subseq(const IndexDev& ix, const int32_t* q_tok, const int32_t* q_off, int32_t n_q, int n_matches, int no_perfect, int ml, float mr,
+                   int idf_weighting, uint32_t* seen, int seen_cap, fm_subseq* out, cudaStream_t st) {
+  const int stride = dp_stride(ix);
+  const size_t smem = (size_t)4 * 5 * stride * sizeof(int);
+  static SmemOptIn opt;
+  opt.ensure(fm_subseq_kernel, 200 * 1024);
+  fm_subseq_kernel<<<(n_q + 3) / 4, 128, smem, st>>>(ix, q_tok, q_off, n_q, n_matches, no_perfect, ml, mr, idf_weighting, stride, seen, seen_cap, out);
+}
 void launch_wire_pack(int32_t* block, const Counters* ctr, const fm_wire* stage, const int32_t* q_base, int32_t n_q, int capacity,
                       cudaStream_t st) {
   fm_wire_pack_kernel<<<(n_q + 255) / 256, 256, 0, st>>>(block, ctr, stage, q_base, n_q, capacity);

@@ -3,14 +3,14 @@
 // Replaces SuffixArray::sort (reference src/suffix_array.cc:58-102: bucket by first word, std::sort of
 // every bucket with a token-wise comparator, :214-251) by prefix doubling on the device: ranks of the
 // first h tokens of every suffix are combined pairwise, rank_2h(i) = order of (rank_h(i), rank_h(i+h)),
-// each round one hand-written LSD radix sort of 64-bit keys. The zero separator has rank 0, so a
-// suffix that ends sorts before every longer suffix with the same prefix -- exactly the reference's
-// order; suffixes with identical content are tied there too (the reference breaks the tie by
-// sentence id, which match() cannot observe: ranges are sets).
+// each round one hand-written LSD radix sort of 64-bit keys. The separator behind sentence s has the rank s,
+// below every word: a suffix that ends sorts before every longer suffix with the same prefix, and suffixes
+// with identical content are ordered by sentence id -- exactly the reference's comparator (shorter first,
+// ties by sentence id). match() cannot observe the order inside a range, subsequence() can: it walks ranges
+// in this order and stops after number_of_matches candidates (src/fuzzy_match.cc:308-309).
 //
-// A suffix shorter than h reads rank_h(i+h) from beyond its separator. That value only ever compares
-// suffixes whose first h tokens INCLUDING the separator are equal, i.e. identical suffixes, so it can
-// only permute true ties.
+// Separators are unique, so every suffix is a unique string up to and including its separator: what
+// rank_h(i+h) reads from beyond a separator never decides a comparison.
 #include <algorithm>
 #include <vector>
 
@@ -89,8 +89,9 @@ __global__ void fm_sa_init_kernel(const int32_t* __restrict__ tok, const int32_t
   const int st = sent_start[s], len = coff[s + 1] - coff[s], c0 = coff[s];
   for (int j = lane; j < len; j += 32) {
     sa[c0 + j] = (uint32_t)(st + j);
-    rank[st + j] = tok[st + j];
+    rank[st + j] = n_sent + tok[st + j];
   }
+  if (lane == 0) rank[st + len] = s;  // the separator: below every word, sentences in order
 }
 __global__ void fm_sa_keys_kernel(const uint32_t* __restrict__ sa, const int32_t* __restrict__ rank, long long n, int h,
                                   unsigned long long* keys) {
@@ -105,10 +106,10 @@ __global__ void fm_sa_heads_kernel(const unsigned long long* __restrict__ keys, 
   head[k] = (k == 0 || keys[k] != keys[k - 1]) ? 1 : 0;
 }
 __global__ void fm_sa_rank_kernel(const uint32_t* __restrict__ sa, const int32_t* __restrict__ head,
-                                  const int32_t* __restrict__ excl, long long n, int32_t* rank) {
+                                  const int32_t* __restrict__ excl, long long n, int n_sent, int32_t* rank) {
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  rank[sa[k]] = excl[k] + head[k];  // 1-based group index; 0 stays the separator's rank
+  rank[sa[k]] = n_sent + excl[k] + head[k];  // group index above the separators' ranks 0 .. n_sent-1
 }
 
 static int bits_for(unsigned long long v) {
@@ -158,8 +159,8 @@ int gpu_suffix_sort(const int32_t* d_tok, int64_t n_buf, const std::vector<int32
   SORT_CUDA(cudaMemcpy(d_coff, compact_off.data(), (size_t)(n_sent + 1) * 4, cudaMemcpyHostToDevice));
   fm_sa_init_kernel<<<(n_sent + 7) / 8, 256>>>(d_tok, d_start, d_coff, n_sent, d_va, d_rank);
   {
-    unsigned long long max_rank = (unsigned long long)std::max<int64_t>(vocab_size, 2);
-    for (int h = 1; h < std::max(max_len, 2); h <<= 1) {
+    unsigned long long max_rank = (unsigned long long)n_sent + (unsigned long long)std::max<int64_t>(vocab_size, 2);
+    for (int h = 1; h < std::max(max_len + 1, 2); h <<= 1) {  // until the ranks cover the longest sentence and its separator
       fm_sa_keys_kernel<<<gs, tb>>>(d_va, d_rank, n_suf, h, d_ka);
       // LSD passes over the bits that can differ: low word (rank at i+h) then high word (rank at i)
       const int nb = bits_for(max_rank);
@@ -174,8 +175,8 @@ int gpu_suffix_sort(const int32_t* d_tok, int64_t n_buf, const std::vector<int32
         }
       fm_sa_heads_kernel<<<gs, tb>>>(d_ka, n_suf, d_head);
       launch_scan(d_head, d_excl, (int32_t)n_suf, d_chain, ++epoch, sm_count, 0);
-      fm_sa_rank_kernel<<<gs, tb>>>(d_va, d_head, d_excl, n_suf, d_rank);
-      max_rank = (unsigned long long)n_suf + 1;
+      fm_sa_rank_kernel<<<gs, tb>>>(d_va, d_head, d_excl, n_suf, n_sent, d_rank);
+      max_rank = (unsigned long long)n_sent + (unsigned long long)n_suf + 1;
     }
   }
   SORT_CUDA(cudaMemcpy(d_sa, d_va, (size_t)n_suf * 4, cudaMemcpyDeviceToDevice));

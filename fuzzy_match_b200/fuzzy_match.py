@@ -2,7 +2,8 @@
 
 Same names, argument meaning, defaults and error behaviour as include/fuzzy/fuzzy_match.hh:17-119
 (add_tm(id, Tokens, sort) :52, sort() :57, match(Tokens, fuzzy, N, matches, ml=2, mr=0, idf=0,
-EditCosts(), contrast=0, reduce=MEAN, buffer=-1) :59-69, max_tokens_in_pattern() :119), so the
+EditCosts(), contrast=0, reduce=MEAN, buffer=-1) :59-69, subsequence(pattern, N, no_perfect, matches,
+ml=3, mr=0.3, idf_weighting=False) :96-102 behind its tokenizer, max_tokens_in_pattern() :119), so the
 reference's own Tokens-API tests read the same against this class. The vocabulary (string -> id,
 reference src/vocab_indexer.cc) stays on the host; everything match() computes runs on the GPU
 through the C ABI. The tokenizer front-end (match(std::string)) is out of scope.
@@ -120,3 +121,32 @@ class FuzzyMatch:
                                  s_id=sid, id=self._ids[sid], length=int(m["length"]),
                                  s=np.asarray(self._sentences[sid], dtype=np.int32)))
         return [len(m) > 0 for m in matches_out]
+
+    def subsequence(self, pattern, number_of_matches, no_perfect, matches, min_subseq_length=3, min_subseq_ratio=0.3,
+                    idf_weighting=False):
+        """subsequence() for a tokenised pattern: appends at most one Match (fuzzy_match.cc:360-363) whose id is
+        "<tm id>\t<the sub-sequence, tokens joined by blanks>" and returns whether one was found."""
+        return self.subsequence_batch([pattern], number_of_matches, no_perfect, [matches], min_subseq_length, min_subseq_ratio,
+                                      idf_weighting)[0]
+
+    def subsequence_batch(self, patterns, number_of_matches, no_perfect, matches_out, min_subseq_length=3, min_subseq_ratio=0.3,
+                          idf_weighting=False):
+        if self._index is None:
+            self.sort()
+        wids = [self._wids(p) for p in patterns]
+        q_off = np.zeros(len(wids) + 1, dtype=np.int64)
+        if wids:
+            np.cumsum([len(w) for w in wids], out=q_off[1:])
+        q_tok = np.fromiter((t for w in wids for t in w), dtype=np.int32, count=int(q_off[-1]))
+        rec = self._index.subsequence_batch(q_tok, q_off, n=number_of_matches, no_perfect=no_perfect, ml=min_subseq_length,
+                                            mr=min_subseq_ratio, idf_weighting=idf_weighting)
+        found = []
+        for q, dst in enumerate(matches_out):
+            r = rec[q]
+            found.append(bool(r["found"]))
+            if r["found"]:
+                sid, pos, n = int(r["s_id"]), int(r["position"]), int(r["length"])
+                dst.append(Match(score=float(r["score"]), penalty=0.0, max_subseq=n, s_id=sid,
+                                 id=self._ids[sid] + "\t" + " ".join(list(patterns[q])[pos:pos + n]), length=0,
+                                 s=np.asarray(self._sentences[sid], dtype=np.int32)))
+        return found

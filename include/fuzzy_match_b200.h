@@ -118,6 +118,25 @@ int fm_match_batch_real(fm_index* index, const int32_t* q_tokens, const int32_t*
 int fm_match_batch(fm_index* index, const int32_t* q_tokens, const int64_t* q_off, int64_t n_q,
                    const fm_params* params, int64_t cap, fm_match* out, int32_t* out_count);
 
+/* FuzzyMatch::subsequence (fuzzy_match.hh:96-102, src/fuzzy_match.cc:238-365) behind its tokenizer, for a batch of
+ * patterns (host CSR): the sub-sequences of a pattern are tried by weight -- length, or summed IDF with idf_weighting --
+ * until one occurs in a sentence that no_perfect does not skip; among the first number_of_matches sentences of its
+ * suffix-array range the one the reference keeps is returned. The text the reference appends to Match::id (the
+ * detokenised sub-sequence) is described by (position, length): the caller owns the token strings. The walk order
+ * inside a range follows the word ids, so ids must be assigned in first-seen order like VocabIndexer::addWords
+ * (src/vocab_indexer.cc:37-50) for the reference's choice among equally good sentences. */
+typedef struct fm_subseq {
+  uint32_t s_id;
+  float score;
+  float cost;
+  int32_t position; /* first pattern token of the sub-sequence that located the match */
+  int32_t length;   /* its length = Match::max_subseq */
+  int32_t found;    /* 1 = match, 0 = none */
+} fm_subseq;
+int fm_subsequence_batch(fm_index* index, const int32_t* q_tokens, const int64_t* q_off, int64_t n_q, int32_t number_of_matches,
+                         int32_t no_perfect, int32_t min_subseq_length, float min_subseq_ratio, int32_t idf_weighting,
+                         fm_subseq* out);
+
 /* Same with device-resident buffers; q_off is int32 here ([n_q+1], device). The batch is enqueued on
  * `stream` (a cudaStream_t) and the call returns once that stream has finished it (the worklist
  * overflow counters are read back; a batch that outgrew the workspace is rerun after regrowing it):

@@ -161,11 +161,25 @@ class OracleIndex:
                                      _ptr(out), _ptr(dbg), C.c_int64(dbg_cap), C.byref(dbg_n))
         return out[:min(n, cap)].copy(), dbg[:dbg_n.value].copy()
 
+    def subsequence_batch(self, q_tokens, q_off, n=1, no_perfect=False, ml=3, mr=0.3, idf_weighting=False):
+        """fmo_subsequence_batch: FuzzyMatch::subsequence per pattern -> structured array (found, s_id, score, cost, position, length)."""
+        q_tokens, q_off = _csr(q_tokens, q_off)
+        n_q = len(q_off) - 1
+        out = np.zeros(n_q, dtype=SUBSEQ_DTYPE)
+        self.lib.fmo_subsequence_batch(self.h, _ptr(q_tokens), _ptr(q_off), C.c_int64(n_q), C.c_int32(n), C.c_int32(int(no_perfect)),
+                                       C.c_int32(ml), C.c_float(mr), C.c_int32(int(idf_weighting)), _ptr(out))
+        return out
+
     def equal_range(self, ngram):
         ngram = np.ascontiguousarray(ngram, dtype=np.int32)
         lo, hi = C.c_int64(0), C.c_int64(0)
         self.lib.fmo_equal_range(self.h, _ptr(ngram), C.c_int64(len(ngram)), C.byref(lo), C.byref(hi))
         return lo.value, hi.value
+
+
+SUBSEQ_DTYPE = np.dtype([("s_id", np.uint32), ("score", np.float32), ("cost", np.float32), ("position", np.int32), ("length", np.int32),
+                         ("found", np.int32)])
+REF_SUBSEQ_DTYPE = np.dtype([("s_id", np.uint32), ("score", np.float32), ("max_subseq", np.int32), ("found", np.int32)])
 
 
 def _scrub_uninitialised_penalty(res):
@@ -215,6 +229,19 @@ class RefIndex:
                                                             C.c_int64(n_q), C.byref(p), C.c_int(int(no_perfect)), C.c_int(nthreads),
                                                             C.c_int64(cap), _ptr(out), _ptr(cnt), _ptr(self._itok[0]), _ptr(self._itok[1]))
         return _scrub_uninitialised_penalty(_split(out, cnt, cap)), cnt
+
+    def subsequence_batch(self, q_tokens, q_off, n=1, no_perfect=False, ml=3, mr=0.3, idf_weighting=False):
+        """FuzzyMatch::subsequence(string, ...) of the reference per pattern -> (records, texts): texts[q] is the
+        detokenised sub-sequence the reference appends to Match::id (decimal token strings joined by blanks)."""
+        q_tokens, q_off = _csr(q_tokens, q_off)
+        n_q = len(q_off) - 1
+        out = np.zeros(n_q, dtype=REF_SUBSEQ_DTYPE)
+        stride = 16 * int(max(1, np.diff(q_off).max() if n_q else 1)) + 16
+        text = np.zeros(n_q * stride, dtype=np.uint8)
+        self.lib.fmref_subsequence_batch(self.h, _ptr(q_tokens), _ptr(q_off), C.c_int64(n_q), C.c_int32(n), C.c_int32(int(no_perfect)),
+                                         C.c_int32(ml), C.c_float(mr), C.c_int32(int(idf_weighting)), _ptr(out), _ptr(text), C.c_int64(stride))
+        texts = [bytes(text[q * stride:(q + 1) * stride]).split(b"\0")[0].decode() for q in range(n_q)]
+        return out, texts
 
     def __del__(self):
         if getattr(self, "h", None):

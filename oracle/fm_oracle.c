@@ -6,7 +6,7 @@
  * reference computes through match(const Tokens&, ...) (src/fuzzy_match.cc:415-432) where the
  * "real" sentence equals the normalised one and there are no penalty tokens (itoks).
  *
- * Parity pin: tests/test_oracle_vs_ref.py checks this file against the reference's own sources
+ * Parity pin: tests/test_oracle.py checks this file against the reference's own sources
  * compiled unmodified (oracle/_ref/libfm_ref.so, see oracle/Makefile) on the reference's
  * tokenizer-free known-answer tests (test/test.cc:223-262, 337-632), on the order-dependence
  * vectors Q1/Q2 of SURVEY.md section 3.1, and on seeded random TMs; the resulting vectors are
@@ -864,4 +864,105 @@ void fmo_equal_range(const fmo_index* ix, const int32_t* ngram, int64_t length, 
     if (*lo == *hi) return;
     plo = *lo; phi = *hi;
   }
+}
+
+/* ------------------------------------------------------------------ subsequence()
+ *
+ * FuzzyMatch::subsequence (reference src/fuzzy_match.cc:238-365) behind its tokenizer: the pattern arrives as
+ * word ids (real == normalised tokens, no penalty tokens, like match(Tokens)); the text the reference appends to
+ * Match::id (the detokenised sub-sequence) is described by (position, length) instead. */
+typedef struct fmo_subseq {
+  uint32_t s_id;
+  float score;
+  float cost;
+  int32_t position; /* first pattern token of the sub-sequence that located the match */
+  int32_t length;   /* its length = Match::max_subseq */
+  int32_t found;
+} fmo_subseq;
+
+typedef struct { float weight; int32_t position; int32_t length; } subseq_t;
+/* priority_queue<Subseq> pops the largest element: weight desc, then position asc (operator< :238-248) */
+static int cmp_subseq(const void* a, const void* b) {
+  const subseq_t* x = (const subseq_t*)a; const subseq_t* y = (const subseq_t*)b;
+  if (x->weight != y->weight) return x->weight > y->weight ? -1 : 1;
+  if (x->position != y->position) return x->position < y->position ? -1 : 1;
+  return x->length > y->length ? -1 : (x->length < y->length ? 1 : 0); /* (only reachable with zero idf weights) */
+}
+
+static void subsequence_one(const fmo_index* ix, const int32_t* pattern_in, int64_t p_length, unsigned number_of_matches,
+                            int no_perfect, int min_subseq_length, float min_subseq_ratio, int idf_weighting, fmo_subseq* out) {
+  memset(out, 0, sizeof *out);
+  if ((int)(min_subseq_ratio * p_length) > min_subseq_length) min_subseq_length = (int)(min_subseq_ratio * p_length); /* :263-264 */
+  if ((int)p_length < min_subseq_length) return;                                                                   /* :266-267 */
+  int32_t* pidx = (int32_t*)malloc((size_t)(p_length + 1) * 4);
+  float* idf = (float*)malloc((size_t)(p_length + 1) * 4);
+  const unsigned num_sentences = (unsigned)ix->n_sent_global;
+  for (int64_t j = 0; j < p_length; j++) {
+    const int32_t t = pattern_in[j];
+    pidx[j] = (t >= 2 && t < ix->vocab_size && ix->sfreq[t] > 0) ? t : 1;
+    idf[j] = pidx[j] != 1 ? logf((float)num_sentences / (float)ix->sfreq[pidx[j]]) : -1.f; /* :372-390, unknown = -1 */
+  }
+  /* all sub-sequences without unknown words, by weight (:277-288) */
+  subseq_t* sq = (subseq_t*)malloc((size_t)(p_length * (p_length + 1) / 2 + 1) * sizeof(subseq_t));
+  int64_t n_sq = 0;
+  for (int64_t it = 0; it < p_length; it++) {
+    float idf_weight = 0;
+    for (int64_t jt = it; jt < p_length; jt++) {
+      const float weight = idf[jt];
+      if (weight == -1) break;
+      idf_weight += idf_weighting ? weight : 1;
+      if ((int)(jt - it + 1) >= min_subseq_length) { sq[n_sq].weight = idf_weight; sq[n_sq].position = (int32_t)it; sq[n_sq].length = (int32_t)(jt - it + 1); n_sq++; }
+    }
+  }
+  qsort(sq, (size_t)n_sq, sizeof(subseq_t), cmp_subseq);
+  int max_distance = 10000;
+  uint32_t* candidates = (uint32_t*)malloc(((size_t)number_of_matches + 1) * 4);
+  size_t n_cand = 0, n_perfect = 0, perfect_cap = 16;
+  uint32_t* perfect = (uint32_t*)malloc(perfect_cap * 4);
+  float* scratch = (float*)malloc((size_t)(2 * (p_length + 2)) * 4);
+  fmo_params unit; memset(&unit, 0, sizeof unit);
+  unit.insert_cost = unit.delete_cost = unit.replace_cost = 1.f;
+  for (int64_t k = 0; k < n_sq && max_distance == 10000; k++) { /* :300-301 */
+    int64_t lo = 0, hi = 0, plo = 0, phi = 0;
+    for (int64_t len = 1; len <= sq[k].length; len++) { /* canonical range of the whole n-gram (:306) */
+      equal_range(ix, pidx + sq[k].position, len, plo, phi, &lo, &hi, NULL);
+      if (lo == hi) break;
+      plo = lo; phi = hi;
+    }
+    for (int64_t su = lo; su < hi && n_cand < number_of_matches; su++) { /* :308-309 */
+      const uint32_t s_id = ix->sa_sid[su];
+      int seen = 0;
+      for (size_t i = 0; i < n_cand && !seen; i++) seen = candidates[i] == s_id;
+      for (size_t i = 0; i < n_perfect && !seen; i++) seen = perfect[i] == s_id;
+      if (seen) continue;
+      const int64_t s_length = ix->sent_pos[s_id + 1] - ix->sent_pos[s_id] - 1;
+      const float diff_word = 100.f / get_normalizer(p_length, s_length, &unit); /* Costs(p, s, EditCosts()) :317-318 */
+      const float cost = edit_distance_full(ix->buf + ix->sent_pos[s_id], (int)s_length, pidx, (int)p_length, idf, 0.f, &unit, diff_word,
+                                            (float)max_distance, NULL, scratch); /* :321-326 */
+      if (cost == 0 && no_perfect) { /* :327-330 */
+        if (n_perfect == perfect_cap) { perfect_cap *= 2; perfect = (uint32_t*)realloc(perfect, perfect_cap * 4); }
+        perfect[n_perfect++] = s_id;
+        continue;
+      }
+      if (cost < max_distance) { /* :331-350 */
+        out->found = 1;
+        out->score = (float)((int)(10000 - cost * 100) / 10000.0);
+        out->cost = cost;
+        out->length = sq[k].length;
+        out->position = sq[k].position;
+        out->s_id = s_id;
+        max_distance = (int)cost; /* int max_distance = cost: truncated */
+        if (cost == 0) break;
+      }
+      candidates[n_cand++] = s_id;
+    }
+  }
+  free(pidx); free(idf); free(sq); free(candidates); free(perfect); free(scratch);
+}
+
+void fmo_subsequence_batch(const fmo_index* ix, const int32_t* q_tokens, const int64_t* q_off, int64_t n_q, int32_t number_of_matches,
+                           int32_t no_perfect, int32_t min_subseq_length, float min_subseq_ratio, int32_t idf_weighting, fmo_subseq* out) {
+  for (int64_t q = 0; q < n_q; q++)
+    subsequence_one(ix, q_tokens + q_off[q], q_off[q + 1] - q_off[q], (unsigned)number_of_matches, no_perfect, min_subseq_length,
+                    min_subseq_ratio, idf_weighting, out + q);
 }

@@ -16,6 +16,7 @@
 #include <atomic>
 #include <chrono>
 #include <cstdint>
+#include <cstdio>
 #include <string>
 #include <thread>
 #include <vector>
@@ -183,6 +184,33 @@ double fmref_match_batch_real(void* h, const int32_t* q_tokens, const int32_t* q
     for (auto& t : pool) t.join();
   }
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// FuzzyMatch::subsequence(string, ...) (include/fuzzy/fuzzy_match.hh:96-102) for a batch: the pattern is handed over as
+// the decimal token strings joined by blanks, which the stand-in tokenizer splits again and the reference's own
+// _tokenize_and_normalize passes through unchanged (pt_none). text receives what the reference appends to Match::id
+// behind the tab (the detokenised sub-sequence), NUL-terminated, text_stride bytes per query.
+struct fmref_subseq { uint32_t s_id; float score; int32_t max_subseq; int32_t found; };
+void fmref_subsequence_batch(void* h, const int32_t* q_tokens, const int64_t* q_off, int64_t n_q, int32_t number_of_matches,
+                             int32_t no_perfect, int32_t min_subseq_length, float min_subseq_ratio, int32_t idf_weighting,
+                             fmref_subseq* out, char* text, int64_t text_stride) {
+  fuzzy::FuzzyMatch& fm = static_cast<RefHandle*>(h)->fm;
+  for (int64_t q = 0; q < n_q; q++) {
+    std::string sentence;
+    for (int64_t i = q_off[q]; i < q_off[q + 1]; i++) { if (i > q_off[q]) sentence += " "; sentence += std::to_string(q_tokens[i]); }
+    std::vector<fuzzy::FuzzyMatch::Match> matches;
+    const bool ok = fm.subsequence(sentence, (unsigned)number_of_matches, no_perfect != 0, matches, min_subseq_length, min_subseq_ratio,
+                                   idf_weighting != 0);
+    out[q] = fmref_subseq{0, 0.f, 0, 0};
+    text[q * text_stride] = 0;
+    if (ok && !matches.empty()) {
+      const auto& m = matches.back();
+      out[q] = fmref_subseq{m.s_id, m.score, m.max_subseq, 1};
+      const size_t tab = m.id.find('\t');
+      const std::string sub = tab == std::string::npos ? std::string() : m.id.substr(tab + 1);
+      snprintf(text + q * text_stride, (size_t)text_stride, "%s", sub.c_str());
+    }
+  }
 }
 
 int64_t fmref_max_tokens_in_pattern(void* h) { return (int64_t) static_cast<RefHandle*>(h)->fm.max_tokens_in_pattern(); }

@@ -174,7 +174,39 @@ static void sentence_api() {
   }
 }
 
+static void subsequence() {  // no gtest in the reference calls subsequence(): answers taken from the live reference (oracle/ref_driver.cc)
+  fuzzy::FuzzyMatch fm;
+  fm.add_tm("id0", split("the quick brown fox jumps over the lazy dog"), false);
+  fm.add_tm("id1", split("a quick brown dog"), false);
+  fm.add_tm("id2", split("lazy dog sleeps all day"), false);
+  fm.add_tm("id3", split("the quick brown fox"), false);
+  fm.sort();
+  {
+    std::vector<fuzzy::FuzzyMatch::Match> m;
+    EXPECT(fm.subsequence(split("my quick brown fox sleeps all day"), 1, false, m));
+    EXPECT(m.size() == 1);
+    if (m.size() == 1) { EXPECT(m[0].s_id == 3); EXPECT_NEAR(m[0].score, 0.4285f, 1e-6); EXPECT(m[0].max_subseq == 3); EXPECT(m[0].id == "id3\tquick brown fox"); }
+  }
+  {
+    std::vector<fuzzy::FuzzyMatch::Match> m;
+    EXPECT(fm.subsequence(split("the quick brown fox"), 2, true, m));  // the perfect match is skipped
+    if (m.size() == 1) { EXPECT(m[0].s_id == 0); EXPECT_NEAR(m[0].score, 0.4444f, 1e-6); EXPECT(m[0].max_subseq == 4); EXPECT(m[0].id == "id0\tthe quick brown fox"); }
+    m.clear();
+    EXPECT(fm.subsequence(split("the quick brown fox"), 2, false, m));
+    if (m.size() == 1) { EXPECT(m[0].s_id == 3); EXPECT_NEAR(m[0].score, 1.0f, 1e-6); }
+  }
+  {
+    std::vector<fuzzy::FuzzyMatch::Match> m;
+    EXPECT(fm.subsequence(split("lazy dog sleeps"), 3, false, m, 2, 0.f, true));
+    if (m.size() == 1) { EXPECT(m[0].s_id == 2); EXPECT_NEAR(m[0].score, 0.6f, 1e-6); EXPECT(m[0].max_subseq == 3); }
+    m.clear();
+    EXPECT(!fm.subsequence(split("nothing here matches"), 1, false, m));
+    EXPECT(m.empty());
+  }
+}
+
 int main() {
+  subsequence();
   small_sentence_matches();
   max_tokens_in_pattern();
   lcs_cost();

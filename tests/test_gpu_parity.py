@@ -7,7 +7,7 @@ import pytest
 import fuzzy_match_b200 as fmb
 from fuzzy_match_b200 import synth
 from oracle import binding as ob
-from tests.util import as_tuples, csr, fix_params, load_golden
+from tests.util import as_tuples, csr, first_seen_ids, fix_params, load_golden, load_subseq_golden
 
 pytestmark = pytest.mark.gpu
 CASES = load_golden()
@@ -293,6 +293,10 @@ def test_gpu_suffix_sort_matches_host_sort(monkeypatch):
         assert (ca == cb).all() and a.tobytes() == b.tobytes()
         ro, oc = oracle.match_batch(q, qo, cap=64, **params)
         assert (ca == oc).all() and all(a[i, :min(ca[i], 64)].tobytes() == ro[i].tobytes() for i in range(len(oc)))
+    # subsequence() walks ranges in suffix order and stops early: the order among identical suffixes (by sentence id) shows
+    for kw in (dict(n=1), dict(n=3, ml=1, mr=0.0, no_perfect=True)):
+        a, b, o = gpu_built.subsequence_batch(q, qo, **kw), host_built.subsequence_batch(q, qo, **kw), oracle.subsequence_batch(q, qo, **kw)
+        assert a.tobytes() == b.tobytes() == o.tobytes()
 
 
 def test_sentence_api_vs_oracle(tmp_path):
@@ -457,3 +461,53 @@ def test_submit_wait_pipeline(medium):
         got = d_out.cpu().numpy().view(capi.MATCH_DTYPE).reshape(b - a, cap)
         assert (cnt == wcnt[a:b]).all()
         assert all(got[i, :cnt[i]].tobytes() == want[a + i, :cnt[i]].tobytes() for i in range(b - a))
+
+
+# ---- subsequence() (reference src/fuzzy_match.cc:238-365) through fm_subsequence_batch
+SUBSEQ = load_subseq_golden()
+
+
+def subseq_tuples(rec, with_cost=False):
+    return [([int(r["found"]), int(r["s_id"]), int(r["score"].view(np.uint32)), int(r["length"]), int(r["position"])]
+             + ([int(r["cost"].view(np.uint32))] if with_cost else [])) if r["found"] else [0, 0, 0, 0, 0] + ([0] if with_cost else [])
+            for r in rec]
+
+
+@pytest.mark.parametrize("case", SUBSEQ["cases"], ids=[c["name"] for c in SUBSEQ["cases"]])
+def test_subsequence_golden_vectors(case):
+    t = SUBSEQ["tms"][case["tm"]]
+    tok, off = csr(t["tm"])
+    q, qo = csr(t["queries"])
+    index = fmb.Index(tok, off, t["vocab_size"])
+    assert subseq_tuples(index.subsequence_batch(q, qo, **case["params"])) == case["expected"]
+
+
+SUBSEQ_PARAMS = [dict(n=1), dict(n=5, no_perfect=True), dict(n=3, ml=2, mr=0.0, idf_weighting=True),
+                 dict(n=50, ml=1, mr=0.5, no_perfect=True, idf_weighting=True), dict(n=0), dict(n=2, ml=40, mr=0.0),
+                 dict(n=4000, ml=1, mr=0.0)]
+
+
+@pytest.mark.parametrize("n_sent,vocab,n_long", [(3000, 8, 0), (20000, 300, 0), (50000, 20000, 0), (4000, 50, 40)])
+def test_subsequence_vs_oracle(n_sent, vocab, n_long):
+    tm, off, _ = synth.make_tm(n_sent, vocab=vocab, seed=n_sent + vocab, n_long=n_long)
+    src = np.arange(n_sent - n_long, n_sent) if n_long else None
+    q, qo = synth.make_queries(tm, off, 400, vocab=vocab, seed=n_sent + vocab + 1, source_ids=src,
+                               **(dict(len_lo=200, len_hi=300) if n_long else {}))
+    tm, q, V = first_seen_ids(tm, q)
+    index, oracle = fmb.Index(tm, off, V, max_tokens=400), ob.OracleIndex(tm, off, V, max_tokens=400)  # perturbed long patterns may exceed 300
+    for kw in SUBSEQ_PARAMS:
+        got = subseq_tuples(index.subsequence_batch(q, qo, **kw), True)
+        want = subseq_tuples(oracle.subsequence_batch(q, qo, **kw), True)
+        bad = [i for i in range(len(want)) if got[i] != want[i]]
+        assert not bad, "%s query %d: gpu %s != oracle %s" % (kw, bad[0], got[bad[0]], want[bad[0]])
+
+
+def test_subsequence_degenerate_inputs():
+    tm, off, V = synth.make_tm(500, vocab=40, seed=3)
+    index, oracle = fmb.Index(tm, off, V), ob.OracleIndex(tm, off, V)
+    q, qo = csr([[], [5], [V + 3, V + 4, V + 5], [1, 1, 1, 1], tm[off[7]:off[8]].tolist(), list(range(2, 12)) * 30])
+    for kw in (dict(n=1), dict(n=1, ml=0, mr=0.0), dict(n=3, ml=1, mr=0.0, no_perfect=True)):
+        assert subseq_tuples(index.subsequence_batch(q, qo, **kw), True) == subseq_tuples(oracle.subsequence_batch(q, qo, **kw), True)
+    assert len(index.subsequence_batch(*csr([]), n=1)) == 0
+    with pytest.raises(fmb.FuzzyMatchError):  # longer than max_tokens_in_pattern: refused, never silently unmatched
+        index.subsequence_batch(*csr([list(range(2, 12)) * 40]), n=1)

@@ -5,7 +5,8 @@ import pytest
 
 from fuzzy_match_b200 import synth
 from oracle import binding as ob
-from tests.util import REALTEXT_PARAM_SETS, as_tuples, csr, fix_params, load_golden, load_realtext
+from tests.util import (REALTEXT_PARAM_SETS, as_tuples, csr, first_seen_ids, fix_params, load_golden, load_realtext,
+                        load_subseq_golden)
 
 CASES = load_golden()
 
@@ -154,3 +155,40 @@ def test_oracle_matches_reference_on_real_text():
     for params, want in zip(REALTEXT_PARAM_SETS, expected):
         res, cnt = O.match_batch(q, qo, cap=256, nthreads=8, **params)
         assert [as_tuples(r) for r in res] == want, params
+
+
+# ---- subsequence() (src/fuzzy_match.cc:238-365): the reference's tests never call it, so the pin is the
+# reference itself -- committed outputs (tests/golden/subseq.json) and, where oracle/_ref exists, live runs.
+SUBSEQ = load_subseq_golden()
+
+
+def subseq_tuples(rec):
+    return [[int(r["found"]), int(r["s_id"]), int(r["score"].view(np.uint32)), int(r["length"]), int(r["position"])] if r["found"]
+            else [0, 0, 0, 0, 0] for r in rec]
+
+
+@pytest.mark.parametrize("case", SUBSEQ["cases"], ids=[c["name"] for c in SUBSEQ["cases"]])
+def test_oracle_subsequence_matches_golden(case):
+    t = SUBSEQ["tms"][case["tm"]]
+    tok, off = csr(t["tm"])
+    q, qo = csr(t["queries"])
+    O = ob.OracleIndex(tok, off, t["vocab_size"])
+    assert subseq_tuples(O.subsequence_batch(q, qo, **case["params"])) == case["expected"]
+
+
+@pytest.mark.skipif(not ob.ref_available(), reason="oracle/_ref not built (no /root/reference here)")
+@pytest.mark.parametrize("seed,vocab", [(0, 8), (1, 30), (2, 2000), (3, 12)])
+def test_oracle_subsequence_matches_live_reference(seed, vocab):
+    tm, off, _ = synth.make_tm(3000, vocab=vocab, seed=seed)
+    q, qo = synth.make_queries(tm, off, 300, vocab=vocab, seed=seed + 100)
+    tm, q, V = first_seen_ids(tm, q)
+    O, R = ob.OracleIndex(tm, off, V), ob.RefIndex(tm, off)
+    for kw in (dict(n=1), dict(n=5, no_perfect=True), dict(n=3, ml=2, mr=0.0, idf_weighting=True),
+               dict(n=50, ml=1, mr=0.5, no_perfect=True, idf_weighting=True), dict(n=0), dict(n=2, ml=40, mr=0.0)):
+        a = O.subsequence_batch(q, qo, **kw)
+        b, texts = R.subsequence_batch(q, qo, **kw)
+        assert (a["found"] == b["found"]).all()
+        for i in np.nonzero(a["found"])[0]:
+            assert a[i]["s_id"] == b[i]["s_id"] and a[i]["score"].tobytes() == b[i]["score"].tobytes() and a[i]["length"] == b[i]["max_subseq"]
+            lo = qo[i] + a[i]["position"]
+            assert " ".join(str(x) for x in q[lo:lo + a[i]["length"]]) == texts[i]  # what the reference appends to Match::id

@@ -67,3 +67,23 @@ def load_realtext():
                         d["lm_%d" % k].tolist(), d["len_%d" % k].tolist()))
         expected.append([rows[off[i]:off[i + 1]] for i in range(len(cnt))])
     return d["tm_tok"], d["tm_off"], int(d["vocab_size"]), d["q_tok"], d["q_off"], expected
+
+
+def first_seen_ids(tm_tokens, q_tokens):
+    """Relabels word ids in first-seen order over the TM, the order in which VocabIndexer::addWords hands them out
+    (reference src/vocab_indexer.cc:37-50); query words the TM does not hold get ids beyond the vocabulary.
+    Returns (tm, queries, vocab_size). subsequence() observes the walk order inside a suffix-array range, which
+    follows the word ids, so comparisons with the live reference need the reference's own numbering."""
+    ids = {}
+    tm = np.empty(len(tm_tokens), dtype=np.int32)
+    for i, t in enumerate(np.asarray(tm_tokens).tolist()):
+        tm[i] = ids.setdefault(t, len(ids) + 2)
+    vocab_size = len(ids) + 2
+    q = np.array([ids.get(t, vocab_size + 7) for t in np.asarray(q_tokens).tolist()], dtype=np.int32)
+    return tm, q, vocab_size
+
+
+def load_subseq_golden():
+    """tests/golden/subseq.json (made by tests/golden/make_subseq.py from the live reference)."""
+    with open(os.path.join(os.path.dirname(GOLDEN), "subseq.json")) as f:
+        return json.load(f)

@@ -17,14 +17,20 @@ FULL = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 def launches(path):
     rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0].isdigit()]
-    d = defaultdict(list)
+    d = defaultdict(lambda: defaultdict(list))  # kernel -> metric -> values (one row per launch and metric)
     for r in rows:
-        d[r[4].split("(")[0]].append(float(r[-1]) / 1e3)
-    tot = sum(sum(v) for v in d.values())
-    print("# per-kernel device time from `ncu --metrics gpu__time_duration.sum --clock-control none` (cold-cache, serialised)")
-    print("%-44s %5s %12s %8s" % ("kernel", "n", "avg_us", "share"))
-    for k, v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
-        print("%-44s %5d %12.1f %8.3f" % (k[:44], len(v), sum(v) / len(v), sum(v) / tot))
+        d[r[4].split("(")[0]][r[12]].append(float(r[-1].replace(",", "")))
+    T = "gpu__time_duration.sum"
+    tot = sum(sum(v[T]) for v in d.values())
+    extra = sorted({m for v in d.values() for m in v} - {T})
+    short = {"smsp__inst_executed.sum": "warp_inst", "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue%",
+             "sm__warps_active.avg.pct_of_peak_sustained_active": "warps%"}
+    print("# per-kernel device time from `ncu --metrics gpu__time_duration.sum[,...] --clock-control none` (cold-cache, serialised)")
+    print("%-32s %4s %10s %7s" % ("kernel", "n", "avg_us", "share") + "".join(" %12s" % short.get(m, m[:12]) for m in extra))
+    for k, v in sorted(d.items(), key=lambda kv: -sum(kv[1][T])):
+        t = v[T]
+        print("%-32s %4d %10.1f %7.3f" % (k[:32], len(t), sum(t) / len(t) / 1e3, sum(t) / tot)
+              + "".join(" %12.1f" % (sum(v[m]) / len(v[m])) if v[m] else " %12s" % "-" for m in extra))
 
 
 def full(path):
