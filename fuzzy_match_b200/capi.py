@@ -72,7 +72,7 @@ WIRE_DTYPE = np.dtype([("s_id", np.uint32), ("lm_len", np.uint32), ("cost", np.f
 EXPORTS = ["fm_index_create", "fm_index_destroy", "fm_index_save", "fm_index_load", "fm_index_num_sentences", "fm_index_num_suffixes",
            "fm_index_max_tokens_in_pattern", "fm_index_device_bytes", "fm_index_kept_sources", "fm_index_sfreq",
            "fm_index_sentence", "fm_index_set_idf_stats", "fm_index_set_real", "fm_match_batch", "fm_match_batch_real", "fm_match_batch_device",
-           "fm_subsequence_batch",
+           "fm_subsequence_batch", "fm_match_batch_prior",
            "fm_match_batch_submit", "fm_match_batch_device_submit", "fm_ticket_wait", "fm_wire_block_bytes", "fm_shard_accept_device",
            "fm_merge_accepted_device", "fm_comm_unique_id", "fm_comm_create", "fm_comm_destroy", "fm_match_batch_sharded_device", "fm_match_batch_sharded_submit",
            "fm_comm_last_gather_bytes", "fm_comm_block_capacity", "fm_set_profiling", "fm_get_profile", "fm_last_error", "fm_version"]
@@ -107,6 +107,8 @@ def load_library():
     lib.fm_index_sentence.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32)]
     lib.fm_match_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Params), C.c_int64,
                                    C.c_void_p, C.c_void_p]
+    lib.fm_match_batch_prior.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Params), C.c_void_p, C.c_void_p,
+                                         C.c_int64, C.c_void_p, C.c_void_p]
     lib.fm_subsequence_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                          C.c_int32, C.c_void_p]
     lib.fm_index_set_real.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
@@ -252,6 +254,23 @@ class Index:
         assert out.dtype == MATCH_DTYPE and out.size == n_q * cap and out.flags.c_contiguous and len(cnt) == n_q
         _check(self.lib, self.lib.fm_match_batch(self.h, _ptr(q_tokens), _ptr(q_off), n_q, C.byref(p), cap, _ptr(out),
                                                  _ptr(cnt)))
+        return out, cnt
+
+    def match_batch_prior(self, q_tokens, q_off, prior_sid, prior_off, cap=None, params=None, **kw):
+        """fm_match_batch_prior: match() into result vectors that already hold the sentences prior_sid (CSR per query)."""
+        p = params if params is not None else Params.make(**kw)
+        if cap is None:
+            cap = max(1, p.number_of_matches)
+        q_tokens = np.ascontiguousarray(q_tokens, dtype=np.int32)
+        q_off = np.ascontiguousarray(q_off, dtype=np.int64)
+        prior_sid = np.ascontiguousarray(prior_sid, dtype=np.uint32)
+        prior_off = np.ascontiguousarray(prior_off, dtype=np.int64)
+        n_q = len(q_off) - 1
+        assert len(prior_off) == n_q + 1
+        out = np.zeros((n_q, cap), dtype=MATCH_DTYPE)
+        cnt = np.zeros(n_q, dtype=np.int32)
+        _check(self.lib, self.lib.fm_match_batch_prior(self.h, _ptr(q_tokens), _ptr(q_off), n_q, C.byref(p), _ptr(prior_sid),
+                                                       _ptr(prior_off), cap, _ptr(out), _ptr(cnt)))
         return out, cnt
 
     def subsequence_batch(self, q_tokens, q_off, n=1, no_perfect=False, ml=3, mr=0.3, idf_weighting=False):

@@ -125,6 +125,16 @@ public:
              const EditCosts& edit_costs = EditCosts(), float contrastive_factor = 0,
              ContrastReduce reduce = ContrastReduce::MEAN, int contrast_buffer = -1, bool no_perfect = false) const {
     std::vector<std::vector<Match>> out(1);
+    if (!matches.empty() && _tm_plain) {
+      // entries already in `matches` count against number_of_matches and take part in the contrastive penalties
+      // (src/fuzzy_match.cc:626-679): their sentence ids go with the call (fm_match_batch_prior)
+      std::vector<uint32_t> prior;
+      for (const Match& m : matches) prior.push_back(m.s_id);
+      run_batch({pattern}, nullptr, fuzzy, number_of_matches, out, min_subseq_length, min_subseq_ratio, vocab_idf_penalty, edit_costs,
+                contrastive_factor, reduce, contrast_buffer, no_perfect, &prior);
+      matches.insert(matches.end(), out[0].begin(), out[0].end());
+      return true;
+    }
     match_batch({pattern}, fuzzy, number_of_matches, out, min_subseq_length, min_subseq_ratio, vocab_idf_penalty, edit_costs,
                 contrastive_factor, reduce, contrast_buffer, no_perfect);
     append_results(matches, out[0], number_of_matches, contrastive_factor);
@@ -183,8 +193,8 @@ public:
 private:
   // The reference APPENDS to `matches` and stops at number_of_matches entries in total, so entries that are
   // already there shorten what a call adds (src/fuzzy_match.cc:670-679). Its contrastive rerank also penalises
-  // the candidates against entries that were there before the call (:634-652); that needs the earlier matches
-  // on the device and is not offered: refused instead of answered differently.
+  // the candidates against entries that were there before the call (:634-652): match(Tokens) hands them to the
+  // library (above); the Sentence overload has no such entry point and refuses instead of answering differently.
   static void append_results(std::vector<Match>& matches, const std::vector<Match>& found, unsigned number_of_matches,
                              float contrastive_factor) {
     if (contrastive_factor > 0 && !matches.empty())
@@ -199,7 +209,7 @@ private:
   void run_batch(const std::vector<Tokens>& patterns, const std::vector<Sentence>* reals, float fuzzy, unsigned number_of_matches,
                  std::vector<std::vector<Match>>& out, int min_subseq_length, float min_subseq_ratio, float vocab_idf_penalty,
                  const EditCosts& edit_costs, float contrastive_factor, ContrastReduce reduce, int contrast_buffer,
-                 bool no_perfect) const {
+                 bool no_perfect, const std::vector<uint32_t>* prior = nullptr) const {
     if (!_index || _dirty) throw std::logic_error("FuzzyMatch::sort() must be called before match()");
     std::vector<int32_t> q_tok, q_real, q_gaps;
     std::vector<int64_t> q_off(1, 0);
@@ -224,7 +234,10 @@ private:
     std::vector<int32_t> cnt((size_t)n_q);
     for (;;) {
       res.assign((size_t)(n_q * cap), fm_match());
-      if (!reals && _tm_plain) {  // nothing but normalised tokens anywhere: the plain path is equivalent
+      if (!reals && _tm_plain && prior) {  // one pattern, result vector not empty
+        const int64_t prior_off[2] = {0, (int64_t)prior->size()};
+        check(fm_match_batch_prior(_index, q_tok.data(), q_off.data(), n_q, &prm, prior->data(), prior_off, cap, res.data(), cnt.data()));
+      } else if (!reals && _tm_plain) {  // nothing but normalised tokens anywhere: the plain path is equivalent
         check(fm_match_batch(_index, q_tok.data(), q_off.data(), n_q, &prm, cap, res.data(), cnt.data()));
       } else {
         if (!_real_uploaded) {

@@ -161,6 +161,9 @@ static int ensure_out(Workspace* w, int64_t n_q, int64_t cap) {
 }
 
 static void free_workspace(Workspace* w) {
+  cudaFree(w->d_prior); cudaFree(w->d_prior_off);
+  cudaFree(w->ctok); cudaFree(w->c_cnt); cudaFree(w->c_base);
+  if (w->h_ctotal) cudaFreeHost(w->h_ctotal);
   cudaFree(w->d_q_tok); cudaFree(w->d_q_off); cudaFree(w->d_q_real); cudaFree(w->d_q_gap); cudaFree(w->d_itok_dist); cudaFree(w->pat); cudaFree(w->chain_q); cudaFree(w->qmeta); cudaFree(w->tbl); cudaFree(w->cmin_tab); cudaFree(w->span_slice); cudaFree(w->qmask); cudaFree(w->wq); cudaFree(w->peq64); cudaFree(w->cmin64); cudaFree(w->sm_rec);
   cudaFree(w->sl_start); cudaFree(w->sl_rec); cudaFree(w->hkey); cudaFree(w->hlm); cudaFree(w->surv); cudaFree(w->cand); cudaFree(w->surv_len);
   cudaFree(w->q_cnt); cudaFree(w->q_base); cudaFree(w->acc_cnt); cudaFree(w->rec); cudaFree(w->heapbuf); cudaFree(w->ctr); cudaFree(w->mctr); cudaFree(w->wire_stage); cudaFree(w->wire_send); cudaFree(w->wire_recv); cudaFree(w->scan_chain);
@@ -312,7 +315,8 @@ static int wait_and_check(Workspace* w, int attempt, int* retries) {
 static int run_replay(Index* ix, Workspace* w, fm_record* rec, const int32_t* q_cnt, const int32_t* q_base, float* heapbuf,
                       unsigned long long* sort_key, unsigned long long* sort_key2, int32_t* sort_idx, int32_t* acc_cnt,
                       int32_t* mid_q, int32_t* heavy_q, const int32_t* d_q_off, int64_t n_q, const Params& pr, int64_t cap, fm_match* d_out, int32_t* d_out_count,
-                      cudaStream_t st, int* launches, Counters* ctr = nullptr, int32_t* wire_cnt = nullptr, fm_wire* wire_stage = nullptr) {
+                      cudaStream_t st, int* launches, Counters* ctr = nullptr, int32_t* wire_cnt = nullptr, fm_wire* wire_stage = nullptr,
+                      bool defer_contrast = false) {
   if (!ctr) ctr = w->ctr;
   launch_replay(ix->dev, rec, q_cnt, q_base, heapbuf, sort_key, sort_key2, sort_idx, acc_cnt, mid_q, heavy_q, d_q_off, (int32_t)n_q, pr, cap, d_out,
                 d_out_count, ctr, ix->sm_count, st, w->stream2, w->ev_fork, w->ev_join, wire_cnt, wire_stage);
@@ -321,8 +325,9 @@ static int run_replay(Index* ix, Workspace* w, fm_record* rec, const int32_t* q_
     int rc;
     if ((rc = stage_check(st, "replay kernels"))) return rc;
   }
-  if (pr.contrast > 0.f && !wire_cnt) {
-    launch_contrast(ix->dev, rec, q_base, sort_idx, acc_cnt, (int32_t)n_q, pr, cap, d_out, d_out_count, ctr, ix->sm_count, st);
+  if (pr.contrast > 0.f && !wire_cnt && !defer_contrast) {
+    launch_contrast(ix->dev, rec, q_base, sort_idx, acc_cnt, (int32_t)n_q, pr, cap, d_out, d_out_count, ctr, ix->sm_count, st,
+                    w->prior_active ? w->d_prior : nullptr, w->prior_active ? w->d_prior_off : nullptr);
     (*launches)++;
   }
   if (ix->profiling) cudaEventRecord(w->ev[6], st);
@@ -379,6 +384,7 @@ static int enqueue_device(Index* ix, DeviceJob& j, const Params& pr) {
 static int submit_device(Index* ix, DeviceJob& j, const Params& pr) {
   int rc;
   j.w->real_active = false;
+  j.w->prior_active = false;
   if ((rc = ensure_queries(j.w, j.n_q, j.n_tok, false)) || (rc = initial_worklists(ix, j.w, j.n_q, j.n_tok))) return rc;
   return enqueue_device(ix, j, pr);
 }
@@ -404,12 +410,46 @@ struct HostChunk {
   int launches = 0;
 };
 
-struct RealInputs {  // Sentence API extras of a host batch (all NULL / 0 when absent)
+struct RealInputs {  // extras of a host batch (all NULL / 0 when absent): Sentence API; entries already in `matches`
   const int32_t* q_real = nullptr;
   const int32_t* q_gaps = nullptr;
   const int32_t* itok_dist = nullptr;
   int32_t n_itok = 0;
+  const uint32_t* prior_sid = nullptr;  // fm_match_batch_prior: sentence ids per query, CSR by prior_off
+  const int64_t* prior_off = nullptr;
 };
+
+// Entries already in the callers' result vectors -> (sentence start, length) per entry on the device.
+static int stage_prior(Index* ix, Workspace* w, const HostChunk& c, const RealInputs& ri, cudaStream_t st) {
+  w->prior_active = ri.prior_sid != nullptr;
+  if (!w->prior_active) return FM_OK;
+  int rc;
+  const int64_t p0 = ri.prior_off[c.q0], np = ri.prior_off[c.q0 + c.nq] - p0;
+  if (np > w->cap_prior) {
+    if ((rc = dev_realloc(&w->d_prior, np + np / 4 + 256))) return rc;
+    w->cap_prior = np + np / 4 + 256;
+  }
+  if (c.nq + 1 > w->cap_prior_q) {
+    if ((rc = dev_realloc(&w->d_prior_off, c.nq + 1 + 256))) return rc;
+    w->cap_prior_q = c.nq + 1 + 256;
+  }
+  std::vector<int2> ent((size_t)np);
+  std::vector<int32_t> off((size_t)c.nq + 1);
+  for (int64_t i = 0; i <= c.nq; i++) off[(size_t)i] = (int32_t)(ri.prior_off[c.q0 + i] - p0);
+  for (int64_t k = 0; k < np; k++) {
+    const int64_t s = (int64_t)ri.prior_sid[p0 + k] - (int64_t)ix->dev.sid_base;
+    if (s < 0 || s >= ix->n_sent) { set_error("prior match: sentence id not in this index"); return FM_ERR_INVALID; }
+    const int32_t start = ix->h_sent_start[(size_t)s];
+    int32_t n = 0;
+    while (ix->h_tok[(size_t)start + n] != 0) n++;
+    ent[(size_t)k] = make_int2(start, n);
+  }
+  // pageable sources: the copies are staged before cudaMemcpyAsync returns, so the vectors may go out of scope
+  if (np) FM_CUDA(cudaMemcpyAsync(w->d_prior, ent.data(), (size_t)np * sizeof(int2), cudaMemcpyHostToDevice, st));
+  FM_CUDA(cudaMemcpyAsync(w->d_prior_off, off.data(), (size_t)(c.nq + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  FM_CUDA(cudaStreamSynchronize(st));
+  return FM_OK;
+}
 
 static int stage_real(Workspace* w, const HostChunk& c, const int64_t* q_off, const RealInputs& ri, cudaStream_t st) {
   w->real_active = ri.q_real != nullptr;
@@ -458,7 +498,7 @@ static int launch_host_chunk(Index* ix, HostChunk& c, const int32_t* q_tokens, c
   const double t1 = g_host_timing ? now_ms() : 0;
   for (int64_t i = 0; i <= c.nq; i++) w->h_q_off32[i] = (int32_t)(q_off[c.q0 + i] - q_off[c.q0]);
   FM_CUDA(cudaMemcpyAsync(w->d_q_off, w->h_q_off32, (c.nq + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  if ((rc = stage_real(w, c, q_off, ri, st))) return rc;
+  if ((rc = stage_real(w, c, q_off, ri, st)) || (rc = stage_prior(ix, w, c, ri, st))) return rc;
   FM_CUDA(cudaMemsetAsync(w->d_out, 0, c.nq * cap * sizeof(fm_match), st));  // slots past the count read as zero
   c.launches = 0;
   if ((rc = launch_shard(ix, w, w->d_q_tok, w->d_q_off, c.nq, c.ntok, pr, st, &c.launches))) return rc;
@@ -639,6 +679,28 @@ int fm_match_batch_real(fm_index* index, const int32_t* q_tokens, const int32_t*
   RealInputs ri;
   ri.q_real = q_real; ri.q_gaps = q_gaps; ri.itok_dist = itok_dist; ri.n_itok = n_itok;
   return match_batch_host(index, q_tokens, q_off, n_q, params, cap, out, out_count, ri);
+}
+
+int fm_match_batch_prior(fm_index* index, const int32_t* q_tokens, const int64_t* q_off, int64_t n_q, const fm_params* params,
+                         const uint32_t* prior_sid, const int64_t* prior_off, int64_t cap, fm_match* out, int32_t* out_count) {
+  if (!prior_off || (!prior_sid && n_q > 0 && prior_off[n_q] != prior_off[0])) { set_error("bad argument (prior CSR)"); return FM_ERR_INVALID; }
+  for (int64_t q = 0; q < n_q; q++)
+    if (prior_off[q + 1] < prior_off[q]) { set_error("prior_off not ascending"); return FM_ERR_INVALID; }
+  RealInputs ri;
+  static const uint32_t none = 0;
+  ri.prior_sid = prior_sid ? prior_sid : &none;
+  ri.prior_off = prior_off;
+  const int rc = match_batch_host(index, q_tokens, q_off, n_q, params, cap, out, out_count, ri);
+  if (rc || !params || params->contrastive_factor > 0.f || params->number_of_matches == 0) return rc;
+  // without the rerank the earlier entries only count against number_of_matches (src/fuzzy_match.cc:672)
+  for (int64_t q = 0; q < n_q; q++) {
+    const int64_t room = std::max<int64_t>(0, (int64_t)params->number_of_matches - (prior_off[q + 1] - prior_off[q]));
+    if (out_count[q] > room) {
+      for (int64_t k = room; k < std::min<int64_t>(out_count[q], cap); k++) out[q * cap + k] = fm_match{};
+      out_count[q] = (int32_t)room;
+    }
+  }
+  return rc;
 }
 
 int fm_index_set_real(fm_index* index, const int32_t* real, const int32_t* gaps, const int64_t* sent_off, int64_t n_sent) {
@@ -830,7 +892,8 @@ static int ensure_merge(Workspace* w, int64_t n_q, int64_t total) {
 }
 // total_capacity = sum of the blocks' capacities (an upper bound on the records of the union)
 static int enqueue_merge(Index* ix, Workspace* w, int n_shards, const int32_t* const* blocks, int64_t total_capacity, const int32_t* d_q_off,
-                         int64_t n_q, const Params& pr, int64_t cap, fm_match* d_out, int32_t* d_out_count, cudaStream_t st, int* launches) {
+                         int64_t n_q, const Params& pr, int64_t cap, fm_match* d_out, int32_t* d_out_count, cudaStream_t st, int* launches,
+                         bool defer_contrast = false) {
   int rc;
   if ((rc = ensure_merge(w, n_q, total_capacity))) return rc;
   FM_CUDA(cudaMemsetAsync(w->mctr, 0, sizeof(Counters), st));
@@ -840,7 +903,7 @@ static int enqueue_merge(Index* ix, Workspace* w, int n_shards, const int32_t* c
   *launches += 3;
   if ((rc = stage_check(st, "wire merge"))) return rc;
   if ((rc = run_replay(ix, w, w->mrec, w->m_cnt, w->m_base, w->m_heap, w->m_key, w->m_key2, w->m_idx, w->m_acc, w->m_mid, w->m_heavy, d_q_off,
-                       n_q, pr, cap, d_out, d_out_count, st, launches, w->mctr)))
+                       n_q, pr, cap, d_out, d_out_count, st, launches, w->mctr, nullptr, nullptr, defer_contrast)))
     return rc;
   FM_CUDA(cudaMemcpyAsync(w->h_mctr, w->mctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
   return FM_OK;
@@ -860,6 +923,7 @@ int fm_shard_accept_device(fm_index* index, const int32_t* d_q_tokens, const int
   if ((rc = ensure_base(w)) || (rc = ensure_queries(w, n_q, n_query_tokens, false))) return rc;
   int launches = 0, retries = 0;
   w->real_active = false;
+  w->prior_active = false;
   if ((rc = ensure_stage(w)) || (rc = initial_worklists(ix, w, n_q, n_query_tokens))) return rc;
   for (int attempt = 0;; attempt++) {
     if ((rc = enqueue_accept(ix, w, d_q_tokens, d_q_off, n_q, n_query_tokens, pr, capacity, d_block, st, &launches))) return rc;
@@ -915,6 +979,7 @@ struct Nccl {
   int (*CommInitRank)(void** comm, int nranks, NcclId id, int rank) = nullptr;
   int (*CommDestroy)(void* comm) = nullptr;
   int (*AllGather)(const void* send, void* recv, size_t count, int dtype, void* comm, cudaStream_t st) = nullptr;
+  int (*AllReduce)(const void* send, void* recv, size_t count, int dtype, int op, void* comm, cudaStream_t st) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool ok = false;
 };
@@ -933,8 +998,9 @@ static Nccl& nccl() {
     n.CommInitRank = reinterpret_cast<int (*)(void**, int, NcclId, int)>(dlsym(n.lib, "ncclCommInitRank"));
     n.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(n.lib, "ncclCommDestroy"));
     n.AllGather = reinterpret_cast<int (*)(const void*, void*, size_t, int, void*, cudaStream_t)>(dlsym(n.lib, "ncclAllGather"));
+    n.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(dlsym(n.lib, "ncclAllReduce"));
     n.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(n.lib, "ncclGetErrorString"));
-    n.ok = n.GetUniqueId && n.CommInitRank && n.CommDestroy && n.AllGather;
+    n.ok = n.GetUniqueId && n.CommInitRank && n.CommDestroy && n.AllGather && n.AllReduce;
   });
   return n;
 }
@@ -1014,9 +1080,58 @@ static int enqueue_sharded(fm_ticket* t) {
   c->last_gather_bytes = bytes * c->world;
   const int32_t* blocks[16];
   for (int k = 0; k < c->world; k++) blocks[k] = reinterpret_cast<const int32_t*>(w->wire_recv + (size_t)k * bytes);
-  if ((rc = enqueue_merge(ix, w, c->world, blocks, capacity * c->world, j.d_q_off, j.n_q, t->pr, j.cap, j.d_out, j.d_out_count, j.st, &j.launches)))
+  if ((rc = enqueue_merge(ix, w, c->world, blocks, capacity * c->world, j.d_q_off, j.n_q, t->pr, j.cap, j.d_out, j.d_out_count, j.st, &j.launches,
+                          /*defer_contrast=*/true)))
     return rc;
   return enqueue_done(w, j.st);
+}
+
+// Contrastive rerank of a settled sharded batch (src/fuzzy_match.cc:613-669): the merged, accepted records are on every
+// rank; the sentences behind them are gathered into one token slab (each rank fills what it owns, one all-reduce sums the
+// slabs) and every rank runs the rerank on it. Collective: all ranks see the same accepted lists, hence the same layout.
+static int contrast_sharded(fm_ticket* t) {
+  Index* ix = t->ix;
+  fm_comm* c = t->comm;
+  DeviceJob& j = t->dev;
+  Workspace* w = j.w;
+  cudaStream_t st = j.st;
+  int rc;
+  {
+    std::lock_guard<std::mutex> g(ix->mu);
+    if (!ix->d_sent_start) {
+      FM_CUDA(cudaMalloc((void**)&ix->d_sent_start, (size_t)(ix->n_sent + 1) * sizeof(int32_t)));
+      FM_CUDA(cudaMemcpy(ix->d_sent_start, ix->h_sent_start.data(), (size_t)(ix->n_sent + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+      ix->dev.sent_start = ix->d_sent_start;
+    }
+  }
+  if (j.n_q + 1 > w->cap_cq) {
+    if ((rc = dev_realloc(&w->c_cnt, j.n_q + 1 + 256)) || (rc = dev_realloc(&w->c_base, j.n_q + 1 + 256))) return rc;
+    w->cap_cq = j.n_q + 1 + 256;
+  }
+  if (!w->h_ctotal) FM_CUDA(cudaMallocHost((void**)&w->h_ctotal, sizeof(int32_t)));
+  launch_contrast_need(w->mrec, w->m_base, w->m_idx, w->m_acc, (int32_t)j.n_q, w->c_cnt, st);
+  launch_scan(w->c_cnt, w->c_base, (int32_t)j.n_q, w->scan_chain, ++w->scan_epoch, ix->sm_count, st);
+  FM_CUDA(cudaMemcpyAsync(w->h_ctotal, w->c_base + j.n_q, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  FM_CUDA(cudaStreamSynchronize(st));
+  const int64_t total = *w->h_ctotal;
+  if (total < 0) { set_error("contrastive rerank: more than 2^31 tokens behind the accepted records of one batch (split it)"); return FM_ERR_NOMEM; }
+  if (total + 1 > w->cap_ctok) {
+    if ((rc = dev_realloc(&w->ctok, total + total / 4 + 1024))) return rc;
+    w->cap_ctok = total + total / 4 + 1024;
+  }
+  FM_CUDA(cudaMemsetAsync(w->ctok, 0, (size_t)(total + 1) * sizeof(int32_t), st));
+  launch_contrast_fill(ix->dev, ix->n_sent, w->mrec, w->m_base, w->m_idx, w->m_acc, w->c_base, (int32_t)j.n_q, w->ctok, st);
+  if (total) {
+    const int nr = nccl().AllReduce(w->ctok, w->ctok, (size_t)total, /*ncclInt32*/ 2, /*ncclSum*/ 0, c->comm, st);
+    if (nr) return nccl_fail(nr, "ncclAllReduce");
+  }
+  IndexDev slab = ix->dev;
+  slab.tok = w->ctok;
+  launch_contrast(slab, w->mrec, w->m_base, w->m_idx, w->m_acc, (int32_t)j.n_q, t->pr, j.cap, j.d_out, j.d_out_count, w->mctr, ix->sm_count, st);
+  j.launches += 4;
+  FM_CUDA(cudaStreamSynchronize(st));
+  FM_CUDA(cudaGetLastError());
+  return FM_OK;
 }
 
 // Every rank takes the same decisions from the same gathered data, so the collectives stay matched: a batch
@@ -1040,6 +1155,7 @@ static int finish_sharded(fm_ticket* t) {
     if (++t->attempts >= 10) { set_error("sharded batch does not settle (workspace / block size keep growing)"); return FM_ERR_NOMEM; }
     if ((rc = enqueue_sharded(t))) return rc;
   }
+  if (t->pr.contrast > 0.f && (rc = contrast_sharded(t))) return rc;
   finish_profile(ix, w, j.n_q, j.n_tok, j.launches, retries);
   return FM_OK;
 }
@@ -1058,10 +1174,6 @@ int fm_match_batch_sharded_submit(fm_index* index, fm_comm* c, const int32_t* d_
   if ((rc = check_params(params, &pr))) return rc;
   if (c->world == 1)  // one shard is the whole TM
     return fm_match_batch_device_submit(index, d_q_tokens, d_q_off, n_q, n_query_tokens, params, cap, d_out, d_out_count, stream, ticket);
-  if (pr.contrast > 0.f) {
-    set_error("contrastive rerank needs the sentences of every shard; not supported on a sharded TM");
-    return FM_ERR_INVALID;
-  }
   FM_CUDA(cudaSetDevice(ix->device));
   std::lock_guard<std::mutex> coll(ix->shard_mu);  // collectives of one communicator are issued one call at a time
   fm_ticket* t = new fm_ticket();
@@ -1071,6 +1183,7 @@ int fm_match_batch_sharded_submit(fm_index* index, fm_comm* c, const int32_t* d_
   j.d_q_tok = d_q_tokens; j.d_q_off = d_q_off; j.n_q = n_q; j.n_tok = n_query_tokens; j.cap = cap;
   j.d_out = d_out; j.d_out_count = d_out_count; j.st = static_cast<cudaStream_t>(stream);
   j.w->real_active = false;
+  j.w->prior_active = false;
   if ((rc = ensure_base(j.w)) || (rc = ensure_queries(j.w, n_q, n_query_tokens, false)) || (rc = ensure_stage(j.w)) ||
       (rc = initial_worklists(ix, j.w, n_q, n_query_tokens)) || (rc = enqueue_sharded(t))) {
     drop_ticket(t);

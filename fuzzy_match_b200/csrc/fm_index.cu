@@ -461,6 +461,7 @@ void free_index(Index* ix) {
   cudaSetDevice(ix->device);
   for (void* p : ix->d_blocks)
     if (p) cudaFree(p);
+  cudaFree(ix->d_sent_start);
   delete ix;
 }
 

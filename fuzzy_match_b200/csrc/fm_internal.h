@@ -60,6 +60,7 @@ struct IndexDev {
   int64_t n_suf;
   uint32_t sid_base;
   float idf_max;  // (float)log((double)N_sent_global)
+  const int32_t* sent_start;  // optional [n_sent]: start of local sentence s in tok (uploaded on first use: contrastive rerank on a sharded TM)
 };
 
 // per-query metadata written by the prepare kernel
@@ -207,6 +208,11 @@ struct Workspace {
   int64_t cap_real_tok = 0, cap_real_gap = 0, cap_itok = 0;
   int32_t n_itok = 0;
   bool real_active = false;  // the batch in flight carries real tokens / penalty tokens
+  // entries already in the callers' result vectors (fm_match_batch_prior): (sentence start in tok, length) per entry
+  int2* d_prior = nullptr;
+  int32_t* d_prior_off = nullptr;  // [n_q+1]
+  int64_t cap_prior = 0, cap_prior_q = 0;
+  bool prior_active = false;
   int32_t *pat = nullptr, *chain_q = nullptr;
   QMeta* qmeta = nullptr;
   int2* tbl = nullptr;
@@ -252,6 +258,11 @@ struct Workspace {
   int32_t *m_cnt = nullptr, *m_base = nullptr, *m_acc = nullptr;
   float* m_heap = nullptr;
   int64_t cap_mrec = 0, cap_mq = 0;
+  // contrastive rerank on a sharded TM: tokens of every accepted sentence, filled by the owning shard and summed over the ranks
+  int32_t* ctok = nullptr;
+  int32_t *c_cnt = nullptr, *c_base = nullptr;
+  int64_t cap_ctok = 0, cap_cq = 0;
+  int32_t* h_ctotal = nullptr;  // pinned
   // pinned host staging
   Counters* h_ctr = nullptr;
   int32_t* h_q_off32 = nullptr;
@@ -279,6 +290,7 @@ struct Index {
   // workspaces
   std::mutex mu;
   std::vector<Workspace*> pool;
+  int32_t* d_sent_start = nullptr;  // device copy of h_sent_start (lazily, under mu)
   std::mutex shard_mu;  // the sharded calls of one index run one at a time (collectives must not interleave)
   bool profiling = false;
   fm_profile last_profile{};
@@ -321,7 +333,11 @@ void launch_replay(const IndexDev& ix, const fm_record* rec, const int32_t* q_cn
                    int32_t* wire_cnt = nullptr, fm_wire* wire_stage = nullptr);  // wire_cnt != NULL: shard mode (accepted records out)
 void launch_contrast(const IndexDev& ix, fm_record* rec, const int32_t* q_base, const int32_t* sort_idx,
                      const int32_t* acc_cnt, int32_t n_q, const Params& p, int64_t cap, fm_match* out, int32_t* out_count,
-                     Counters* ctr, int sm_count, cudaStream_t st);
+                     Counters* ctr, int sm_count, cudaStream_t st, const int2* prior = nullptr, const int32_t* prior_off = nullptr);
+void launch_contrast_need(const fm_record* rec, const int32_t* q_base, const int32_t* sort_idx, const int32_t* acc_cnt, int32_t n_q,
+                          int32_t* tok_cnt, cudaStream_t st);
+void launch_contrast_fill(const IndexDev& ix, int64_t n_sent_local, fm_record* rec, const int32_t* q_base, const int32_t* sort_idx,
+                          const int32_t* acc_cnt, const int32_t* tok_base, int32_t n_q, int32_t* slab, cudaStream_t st);
 void launch_subseq(const IndexDev& ix, const int32_t* q_tok, const int32_t* q_off, int32_t n_q, int n_matches, int no_perfect, int ml, float mr,
                    int idf_weighting, uint32_t* seen, int seen_cap, fm_subseq* out, cudaStream_t st);
 // wire blocks (one shard's accepted records of a batch; layout in fm_kernels.cu / include/fuzzy_match_b200.h)

@@ -1262,10 +1262,9 @@ __device__ __forceinline__ void thread_edit_distance(const int32_t* __restrict__
     }
     K = fmaxf(K, rmin);
   }
-  float C = 0.f;
+  float C = 0.f;  // row[p - 1] as a chain of selects: a dynamic index would put the row into local memory
 #pragma unroll
-  for (int j = 0; j < 32; j++)
-    if (j == p - 1) C = row[j];
+  for (int j = 0; j < 32; j++) C = (j < p) ? row[j] : C;
   C_out = C;
   K_out = K;
 }
@@ -2075,14 +2074,16 @@ __global__ void __launch_bounds__(256) fm_replay_heavy_kernel(fm_record* rec, co
   }
 }
 
-// One warp per query: contrastive rerank of src/fuzzy_match.cc:613-669. Penalties against the newly
-// selected match are edit distances between TM sentences (plain variant, unit costs), accumulated in
-// selection order (running float sum for MEAN, running max for MAX).
+// One warp per query: contrastive rerank of src/fuzzy_match.cc:613-669. Penalties are edit distances between TM
+// sentences (plain variant, unit costs) against every entry of `matches`, accumulated in vector order (running float
+// sum for MEAN, running max for MAX): first the entries that were in the vector before the call (prior, optional:
+// (sentence start, length) per entry, CSR by prior_off), then the matches this call selects.
 __global__ void __launch_bounds__(256) fm_contrast_kernel(IndexDev ix, fm_record* rec, const int32_t* __restrict__ q_base,
                                                           const int32_t* __restrict__ sort_idx,
                                                           const int32_t* __restrict__ acc_cnt, int n_q, Params pr,
                                                           long long cap, fm_match* out, int32_t* out_count, Counters* ctr,
-                                                          int stride) {
+                                                          int stride, const int2* __restrict__ prior,
+                                                          const int32_t* __restrict__ prior_off) {
   extern __shared__ int smem[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -2098,30 +2099,41 @@ __global__ void __launch_bounds__(256) fm_contrast_kernel(IndexDev ix, fm_record
     const int n = acc_cnt[q];
     fm_record* seg = rec + q_base[q];
     const int32_t* idx = sort_idx + q_base[q];  // accepted records, best first
-    int n_out = 0, remaining = n, n_sel = 0;
-    int last = -1;
-    while (remaining > 0 && (pr.n_matches == 0 || n_out < pr.n_matches)) {
-      if (last >= 0) {
-        const fm_record lr = seg[idx[last]];
-        for (int k = lane; k < lr.length; k += 32) s_pat[k] = ix.tok[lr.reserved[0] + k];
-        for (int k = lane; k < lr.length; k += 32) s_pen[k] = 0.f;
+    const int p0 = prior ? prior_off[q] : 0, n_prior = prior ? prior_off[q + 1] - p0 : 0;
+    int n_out = 0, remaining = n;
+    int n_pen = 0;  // penalties accumulated so far for every remaining candidate = entries of `matches` accounted for
+    int last = -1, j_prior = 0;
+    while (remaining > 0 && (pr.n_matches == 0 || n_out + n_prior < pr.n_matches)) {
+      while (last >= 0 || j_prior < n_prior) {
+        int o_start, o_len;
+        if (last >= 0) {
+          const fm_record lr = seg[idx[last]];
+          o_start = lr.reserved[0]; o_len = lr.length;
+          last = -1;
+        } else {
+          const int2 e = prior[p0 + j_prior++];
+          o_start = e.x; o_len = e.y;
+        }
+        for (int k = lane; k < o_len; k += 32) s_pat[k] = ix.tok[o_start + k];
+        for (int k = lane; k < o_len; k += 32) s_pen[k] = 0.f;
         __syncwarp();
         for (int i = 0; i < n; i++) {
           const fm_record cr = seg[idx[i]];
           if (cr.reserved[2]) continue;  // already selected
           for (int k = lane; k < cr.length; k += 32) s_sent[k] = ix.tok[cr.reserved[0] + k];
           __syncwarp();
-          const float wdiff = __fdiv_rn(100.f, normalizer(cr.length, lr.length, unit));
+          const float wdiff = __fdiv_rn(100.f, normalizer(cr.length, o_len, unit));
           float C, K;
-          warp_edit_distance<false>(s_sent, cr.length, s_pat, lr.length, s_pen, s_up, wdiff, wdiff, wdiff, C, K, RealSide{});
+          warp_edit_distance<false>(s_sent, cr.length, s_pat, o_len, s_pen, s_up, wdiff, wdiff, wdiff, C, K, RealSide{});
           if (lane == 0) {
             const float pen = score_of(C);
             float acc = __int_as_float(cr.reserved[1]);
-            if (pr.reduce == 1) acc = (n_sel == 1 || pen > acc) ? pen : acc;
+            if (pr.reduce == 1) acc = (n_pen == 0 || pen > acc) ? pen : acc;
             else acc = __fadd_rn(acc, pen);
             seg[idx[i]].reserved[1] = __float_as_int(acc);
           }
         }
+        n_pen++;
         __syncwarp();
       }
       int best = -1;
@@ -2131,25 +2143,62 @@ __global__ void __launch_bounds__(256) fm_contrast_kernel(IndexDev ix, fm_record
           const fm_record cr = seg[idx[i]];
           if (cr.reserved[2]) continue;
           const float acc = __int_as_float(cr.reserved[1]);
-          const float pen = n_sel == 0 ? 0.f : (pr.reduce == 1 ? acc : __fdiv_rn(acc, (float)n_sel));
+          const float pen = n_pen == 0 ? 0.f : (pr.reduce == 1 ? acc : __fdiv_rn(acc, (float)n_pen));
           const float key = __fsub_rn(cr.rowmin_max, __fmul_rn(pr.contrast, pen));
           if (best < 0 || best_key < key) { best = i; best_key = key; }
         }
         const fm_record br = seg[idx[best]];
         const float acc = __int_as_float(br.reserved[1]);
-        const float pen = n_sel == 0 ? 0.f : (pr.reduce == 1 ? acc : __fdiv_rn(acc, (float)n_sel));
+        const float pen = n_pen == 0 ? 0.f : (pr.reduce == 1 ? acc : __fdiv_rn(acc, (float)n_pen));
         if (n_out < cap) out[(long long)q * cap + n_out] = to_match(br, pen);
         seg[idx[best]].reserved[2] = 1;
       }
       best = __shfl_sync(FULL, best, 0);
       last = best;
-      n_out++; n_sel++; remaining--;
+      n_out++; remaining--;
       __syncwarp();
     }
     if (lane == 0) {
       out_count[q] = n_out;
       if (n_out) atomicAdd(&ctr->n_matches, (unsigned)n_out);
     }
+  }
+}
+
+// Contrastive rerank on a sharded TM (the accepted records of all shards are on every rank, the sentences are not):
+// every rank lays out one token slab in the order of the merged accepted lists -- tok_cnt[q] = tokens of the accepted
+// sentences of query q, scanned into tok_base -- fills the sentences it owns and leaves zeros elsewhere; the sum over
+// the ranks (one all-reduce) is the slab the rerank kernel reads instead of the index's token array.
+__global__ void fm_contrast_need_kernel(const fm_record* __restrict__ rec, const int32_t* __restrict__ q_base,
+                                        const int32_t* __restrict__ sort_idx, const int32_t* __restrict__ acc_cnt, int n_q,
+                                        int32_t* tok_cnt) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_q) return;
+  const fm_record* seg = rec + q_base[q];
+  const int32_t* idx = sort_idx + q_base[q];
+  int c = 0;
+  for (int i = 0; i < acc_cnt[q]; i++) c += seg[idx[i]].length;
+  tok_cnt[q] = c;
+}
+__global__ void __launch_bounds__(256) fm_contrast_fill_kernel(IndexDev ix, long long n_sent_local, fm_record* rec,
+                                                               const int32_t* __restrict__ q_base, const int32_t* __restrict__ sort_idx,
+                                                               const int32_t* __restrict__ acc_cnt, const int32_t* __restrict__ tok_base,
+                                                               int n_q, int32_t* slab) {
+  const int lane = threadIdx.x & 31;
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= n_q) return;
+  fm_record* seg = rec + q_base[q];
+  const int32_t* idx = sort_idx + q_base[q];
+  int off = tok_base[q];
+  for (int i = 0; i < acc_cnt[q]; i++) {
+    const fm_record r = seg[idx[i]];
+    const long long local = (long long)r.s_id - (long long)ix.sid_base;
+    if (local >= 0 && local < n_sent_local) {
+      const int start = ix.sent_start[local];
+      for (int k = lane; k < r.length; k += 32) slab[off + k] = ix.tok[start + k];
+    }
+    if (lane == 0) seg[idx[i]].reserved[0] = off;  // where the rerank finds the sentence
+    off += r.length;
   }
 }
 
@@ -2541,16 +2590,24 @@ void launch_replay(const IndexDev& ix, const fm_record* rec, const int32_t* q_cn
 }
 void launch_contrast(const IndexDev& ix, fm_record* rec, const int32_t* q_base, const int32_t* sort_idx,
                      const int32_t* acc_cnt, int32_t n_q, const Params& p, int64_t cap, fm_match* out, int32_t* out_count, Counters* ctr, int sm_count,
-                     cudaStream_t st) {
+                     cudaStream_t st, const int2* prior, const int32_t* prior_off) {
   const int stride = dp_stride(ix);
   const size_t smem = (size_t)8 * 4 * stride * sizeof(int);
   static SmemOptIn opt_contrast;
   opt_contrast.ensure(fm_contrast_kernel, 200 * 1024);
   int grid = (n_q + 7) / 8;
   if (grid > sm_count * 4) grid = sm_count * 4;
-  fm_contrast_kernel<<<grid, 256, smem, st>>>(ix, rec, q_base, sort_idx, acc_cnt, n_q, p, (long long)cap, out, out_count, ctr, stride);
+  fm_contrast_kernel<<<grid, 256, smem, st>>>(ix, rec, q_base, sort_idx, acc_cnt, n_q, p, (long long)cap, out, out_count, ctr, stride, prior, prior_off);
 }
 
+void launch_contrast_need(const fm_record* rec, const int32_t* q_base, const int32_t* sort_idx, const int32_t* acc_cnt, int32_t n_q,
+                          int32_t* tok_cnt, cudaStream_t st) {
+  fm_contrast_need_kernel<<<(n_q + 255) / 256, 256, 0, st>>>(rec, q_base, sort_idx, acc_cnt, n_q, tok_cnt);
+}
+void launch_contrast_fill(const IndexDev& ix, int64_t n_sent_local, fm_record* rec, const int32_t* q_base, const int32_t* sort_idx,
+                          const int32_t* acc_cnt, const int32_t* tok_base, int32_t n_q, int32_t* slab, cudaStream_t st) {
+  fm_contrast_fill_kernel<<<(n_q + 7) / 8, 256, 0, st>>>(ix, (long long)n_sent_local, rec, q_base, sort_idx, acc_cnt, tok_base, n_q, slab);
+}
 void launch_subseq(const IndexDev& ix, const int32_t* q_tok, const int32_t* q_off, int32_t n_q, int n_matches, int no_perfect, int ml, float mr,
                    int idf_weighting, uint32_t* seen, int seen_cap, fm_subseq* out, cudaStream_t st) {
   const int stride = dp_stride(ix);

@@ -87,7 +87,8 @@ class FuzzyMatch:
     def match(self, pattern, fuzzy, number_of_matches, matches, min_subseq_length=2, min_subseq_ratio=0.0,
               vocab_idf_penalty=0.0, edit_costs=EditCosts(), contrastive_factor=0.0, reduce=ContrastReduce.MEAN,
               contrast_buffer=-1, no_perfect=False):
-        """Appends to `matches` and returns len(matches) > 0, like the reference."""
+        """Appends to `matches` and returns len(matches) > 0, like the reference: entries already in `matches` count
+        against number_of_matches and take part in the contrastive penalties (src/fuzzy_match.cc:626-679)."""
         self.match_batch([pattern], fuzzy, number_of_matches, [matches], min_subseq_length, min_subseq_ratio,
                          vocab_idf_penalty, edit_costs, contrastive_factor, reduce, contrast_buffer, no_perfect)
         return len(matches) > 0
@@ -109,8 +110,14 @@ class FuzzyMatch:
                                   contrast=contrastive_factor, reduce=int(reduce), buffer=contrast_buffer,
                                   no_perfect=no_perfect)
         cap = max(1, number_of_matches) if number_of_matches > 0 else 64
+        prior_off = np.zeros(len(wids) + 1, dtype=np.int64)
+        np.cumsum([len(m) for m in matches_out], out=prior_off[1:])
+        prior_sid = np.fromiter((m.s_id for ms in matches_out for m in ms), dtype=np.uint32, count=int(prior_off[-1]))
         while True:
-            out, cnt = self._index.match_batch(q_tok, q_off, cap=cap, params=params)
+            if prior_off[-1]:
+                out, cnt = self._index.match_batch_prior(q_tok, q_off, prior_sid, prior_off, cap=cap, params=params)
+            else:
+                out, cnt = self._index.match_batch(q_tok, q_off, cap=cap, params=params)
             if len(cnt) == 0 or cnt.max() <= cap:
                 break
             cap = int(cnt.max())  # number_of_matches == 0 returns everything: rerun with room for it

@@ -118,6 +118,14 @@ int fm_match_batch_real(fm_index* index, const int32_t* q_tokens, const int32_t*
 int fm_match_batch(fm_index* index, const int32_t* q_tokens, const int64_t* q_off, int64_t n_q,
                    const fm_params* params, int64_t cap, fm_match* out, int32_t* out_count);
 
+/* match() into result vectors that already hold matches. The reference APPENDS to `matches` (src/fuzzy_match.cc:626-679):
+ * entries that are there before the call count against number_of_matches, and the contrastive rerank penalises every
+ * candidate against them as well (:634-652), in vector order before the matches it selects itself. prior_sid[prior_off[q]
+ * .. prior_off[q+1]) are the sentence ids (of this index) already in the vector of query q; out / out_count receive what
+ * the call appends. With empty prior lists this is fm_match_batch. */
+int fm_match_batch_prior(fm_index* index, const int32_t* q_tokens, const int64_t* q_off, int64_t n_q, const fm_params* params,
+                         const uint32_t* prior_sid, const int64_t* prior_off, int64_t cap, fm_match* out, int32_t* out_count);
+
 /* FuzzyMatch::subsequence (fuzzy_match.hh:96-102, src/fuzzy_match.cc:238-365) behind its tokenizer, for a batch of
  * patterns (host CSR): the sub-sequences of a pattern are tried by weight -- length, or summed IDF with idf_weighting --
  * until one occurs in a sentence that no_perfect does not skip; among the first number_of_matches sentences of its
@@ -190,7 +198,8 @@ int fm_shard_accept_device(fm_index* shard, const int32_t* d_q_tokens, const int
  * candidate loop (bound heap, top-N). total_capacity = sum of the blocks' capacities. If a shard accepted more
  * records than its block holds, *need_capacity = the largest total of one shard and the results are not written:
  * rerun both halves with blocks of at least that capacity (otherwise 0). `index` only provides the device and a
- * workspace (any shard). Contrastive rerank needs the sentences behind the records: FM_ERR_INVALID. */
+ * workspace (any shard). Contrastive rerank needs the sentences behind the records: FM_ERR_INVALID here (the NCCL
+ * entry points below gather them). */
 int fm_merge_accepted_device(fm_index* index, int n_shards, const void* const* d_blocks, int64_t total_capacity,
                              const int32_t* d_q_off, int64_t n_q, const fm_params* params, int64_t cap, fm_match* d_out,
                              int32_t* d_out_count, int64_t* need_capacity, void* stream);
@@ -207,7 +216,10 @@ void fm_comm_destroy(fm_comm* comm);
 /* One batch against the sharded TM: every rank passes the same queries (device) and gets the complete result
  * in d_out / d_out_count. Collective; returns after the stream has finished. The block capacity follows the
  * number of records recent batches accepted; a batch that needs more is rerun by all ranks together, as is a
- * batch during which some rank had to regrow its workspace. */
+ * batch during which some rank had to regrow its workspace.
+ * Contrastive rerank (src/fuzzy_match.cc:613-669) compares the accepted sentences with each other: their tokens
+ * (the accepted ones only) are gathered behind the merged replay -- every rank fills the sentences it owns into one
+ * slab laid out by the merged lists, one ncclAllReduce sums the slabs -- and every rank reranks on the slab. */
 int fm_match_batch_sharded_device(fm_index* shard, fm_comm* comm, const int32_t* d_q_tokens, const int32_t* d_q_off,
                                   int64_t n_q, int64_t n_query_tokens, const fm_params* params, int64_t cap,
                                   fm_match* d_out, int32_t* d_out_count, void* stream);

@@ -128,6 +128,19 @@ class OracleIndex:
             return res, cnt, dict(zip(COUNTER_NAMES, list(ct)))
         return res, cnt
 
+    def match_batch_prior(self, q_tokens, q_off, prior_sid, prior_off, cap=16, **kw):
+        """fmo_match_batch_prior: match() into result vectors that already hold the sentences prior_sid (CSR per query)."""
+        q_tokens, q_off = _csr(q_tokens, q_off)
+        prior_sid = np.ascontiguousarray(prior_sid, dtype=np.uint32)
+        prior_off = np.ascontiguousarray(prior_off, dtype=np.int64)
+        n_q = len(q_off) - 1
+        p = make_params(Params, **kw)
+        out = np.zeros(n_q * cap, dtype=MATCH_DTYPE)
+        cnt = np.zeros(n_q, dtype=np.int32)
+        self.lib.fmo_match_batch_prior(self.h, _ptr(q_tokens), _ptr(q_off), C.c_int64(n_q), C.byref(p), _ptr(prior_sid), _ptr(prior_off),
+                                       C.c_int64(cap), _ptr(out), _ptr(cnt))
+        return _split(out, cnt, cap), cnt
+
     def set_real(self, real, gaps, off, itok_blob, itok_off):
         """Attach real tokens / penalty tokens (Sentence API) to the indexed sentences."""
         real = np.ascontiguousarray(real, dtype=np.int32)
@@ -229,6 +242,20 @@ class RefIndex:
                                                             C.c_int64(n_q), C.byref(p), C.c_int(int(no_perfect)), C.c_int(nthreads),
                                                             C.c_int64(cap), _ptr(out), _ptr(cnt), _ptr(self._itok[0]), _ptr(self._itok[1]))
         return _scrub_uninitialised_penalty(_split(out, cnt, cap)), cnt
+
+    def match_batch_twice(self, q1_tokens, q1_off, q2_tokens, q2_off, params1, params2, cap=16):
+        """Per query: matches = []; match(pattern 1, **params1, matches); match(pattern 2, **params2, matches).
+        Returns (prior lists, prior counts, appended lists, appended counts)."""
+        q1_tokens, q1_off = _csr(q1_tokens, q1_off)
+        q2_tokens, q2_off = _csr(q2_tokens, q2_off)
+        n_q = len(q1_off) - 1
+        assert len(q2_off) - 1 == n_q
+        p1, p2 = make_params(RefParams, **params1), make_params(RefParams, **params2)
+        pri, out = np.zeros(n_q * cap, dtype=REF_MATCH_DTYPE), np.zeros(n_q * cap, dtype=REF_MATCH_DTYPE)
+        pcnt, cnt = np.zeros(n_q, dtype=np.int32), np.zeros(n_q, dtype=np.int32)
+        self.lib.fmref_match_batch_twice(self.h, _ptr(q1_tokens), _ptr(q1_off), _ptr(q2_tokens), _ptr(q2_off), C.c_int64(n_q), C.byref(p1),
+                                         C.byref(p2), C.c_int64(cap), _ptr(pri), _ptr(pcnt), _ptr(out), _ptr(cnt))
+        return _split(pri, pcnt, cap), pcnt, _split(out, cnt, cap), cnt
 
     def subsequence_batch(self, q_tokens, q_off, n=1, no_perfect=False, ml=3, mr=0.3, idf_weighting=False):
         """FuzzyMatch::subsequence(string, ...) of the reference per pattern -> (records, texts): texts[q] is the

@@ -498,6 +498,9 @@ typedef struct scratch_t {
   float* dp; int64_t dp_cap;
   float* idf; int32_t* pat; int64_t pat_cap;
   float* pen_sum; float* pen_max; int32_t* pen_n;
+  /* sentence ids already in the caller's `matches` vector when match() is called (the reference appends, counts them
+   * against number_of_matches and penalises the contrastive candidates against them, src/fuzzy_match.cc:626-679) */
+  const uint32_t* prior; int64_t n_prior;
 } scratch_t;
 
 static void hmap_reset(scratch_t* sc) {
@@ -736,20 +739,26 @@ static int64_t match_one(const fmo_index* ix, const int32_t* pattern_in, const i
     unit_costs.insert_cost = unit_costs.delete_cost = unit_costs.replace_cost = 1.f; /* :630 */
     const fmo_match* last = NULL;
     fmo_match last_copy;
-    while (remaining > 0 && (number_of_matches == 0 || (uint64_t)n_out < number_of_matches)) {
-      if (last) { /* rescore penalties against the newly selected match (the older ones are memoised) */
+    /* penalties are accumulated in the order of `matches`: the entries that were there before the call first
+     * (j < n_prior), then the matches selected by this call (last) */
+    int64_t j_prior = 0;
+    while (remaining > 0 && (number_of_matches == 0 || (uint64_t)(n_out + sc->n_prior) < number_of_matches)) {
+      while (last || j_prior < sc->n_prior) { /* rescore penalties against the entries not yet accounted for (the older ones are memoised) */
+        const uint32_t other = last ? last->s_id : sc->prior[j_prior];
+        const int32_t other_len = last ? last->length : (int32_t)(ix->sent_pos[other + 1] - ix->sent_pos[other] - 1);
         for (int64_t i = 0; i < remaining; i++) {
           fmo_match* m = &sc->res[i];
           const int32_t* a = ix->buf + ix->sent_pos[m->s_id];
-          const int32_t* b = ix->buf + ix->sent_pos[last->s_id];
-          const float dw = 100.f / get_normalizer(m->length, last->length, &unit_costs); /* Costs(c.len, m.len, EditCosts()) */
-          float pen = edit_distance_plain(a, m->length, b, last->length, 1.f, 1.f, 1.f, dw, sc->dp);
+          const int32_t* b = ix->buf + ix->sent_pos[other];
+          const float dw = 100.f / get_normalizer(m->length, other_len, &unit_costs); /* Costs(c.len, m.len, EditCosts()) */
+          float pen = edit_distance_plain(a, m->length, b, other_len, 1.f, 1.f, 1.f, dw, sc->dp);
           pen = (float)((int)(10000 - pen * 100) / 10000.0);
           sc->pen_sum[i] = sc->pen_sum[i] + pen;
           sc->pen_max[i] = (sc->pen_n[i] == 0 || pen > sc->pen_max[i]) ? pen : sc->pen_max[i];
           sc->pen_n[i]++;
           m->penalty = pr->contrast_reduce == 1 ? sc->pen_max[i] : sc->pen_sum[i] / (float)sc->pen_n[i];
         }
+        if (last) last = NULL; else j_prior++;
       }
       int64_t best = 0; /* std::max_element: first maximum in list order */
       for (int64_t i = 1; i < remaining; i++) {
@@ -768,7 +777,7 @@ static int64_t match_one(const fmo_index* ix, const int32_t* pattern_in, const i
       remaining--;
     }
   } else { /* src/fuzzy_match.cc:670-679 */
-    for (int64_t i = 0; i < n_res && (number_of_matches == 0 || (uint64_t)n_out < number_of_matches); i++) {
+    for (int64_t i = 0; i < n_res && (number_of_matches == 0 || (uint64_t)(n_out + sc->n_prior) < number_of_matches); i++) {
       if (out && n_out < cap) out[n_out] = sc->res[i];
       n_out++;
     }
@@ -783,6 +792,7 @@ typedef struct job_t {
   const fmo_index* ix;
   const int32_t* q_tokens; const int64_t* q_off; int64_t n_q;
   const int32_t* q_real; const int32_t* q_gaps; /* optional (Sentence API) */
+  const uint32_t* prior_sid; const int64_t* prior_off; /* optional: entries already in `matches` per query (CSR) */
   const fmo_params* pr;
   int64_t cap; fmo_match* out; int32_t* out_count;
   int64_t next; pthread_mutex_t mu;
@@ -799,6 +809,8 @@ static void* worker(void* arg) {
     if (q0 >= jb->n_q) break;
     const int64_t q1 = q0 + 16 < jb->n_q ? q0 + 16 : jb->n_q;
     for (int64_t q = q0; q < q1; q++) {
+      sc.prior = jb->prior_sid ? jb->prior_sid + jb->prior_off[q] : NULL;
+      sc.n_prior = jb->prior_sid ? jb->prior_off[q + 1] - jb->prior_off[q] : 0;
       const int64_t n = match_one(jb->ix, jb->q_tokens + jb->q_off[q], jb->q_real ? jb->q_real + jb->q_off[q] : NULL,
                                   jb->q_gaps ? jb->q_gaps + jb->q_off[q] + q : NULL, jb->q_off[q + 1] - jb->q_off[q], jb->pr, &sc,
                                   jb->out ? jb->out + q * jb->cap : NULL, jb->cap, jb->want_counters ? &ct : NULL, NULL, 0, NULL);
@@ -843,6 +855,18 @@ void fmo_match_batch_real(const fmo_index* ix, const int32_t* q_tokens, const in
     free(th);
   }
   if (counters) *counters = jb.total;
+  pthread_mutex_destroy(&jb.mu);
+}
+
+/* match(Tokens) into result vectors that already hold matches of the same TM: prior_sid[prior_off[q] .. prior_off[q+1])
+ * are their sentence ids in vector order. Returns per query what the call appends (src/fuzzy_match.cc:626-679). */
+void fmo_match_batch_prior(const fmo_index* ix, const int32_t* q_tokens, const int64_t* q_off, int64_t n_q, const fmo_params* pr,
+                           const uint32_t* prior_sid, const int64_t* prior_off, int64_t cap, fmo_match* out, int32_t* out_count) {
+  job_t jb; memset(&jb, 0, sizeof jb);
+  jb.ix = ix; jb.q_tokens = q_tokens; jb.q_off = q_off; jb.n_q = n_q; jb.pr = pr; jb.prior_sid = prior_sid; jb.prior_off = prior_off;
+  jb.cap = cap; jb.out = out; jb.out_count = out_count;
+  pthread_mutex_init(&jb.mu, NULL);
+  worker(&jb);
   pthread_mutex_destroy(&jb.mu);
 }
 

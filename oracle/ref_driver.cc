@@ -213,6 +213,37 @@ void fmref_subsequence_batch(void* h, const int32_t* q_tokens, const int64_t* q_
   }
 }
 
+// match(Tokens) into a result vector that already holds matches: for every query the vector is first filled by
+// match(first pattern, p1) and then handed, as it is, to match(second pattern, p2) -- the reference appends, counts the
+// earlier entries against number_of_matches and penalises contrastive candidates against them
+// (src/fuzzy_match.cc:626-679). prior_* receive the entries of the first call, out_* what the second call appended.
+void fmref_match_batch_twice(void* h, const int32_t* q1_tokens, const int64_t* q1_off, const int32_t* q2_tokens, const int64_t* q2_off,
+                             int64_t n_q, const fmref_params* p1, const fmref_params* p2, int64_t cap, fmref_match* prior,
+                             int32_t* prior_count, fmref_match* out, int32_t* out_count) {
+  auto* r = static_cast<RefHandle*>(h);
+  auto call = [&](const fuzzy::Tokens& pat, const fmref_params* p, std::vector<fuzzy::FuzzyMatch::Match>& matches) {
+    const fuzzy::EditCosts costs(p->insert_cost, p->delete_cost, p->replace_cost);
+    r->fm.match(pat, p->fuzzy, (unsigned)p->number_of_matches, matches, p->min_subseq_length, p->min_subseq_ratio, p->vocab_idf_penalty,
+                costs, p->contrastive_factor, p->contrast_reduce ? fuzzy::ContrastReduce::MAX : fuzzy::ContrastReduce::MEAN,
+                p->contrast_buffer);
+  };
+  auto store = [&](const fuzzy::FuzzyMatch::Match& m, fmref_match& o, bool penalty_valid) {
+    o.s_id = m.s_id; o.score = m.score; o.penalty = penalty_valid ? m.penalty : 0.f; o.max_subseq = m.max_subseq; o.length = m.length;
+  };
+  for (int64_t q = 0; q < n_q; q++) {
+    std::vector<fuzzy::FuzzyMatch::Match> matches;
+    call(to_tokens(q1_tokens + q1_off[q], q1_off[q + 1] - q1_off[q]), p1, matches);
+    const size_t n1 = matches.size();
+    prior_count[q] = (int32_t)n1;
+    for (size_t k = 0; k < n1 && (int64_t)k < cap; k++) store(matches[k], prior[q * cap + (int64_t)k], false);
+    call(to_tokens(q2_tokens + q2_off[q], q2_off[q + 1] - q2_off[q]), p2, matches);
+    out_count[q] = (int32_t)(matches.size() - n1);
+    // Match::penalty of an appended entry is computed iff the rerank ran with a non-empty vector (:634-662)
+    for (size_t k = n1; k < matches.size() && (int64_t)(k - n1) < cap; k++)
+      store(matches[k], out[q * cap + (int64_t)(k - n1)], p2->contrastive_factor > 0 && k > 0);
+  }
+}
+
 int64_t fmref_max_tokens_in_pattern(void* h) { return (int64_t) static_cast<RefHandle*>(h)->fm.max_tokens_in_pattern(); }
 
 }  // extern "C"

@@ -135,9 +135,29 @@ static void batch_and_append() {
   EXPECT(m.size() == 2 && m[1].s_id == 2);
   EXPECT(fm.match(split("a b c d e"), 0.5, 0, m));  // 0 = all
   EXPECT(m.size() == 4);
-  bool refused = false;
-  try { fm.match(split("a b c d e"), 0.5, 0, m, 2, 0, 0, fuzzy::EditCosts(), 0.5f); } catch (const std::logic_error&) { refused = true; }
-  EXPECT(refused);  // contrastive rerank against earlier entries is refused, not answered differently
+}
+
+static void contrastive_into_nonempty_vector() {
+  // The contrastive rerank penalises the candidates against entries that are in `matches` before the call
+  // (reference src/fuzzy_match.cc:634-652). Expected values: the live reference on the same two calls
+  // (oracle/ref_driver.cc fmref_match_batch_twice).
+  fuzzy::FuzzyMatch fm;
+  add(fm, "a b c d e"); add(fm, "a b c d e f"); add(fm, "x y z"); add(fm, "a b c x y");
+  fm.sort();
+  std::vector<fuzzy::FuzzyMatch::Match> m;
+  EXPECT(fm.match(split("a b c d e"), 0.9f, 1, m));
+  EXPECT(m.size() == 1 && m[0].s_id == 0);
+  std::vector<fuzzy::FuzzyMatch::Match> m3 = m;
+  EXPECT(fm.match(split("a b c d"), 0.3f, 0, m, 2, 0, 0, fuzzy::EditCosts(), 0.5f));
+  EXPECT(m.size() == 4);
+  if (m.size() == 4) {
+    EXPECT(m[1].s_id == 0); EXPECT_NEAR(m[1].score, 0.8f, 1e-6); EXPECT_NEAR(m[1].penalty, 1.0f, 1e-6);
+    EXPECT(m[2].s_id == 3); EXPECT_NEAR(m[2].score, 0.6f, 1e-6); EXPECT_NEAR(m[2].penalty, 0.6f, 1e-6);  // ahead of the better-scoring s1
+    EXPECT(m[3].s_id == 1); EXPECT_NEAR(m[3].score, 0.6666f, 1e-6); EXPECT_NEAR(m[3].penalty, 0.7222f, 1e-6);
+  }
+  EXPECT(fm.match(split("a b c d"), 0.3f, 3, m3, 2, 0, 0, fuzzy::EditCosts(), 0.5f, fuzzy::ContrastReduce::MAX));
+  EXPECT(m3.size() == 3);  // the earlier entry counts against number_of_matches
+  if (m3.size() == 3) { EXPECT(m3[1].s_id == 0 && m3[2].s_id == 3); EXPECT_NEAR(m3[2].penalty, 0.6f, 1e-6); }
 }
 
 static void sentence_api() {
@@ -214,6 +234,7 @@ int main() {
   idf_weight();
   contrastive();
   batch_and_append();
+  contrastive_into_nonempty_vector();
   sentence_api();
   std::printf(failures ? "%d FAILURES\n" : "all adapter tests passed\n", failures);
   return failures ? 1 : 0;

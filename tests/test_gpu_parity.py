@@ -511,3 +511,26 @@ def test_subsequence_degenerate_inputs():
     assert len(index.subsequence_batch(*csr([]), n=1)) == 0
     with pytest.raises(fmb.FuzzyMatchError):  # longer than max_tokens_in_pattern: refused, never silently unmatched
         index.subsequence_batch(*csr([list(range(2, 12)) * 40]), n=1)
+
+
+def test_match_into_nonempty_result_vectors():
+    """fm_match_batch_prior: entries already in `matches` (src/fuzzy_match.cc:626-679) against the oracle, whose prior
+    handling is pinned to the live reference in tests/test_oracle.py."""
+    from tests.test_oracle import PRIOR_PARAM_PAIRS
+    for seed, vocab in [(0, 30), (1, 200), (2, 12), (3, 5000)]:
+        tm, off, V = synth.make_tm(20000 if vocab == 5000 else 3000, vocab=vocab, seed=seed)
+        q1, q1o = synth.make_queries(tm, off, 300, vocab=vocab, seed=seed + 100)
+        q2, q2o = synth.make_queries(tm, off, 300, vocab=vocab, seed=seed + 100, p_sub=0.2)
+        index, oracle = fmb.Index(tm, off, V), ob.OracleIndex(tm, off, V)
+        for p1, p2 in PRIOR_PARAM_PAIRS:
+            first, fcnt = index.match_batch(q1, q1o, cap=64, **p1)
+            poff = np.zeros(len(fcnt) + 1, dtype=np.int64)
+            np.cumsum(np.minimum(fcnt, 64), out=poff[1:])
+            psid = np.concatenate([first[i, :min(fcnt[i], 64)]["s_id"] for i in range(len(fcnt))] + [np.zeros(0, np.uint32)]).astype(np.uint32)
+            got, gcnt = index.match_batch_prior(q2, q2o, psid, poff, cap=64, **p2)
+            want, wcnt = oracle.match_batch_prior(q2, q2o, psid, poff, cap=64, **p2)
+            assert (gcnt == wcnt).all()
+            for i in range(len(wcnt)):
+                assert as_tuples(got[i, :min(gcnt[i], 64)], True) == as_tuples(want[i], True), (p2, i)
+    with pytest.raises(fmb.FuzzyMatchError):  # a sentence id the index does not hold
+        index.match_batch_prior(q2[:q2o[1]], q2o[:2], np.array([10 ** 9], dtype=np.uint32), np.array([0, 1]), fuzzy=0.5, n=2, contrast=0.5)

@@ -202,4 +202,4 @@ def test_sharded_tm_over_nccl_two_gpus():
                           "--master-port", "29731", os.path.join(ROOT, "tools", "check_sharded_nccl.py")],
                          cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "identical to oracle: False" not in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
-    assert out.stdout.count("identical to oracle: True") >= 3
+    assert out.stdout.count("identical to oracle: True") >= 6  # three of them contrastive

@@ -192,3 +192,32 @@ def test_oracle_subsequence_matches_live_reference(seed, vocab):
             assert a[i]["s_id"] == b[i]["s_id"] and a[i]["score"].tobytes() == b[i]["score"].tobytes() and a[i]["length"] == b[i]["max_subseq"]
             lo = qo[i] + a[i]["position"]
             assert " ".join(str(x) for x in q[lo:lo + a[i]["length"]]) == texts[i]  # what the reference appends to Match::id
+
+
+# ---- match() into a non-empty result vector (src/fuzzy_match.cc:626-679): earlier entries count against
+# number_of_matches and the contrastive rerank penalises the candidates against them
+PRIOR_PARAM_PAIRS = [(dict(fuzzy=0.5, n=3, ml=2), dict(fuzzy=0.4, n=6, ml=2, contrast=0.5)),
+                     (dict(fuzzy=0.5, n=2, ml=2, contrast=0.3), dict(fuzzy=0.3, n=5, ml=2, contrast=0.8, reduce=1, buffer=10)),
+                     (dict(fuzzy=0.5, n=2, ml=2), dict(fuzzy=0.3, n=4, ml=2)),
+                     (dict(fuzzy=0.5, n=4, ml=2), dict(fuzzy=0.3, n=3, ml=2, contrast=0.5)),
+                     (dict(fuzzy=0.8, n=0, ml=2), dict(fuzzy=0.75, n=0, ml=3, contrast=0.5, idf=1.0))]
+
+
+@pytest.mark.skipif(not ob.ref_available(), reason="oracle/_ref not built (no /root/reference here)")
+@pytest.mark.parametrize("seed,vocab", [(0, 30), (1, 200), (2, 12)])
+def test_oracle_prior_matches_vs_live_reference(seed, vocab):
+    tm, off, V = synth.make_tm(3000, vocab=vocab, seed=seed)
+    q1, q1o = synth.make_queries(tm, off, 100, vocab=vocab, seed=seed + 100)
+    q2, q2o = synth.make_queries(tm, off, 100, vocab=vocab, seed=seed + 100, p_sub=0.2)  # same sources, perturbed differently
+    O, R = ob.OracleIndex(tm, off, V), ob.RefIndex(tm, off)
+    both = 0
+    for p1, p2 in PRIOR_PARAM_PAIRS:
+        pri, pcnt, out, cnt = R.match_batch_twice(q1, q1o, q2, q2o, p1, p2, cap=64)
+        poff = np.zeros(len(pcnt) + 1, dtype=np.int64)
+        np.cumsum(pcnt, out=poff[1:])
+        psid = np.array([m["s_id"] for r in pri for m in r], dtype=np.uint32)
+        o, ocnt = O.match_batch_prior(q2, q2o, psid, poff, cap=64, **p2)
+        assert (cnt == ocnt).all()
+        assert [as_tuples(r) for r in out] == [as_tuples(r) for r in o]
+        both += int(((pcnt > 0) & (cnt > 0)).sum())
+    assert both > 100  # the case under test occurs

@@ -22,7 +22,10 @@ def main():
     q, qo = synth.make_queries(tm, off, 3000, vocab=3000, seed=202, len_lo=1, len_hi=30)
     idx = ShardedIndex(tm, off, V, max_tokens=28, device=torch.device("cuda", local))
     ok = True
-    for params in (dict(fuzzy=0.5, n=4, ml=2), dict(fuzzy=0.4, n=3, ml=3, idf=1.0, costs=(1, 0, 1)), dict(fuzzy=0.7, n=1, ml=3)):
+    for params in (dict(fuzzy=0.5, n=4, ml=2), dict(fuzzy=0.4, n=3, ml=3, idf=1.0, costs=(1, 0, 1)), dict(fuzzy=0.7, n=1, ml=3),
+                   # contrastive rerank across shards: the accepted sentences travel in one all-reduced token slab
+                   dict(fuzzy=0.5, n=5, ml=2, contrast=0.5), dict(fuzzy=0.4, n=4, ml=2, idf=0.7, costs=(1, 0, 1), contrast=0.5, reduce=1, buffer=8),
+                   dict(fuzzy=0.3, n=0, ml=3, contrast=0.8)):
         out, cnt = idx.match_batch(q, qo, cap=8, **params)
         if rank == 0:
             from oracle import binding as ob
