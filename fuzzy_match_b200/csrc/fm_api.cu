@@ -555,6 +555,13 @@ static int match_batch_host(fm_index* index, const int32_t* q_tokens, const int6
   }
   if ((rc = check_params(params, &pr))) return rc;
   if (n_q == 0) return FM_OK;
+  if (ri.q_real) {  // every penalty-token id indexes the caller's n_itok x n_itok table on the device
+    if (ix->max_gap_id >= ri.n_itok) { set_error("penalty-token table smaller than the ids stored with the TM"); return FM_ERR_INVALID; }
+    const int64_t n_gap = q_off[n_q] - q_off[0] + n_q;
+    const int32_t* g = ri.q_gaps + q_off[0];
+    for (int64_t i = 0; i < n_gap; i++)
+      if (g[i] < 0 || g[i] >= ri.n_itok) { set_error("query penalty-token id outside the table"); return FM_ERR_INVALID; }
+  }
   FM_CUDA(cudaSetDevice(ix->device));
   // The batch is cut into chunks that run on up to kSlots workspaces / streams, so the H2D copy of
   // one chunk and the D2H copy of another overlap the kernels of a third. Chunks also keep the

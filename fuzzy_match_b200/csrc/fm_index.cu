@@ -173,6 +173,12 @@ int load_index(const char* path, int device, Index** out) {
       ix->blk_bytes[k] = (size_t)n;
       ix->device_bytes += n;
       if (k == BLK_TOK && ok) ix->h_tok.assign(reinterpret_cast<int32_t*>(buf.data()), reinterpret_cast<int32_t*>(buf.data()) + n / 4);
+      if (k == BLK_GAP && ok)  // penalty-token ids index the caller's table on the device: remember (and bound) the largest
+        for (int64_t i = 0; i < n / 4 && ok; i++) {
+          const int32_t g = reinterpret_cast<int32_t*>(buf.data())[i];
+          ok = g >= 0 && g < 2048;
+          if (g > ix->max_gap_id) ix->max_gap_id = g;
+        }
     }
     ix->h_sent_start.resize((size_t)ix->n_sent + 1);
     ix->kept.resize((size_t)ix->n_sent);
@@ -439,13 +445,18 @@ int set_real(Index* ix, const int32_t* real, const int32_t* gaps, const int64_t*
   for (int64_t k = 0; k < ix->n_sent; k++)
     if (ix->kept[k] >= n_sent) { set_error("sent_off does not match the CSR the index was built from"); return FM_ERR_INVALID; }
   std::vector<int32_t> h_real((size_t)ix->n_buf, 0), h_gap((size_t)ix->n_buf, 0);
+  ix->max_gap_id = 0;
   for (int64_t k = 0; k < ix->n_sent; k++) {
     const int64_t s = ix->kept[k], st = ix->h_sent_start[k];
     const int64_t n = sent_off[s + 1] - sent_off[s];
+    int64_t stored = 0;
+    while (ix->h_tok[(size_t)(st + stored)] != 0) stored++;
+    if (n != stored) { set_error("sent_off does not match the CSR the index was built from (sentence length differs)"); return FM_ERR_INVALID; }
     for (int64_t j = 0; j < n; j++) h_real[st + j] = real[sent_off[s] + j];
     for (int64_t j = 0; j <= n; j++) {
       const int32_t g = gaps[sent_off[s] + s + j];
       if (g < 0 || g >= 2048) { set_error("penalty-token id outside [0, 2048)"); return FM_ERR_INVALID; }
+      if (g > ix->max_gap_id) ix->max_gap_id = g;
       h_gap[st + j] = g;
     }
   }

@@ -290,6 +290,7 @@ struct Index {
   // workspaces
   std::mutex mu;
   std::vector<Workspace*> pool;
+  int32_t max_gap_id = 0;  // largest penalty-token id of the TM side (fm_index_set_real): the caller's table must cover it
   int32_t* d_sent_start = nullptr;  // device copy of h_sent_start (lazily, under mu)
   std::mutex shard_mu;  // the sharded calls of one index run one at a time (collectives must not interleave)
   bool profiling = false;
