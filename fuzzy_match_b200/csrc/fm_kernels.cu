@@ -283,10 +283,13 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
 // slice slots and flattened element offsets together, so slice order == element order. Buffering keeps
 // the number of same-address atomics near one per warp instead of one per warp and n-gram level.
 static const int kSliceBuf = 6;
+#ifndef FM_SEARCH_THREADS
+#define FM_SEARCH_THREADS 256  // CTA size of the search kernel (the CTA-wide flush waits for its slowest warp)
+#endif
 struct SliceBuf {
-  int beg[kSliceBuf][256];
-  int sz[kSliceBuf][256];
-  int lm[kSliceBuf][256];
+  int beg[kSliceBuf][FM_SEARCH_THREADS];
+  int sz[kSliceBuf][FM_SEARCH_THREADS];
+  int lm[kSliceBuf][FM_SEARCH_THREADS];
 };
 __device__ __forceinline__ void note_spans(const BatchDev& b, long long slot, long long start, int size) {
   // span_slice[k] = slice that holds flattened element k*kSpan
@@ -365,7 +368,7 @@ __device__ __forceinline__ void flush_slices(const BatchDev& b, SliceBuf& sb, in
 #ifndef FM_SEARCH_CTAS
 #define FM_SEARCH_CTAS 6
 #endif
-__global__ void __launch_bounds__(256, FM_SEARCH_CTAS) fm_search_kernel(IndexDev ix, BatchDev b) {
+__global__ void __launch_bounds__(FM_SEARCH_THREADS, FM_SEARCH_CTAS) fm_search_kernel(IndexDev ix, BatchDev b) {
   __shared__ SliceBuf sb;
   int nbuf = 0;
   const int lane = threadIdx.x & 31;
@@ -525,7 +528,7 @@ __global__ void __launch_bounds__(256, FM_SEARCH_CTAS) fm_search_kernel(IndexDev
     const unsigned long long low54 = (1ull << 54) - 1;
     if (threadIdx.x == 0) {
       unsigned long long tot = 0;
-      for (int k = 0; k < 8; k++) { const unsigned long long v = s_wtot[k]; s_wtot[k] = tot; tot += v; }
+      for (int k = 0; k < FM_SEARCH_THREADS / 32; k++) { const unsigned long long v = s_wtot[k]; s_wtot[k] = tot; tot += v; }
       s_base = (tot & low54) ? atomicAdd(&b.ctr->slice_elem, tot & low54) : 0ull;
       s_sbase = (tot >> 54) ? atomicAdd(&b.ctr->n_small, (unsigned)(tot >> 54)) : 0u;
     }
@@ -2488,8 +2491,8 @@ void launch_prepare(const IndexDev& ix, const BatchDev& b, const Params& p, cuda
   fm_prepare_kernel<<<grid, 256, 0, st>>>(ix, b, p);
 }
 void launch_search(const IndexDev& ix, const BatchDev& b, const Params&, cudaStream_t st) {
-  const int grid = (b.n_tok + 255) / 256;
-  if (grid > 0) fm_search_kernel<<<grid, 256, 0, st>>>(ix, b);
+  const int grid = (b.n_tok + FM_SEARCH_THREADS - 1) / FM_SEARCH_THREADS;
+  if (grid > 0) fm_search_kernel<<<grid, FM_SEARCH_THREADS, 0, st>>>(ix, b);
 }
 void launch_gather(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st, cudaEvent_t between) {
   // grids several times what is resident: CTAs that finish early make room for the next ones
