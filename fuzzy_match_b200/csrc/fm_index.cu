@@ -58,8 +58,8 @@ static int upload(const std::vector<T>& h, size_t extra, Index* ix, int blk, con
 // Boost binary archive, src/fuzzy_matcher_binarization.cc). Header, then the device blocks exactly as
 // they sit in HBM, then the host-side tables. Loading is read + upload: no sort, no hashing.
 static const char kMagic[8] = {'F', 'M', 'B', '2', '0', '0', 'I', 1};
-static const int64_t kFileVersion = 2;  // 2: wide signatures (walk records of long sentences carry a wsig row)
-enum { BLK_TOK = 0, BLK_SA = 1, BLK_WALK = 2, BLK_QVA = 3, BLK_SID = 4, BLK_IDF = 5, BLK_BG = 6, BLK_TG = 7, BLK_REAL = 8, BLK_GAP = 9, BLK_NEXT = 10, BLK_WSIG = 11, BLK_START = 12, N_BLK = 13 };
+static const int64_t kFileVersion = 3;  // 2: wide signatures (walk records of long sentences carry a wsig row); 3: sig2_at
+enum { BLK_TOK = 0, BLK_SA = 1, BLK_WALK = 2, BLK_QVA = 3, BLK_SID = 4, BLK_IDF = 5, BLK_BG = 6, BLK_TG = 7, BLK_REAL = 8, BLK_GAP = 9, BLK_NEXT = 10, BLK_WSIG = 11, BLK_START = 12, BLK_SIG2 = 13, N_BLK = 14 };
 
 static void bind_blocks(Index* ix) {
   IndexDev& d = ix->dev;
@@ -70,6 +70,7 @@ static void bind_blocks(Index* ix) {
   d.sa_next = static_cast<const int32_t*>(ix->d_blocks[BLK_NEXT]);
   d.qva = static_cast<const int32_t*>(ix->d_blocks[BLK_QVA]);
   d.sid_at = static_cast<const int32_t*>(ix->d_blocks[BLK_SID]);
+  d.sig2_at = static_cast<const uint2*>(ix->d_blocks[BLK_SIG2]);
   d.idf = static_cast<const float*>(ix->d_blocks[BLK_IDF]);
   d.bg_tab = static_cast<const int4*>(ix->d_blocks[BLK_BG]);
   d.tg_tab = static_cast<const int4*>(ix->d_blocks[BLK_TG]);
@@ -114,7 +115,9 @@ static bool header_ok(const int64_t* hdr, const int64_t* blk, int n_blk) {
   if (blk[BLK_TOK] != n_buf * 4 || blk[BLK_SA] < n_suf * 4 || blk[BLK_NEXT] < n_suf * 4 || blk[BLK_WALK] < (n_suf + 8) * 8 ||
       blk[BLK_START] < n_suf * 4)
     return false;
-  if (blk[BLK_QVA] != (vocab + 1) * 4 || blk[BLK_IDF] != vocab * 4 || blk[BLK_SID] != (n_buf / 4 + 1) * 4) return false;
+  if (blk[BLK_QVA] != (vocab + 1) * 4 || blk[BLK_IDF] != vocab * 4 || blk[BLK_SID] != (n_buf / 4 + 1) * 4 ||
+      blk[BLK_SIG2] != (n_buf / 4 + 1) * 8)
+    return false;
   if (blk[BLK_BG] != (bgm + 1) * 16 || blk[BLK_TG] != (tgm + 1) * 16) return false;
   if (blk[BLK_WSIG] % (kWideWords * 4) != 0 || blk[BLK_WSIG] / (kWideWords * 4) > n_sent) return false;
   if ((blk[BLK_REAL] != 0 && blk[BLK_REAL] != n_buf * 4) || blk[BLK_GAP] != blk[BLK_REAL]) return false;
@@ -232,15 +235,16 @@ int set_idf_stats(Index* ix, const uint32_t* sf, int64_t n_sent_global) {
 // owns a row), and its walk records carry that row number in place of the 64-bit signature.
 __global__ void fm_build_sentence_kernel(const int32_t* __restrict__ tok, const int32_t* __restrict__ sent_start, int n_sent,
                                          const int32_t* __restrict__ wide_row, uint32_t* wsig, unsigned long long* sig,
-                                         int32_t* sent_len, int32_t* sid_at) {
+                                         int32_t* sent_len, int32_t* sid_at, uint2* sig2_at) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_sent) return;
   const int st = sent_start[s];
   const int row = wide_row[s];
-  unsigned long long sg = 0;
+  unsigned long long sg = 0, sg2 = ~0ull;  // (long sentences are tested against their wide signature instead)
   int n = 0;
   if (row < 0) {
-    for (int t; (t = tok[st + n]) != 0; n++) sg |= 1ull << sig_bit(t);
+    sg2 = 0;
+    for (int t; (t = tok[st + n]) != 0; n++) { sg |= 1ull << sig_bit(t); sg2 |= 1ull << sig2_bit(t); }
     sg |= (unsigned long long)n;  // bits 0-5: the length (<= kWideMin < 63)
   } else {
     uint32_t* w = wsig + (size_t)row * kWideWords;
@@ -253,6 +257,7 @@ __global__ void fm_build_sentence_kernel(const int32_t* __restrict__ tok, const 
   sig[s] = sg;  // the walk record of every suffix of this sentence
   sent_len[s] = n;
   sid_at[st >> 2] = s;
+  sig2_at[st >> 2] = make_uint2((unsigned)sg2, (unsigned)(sg2 >> 32));
 }
 
 __global__ void fm_build_walk_kernel(const int32_t* __restrict__ sa_pos, long long n_suf, const int32_t* __restrict__ sent_start,
@@ -403,6 +408,7 @@ static int build_on_device(Index* ix, const std::vector<int32_t>& sent_start, co
   FM_CUDA(cudaMemcpy(d_start, sent_start.data(), (size_t)(n_sent + 1) * 4, cudaMemcpyHostToDevice));
   int rc;
   if ((rc = dev_alloc(ix, BLK_SID, (size_t)(ix->n_buf / 4) + 1, 0xff, &d.sid_at)) ||
+      (rc = dev_alloc(ix, BLK_SIG2, (size_t)(ix->n_buf / 4) + 1, 0xff, &d.sig2_at)) ||
       (rc = dev_alloc(ix, BLK_WALK, (size_t)n_suf + 8, 0, &d.sa_rec)) || (rc = dev_alloc(ix, BLK_START, (size_t)n_suf + 4, 0, &d.sa_start)) ||
       (rc = derive_next(ix)) ||
       (rc = dev_alloc(ix, BLK_WSIG, (size_t)n_wide * kWideWords, 0, &d.wsig)))
@@ -413,7 +419,7 @@ static int build_on_device(Index* ix, const std::vector<int32_t>& sent_start, co
   const unsigned gs = (unsigned)((n_suf + tb - 1) / tb);
   if (n_sent > 0)
     fm_build_sentence_kernel<<<(n_sent + tb - 1) / tb, tb>>>(d.tok, d_start, n_sent, d_wrow, const_cast<uint32_t*>(d.wsig), d_sig, d_len,
-                                                             const_cast<int32_t*>(d.sid_at));
+                                                             const_cast<int32_t*>(d.sid_at), const_cast<uint2*>(d.sig2_at));
   unsigned long long counts[2] = {0, 0};
   if (n_suf > 0) {
     fm_build_walk_kernel<<<gs, tb>>>(d.sa_pos, n_suf, d_start, n_sent, d_sig, const_cast<uint2*>(d.sa_rec), const_cast<int32_t*>(d.sa_start));

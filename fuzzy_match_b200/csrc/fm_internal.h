@@ -37,6 +37,8 @@ namespace fm {
 // wsig     uint32[n_wide*32] 1024-bit word signatures of the sentences longer than kWideMin tokens (a 64-bit
 //                         signature saturates there); their walk records carry the row number instead of the
 //                         64-bit signature. One row = one 128-byte line.
+// sig2_at  uint2[n_buf/4] second, independent 64-bit word signature per sentence, stored at (sentence start / 4): the
+//                         verify kernel tests it (8 bytes) before it fetches the sentence for the exact count.
 // idf      float[V]       logf(N / sfreq[w]) computed on the host with glibc (0 for unseen words).
 struct IndexDev {
   const int32_t* tok;
@@ -50,6 +52,7 @@ struct IndexDev {
   const int4* tg_tab;
   uint32_t tg_mask;
   const int32_t* sid_at;
+  const uint2* sig2_at;  // [n_buf/4] second 64-bit word signature of the sentence that starts at tok[4 k] (sig2_bit)
   const uint32_t* wsig;
   int32_t n_wide;
   const float* idf;
@@ -66,12 +69,20 @@ struct IndexDev {
 // per-query metadata written by the prepare kernel
 //   x = pattern length p (0 if the query is skipped), y = effective min_subseq_length,
 //   z = offset of the pattern in the token arrays,
-//   w = bit0: query takes part; bits 8..: max(0, (largest number of pattern positions on one signature bit) - 3)
+//   w = bit0: query takes part; bits 8..17: max(0, (largest number of pattern positions on one signature bit) - 3);
+//       bits 18..27: the same for the second signature
 typedef int4 QMeta;
 static const int kQValid = 1;
 
 // word -> signature bit 6..63 (must be identical on host and device); bits 0-5 of a record hold the length
 __host__ __device__ inline unsigned sig_bit(int w) { return 6u + (((((unsigned)w * 0x9E3779B1u) >> 16) * 58u) >> 16); }
+// second, independent word -> bit map (64 bits) of the per-sentence signature the verify kernel tests before it
+// fetches a sentence (sig2_at); must be identical on host and device
+__host__ __device__ inline unsigned sig2_bit(int w) {
+  unsigned x = (unsigned)w * 0x7FEB352Du;
+  x ^= x >> 15;
+  return (x * 0x846CA68Bu) >> 26;
+}
 // sentences longer than this carry a 1024-bit signature (wsig) instead of the 64-bit one
 static const int kWideMin = 48;
 static const int kWideWords = 32;  // 32-bit words per wide signature
@@ -147,6 +158,7 @@ struct BatchDev {
   int2* tbl;         // [4*n_tok] per-query open-addressing tables: (word, distinct_idx | count<<16)
   const uint16_t* cmin_tab; // [(max_tokens+1) << 10] per (pattern length << 10 | sentence length): smallest coverage that passes
   const uint16_t* cmin64;   // [(max_tokens+1) << 6] the same for the 6-bit length field of a walk record (stage 1 of the gather)
+  int4* qmask2;      // [n_q] the same planes over the 64 bits of the second signature (sig2_bit); its mult sits in qmeta.w bits 18..27
   int4* qmask;       // [n_q] per query, in record layout: planes (B0 lo, B0 hi, B1 lo, B1 hi) of min(pattern positions per signature bit, 3)
   uint32_t* wq;      // [kWideStride*n_q] or NULL (index without wide signatures): planes and excess list over the 1024 wide bits
   unsigned long long* peq64;  // [n_tok] patterns of <= 64 tokens: position mask of each distinct word, at q_off + distinct index
@@ -224,6 +236,7 @@ struct Workspace {
   Params bounds_params{};
   bool bounds_valid = false;
   int4* qmask = nullptr;
+  int4* qmask2 = nullptr;
   uint32_t* wq = nullptr;
   unsigned long long* peq64 = nullptr;
   int64_t cap_wq = 0;

@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
   int2* tbl = b.tbl + 4ll * off;
   __shared__ int2 s_tbl[8][128];
   __shared__ int s_cnt[8][64];
+  __shared__ int s_cnt2[8][64];  // pattern positions per bit of the second signature
   __shared__ unsigned long long s_peq[8][64];
   __shared__ uint32_t s_wcnt[8][512];  // 1024 16-bit counters per warp (wide signature bits)
   // Lanes insert their words concurrently (CAS on the key, atomic add on the multiplicity) -- into a
@@ -159,9 +160,12 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
   const bool small = ts <= 128;
   int2* wtbl = small ? s_tbl[threadIdx.x >> 5] : tbl;
   int* cnt = s_cnt[threadIdx.x >> 5];
+  int* cnt2 = s_cnt2[threadIdx.x >> 5];
   for (int j = lane; j < ts; j += 32) wtbl[j] = make_int2(-1, 0);
   cnt[lane] = 0;
   cnt[lane + 32] = 0;
+  cnt2[lane] = 0;
+  cnt2[lane + 32] = 0;
   __syncwarp();
   for (int j = lane; j < p; j += 32) {
     const int w = b.pat[off + j];
@@ -172,7 +176,10 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
       h = (h + 1) & (ts - 1);
     }
     atomicAdd(&wtbl[h].y, 1 << 16);
-    if (w >= 2) atomicAdd(&cnt[sig_bit(w)], 1);  // pattern positions per signature bit; unknown words excluded
+    if (w >= 2) {  // pattern positions per signature bit; unknown words excluded
+      atomicAdd(&cnt[sig_bit(w)], 1);
+      atomicAdd(&cnt2[sig2_bit(w)], 1);
+    }
   }
   __syncwarp();
   int distinct = 0;
@@ -218,6 +225,16 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
     int mult = max(max(c_lo, c_hi) - 3, 0);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) mult = max(mult, __shfl_xor_sync(FULL, mult, d));
+    // the same planes over the second signature's 64 bits (tested by the verify kernel before the exact count)
+    const int d_lo = cnt2[lane], d_hi = cnt2[lane + 32];
+    const int j_lo = min(d_lo, 3), j_hi = min(d_hi, 3);
+    const unsigned s_lo = __ballot_sync(FULL, j_lo & 1), s_hi = __ballot_sync(FULL, j_hi & 1);
+    const unsigned s2_lo = __ballot_sync(FULL, j_lo & 2), s2_hi = __ballot_sync(FULL, j_hi & 2);
+    int mult2 = max(max(d_lo, d_hi) - 3, 0);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mult2 = max(mult2, __shfl_xor_sync(FULL, mult2, d));
+    if (lane == 0) b.qmask2[q] = make_int4((int)s_lo, (int)s_hi, (int)s2_lo, (int)s2_hi);
+    mult |= mult2 << 10;  // both travel in qmeta.w (10 bits each: a pattern has at most 1023 positions)
     // The same over the 1024 bits of the wide signatures (sentences longer than kWideMin), exactly: three planes
     // of min(count, 7) and a short list of the bits that collect more (frequent words of a long pattern), so that
     //   coverage <= sum over the signature's bits of count(bit)
@@ -284,7 +301,8 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
 // the number of same-address atomics near one per warp instead of one per warp and n-gram level.
 static const int kSliceBuf = 6;
 #ifndef FM_SEARCH_THREADS
-#define FM_SEARCH_THREADS 256  // CTA size of the search kernel (the CTA-wide flush waits for its slowest warp)
+#define FM_SEARCH_THREADS 128  // CTA size of the search kernel: the CTA-wide flush waits for its slowest warp (measured:
+                               // 0.134 ms with 128 threads x 12 CTAs/SM, 0.143 ms with 256 x 6, 0.144 ms with 64 x 20)
 #endif
 struct SliceBuf {
   int beg[kSliceBuf][FM_SEARCH_THREADS];
@@ -366,7 +384,7 @@ __device__ __forceinline__ void flush_slices(const BatchDev& b, SliceBuf& sb, in
 // SuffixArray::equal_range (src/suffix_array.cc:105-212) restated as the equal range of the ONE new
 // token at depth k inside the previous range (every suffix there already shares k tokens).
 #ifndef FM_SEARCH_CTAS
-#define FM_SEARCH_CTAS 6
+#define FM_SEARCH_CTAS 12
 #endif
 __global__ void __launch_bounds__(FM_SEARCH_THREADS, FM_SEARCH_CTAS) fm_search_kernel(IndexDev ix, BatchDev b) {
   __shared__ SliceBuf sb;
@@ -381,7 +399,7 @@ __global__ void __launch_bounds__(FM_SEARCH_THREADS, FM_SEARCH_CTAS) fm_search_k
     const QMeta m = b.qmeta[q];
     p = m.x; ml = m.y; it = c - m.z; pat = b.pat + m.z;
     live = (m.w & kQValid) != 0;
-    tag = (p << 10) | ((m.w >> 8) << 20);
+    tag = (p << 10) | (((m.w >> 8) & 0x3ff) << 20);
   }
   int lo = 0, hi = 0, len = 0;
   uint32_t bslot = 0;  // slot of the chain's bigram in the bigram directory
@@ -878,6 +896,18 @@ __device__ __forceinline__ int verify_candidates(const IndexDev& ix, const Batch
     else if (need == kNeedNoTable) {
       need = 0xffff;
       if (reject_length(p, slen, pr)) have = false;
+    } else if (wrow < 0) {
+      // Second signature: an independent 64-bit word -> bit map of the sentence (sig2_at) against the query's planes
+      // over the same map (qmask2). Like stage 1 of the walk it bounds the coverage from above, so a candidate whose
+      // bound stays below the smallest passing coverage cannot pass the exact count: 8 bytes instead of the sentence
+      // and ~s table probes (83 % of the exact counts fail at f=0.7, 93 % at f=0.5; the bound removes about a third of
+      // them -- a candidate that passed the first signature has a coverage close to the bound already).
+      const uint2 s2 = __ldg(ix.sig2_at + (start >> 2));
+      const int4 m2 = __ldg(b.qmask2 + q);
+      const int mult2 = (qm.w >> 18) & 0x3ff;
+      int ub = __popc(s2.x & (unsigned)m2.x) + __popc(s2.y & (unsigned)m2.y) + 2 * (__popc(s2.x & (unsigned)m2.z) + __popc(s2.y & (unsigned)m2.w));
+      if (mult2) ub += mult2 * (__popc(s2.x & (unsigned)m2.x & (unsigned)m2.z) + __popc(s2.y & (unsigned)m2.y & (unsigned)m2.w));
+      if (ub < need) have = false;
     }
   }
   // The sentence a query really matches is reached through many of its n-grams, so many candidates are
