@@ -58,19 +58,18 @@ static int upload(const std::vector<T>& h, size_t extra, Index* ix, int blk, con
 // Boost binary archive, src/fuzzy_matcher_binarization.cc). Header, then the device blocks exactly as
 // they sit in HBM, then the host-side tables. Loading is read + upload: no sort, no hashing.
 static const char kMagic[8] = {'F', 'M', 'B', '2', '0', '0', 'I', 1};
-static const int64_t kFileVersion = 3;  // 2: wide signatures (walk records of long sentences carry a wsig row); 3: sig2_at
-enum { BLK_TOK = 0, BLK_SA = 1, BLK_WALK = 2, BLK_QVA = 3, BLK_SID = 4, BLK_IDF = 5, BLK_BG = 6, BLK_TG = 7, BLK_REAL = 8, BLK_GAP = 9, BLK_NEXT = 10, BLK_WSIG = 11, BLK_START = 12, BLK_SIG2 = 13, N_BLK = 14 };
+static const int64_t kFileVersion = 4;  // 2: wide signatures (walk records of long sentences carry a wsig row); 4: sa_aux (start + second signature + length)
+enum { BLK_TOK = 0, BLK_SA = 1, BLK_WALK = 2, BLK_QVA = 3, BLK_SID = 4, BLK_IDF = 5, BLK_BG = 6, BLK_TG = 7, BLK_REAL = 8, BLK_GAP = 9, BLK_NEXT = 10, BLK_WSIG = 11, BLK_START = 12, N_BLK = 13 };
 
 static void bind_blocks(Index* ix) {
   IndexDev& d = ix->dev;
   d.tok = static_cast<const int32_t*>(ix->d_blocks[BLK_TOK]);
   d.sa_pos = static_cast<const int32_t*>(ix->d_blocks[BLK_SA]);
   d.sa_rec = static_cast<const uint2*>(ix->d_blocks[BLK_WALK]);
-  d.sa_start = static_cast<const int32_t*>(ix->d_blocks[BLK_START]);
+  d.sa_aux = static_cast<const int4*>(ix->d_blocks[BLK_START]);
   d.sa_next = static_cast<const int32_t*>(ix->d_blocks[BLK_NEXT]);
   d.qva = static_cast<const int32_t*>(ix->d_blocks[BLK_QVA]);
   d.sid_at = static_cast<const int32_t*>(ix->d_blocks[BLK_SID]);
-  d.sig2_at = static_cast<const uint2*>(ix->d_blocks[BLK_SIG2]);
   d.idf = static_cast<const float*>(ix->d_blocks[BLK_IDF]);
   d.bg_tab = static_cast<const int4*>(ix->d_blocks[BLK_BG]);
   d.tg_tab = static_cast<const int4*>(ix->d_blocks[BLK_TG]);
@@ -113,11 +112,9 @@ static bool header_ok(const int64_t* hdr, const int64_t* blk, int n_blk) {
   if (n_sent < 0 || n_suf < 0 || n_buf < 8 || n_buf >= (int64_t(1) << 31) || n_sent > n_suf || n_suf > n_buf) return false;
   if (!pow2m1(bgm) || !pow2m1(tgm) || n_blk != N_BLK) return false;
   if (blk[BLK_TOK] != n_buf * 4 || blk[BLK_SA] < n_suf * 4 || blk[BLK_NEXT] < n_suf * 4 || blk[BLK_WALK] < (n_suf + 8) * 8 ||
-      blk[BLK_START] < n_suf * 4)
+      blk[BLK_START] < n_suf * 16)
     return false;
-  if (blk[BLK_QVA] != (vocab + 1) * 4 || blk[BLK_IDF] != vocab * 4 || blk[BLK_SID] != (n_buf / 4 + 1) * 4 ||
-      blk[BLK_SIG2] != (n_buf / 4 + 1) * 8)
-    return false;
+  if (blk[BLK_QVA] != (vocab + 1) * 4 || blk[BLK_IDF] != vocab * 4 || blk[BLK_SID] != (n_buf / 4 + 1) * 4) return false;
   if (blk[BLK_BG] != (bgm + 1) * 16 || blk[BLK_TG] != (tgm + 1) * 16) return false;
   if (blk[BLK_WSIG] % (kWideWords * 4) != 0 || blk[BLK_WSIG] / (kWideWords * 4) > n_sent) return false;
   if ((blk[BLK_REAL] != 0 && blk[BLK_REAL] != n_buf * 4) || blk[BLK_GAP] != blk[BLK_REAL]) return false;
@@ -235,7 +232,7 @@ int set_idf_stats(Index* ix, const uint32_t* sf, int64_t n_sent_global) {
 // owns a row), and its walk records carry that row number in place of the 64-bit signature.
 __global__ void fm_build_sentence_kernel(const int32_t* __restrict__ tok, const int32_t* __restrict__ sent_start, int n_sent,
                                          const int32_t* __restrict__ wide_row, uint32_t* wsig, unsigned long long* sig,
-                                         int32_t* sent_len, int32_t* sid_at, uint2* sig2_at) {
+                                         int32_t* sent_len, int32_t* sid_at, unsigned long long* sig2) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_sent) return;
   const int st = sent_start[s];
@@ -257,12 +254,12 @@ __global__ void fm_build_sentence_kernel(const int32_t* __restrict__ tok, const 
   sig[s] = sg;  // the walk record of every suffix of this sentence
   sent_len[s] = n;
   sid_at[st >> 2] = s;
-  sig2_at[st >> 2] = make_uint2((unsigned)sg2, (unsigned)(sg2 >> 32));
+  sig2[s] = sg2;
 }
 
 __global__ void fm_build_walk_kernel(const int32_t* __restrict__ sa_pos, long long n_suf, const int32_t* __restrict__ sent_start,
                                      int n_sent, const unsigned long long* __restrict__ sig,
-                                     uint2* sa_rec, int32_t* sa_start) {
+                                     const unsigned long long* __restrict__ sig2, uint2* sa_rec, int4* sa_aux) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_suf) return;
   const int pos = sa_pos[i];
@@ -273,7 +270,12 @@ __global__ void fm_build_walk_kernel(const int32_t* __restrict__ sa_pos, long lo
   }
   const unsigned long long sg = sig[a];
   sa_rec[i] = make_uint2((unsigned)sg, (unsigned)(sg >> 32));
-  sa_start[i] = sent_start[a];
+  if (((unsigned)sg & 63u) != 63u) {  // short sentence: second signature and length
+    const unsigned long long s2 = sig2[a];
+    sa_aux[i] = make_int4(sent_start[a], (int)(unsigned)s2, (int)(unsigned)(s2 >> 32), (int)((unsigned)sg & 63u));
+  } else {  // long sentence: row of the wide signature, length | 1 << 31
+    sa_aux[i] = make_int4(sent_start[a], (int)(unsigned)(sg >> 32), 0, (int)((((unsigned)sg >> 6) & 1023u) | 0x80000000u));
+  }
 }
 
 // sa_next[i] = token at depth 3 of suffix i (0 if it has fewer than four tokens)
@@ -391,13 +393,15 @@ static int derive_next(Index* ix) {
   return FM_OK;
 }
 
-// Builds sa_rec, sa_start, sa_next, sid_at and the two directories on the device from tok + sa_pos (already uploaded).
+// Builds sa_rec, sa_aux, sa_next, sid_at and the two directories on the device from tok + sa_pos (already uploaded).
 static int build_on_device(Index* ix, const std::vector<int32_t>& sent_start, const std::vector<int32_t>& wide_row, int64_t n_wide) {
   IndexDev& d = ix->dev;
   const long long n_suf = ix->n_suf;
   const int n_sent = (int)ix->n_sent;
   int32_t* d_start = nullptr; int32_t* d_len = nullptr; unsigned long long* d_sig = nullptr; unsigned long long* d_counts = nullptr;
   int32_t* d_wrow = nullptr;
+  unsigned long long* d_sig2 = nullptr;
+  FM_CUDA(cudaMalloc((void**)&d_sig2, (size_t)(n_sent + 1) * 8));
   FM_CUDA(cudaMalloc((void**)&d_start, (size_t)(n_sent + 1) * 4));
   FM_CUDA(cudaMalloc((void**)&d_wrow, (size_t)(n_sent + 1) * 4));
   if (n_sent > 0) FM_CUDA(cudaMemcpy(d_wrow, wide_row.data(), (size_t)n_sent * 4, cudaMemcpyHostToDevice));
@@ -408,8 +412,7 @@ static int build_on_device(Index* ix, const std::vector<int32_t>& sent_start, co
   FM_CUDA(cudaMemcpy(d_start, sent_start.data(), (size_t)(n_sent + 1) * 4, cudaMemcpyHostToDevice));
   int rc;
   if ((rc = dev_alloc(ix, BLK_SID, (size_t)(ix->n_buf / 4) + 1, 0xff, &d.sid_at)) ||
-      (rc = dev_alloc(ix, BLK_SIG2, (size_t)(ix->n_buf / 4) + 1, 0xff, &d.sig2_at)) ||
-      (rc = dev_alloc(ix, BLK_WALK, (size_t)n_suf + 8, 0, &d.sa_rec)) || (rc = dev_alloc(ix, BLK_START, (size_t)n_suf + 4, 0, &d.sa_start)) ||
+      (rc = dev_alloc(ix, BLK_WALK, (size_t)n_suf + 8, 0, &d.sa_rec)) || (rc = dev_alloc(ix, BLK_START, (size_t)n_suf + 4, 0, &d.sa_aux)) ||
       (rc = derive_next(ix)) ||
       (rc = dev_alloc(ix, BLK_WSIG, (size_t)n_wide * kWideWords, 0, &d.wsig)))
     return rc;
@@ -419,10 +422,10 @@ static int build_on_device(Index* ix, const std::vector<int32_t>& sent_start, co
   const unsigned gs = (unsigned)((n_suf + tb - 1) / tb);
   if (n_sent > 0)
     fm_build_sentence_kernel<<<(n_sent + tb - 1) / tb, tb>>>(d.tok, d_start, n_sent, d_wrow, const_cast<uint32_t*>(d.wsig), d_sig, d_len,
-                                                             const_cast<int32_t*>(d.sid_at), const_cast<uint2*>(d.sig2_at));
+                                                             const_cast<int32_t*>(d.sid_at), d_sig2);
   unsigned long long counts[2] = {0, 0};
   if (n_suf > 0) {
-    fm_build_walk_kernel<<<gs, tb>>>(d.sa_pos, n_suf, d_start, n_sent, d_sig, const_cast<uint2*>(d.sa_rec), const_cast<int32_t*>(d.sa_start));
+    fm_build_walk_kernel<<<gs, tb>>>(d.sa_pos, n_suf, d_start, n_sent, d_sig, d_sig2, const_cast<uint2*>(d.sa_rec), const_cast<int4*>(d.sa_aux));
     fm_count_runs_kernel<<<gs, tb>>>(d.tok, d.sa_pos, n_suf, d_counts);
   }
   FM_CUDA(cudaMemcpy(counts, d_counts, 16, cudaMemcpyDeviceToHost));
@@ -441,7 +444,7 @@ static int build_on_device(Index* ix, const std::vector<int32_t>& sent_start, co
   }
   FM_CUDA(cudaDeviceSynchronize());
   FM_CUDA(cudaGetLastError());
-  cudaFree(d_start); cudaFree(d_len); cudaFree(d_sig); cudaFree(d_counts); cudaFree(d_wrow);
+  cudaFree(d_start); cudaFree(d_len); cudaFree(d_sig); cudaFree(d_counts); cudaFree(d_wrow); cudaFree(d_sig2);
   return FM_OK;
 }
 

@@ -22,7 +22,10 @@ namespace fm {
 //                         sentence (bit sig_bit(w) set for every word w): an upper bound on the coverage
 //                         without touching the sentence. Long sentences: bits 0-5 = 63, bits 6-15 = length,
 //                         high word = row of the sentence's wide signature (wsig).
-// sa_start int32[n_suf]   sentence start in tok of each suffix; read only for elements that pass the test.
+// sa_aux   int4[n_suf]    what the verify kernel needs of an element that passed the walk's test, in ONE 16-byte read:
+//                         x = sentence start in tok, (y, z) = second, independent 64-bit word signature of the sentence
+//                         (sig2_bit; tested before the sentence is fetched for the exact count), w = sentence length.
+//                         Long sentences: y = row of the wide signature, w = length | 1 << 31.
 // sa_next  int32[n_suf]   token at depth 3 of each suffix (tok[sa_pos[k] + 3], 0 when the suffix is shorter):
 //                         the binary search that narrows a trigram range -- the only level where ranges are
 //                         still wide -- reads ONE array instead of sa_pos -> tok (two dependent misses).
@@ -37,14 +40,12 @@ namespace fm {
 // wsig     uint32[n_wide*32] 1024-bit word signatures of the sentences longer than kWideMin tokens (a 64-bit
 //                         signature saturates there); their walk records carry the row number instead of the
 //                         64-bit signature. One row = one 128-byte line.
-// sig2_at  uint2[n_buf/4] second, independent 64-bit word signature per sentence, stored at (sentence start / 4): the
-//                         verify kernel tests it (8 bytes) before it fetches the sentence for the exact count.
 // idf      float[V]       logf(N / sfreq[w]) computed on the host with glibc (0 for unseen words).
 struct IndexDev {
   const int32_t* tok;
   const int32_t* sa_pos;
   const uint2* sa_rec;
-  const int32_t* sa_start;
+  const int4* sa_aux;
   const int32_t* sa_next;
   const int32_t* qva;
   const int4* bg_tab;
@@ -52,7 +53,6 @@ struct IndexDev {
   const int4* tg_tab;
   uint32_t tg_mask;
   const int32_t* sid_at;
-  const uint2* sig2_at;  // [n_buf/4] second 64-bit word signature of the sentence that starts at tok[4 k] (sig2_bit)
   const uint32_t* wsig;
   int32_t n_wide;
   const float* idf;
@@ -77,7 +77,7 @@ static const int kQValid = 1;
 // word -> signature bit 6..63 (must be identical on host and device); bits 0-5 of a record hold the length
 __host__ __device__ inline unsigned sig_bit(int w) { return 6u + (((((unsigned)w * 0x9E3779B1u) >> 16) * 58u) >> 16); }
 // second, independent word -> bit map (64 bits) of the per-sentence signature the verify kernel tests before it
-// fetches a sentence (sig2_at); must be identical on host and device
+// fetches a sentence (sa_aux); must be identical on host and device
 __host__ __device__ inline unsigned sig2_bit(int w) {
   unsigned x = (unsigned)w * 0x7FEB352Du;
   x ^= x >> 15;

@@ -881,28 +881,25 @@ __device__ __forceinline__ int verify_candidates(const IndexDev& ix, const Batch
     const int2 item = items[lane];
     q = item.x & 0xfffff;
     lm = item.x >> 20;
-    const uint2 rec = __ldg(ix.sa_rec + item.y);
-    start = __ldg(ix.sa_start + item.y);
+    const int4 ax = __ldg(ix.sa_aux + item.y);  // start, second signature (or wide row), length: one 16-byte read
+    start = ax.x;
     const QMeta qm = __ldg(b.qmeta + q);
     p = qm.x;
     off = qm.z;
-    slen = (int)(rec.x & 63u);
-    if (slen == 63) {
-      slen = (int)((rec.x >> 6) & 1023u);
-      wrow = (int)rec.y;
-    }
+    slen = ax.w & 0x7fffffff;
+    if (ax.w < 0) wrow = ax.y;
     need = __ldg(b.cmin_tab + ((p << 10) | slen));
     if (need == kNeedReject) have = false;  // (a long sentence outside the length window)
     else if (need == kNeedNoTable) {
       need = 0xffff;
       if (reject_length(p, slen, pr)) have = false;
     } else if (wrow < 0) {
-      // Second signature: an independent 64-bit word -> bit map of the sentence (sig2_at) against the query's planes
+      // Second signature: an independent 64-bit word -> bit map of the sentence (in sa_aux) against the query's planes
       // over the same map (qmask2). Like stage 1 of the walk it bounds the coverage from above, so a candidate whose
       // bound stays below the smallest passing coverage cannot pass the exact count: 8 bytes instead of the sentence
       // and ~s table probes (83 % of the exact counts fail at f=0.7, 93 % at f=0.5; the bound removes about a third of
       // them -- a candidate that passed the first signature has a coverage close to the bound already).
-      const uint2 s2 = __ldg(ix.sig2_at + (start >> 2));
+      const uint2 s2 = make_uint2((unsigned)ax.y, (unsigned)ax.z);
       const int4 m2 = __ldg(b.qmask2 + q);
       const int mult2 = (qm.w >> 18) & 0x3ff;
       int ub = __popc(s2.x & (unsigned)m2.x) + __popc(s2.y & (unsigned)m2.y) + 2 * (__popc(s2.x & (unsigned)m2.z) + __popc(s2.y & (unsigned)m2.w));
@@ -2388,7 +2385,7 @@ __global__ void __launch_bounds__(128) fm_subseq_kernel(IndexDev ix, const int32
     lo = __shfl_sync(FULL, lo, 0);
     hi = __shfl_sync(FULL, hi, 0);
     for (int su = lo; su < hi && n_cand < n_matches; su++) {  // :308-309
-      const int start = __ldg(ix.sa_start + su);
+      const int start = __ldg(reinterpret_cast<const int*>(ix.sa_aux + su));
       const uint32_t sid = (uint32_t)__ldg(ix.sid_at + (start >> 2));
       bool dup = false;
       for (int i = lane; i < n_cand + n_perfect; i += 32) dup |= seen[i < n_cand ? i : n_matches + (i - n_cand)] == sid;
