@@ -61,7 +61,7 @@ static int ensure_queries(Workspace* w, int64_t n_q, int64_t n_tok, bool staging
   if (n_q > w->cap_q) {
     const int64_t c = round_up(n_q + n_q / 4 + 1024, 1024);
     if ((rc = dev_realloc(&w->qmeta, c)) || (rc = dev_realloc(&w->q_cnt, c + 1)) || (rc = dev_realloc(&w->q_base, c + 1)) ||
-        (rc = dev_realloc(&w->acc_cnt, c)) || (rc = dev_realloc(&w->heavy_q, c)) || (rc = dev_realloc(&w->mid_q, c)) || (rc = dev_realloc(&w->qmask, c)) || (rc = dev_realloc(&w->qmask2, c)) || (rc = dev_realloc(&w->d_q_off, c + 1)) || (rc = dev_realloc(&w->d_out_count, c + 1)))
+        (rc = dev_realloc(&w->acc_cnt, c)) || (rc = dev_realloc(&w->heavy_q, c)) || (rc = dev_realloc(&w->mid_q, c)) || (rc = dev_realloc(&w->qmask, c)) || (rc = dev_realloc(&w->qmask2, 3 * c)) || (rc = dev_realloc(&w->d_q_off, c + 1)) || (rc = dev_realloc(&w->d_out_count, c + 1)))
       return rc;
     w->cap_q = c;
     w->cap_surv = 0;  // heapbuf depends on cap_q

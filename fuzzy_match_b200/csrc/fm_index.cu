@@ -58,7 +58,7 @@ static int upload(const std::vector<T>& h, size_t extra, Index* ix, int blk, con
 // Boost binary archive, src/fuzzy_matcher_binarization.cc). Header, then the device blocks exactly as
 // they sit in HBM, then the host-side tables. Loading is read + upload: no sort, no hashing.
 static const char kMagic[8] = {'F', 'M', 'B', '2', '0', '0', 'I', 1};
-static const int64_t kFileVersion = 4;  // 2: wide signatures (walk records of long sentences carry a wsig row); 4: sa_aux (start + second signature + length)
+static const int64_t kFileVersion = 5;  // 2: wide signatures (walk records of long sentences carry a wsig row); 4: sa_aux (start + second signature + length); 5: 192-bit second signature, 32-byte sa_aux records
 enum { BLK_TOK = 0, BLK_SA = 1, BLK_WALK = 2, BLK_QVA = 3, BLK_SID = 4, BLK_IDF = 5, BLK_BG = 6, BLK_TG = 7, BLK_REAL = 8, BLK_GAP = 9, BLK_NEXT = 10, BLK_WSIG = 11, BLK_START = 12, N_BLK = 13 };
 
 static void bind_blocks(Index* ix) {
@@ -112,7 +112,7 @@ static bool header_ok(const int64_t* hdr, const int64_t* blk, int n_blk) {
   if (n_sent < 0 || n_suf < 0 || n_buf < 8 || n_buf >= (int64_t(1) << 31) || n_sent > n_suf || n_suf > n_buf) return false;
   if (!pow2m1(bgm) || !pow2m1(tgm) || n_blk != N_BLK) return false;
   if (blk[BLK_TOK] != n_buf * 4 || blk[BLK_SA] < n_suf * 4 || blk[BLK_NEXT] < n_suf * 4 || blk[BLK_WALK] < (n_suf + 8) * 8 ||
-      blk[BLK_START] < n_suf * 16)
+      blk[BLK_START] < n_suf * 32)
     return false;
   if (blk[BLK_QVA] != (vocab + 1) * 4 || blk[BLK_IDF] != vocab * 4 || blk[BLK_SID] != (n_buf / 4 + 1) * 4) return false;
   if (blk[BLK_BG] != (bgm + 1) * 16 || blk[BLK_TG] != (tgm + 1) * 16) return false;
@@ -232,16 +232,24 @@ int set_idf_stats(Index* ix, const uint32_t* sf, int64_t n_sent_global) {
 // owns a row), and its walk records carry that row number in place of the 64-bit signature.
 __global__ void fm_build_sentence_kernel(const int32_t* __restrict__ tok, const int32_t* __restrict__ sent_start, int n_sent,
                                          const int32_t* __restrict__ wide_row, uint32_t* wsig, unsigned long long* sig,
-                                         int32_t* sent_len, int32_t* sid_at, unsigned long long* sig2) {
+                                         int32_t* sent_len, int32_t* sid_at, uint32_t* sig2) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_sent) return;
   const int st = sent_start[s];
   const int row = wide_row[s];
-  unsigned long long sg = 0, sg2 = ~0ull;  // (long sentences are tested against their wide signature instead)
+  unsigned long long sg = 0;
+  uint32_t sg2[kSig2Words];  // (long sentences are tested against their wide signature instead)
+#pragma unroll
+  for (int k = 0; k < kSig2Words; k++) sg2[k] = 0;
   int n = 0;
   if (row < 0) {
-    sg2 = 0;
-    for (int t; (t = tok[st + n]) != 0; n++) { sg |= 1ull << sig_bit(t); sg2 |= 1ull << sig2_bit(t); }
+    for (int t; (t = tok[st + n]) != 0; n++) {
+      sg |= 1ull << sig_bit(t);
+      const unsigned b2 = sig2_bit(t);
+#pragma unroll
+      for (int k = 0; k < kSig2Words; k++)
+        if ((int)(b2 >> 5) == k) sg2[k] |= 1u << (b2 & 31u);
+    }
     sg |= (unsigned long long)n;  // bits 0-5: the length (<= kWideMin < 63)
   } else {
     uint32_t* w = wsig + (size_t)row * kWideWords;
@@ -254,12 +262,13 @@ __global__ void fm_build_sentence_kernel(const int32_t* __restrict__ tok, const 
   sig[s] = sg;  // the walk record of every suffix of this sentence
   sent_len[s] = n;
   sid_at[st >> 2] = s;
-  sig2[s] = sg2;
+#pragma unroll
+  for (int k = 0; k < kSig2Words; k++) sig2[(size_t)s * kSig2Words + k] = sg2[k];
 }
 
 __global__ void fm_build_walk_kernel(const int32_t* __restrict__ sa_pos, long long n_suf, const int32_t* __restrict__ sent_start,
                                      int n_sent, const unsigned long long* __restrict__ sig,
-                                     const unsigned long long* __restrict__ sig2, uint2* sa_rec, int4* sa_aux) {
+                                     const uint32_t* __restrict__ sig2, uint2* sa_rec, int4* sa_aux) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_suf) return;
   const int pos = sa_pos[i];
@@ -270,11 +279,13 @@ __global__ void fm_build_walk_kernel(const int32_t* __restrict__ sa_pos, long lo
   }
   const unsigned long long sg = sig[a];
   sa_rec[i] = make_uint2((unsigned)sg, (unsigned)(sg >> 32));
-  if (((unsigned)sg & 63u) != 63u) {  // short sentence: second signature and length
-    const unsigned long long s2 = sig2[a];
-    sa_aux[i] = make_int4(sent_start[a], (int)(unsigned)s2, (int)(unsigned)(s2 >> 32), (int)((unsigned)sg & 63u));
-  } else {  // long sentence: row of the wide signature, length | 1 << 31
-    sa_aux[i] = make_int4(sent_start[a], (int)(unsigned)(sg >> 32), 0, (int)((((unsigned)sg >> 6) & 1023u) | 0x80000000u));
+  if (((unsigned)sg & 63u) != 63u) {  // short sentence: length and second signature
+    const uint32_t* s2 = sig2 + (size_t)a * kSig2Words;
+    sa_aux[2 * i] = make_int4(sent_start[a], (int)((unsigned)sg & 63u), (int)s2[0], (int)s2[1]);
+    sa_aux[2 * i + 1] = make_int4((int)s2[2], (int)s2[3], (int)s2[4], (int)s2[5]);
+  } else {  // long sentence: length | 1 << 31, row of the wide signature
+    sa_aux[2 * i] = make_int4(sent_start[a], (int)((((unsigned)sg >> 6) & 1023u) | 0x80000000u), (int)(unsigned)(sg >> 32), 0);
+    sa_aux[2 * i + 1] = make_int4(0, 0, 0, 0);
   }
 }
 
@@ -400,8 +411,8 @@ static int build_on_device(Index* ix, const std::vector<int32_t>& sent_start, co
   const int n_sent = (int)ix->n_sent;
   int32_t* d_start = nullptr; int32_t* d_len = nullptr; unsigned long long* d_sig = nullptr; unsigned long long* d_counts = nullptr;
   int32_t* d_wrow = nullptr;
-  unsigned long long* d_sig2 = nullptr;
-  FM_CUDA(cudaMalloc((void**)&d_sig2, (size_t)(n_sent + 1) * 8));
+  uint32_t* d_sig2 = nullptr;
+  FM_CUDA(cudaMalloc((void**)&d_sig2, (size_t)(n_sent + 1) * kSig2Words * 4));
   FM_CUDA(cudaMalloc((void**)&d_start, (size_t)(n_sent + 1) * 4));
   FM_CUDA(cudaMalloc((void**)&d_wrow, (size_t)(n_sent + 1) * 4));
   if (n_sent > 0) FM_CUDA(cudaMemcpy(d_wrow, wide_row.data(), (size_t)n_sent * 4, cudaMemcpyHostToDevice));
@@ -412,7 +423,7 @@ static int build_on_device(Index* ix, const std::vector<int32_t>& sent_start, co
   FM_CUDA(cudaMemcpy(d_start, sent_start.data(), (size_t)(n_sent + 1) * 4, cudaMemcpyHostToDevice));
   int rc;
   if ((rc = dev_alloc(ix, BLK_SID, (size_t)(ix->n_buf / 4) + 1, 0xff, &d.sid_at)) ||
-      (rc = dev_alloc(ix, BLK_WALK, (size_t)n_suf + 8, 0, &d.sa_rec)) || (rc = dev_alloc(ix, BLK_START, (size_t)n_suf + 4, 0, &d.sa_aux)) ||
+      (rc = dev_alloc(ix, BLK_WALK, (size_t)n_suf + 8, 0, &d.sa_rec)) || (rc = dev_alloc(ix, BLK_START, 2 * ((size_t)n_suf + 4), 0, &d.sa_aux)) ||
       (rc = derive_next(ix)) ||
       (rc = dev_alloc(ix, BLK_WSIG, (size_t)n_wide * kWideWords, 0, &d.wsig)))
     return rc;

@@ -22,10 +22,11 @@ namespace fm {
 //                         sentence (bit sig_bit(w) set for every word w): an upper bound on the coverage
 //                         without touching the sentence. Long sentences: bits 0-5 = 63, bits 6-15 = length,
 //                         high word = row of the sentence's wide signature (wsig).
-// sa_aux   int4[n_suf]    what the verify kernel needs of an element that passed the walk's test, in ONE 16-byte read:
-//                         x = sentence start in tok, (y, z) = second, independent 64-bit word signature of the sentence
-//                         (sig2_bit; tested before the sentence is fetched for the exact count), w = sentence length.
-//                         Long sentences: y = row of the wide signature, w = length | 1 << 31.
+// sa_aux   int4[2*n_suf]  what the verify kernel needs of an element that passed the walk's test, in ONE 32-byte read
+//                         (a single sector): word 0 = sentence start in tok, word 1 = sentence length, words 2..7 =
+//                         second, independent 192-bit word signature of the sentence (sig2_bit; tested before the
+//                         sentence is fetched for the exact count). Long sentences: word 1 = length | 1 << 31,
+//                         word 2 = row of the wide signature.
 // sa_next  int32[n_suf]   token at depth 3 of each suffix (tok[sa_pos[k] + 3], 0 when the suffix is shorter):
 //                         the binary search that narrows a trigram range -- the only level where ranges are
 //                         still wide -- reads ONE array instead of sa_pos -> tok (two dependent misses).
@@ -76,12 +77,16 @@ static const int kQValid = 1;
 
 // word -> signature bit 6..63 (must be identical on host and device); bits 0-5 of a record hold the length
 __host__ __device__ inline unsigned sig_bit(int w) { return 6u + (((((unsigned)w * 0x9E3779B1u) >> 16) * 58u) >> 16); }
-// second, independent word -> bit map (64 bits) of the per-sentence signature the verify kernel tests before it
-// fetches a sentence (sa_aux); must be identical on host and device
+// second, independent word -> bit map (kSig2Words * 32 = 192 bits) of the per-sentence signature the verify kernel
+// tests before it fetches a sentence (sa_aux): three times the bits of the walk's signature, so that few candidates whose
+// exact coverage fails get as far as the sentence fetch (at f=0.5: 2.7 times fewer than with 64 bits)
+static const int kSig2Words = 6;
 __host__ __device__ inline unsigned sig2_bit(int w) {
   unsigned x = (unsigned)w * 0x7FEB352Du;
   x ^= x >> 15;
-  return (x * 0x846CA68Bu) >> 26;
+  x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  return (((x & 0xffffu) * (unsigned)kSig2Words) >> 16) * 32u + (x >> 27);
 }
 // sentences longer than this carry a 1024-bit signature (wsig) instead of the 64-bit one
 static const int kWideMin = 48;
@@ -158,7 +163,7 @@ struct BatchDev {
   int2* tbl;         // [4*n_tok] per-query open-addressing tables: (word, distinct_idx | count<<16)
   const uint16_t* cmin_tab; // [(max_tokens+1) << 10] per (pattern length << 10 | sentence length): smallest coverage that passes
   const uint16_t* cmin64;   // [(max_tokens+1) << 6] the same for the 6-bit length field of a walk record (stage 1 of the gather)
-  int4* qmask2;      // [n_q] the same planes over the 64 bits of the second signature (sig2_bit); its mult sits in qmeta.w bits 18..27
+  int4* qmask2;      // [3*n_q] the same planes over the 192 bits of the second signature (sig2_bit): B0 words 0..5, then B1 words 0..5; its mult sits in qmeta.w bits 18..27
   int4* qmask;       // [n_q] per query, in record layout: planes (B0 lo, B0 hi, B1 lo, B1 hi) of min(pattern positions per signature bit, 3)
   uint32_t* wq;      // [kWideStride*n_q] or NULL (index without wide signatures): planes and excess list over the 1024 wide bits
   unsigned long long* peq64;  // [n_tok] patterns of <= 64 tokens: position mask of each distinct word, at q_off + distinct index

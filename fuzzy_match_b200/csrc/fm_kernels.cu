@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
   int2* tbl = b.tbl + 4ll * off;
   __shared__ int2 s_tbl[8][128];
   __shared__ int s_cnt[8][64];
-  __shared__ int s_cnt2[8][64];  // pattern positions per bit of the second signature
+  __shared__ int s_cnt2[8][32 * kSig2Words];  // pattern positions per bit of the second signature
   __shared__ unsigned long long s_peq[8][64];
   __shared__ uint32_t s_wcnt[8][512];  // 1024 16-bit counters per warp (wide signature bits)
   // Lanes insert their words concurrently (CAS on the key, atomic add on the multiplicity) -- into a
@@ -164,8 +164,8 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
   for (int j = lane; j < ts; j += 32) wtbl[j] = make_int2(-1, 0);
   cnt[lane] = 0;
   cnt[lane + 32] = 0;
-  cnt2[lane] = 0;
-  cnt2[lane + 32] = 0;
+#pragma unroll
+  for (int k = 0; k < kSig2Words; k++) cnt2[32 * k + lane] = 0;
   __syncwarp();
   for (int j = lane; j < p; j += 32) {
     const int w = b.pat[off + j];
@@ -223,17 +223,23 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
     const unsigned a_lo = __ballot_sync(FULL, k_lo & 1), a_hi = __ballot_sync(FULL, k_hi & 1);
     const unsigned a2_lo = __ballot_sync(FULL, k_lo & 2), a2_hi = __ballot_sync(FULL, k_hi & 2);
     int mult = max(max(c_lo, c_hi) - 3, 0);
+    mult = __reduce_max_sync(FULL, mult);
+    // the same planes over the second signature's 192 bits (tested by the verify kernel before the exact count):
+    // lane k keeps word k of plane B0 (k < 6) or word k - 6 of plane B1 and writes it
+    int dmax = 0;
+    unsigned mine = 0;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) mult = max(mult, __shfl_xor_sync(FULL, mult, d));
-    // the same planes over the second signature's 64 bits (tested by the verify kernel before the exact count)
-    const int d_lo = cnt2[lane], d_hi = cnt2[lane + 32];
-    const int j_lo = min(d_lo, 3), j_hi = min(d_hi, 3);
-    const unsigned s_lo = __ballot_sync(FULL, j_lo & 1), s_hi = __ballot_sync(FULL, j_hi & 1);
-    const unsigned s2_lo = __ballot_sync(FULL, j_lo & 2), s2_hi = __ballot_sync(FULL, j_hi & 2);
-    int mult2 = max(max(d_lo, d_hi) - 3, 0);
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) mult2 = max(mult2, __shfl_xor_sync(FULL, mult2, d));
-    if (lane == 0) b.qmask2[q] = make_int4((int)s_lo, (int)s_hi, (int)s2_lo, (int)s2_hi);
+    for (int k = 0; k < kSig2Words; k++) {
+      const int c2 = cnt2[32 * k + lane];
+      const int j2 = min(c2, 3);
+      dmax = max(dmax, c2);
+      const unsigned p0 = __ballot_sync(FULL, j2 & 1), p1 = __ballot_sync(FULL, j2 & 2);
+      if (lane == k) mine = p0;
+      if (lane == k + kSig2Words) mine = p1;
+    }
+    int mult2 = max(dmax - 3, 0);
+    mult2 = __reduce_max_sync(FULL, mult2);
+    if (lane < 2 * kSig2Words) reinterpret_cast<unsigned*>(b.qmask2)[(size_t)q * (2 * kSig2Words) + lane] = mine;
     mult |= mult2 << 10;  // both travel in qmeta.w (10 bits each: a pattern has at most 1023 positions)
     // The same over the 1024 bits of the wide signatures (sentences longer than kWideMin), exactly: three planes
     // of min(count, 7) and a short list of the bits that collect more (frequent words of a long pattern), so that
@@ -881,30 +887,38 @@ __device__ __forceinline__ int verify_candidates(const IndexDev& ix, const Batch
     const int2 item = items[lane];
     q = item.x & 0xfffff;
     lm = item.x >> 20;
-    const int4 ax = __ldg(ix.sa_aux + item.y);  // start, second signature (or wide row), length: one 16-byte read
-    start = ax.x;
+    unsigned ax[8];
+    ldg_nc_v8(ix.sa_aux + 2ll * item.y, ax);  // start, length, second signature (or wide row): one 32-byte read
+    start = (int)ax[0];
     const QMeta qm = __ldg(b.qmeta + q);
     p = qm.x;
     off = qm.z;
-    slen = ax.w & 0x7fffffff;
-    if (ax.w < 0) wrow = ax.y;
+    slen = (int)(ax[1] & 0x7fffffffu);
+    if ((int)ax[1] < 0) wrow = (int)ax[2];
     need = __ldg(b.cmin_tab + ((p << 10) | slen));
     if (need == kNeedReject) have = false;  // (a long sentence outside the length window)
     else if (need == kNeedNoTable) {
       need = 0xffff;
       if (reject_length(p, slen, pr)) have = false;
     } else if (wrow < 0) {
-      // Second signature: an independent 64-bit word -> bit map of the sentence (in sa_aux) against the query's planes
+      // Second signature: an independent 192-bit word -> bit map of the sentence (in sa_aux) against the query's planes
       // over the same map (qmask2). Like stage 1 of the walk it bounds the coverage from above, so a candidate whose
-      // bound stays below the smallest passing coverage cannot pass the exact count: 8 bytes instead of the sentence
-      // and ~s table probes (83 % of the exact counts fail at f=0.7, 93 % at f=0.5; the bound removes about a third of
-      // them -- a candidate that passed the first signature has a coverage close to the bound already).
-      const uint2 s2 = make_uint2((unsigned)ax.y, (unsigned)ax.z);
-      const int4 m2 = __ldg(b.qmask2 + q);
+      // bound stays below the smallest passing coverage cannot pass the exact count: no sentence fetch and no table
+      // probes for it. Three times as wide as the walk's signature, so word collisions add little to the bound:
+      // at f=0.5, 83 % of the candidates whose exact count would fail stop here (56 % with a 64-bit map).
+      const int4* mq = b.qmask2 + 3ll * q;
+      const int4 ma = __ldg(mq), mb = __ldg(mq + 1), mc = __ldg(mq + 2);
+      const unsigned b0[kSig2Words] = {(unsigned)ma.x, (unsigned)ma.y, (unsigned)ma.z, (unsigned)ma.w, (unsigned)mb.x, (unsigned)mb.y};
+      const unsigned b1[kSig2Words] = {(unsigned)mb.z, (unsigned)mb.w, (unsigned)mc.x, (unsigned)mc.y, (unsigned)mc.z, (unsigned)mc.w};
       const int mult2 = (qm.w >> 18) & 0x3ff;
-      int ub = __popc(s2.x & (unsigned)m2.x) + __popc(s2.y & (unsigned)m2.y) + 2 * (__popc(s2.x & (unsigned)m2.z) + __popc(s2.y & (unsigned)m2.w));
-      if (mult2) ub += mult2 * (__popc(s2.x & (unsigned)m2.x & (unsigned)m2.z) + __popc(s2.y & (unsigned)m2.y & (unsigned)m2.w));
-      if (ub < need) have = false;
+      int u0 = 0, u1 = 0, u2 = 0;
+#pragma unroll
+      for (int k = 0; k < kSig2Words; k++) {
+        u0 += __popc(ax[2 + k] & b0[k]);
+        u1 += __popc(ax[2 + k] & b1[k]);
+        u2 += __popc(ax[2 + k] & b0[k] & b1[k]);
+      }
+      if (u0 + 2 * u1 + mult2 * u2 < need) have = false;
     }
   }
   // The sentence a query really matches is reached through many of its n-grams, so many candidates are
@@ -2385,7 +2399,7 @@ __global__ void __launch_bounds__(128) fm_subseq_kernel(IndexDev ix, const int32
     lo = __shfl_sync(FULL, lo, 0);
     hi = __shfl_sync(FULL, hi, 0);
     for (int su = lo; su < hi && n_cand < n_matches; su++) {  // :308-309
-      const int start = __ldg(reinterpret_cast<const int*>(ix.sa_aux + su));
+      const int start = __ldg(reinterpret_cast<const int*>(ix.sa_aux + 2ll * su));
       const uint32_t sid = (uint32_t)__ldg(ix.sid_at + (start >> 2));
       bool dup = false;
       for (int i = lane; i < n_cand + n_perfect; i += 32) dup |= seen[i < n_cand ? i : n_matches + (i - n_cand)] == sid;
