@@ -58,8 +58,8 @@ static int upload(const std::vector<T>& h, size_t extra, Index* ix, int blk, con
 // Boost binary archive, src/fuzzy_matcher_binarization.cc). Header, then the device blocks exactly as
 // they sit in HBM, then the host-side tables. Loading is read + upload: no sort, no hashing.
 static const char kMagic[8] = {'F', 'M', 'B', '2', '0', '0', 'I', 1};
-static const int64_t kFileVersion = 5;  // 2: wide signatures (walk records of long sentences carry a wsig row); 4: sa_aux (start + second signature + length); 5: 192-bit second signature, 32-byte sa_aux records
-enum { BLK_TOK = 0, BLK_SA = 1, BLK_WALK = 2, BLK_QVA = 3, BLK_SID = 4, BLK_IDF = 5, BLK_BG = 6, BLK_TG = 7, BLK_REAL = 8, BLK_GAP = 9, BLK_NEXT = 10, BLK_WSIG = 11, BLK_START = 12, N_BLK = 13 };
+static const int64_t kFileVersion = 6;  // 2: wide signatures (walk records of long sentences carry a wsig row); 4: sa_aux (start + second signature + length); 5: 192-bit second signature, 32-byte sa_aux records; 6: 4-gram directory
+enum { BLK_TOK = 0, BLK_SA = 1, BLK_WALK = 2, BLK_QVA = 3, BLK_SID = 4, BLK_IDF = 5, BLK_BG = 6, BLK_TG = 7, BLK_REAL = 8, BLK_GAP = 9, BLK_NEXT = 10, BLK_WSIG = 11, BLK_START = 12, BLK_QG = 13, N_BLK = 14 };
 
 static void bind_blocks(Index* ix) {
   IndexDev& d = ix->dev;
@@ -73,6 +73,7 @@ static void bind_blocks(Index* ix) {
   d.idf = static_cast<const float*>(ix->d_blocks[BLK_IDF]);
   d.bg_tab = static_cast<const int4*>(ix->d_blocks[BLK_BG]);
   d.tg_tab = static_cast<const int4*>(ix->d_blocks[BLK_TG]);
+  d.qg_tab = static_cast<const int4*>(ix->d_blocks[BLK_QG]);
   d.wsig = static_cast<const uint32_t*>(ix->d_blocks[BLK_WSIG]);
   d.n_wide = (int32_t)(ix->blk_bytes[BLK_WSIG] / (kWideWords * sizeof(uint32_t)));
   d.real = ix->blk_bytes[BLK_REAL] ? static_cast<const int32_t*>(ix->d_blocks[BLK_REAL]) : nullptr;
@@ -84,7 +85,7 @@ int save_index(const Index* ix, const char* path) {
   FILE* f = fopen(path, "wb");
   if (!f) { set_error(std::string("cannot open ") + path + " for writing"); return FM_ERR_INVALID; }
   int64_t hdr[16] = {kFileVersion, ix->vocab_size, ix->max_tokens, ix->n_sent, ix->n_suf, ix->n_buf, (int64_t)ix->dev.bg_mask,
-                     (int64_t)ix->dev.tg_mask, (int64_t)ix->dev.sid_base, ix->n_sent_global, 0, N_BLK, 0, 0, 0, 0};
+                     (int64_t)ix->dev.tg_mask, (int64_t)ix->dev.sid_base, ix->n_sent_global, 0, N_BLK, (int64_t)ix->dev.qg_mask, 0, 0, 0};
   memcpy(&hdr[10], &ix->dev.idf_max, sizeof(float));
   bool ok = fwrite(kMagic, 1, 8, f) == 8 && fwrite(hdr, sizeof(int64_t), 16, f) == 16;
   std::vector<char> buf;
@@ -106,16 +107,16 @@ int save_index(const Index* ix, const char* path) {
 // before anything is allocated from it, so a truncated or corrupt file yields FM_ERR_INVALID, not a crash
 // or an out-of-bounds read in a later kernel.
 static bool header_ok(const int64_t* hdr, const int64_t* blk, int n_blk) {
-  const int64_t vocab = hdr[1], max_tok = hdr[2], n_sent = hdr[3], n_suf = hdr[4], n_buf = hdr[5], bgm = hdr[6], tgm = hdr[7];
+  const int64_t vocab = hdr[1], max_tok = hdr[2], n_sent = hdr[3], n_suf = hdr[4], n_buf = hdr[5], bgm = hdr[6], tgm = hdr[7], qgm = hdr[12];
   auto pow2m1 = [](int64_t m) { return m >= 0 && m < (int64_t(1) << 32) && ((m + 1) & m) == 0; };
   if (vocab < 2 || vocab > (int64_t(1) << 30) || max_tok < 1 || max_tok > FM_MAX_TOKENS) return false;
   if (n_sent < 0 || n_suf < 0 || n_buf < 8 || n_buf >= (int64_t(1) << 31) || n_sent > n_suf || n_suf > n_buf) return false;
-  if (!pow2m1(bgm) || !pow2m1(tgm) || n_blk != N_BLK) return false;
+  if (!pow2m1(bgm) || !pow2m1(tgm) || !pow2m1(qgm) || n_blk != N_BLK) return false;
   if (blk[BLK_TOK] != n_buf * 4 || blk[BLK_SA] < n_suf * 4 || blk[BLK_NEXT] < n_suf * 4 || blk[BLK_WALK] < (n_suf + 8) * 8 ||
       blk[BLK_START] < n_suf * 32)
     return false;
   if (blk[BLK_QVA] != (vocab + 1) * 4 || blk[BLK_IDF] != vocab * 4 || blk[BLK_SID] != (n_buf / 4 + 1) * 4) return false;
-  if (blk[BLK_BG] != (bgm + 1) * 16 || blk[BLK_TG] != (tgm + 1) * 16) return false;
+  if (blk[BLK_BG] != (bgm + 1) * 16 || blk[BLK_TG] != (tgm + 1) * 16 || blk[BLK_QG] != (qgm + 1) * 16) return false;
   if (blk[BLK_WSIG] % (kWideWords * 4) != 0 || blk[BLK_WSIG] / (kWideWords * 4) > n_sent) return false;
   if ((blk[BLK_REAL] != 0 && blk[BLK_REAL] != n_buf * 4) || blk[BLK_GAP] != blk[BLK_REAL]) return false;
   return true;
@@ -200,7 +201,7 @@ int load_index(const char* path, int device, Index** out) {
   bind_blocks(ix);
   IndexDev& d = ix->dev;
   d.vocab_size = ix->vocab_size; d.max_tokens = ix->max_tokens; d.n_suf = ix->n_suf;
-  d.bg_mask = (uint32_t)hdr[6]; d.tg_mask = (uint32_t)hdr[7]; d.sid_base = (uint32_t)hdr[8];
+  d.bg_mask = (uint32_t)hdr[6]; d.tg_mask = (uint32_t)hdr[7]; d.qg_mask = (uint32_t)hdr[12]; d.sid_base = (uint32_t)hdr[8];
   memcpy(&d.idf_max, &hdr[10], sizeof(float));
   *out = ix;
   return FM_OK;
@@ -298,26 +299,34 @@ __global__ void fm_build_next_kernel(const int32_t* __restrict__ tok, const int3
   sa_next[i] = (tok[p + 1] != 0 && tok[p + 2] != 0) ? tok[p + 3] : 0;
 }
 
-// counts[0] = distinct bigrams, counts[1] = distinct trigrams (run starts in the suffix array)
+// counts[0] = distinct bigrams, counts[1] = distinct trigrams (run starts in the suffix array), counts[2] = distinct
+// 4-grams whose trigram occurs more than once (the entries of the 4-gram directory)
 __global__ void fm_count_runs_kernel(const int32_t* __restrict__ tok, const int32_t* __restrict__ sa_pos, long long n_suf,
                                      unsigned long long* counts) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  int bg = 0, tg = 0;
+  int bg = 0, tg = 0, qg = 0;
   if (i < n_suf) {
     const int p = sa_pos[i];
     const int t0 = tok[p], t1 = tok[p + 1];
     if (t1 != 0) {
       const int t2 = tok[p + 2];
-      int q0 = -1, q1 = -1, q2 = -1;
-      if (i > 0) { const int pp = sa_pos[i - 1]; q0 = tok[pp]; q1 = tok[pp + 1]; q2 = q1 ? tok[pp + 2] : 0; }
+      int q0 = -1, q1 = -1, q2 = -1, q3 = -1;
+      if (i > 0) { const int pp = sa_pos[i - 1]; q0 = tok[pp]; q1 = tok[pp + 1]; q2 = q1 ? tok[pp + 2] : 0; q3 = q2 ? tok[pp + 3] : 0; }
       bg = q0 != t0 || q1 != t1;
       tg = t2 != 0 && (bg || q2 != t2);
+      if (t2 != 0 && tok[p + 3] != 0) {
+        const bool same_prev = !bg && q2 == t2;  // the previous suffix shares the trigram
+        bool same_next = false;
+        if (i + 1 < n_suf) { const int pn = sa_pos[i + 1]; same_next = tok[pn] == t0 && tok[pn + 1] == t1 && tok[pn + 2] == t2; }
+        qg = (same_prev || same_next) && !(same_prev && q3 == tok[p + 3]);
+      }
     }
   }
-  const unsigned b1 = __ballot_sync(0xffffffffu, bg), b2 = __ballot_sync(0xffffffffu, tg);
+  const unsigned b1 = __ballot_sync(0xffffffffu, bg), b2 = __ballot_sync(0xffffffffu, tg), b3 = __ballot_sync(0xffffffffu, qg);
   if ((threadIdx.x & 31) == 0) {
     if (b1) atomicAdd(&counts[0], (unsigned long long)__popc(b1));
     if (b2) atomicAdd(&counts[1], (unsigned long long)__popc(b2));
+    if (b3) atomicAdd(&counts[2], (unsigned long long)__popc(b3));
   }
 }
 
@@ -379,6 +388,39 @@ __global__ void fm_build_trigram_kernel(const int32_t* __restrict__ tok, const i
     tg_tab[dir_find(tg_tab, tg_mask, bs, t2)].w = single ? -p - 1 : (int)(i + 1);
   }
 }
+// 4-gram directory: (trigram slot, word3) -> [lo, hi), or (lo, -position-1) for a 4-gram that occurs once. Only
+// for trigrams that occur more than once (the others carry their position in the trigram directory): it replaces
+// the one narrowing step of the search where ranges are still wide by one probe.
+__global__ void fm_build_quadgram_kernel(const int32_t* __restrict__ tok, const int32_t* __restrict__ sa_pos, long long n_suf,
+                                         const int4* __restrict__ bg_tab, uint32_t bg_mask, const int4* __restrict__ tg_tab,
+                                         uint32_t tg_mask, int4* qg_tab, uint32_t qg_mask, int pass) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_suf) return;
+  const int p = sa_pos[i];
+  const int t0 = tok[p], t1 = tok[p + 1];
+  if (t1 == 0) return;
+  const int t2 = tok[p + 2];
+  if (t2 == 0) return;
+  const int t3 = tok[p + 3];
+  if (t3 == 0) return;
+  bool same_prev = false, same_next = false, eq_prev = false, eq_next = false;  // trigram / 4-gram shared with the neighbours
+  if (i > 0) {
+    const int pj = sa_pos[i - 1];
+    same_prev = tok[pj] == t0 && tok[pj + 1] == t1 && tok[pj + 2] == t2;
+    eq_prev = same_prev && tok[pj + 3] == t3;
+  }
+  if (i + 1 < n_suf) {
+    const int pj = sa_pos[i + 1];
+    same_next = tok[pj] == t0 && tok[pj + 1] == t1 && tok[pj + 2] == t2;
+    eq_next = same_next && tok[pj + 3] == t3;
+  }
+  if (!same_prev && !same_next) return;  // the trigram occurs once
+  if (pass == 0 ? eq_prev : eq_next) return;  // not a run start / run end
+  const int bs = (int)dir_find(bg_tab, bg_mask, t0, t1);
+  const int ts = (int)dir_find(tg_tab, tg_mask, bs, t2);
+  if (pass == 0) qg_tab[dir_insert(qg_tab, qg_mask, ts, t3)].z = (int)i;
+  else qg_tab[dir_find(qg_tab, qg_mask, ts, t3)].w = !eq_prev ? -p - 1 : (int)(i + 1);
+}
 
 template <class T>
 static int dev_alloc(Index* ix, int blk, size_t count, int fill_byte, const T** out) {
@@ -418,8 +460,8 @@ static int build_on_device(Index* ix, const std::vector<int32_t>& sent_start, co
   if (n_sent > 0) FM_CUDA(cudaMemcpy(d_wrow, wide_row.data(), (size_t)n_sent * 4, cudaMemcpyHostToDevice));
   FM_CUDA(cudaMalloc((void**)&d_len, (size_t)(n_sent + 1) * 4));
   FM_CUDA(cudaMalloc((void**)&d_sig, (size_t)(n_sent + 1) * 8));
-  FM_CUDA(cudaMalloc((void**)&d_counts, 16));
-  FM_CUDA(cudaMemset(d_counts, 0, 16));
+  FM_CUDA(cudaMalloc((void**)&d_counts, 32));
+  FM_CUDA(cudaMemset(d_counts, 0, 32));
   FM_CUDA(cudaMemcpy(d_start, sent_start.data(), (size_t)(n_sent + 1) * 4, cudaMemcpyHostToDevice));
   int rc;
   if ((rc = dev_alloc(ix, BLK_SID, (size_t)(ix->n_buf / 4) + 1, 0xff, &d.sid_at)) ||
@@ -434,24 +476,29 @@ static int build_on_device(Index* ix, const std::vector<int32_t>& sent_start, co
   if (n_sent > 0)
     fm_build_sentence_kernel<<<(n_sent + tb - 1) / tb, tb>>>(d.tok, d_start, n_sent, d_wrow, const_cast<uint32_t*>(d.wsig), d_sig, d_len,
                                                              const_cast<int32_t*>(d.sid_at), d_sig2);
-  unsigned long long counts[2] = {0, 0};
+  unsigned long long counts[4] = {0, 0, 0, 0};
   if (n_suf > 0) {
     fm_build_walk_kernel<<<gs, tb>>>(d.sa_pos, n_suf, d_start, n_sent, d_sig, d_sig2, const_cast<uint2*>(d.sa_rec), const_cast<int4*>(d.sa_aux));
     fm_count_runs_kernel<<<gs, tb>>>(d.tok, d.sa_pos, n_suf, d_counts);
   }
-  FM_CUDA(cudaMemcpy(counts, d_counts, 16, cudaMemcpyDeviceToHost));
-  uint64_t cap_bg = 1024, cap_tg = 1024;
+  FM_CUDA(cudaMemcpy(counts, d_counts, 32, cudaMemcpyDeviceToHost));
+  uint64_t cap_bg = 1024, cap_tg = 1024, cap_qg = 1024;
   while (cap_bg < counts[0] * 2) cap_bg <<= 1;
   while (cap_tg < counts[1] * 2) cap_tg <<= 1;
+  while (cap_qg < counts[2] * 2) cap_qg <<= 1;
   d.bg_mask = (uint32_t)(cap_bg - 1);
   d.tg_mask = (uint32_t)(cap_tg - 1);
-  if ((rc = dev_alloc(ix, BLK_BG, (size_t)cap_bg, 0xff, &d.bg_tab)) || (rc = dev_alloc(ix, BLK_TG, (size_t)cap_tg, 0xff, &d.tg_tab)))
+  d.qg_mask = (uint32_t)(cap_qg - 1);
+  if ((rc = dev_alloc(ix, BLK_BG, (size_t)cap_bg, 0xff, &d.bg_tab)) || (rc = dev_alloc(ix, BLK_TG, (size_t)cap_tg, 0xff, &d.tg_tab)) ||
+      (rc = dev_alloc(ix, BLK_QG, (size_t)cap_qg, 0xff, &d.qg_tab)))
     return rc;
   if (n_suf > 0) {
     fm_build_bigram_kernel<<<gs, tb>>>(d.tok, d.sa_pos, n_suf, const_cast<int4*>(d.bg_tab), d.bg_mask, 0);
     fm_build_bigram_kernel<<<gs, tb>>>(d.tok, d.sa_pos, n_suf, const_cast<int4*>(d.bg_tab), d.bg_mask, 1);
     fm_build_trigram_kernel<<<gs, tb>>>(d.tok, d.sa_pos, n_suf, d.bg_tab, d.bg_mask, const_cast<int4*>(d.tg_tab), d.tg_mask, 0);
     fm_build_trigram_kernel<<<gs, tb>>>(d.tok, d.sa_pos, n_suf, d.bg_tab, d.bg_mask, const_cast<int4*>(d.tg_tab), d.tg_mask, 1);
+    fm_build_quadgram_kernel<<<gs, tb>>>(d.tok, d.sa_pos, n_suf, d.bg_tab, d.bg_mask, d.tg_tab, d.tg_mask, const_cast<int4*>(d.qg_tab), d.qg_mask, 0);
+    fm_build_quadgram_kernel<<<gs, tb>>>(d.tok, d.sa_pos, n_suf, d.bg_tab, d.bg_mask, d.tg_tab, d.tg_mask, const_cast<int4*>(d.qg_tab), d.qg_mask, 1);
   }
   FM_CUDA(cudaDeviceSynchronize());
   FM_CUDA(cudaGetLastError());

@@ -33,6 +33,10 @@ namespace fm {
 // tg_tab   int4[pow2]     trigram directory: (bigram slot, word2) -> [lo, hi), or (lo, -position-1) for a
 //                         trigram that occurs once; the third narrowing step in
 //                         one more probe (the reference's CLI default ml=3 only ever walks trigram ranges).
+// qg_tab   int4[pow2]     4-gram directory: (trigram slot, word3) -> [lo, hi), or (lo, -position-1) for a 4-gram that
+//                         occurs once; only for trigrams that occur more than once. The fourth narrowing step --
+//                         the one where ranges are still wide (a frequent trigram: thousands of suffixes, a dozen
+//                         dependent bisection rounds) -- in one probe.
 // qva      int32[V+1]     first-word bucket table (reference _quickVocabAccess).
 // bg_tab   int4[pow2]     bigram directory: open-addressing table (word0, word1) -> [lo, hi) of the suffixes
 //                         that start with that bigram, so the two widest narrowing steps of every chain
@@ -53,6 +57,8 @@ struct IndexDev {
   uint32_t bg_mask;
   const int4* tg_tab;
   uint32_t tg_mask;
+  const int4* qg_tab;
+  uint32_t qg_mask;
   const int32_t* sid_at;
   const uint32_t* wsig;
   int32_t n_wide;

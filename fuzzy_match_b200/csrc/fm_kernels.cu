@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(FM_SEARCH_THREADS, FM_SEARCH_CTAS) fm_search_k
     tag = (p << 10) | (((m.w >> 8) & 0x3ff) << 20);
   }
   int lo = 0, hi = 0, len = 0;
-  uint32_t bslot = 0;  // slot of the chain's bigram in the bigram directory
+  uint32_t bslot = 0;  // slot of the chain's bigram in the bigram directory, then of its trigram in the trigram directory
   if (live) {
     const int t0 = pat[it];
     if (it + 1 < p) {
@@ -450,10 +450,26 @@ __global__ void __launch_bounds__(FM_SEARCH_THREADS, FM_SEARCH_CTAS) fm_search_k
             nlo = e.z;
             nhi = e.w;
             if (e.w < 0) { nhi = e.z + 1; npos1 = -e.w - 1; }  // a trigram that occurs once carries its position
+            bslot = h;
             break;
           }
           if (e.x == -1) break;
           h = (h + 1) & ix.tg_mask;
+        }
+      } else if (t >= 2 && len == 3 && hi - lo > 1) {
+        // trigram -> 4-gram through the 4-gram directory (it holds every 4-gram of a trigram that occurs more than
+        // once): the one level where ranges are still wide costs one probe instead of a bisection
+        uint32_t h = bigram_hash((int)bslot, t) & ix.qg_mask;
+        for (;;) {
+          const int4 e = __ldg(ix.qg_tab + h);
+          if (e.x == (int)bslot && e.y == t) {
+            nlo = e.z;
+            nhi = e.w;
+            if (e.w < 0) { nhi = e.z + 1; npos1 = -e.w - 1; }
+            break;
+          }
+          if (e.x == -1) break;
+          h = (h + 1) & ix.qg_mask;
         }
       } else if (t >= 2 && hi - lo == 1) {
         // a single suffix left: the rest of the chain is the common prefix of the pattern and that
@@ -464,13 +480,11 @@ __global__ void __launch_bounds__(FM_SEARCH_THREADS, FM_SEARCH_CTAS) fm_search_k
         if (l2 > len) { nlo = lo; nhi = hi; len = l2 - 1; }
         last = true;
       } else if (t >= 2) {
-        // equal range of t at depth len inside [lo, hi). The search is latency bound, so it trades
-        // probes for dependent steps: (1) quaternary narrowing, three independent pivots per step,
-        // until a pivot hits t; (2) from the hit the two ends of the run of t gallop outwards together
-        // (runs are short: the typical 4-gram range is 1-2 suffixes) and finish by bisection. At depth 3
-        // -- the only level where ranges are still wide -- the key comes from sa_next in one load.
-        const bool d3 = len == 3;
-        auto key = [&](int k) { return d3 ? __ldg(ix.sa_next + k) : __ldg(ix.tok + (__ldg(ix.sa_pos + k) + len)); };
+        // equal range of t at depth len >= 4 inside [lo, hi) (ranges are short there: the typical 4-gram range is
+        // 1-2 suffixes). The search is latency bound, so it trades probes for dependent steps: (1) quaternary
+        // narrowing, three independent pivots per step, until a pivot hits t; (2) from the hit the two ends of the
+        // run of t gallop outwards together and finish by bisection.
+        auto key = [&](int k) { return __ldg(ix.tok + (__ldg(ix.sa_pos + k) + len)); };
         int a = lo, e = hi, m = -1;
         while (m < 0 && a < e) {
           const int n = e - a;
@@ -493,14 +507,9 @@ __global__ void __launch_bounds__(FM_SEARCH_THREADS, FM_SEARCH_CTAS) fm_search_k
             const int pl = ls ? max(le - ls, la) : (int)(((unsigned)la + (unsigned)le) >> 1);
             const int pu = us ? min(ua + us - 1, ue - 1) : (int)(((unsigned)ua + (unsigned)ue) >> 1);
             int vl = 0, vu = 0;
-            if (d3) {
-              if (dl) vl = __ldg(ix.sa_next + pl);
-              if (du) vu = __ldg(ix.sa_next + pu);
-            } else {
-              const int sl = dl ? __ldg(ix.sa_pos + pl) : 0, su = du ? __ldg(ix.sa_pos + pu) : 0;
-              if (dl) vl = __ldg(ix.tok + (sl + len));
-              if (du) vu = __ldg(ix.tok + (su + len));
-            }
+            const int sl = dl ? __ldg(ix.sa_pos + pl) : 0, su = du ? __ldg(ix.sa_pos + pu) : 0;
+            if (dl) vl = __ldg(ix.tok + (sl + len));
+            if (du) vu = __ldg(ix.tok + (su + len));
             if (dl) {
               if (vl < t) { la = pl + 1; ls = 0; } else { le = pl; ls <<= 1; }
             }
