@@ -140,7 +140,7 @@ struct Counters {
   unsigned int n_matches;
   unsigned int n_heavy;  // queries with more than kWarpMax scored candidates (CTA each)
   unsigned int n_mid;    // queries with 2..kWarpMax scored candidates (warp each)
-  unsigned int n_stage2;  // (unused)
+  unsigned int n_prep;  // queries the thread-per-query prepare kernel left to the warp-per-query one (prep_list)
   unsigned int n_small;  // slices of at most kSmallSlice elements (their own list, a lane each)
   unsigned int n_long;  // bit0 / bit1: some survivor's pattern is too long for the first / second scoring kernel
   unsigned int n_cand;   // suffix-array elements that passed stage 1 of the gather (the candidate list)
@@ -165,6 +165,7 @@ struct BatchDev {
   // prepared
   int32_t* pat;      // [n_tok] sanitised pattern tokens
   int32_t* chain_q;  // [n_tok] query of each chain (= pattern position)
+  int32_t* prep_list;  // [n_q] queries for the warp-per-query prepare kernel
   QMeta* qmeta;      // [n_q]
   int2* tbl;         // [4*n_tok] per-query open-addressing tables: (word, distinct_idx | count<<16)
   const uint16_t* cmin_tab; // [(max_tokens+1) << 10] per (pattern length << 10 | sentence length): smallest coverage that passes
@@ -236,7 +237,7 @@ struct Workspace {
   int32_t* d_prior_off = nullptr;  // [n_q+1]
   int64_t cap_prior = 0, cap_prior_q = 0;
   bool prior_active = false;
-  int32_t *pat = nullptr, *chain_q = nullptr;
+  int32_t *pat = nullptr, *chain_q = nullptr, *prep_list = nullptr;
   QMeta* qmeta = nullptr;
   int2* tbl = nullptr;
   uint16_t* cmin_tab = nullptr;
@@ -345,7 +346,7 @@ int gpu_suffix_sort(const int32_t* d_tok, int64_t n_buf, const std::vector<int32
 
 // fm_kernels.cu -- launchers (all asynchronous on `st`)
 void launch_bounds(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st);
-void launch_prepare(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st);
+int launch_prepare(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st);
 void launch_search(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st);
 void launch_gather(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st, cudaEvent_t between);  // walk + verify
 void launch_scan(const int32_t* in, int32_t* out, int32_t n, unsigned long long* chain, unsigned int epoch, int sm_count,

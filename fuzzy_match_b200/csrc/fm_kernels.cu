@@ -124,10 +124,7 @@ __global__ void __launch_bounds__(256) fm_bounds_kernel(int max_tokens, Params p
 // One warp per query. Guards and ml clamp of src/fuzzy_match.cc:450-467; ids outside the vocabulary
 // become VOCAB_UNK (src/vocab_indexer.cc:52-60); the table is PatternCoverage's multiset
 // (src/pattern_coverage.cc:8-13) as an open-addressing table: word -> (distinct index, multiplicity).
-__global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b, Params pr) {
-  const int lane = threadIdx.x & 31;
-  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (q >= b.n_q) return;
+__device__ __forceinline__ void prepare_query(const IndexDev& ix, const BatchDev& b, const Params& pr, int q, int lane) {
   const int off = b.q_off[q];
   const int p = b.q_off[q + 1] - off;
   const bool valid = p > 0 && p <= ix.max_tokens;
@@ -296,6 +293,139 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b
       b.qmask[q] = make_int4((int)a_lo, (int)a_hi, (int)a2_lo, (int)a2_hi);
       b.qmeta[q] = make_int4(p, ml, off, kQValid | (mult << 8));
     }
+  }
+}
+// warp w prepares query w
+__global__ void __launch_bounds__(256) fm_prepare_kernel(IndexDev ix, BatchDev b, Params pr) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid < b.n_q) prepare_query(ix, b, pr, wid, threadIdx.x & 31);
+}
+// the queries fm_prepare_short_kernel left over (patterns of more than kPrepShort words, invalid ones, a signature
+// bit with more than three positions): b.prep_list, persistent warps
+__global__ void __launch_bounds__(256, 4) fm_prepare_list_kernel(IndexDev ix, BatchDev b, Params pr) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n = (int)b.ctr->n_prep, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = wid; i < n; i += n_warps) {
+    prepare_query(ix, b, pr, b.prep_list[i], threadIdx.x & 31);
+    __syncwarp();
+  }
+}
+
+// The same for the common case, one THREAD per query: patterns of at most kPrepShort words on an index without wide
+// signatures. A warp-per-query pass spends ~500 warp instructions on a 15-word pattern, most of them on
+// warp-wide bookkeeping of a handful of active lanes; here a lane walks its own pattern: every word goes into the
+// lane's table in shared memory (slot-major: a lane only ever touches its own bank) and into bit-sliced 3-bit
+// counters of the two signatures (the walk's 58 bits in registers, the 192 bits of the second one in shared
+// memory) -- a counter that would pass seven sends the query to the warp kernel, which keeps the exact
+// multiplicities. The finished table is copied to the query's place in global memory. Distinct indices are handed
+// out in insertion order (any numbering will do: they only name bits of the verify kernel's seen-mask).
+static const int kPrepShort = 32;
+static const int kPrepThreads = 64;
+__global__ void __launch_bounds__(kPrepThreads) fm_prepare_short_kernel(IndexDev ix, BatchDev b, Params pr) {
+  __shared__ int s_key[2 * kPrepShort][kPrepThreads];
+  __shared__ int s_val[2 * kPrepShort][kPrepThreads];
+  __shared__ unsigned s_p2[3 * kSig2Words][kPrepThreads];
+  const int lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool inb = q < b.n_q;
+  int off = 0, p = 0;
+  if (inb) {
+    off = b.q_off[q];
+    p = b.q_off[q + 1] - off;
+    b.q_cnt[q] = 0;
+    if (q == 0) b.q_cnt[b.n_q] = 0;
+  }
+  const bool mine = inb && p > 0 && p <= kPrepShort && p <= ix.max_tokens;
+  bool redo = inb && !mine;
+  if (mine) {
+    const int ts = next_pow2(2 * p);
+    for (int k = 0; k < ts; k++) s_key[k][tid] = -1;
+#pragma unroll
+    for (int k = 0; k < 3 * kSig2Words; k++) s_p2[k][tid] = 0;
+    unsigned long long a0 = 0, a1 = 0, a2 = 0;  // the walk signature's counters, bit-sliced: planes 0, 1, 2
+    unsigned sat = 0;
+    int distinct = 0;
+    int t = b.q_tok_in[off];
+    for (int j = 0; j < p; j++) {
+      const int w = (t >= 2 && t < ix.vocab_size) ? t : 1;
+      if (j + 1 < p) t = b.q_tok_in[off + j + 1];
+      b.pat[off + j] = w;
+      b.chain_q[off + j] = q;
+      int h = hash32((uint32_t)w) & (ts - 1);
+      for (;;) {
+        const int k = s_key[h][tid];
+        if (k == w) { s_val[h][tid] += 1 << 16; break; }
+        if (k == -1) { s_key[h][tid] = w; s_val[h][tid] = (1 << 16) | distinct; distinct++; break; }
+        h = (h + 1) & (ts - 1);
+      }
+      if (w >= 2) {  // unknown words take no part in the signatures
+        const unsigned long long m = 1ull << sig_bit(w);
+        const unsigned long long c0 = a0 & m, c1 = a1 & c0;  // carries into planes 1 and 2
+        sat |= (unsigned)((a2 & c1) != 0);
+        a0 ^= m;
+        a1 ^= c0;
+        a2 |= c1;
+        const unsigned b2 = sig2_bit(w), k2 = b2 >> 5, m2 = 1u << (b2 & 31u);
+        const unsigned x0 = s_p2[k2][tid], x1 = s_p2[kSig2Words + k2][tid], x2 = s_p2[2 * kSig2Words + k2][tid];
+        const unsigned d0 = x0 & m2, d1 = x1 & d0;
+        sat |= (unsigned)((x2 & d1) != 0);
+        s_p2[k2][tid] = x0 ^ m2;
+        s_p2[kSig2Words + k2][tid] = x1 ^ d0;
+        if (d1) s_p2[2 * kSig2Words + k2][tid] = x2 | d1;
+      }
+    }
+    if (sat) {
+      redo = true;  // (the warp kernel builds the table as well)
+    } else {
+      // four entries -- one 32-byte sector -- per store (the table starts on a 32-byte boundary; ts >= 4 here or the
+      // two entries of a one-word pattern go out on their own)
+      int2* tbl = b.tbl + 4ll * off;
+      if (ts < 4) {
+        for (int k = 0; k < ts; k++) {
+          const int key = s_key[k][tid];
+          tbl[k] = make_int2(key, key == -1 ? 0 : s_val[k][tid]);
+        }
+      } else {
+        for (int k = 0; k < ts; k += 4) {
+          const int k0 = s_key[k][tid], k1 = s_key[k + 1][tid], k2 = s_key[k + 2][tid], k3 = s_key[k + 3][tid];
+          const int v0 = k0 == -1 ? 0 : s_val[k][tid], v1 = k1 == -1 ? 0 : s_val[k + 1][tid];
+          const int v2 = k2 == -1 ? 0 : s_val[k + 2][tid], v3 = k3 == -1 ? 0 : s_val[k + 3][tid];
+          asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(tbl + k), "r"(k0), "r"(v0), "r"(k1), "r"(v1),
+                       "r"(k2), "r"(v2), "r"(k3), "r"(v3)
+                       : "memory");
+        }
+      }
+      int ml = pr.ml;
+      if (ml < 0 || ml > p) ml = p;  // (size_t)ml > pattern.size()
+      const int by_ratio = (int)__fmul_rn(pr.mr, (float)p);
+      if (by_ratio > ml) ml = by_ratio;
+      // planes of min(count, 3) and mult = (largest count) - 3, like the warp kernel: a counter of 4..7 has plane 2 set
+      int mult = 0;
+      if (a2) mult = (a2 & a1 & a0) ? 4 : (a2 & a1) ? 3 : (a2 & a0) ? 2 : 1;
+      const unsigned long long s0 = a0 | a2, s1 = a1 | a2;
+      b.qmask[q] = make_int4((int)(unsigned)s0, (int)(unsigned)(s0 >> 32), (int)(unsigned)s1, (int)(unsigned)(s1 >> 32));
+      unsigned y[2 * kSig2Words];
+      int mult2 = 0;
+#pragma unroll
+      for (int k = 0; k < kSig2Words; k++) {
+        const unsigned x0 = s_p2[k][tid], x1 = s_p2[kSig2Words + k][tid], x2 = s_p2[2 * kSig2Words + k][tid];
+        y[k] = x0 | x2;
+        y[kSig2Words + k] = x1 | x2;
+        if (x2) mult2 = max(mult2, (x2 & x1 & x0) ? 4 : (x2 & x1) ? 3 : (x2 & x0) ? 2 : 1);
+      }
+      int4* mq = b.qmask2 + 3ll * q;
+      mq[0] = make_int4((int)y[0], (int)y[1], (int)y[2], (int)y[3]);
+      mq[1] = make_int4((int)y[4], (int)y[5], (int)y[6], (int)y[7]);
+      mq[2] = make_int4((int)y[8], (int)y[9], (int)y[10], (int)y[11]);
+      b.qmeta[q] = make_int4(p, ml, off, kQValid | (mult << 8) | (mult2 << 18));
+    }
+  }
+  const unsigned rb = __ballot_sync(FULL, redo);
+  if (rb) {
+    int base = 0;
+    if (lane == 0) base = (int)atomicAdd(&b.ctr->n_prep, (unsigned)__popc(rb));
+    base = __shfl_sync(FULL, base, 0);
+    if (redo) b.prep_list[base + __popc(rb & ((1u << lane) - 1))] = q;
   }
 }
 
@@ -2535,10 +2665,17 @@ void launch_bounds(const IndexDev& ix, const BatchDev& b, const Params& p, cudaS
   fm_bounds_kernel<<<(ix.max_tokens + 8) / 8, 256, 0, st>>>(ix.max_tokens, p, const_cast<uint16_t*>(b.cmin_tab),
                                                             const_cast<uint16_t*>(b.cmin64));
 }
-void launch_prepare(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st) {
+int launch_prepare(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st) {  // returns the launches
   const int warps_per_block = 8;
   const int grid = (b.n_q + warps_per_block - 1) / warps_per_block;
-  fm_prepare_kernel<<<grid, 256, 0, st>>>(ix, b, p);
+  static const bool warp_only = getenv("FM_PREPARE_WARP_ONLY") != nullptr;  // (tests: the warp kernel for every query)
+  if (b.wq || warp_only) {  // wide signatures need the warp kernel's planes for every query
+    fm_prepare_kernel<<<grid, 256, 0, st>>>(ix, b, p);
+    return 1;
+  }
+  fm_prepare_short_kernel<<<(b.n_q + kPrepThreads - 1) / kPrepThreads, kPrepThreads, 0, st>>>(ix, b, p);
+  fm_prepare_list_kernel<<<std::min(grid, sm_count), 256, 0, st>>>(ix, b, p);
+  return 2;
 }
 void launch_search(const IndexDev& ix, const BatchDev& b, const Params&, cudaStream_t st) {
   const int grid = (b.n_tok + FM_SEARCH_THREADS - 1) / FM_SEARCH_THREADS;

@@ -48,7 +48,19 @@ def all_scoring_paths():
     return ok
 
 
-CASES = {"many_candidates": many_candidates, "all_scoring_paths": all_scoring_paths}
+def short_patterns():
+    """Sentences of at most 40 words (no wide signatures): the thread-per-query prepare kernel, patterns of up to 60
+    words and repeated words for the warp kernel it hands over to."""
+    tm, off, V = synth.make_tm(8000, vocab=300, len_lo=1, len_hi=40, seed=81)
+    q, qo = synth.make_queries(tm, off, 1500, vocab=300, seed=82, len_lo=1, len_hi=60)
+    index, oracle = fmb.Index(tm, off, V), ob.OracleIndex(tm, off, V)
+    ok = True
+    for params in (dict(fuzzy=0.5, n=3, ml=2), dict(fuzzy=0.7, n=1, ml=3), dict(fuzzy=0.4, n=4, ml=3, mr=0.3, idf=1.0)):
+        ok &= same(index, oracle, q, qo, 8, **params)
+    return ok
+
+
+CASES = {"many_candidates": many_candidates, "all_scoring_paths": all_scoring_paths, "short_patterns": short_patterns}
 
 if __name__ == "__main__":
     ob.build()

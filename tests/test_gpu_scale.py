@@ -170,6 +170,14 @@ def test_env_gated_scoring_paths(env):
     run_case("all_scoring_paths", env)
 
 
+def test_env_gated_prepare_warp_kernel():
+    """The warp-per-query prepare kernel for every query (the default on an index without long sentences is the
+    thread-per-query kernel, with the warp kernel for the patterns it leaves over)."""
+    run_case("many_candidates", {"FM_PREPARE_WARP_ONLY": "1"})
+    run_case("short_patterns", {"FM_PREPARE_WARP_ONLY": "1"})
+    run_case("short_patterns", {})
+
+
 def test_more_than_24576_candidates_per_query():
     """Vocabulary of 8 words: ~55k scored candidates per query -- the CTA radix sort in global memory
     (lists beyond the shared-memory sort) without any environment switch."""
