@@ -837,6 +837,37 @@ __device__ __forceinline__ void block_push(const BatchDev& b, int2* queue, int* 
     }
   }
 }
+// The same for the four elements a lane tested in one group: one reservation for all of them.
+__device__ __forceinline__ void block_push4(const BatchDev& b, int2* queue, int* nfill, bool p0, bool p1, bool p2, bool p3, int qlm,
+                                            int sa0, int lane) {
+  const unsigned b0 = __ballot_sync(FULL, p0), b1 = __ballot_sync(FULL, p1), b2 = __ballot_sync(FULL, p2), b3 = __ballot_sync(FULL, p3);
+  const int c0 = __popc(b0), c1 = __popc(b1), c2 = __popc(b2);
+  const int cnt = c0 + c1 + c2 + __popc(b3);
+  int base = 0;
+  if (lane == 0) base = atomicAdd(&nfill[0], cnt);
+  base = __shfl_sync(FULL, base, 0);
+  const unsigned lt = (1u << lane) - 1;
+  const int o0 = __popc(b0 & lt), o1 = c0 + __popc(b1 & lt), o2 = c0 + c1 + __popc(b2 & lt), o3 = c0 + c1 + c2 + __popc(b3 & lt);
+  if (base + cnt <= kWalkQueue) {
+    if (p0) queue[base + o0] = make_int2(qlm, sa0);
+    if (p1) queue[base + o1] = make_int2(qlm, sa0 + 1);
+    if (p2) queue[base + o2] = make_int2(qlm, sa0 + 2);
+    if (p3) queue[base + o3] = make_int2(qlm, sa0 + 3);
+    if (lane == 0) atomicMax(&nfill[1], base + cnt);
+  } else {  // the block's queue is full (dense candidates): this push goes straight to the list
+    unsigned g = 0;
+    if (lane == 0) g = atomicAdd(&b.ctr->n_cand, (unsigned)cnt);
+    g = __shfl_sync(FULL, g, 0);
+    if ((long long)g + cnt <= b.cand_cap) {
+      if (p0) b.cand[(long long)g + o0] = make_int2(qlm, sa0);
+      if (p1) b.cand[(long long)g + o1] = make_int2(qlm, sa0 + 1);
+      if (p2) b.cand[(long long)g + o2] = make_int2(qlm, sa0 + 2);
+      if (p3) b.cand[(long long)g + o3] = make_int2(qlm, sa0 + 3);
+    } else if (lane == 0) {
+      atomicOr(&b.ctr->overflow, 8u);
+    }
+  }
+}
 __global__ void __launch_bounds__(256, FM_GATHER_CTAS) fm_gather_kernel(IndexDev ix, BatchDev b) {
   __shared__ int2 s_queue[kWalkQueue];
   __shared__ SliceWin s_win[8];
@@ -912,12 +943,7 @@ __global__ void __launch_bounds__(256, FM_GATHER_CTAS) fm_gather_kernel(IndexDev
             const unsigned rel = (unsigned)(base - a0);  // element base + i is inside iff rel + i < len (unsigned)
             const bool p0 = (d0 >= 0) & (rel < len), p1 = (d1 >= 0) & (rel + 1u < len);
             const bool p2 = (d2 >= 0) & (rel + 2u < len), p3 = (d3 >= 0) & (rel + 3u < len);
-            if (__any_sync(FULL, p0 | p1 | p2 | p3)) {
-              block_push(b, s_queue, s_n, p0, make_int2(qlm, base), lane);
-              block_push(b, s_queue, s_n, p1, make_int2(qlm, base + 1), lane);
-              block_push(b, s_queue, s_n, p2, make_int2(qlm, base + 2), lane);
-              block_push(b, s_queue, s_n, p3, make_int2(qlm, base + 3), lane);
-            }
+            if (__any_sync(FULL, p0 | p1 | p2 | p3)) block_push4(b, s_queue, s_n, p0, p1, p2, p3, qlm, base, lane);
           }
         }
       }
