@@ -68,7 +68,7 @@ static int ensure_queries(Workspace* w, int64_t n_q, int64_t n_tok, bool staging
   }
   if (n_tok > w->cap_tok) {
     const int64_t c = round_up(n_tok + n_tok / 4 + 4096, 4096);
-    if ((rc = dev_realloc(&w->pat, c)) || (rc = dev_realloc(&w->chain_q, c)) || (rc = dev_realloc(&w->tbl, 4 * c)) ||
+    if ((rc = dev_realloc(&w->pat, c)) || (rc = dev_realloc(&w->chain_rec, c)) || (rc = dev_realloc(&w->tbl, 4 * c)) ||
         (rc = dev_realloc(&w->d_q_tok, c)) || (rc = dev_realloc(&w->peq64, c)))
       return rc;
     w->cap_tok = c;
@@ -164,7 +164,7 @@ static void free_workspace(Workspace* w) {
   cudaFree(w->d_prior); cudaFree(w->d_prior_off);
   cudaFree(w->ctok); cudaFree(w->c_cnt); cudaFree(w->c_base);
   if (w->h_ctotal) cudaFreeHost(w->h_ctotal);
-  cudaFree(w->d_q_tok); cudaFree(w->d_q_off); cudaFree(w->d_q_real); cudaFree(w->d_q_gap); cudaFree(w->d_itok_dist); cudaFree(w->pat); cudaFree(w->chain_q); cudaFree(w->prep_list); cudaFree(w->qmeta); cudaFree(w->tbl); cudaFree(w->cmin_tab); cudaFree(w->span_slice); cudaFree(w->qmask); cudaFree(w->qmask2); cudaFree(w->wq); cudaFree(w->peq64); cudaFree(w->cmin64); cudaFree(w->sm_rec);
+  cudaFree(w->d_q_tok); cudaFree(w->d_q_off); cudaFree(w->d_q_real); cudaFree(w->d_q_gap); cudaFree(w->d_itok_dist); cudaFree(w->pat); cudaFree(w->chain_rec); cudaFree(w->prep_list); cudaFree(w->qmeta); cudaFree(w->tbl); cudaFree(w->cmin_tab); cudaFree(w->span_slice); cudaFree(w->qmask); cudaFree(w->qmask2); cudaFree(w->wq); cudaFree(w->peq64); cudaFree(w->cmin64); cudaFree(w->sm_rec);
   cudaFree(w->sl_start); cudaFree(w->sl_rec); cudaFree(w->hkey); cudaFree(w->hlm); cudaFree(w->surv); cudaFree(w->cand); cudaFree(w->surv_len);
   cudaFree(w->q_cnt); cudaFree(w->q_base); cudaFree(w->acc_cnt); cudaFree(w->rec); cudaFree(w->heapbuf); cudaFree(w->ctr); cudaFree(w->mctr); cudaFree(w->wire_stage); cudaFree(w->wire_send); cudaFree(w->wire_recv); cudaFree(w->scan_chain);
   cudaFree(w->d_out); cudaFree(w->d_out_count); cudaFree(w->mrec); cudaFree(w->m_cnt); cudaFree(w->m_base); cudaFree(w->m_acc); cudaFree(w->m_heap); cudaFree(w->heavy_q); cudaFree(w->m_heavy); cudaFree(w->mid_q); cudaFree(w->m_mid); cudaFree(w->sort_key); cudaFree(w->sort_key2); cudaFree(w->m_key2); cudaFree(w->sort_idx); cudaFree(w->m_key); cudaFree(w->m_idx);
@@ -211,7 +211,7 @@ static int stage_check(cudaStream_t st, const char* what) {
 static BatchDev make_batch(Workspace* w, const int32_t* d_q_tok, const int32_t* d_q_off, int64_t n_q, int64_t n_tok) {
   BatchDev b{};
   b.q_tok_in = d_q_tok; b.q_off = d_q_off; b.n_q = (int32_t)n_q; b.n_tok = (int32_t)n_tok;
-  b.pat = w->pat; b.chain_q = w->chain_q; b.prep_list = w->prep_list; b.qmeta = w->qmeta; b.tbl = w->tbl; b.cmin_tab = w->cmin_tab; b.cmin64 = w->cmin64; b.qmask = w->qmask; b.qmask2 = w->qmask2; b.wq = w->cap_wq ? w->wq : nullptr; b.peq64 = w->peq64;
+  b.pat = w->pat; b.chain_rec = w->chain_rec; b.prep_list = w->prep_list; b.qmeta = w->qmeta; b.tbl = w->tbl; b.cmin_tab = w->cmin_tab; b.cmin64 = w->cmin64; b.qmask = w->qmask; b.qmask2 = w->qmask2; b.wq = w->cap_wq ? w->wq : nullptr; b.peq64 = w->peq64;
   b.span_slice = w->span_slice; b.span_cap = w->cap_spans;
   b.sl_start = w->sl_start; b.sl_rec = w->sl_rec; b.sm_rec = w->sm_rec; b.slice_cap = w->cap_slices;
   b.hkey = w->hkey; b.hlm = w->hlm; b.hmask = w->hs_use - 1;

@@ -164,7 +164,7 @@ struct BatchDev {
   int32_t n_tok;
   // prepared
   int32_t* pat;      // [n_tok] sanitised pattern tokens
-  int32_t* chain_q;  // [n_tok] query of each chain (= pattern position)
+  int2* chain_rec;   // [n_tok] per chain (= pattern position) of the search: (query, start position | pattern length << 10 | mult << 20); length 0 = dead
   int32_t* prep_list;  // [n_q] queries for the warp-per-query prepare kernel
   QMeta* qmeta;      // [n_q]
   int2* tbl;         // [4*n_tok] per-query open-addressing tables: (word, distinct_idx | count<<16)
@@ -237,7 +237,8 @@ struct Workspace {
   int32_t* d_prior_off = nullptr;  // [n_q+1]
   int64_t cap_prior = 0, cap_prior_q = 0;
   bool prior_active = false;
-  int32_t *pat = nullptr, *chain_q = nullptr, *prep_list = nullptr;
+  int32_t *pat = nullptr, *prep_list = nullptr;
+  int2* chain_rec = nullptr;
   QMeta* qmeta = nullptr;
   int2* tbl = nullptr;
   uint16_t* cmin_tab = nullptr;

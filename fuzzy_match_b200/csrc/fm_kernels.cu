@@ -141,7 +141,7 @@ __device__ __forceinline__ void prepare_query(const IndexDev& ix, const BatchDev
   for (int j = lane; j < p; j += 32) {
     const int t = b.q_tok_in[off + j];
     b.pat[off + j] = (t >= 2 && t < ix.vocab_size) ? t : 1;
-    b.chain_q[off + j] = q;
+    if (!valid) b.chain_rec[off + j] = make_int2(q, 0);  // (pattern length 0: the chain is dead)
   }
   if (!valid) return;
   const int ts = next_pow2(2 * p);
@@ -237,6 +237,9 @@ __device__ __forceinline__ void prepare_query(const IndexDev& ix, const BatchDev
     int mult2 = max(dmax - 3, 0);
     mult2 = __reduce_max_sync(FULL, mult2);
     if (lane < 2 * kSig2Words) reinterpret_cast<unsigned*>(b.qmask2)[(size_t)q * (2 * kSig2Words) + lane] = mine;
+    // what a chain of the search needs to start, in one coalesced 8-byte read: query, start position, pattern length
+    // and the mult of the walk's signature (the tag of its slice records)
+    for (int j = lane; j < p; j += 32) b.chain_rec[off + j] = make_int2(q, j | (p << 10) | (mult << 20));
     mult |= mult2 << 10;  // both travel in qmeta.w (10 bits each: a pattern has at most 1023 positions)
     // The same over the 1024 bits of the wide signatures (sentences longer than kWideMin), exactly: three planes
     // of min(count, 7) and a short list of the bits that collect more (frequent words of a long pattern), so that
@@ -350,7 +353,6 @@ __global__ void __launch_bounds__(kPrepThreads) fm_prepare_short_kernel(IndexDev
       const int w = (t >= 2 && t < ix.vocab_size) ? t : 1;
       if (j + 1 < p) t = b.q_tok_in[off + j + 1];
       b.pat[off + j] = w;
-      b.chain_q[off + j] = q;
       int h = hash32((uint32_t)w) & (ts - 1);
       for (;;) {
         const int k = s_key[h][tid];
@@ -418,6 +420,7 @@ __global__ void __launch_bounds__(kPrepThreads) fm_prepare_short_kernel(IndexDev
       mq[1] = make_int4((int)y[4], (int)y[5], (int)y[6], (int)y[7]);
       mq[2] = make_int4((int)y[8], (int)y[9], (int)y[10], (int)y[11]);
       b.qmeta[q] = make_int4(p, ml, off, kQValid | (mult << 8) | (mult2 << 18));
+      for (int j = 0; j < p; j++) b.chain_rec[off + j] = make_int2(q, j | (p << 10) | (mult << 20));
     }
   }
   const unsigned rb = __ballot_sync(FULL, redo);
@@ -522,7 +525,7 @@ __device__ __forceinline__ void flush_slices(const BatchDev& b, SliceBuf& sb, in
 #ifndef FM_SEARCH_CTAS
 #define FM_SEARCH_CTAS 12
 #endif
-__global__ void __launch_bounds__(FM_SEARCH_THREADS, FM_SEARCH_CTAS) fm_search_kernel(IndexDev ix, BatchDev b) {
+__global__ void __launch_bounds__(FM_SEARCH_THREADS, FM_SEARCH_CTAS) fm_search_kernel(IndexDev ix, BatchDev b, Params pr) {
   __shared__ SliceBuf sb;
   int nbuf = 0;
   const int lane = threadIdx.x & 31;
@@ -530,21 +533,30 @@ __global__ void __launch_bounds__(FM_SEARCH_THREADS, FM_SEARCH_CTAS) fm_search_k
   int q = 0, it = 0, p = 0, ml = 0, tag = 0;
   const int32_t* pat = b.pat;
   bool live = c < b.n_tok;
+  int t0 = 0, t1 = 0;
   if (live) {
-    q = b.chain_q[c];
-    const QMeta m = b.qmeta[q];
-    p = m.x; ml = m.y; it = c - m.z; pat = b.pat + m.z;
-    live = (m.w & kQValid) != 0;
-    tag = (p << 10) | (((m.w >> 8) & 0x3ff) << 20);
+    // the chain's record and its first two words, three independent reads (pat is padded: the read past the last
+    // pattern stays inside)
+    const int2 cr = __ldg(b.chain_rec + c);
+    t0 = b.pat[c];
+    t1 = b.pat[c + 1];
+    q = cr.x;
+    it = cr.y & 1023;
+    p = (cr.y >> 10) & 1023;
+    tag = cr.y & ~1023;  // p << 10 | mult << 20
+    pat = b.pat + (c - it);
+    live = p > 0;
+    ml = pr.ml;  // the clamp of the prepare kernels (src/fuzzy_match.cc:450-467)
+    if (ml < 0 || ml > p) ml = p;
+    const int by_ratio = (int)__fmul_rn(pr.mr, (float)p);
+    if (by_ratio > ml) ml = by_ratio;
   }
   int lo = 0, hi = 0, len = 0;
   uint32_t bslot = 0;  // slot of the chain's bigram in the bigram directory, then of its trigram in the trigram directory
   if (live) {
-    const int t0 = pat[it];
     if (it + 1 < p) {
       // whole array -> first word -> bigram in one probe of the bigram directory. A chain that does
       // not reach length 2 registers nothing (src/fuzzy_match.cc:546-550), so length 1 is skipped.
-      const int t1 = pat[it + 1];
       if (t0 >= 2 && t1 >= 2) {
         uint32_t h = bigram_hash(t0, t1) & ix.bg_mask;
         for (;;) {
@@ -2706,9 +2718,9 @@ int launch_prepare(const IndexDev& ix, const BatchDev& b, const Params& p, int s
   fm_prepare_list_kernel<<<std::min(grid, sm_count), 256, 0, st>>>(ix, b, p);
   return 2;
 }
-void launch_search(const IndexDev& ix, const BatchDev& b, const Params&, cudaStream_t st) {
+void launch_search(const IndexDev& ix, const BatchDev& b, const Params& p, cudaStream_t st) {
   const int grid = (b.n_tok + FM_SEARCH_THREADS - 1) / FM_SEARCH_THREADS;
-  if (grid > 0) fm_search_kernel<<<grid, FM_SEARCH_THREADS, 0, st>>>(ix, b);
+  if (grid > 0) fm_search_kernel<<<grid, FM_SEARCH_THREADS, 0, st>>>(ix, b, p);
 }
 void launch_gather(const IndexDev& ix, const BatchDev& b, const Params& p, int sm_count, cudaStream_t st, cudaEvent_t between) {
   // grids several times what is resident: CTAs that finish early make room for the next ones
