@@ -58,7 +58,7 @@ static int upload(const std::vector<T>& h, size_t extra, Index* ix, int blk, con
 // Boost binary archive, src/fuzzy_matcher_binarization.cc). Header, then the device blocks exactly as
 // they sit in HBM, then the host-side tables. Loading is read + upload: no sort, no hashing.
 static const char kMagic[8] = {'F', 'M', 'B', '2', '0', '0', 'I', 1};
-static const int64_t kFileVersion = 6;  // 2: wide signatures (walk records of long sentences carry a wsig row); 4: sa_aux (start + second signature + length); 5: 192-bit second signature, 32-byte sa_aux records; 6: 4-gram directory
+static const int64_t kFileVersion = 7;  // 2: wide signatures (walk records of long sentences carry a wsig row); 4: sa_aux (start + second signature + length); 5: 192-bit second signature, 32-byte sa_aux records; 6: 4-gram directory; 7: trigram directory keyed by the three words, 32-byte entries
 enum { BLK_TOK = 0, BLK_SA = 1, BLK_WALK = 2, BLK_QVA = 3, BLK_SID = 4, BLK_IDF = 5, BLK_BG = 6, BLK_TG = 7, BLK_REAL = 8, BLK_GAP = 9, BLK_NEXT = 10, BLK_WSIG = 11, BLK_START = 12, BLK_QG = 13, N_BLK = 14 };
 
 static void bind_blocks(Index* ix) {
@@ -116,7 +116,7 @@ static bool header_ok(const int64_t* hdr, const int64_t* blk, int n_blk) {
       blk[BLK_START] < n_suf * 32)
     return false;
   if (blk[BLK_QVA] != (vocab + 1) * 4 || blk[BLK_IDF] != vocab * 4 || blk[BLK_SID] != (n_buf / 4 + 1) * 4) return false;
-  if (blk[BLK_BG] != (bgm + 1) * 16 || blk[BLK_TG] != (tgm + 1) * 16 || blk[BLK_QG] != (qgm + 1) * 16) return false;
+  if (blk[BLK_BG] != (bgm + 1) * 16 || blk[BLK_TG] != (tgm + 1) * 32 || blk[BLK_QG] != (qgm + 1) * 16) return false;
   if (blk[BLK_WSIG] % (kWideWords * 4) != 0 || blk[BLK_WSIG] / (kWideWords * 4) > n_sent) return false;
   if ((blk[BLK_REAL] != 0 && blk[BLK_REAL] != n_buf * 4) || blk[BLK_GAP] != blk[BLK_REAL]) return false;
   return true;
@@ -363,9 +363,30 @@ __global__ void fm_build_bigram_kernel(const int32_t* __restrict__ tok, const in
     if (end) bg_tab[dir_find(bg_tab, bg_mask, t0, t1)].w = (int)(i + 1);
   }
 }
+// trigram directory: 32-byte entries keyed by the three words; the slot is claimed in two steps (words 0-1 with a
+// 64-bit CAS, then word 2: contenders for the second step agree on the first)
+__device__ __forceinline__ uint32_t tg_insert(int4* tab, uint32_t mask, int t0, int t1, int t2) {
+  const unsigned long long key = ((unsigned long long)(unsigned)t1 << 32) | (unsigned)t0;
+  uint32_t h = trigram_hash(t0, t1, t2) & mask;
+  for (;;) {
+    const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(tab + 2 * (size_t)h), ~0ull, key);
+    if (prev == ~0ull || prev == key) {
+      const int prev2 = atomicCAS(&tab[2 * (size_t)h].z, -1, t2);
+      if (prev2 == -1 || prev2 == t2) return h;
+    }
+    h = (h + 1) & mask;
+  }
+}
+__device__ __forceinline__ uint32_t tg_find(const int4* tab, uint32_t mask, int t0, int t1, int t2) {
+  uint32_t h = trigram_hash(t0, t1, t2) & mask;
+  for (;;) {
+    const int4 e = tab[2 * (size_t)h];
+    if (e.x == t0 && e.y == t1 && e.z == t2) return h;
+    h = (h + 1) & mask;
+  }
+}
 __global__ void fm_build_trigram_kernel(const int32_t* __restrict__ tok, const int32_t* __restrict__ sa_pos, long long n_suf,
-                                        const int4* __restrict__ bg_tab, uint32_t bg_mask, int4* tg_tab, uint32_t tg_mask,
-                                        int pass) {
+                                        int4* tg_tab, uint32_t tg_mask, int pass) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_suf) return;
   const int p = sa_pos[i];
@@ -377,23 +398,22 @@ __global__ void fm_build_trigram_kernel(const int32_t* __restrict__ tok, const i
   bool edge = j < 0 || j >= n_suf;
   if (!edge) { const int pj = sa_pos[j]; edge = tok[pj] != t0 || tok[pj + 1] != t1 || tok[pj + 2] != t2; }
   if (!edge) return;
-  const int bs = (int)dir_find(bg_tab, bg_mask, t0, t1);
   if (pass == 0) {
-    tg_tab[dir_insert(tg_tab, tg_mask, bs, t2)].z = (int)i;
+    tg_tab[2 * (size_t)tg_insert(tg_tab, tg_mask, t0, t1, t2)].w = (int)i;
   } else {
     // hi, or for a trigram that occurs once -(position) - 1: the search then follows that suffix
     // without reading sa_pos
     bool single = i == 0;
     if (!single) { const int pj = sa_pos[i - 1]; single = tok[pj] != t0 || tok[pj + 1] != t1 || tok[pj + 2] != t2; }
-    tg_tab[dir_find(tg_tab, tg_mask, bs, t2)].w = single ? -p - 1 : (int)(i + 1);
+    tg_tab[2 * (size_t)tg_find(tg_tab, tg_mask, t0, t1, t2) + 1].x = single ? -p - 1 : (int)(i + 1);
   }
 }
 // 4-gram directory: (trigram slot, word3) -> [lo, hi), or (lo, -position-1) for a 4-gram that occurs once. Only
 // for trigrams that occur more than once (the others carry their position in the trigram directory): it replaces
 // the one narrowing step of the search where ranges are still wide by one probe.
 __global__ void fm_build_quadgram_kernel(const int32_t* __restrict__ tok, const int32_t* __restrict__ sa_pos, long long n_suf,
-                                         const int4* __restrict__ bg_tab, uint32_t bg_mask, const int4* __restrict__ tg_tab,
-                                         uint32_t tg_mask, int4* qg_tab, uint32_t qg_mask, int pass) {
+                                         const int4* __restrict__ tg_tab, uint32_t tg_mask, int4* qg_tab, uint32_t qg_mask,
+                                         int pass) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_suf) return;
   const int p = sa_pos[i];
@@ -416,8 +436,7 @@ __global__ void fm_build_quadgram_kernel(const int32_t* __restrict__ tok, const 
   }
   if (!same_prev && !same_next) return;  // the trigram occurs once
   if (pass == 0 ? eq_prev : eq_next) return;  // not a run start / run end
-  const int bs = (int)dir_find(bg_tab, bg_mask, t0, t1);
-  const int ts = (int)dir_find(tg_tab, tg_mask, bs, t2);
+  const int ts = (int)tg_find(tg_tab, tg_mask, t0, t1, t2);
   if (pass == 0) qg_tab[dir_insert(qg_tab, qg_mask, ts, t3)].z = (int)i;
   else qg_tab[dir_find(qg_tab, qg_mask, ts, t3)].w = !eq_prev ? -p - 1 : (int)(i + 1);
 }
@@ -489,16 +508,16 @@ static int build_on_device(Index* ix, const std::vector<int32_t>& sent_start, co
   d.bg_mask = (uint32_t)(cap_bg - 1);
   d.tg_mask = (uint32_t)(cap_tg - 1);
   d.qg_mask = (uint32_t)(cap_qg - 1);
-  if ((rc = dev_alloc(ix, BLK_BG, (size_t)cap_bg, 0xff, &d.bg_tab)) || (rc = dev_alloc(ix, BLK_TG, (size_t)cap_tg, 0xff, &d.tg_tab)) ||
+  if ((rc = dev_alloc(ix, BLK_BG, (size_t)cap_bg, 0xff, &d.bg_tab)) || (rc = dev_alloc(ix, BLK_TG, 2 * (size_t)cap_tg, 0xff, &d.tg_tab)) ||
       (rc = dev_alloc(ix, BLK_QG, (size_t)cap_qg, 0xff, &d.qg_tab)))
     return rc;
   if (n_suf > 0) {
     fm_build_bigram_kernel<<<gs, tb>>>(d.tok, d.sa_pos, n_suf, const_cast<int4*>(d.bg_tab), d.bg_mask, 0);
     fm_build_bigram_kernel<<<gs, tb>>>(d.tok, d.sa_pos, n_suf, const_cast<int4*>(d.bg_tab), d.bg_mask, 1);
-    fm_build_trigram_kernel<<<gs, tb>>>(d.tok, d.sa_pos, n_suf, d.bg_tab, d.bg_mask, const_cast<int4*>(d.tg_tab), d.tg_mask, 0);
-    fm_build_trigram_kernel<<<gs, tb>>>(d.tok, d.sa_pos, n_suf, d.bg_tab, d.bg_mask, const_cast<int4*>(d.tg_tab), d.tg_mask, 1);
-    fm_build_quadgram_kernel<<<gs, tb>>>(d.tok, d.sa_pos, n_suf, d.bg_tab, d.bg_mask, d.tg_tab, d.tg_mask, const_cast<int4*>(d.qg_tab), d.qg_mask, 0);
-    fm_build_quadgram_kernel<<<gs, tb>>>(d.tok, d.sa_pos, n_suf, d.bg_tab, d.bg_mask, d.tg_tab, d.tg_mask, const_cast<int4*>(d.qg_tab), d.qg_mask, 1);
+    fm_build_trigram_kernel<<<gs, tb>>>(d.tok, d.sa_pos, n_suf, const_cast<int4*>(d.tg_tab), d.tg_mask, 0);
+    fm_build_trigram_kernel<<<gs, tb>>>(d.tok, d.sa_pos, n_suf, const_cast<int4*>(d.tg_tab), d.tg_mask, 1);
+    fm_build_quadgram_kernel<<<gs, tb>>>(d.tok, d.sa_pos, n_suf, d.tg_tab, d.tg_mask, const_cast<int4*>(d.qg_tab), d.qg_mask, 0);
+    fm_build_quadgram_kernel<<<gs, tb>>>(d.tok, d.sa_pos, n_suf, d.tg_tab, d.tg_mask, const_cast<int4*>(d.qg_tab), d.qg_mask, 1);
   }
   FM_CUDA(cudaDeviceSynchronize());
   FM_CUDA(cudaGetLastError());

@@ -30,9 +30,11 @@ namespace fm {
 // sa_next  int32[n_suf]   token at depth 3 of each suffix (tok[sa_pos[k] + 3], 0 when the suffix is shorter):
 //                         the binary search that narrows a trigram range -- the only level where ranges are
 //                         still wide -- reads ONE array instead of sa_pos -> tok (two dependent misses).
-// tg_tab   int4[pow2]     trigram directory: (bigram slot, word2) -> [lo, hi), or (lo, -position-1) for a
-//                         trigram that occurs once; the third narrowing step in
-//                         one more probe (the reference's CLI default ml=3 only ever walks trigram ranges).
+// tg_tab   int4[2*pow2]   trigram directory, 32-byte entries (one sector): (word0, word1, word2, lo | hi, -, -, -), hi =
+//                         -position-1 for a trigram that occurs once. Keyed by the three words, not by the bigram's
+//                         slot: with min_subseq_length >= 3 (the reference's CLI default) a chain that does not reach
+//                         a trigram registers nothing, so the search probes this table FIRST and never reads the
+//                         bigram directory -- one random sector and one dependent round less per chain.
 // qg_tab   int4[pow2]     4-gram directory: (trigram slot, word3) -> [lo, hi), or (lo, -position-1) for a 4-gram that
 //                         occurs once; only for trigrams that occur more than once. The fourth narrowing step --
 //                         the one where ranges are still wide (a frequent trigram: thousands of suffixes, a dozen
@@ -113,6 +115,9 @@ __host__ __device__ inline uint32_t bigram_hash(int w0, int w1) {
   k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
   return (uint32_t)k;
 }
+
+// trigram -> first slot probed in the trigram directory
+__host__ __device__ inline uint32_t trigram_hash(int w0, int w1, int w2) { return bigram_hash((int)bigram_hash(w0, w1), w2); }
 
 // A scored candidate: what the replay of the candidate loop needs. rowmin_max = max over DP rows of the row
 // minimum (reproduces the reference's early exit); reserved[0] = sentence start in tok (contrastive rerank),

@@ -432,6 +432,34 @@ __global__ void __launch_bounds__(kPrepThreads) fm_prepare_short_kernel(IndexDev
   }
 }
 
+__device__ __forceinline__ void ldg_nc_v8(const void* p, unsigned (&r)[8]) {  // one 256-bit load (32-byte aligned)
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Trigram directory lookup: one 32-byte entry (a sector) per probe. Returns false when no suffix starts with the
+// trigram; pos1 = position of the only suffix when it occurs once (else -1), slot = the entry's slot (key of the
+// 4-gram directory).
+__device__ __forceinline__ bool tg_lookup(const IndexDev& ix, int t0, int t1, int t2, int& lo, int& hi, int& pos1, uint32_t& slot) {
+  uint32_t h = trigram_hash(t0, t1, t2) & ix.tg_mask;
+  for (;;) {
+    unsigned e[8];
+    ldg_nc_v8(ix.tg_tab + 2 * (size_t)h, e);
+    if ((int)e[0] == t0 && (int)e[1] == t1 && (int)e[2] == t2) {
+      lo = (int)e[3];
+      hi = (int)e[4];
+      pos1 = -1;
+      if (hi < 0) { pos1 = -hi - 1; hi = lo + 1; }
+      slot = h;
+      return true;
+    }
+    if ((int)e[0] == -1) return false;
+    h = (h + 1) & ix.tg_mask;
+  }
+}
+
 // ---------------------------------------------------------------- search
 
 // Range slices are first buffered per thread in shared memory (kSliceBuf slots) and appended to the
@@ -533,13 +561,14 @@ __global__ void __launch_bounds__(FM_SEARCH_THREADS, FM_SEARCH_CTAS) fm_search_k
   int q = 0, it = 0, p = 0, ml = 0, tag = 0;
   const int32_t* pat = b.pat;
   bool live = c < b.n_tok;
-  int t0 = 0, t1 = 0;
+  int t0 = 0, t1 = 0, t2 = 0;
   if (live) {
-    // the chain's record and its first two words, three independent reads (pat is padded: the read past the last
-    // pattern stays inside)
+    // the chain's record and its first three words, independent reads (pat is padded: the reads past the last
+    // pattern stay inside)
     const int2 cr = __ldg(b.chain_rec + c);
     t0 = b.pat[c];
     t1 = b.pat[c + 1];
+    t2 = b.pat[c + 2];
     q = cr.x;
     it = cr.y & 1023;
     p = (cr.y >> 10) & 1023;
@@ -552,16 +581,23 @@ __global__ void __launch_bounds__(FM_SEARCH_THREADS, FM_SEARCH_CTAS) fm_search_k
     if (by_ratio > ml) ml = by_ratio;
   }
   int lo = 0, hi = 0, len = 0;
-  uint32_t bslot = 0;  // slot of the chain's bigram in the bigram directory, then of its trigram in the trigram directory
+  uint32_t bslot = 0;  // slot of the chain's trigram in the trigram directory (key of the 4-gram directory)
+  int pos1 = -1;  // sa_pos[lo] once the range has shrunk to one suffix
   if (live) {
-    if (it + 1 < p) {
+    if (ml >= 3) {
+      // Nothing shorter than three words is registered (src/fuzzy_match.cc:546-550: a chain registers matches of
+      // at least min_subseq_length words): whole array -> trigram in ONE probe of the trigram directory, the
+      // bigram directory is never read. A chain without a third word, or with an unknown word, is dead at once.
+      live = it + 2 < p && t0 >= 2 && t1 >= 2 && t2 >= 2 && tg_lookup(ix, t0, t1, t2, lo, hi, pos1, bslot);
+      len = live ? 3 : 0;
+    } else if (it + 1 < p) {
       // whole array -> first word -> bigram in one probe of the bigram directory. A chain that does
-      // not reach length 2 registers nothing (src/fuzzy_match.cc:546-550), so length 1 is skipped.
+      // not reach length 2 registers nothing, so length 1 is skipped.
       if (t0 >= 2 && t1 >= 2) {
         uint32_t h = bigram_hash(t0, t1) & ix.bg_mask;
         for (;;) {
           const int4 e = __ldg(ix.bg_tab + h);
-          if (e.x == t0 && e.y == t1) { lo = e.z; hi = e.w; len = 2; bslot = h; break; }
+          if (e.x == t0 && e.y == t1) { lo = e.z; hi = e.w; len = 2; break; }
           if (e.x == -1) break;
           h = (h + 1) & ix.bg_mask;
         }
@@ -576,7 +612,6 @@ __global__ void __launch_bounds__(FM_SEARCH_THREADS, FM_SEARCH_CTAS) fm_search_k
   // p == 1: the unigram range itself is registered (src/fuzzy_match.cc:484-493)
   if (live && p == 1 && 1 >= ml) push_slice(sb, nbuf, lo, hi - lo, 1);
   bool extending = live && it + len < p;
-  int pos1 = -1;  // sa_pos[lo] once the range has shrunk to one suffix
   while (__any_sync(FULL, extending)) {
     if (__any_sync(FULL, nbuf > kSliceBuf - 2)) flush_slices(b, sb, nbuf, lane, q, tag);  // room for two more
     if (extending) {
@@ -584,20 +619,8 @@ __global__ void __launch_bounds__(FM_SEARCH_THREADS, FM_SEARCH_CTAS) fm_search_k
       int nlo = lo, nhi = lo, npos1 = -1;
       bool last = false;
       if (t >= 2 && len == 2) {
-        // bigram -> trigram through the trigram directory
-        uint32_t h = bigram_hash((int)bslot, t) & ix.tg_mask;
-        for (;;) {
-          const int4 e = __ldg(ix.tg_tab + h);
-          if (e.x == (int)bslot && e.y == t) {
-            nlo = e.z;
-            nhi = e.w;
-            if (e.w < 0) { nhi = e.z + 1; npos1 = -e.w - 1; }  // a trigram that occurs once carries its position
-            bslot = h;
-            break;
-          }
-          if (e.x == -1) break;
-          h = (h + 1) & ix.tg_mask;
-        }
+        // bigram -> trigram through the trigram directory (min_subseq_length < 3: the bigram range came first)
+        if (!tg_lookup(ix, pat[it], pat[it + 1], t, nlo, nhi, npos1, bslot)) { nlo = nhi = lo; npos1 = -1; }
       } else if (t >= 2 && len == 3 && hi - lo > 1) {
         // trigram -> 4-gram through the 4-gram directory (it holds every 4-gram of a trigram that occurs more than
         // once): the one level where ranges are still wide costs one probe instead of a bisection
@@ -784,12 +807,6 @@ __device__ __forceinline__ int cover_sentence(const int32_t* __restrict__ sent, 
   return cover;
 }
 
-__device__ __forceinline__ void ldg_nc_v8(const void* p, unsigned (&r)[8]) {  // one 256-bit load (32-byte aligned)
-  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "l"(p));
-}
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Stage 1 for one walk record: upper bound on the coverage from the signature against the smallest
 // coverage that passes for this (pattern length, sentence length). row = cmin64 + (p << 6); m = the
@@ -2446,15 +2463,11 @@ __device__ __forceinline__ bool dir_bigram(const IndexDev& ix, int t0, int t1, i
     h = (h + 1) & ix.bg_mask;
   }
 }
-__device__ __forceinline__ bool dir_trigram(const IndexDev& ix, uint32_t bslot, int t2, int& lo, int& hi) {
+__device__ __forceinline__ bool dir_trigram(const IndexDev& ix, int t0, int t1, int t2, int& lo, int& hi) {
   if (t2 < 2) return false;
-  uint32_t h = bigram_hash((int)bslot, t2) & ix.tg_mask;
-  for (;;) {
-    const int4 e = __ldg(ix.tg_tab + h);
-    if (e.x == (int)bslot && e.y == t2) { lo = e.z; hi = e.w < 0 ? e.z + 1 : e.w; return true; }
-    if (e.x == -1) return false;
-    h = (h + 1) & ix.tg_mask;
-  }
+  int pos1;
+  uint32_t slot;
+  return tg_lookup(ix, t0, t1, t2, lo, hi, pos1, slot);
 }
 // equal range of word t at depth `depth` inside [lo, hi) (all suffixes there share `depth` words)
 __device__ __forceinline__ void narrow_range(const IndexDev& ix, int depth, int t, int& lo, int& hi) {
@@ -2481,7 +2494,7 @@ __device__ bool ngram_range(const IndexDev& ix, const int32_t* pat, int len, int
   if (len == 1) { lo = __ldg(ix.qva + t0); hi = __ldg(ix.qva + t0 + 1); return hi > lo; }
   uint32_t slot = 0;
   if (!dir_bigram(ix, t0, pat[1], lo, hi, slot)) return false;
-  if (len >= 3 && !dir_trigram(ix, slot, pat[2], lo, hi)) return false;
+  if (len >= 3 && !dir_trigram(ix, t0, pat[1], pat[2], lo, hi)) return false;
   for (int d = 3; d < len; d++) {
     narrow_range(ix, d, pat[d], lo, hi);
     if (hi <= lo) return false;
@@ -2495,7 +2508,7 @@ __device__ int longest_prefix(const IndexDev& ix, const int32_t* pat, int n) {
   if (n < 2) return 1;
   uint32_t slot = 0;
   if (!dir_bigram(ix, pat[0], pat[1], lo, hi, slot)) return 1;
-  if (n < 3 || !dir_trigram(ix, slot, pat[2], lo, hi)) return 2;
+  if (n < 3 || !dir_trigram(ix, pat[0], pat[1], pat[2], lo, hi)) return 2;
   int len = 3;
   while (len < n) {
     narrow_range(ix, len, pat[len], lo, hi);
