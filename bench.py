@@ -625,7 +625,7 @@ def main():
     peak, peak_src = measured_peak()
     # the two kernels of the gather stage are timed separately
     stages = {k[3:]: prof[k] for k in ("ms_prepare", "ms_search", "ms_walk", "ms_verify", "ms_scan", "ms_score", "ms_replay")}
-    kernel_of = {"walk": "fm_gather_kernel", "verify": "fm_verify_kernel", "search": "fm_search_kernel", "prepare": "fm_prepare_kernel",
+    kernel_of = {"walk": "fm_gather_kernel", "verify": "fm_verify_kernel", "search": "fm_search_kernel", "prepare": "fm_prepare_short_kernel",
                  "scan": "fm_scan_kernel", "score": "fm_score_bp_kernel", "replay": "fm_replay_small_kernel"}
     dom = max(stages, key=stages.get)
     ncu = {}

@@ -9,7 +9,7 @@ import sys
 def main():
     rep, kern = sys.argv[1], sys.argv[2]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 30
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name",
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--launch-count", "1", "--kernel-name",
                           "regex:" + kern], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     lines, tot_i, tot_s = [], 0, 0

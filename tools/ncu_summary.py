@@ -17,6 +17,10 @@ FULL = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 def launches(path):
     rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0].isdigit()]
+    # the match path starts with the bounds / prepare kernels: launches before the first of them belong to the index
+    # build (which shares fm_scan_kernel)
+    first = next((i for i, r in enumerate(rows) if r[4].startswith(("fm_bounds", "fm_prepare"))), 0)
+    rows = rows[first:]
     d = defaultdict(lambda: defaultdict(list))  # kernel -> metric -> values (one row per launch and metric)
     for r in rows:
         d[r[4].split("(")[0]][r[12]].append(float(r[-1].replace(",", "")))
