@@ -1013,9 +1013,10 @@ __global__ void __launch_bounds__(256, FM_GATHER_CTAS) fm_gather_kernel(IndexDev
 // Insert (q, start) into the dedup table keeping the max match length: NGramMatches::_longest_matches
 // (src/ngram_matches.cc:79-81). The survivor's slot in the compact list comes from the caller (reserved per
 // CTA); the first inserter also claims the candidate's slot inside its query.
+static const int kSurvStage = 512;
 struct SurvStage {  // survivors of one CTA block, staged in shared memory
-  SurvRec rec[512];
-  uint16_t len[512];
+  SurvRec rec[kSurvStage];
+  uint16_t len[kSurvStage];
 };
 __device__ __forceinline__ int add_survivor(const BatchDev& b, SurvStage& stage, int* n_stage, int q, int start, int slen, int lm) {
   const unsigned long long key = ((unsigned long long)(unsigned)q << 32) | (unsigned)start;
@@ -1026,8 +1027,18 @@ __device__ __forceinline__ int add_survivor(const BatchDev& b, SurvStage& stage,
       const int j = atomicAdd(&b.q_cnt[q], 1);
       atomicMax(&b.hlm[h], (unsigned)lm);
       const int i = atomicAdd(n_stage, 1);
-      stage.rec[i] = SurvRec{q, start, (int32_t)h, j};
-      stage.len[i] = (uint16_t)slen;
+      if (i < kSurvStage) {
+        stage.rec[i] = SurvRec{q, start, (int32_t)h, j};
+        stage.len[i] = (uint16_t)slen;
+      } else {  // the block's stage is full (a block of several rounds with dense survivors): straight to the list
+        const unsigned g = atomicAdd(&b.ctr->n_surv, 1u);
+        if ((long long)g < b.surv_cap) {
+          b.surv[g] = SurvRec{q, start, (int32_t)h, j};
+          b.surv_len[g] = (uint16_t)slen;
+        } else {
+          atomicOr(&b.ctr->overflow, 2u);
+        }
+      }
       return (int)h;
     }
     if (prev == key) {
@@ -1249,18 +1260,24 @@ __global__ void __launch_bounds__(256, FM_VERIFY_CTAS) fm_verify_kernel(IndexDev
   __syncthreads();
   if (stop) return;
   const long long n_cand = (long long)b.ctr->n_cand;
-  const int n_blocks = (int)((n_cand + 511) >> 9);
+  // A block ends with a CTA barrier (its survivors leave the shared-memory stage together), and the warps of a CTA
+  // finish their rounds at different times (exact counts are unevenly spread): 19 % of the stall samples at f=0.5
+  // with two rounds per block. Long candidate lists take eight rounds per block -- a quarter of the barriers, and
+  // the differences average out over the rounds; short lists keep small blocks so that every CTA gets some.
+  const int rounds = n_cand > (long long)gridDim.x * 2048 ? 8 : n_cand > (long long)gridDim.x * 1024 ? 4 : 2;
+  const int per_block = rounds * 256;
+  const int n_blocks = (int)((n_cand + per_block - 1) / per_block);
   int verified = 0;
   for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
-    for (int r = 0; r < 2; r++) {
-      const long long first = (long long)blk * 512 + (r * 8 + wib) * 32;
+    for (int r = 0; r < rounds; r++) {
+      const long long first = (long long)blk * per_block + (r * 8 + wib) * 32;
       const int n = (int)min(32ll, n_cand - first);
       if (n > 0) verified += verify_candidates(ix, b, pr, b.cand + first, n, s_cand[wib], s_seen[wib], s_stage, &s_n, lane);
     }
     __syncthreads();
-    const int n = s_n;
+    const int n = min(s_n, kSurvStage);
     if (n) {  // (uniform)
       if (threadIdx.x == 0) s_base = (int)atomicAdd(&b.ctr->n_surv, (unsigned)n);
       __syncthreads();
