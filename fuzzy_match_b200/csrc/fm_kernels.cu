@@ -1,12 +1,14 @@
 // fm_kernels.cu -- hand-written sm_100a kernels of the fuzzy-match hot path.
 //
-// One batch of patterns streams through nine launches (no host round trip in between):
-//   prepare      per query: clamp ml, sanitise ids, build the pattern's word table and signature masks
-//   search       per (query, start position): bigram / trigram directory probes, then narrow the
-//                suffix-array range token by token; emit range slices
-//   gather       per suffix-array element of every slice: length window + signature bound from one
-//                128-bit load, exact coverage for the few that pass, dedup (query, sentence) with max
-//                match length                                          <- the "suffix-range gather"
+// One batch of patterns streams through eleven launches (no host round trip in between):
+//   prepare      per query: clamp ml, sanitise ids, build the pattern's word table and signature planes (a thread
+//                per query for short patterns, a warp per query for the rest: two launches)
+//   search       per (query, start position): trigram directory probe (bigram first when min_subseq_length < 3),
+//                4-gram directory, then narrow the suffix-array range token by token; emit range slices
+//   gather       walk: per suffix-array element of every slice, length window + signature bound from its 8-byte
+//                record (four per 256-bit load); verify: second signature, exact coverage for the few that
+//                pass, dedup (query, sentence) with max match length (two launches)
+//                                                                      <- the "suffix-range gather"
 //   scan         exclusive scan of survivors per query (co-resident CTAs, epoch-tagged tile totals)
 //   score        per surviving (query, sentence): edit-distance DP -- registers for p <= 32 (thread per
 //                pair), warp-wide wavefront in shared memory above     <- the "DP kernel"
@@ -2088,7 +2090,10 @@ __global__ void __launch_bounds__(256) fm_replay_small_kernel(fm_record* rec, co
 // longest match desc, s_id asc) by register rank sort (<= 32) or a shared-memory bitonic sort of packed
 // keys, the replay, result order, top-N output (:670-679). Larger queries are queued for
 // fm_replay_heavy_kernel.
-static const int kWarpMax = 128;
+#ifndef FM_KWARPMAX
+#define FM_KWARPMAX 128
+#endif
+static const int kWarpMax = FM_KWARPMAX;
 __global__ void __launch_bounds__(256) fm_replay_kernel(fm_record* rec, const int32_t* __restrict__ q_cnt,
                                                         const int32_t* __restrict__ q_base, float* heapbuf,
                                                         unsigned long long* sort_key, int32_t* sort_idx, int32_t* acc_cnt,
@@ -2469,7 +2474,7 @@ __global__ void __launch_bounds__(256) fm_contrast_fill_kernel(IndexDev ix, long
 // under the reference's integer-truncated running bound is returned. Nothing here is throughput critical
 // (a handful of dependent lookups and one or two edit distances per pattern); the batch gives the parallelism.
 
-// suffixes that start with the bigram / extend a bigram slot by one word (the directories of the search kernel)
+// suffixes that start with the bigram / the trigram (the directories of the search kernel)
 __device__ __forceinline__ bool dir_bigram(const IndexDev& ix, int t0, int t1, int& lo, int& hi, uint32_t& slot) {
   if (t0 < 2 || t1 < 2) return false;
   uint32_t h = bigram_hash(t0, t1) & ix.bg_mask;
