@@ -153,7 +153,10 @@ struct Counters {
   unsigned int wire_need;   // merge stage: largest number of accepted records of one shard
 };
 static const int kElemBits = 38;
-static const int kSmallSlice = 4;
+#ifndef FM_SMALL_SLICE
+#define FM_SMALL_SLICE 8
+#endif
+static const int kSmallSlice = FM_SMALL_SLICE;
 static const int kSpan = 1024;  // flattened elements per gather work unit (one warp)
 
 // per-batch workspace pointers (device)

@@ -839,6 +839,7 @@ __device__ __forceinline__ int stage1_extra(unsigned lo, unsigned hi, const int4
 #ifndef FM_GATHER_CTAS
 #define FM_GATHER_CTAS 5
 #endif
+static const int kPackMax = 28;  // segments of up to 28 records (32 with the alignment of the 256-bit loads) are walked four to an iteration
 static const int kWalkQueue = 3072;  // candidates of a block staged in shared memory (8 * kSpan elements; beyond: straight to the list)
 struct SliceWin {  // the slice records of the span a warp is walking
   int4 rec[32];
@@ -953,6 +954,49 @@ __global__ void __launch_bounds__(256, FM_GATHER_CTAS) fm_gather_kernel(IndexDev
           const int4 m = win.planes[k - kwin];
           const int st = win.st[k - kwin];
           const int seg_end = (int)min((long long)st + sr.w, (long long)span_len);
+          if (seg_end - pos <= kPackMax) {
+            // Short segments (a third of the loop iterations belong to slices that fill a fraction of the 128
+            // records of an iteration): up to four consecutive slices share one iteration, eight lanes -- 32 aligned
+            // records -- each, every group of lanes with its own slice record from the window.
+            int npk = 1, last_end = seg_end;
+#pragma unroll
+            for (int j = 1; j < 4; j++) {
+              const int wj = k - kwin + j;
+              if (npk == j && wj < 32 && k + j < n_big) {
+                const int stj = win.st[wj];
+                const int endj = (int)min((long long)stj + win.rec[wj].w, (long long)span_len);
+                if (stj < span_len && endj - stj <= kPackMax) { npk = j + 1; last_end = endj; }
+              }
+            }
+            const int grp = lane >> 3, sub = lane & 7;
+            const bool act = grp < npk;
+            const int wi = k - kwin + (act ? grp : 0);
+            const int4 gsr = win.rec[wi];
+            const int4 gm = win.planes[wi];
+            const int gst = win.st[wi];
+            const int gbeg = max(gst, pos), gend = (int)min((long long)gst + gsr.w, (long long)span_len);
+            const int ga0 = gsr.y + (gbeg - gst), ga1 = gsr.y + (gend - gst);
+            const unsigned glen = (unsigned)(ga1 - ga0);
+            const int gmult = gsr.z >> 20;
+            const uint16_t* grow = b.cmin64 + (((gsr.z >> 10) & 1023) << 6);
+            const int gqlm = gsr.x | ((gsr.z & 1023) << 20);
+            const int base = (ga0 & ~3) + 4 * sub;
+            unsigned r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (act && base < ga1) ldg_nc_v8(ix.sa_rec + base, r);
+            int d0 = stage1_margin(r[0], r[1], gm, grow), d1 = stage1_margin(r[2], r[3], gm, grow);
+            int d2 = stage1_margin(r[4], r[5], gm, grow), d3 = stage1_margin(r[6], r[7], gm, grow);
+            if (__any_sync(FULL, gmult != 0)) {
+              d0 += stage1_extra(r[0], r[1], gm, gmult); d1 += stage1_extra(r[2], r[3], gm, gmult);
+              d2 += stage1_extra(r[4], r[5], gm, gmult); d3 += stage1_extra(r[6], r[7], gm, gmult);
+            }
+            const unsigned rel = (unsigned)(base - ga0);
+            const bool p0 = act & (d0 >= 0) & (rel < glen), p1 = act & (d1 >= 0) & (rel + 1u < glen);
+            const bool p2 = act & (d2 >= 0) & (rel + 2u < glen), p3 = act & (d3 >= 0) & (rel + 3u < glen);
+            if (__any_sync(FULL, p0 | p1 | p2 | p3)) block_push4(b, s_queue, s_n, p0, p1, p2, p3, gqlm, base, lane);
+            pos = last_end;
+            k += npk;
+            continue;
+          }
           const int mult = sr.z >> 20;
           const uint16_t* row = b.cmin64 + (((sr.z >> 10) & 1023) << 6);
           const int qlm = sr.x | ((sr.z & 1023) << 20);
