@@ -27,9 +27,9 @@ namespace fm {
 //                         second, independent 192-bit word signature of the sentence (sig2_bit; tested before the
 //                         sentence is fetched for the exact count). Long sentences: word 1 = length | 1 << 31,
 //                         word 2 = row of the wide signature.
-// sa_next  int32[n_suf]   token at depth 3 of each suffix (tok[sa_pos[k] + 3], 0 when the suffix is shorter):
-//                         the binary search that narrows a trigram range -- the only level where ranges are
-//                         still wide -- reads ONE array instead of sa_pos -> tok (two dependent misses).
+// sa_next  int32[n_suf]   token at depth 3 of each suffix (tok[sa_pos[k] + 3], 0 when the suffix is shorter): keys of
+//                         the bisection that narrows a trigram range in subsequence() -- one array instead of
+//                         sa_pos -> tok (two dependent misses); the search kernel uses qg_tab at that level.
 // tg_tab   int4[2*pow2]   trigram directory, 32-byte entries (one sector): (word0, word1, word2, lo | hi, -, -, -), hi =
 //                         -position-1 for a trigram that occurs once. Keyed by the three words, not by the bigram's
 //                         slot: with min_subseq_length >= 3 (the reference's CLI default) a chain that does not reach
@@ -41,8 +41,9 @@ namespace fm {
 //                         dependent bisection rounds) -- in one probe.
 // qva      int32[V+1]     first-word bucket table (reference _quickVocabAccess).
 // bg_tab   int4[pow2]     bigram directory: open-addressing table (word0, word1) -> [lo, hi) of the suffixes
-//                         that start with that bigram, so the two widest narrowing steps of every chain
-//                         (whole array -> first word -> bigram) cost one probe instead of ~40.
+//                         that start with that bigram (whole array -> first word -> bigram in one probe instead of
+//                         ~40); read when min_subseq_length < 3 -- bigram ranges are registered then -- and by
+//                         subsequence().
 // sid_at   int32[n_buf/4] local sentence id, stored at (sentence start / 4); only read for survivors.
 // wsig     uint32[n_wide*32] 1024-bit word signatures of the sentences longer than kWideMin tokens (a 64-bit
 //                         signature saturates there); their walk records carry the row number instead of the
