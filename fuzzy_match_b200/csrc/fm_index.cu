@@ -200,7 +200,7 @@ int load_index(const char* path, int device, Index** out) {
   }
   bind_blocks(ix);
   IndexDev& d = ix->dev;
-  d.vocab_size = ix->vocab_size; d.max_tokens = ix->max_tokens; d.n_suf = ix->n_suf;
+  d.vocab_size = ix->vocab_size; d.max_tokens = ix->max_tokens; d.n_suf = ix->n_suf; d.n_buf = (int32_t)ix->n_buf;
   d.bg_mask = (uint32_t)hdr[6]; d.tg_mask = (uint32_t)hdr[7]; d.qg_mask = (uint32_t)hdr[12]; d.sid_base = (uint32_t)hdr[8];
   memcpy(&d.idf_max, &hdr[10], sizeof(float));
   *out = ix;
@@ -713,6 +713,7 @@ int build_index(const int32_t* tokens, const int64_t* sent_off, int64_t n_in, in
   d.vocab_size = vocab_size;
   d.max_tokens = max_tokens;
   d.n_suf = n_suf;
+  d.n_buf = (int32_t)ix->n_buf;
   d.sid_base = (uint32_t)s_id_base;
   *out = ix;
   return FM_OK;

@@ -71,6 +71,7 @@ struct IndexDev {
   int32_t vocab_size;
   int32_t max_tokens;
   int64_t n_suf;
+  int32_t n_buf;  // tokens in tok (the last one is a separator)
   uint32_t sid_base;
   float idf_max;  // (float)log((double)N_sent_global)
   const int32_t* sent_start;  // optional [n_sent]: start of local sentence s in tok (uploaded on first use: contrastive rerank on a sharded TM)

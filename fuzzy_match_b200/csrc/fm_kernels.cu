@@ -2665,7 +2665,7 @@ __global__ void __launch_bounds__(128) fm_subseq_kernel(IndexDev ix, const int32
       if (__any_sync(FULL, dup)) continue;
       int slen = 0;
       for (int k0 = 0;; k0 += 32) {  // stage the sentence (it ends at the separator)
-        const int t = __ldg(ix.tok + start + k0 + lane);
+        const int t = __ldg(ix.tok + min(start + k0 + lane, ix.n_buf - 1));  // (the buffer ends with a separator)
         const unsigned z = __ballot_sync(FULL, t == 0);
         s_sent[k0 + lane] = t;
         if (z) { slen = k0 + __ffs(z) - 1; break; }
