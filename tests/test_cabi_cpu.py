@@ -62,3 +62,35 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".h", ".hh", ".cc")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no CPU fallback", ""), os.path.join(dirpath, f)
+
+
+def test_index_load_rejects_bad_files_without_a_gpu(lib, tmp_path):
+    """fm_index_load validates magic, version, every header count and the block sizes before it allocates or touches
+    CUDA: foreign, outdated, corrupt or truncated files give FM_ERR_INVALID and a message, never a crash."""
+    import struct
+    magic = bytes([ord(c) for c in "FMB200I"] + [1])
+
+    def load(data):
+        path = tmp_path / "bad.fmb"
+        path.write_bytes(data)
+        h = C.c_void_p()
+        rc = lib.fm_index_load(str(path).encode(), 0, C.byref(h))
+        assert h.value is None
+        return rc, lib.fm_last_error()
+
+    rc, msg = load(b"not an index at all" * 10)
+    assert rc == 1 and b"not a fuzzy_match_b200 index" in msg
+    rc, msg = load(magic + struct.pack("<16q", 3, 100, 300, 10, 50, 64, 1023, 1023, 0, 10, 0, 13, 0, 0, 0, 0))
+    assert rc == 1 and b"version" in msg  # a file of an older layout
+    version = int(re.search(rb"version (\d+)", msg).group(1))
+    n_blk = 14
+    # negative / inconsistent counts, absurd block sizes, a header with no payload behind it
+    for hdr in ((version, 100, 300, -5, 50, 64, 1023, 1023, 0, 10, 0, n_blk, 1023, 0, 0, 0),
+                (version, 100, 300, 10, 50, 64, 1000, 1023, 0, 10, 0, n_blk, 1023, 0, 0, 0),
+                (version, 1 << 40, 300, 10, 50, 64, 1023, 1023, 0, 10, 0, n_blk, 1023, 0, 0, 0),
+                (version, 100, 300, 10, 50, 64, 1023, 1023, 0, 10, 0, n_blk, 1023, 0, 0, 0)):
+        rc, msg = load(magic + struct.pack("<16q", *hdr))
+        assert rc == 1 and b"corrupt or truncated" in msg, (hdr, msg)
+    rc, msg = load(magic + struct.pack("<16q", version, 100, 300, 10, 50, 64, 1023, 1023, 0, 10, 0, n_blk, 1023, 0, 0, 0)
+                   + struct.pack("<q", 1 << 45) + b"\0" * 64)
+    assert rc == 1 and b"corrupt or truncated" in msg
