@@ -94,3 +94,18 @@ def test_index_load_rejects_bad_files_without_a_gpu(lib, tmp_path):
     rc, msg = load(magic + struct.pack("<16q", version, 100, 300, 10, 50, 64, 1023, 1023, 0, 10, 0, n_blk, 1023, 0, 0, 0)
                    + struct.pack("<q", 1 << 45) + b"\0" * 64)
     assert rc == 1 and b"corrupt or truncated" in msg
+
+
+def test_library_is_sm_100a_only_and_uses_256_bit_memory_ops(lib):
+    """The cubins in the library are built for sm_100a alone, and the Blackwell 256-bit global loads / stores the
+    walk, verify, search and prepare kernels rely on made it into the SASS (LDG/STG.E.ENL2.256)."""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    path = capi.library_path()
+    elfs = subprocess.run(["cuobjdump", "--list-elf", path], capture_output=True, text=True).stdout.split("\n")
+    archs = {m.group(1) for line in elfs for m in [re.search(r"\.(sm_\w+)\.cubin", line)] if m}
+    assert archs == {"sm_100a"}, archs
+    sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
+    assert sass.count("LDG.E.ENL2.256") >= 3 and sass.count("STG.E.ENL2.256") >= 1
